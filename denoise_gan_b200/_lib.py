@@ -1,0 +1,141 @@
+"""ctypes binding of the dg_b200 C ABI (include/dg_b200.h).
+
+PyTorch is used for device memory and streams only; every arithmetic kernel on the hot path is
+reached through this module.  There is no CPU or eager-PyTorch fallback: a missing library or a
+non-zero return code raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdg_b200.so")
+
+DG_F32, DG_BF16 = 0, 1
+ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4, "prelu": 5}
+
+
+class DgTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("cpitch", C.c_int32), ("coff", C.c_int32)]
+
+
+class DgConvParams(C.Structure):
+    _fields_ = [("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad_t", C.c_int32),
+                ("pad_l", C.c_int32), ("act", C.c_int32), ("act_alpha", C.c_float)]
+
+
+class DgError(RuntimeError):
+    pass
+
+
+_lib = None
+_ctx = {}
+
+_P, _T, _CP = C.c_void_p, C.POINTER(DgTensor), C.POINTER(DgConvParams)
+_i, _f, _u32, _i64, _sz = C.c_int, C.c_float, C.c_uint32, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/dg_b200.h declares
+SIGNATURES = {
+    "dg_init": (_i, [_i, C.POINTER(_P)]),
+    "dg_destroy": (None, [_P]),
+    "dg_last_error": (C.c_char_p, []),
+    "dg_version": (_i, []),
+    "dg_has_umma": (_i, [_P]),
+    "dg_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
+    "dg_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
+    "dg_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),
+    "dg_conv2d_wgrad": (_i, [_P, _T, _T, _P, _P, _CP, _i, _P, _sz, _P]),
+    "dg_umma_packed_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "dg_umma_pack_weights": (_i, [_P, _P, _P, _i, _i, _i, _i, _i, _P]),
+    "dg_umma_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
+    "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
+    "dg_umma_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),
+    "dg_umma_conv2d_wgrad": (_i, [_P, _T, _T, _P, _P, _CP, _i, _P, _sz, _P]),
+    "dg_dwconv3x3_fwd": (_i, [_P, _T, _P, _P, _T, _P]),
+    "dg_dwconv3x3_dgrad": (_i, [_P, _T, _P, _T, _P]),
+    "dg_dwconv3x3_wgrad_workspace_bytes": (_sz, [_T]),
+    "dg_dwconv3x3_wgrad": (_i, [_P, _T, _T, _P, _P, _i, _P, _sz, _P]),
+    "dg_bn_workspace_bytes": (_sz, [_T]),
+    "dg_bn_stats": (_i, [_P, _T, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
+    "dg_bn_infer_affine": (_i, [_P, _i, _P, _P, _P, _P, _f, _P, _P, _P]),
+    "dg_bn_act_fwd": (_i, [_P, _T, _P, _P, _i, _f, _P, _T, _i, _u32, _u32, _T, _P]),
+    "dg_bn_act_bwd": (_i, [_P, _T, _T, _P, _P, _P, _P, _P, _i, _f, _P, _i, _u32, _u32, _T, _P, _P, _P, _i, _P, _sz, _P]),
+    "dg_act_bwd_from_output": (_i, [_P, _T, _T, _i, _f, _T, _P]),
+    "dg_d2s_prelu_fwd": (_i, [_P, _T, _P, _T, _P]),
+    "dg_d2s_prelu_bwd": (_i, [_P, _T, _T, _P, _T, _P, _i, _P, _sz, _P]),
+    "dg_add": (_i, [_P, _T, _T, _T, _P]),
+    "dg_copy": (_i, [_P, _T, _T, _i, _P]),
+    "dg_maxpool2x2_fwd": (_i, [_P, _T, _T, _P]),
+    "dg_maxpool2x2_bwd": (_i, [_P, _T, _T, _T, _T, _P]),
+    "dg_upsample2x_relu_fwd": (_i, [_P, _T, _T, _P]),
+    "dg_upsample2x_relu_bwd": (_i, [_P, _T, _T, _T, _P]),
+    "dg_vgg_preprocess_fwd": (_i, [_P, _T, _T, _P]),
+    "dg_vgg_preprocess_bwd": (_i, [_P, _T, _T, _P]),
+    "dg_loss_workspace_bytes": (_sz, [_T]),
+    "dg_image_losses": (_i, [_P, _T, _T, _f, _f, _f, _P, _T, _i, _P, _sz, _P]),
+    "dg_bce_const_target": (_i, [_P, _T, _f, _i, _f, _P, _T, _P, _sz, _P]),
+    "dg_feature_mse": (_i, [_P, _T, _T, _f, _P, _T, _P, _sz, _P]),
+    "dg_adam_step": (_i, [_P, _P, _P, _P, _P, _i64, _f, _f, _f, _f, _i64, _f, _f, _P, _P]),
+}
+
+
+def load():
+    """Loads libdg_b200.so and binds every entry point.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DgError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no fallback path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ctx(device: int | None = None):
+    lib = load()
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _ctx:
+        h = C.c_void_p()
+        rc = lib.dg_init(int(device), C.byref(h))
+        if rc != 0:
+            raise DgError(lib.dg_last_error().decode())
+        _ctx[device] = h
+    return _ctx[device]
+
+
+def check(rc: int):
+    if rc != 0:
+        raise DgError(_lib.dg_last_error().decode())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DG_F32
+    if t.dtype == torch.bfloat16:
+        return DG_BF16
+    raise DgError(f"unsupported dtype {t.dtype}")
+
+
+def tensor(t: torch.Tensor, c: int | None = None, coff: int = 0) -> DgTensor:
+    """NHWC view descriptor of `t` ([N,H,W,Cpitch], dense); optional logical channel slice."""
+    assert t.is_cuda and t.dim() == 4 and t.is_contiguous(), "expected a dense CUDA NHWC tensor"
+    n, h, w, cp = t.shape
+    return DgTensor(t.data_ptr(), dtype_code(t), n, h, w, cp if c is None else c, cp, coff)
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()

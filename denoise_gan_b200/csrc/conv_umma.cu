@@ -1,0 +1,513 @@
+// Tensor-core convolution for sm_100a: NHWC implicit GEMM on tcgen05.mma with the accumulator
+// in TMEM and operands staged by TMA.
+//
+// Formulation ("multi-source halo conv").  One launch computes, for an output VIEW y (a dense or
+// stride-2 sub-lattice of an NHWC tensor, possibly a channel slice),
+//      y[n,h,w,o] = act( bias[o] + sum_taps sum_c  S_t[n, h+dh_t, w+dw_t, c] * Wt[t][o][c] )
+// where every source S_t is itself a view (dense or a stride-2 parity lattice) of the input.
+//   forward stride 1      : one source (x), taps (r-pad_t, s-pad_l)
+//   forward stride 2      : four parity lattices of x, taps fall on one lattice each
+//   dgrad stride 1        : one source (dy), flipped taps, transposed weight blocks
+//   dgrad stride 2 / Conv2DTranspose forward : four launches, one per output parity phase
+// A CTA owns an output tile of (16*MT) x 8 pixels.  Per 64/32/16-channel chunk it TMA-loads ONE
+// halo box per source ((16*MT+ext_h) x (8+ext_w) pixels, out-of-image pixels zero-filled by TMA =
+// SAME padding) and every tap's A operand is a row-shifted window of that box: the UMMA shared
+// memory descriptor starts at (row shift)*pixel_bytes and uses SBO = halo_width*pixel_bytes, which
+// is legal because the 128B/64B/32B swizzle is a function of the absolute shared-memory address
+// (probes/umma_probe.cu, cases halo10_*).  Input traffic per tile is therefore ~1.4x the tile
+// instead of taps x.  Weight blocks [Cout_blk][chunk] (K-major) stay resident in shared memory
+// when they fit, else they stream with the halo stage.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
+// warps 2-5 epilogue (TMEM -> registers -> bias/activation -> global).  Three mbarrier pipelines:
+// halo stages (full/empty), TMEM accumulators (double-buffered full/empty), resident weights.
+//
+// Reference call sites: Conv2D srgan.py:154-182,246-268, fsrgan.py:134-217, autoencoder.py:95-104,
+// pix2pix.py:115,207-218; Conv2DTranspose pix2pix.py:130,169; gradients train_srgan.py:111-112.
+#include <cuda.h>
+
+#include "dg_common.cuh"
+#include "sm100.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int MAX_SRC = 4;
+constexpr int MAX_TAPS = 16;
+constexpr int MAX_STAGES = 6;
+constexpr int CONV_THREADS = 192;
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+
+struct UmmaConvParams {
+  CUtensorMap src[MAX_SRC];
+  CUtensorMap wmap;
+  int n_src, n_taps, n_chunks, kc, nb, mt;
+  int tiles_h, tiles_w, n_img, out_h, out_w;
+  int src_h0[MAX_SRC], src_w0[MAX_SRC];
+  uint32_t src_off[MAX_SRC];
+  uint32_t a_sbo[MAX_SRC], mt_stride[MAX_SRC];
+  uint32_t tap_off[MAX_TAPS];
+  int tap_src[MAX_TAPS], tap_w[MAX_TAPS];
+  uint32_t stage_bytes, stage_tx, w_stage_off, w_block_bytes, w_res_bytes, w_res_tx;
+  int n_stages, resident, cout_total;
+  void* out;
+  long out_sn, out_sh, out_sw;
+  int out_f32;
+  const float* bias;
+  int act;
+  float alpha;
+  uint32_t layout, idesc;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_w;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base;
+  const uint32_t stage_base = base + (P.resident ? P.w_res_bytes : 0u);
+  const int nb0 = blockIdx.y * P.nb;
+  const int total_tiles = P.n_img * P.tiles_h * P.tiles_w;
+
+  if (tid == 0) {
+    for (int s = 0; s < P.n_stages; ++s) {
+      mbar_init(smem_u32(&bar_a_full[s]), 1);
+      mbar_init(smem_u32(&bar_a_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 4);
+    }
+    mbar_init(smem_u32(&bar_w), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
+      tma_prefetch_desc(&P.wmap);
+      if (P.resident) {
+        const uint32_t bw = smem_u32(&bar_w);
+        mbar_expect_tx(bw, P.w_res_tx);
+        for (int b = 0; b < P.n_taps * P.n_chunks; ++b) {
+          // resident block b = tap_slot * n_chunks + chunk; source rows come from the tap's weight index
+          int t = b / P.n_chunks, kc = b - t * P.n_chunks;
+          tma_load_2d(w_base + (uint32_t)b * P.w_block_bytes, &P.wmap, bw, 0,
+                      (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
+        }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tw = tile % P.tiles_w;
+        int t2 = tile / P.tiles_w;
+        int th = t2 % P.tiles_h;
+        int n = t2 / P.tiles_h;
+        const int h0 = th * 16 * P.mt, w0 = tw * 8;
+        for (int kc = 0; kc < P.n_chunks; ++kc) {
+          const uint32_t full = smem_u32(&bar_a_full[stage]);
+          mbar_wait(smem_u32(&bar_a_empty[stage]), phase ^ 1u);
+          mbar_expect_tx(full, P.stage_tx);
+          const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
+          for (int s = 0; s < P.n_src; ++s)
+            tma_load_4d(sa + P.src_off[s], &P.src[s], full, kc * P.kc, w0 + P.src_w0[s], h0 + P.src_h0[s], n);
+          if (!P.resident)
+            for (int t = 0; t < P.n_taps; ++t)
+              tma_load_2d(sa + P.w_stage_off + (uint32_t)t * P.w_block_bytes, &P.wmap, full, 0,
+                          (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
+          if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      if (P.resident) {
+        mbar_wait(smem_u32(&bar_w), 0);
+        tc_fence_after();
+      }
+      const uint32_t w_sbo = 8u * (uint32_t)P.kc * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
+        tc_fence_after();
+        for (int kc = 0; kc < P.n_chunks; ++kc) {
+          mbar_wait(smem_u32(&bar_a_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
+          for (int t = 0; t < P.n_taps; ++t) {
+            const uint32_t wb = P.resident ? w_base + (uint32_t)(t * P.n_chunks + kc) * P.w_block_bytes
+                                           : sa + P.w_stage_off + (uint32_t)t * P.w_block_bytes;
+            const int s = P.tap_src[t];
+            for (int k16 = 0; k16 < P.kc / 16; ++k16) {
+              const uint64_t bd = make_smem_desc(wb + k16 * 32, 16, w_sbo, P.layout);
+              for (int m = 0; m < P.mt; ++m) {
+                const uint64_t ad =
+                    make_smem_desc(sa + P.tap_off[t] + (uint32_t)m * P.mt_stride[s] + k16 * 32, 16, P.a_sbo[s], P.layout);
+                umma_f16(tmem + (uint32_t)((b * P.mt + m) * P.nb), ad, bd, P.idesc, (kc | t | k16) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(smem_u32(&bar_a_empty[stage]));
+          if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bar_acc_full[b]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m_idx = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      int tw = tile % P.tiles_w;
+      int t2 = tile / P.tiles_w;
+      int th = t2 % P.tiles_h;
+      int n = t2 / P.tiles_h;
+      mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
+      tc_fence_after();
+      for (int m = 0; m < P.mt; ++m) {
+        const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
+        const int pw = tw * 8 + (m_idx & 7);
+        const bool valid = ph < P.out_h && pw < P.out_w;
+        const long pix = (long)n * P.out_sn + (long)ph * P.out_sh + (long)pw * P.out_sw + nb0;
+        for (int c0 = 0; c0 < P.nb; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * P.mt + m) * P.nb + c0), v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(v[j]);
+              if (P.bias) x += __ldg(P.bias + nb0 + c0 + j);
+              f[j] = apply_act(x, P.act, P.alpha);
+            }
+            if (P.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix + c0);
+              dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                  pack_bf16x2(f[6], f[7]));
+              dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                  pack_bf16x2(f[14], f[15]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------ weight packing
+// mode 0 (forward): dst[((t*nch+kc)*Cout + o)*KC + j] = w[t][kc*KC + j][o]      (KC chunks over Cin)
+// mode 1 (dgrad)  : dst[((t*nch+kc)*Cin  + c)*KC + j] = w[t][c][kc*KC + j]      (KC chunks over Cout)
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int taps, int cin,
+                                    int cout, int kc, int mode) {
+  long total = (long)taps * cin * cout;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int rows = mode == 0 ? cout : cin;  // rows of a block
+    int kdim = mode == 0 ? cin : cout;  // contraction length
+    int nch = kdim / kc;
+    int j = (int)(i % kc);
+    long r1 = i / kc;
+    int row = (int)(r1 % rows);
+    long r2 = r1 / rows;
+    int ch = (int)(r2 % nch);
+    int t = (int)(r2 / nch);
+    int k = ch * kc + j;
+    float v = mode == 0 ? w[((long)t * cin + k) * cout + row] : w[((long)t * cin + row) * cout + k];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+inline int kc_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(dg_ctx* ctx, CUtensorMap* m, void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
+               const uint32_t* box, int kc) {
+  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  uint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = ((EncodeFn)ctx->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, ptr, (const cuuint64_t*)dims,
+                                             (const cuuint64_t*)strides_b, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DG_FAIL("cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// A lattice view of an NHWC tensor: element (n,h,w,c) of the view is element
+// (n, h*step+h_first, w*step+w_first, c) of the tensor.
+struct Lattice {
+  int step, h_first, w_first;
+};
+
+struct TapSpec {
+  int src, dh, dw, widx;
+};
+
+// Builds the launch description and runs the kernel.
+int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
+                const TapSpec* taps, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
+                const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st) {
+  DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
+  DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
+  DG_REQUIRE(in->cpitch % 8 == 0 && in->coff % 8 == 0 && ((uintptr_t)in->ptr % 16) == 0, "%s: input view not 16-byte aligned", name);
+  const int out_esz = out->dtype == DG_F32 ? 4 : 2;
+  DG_REQUIRE(((uintptr_t)out->ptr % 16) == 0 && (out->cpitch * out_esz) % 16 == 0 && (out->coff * out_esz) % 16 == 0,
+             "%s: output view not 16-byte aligned", name);
+  DG_REQUIRE(n_src >= 1 && n_src <= MAX_SRC && n_taps >= 1 && n_taps <= MAX_TAPS, "%s: too many sources/taps", name);
+  DG_REQUIRE(act != DG_ACT_PRELU, "%s: PReLU is not a conv epilogue", name);
+
+  UmmaConvParams P;
+  memset(&P, 0, sizeof(P));
+  const int kc = kc_for(in->c);
+  const int n_chunks = in->c / kc;
+  const int cout = out->c;
+  P.kc = kc; P.n_chunks = n_chunks; P.n_src = n_src; P.n_taps = n_taps; P.cout_total = w_rows_per_block;
+  P.layout = kc == 64 ? LAYOUT_SW128 : (kc == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
+
+  // output view extents
+  const int out_h = (out->h - out_lat.h_first + out_lat.step - 1) / out_lat.step;
+  const int out_w = (out->w - out_lat.w_first + out_lat.step - 1) / out_lat.step;
+  DG_REQUIRE(out_h > 0 && out_w > 0, "%s: empty output view", name);
+  P.out_h = out_h; P.out_w = out_w; P.n_img = out->n;
+
+  // per-source halo extents from the taps
+  int dh_min[MAX_SRC], dh_max[MAX_SRC], dw_min[MAX_SRC], dw_max[MAX_SRC];
+  bool used[MAX_SRC] = {false, false, false, false};
+  for (int t = 0; t < n_taps; ++t) {
+    int s = taps[t].src;
+    DG_REQUIRE(s >= 0 && s < n_src, "%s: bad tap source", name);
+    if (!used[s]) { dh_min[s] = dh_max[s] = taps[t].dh; dw_min[s] = dw_max[s] = taps[t].dw; used[s] = true; }
+    dh_min[s] = taps[t].dh < dh_min[s] ? taps[t].dh : dh_min[s];
+    dh_max[s] = taps[t].dh > dh_max[s] ? taps[t].dh : dh_max[s];
+    dw_min[s] = taps[t].dw < dw_min[s] ? taps[t].dw : dw_min[s];
+    dw_max[s] = taps[t].dw > dw_max[s] ? taps[t].dw : dw_max[s];
+  }
+  for (int s = 0; s < n_src; ++s) DG_REQUIRE(used[s], "%s: unused source %d", name, s);
+
+  // choose (MT, NB, resident) : prefer resident weights with the widest N block
+  const uint32_t budget = SMEM_LIMIT - 4096;
+  auto halo_bytes = [&](int mt) {
+    uint32_t tot = 0;
+    for (int s = 0; s < n_src; ++s) {
+      uint32_t hb = (uint32_t)(16 * mt + dh_max[s] - dh_min[s]) * (uint32_t)(8 + dw_max[s] - dw_min[s]) * kc * 2;
+      tot += (hb + 1023u) & ~1023u;
+    }
+    return tot;
+  };
+  int best_nb = 0, best_mt = 0, best_res = 0;
+  for (int res = 1; res >= 0 && !best_nb; --res)
+    for (int mt = (res ? 1 : 2); mt >= 1 && !best_nb; --mt)
+      for (int nb = cout > 256 ? 256 : cout; nb >= 16 && !best_nb; nb -= 16) {
+        if (cout % nb != 0 || 2 * mt * nb > 512) continue;
+        uint32_t wblk = (uint32_t)nb * kc * 2;
+        uint32_t wres = (uint32_t)n_taps * n_chunks * wblk;
+        uint32_t stage = halo_bytes(mt) + (res ? 0 : (uint32_t)n_taps * wblk);
+        uint32_t need = (res ? ((wres + 1023u) & ~1023u) : 0) + 2 * ((stage + 1023u) & ~1023u);
+        if (need <= budget) { best_nb = nb; best_mt = mt; best_res = res; }
+      }
+  DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d taps=%d)", name, in->c, cout, n_taps);
+  const int nb = best_nb, mt = best_mt;
+  P.nb = nb; P.mt = mt; P.resident = best_res;
+  P.w_block_bytes = (uint32_t)nb * kc * 2;
+  P.w_res_tx = best_res ? (uint32_t)n_taps * n_chunks * P.w_block_bytes : 0;
+  P.w_res_bytes = (P.w_res_tx + 1023u) & ~1023u;
+  P.idesc = make_idesc_bf16(128, nb, 0, 0);
+  P.tiles_h = (out_h + 16 * mt - 1) / (16 * mt);
+  P.tiles_w = (out_w + 7) / 8;
+
+  // sources: tensor maps + placement in the stage
+  uint32_t off = 0, tx = 0;
+  for (int s = 0; s < n_src; ++s) {
+    const Lattice& L = src_lat[s];
+    const int HH = 16 * mt + dh_max[s] - dh_min[s], WW = 8 + dw_max[s] - dw_min[s];
+    DG_REQUIRE(HH <= 256 && WW <= 256, "%s: halo box too large", name);
+    const int vh = (in->h - L.h_first + L.step - 1) / L.step, vw = (in->w - L.w_first + L.step - 1) / L.step;
+    DG_REQUIRE(vh > 0 && vw > 0, "%s: empty source view", name);
+    uint64_t dims[4] = {(uint64_t)in->c, (uint64_t)vw, (uint64_t)vh, (uint64_t)in->n};
+    uint64_t strides[3] = {(uint64_t)in->cpitch * 2 * L.step, (uint64_t)in->cpitch * 2 * in->w * L.step,
+                           (uint64_t)in->cpitch * 2 * in->w * in->h};
+    uint32_t box[4] = {(uint32_t)kc, (uint32_t)WW, (uint32_t)HH, 1};
+    char* p = (char*)in->ptr + ((size_t)in->coff + ((size_t)L.h_first * in->w + L.w_first) * in->cpitch) * 2;
+    if (encode_map(ctx, &P.src[s], p, 4, dims, strides, box, kc)) return 1;
+    P.src_h0[s] = dh_min[s]; P.src_w0[s] = dw_min[s];
+    P.src_off[s] = off;
+    P.a_sbo[s] = (uint32_t)WW * kc * 2;
+    P.mt_stride[s] = (uint32_t)16 * WW * kc * 2;
+    uint32_t hb = (uint32_t)HH * WW * kc * 2;
+    tx += hb;
+    off += (hb + 1023u) & ~1023u;
+  }
+  P.w_stage_off = off;
+  if (!best_res) { off += (uint32_t)n_taps * P.w_block_bytes; tx += (uint32_t)n_taps * P.w_block_bytes; }
+  P.stage_bytes = (off + 1023u) & ~1023u;
+  P.stage_tx = tx;
+  int n_stages = (int)((budget - P.w_res_bytes) / P.stage_bytes);
+  if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
+  DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
+  P.n_stages = n_stages;
+  for (int t = 0; t < n_taps; ++t) {
+    int s = taps[t].src;
+    int WW = 8 + dw_max[s] - dw_min[s];
+    P.tap_src[t] = s;
+    P.tap_w[t] = taps[t].widx;
+    P.tap_off[t] = P.src_off[s] + (uint32_t)((taps[t].dh - dh_min[s]) * WW + (taps[t].dw - dw_min[s])) * kc * 2;
+  }
+  // weights: 2D [rows][kc]
+  {
+    // total rows are not needed exactly for correctness of in-bounds loads; give the true extent
+    uint64_t rows = (uint64_t)w_rows_per_block * n_chunks * MAX_TAPS;  // upper bound, never read past real data
+    uint64_t dims[2] = {(uint64_t)kc, rows};
+    uint64_t strides[1] = {(uint64_t)kc * 2};
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)nb};
+    if (encode_map(ctx, &P.wmap, const_cast<void*>(w_packed), 2, dims, strides, box, kc)) return 1;
+  }
+  // output
+  P.out = (char*)out->ptr + ((size_t)out->coff + ((size_t)out_lat.h_first * out->w + out_lat.w_first) * out->cpitch) * out_esz;
+  P.out_sw = (long)out->cpitch * out_lat.step;
+  P.out_sh = (long)out->cpitch * out->w * out_lat.step;
+  P.out_sn = (long)out->cpitch * out->w * out->h;
+  P.out_f32 = out->dtype == DG_F32;
+  P.bias = bias; P.act = act; P.alpha = alpha;
+
+  const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    if (e != cudaSuccess) DG_FAIL("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int n_blocks = cout / nb;
+  const int total_tiles = P.n_img * P.tiles_h * P.tiles_w;
+  int ctas = ctx->sm_count / n_blocks;
+  if (ctas < 1) ctas = 1;
+  if (ctas > total_tiles) ctas = total_tiles;
+  dim3 grid(ctas, n_blocks);
+  umma_conv_kernel<<<grid, CONV_THREADS, smem, st>>>(P);
+  DG_CHECK_LAUNCH(name);
+  return 0;
+}
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int pymod(int a, int b) { return a - floordiv(a, b) * b; }
+
+}  // namespace
+
+extern "C" size_t dg_umma_packed_bytes(int kh, int kw, int cin, int cout, int mode) {
+  return (size_t)kh * kw * cin * cout * 2;
+}
+
+extern "C" int dg_umma_pack_weights(dg_ctx* ctx, const float* w, void* packed, int kh, int kw, int cin, int cout,
+                                    int mode, void* stream) {
+  DG_REQUIRE(w && packed, "dg_umma_pack_weights: null argument");
+  DG_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "dg_umma_pack_weights: channels must be multiples of 16");
+  DG_REQUIRE(mode == 0 || mode == 1, "dg_umma_pack_weights: bad mode");
+  int kc = kc_for(mode == 0 ? cin : cout);
+  long total = (long)kh * kw * cin * cout;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin, cout, kc, mode);
+  DG_CHECK_LAUNCH("dg_umma_pack_weights");
+  return 0;
+}
+
+extern "C" int dg_umma_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias,
+                                  const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y) && w_packed && p, "dg_umma_conv2d_fwd: null argument");
+  DG_REQUIRE(bn_partials == nullptr, "dg_umma_conv2d_fwd: fused BN partials not available in this build");
+  DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
+  DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
+  DG_REQUIRE(p->kh * p->kw <= MAX_TAPS, "dg_umma_conv2d_fwd: kernel too large");
+  TapSpec taps[MAX_TAPS];
+  Lattice lat[MAX_SRC];
+  int n_src = 0, n_taps = 0;
+  if (p->stride == 1) {
+    lat[0] = Lattice{1, 0, 0};
+    n_src = 1;
+    for (int r = 0; r < p->kh; ++r)
+      for (int s = 0; s < p->kw; ++s) taps[n_taps++] = TapSpec{0, r - p->pad_t, s - p->pad_l, r * p->kw + s};
+  } else {
+    DG_REQUIRE(x->h % 2 == 0 && x->w % 2 == 0, "dg_umma_conv2d_fwd: stride 2 needs even input size");
+    int src_of[2][2] = {{-1, -1}, {-1, -1}};
+    for (int r = 0; r < p->kh; ++r)
+      for (int s = 0; s < p->kw; ++s) {
+        int ph = pymod(r - p->pad_t, 2), pw = pymod(s - p->pad_l, 2);
+        if (src_of[ph][pw] < 0) { src_of[ph][pw] = n_src; lat[n_src++] = Lattice{2, ph, pw}; }
+        taps[n_taps++] = TapSpec{src_of[ph][pw], floordiv(r - p->pad_t - ph, 2), floordiv(s - p->pad_l - pw, 2), r * p->kw + s};
+      }
+  }
+  return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
+                     p->act, p->act_alpha, (cudaStream_t)stream);
+}
+
+extern "C" int dg_umma_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const float* bias,
+                                    const dg_tensor* dx, const dg_conv_params* p, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(dx) && w_packed && p, "dg_umma_conv2d_dgrad: null argument");
+  DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_dgrad: stride must be 1 or 2");
+  DG_REQUIRE(dx->n == dy->n, "dg_umma_conv2d_dgrad: batch mismatch");
+  DG_REQUIRE(p->kh * p->kw <= MAX_TAPS, "dg_umma_conv2d_dgrad: kernel too large");
+  Lattice dense{1, 0, 0};
+  TapSpec taps[MAX_TAPS];
+  if (p->stride == 1) {
+    int n_taps = 0;
+    for (int r = 0; r < p->kh; ++r)
+      for (int s = 0; s < p->kw; ++s) taps[n_taps++] = TapSpec{0, p->pad_t - r, p->pad_l - s, r * p->kw + s};
+    return launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_taps, w_packed, dx->c, dx, dense, bias,
+                       p->act, p->act_alpha, (cudaStream_t)stream);
+  }
+  DG_REQUIRE(dx->h % 2 == 0 && dx->w % 2 == 0, "dg_umma_conv2d_dgrad: stride 2 needs even image size");
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      int n_taps = 0;
+      for (int r = 0; r < p->kh; ++r) {
+        if (pymod(a + p->pad_t - r, 2) != 0) continue;
+        for (int s = 0; s < p->kw; ++s) {
+          if (pymod(b + p->pad_l - s, 2) != 0) continue;
+          taps[n_taps++] = TapSpec{0, floordiv(a + p->pad_t - r, 2), floordiv(b + p->pad_l - s, 2), r * p->kw + s};
+        }
+      }
+      DG_REQUIRE(n_taps > 0, "dg_umma_conv2d_dgrad: output phase without taps (kernel smaller than stride)");
+      if (launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_taps, w_packed, dx->c, dx, Lattice{2, a, b},
+                      bias, p->act, p->act_alpha, (cudaStream_t)stream))
+        return 1;
+    }
+  return 0;
+}
+
+// wgrad on tensor cores: see conv_umma_wgrad.cu

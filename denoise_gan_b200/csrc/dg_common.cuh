@@ -1,0 +1,107 @@
+// Shared host/device helpers for the dg_b200 library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dg_b200.h"
+
+struct dg_ctx {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  void* encode_tiled;  // cuTensorMapEncodeTiled entry point (driver API, resolved at init)
+};
+
+void dg_set_error(const char* fmt, ...);
+
+#define DG_FAIL(...)            \
+  do {                          \
+    dg_set_error(__VA_ARGS__);  \
+    return 1;                   \
+  } while (0)
+
+#define DG_CHECK_LAUNCH(name)                                                     \
+  do {                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                          \
+    if (e_ != cudaSuccess) DG_FAIL("%s: launch failed: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define DG_REQUIRE(cond, ...)       \
+  do {                              \
+    if (!(cond)) DG_FAIL(__VA_ARGS__); \
+  } while (0)
+
+// ---- element access for the two storage types
+template <typename T>
+__device__ __forceinline__ float ld_f(const T* p);
+template <>
+__device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void st_f(T* p, float v);
+template <>
+__device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// value as it will read back from storage of type T (bf16 rounding made explicit)
+template <typename T>
+__device__ __forceinline__ float round_to(float v);
+template <>
+__device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+  switch (act) {
+    case DG_ACT_RELU: return v > 0.f ? v : 0.f;
+    case DG_ACT_LRELU: return v >= 0.f ? v : alpha * v;
+    case DG_ACT_TANH: return tanhf(v);
+    case DG_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// Counter-based Bernoulli(0.5) keep decision shared with oracle/ops_np.py:dropout_keep_mask.
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx) {
+  uint32_t x = idx ^ seed;
+  x = (x ^ (x >> 16)) * 0x7FEB352Du;
+  x = (x ^ (x >> 15)) * 0x846CA68Bu;
+  x = x ^ (x >> 16);
+  return (x >> 31) == 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dispatch a lambda-like macro over the (input, output) storage types of two tensors
+#define DG_DISPATCH_2(tin, tout, NAME, ...)                                               \
+  do {                                                                                    \
+    if ((tin) == DG_F32 && (tout) == DG_F32) { using TI = float; using TO = float; __VA_ARGS__ }                 \
+    else if ((tin) == DG_F32 && (tout) == DG_BF16) { using TI = float; using TO = __nv_bfloat16; __VA_ARGS__ }   \
+    else if ((tin) == DG_BF16 && (tout) == DG_F32) { using TI = __nv_bfloat16; using TO = float; __VA_ARGS__ }   \
+    else if ((tin) == DG_BF16 && (tout) == DG_BF16) { using TI = __nv_bfloat16; using TO = __nv_bfloat16; __VA_ARGS__ } \
+    else DG_FAIL("%s: unsupported dtype", NAME);                                          \
+  } while (0)
+
+#define DG_DISPATCH_1(t, NAME, ...)                                     \
+  do {                                                                  \
+    if ((t) == DG_F32) { using T = float; __VA_ARGS__ }                 \
+    else if ((t) == DG_BF16) { using T = __nv_bfloat16; __VA_ARGS__ }   \
+    else DG_FAIL("%s: unsupported dtype", NAME);                        \
+  } while (0)
+
+static inline bool dg_same_shape(const dg_tensor* a, const dg_tensor* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+static inline int64_t dg_pixels(const dg_tensor* a) { return (int64_t)a->n * a->h * a->w; }
+static inline bool dg_valid(const dg_tensor* a) {
+  return a && a->ptr && a->n > 0 && a->h > 0 && a->w > 0 && a->c > 0 && a->cpitch >= a->coff + a->c && a->coff >= 0;
+}

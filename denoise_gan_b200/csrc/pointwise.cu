@@ -1,0 +1,653 @@
+// HBM-bound kernels of the hot path: BatchNorm statistics / apply / backward, activation
+// backward, depth_to_space(+PReLU), add, copy-into-slice, max-pool, nearest upsample(+ReLU).
+// All reductions are warp-shuffle + shared-memory block reductions into per-block partials that
+// a finalize kernel sums in a fixed order (deterministic; no float atomics).
+//
+// Reference call sites: BatchNormalization srgan.py:155,248, fsrgan.py:140-172, pix2pix.py:119,135,211;
+// tf.nn.depth_to_space + PReLU srgan.py:145-146; MaxPool2D / UpSampling2D autoencoder.py:110,122-124;
+// Dropout pix2pix.py:138; Add srgan.py:169,175.
+#include "dg_common.cuh"
+#include "reduce.cuh"
+
+namespace {
+
+struct View {
+  int pitch, off;
+};
+
+using namespace dgred;
+
+// ------------------------------------------------------------------ BN statistics
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) bn_stats_kernel(const T* __restrict__ x, View xv, long P, int C,
+                                                               float* __restrict__ partial) {
+  channel_reduce<2>(P, C, partial, [&](long p, int c, float* a) {
+    float v = ld_f(x + (p * xv.pitch + xv.off + c));
+    a[0] += v;
+    a[1] += v * v;
+  });
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, long P, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += partial[(long)b * 2 * C + c];
+    ss += partial[(long)b * 2 * C + C + c];
+  }
+  double mean = s / (double)P;
+  double var = ss / (double)P - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma[c], b = beta[c];
+  scale[c] = g * invstd;
+  shift[c] = b - (float)mean * g * invstd;
+  save_mean[c] = (float)mean;
+  save_invstd[c] = invstd;
+  if (moving_mean) {
+    moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+  }
+}
+
+__global__ void bn_infer_affine_kernel(int C, const float* gamma, const float* beta, const float* mm, const float* mv,
+                                       float eps, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float invstd = rsqrtf(mv[c] + eps);
+  scale[c] = gamma[c] * invstd;
+  shift[c] = beta[c] - mm[c] * gamma[c] * invstd;
+}
+
+// ------------------------------------------------------------------ BN apply (+dropout +act +residual)
+template <typename TI, typename TO>
+__global__ void bn_act_fwd_kernel(const TI* __restrict__ x, View xv, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int act, float alpha,
+                                  const float* __restrict__ prelu_alpha, const TO* __restrict__ res, View rv,
+                                  int dropout, uint32_t seed, uint32_t offset, TO* __restrict__ y, View yv, long P,
+                                  int C) {
+  long total = P * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long p = i / C;
+    int c = (int)(i - p * C);
+    float t = ld_f(x + (p * xv.pitch + xv.off + c)) * scale[c] + shift[c];
+    if (dropout) t = dropout_keep(seed, offset + (uint32_t)i) ? 2.f * t : 0.f;
+    if (act == DG_ACT_PRELU) t = t > 0.f ? t : prelu_alpha[c] * t;
+    else t = apply_act(t, act, alpha);
+    if (res) t += ld_f(res + (p * rv.pitch + rv.off + c));
+    st_f(y + (p * yv.pitch + yv.off + c), t);
+  }
+}
+
+// g = dL/d(bn output) for one element
+template <typename TG, typename TX>
+__device__ __forceinline__ float bn_bwd_g(const TG* dy, View dv, const TX* x, View xv, const float* scale,
+                                          const float* shift, int act, float alpha, const float* prelu_alpha,
+                                          int dropout, uint32_t seed, uint32_t offset, long p, int c, int C,
+                                          float* t_out) {
+  float xin = ld_f(x + (p * xv.pitch + xv.off + c));
+  float t = xin * scale[c] + shift[c];
+  float g = ld_f(dy + (p * dv.pitch + dv.off + c));
+  float td = t;
+  float dmul = 1.f;
+  if (dropout) {
+    bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c));
+    td = keep ? 2.f * t : 0.f;
+    dmul = keep ? 2.f : 0.f;
+  }
+  *t_out = td;
+  float d;
+  switch (act) {
+    case DG_ACT_RELU: d = td > 0.f ? 1.f : 0.f; break;
+    case DG_ACT_LRELU: d = td >= 0.f ? 1.f : alpha; break;
+    case DG_ACT_PRELU: d = td > 0.f ? 1.f : prelu_alpha[c]; break;
+    case DG_ACT_TANH: { float y = tanhf(td); d = 1.f - y * y; break; }
+    case DG_ACT_SIGMOID: { float y = 1.f / (1.f + expf(-td)); d = y * (1.f - y); break; }
+    default: d = 1.f;
+  }
+  return g * d * dmul;
+}
+
+template <typename TG, typename TX>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_reduce_kernel(const TG* __restrict__ dy, View dv, const TX* __restrict__ x, View xv,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int act, float alpha,
+                     const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset, long P, int C,
+                     float* __restrict__ partial) {
+  channel_reduce<3>(P, C, partial, [&](long p, int c, float* a) {
+    float t;
+    float g = bn_bwd_g(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c, C, &t);
+    float xhat = (ld_f(x + (p * xv.pitch + xv.off + c)) - mean[c]) * invstd[c];
+    a[0] += g;
+    a[1] += g * xhat;
+    if (act == DG_ACT_PRELU) a[2] += ld_f(dy + (p * dv.pitch + dv.off + c)) * fminf(t, 0.f);
+  });
+}
+
+// sums partials; writes dgamma/dbeta/dalpha and the per-channel means used by the dx pass
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, long P, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ dalpha, int accumulate, float* __restrict__ coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    s0 += partial[(long)b * 3 * C + c];
+    s1 += partial[(long)b * 3 * C + C + c];
+    s2 += partial[(long)b * 3 * C + 2 * C + c];
+  }
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+  if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
+  coef[c] = (float)(s0 / (double)P);
+  coef[C + c] = (float)(s1 / (double)P);
+}
+
+template <typename TG, typename TX, typename TO>
+__global__ void bn_bwd_dx_kernel(const TG* __restrict__ dy, View dv, const TX* __restrict__ x, View xv,
+                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                 const float* __restrict__ gamma, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, int act, float alpha,
+                                 const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset,
+                                 const float* __restrict__ coef, TO* __restrict__ dx, View ov, long P, int C) {
+  long total = P * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long p = i / C;
+    int c = (int)(i - p * C);
+    float t;
+    float g = bn_bwd_g(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c, C, &t);
+    float xhat = (ld_f(x + (p * xv.pitch + xv.off + c)) - mean[c]) * invstd[c];
+    float v = gamma[c] * invstd[c] * (g - coef[c] - xhat * coef[C + c]);
+    st_f(dx + (p * ov.pitch + ov.off + c), v);
+  }
+}
+
+// ------------------------------------------------------------------ activation backward from output
+template <typename TG, typename TY, typename TO>
+__global__ void act_bwd_kernel(const TG* __restrict__ dy, View dv, const TY* __restrict__ y, View yv, int act,
+                               float alpha, TO* __restrict__ dpre, View ov, long P, int C) {
+  long total = P * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long p = i / C;
+    int c = (int)(i - p * C);
+    float yo = ld_f(y + (p * yv.pitch + yv.off + c));
+    float g = ld_f(dy + (p * dv.pitch + dv.off + c));
+    float d;
+    switch (act) {
+      case DG_ACT_RELU: d = yo > 0.f ? 1.f : 0.f; break;
+      case DG_ACT_LRELU: d = yo >= 0.f ? 1.f : alpha; break;
+      case DG_ACT_TANH: d = 1.f - yo * yo; break;
+      case DG_ACT_SIGMOID: d = yo * (1.f - yo); break;
+      default: d = 1.f;
+    }
+    st_f(dpre + (p * ov.pitch + ov.off + c), g * d);
+  }
+}
+
+// ------------------------------------------------------------------ depth_to_space(2) + PReLU
+// y[b,2h+i,2w+j,c] = prelu(u[b,h,w,(2i+j)*Co+c], alpha[c])      (TF "DCR" order)
+template <typename T>
+__global__ void d2s_prelu_fwd_kernel(const T* __restrict__ u, View uv, const float* __restrict__ alpha,
+                                     T* __restrict__ y, View yv, int N, int H, int W, int Co) {
+  long total = (long)N * H * W * 4 * Co;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % (4 * Co));
+    long p = i / (4 * Co);
+    int w = (int)(p % W);
+    long t = p / W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    int sub = ch / Co, c = ch - sub * Co;
+    int di = sub >> 1, dj = sub & 1;
+    float v = ld_f(u + (p * uv.pitch + uv.off + ch));
+    if (alpha) v = v > 0.f ? v : alpha[c] * v;
+    long q = ((long)n * 2 * H + 2 * h + di) * 2 * W + 2 * w + dj;
+    st_f(y + (q * yv.pitch + yv.off + c), v);
+  }
+}
+
+// du = dy_perm * (u > 0 ? 1 : alpha[c]) ; dalpha[c] = sum dy_perm * min(u, 0)
+template <typename T>
+__global__ void d2s_prelu_bwd_kernel(const T* __restrict__ dy, View dv, const T* __restrict__ u, View uv,
+                                     const float* __restrict__ alpha, T* __restrict__ du, View ov, int N, int H, int W,
+                                     int Co) {
+  long total = (long)N * H * W * 4 * Co;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % (4 * Co));
+    long p = i / (4 * Co);
+    int w = (int)(p % W);
+    long t = p / W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    int sub = ch / Co, c = ch - sub * Co;
+    long q = ((long)n * 2 * H + 2 * h + (sub >> 1)) * 2 * W + 2 * w + (sub & 1);
+    float g = ld_f(dy + (q * dv.pitch + dv.off + c));
+    if (alpha) {
+      float uu = ld_f(u + (p * uv.pitch + uv.off + ch));
+      g = uu > 0.f ? g : alpha[c] * g;
+    }
+    st_f(du + (p * ov.pitch + ov.off + ch), g);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+d2s_prelu_dalpha_kernel(const T* __restrict__ dy, View dv, const T* __restrict__ u, View uv, long Pout, int H2, int W2,
+                        int Co, float* __restrict__ partial) {
+  // reduction over OUTPUT pixels q, channel c; the source element is u[q/2][(2(i)+j)*Co + c]
+  channel_reduce<1>(Pout, Co, partial, [&](long q, int c, float* a) {
+    int w2 = (int)(q % W2);
+    long t = q / W2;
+    int h2 = (int)(t % H2);
+    long n = t / H2;
+    long p = (n * (H2 / 2) + h2 / 2) * (W2 / 2) + w2 / 2;
+    int sub = (h2 & 1) * 2 + (w2 & 1);
+    float uu = ld_f(u + (p * uv.pitch + uv.off + sub * Co + c));
+    a[0] += ld_f(dy + (q * dv.pitch + dv.off + c)) * fminf(uu, 0.f);
+  });
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out,
+                                    int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(long)b * C + c];
+  out[c] = (accumulate ? out[c] : 0.f) + (float)s;
+}
+
+// ------------------------------------------------------------------ add / copy
+template <typename TA, typename TO>
+__global__ void add_kernel(const TA* __restrict__ a, View av, const TA* __restrict__ b, View bv, TO* __restrict__ o,
+                           View ov, long P, int C) {
+  long total = P * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long p = i / C;
+    int c = (int)(i - p * C);
+    st_f(o + (p * ov.pitch + ov.off + c),
+         ld_f(a + (p * av.pitch + av.off + c)) + ld_f(b + (p * bv.pitch + bv.off + c)));
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void copy_kernel(const TI* __restrict__ s, View sv, TO* __restrict__ o, View ov, long P, int C,
+                            int accumulate) {
+  long total = P * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long p = i / C;
+    int c = (int)(i - p * C);
+    float v = ld_f(s + (p * sv.pitch + sv.off + c));
+    TO* dst = o + (p * ov.pitch + ov.off + c);
+    if (accumulate) v += ld_f(dst);
+    st_f(dst, v);
+  }
+}
+
+// ------------------------------------------------------------------ max-pool 2x2 / upsample 2x
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, View xv, T* __restrict__ y, View yv, int N, int Ho, int Wo,
+                                   int C) {
+  long total = (long)N * Ho * Wo * C;
+  const int W = Wo * 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long q = i / C;
+    int wo = (int)(q % Wo);
+    long t = q / Wo;
+    int ho = (int)(t % Ho);
+    long n = t / Ho;
+    long p00 = (n * 2 * Ho + 2 * ho) * W + 2 * wo;
+    float v = ld_f(x + (p00 * xv.pitch + xv.off + c));
+    v = fmaxf(v, ld_f(x + ((p00 + 1) * xv.pitch + xv.off + c)));
+    v = fmaxf(v, ld_f(x + ((p00 + W) * xv.pitch + xv.off + c)));
+    v = fmaxf(v, ld_f(x + ((p00 + W + 1) * xv.pitch + xv.off + c)));
+    st_f(y + (q * yv.pitch + yv.off + c), v);
+  }
+}
+
+// dx = dy routed to the first window position (row-major) whose value equals the max
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, View dv, const T* __restrict__ x, View xv,
+                                   const T* __restrict__ y, View yv, T* __restrict__ dx, View ov, int N, int Ho, int Wo,
+                                   int C) {
+  long total = (long)N * Ho * Wo * C;
+  const int W = Wo * 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long q = i / C;
+    int wo = (int)(q % Wo);
+    long t = q / Wo;
+    int ho = (int)(t % Ho);
+    long n = t / Ho;
+    long p00 = (n * 2 * Ho + 2 * ho) * W + 2 * wo;
+    float m = ld_f(y + (q * yv.pitch + yv.off + c));
+    float g = ld_f(dy + (q * dv.pitch + dv.off + c));
+    long pos[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = ld_f(x + (pos[k] * xv.pitch + xv.off + c));
+      bool hit = !done && v == m;
+      st_f(dx + (pos[k] * ov.pitch + ov.off + c), hit ? g : 0.f);
+      done = done || hit;
+    }
+  }
+}
+
+// y[n,2h+i,2w+j,c] = relu(x[n,h,w,c])
+template <typename T>
+__global__ void upsample_relu_fwd_kernel(const T* __restrict__ x, View xv, T* __restrict__ y, View yv, int N, int H,
+                                         int W, int C) {
+  long total = (long)N * 2 * H * 2 * W * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long q = i / C;
+    int w2 = (int)(q % (2 * W));
+    long t = q / (2 * W);
+    int h2 = (int)(t % (2 * H));
+    long n = t / (2 * H);
+    long p = (n * H + h2 / 2) * W + w2 / 2;
+    float v = ld_f(x + (p * xv.pitch + xv.off + c));
+    st_f(y + (q * yv.pitch + yv.off + c), v > 0.f ? v : 0.f);
+  }
+}
+
+// dx[n,h,w,c] = (x > 0) * sum_{i,j} dy[n,2h+i,2w+j,c]
+template <typename T>
+__global__ void upsample_relu_bwd_kernel(const T* __restrict__ dy, View dv, const T* __restrict__ x, View xv,
+                                         T* __restrict__ dx, View ov, int N, int H, int W, int C) {
+  long total = (long)N * H * W * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long p = i / C;
+    int w = (int)(p % W);
+    long t = p / W;
+    int h = (int)(t % H);
+    long n = t / H;
+    long q00 = (n * 2 * H + 2 * h) * 2 * W + 2 * w;
+    float g = ld_f(dy + (q00 * dv.pitch + dv.off + c)) + ld_f(dy + ((q00 + 1) * dv.pitch + dv.off + c)) +
+              ld_f(dy + ((q00 + 2 * W) * dv.pitch + dv.off + c)) + ld_f(dy + ((q00 + 2 * W + 1) * dv.pitch + dv.off + c));
+    float v = ld_f(x + (p * xv.pitch + xv.off + c));
+    st_f(dx + (p * ov.pitch + ov.off + c), v > 0.f ? g : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ VGG19 'caffe' preprocessing
+// out[p][c'] = (in[p][2-c'] + 1) * 127.5 - mean_bgr[c']      (srgan.py:71-72)
+template <typename TI, typename TO>
+__global__ void vgg_pre_fwd_kernel(const TI* __restrict__ x, View xv, TO* __restrict__ y, View yv, long P) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < P * 3; i += (long)gridDim.x * blockDim.x) {
+    long p = i / 3;
+    int c = (int)(i - p * 3);
+    const float mean = c == 0 ? 103.939f : (c == 1 ? 116.779f : 123.68f);
+    float v = ((ld_f(x + (p * xv.pitch + xv.off + 2 - c)) + 1.0f) * 255.0f) / 2.0f - mean;
+    st_f(y + (p * yv.pitch + yv.off + c), v);
+  }
+}
+// dx[p][c] = 127.5 * dy[p][2-c]
+template <typename TI, typename TO>
+__global__ void vgg_pre_bwd_kernel(const TI* __restrict__ dy, View dv, TO* __restrict__ dx, View ov, long P) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < P * 3; i += (long)gridDim.x * blockDim.x) {
+    long p = i / 3;
+    int c = (int)(i - p * 3);
+    st_f(dx + (p * ov.pitch + ov.off + c), 127.5f * ld_f(dy + (p * dv.pitch + dv.off + 2 - c)));
+  }
+}
+
+inline View view_of(const dg_tensor* t) { return View{t->cpitch, t->coff}; }
+inline unsigned ew_blocks(long total, int sm_count) {
+  long b = (total + 255) / 256;
+  long cap = (long)sm_count * 16;
+  return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" size_t dg_bn_workspace_bytes(const dg_tensor* x) {
+  // partials [blocks][3][C] + coef [2][C]; blocks <= 148*8 (sized for any device <= 256 SMs)
+  return ((size_t)256 * 8 * 3 * x->c + 2 * (size_t)x->c) * sizeof(float);
+}
+
+extern "C" int dg_bn_stats(dg_ctx* ctx, const dg_tensor* x, const float* gamma, const float* beta, float eps,
+                           float momentum, float* moving_mean, float* moving_var, float* scale, float* shift,
+                           float* save_mean, float* save_invstd, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  DG_REQUIRE(dg_valid(x) && gamma && beta && scale && shift && save_mean && save_invstd && workspace,
+             "dg_bn_stats: null argument");
+  DG_REQUIRE(x->c <= RED_THREADS * MAX_CPT, "dg_bn_stats: C=%d too large", x->c);
+  DG_REQUIRE(workspace_bytes >= dg_bn_workspace_bytes(x), "dg_bn_stats: workspace too small");
+  long P = dg_pixels(x);
+  int C = x->c;
+  int blocks = red_blocks(P, C, ctx->sm_count);
+  int R = RED_THREADS / red_lanes(C);
+  size_t smem = (size_t)R * 2 * C * sizeof(float);
+  float* partial = (float*)workspace;
+  DG_DISPATCH_1(x->dtype, "dg_bn_stats",
+                bn_stats_kernel<T><<<blocks, RED_THREADS, smem, ST>>>((const T*)x->ptr, view_of(x), P, C, partial););
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partial, blocks, P, C, gamma, beta, eps, momentum, moving_mean,
+                                                      moving_var, scale, shift, save_mean, save_invstd);
+  DG_CHECK_LAUNCH("dg_bn_stats");
+  return 0;
+}
+
+extern "C" int dg_bn_infer_affine(dg_ctx* ctx, int c, const float* gamma, const float* beta, const float* moving_mean,
+                                  const float* moving_var, float eps, float* scale, float* shift, void* stream) {
+  DG_REQUIRE(c > 0 && gamma && beta && moving_mean && moving_var && scale && shift, "dg_bn_infer_affine: null argument");
+  bn_infer_affine_kernel<<<(c + 127) / 128, 128, 0, ST>>>(c, gamma, beta, moving_mean, moving_var, eps, scale, shift);
+  DG_CHECK_LAUNCH("dg_bn_infer_affine");
+  return 0;
+}
+
+extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale, const float* shift, int act,
+                             float act_alpha, const float* prelu_alpha, const dg_tensor* residual, int dropout,
+                             uint32_t seed, uint32_t offset, const dg_tensor* y, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y) && scale && shift, "dg_bn_act_fwd: null argument");
+  DG_REQUIRE(dg_same_shape(x, y), "dg_bn_act_fwd: shape mismatch");
+  DG_REQUIRE(act != DG_ACT_PRELU || prelu_alpha, "dg_bn_act_fwd: PReLU needs alpha");
+  if (residual) DG_REQUIRE(dg_valid(residual) && dg_same_shape(residual, y) && residual->dtype == y->dtype,
+                           "dg_bn_act_fwd: residual mismatch");
+  long P = dg_pixels(x);
+  int C = x->c;
+  View rv = residual ? view_of(residual) : View{0, 0};
+  DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
+                bn_act_fwd_kernel<TI, TO><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
+                    (const TI*)x->ptr, view_of(x), scale, shift, act, act_alpha, prelu_alpha,
+                    residual ? (const TO*)residual->ptr : nullptr, rv, dropout, seed, offset, (TO*)y->ptr, view_of(y), P, C););
+  DG_CHECK_LAUNCH("dg_bn_act_fwd");
+  return 0;
+}
+
+extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const float* scale,
+                             const float* shift, const float* gamma, const float* save_mean, const float* save_invstd,
+                             int act, float act_alpha, const float* prelu_alpha, int dropout, uint32_t seed,
+                             uint32_t offset, const dg_tensor* dx, float* dgamma, float* dbeta, float* dprelu_alpha,
+                             int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(dx) && scale && shift && gamma && save_mean && save_invstd &&
+                 workspace, "dg_bn_act_bwd: null argument");
+  DG_REQUIRE(dg_same_shape(dy, x) && dg_same_shape(dx, x), "dg_bn_act_bwd: shape mismatch");
+  DG_REQUIRE(dy->dtype == dx->dtype, "dg_bn_act_bwd: dy/dx dtype mismatch");
+  DG_REQUIRE(x->c <= RED_THREADS * MAX_CPT, "dg_bn_act_bwd: C too large");
+  DG_REQUIRE(workspace_bytes >= dg_bn_workspace_bytes(x), "dg_bn_act_bwd: workspace too small");
+  long P = dg_pixels(x);
+  int C = x->c;
+  int blocks = red_blocks(P, C, ctx->sm_count);
+  int R = RED_THREADS / red_lanes(C);
+  size_t smem = (size_t)R * 3 * C * sizeof(float);
+  float* partial = (float*)workspace;
+  float* coef = partial + (size_t)256 * 8 * 3 * C;
+  DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
+    bn_bwd_reduce_kernel<TI, TO><<<blocks, RED_THREADS, smem, ST>>>(
+        (const TI*)dy->ptr, view_of(dy), (const TO*)x->ptr, view_of(x), scale, shift, save_mean, save_invstd, act,
+        act_alpha, prelu_alpha, dropout, seed, offset, P, C, partial);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partial, blocks, P, C, dgamma, dbeta,
+                                                            act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
+    bn_bwd_dx_kernel<TI, TO, TI><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
+        (const TI*)dy->ptr, view_of(dy), (const TO*)x->ptr, view_of(x), scale, shift, gamma, save_mean, save_invstd,
+        act, act_alpha, prelu_alpha, dropout, seed, offset, coef, (TI*)dx->ptr, view_of(dx), P, C);
+  });
+  DG_CHECK_LAUNCH("dg_bn_act_bwd");
+  return 0;
+}
+
+extern "C" int dg_act_bwd_from_output(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* y, int act, float act_alpha,
+                                      const dg_tensor* dpre, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(y) && dg_valid(dpre), "dg_act_bwd_from_output: null argument");
+  DG_REQUIRE(dg_same_shape(dy, y) && dg_same_shape(dpre, y), "dg_act_bwd_from_output: shape mismatch");
+  DG_REQUIRE(dy->dtype == dpre->dtype, "dg_act_bwd_from_output: dy/dpre dtype mismatch");
+  DG_REQUIRE(act != DG_ACT_PRELU, "dg_act_bwd_from_output: PReLU needs the pre-activation");
+  long P = dg_pixels(y);
+  int C = y->c;
+  DG_DISPATCH_2(dy->dtype, y->dtype, "dg_act_bwd_from_output",
+                act_bwd_kernel<TI, TO, TI><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
+                    (const TI*)dy->ptr, view_of(dy), (const TO*)y->ptr, view_of(y), act, act_alpha, (TI*)dpre->ptr,
+                    view_of(dpre), P, C););
+  DG_CHECK_LAUNCH("dg_act_bwd_from_output");
+  return 0;
+}
+
+extern "C" int dg_d2s_prelu_fwd(dg_ctx* ctx, const dg_tensor* u, const float* prelu_alpha, const dg_tensor* y,
+                                void* stream) {
+  DG_REQUIRE(dg_valid(u) && dg_valid(y), "dg_d2s_prelu_fwd: null argument");
+  DG_REQUIRE(u->c % 4 == 0 && y->c * 4 == u->c && y->h == 2 * u->h && y->w == 2 * u->w && y->n == u->n,
+             "dg_d2s_prelu_fwd: shape mismatch");
+  DG_REQUIRE(u->dtype == y->dtype, "dg_d2s_prelu_fwd: dtype mismatch");
+  long total = dg_pixels(u) * u->c;
+  DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_fwd",
+                d2s_prelu_fwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+                    (const T*)u->ptr, view_of(u), prelu_alpha, (T*)y->ptr, view_of(y), u->n, u->h, u->w, y->c););
+  DG_CHECK_LAUNCH("dg_d2s_prelu_fwd");
+  return 0;
+}
+
+extern "C" int dg_d2s_prelu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* u, const float* prelu_alpha,
+                                const dg_tensor* du, float* dprelu_alpha, int accumulate, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(u) && dg_valid(du), "dg_d2s_prelu_bwd: null argument");
+  DG_REQUIRE(dy->c * 4 == u->c && dy->h == 2 * u->h && dy->w == 2 * u->w && dg_same_shape(u, du),
+             "dg_d2s_prelu_bwd: shape mismatch");
+  DG_REQUIRE(dy->dtype == u->dtype && du->dtype == u->dtype, "dg_d2s_prelu_bwd: dtype mismatch");
+  long total = dg_pixels(u) * u->c;
+  int Co = dy->c;
+  DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_bwd", {
+    d2s_prelu_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+        (const T*)dy->ptr, view_of(dy), (const T*)u->ptr, view_of(u), prelu_alpha, (T*)du->ptr, view_of(du), u->n, u->h,
+        u->w, Co);
+    if (prelu_alpha && dprelu_alpha) {
+      DG_REQUIRE(workspace && workspace_bytes >= dg_bn_workspace_bytes(dy), "dg_d2s_prelu_bwd: workspace too small");
+      long Pout = dg_pixels(dy);
+      int blocks = red_blocks(Pout, Co, ctx->sm_count);
+      int R = RED_THREADS / red_lanes(Co);
+      float* partial = (float*)workspace;
+      d2s_prelu_dalpha_kernel<T><<<blocks, RED_THREADS, (size_t)R * Co * sizeof(float), ST>>>(
+          (const T*)dy->ptr, view_of(dy), (const T*)u->ptr, view_of(u), Pout, dy->h, dy->w, Co, partial);
+      sum_partials_kernel<<<(Co + 127) / 128, 128, 0, ST>>>(partial, blocks, Co, dprelu_alpha, accumulate);
+    }
+  });
+  DG_CHECK_LAUNCH("dg_d2s_prelu_bwd");
+  return 0;
+}
+
+extern "C" int dg_add(dg_ctx* ctx, const dg_tensor* a, const dg_tensor* b, const dg_tensor* out, void* stream) {
+  DG_REQUIRE(dg_valid(a) && dg_valid(b) && dg_valid(out), "dg_add: null argument");
+  DG_REQUIRE(dg_same_shape(a, b) && dg_same_shape(a, out) && a->dtype == b->dtype, "dg_add: shape/dtype mismatch");
+  long P = dg_pixels(a);
+  DG_DISPATCH_2(a->dtype, out->dtype, "dg_add",
+                add_kernel<TI, TO><<<ew_blocks(P * a->c, ctx->sm_count), 256, 0, ST>>>(
+                    (const TI*)a->ptr, view_of(a), (const TI*)b->ptr, view_of(b), (TO*)out->ptr, view_of(out), P, a->c););
+  DG_CHECK_LAUNCH("dg_add");
+  return 0;
+}
+
+extern "C" int dg_copy(dg_ctx* ctx, const dg_tensor* src, const dg_tensor* out, int accumulate, void* stream) {
+  DG_REQUIRE(dg_valid(src) && dg_valid(out), "dg_copy: null argument");
+  DG_REQUIRE(dg_same_shape(src, out), "dg_copy: shape mismatch");
+  long P = dg_pixels(src);
+  DG_DISPATCH_2(src->dtype, out->dtype, "dg_copy",
+                copy_kernel<TI, TO><<<ew_blocks(P * src->c, ctx->sm_count), 256, 0, ST>>>(
+                    (const TI*)src->ptr, view_of(src), (TO*)out->ptr, view_of(out), P, src->c, accumulate););
+  DG_CHECK_LAUNCH("dg_copy");
+  return 0;
+}
+
+extern "C" int dg_maxpool2x2_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y), "dg_maxpool2x2_fwd: null argument");
+  DG_REQUIRE(x->h == 2 * y->h && x->w == 2 * y->w && x->c == y->c && x->n == y->n && x->dtype == y->dtype,
+             "dg_maxpool2x2_fwd: shape mismatch (even sizes only)");
+  long total = dg_pixels(y) * y->c;
+  DG_DISPATCH_1(x->dtype, "dg_maxpool2x2_fwd",
+                maxpool_fwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+                    (const T*)x->ptr, view_of(x), (T*)y->ptr, view_of(y), y->n, y->h, y->w, y->c););
+  DG_CHECK_LAUNCH("dg_maxpool2x2_fwd");
+  return 0;
+}
+
+extern "C" int dg_maxpool2x2_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y,
+                                 const dg_tensor* dx, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(y) && dg_valid(dx), "dg_maxpool2x2_bwd: null argument");
+  DG_REQUIRE(dg_same_shape(dy, y) && dg_same_shape(dx, x) && x->h == 2 * y->h && x->w == 2 * y->w,
+             "dg_maxpool2x2_bwd: shape mismatch");
+  DG_REQUIRE(dy->dtype == x->dtype && y->dtype == x->dtype && dx->dtype == x->dtype, "dg_maxpool2x2_bwd: dtype mismatch");
+  long total = dg_pixels(y) * y->c;
+  DG_DISPATCH_1(x->dtype, "dg_maxpool2x2_bwd",
+                maxpool_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+                    (const T*)dy->ptr, view_of(dy), (const T*)x->ptr, view_of(x), (const T*)y->ptr, view_of(y),
+                    (T*)dx->ptr, view_of(dx), y->n, y->h, y->w, y->c););
+  DG_CHECK_LAUNCH("dg_maxpool2x2_bwd");
+  return 0;
+}
+
+extern "C" int dg_upsample2x_relu_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y), "dg_upsample2x_relu_fwd: null argument");
+  DG_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && x->c == y->c && x->n == y->n && x->dtype == y->dtype,
+             "dg_upsample2x_relu_fwd: shape mismatch");
+  long total = dg_pixels(y) * y->c;
+  DG_DISPATCH_1(x->dtype, "dg_upsample2x_relu_fwd",
+                upsample_relu_fwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+                    (const T*)x->ptr, view_of(x), (T*)y->ptr, view_of(y), x->n, x->h, x->w, x->c););
+  DG_CHECK_LAUNCH("dg_upsample2x_relu_fwd");
+  return 0;
+}
+
+extern "C" int dg_upsample2x_relu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* dx,
+                                      void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(dx), "dg_upsample2x_relu_bwd: null argument");
+  DG_REQUIRE(dy->h == 2 * x->h && dy->w == 2 * x->w && dy->c == x->c && dg_same_shape(dx, x) &&
+                 dy->dtype == x->dtype && dx->dtype == x->dtype, "dg_upsample2x_relu_bwd: shape mismatch");
+  long total = dg_pixels(x) * x->c;
+  DG_DISPATCH_1(x->dtype, "dg_upsample2x_relu_bwd",
+                upsample_relu_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+                    (const T*)dy->ptr, view_of(dy), (const T*)x->ptr, view_of(x), (T*)dx->ptr, view_of(dx), x->n, x->h,
+                    x->w, x->c););
+  DG_CHECK_LAUNCH("dg_upsample2x_relu_bwd");
+  return 0;
+}
+
+extern "C" int dg_vgg_preprocess_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y), "dg_vgg_preprocess_fwd: null argument");
+  DG_REQUIRE(x->c == 3 && dg_same_shape(x, y), "dg_vgg_preprocess_fwd: expects 3-channel images");
+  long P = dg_pixels(x);
+  DG_DISPATCH_2(x->dtype, y->dtype, "dg_vgg_preprocess_fwd",
+                vgg_pre_fwd_kernel<TI, TO><<<ew_blocks(P * 3, ctx->sm_count), 256, 0, ST>>>(
+                    (const TI*)x->ptr, view_of(x), (TO*)y->ptr, view_of(y), P););
+  DG_CHECK_LAUNCH("dg_vgg_preprocess_fwd");
+  return 0;
+}
+
+extern "C" int dg_vgg_preprocess_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* dx, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(dx), "dg_vgg_preprocess_bwd: null argument");
+  DG_REQUIRE(dy->c == 3 && dg_same_shape(dy, dx), "dg_vgg_preprocess_bwd: expects 3-channel images");
+  long P = dg_pixels(dy);
+  DG_DISPATCH_2(dy->dtype, dx->dtype, "dg_vgg_preprocess_bwd",
+                vgg_pre_bwd_kernel<TI, TO><<<ew_blocks(P * 3, ctx->sm_count), 256, 0, ST>>>(
+                    (const TI*)dy->ptr, view_of(dy), (TO*)dx->ptr, view_of(dx), P););
+  DG_CHECK_LAUNCH("dg_vgg_preprocess_bwd");
+  return 0;
+}

@@ -1,0 +1,563 @@
+"""Tape executor for the hot path: a tiny define-by-run graph whose nodes are calls into the
+dg_b200 C ABI.  It stands where TensorFlow's GradientTape stands in the reference
+(train_srgan.py:73-112): `forward` ops append nodes, `backward(seeds, group)` replays them in
+reverse for one variable group ('g' or 'd'), exactly the two `tape.gradient` calls of the
+reference's train_step.
+
+All activation, gradient and workspace buffers come from a persistent pool keyed by the op's
+position in the step, so addresses are identical every step and a whole train step can be
+captured into one CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, DgConvParams, check, tensor
+from .params import Param
+
+
+def same_pads(in_size: int, k: int, s: int):
+    """TF 'SAME' (pad_before, pad_after)."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return total // 2, total - total // 2
+
+
+class Var:
+    """An NHWC activation on the tape."""
+    __slots__ = ("t", "deps", "seq")
+
+    def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
+        self.t, self.deps, self.seq = t, deps, seq
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+
+class Node:
+    __slots__ = ("seq", "inputs", "out", "group", "bwd")
+
+    def __init__(self, seq, inputs, out, group, bwd):
+        self.seq, self.inputs, self.out, self.group, self.bwd = seq, inputs, out, group, bwd
+
+
+class Engine:
+    def __init__(self, device=None, bf16: bool = False):
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.ctx = _lib.ctx(self.device.index)
+        self.bf16 = bool(bf16)
+        self.act_dtype = torch.bfloat16 if bf16 else torch.float32
+        self.pool: dict = {}
+        self.tape: list[Node] = []
+        self.seq = 0
+        self._ws = None
+        self.written: set = set()      # param names whose grad slice was written this step
+        self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
+        self.use_umma_wgrad = False
+        self.launches = 0
+        self.record = None             # dict name -> Var when a test wants per-layer activations
+
+    def mark(self, name: str, v: "Var") -> "Var":
+        if self.record is not None:
+            self.record[name] = v
+        return v
+
+    # ------------------------------------------------------------------ plumbing
+    def new_step(self):
+        self.tape.clear()
+        self.seq = 0
+        self.written.clear()
+        self.launches = 0
+
+    def buf(self, key, shape, dtype) -> torch.Tensor:
+        k = (key, tuple(shape), dtype)
+        t = self.pool.get(k)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.pool[k] = t
+        return t
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _next(self):
+        self.seq += 1
+        return self.seq
+
+    def _push(self, inputs, out: Var, group, bwd):
+        self.tape.append(Node(out.seq, inputs, out, group, bwd))
+
+    @staticmethod
+    def _deps(inputs, group=None):
+        d = frozenset()
+        for v in inputs:
+            d = d | v.deps
+        return d | {group} if group else d
+
+    def _acc_flag(self, p: Param) -> int:
+        if p.name in self.written:
+            return 1
+        self.written.add(p.name)
+        return 0
+
+    def input(self, t: torch.Tensor) -> Var:
+        return Var(t.contiguous(), frozenset(), self._next())
+
+    @property
+    def st(self):
+        return _lib.stream_ptr()
+
+    # ------------------------------------------------------------------ convolution
+    def _conv_geom(self, H, W, kh, kw, stride, padding):
+        if padding == "same":
+            (pt, pb), (pl, pr) = same_pads(H, kh, stride), same_pads(W, kw, stride)
+        elif padding == "valid":
+            pt = pb = pl = pr = 0
+        else:
+            (pt, pb), (pl, pr) = padding
+        Ho = (H + pt + pb - kh) // stride + 1
+        Wo = (W + pl + pr - kw) // stride + 1
+        return pt, pl, Ho, Wo
+
+    def _umma_ok(self, x: torch.Tensor, cin, cout, kh, kw, stride, H, W):
+        return (self.use_umma and x.dtype == torch.bfloat16 and cin % 16 == 0 and cout % 16 == 0 and kh * kw <= 16
+                and stride in (1, 2) and (stride == 1 or (H % 2 == 0 and W % 2 == 0)))
+
+    def _packed(self, p: Param, mode: int) -> torch.Tensor:
+        attr = "packed_fwd" if mode == 0 else "packed_dgrad"
+        t = getattr(p, attr)
+        if t is None:
+            kh, kw, cin, cout = p.shape
+            t = torch.empty(p.numel, dtype=torch.bfloat16, device=self.device)
+            setattr(p, attr, t)
+            check(self.lib.dg_umma_pack_weights(self.ctx, p.data.data_ptr(), t.data_ptr(), kh, kw, cin, cout, mode, self.st))
+        return t
+
+    def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
+               out_dtype=None) -> Var:
+        """keras Conv2D (+bias, +activation epilogue)."""
+        N, H, W, Cin = x.shape
+        kh, kw, cin, cout = w.shape
+        assert cin == Cin, f"{w.name}: Cin {cin} != input {Cin}"
+        pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, stride, padding)
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
+        cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
+        umma = self._umma_ok(x.t, cin, cout, kh, kw, stride, H, W)
+        tx, ty = tensor(x.t), tensor(y)
+        bias = _lib.ptr(b.data) if b is not None else None
+        if umma:
+            check(self.lib.dg_umma_conv2d_fwd(self.ctx, C.byref(tx), self._packed(w, 0).data_ptr(), bias, C.byref(ty),
+                                              C.byref(cp), None, self.st))
+        else:
+            check(self.lib.dg_conv2d_fwd(self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st))
+        out = Var(y, self._deps([x], w.group), seq)
+        lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
+
+        def bwd(gy: torch.Tensor, need_in, need_p, tag):
+            dpre = gy
+            if ACT[act]:
+                dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
+                tg, tyy, td = tensor(gy), tensor(y), tensor(dpre)
+                check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
+            tdp = tensor(dpre)
+            if need_p:
+                self._wgrad(x.t, dpre, w, b, lin)
+            dx = None
+            if need_in[0]:
+                dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                tdx = tensor(dx)
+                if umma and dpre.dtype == torch.bfloat16:
+                    check(self.lib.dg_umma_conv2d_dgrad(self.ctx, C.byref(tdp), self._packed(w, 1).data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
+                else:
+                    check(self.lib.dg_conv2d_dgrad(self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
+            return [dx]
+
+        self._push([x], out, w.group, bwd)
+        return out
+
+    def _wgrad(self, x: torch.Tensor, dy: torch.Tensor, w: Param, b: Param | None, lin: DgConvParams):
+        """dW (+ dbias) of the forward conv `lin` with input x and output-gradient dy, into the grad arena."""
+        tx, tdy = tensor(x), tensor(dy)
+        acc = self._acc_flag(w)
+        if b is not None:
+            accb = self._acc_flag(b)
+            assert accb == acc
+        dbias = b.grad.data_ptr() if b is not None else None
+        kh, kw, cin, cout = lin.kh, lin.kw, x.shape[3], dy.shape[3]
+        if (self.use_umma_wgrad and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and
+                self._umma_ok(x, cin, cout, kh, kw, lin.stride, x.shape[1], x.shape[2])):
+            nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))
+            ws = self.workspace(nbytes)
+            check(self.lib.dg_umma_conv2d_wgrad(self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc,
+                                                ws.data_ptr(), nbytes, self.st))
+        else:
+            nbytes = self.lib.dg_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))
+            ws = self.workspace(nbytes)
+            check(self.lib.dg_conv2d_wgrad(self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc,
+                                           ws.data_ptr(), nbytes, self.st))
+
+    def conv2d_transpose(self, x: Var, w: Param, b: Param | None = None, *, stride=2, act=None, alpha=0.0,
+                         out_dtype=None) -> Var:
+        """keras Conv2DTranspose(padding='same'), kernel [kh,kw,Cout,Cin]: the input-gradient of the SAME conv
+        f: [N,sH,sW,Cout] -> [N,H,W,Cin]."""
+        N, H, W, Cin = x.shape
+        kh, kw, cout, cin = w.shape
+        assert cin == Cin
+        Ho, Wo = H * stride, W * stride
+        pt, _ = same_pads(Ho, kh, stride)
+        pl, _ = same_pads(Wo, kw, stride)
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
+        cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
+        lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
+        # as a forward conv f, the kernel is HWIO with I = cout (of the transposed conv), O = cin
+        umma = self._umma_ok(x.t, cin, cout, kh, kw, stride, Ho, Wo)
+        tx, ty = tensor(x.t), tensor(y)
+        bias = _lib.ptr(b.data) if b is not None else None
+        if umma:
+            check(self.lib.dg_umma_conv2d_dgrad(self.ctx, C.byref(tx), self._packed(w, 1).data_ptr(), bias, C.byref(ty), C.byref(cp), self.st))
+        else:
+            check(self.lib.dg_conv2d_dgrad(self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st))
+        out = Var(y, self._deps([x], w.group), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            dpre = gy
+            if ACT[act]:
+                dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
+                tg, tyy, td = tensor(gy), tensor(y), tensor(dpre)
+                check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
+            if need_p:
+                # dWt = wgrad of f with "input" = dY (large image) and "output grad" = x (small image)
+                self._wgrad(dpre, x.t, w, None, lin)
+                if b is not None:
+                    raise NotImplementedError("bias gradient of Conv2DTranspose handled by caller")
+            dx = None
+            if need_in[0]:
+                dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                tdp, tdx = tensor(dpre), tensor(dx)
+                if umma and dpre.dtype == torch.bfloat16:
+                    check(self.lib.dg_umma_conv2d_fwd(self.ctx, C.byref(tdp), self._packed(w, 0).data_ptr(), None, C.byref(tdx), C.byref(lin), None, self.st))
+                else:
+                    check(self.lib.dg_conv2d_fwd(self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
+            return [dx]
+
+        self._push([x], out, w.group, bwd)
+        return out
+
+    def dwconv3x3(self, x: Var, w: Param, b: Param | None) -> Var:
+        """keras DepthwiseConv2D(3, padding='same')."""
+        seq = self._next()
+        y = self.buf((seq, "y"), x.shape, x.t.dtype)
+        tx, ty = tensor(x.t), tensor(y)
+        check(self.lib.dg_dwconv3x3_fwd(self.ctx, C.byref(tx), w.data.data_ptr(), _lib.ptr(b.data) if b is not None else None, C.byref(ty), self.st))
+        out = Var(y, self._deps([x], w.group), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            tg = tensor(gy)
+            if need_p:
+                acc = self._acc_flag(w)
+                if b is not None:
+                    self._acc_flag(b)
+                nbytes = self.lib.dg_dwconv3x3_wgrad_workspace_bytes(C.byref(tx))
+                ws = self.workspace(nbytes)
+                check(self.lib.dg_dwconv3x3_wgrad(self.ctx, C.byref(tx), C.byref(tg), w.grad.data_ptr(),
+                                                  b.grad.data_ptr() if b is not None else None, acc, ws.data_ptr(), nbytes, self.st))
+            dx = None
+            if need_in[0]:
+                dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                tdx = tensor(dx)
+                check(self.lib.dg_dwconv3x3_dgrad(self.ctx, C.byref(tg), w.data.data_ptr(), C.byref(tdx), self.st))
+            return [dx]
+
+        self._push([x], out, w.group, bwd)
+        return out
+
+    # ------------------------------------------------------------------ batch norm (+act, +residual, +dropout)
+    def bn_act(self, x: Var, pset, name: str, *, training: bool, momentum=0.99, eps=1e-3, act=None, alpha=0.0,
+               prelu: Param | None = None, residual: Var | None = None, dropout_seed=None, dropout_offset=0) -> Var:
+        gamma, beta = pset[name + "/gamma"], pset[name + "/beta"]
+        mm, mv = pset[name + "/moving_mean"], pset[name + "/moving_variance"]
+        Cc = x.shape[3]
+        seq = self._next()
+        scale = self.buf((seq, "scale"), (Cc,), torch.float32)
+        shift = self.buf((seq, "shift"), (Cc,), torch.float32)
+        mean = self.buf((seq, "mean"), (Cc,), torch.float32)
+        invstd = self.buf((seq, "invstd"), (Cc,), torch.float32)
+        tx = tensor(x.t)
+        nbytes = self.lib.dg_bn_workspace_bytes(C.byref(tx))
+        ws = self.workspace(nbytes)
+        if training:
+            check(self.lib.dg_bn_stats(self.ctx, C.byref(tx), gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
+                                       mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                       invstd.data_ptr(), ws.data_ptr(), nbytes, self.st))
+        else:
+            check(self.lib.dg_bn_infer_affine(self.ctx, Cc, gamma.data.data_ptr(), beta.data.data_ptr(), mm.data.data_ptr(),
+                                              mv.data.data_ptr(), float(eps), scale.data_ptr(), shift.data_ptr(), self.st))
+        y = self.buf((seq, "y"), x.shape, x.t.dtype)
+        ty = tensor(y)
+        tres = tensor(residual.t) if residual is not None else None
+        drop = 1 if (dropout_seed is not None and training) else 0
+        a_code = ACT["prelu"] if prelu is not None else ACT[act]
+        check(self.lib.dg_bn_act_fwd(self.ctx, C.byref(tx), scale.data_ptr(), shift.data_ptr(), a_code, float(alpha),
+                                     _lib.ptr(prelu.data) if prelu is not None else None,
+                                     C.byref(tres) if tres is not None else None, drop, int(dropout_seed or 0), int(dropout_offset),
+                                     C.byref(ty), self.st))
+        inputs = [x] + ([residual] if residual is not None else [])
+        out = Var(y, self._deps(inputs, gamma.group), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            assert training, "backward through inference-mode BN is not part of the hot path"
+            dx = self.buf((seq, "dx", tag), x.shape, gy.dtype)
+            tg, tdx = tensor(gy), tensor(dx)
+            if need_p:
+                acc = self._acc_flag(gamma)
+                self._acc_flag(beta)
+                if prelu is not None:
+                    self._acc_flag(prelu)
+                dg, db = gamma.grad.data_ptr(), beta.grad.data_ptr()
+                da = prelu.grad.data_ptr() if prelu is not None else None
+            else:
+                acc, dg, db, da = 0, None, None, None
+            check(self.lib.dg_bn_act_bwd(self.ctx, C.byref(tg), C.byref(tx), scale.data_ptr(), shift.data_ptr(), gamma.data.data_ptr(),
+                                         mean.data_ptr(), invstd.data_ptr(), a_code, float(alpha),
+                                         _lib.ptr(prelu.data) if prelu is not None else None, drop, int(dropout_seed or 0),
+                                         int(dropout_offset), C.byref(tdx), dg, db, da, acc, ws.data_ptr(), nbytes, self.st))
+            res = [dx if need_in[0] else None]
+            if residual is not None:
+                res.append(gy if need_in[1] else None)
+            return res
+
+        self._push(inputs, out, gamma.group, bwd)
+        return out
+
+    # ------------------------------------------------------------------ structural ops
+    def d2s_prelu(self, u: Var, prelu: Param | None) -> Var:
+        """tf.nn.depth_to_space(u, 2) then PReLU(shared_axes=[1,2])."""
+        N, H, W, C4 = u.shape
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, 2 * H, 2 * W, C4 // 4), u.t.dtype)
+        tu, ty = tensor(u.t), tensor(y)
+        check(self.lib.dg_d2s_prelu_fwd(self.ctx, C.byref(tu), _lib.ptr(prelu.data) if prelu is not None else None, C.byref(ty), self.st))
+        group = prelu.group if prelu is not None else None
+        out = Var(y, self._deps([u], group), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            du = self.buf((seq, "du", tag), u.shape, gy.dtype)
+            tg, tdu = tensor(gy), tensor(du)
+            da, acc = None, 0
+            if need_p and prelu is not None:
+                acc = self._acc_flag(prelu)
+                da = prelu.grad.data_ptr()
+            nbytes = self.lib.dg_bn_workspace_bytes(C.byref(tg))
+            ws = self.workspace(nbytes)
+            check(self.lib.dg_d2s_prelu_bwd(self.ctx, C.byref(tg), C.byref(tu), _lib.ptr(prelu.data) if prelu is not None else None,
+                                            C.byref(tdu), da, acc, ws.data_ptr(), nbytes, self.st))
+            return [du if need_in[0] else None]
+
+        self._push([u], out, group, bwd)
+        return out
+
+    def add(self, a: Var, b: Var) -> Var:
+        seq = self._next()
+        y = self.buf((seq, "y"), a.shape, a.t.dtype)
+        ta, tb, ty = tensor(a.t), tensor(b.t), tensor(y)
+        check(self.lib.dg_add(self.ctx, C.byref(ta), C.byref(tb), C.byref(ty), self.st))
+        out = Var(y, self._deps([a, b]), seq)
+        self._push([a, b], out, None, lambda gy, need_in, need_p, tag: [gy if need_in[0] else None, gy if need_in[1] else None])
+        return out
+
+    def concat(self, parts: list[Var]) -> Var:
+        """tf.concat(parts, axis=3) (pix2pix.py:188,200; autoencoder.py:135)."""
+        N, H, W, _ = parts[0].shape
+        ctot = sum(p.shape[3] for p in parts)
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, H, W, ctot), parts[0].t.dtype)
+        off = 0
+        offs = []
+        for p in parts:
+            c = p.shape[3]
+            tp, ty = tensor(p.t), tensor(y, c=c, coff=off)
+            check(self.lib.dg_copy(self.ctx, C.byref(tp), C.byref(ty), 0, self.st))
+            offs.append(off)
+            off += c
+        out = Var(y, self._deps(parts), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            res = []
+            for i, p in enumerate(parts):
+                if not need_in[i]:
+                    res.append(None)
+                    continue
+                g = self.buf((seq, "dpart", i, tag), p.shape, gy.dtype)
+                tg, tgi = tensor(gy, c=p.shape[3], coff=offs[i]), tensor(g)
+                check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tgi), 0, self.st))
+                res.append(g)
+            return res
+
+        self._push(list(parts), out, None, bwd)
+        return out
+
+    def maxpool2x2(self, x: Var) -> Var:
+        N, H, W, Cc = x.shape
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, H // 2, W // 2, Cc), x.t.dtype)
+        tx, ty = tensor(x.t), tensor(y)
+        check(self.lib.dg_maxpool2x2_fwd(self.ctx, C.byref(tx), C.byref(ty), self.st))
+        out = Var(y, self._deps([x]), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            if not need_in[0]:
+                return [None]
+            dx = self.buf((seq, "dx", tag), x.shape, gy.dtype)
+            tg, tdx = tensor(gy), tensor(dx)
+            check(self.lib.dg_maxpool2x2_bwd(self.ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), self.st))
+            return [dx]
+
+        self._push([x], out, None, bwd)
+        return out
+
+    def upsample2x_relu(self, x: Var) -> Var:
+        N, H, W, Cc = x.shape
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, 2 * H, 2 * W, Cc), x.t.dtype)
+        tx, ty = tensor(x.t), tensor(y)
+        check(self.lib.dg_upsample2x_relu_fwd(self.ctx, C.byref(tx), C.byref(ty), self.st))
+        out = Var(y, self._deps([x]), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            if not need_in[0]:
+                return [None]
+            dx = self.buf((seq, "dx", tag), x.shape, gy.dtype)
+            tg, tdx = tensor(gy), tensor(dx)
+            check(self.lib.dg_upsample2x_relu_bwd(self.ctx, C.byref(tg), C.byref(tx), C.byref(tdx), self.st))
+            return [dx]
+
+        self._push([x], out, None, bwd)
+        return out
+
+    def cast(self, x: Var, dtype) -> Var:
+        """dtype conversion (e.g. the fp32 'generator_tanh' output feeding a bf16 network)."""
+        if x.t.dtype == dtype:
+            return x
+        seq = self._next()
+        y = self.buf((seq, "y"), x.shape, dtype)
+        tx, ty = tensor(x.t), tensor(y)
+        check(self.lib.dg_copy(self.ctx, C.byref(tx), C.byref(ty), 0, self.st))
+        out = Var(y, self._deps([x]), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            if not need_in[0]:
+                return [None]
+            dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+            tg, tdx = tensor(gy), tensor(dx)
+            check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tdx), 0, self.st))
+            return [dx]
+
+        self._push([x], out, None, bwd)
+        return out
+
+    def vgg_preprocess(self, x: Var) -> Var:
+        """vgg19.preprocess_input(((x+1)*255)/2) in caffe mode; kept in fp32 (values are O(128))."""
+        seq = self._next()
+        y = self.buf((seq, "y"), x.shape, torch.float32)
+        tx, ty = tensor(x.t), tensor(y)
+        check(self.lib.dg_vgg_preprocess_fwd(self.ctx, C.byref(tx), C.byref(ty), self.st))
+        out = Var(y, self._deps([x]), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            if not need_in[0]:
+                return [None]
+            dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+            tg, tdx = tensor(gy), tensor(dx)
+            check(self.lib.dg_vgg_preprocess_bwd(self.ctx, C.byref(tg), C.byref(tdx), self.st))
+            return [dx]
+
+        self._push([x], out, None, bwd)
+        return out
+
+    # ------------------------------------------------------------------ losses (value + seed gradient)
+    def image_losses(self, gen: Var, target: torch.Tensor, w_mae, w_mse, w_tv, key="img"):
+        """Returns (out3 = [mae, mse, tv_mean] device tensor, dgen seed gradient)."""
+        out3 = self.buf((key, "out3"), (3,), torch.float32)
+        dgen = self.buf((key, "dgen"), gen.shape, gen.t.dtype)
+        tg, tt, td = tensor(gen.t), tensor(target), tensor(dgen)
+        nbytes = self.lib.dg_loss_workspace_bytes(C.byref(tg))
+        ws = self.workspace(nbytes)
+        check(self.lib.dg_image_losses(self.ctx, C.byref(tg), C.byref(tt), float(w_mae), float(w_mse), float(w_tv), out3.data_ptr(),
+                                       C.byref(td), 0, ws.data_ptr(), nbytes, self.st))
+        return out3, dgen
+
+    def bce(self, x: Var, target: float, from_logits: bool, grad_scale: float, key):
+        """Returns (mean BCE device scalar, seed gradient grad_scale * dBCE/dx)."""
+        loss = self.buf((key, "loss"), (1,), torch.float32)
+        dx = self.buf((key, "dx"), x.shape, x.t.dtype)
+        tx, td = tensor(x.t), tensor(dx)
+        nbytes = self.lib.dg_loss_workspace_bytes(C.byref(tx))
+        ws = self.workspace(nbytes)
+        check(self.lib.dg_bce_const_target(self.ctx, C.byref(tx), float(target), 1 if from_logits else 0, float(grad_scale),
+                                           loss.data_ptr(), C.byref(td), ws.data_ptr(), nbytes, self.st))
+        return loss, dx
+
+    def feature_mse(self, a: Var, b: Var, inv_div: float, key="feat"):
+        loss = self.buf((key, "loss"), (1,), torch.float32)
+        da = self.buf((key, "da"), a.shape, a.t.dtype)
+        ta, tb, td = tensor(a.t), tensor(b.t), tensor(da)
+        nbytes = self.lib.dg_loss_workspace_bytes(C.byref(ta))
+        ws = self.workspace(nbytes)
+        check(self.lib.dg_feature_mse(self.ctx, C.byref(ta), C.byref(tb), float(inv_div), loss.data_ptr(), C.byref(td), ws.data_ptr(),
+                                      nbytes, self.st))
+        return loss, da
+
+    # ------------------------------------------------------------------ reverse pass
+    def backward(self, seeds, group: str, tag=None, collect=None):
+        """Equivalent of `tape.gradient(loss, <variables of group>)`: `seeds` = [(Var, dL/dVar tensor)]."""
+        tag = tag or group
+        grads: dict = {}
+
+        def accum(v: Var, g: torch.Tensor):
+            cur = grads.get(v.seq)
+            if cur is None:
+                grads[v.seq] = [g, False]
+                return
+            t, owned = cur
+            if not owned:
+                n = self.buf((v.seq, "gacc", tag), t.shape, t.dtype)
+                ta, tb, tn = tensor(t), tensor(g), tensor(n)
+                check(self.lib.dg_add(self.ctx, C.byref(ta), C.byref(tb), C.byref(tn), self.st))
+                grads[v.seq] = [n, True]
+            else:
+                tg, tt = tensor(g), tensor(t)
+                check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tt), 1, self.st))
+
+        for v, g in seeds:
+            accum(v, g)
+        for node in reversed(self.tape):
+            ent = grads.pop(node.seq, None)
+            if ent is None or group not in node.out.deps:
+                continue
+            if collect is not None:
+                collect[node.seq] = ent[0]
+            need_in = [group in v.deps for v in node.inputs]
+            need_p = node.group == group
+            if not need_p and not any(need_in):
+                continue
+            gin = node.bwd(ent[0], need_in, need_p, tag)
+            for v, g in zip(node.inputs, gin):
+                if g is not None:
+                    accum(v, g)
+
+    # ------------------------------------------------------------------ optimiser
+    def adam(self, pset, lr0, beta1=0.9, beta2=0.999, eps=1e-7, decay_steps=0, decay_rate=0.1, grad_scale=1.0):
+        """Keras Adam over the whole arena; then refresh the packed bf16 kernels."""
+        check(self.lib.dg_adam_step(self.ctx, pset.theta.data_ptr(), pset.grad.data_ptr(), pset.m.data_ptr(), pset.v.data_ptr(),
+                                    pset.numel, float(lr0), float(beta1), float(beta2), float(eps), int(decay_steps), float(decay_rate),
+                                    float(grad_scale), pset.opt_state.data_ptr(), self.st))
+        pset.repack(self.lib, self.ctx, self.st)

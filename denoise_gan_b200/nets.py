@@ -1,0 +1,143 @@
+"""Generator / discriminator / VGG19 graphs of the reference, expressed as calls into the tape
+engine (which calls the CUDA kernels).  Each class is a callable `net(x, training=bool) -> Var`
+like the Keras models it replaces.
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import Engine, Var
+from .params import ParamSet
+
+
+class _Net:
+    def __init__(self, engine: Engine, pset: ParamSet):
+        self.E, self.p = engine, pset
+
+    @property
+    def trainable_variables(self):
+        return list(self.p.params.values())
+
+    def _in(self, x):
+        return x if isinstance(x, Var) else self.E.input(x)
+
+
+class SRGANGenerator(_Net):
+    """srgan.py:129-185."""
+
+    def __init__(self, engine, pset, scale=4):
+        super().__init__(engine, pset)
+        self.scale = scale
+
+    def __call__(self, x, training=True) -> Var:
+        E, p = self.E, self.p
+        n = E.conv2d(self._in(x), p["g/conv_in/kernel"])
+        n = E.bn_act(n, p, "g/bn_in", training=training, prelu=p["g/prelu_in/alpha"])
+        temp = E.mark("g/prelu_in", n)
+        for i in range(16):
+            nn = E.conv2d(n, p[f"g/res{i}/conv1/kernel"])
+            nn = E.bn_act(nn, p, f"g/res{i}/bn1", training=training, act="relu")
+            nn = E.conv2d(nn, p[f"g/res{i}/conv2/kernel"])
+            n = E.mark(f"g/res{i}/add", E.bn_act(nn, p, f"g/res{i}/bn2", training=training, residual=n))
+        n2 = E.conv2d(n, p["g/conv_post/kernel"])
+        n = E.mark("g/post_add", E.bn_act(n2, p, "g/bn_post", training=training, residual=temp))
+        for j in range(self.scale // 2):
+            u = E.conv2d(n, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"])
+            n = E.mark(f"g/up{j}/prelu", E.d2s_prelu(u, p[f"g/up{j}/prelu/alpha"]))
+        # 1x1 conv + tanh, fp32 output ('generator_tanh', dtype float32, srgan.py:183)
+        return E.mark("g/tanh", E.conv2d(n, p["g/conv_out/kernel"], p["g/conv_out/bias"], act="tanh", out_dtype=torch.float32))
+
+
+class PatchDiscriminator(_Net):
+    """srgan.py:232-272 = fsrgan.py:222-258 (logits) = autoencoder.py:190-229 (sigmoid)."""
+    STRIDES = [1, 2, 1, 2, 1, 2, 1, 2]
+
+    def __init__(self, engine, pset, sigmoid=False, prefix="d"):
+        super().__init__(engine, pset)
+        self.sigmoid, self.prefix = sigmoid, prefix
+
+    def __call__(self, x, training=True) -> Var:
+        E, p, px = self.E, self.p, self.prefix
+        d = self._in(x)
+        for i, s in enumerate(self.STRIDES, start=1):
+            w, b = p[f"{px}/conv{i}/kernel"], p[f"{px}/conv{i}/bias"]
+            if i == 1:
+                d = E.conv2d(d, w, b, stride=s, act="lrelu", alpha=0.2)
+            else:
+                d = E.conv2d(d, w, b, stride=s)
+                d = E.bn_act(d, p, f"{px}/bn{i}", training=training, momentum=0.8, act="lrelu", alpha=0.2)
+            E.mark(f"{px}/lrelu{i}", d)
+        return E.conv2d(d, p[f"{px}/logits/kernel"], p[f"{px}/logits/bias"], act="sigmoid" if self.sigmoid else None,
+                        out_dtype=torch.float32)
+
+
+class AutoencoderGenerator(_Net):
+    """autoencoder.py:89-188."""
+
+    def __call__(self, x, training=True) -> Var:
+        E, p = self.E, self.p
+        x = self._in(x)
+        xin = E.cast(x, E.act_dtype)
+
+        def conv(t, name, act="relu", out_dtype=None):
+            return E.conv2d(t, p[f"g/{name}/kernel"], p[f"g/{name}/bias"], act=act, out_dtype=out_dtype)
+
+        def upcat(a, b):
+            return E.concat([E.upsample2x_relu(a), b])
+
+        c1b = conv(conv(x, "conv1"), "conv1b"); p1 = E.maxpool2x2(c1b)
+        p2 = E.maxpool2x2(conv(p1, "conv2"))
+        p3 = E.maxpool2x2(conv(p2, "conv3"))
+        p4 = E.maxpool2x2(conv(p3, "conv4"))
+        p5 = E.maxpool2x2(conv(p4, "conv5"))
+        t = conv(conv(upcat(p5, p4), "conv6"), "conv6b")
+        t = conv(conv(upcat(t, p3), "conv7"), "conv7b")
+        t = conv(conv(upcat(t, p2), "conv8"), "conv8b")
+        t = conv(conv(upcat(t, p1), "conv9"), "conv9b")
+        t = conv(conv(upcat(t, xin), "conv10"), "conv10b")
+        return conv(t, "conv11", act="tanh", out_dtype=torch.float32)
+
+
+class FastSRGANGenerator(_Net):
+    """fsrgan.py:99-220."""
+
+    def __init__(self, engine, pset, n_blocks=6):
+        super().__init__(engine, pset)
+        self.n_blocks = n_blocks
+
+    def __call__(self, x, training=True) -> Var:
+        E, p = self.E, self.p
+        c1 = E.conv2d(self._in(x), p["g/c1/kernel"], p["g/c1/bias"])
+        c1 = E.bn_act(c1, p, "g/c1_bn", training=training, prelu=p["g/c1_prelu/alpha"])
+        r = c1
+        for i in range(self.n_blocks):
+            t = r
+            if i:
+                t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"])
+                t = E.bn_act(t, p, f"g/b{i}/expand_bn", training=training, momentum=0.999, act="relu")
+            t = E.dwconv3x3(t, p[f"g/b{i}/dw/kernel"], p[f"g/b{i}/dw/bias"])
+            t = E.bn_act(t, p, f"g/b{i}/dw_bn", training=training, momentum=0.999, act="relu")
+            t = E.conv2d(t, p[f"g/b{i}/project/kernel"], p[f"g/b{i}/project/bias"])
+            r = E.bn_act(t, p, f"g/b{i}/project_bn", training=training, momentum=0.999, residual=r)
+        c2 = E.conv2d(r, p["g/c2/kernel"], p["g/c2/bias"])
+        u = E.bn_act(c2, p, "g/c2_bn", training=training, residual=c1)
+        for j in range(2):
+            u = E.d2s_prelu(E.conv2d(u, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"]), p[f"g/up{j}/prelu/alpha"])
+        return E.conv2d(u, p["g/conv_out/kernel"], p["g/conv_out/bias"], act="tanh", out_dtype=torch.float32)
+
+
+class VGG19Features(_Net):
+    """keras.applications.VGG19 trunk to block5_conv4 on 'caffe'-preprocessed input (srgan.py:69-93)."""
+    CFG = [(1, 2), (2, 2), (3, 4), (4, 4), (5, 4)]
+
+    def __call__(self, x, training=False) -> Var:
+        E, p = self.E, self.p
+        t = self._in(x)
+        for blk, n in self.CFG:
+            for c in range(1, n + 1):
+                last = blk == 5 and c == n
+                t = E.conv2d(t, p[f"vgg/block{blk}_conv{c}/kernel"], p[f"vgg/block{blk}_conv{c}/bias"], act="relu",
+                             out_dtype=torch.float32 if last else None)
+            if blk < 5:
+                t = E.maxpool2x2(t)
+        return t

@@ -1,0 +1,51 @@
+"""The G+D update shared by the SRGAN / Fast-SRGAN / autoencoder train steps.
+
+Restates train_srgan.py:61-118: one forward of G, D(real), D(fake) [and VGG19 on both images when the
+content loss is enabled], the loss terms, then the two `tape.gradient` calls (discriminator variables
+from disc_loss, generator variables from gen_loss through D(fake) and VGG) computed from the SAME
+forward, an optional data-parallel gradient all-reduce, and both Adam updates.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: float, w_mae=1.0, w_mse=0.0, w_tv=0.0):
+    E = model.engine
+    E.new_step()
+    x = E.input(img_input)
+    y = E.input(img_target)
+    gen_output = model.generator(x, training=True)                     # train_srgan.py:75
+    disc_real = model.discriminator(y, training=True)                  # :78
+    disc_fake = model.discriminator(gen_output, training=True)         # :79
+
+    seeds_g = []
+    if model.use_vgg:
+        content, dgf, gf = model.content_loss(y, gen_output)          # :86
+        seeds_g.append((gf, dgf))
+        content = content[0]
+    else:
+        content = torch.zeros((), dtype=torch.float32, device=E.device)
+    adv_raw, g_adv = E.bce(disc_fake, 1.0, from_logits, 1e-3, key="adv")          # :87
+    out3, dgen = E.image_losses(gen_output, y.t, w_mae, w_mse, w_tv)              # :88-90
+    real_loss, g_real = E.bce(disc_real, 1.0, from_logits, disc_scale, key="dreal")   # :94
+    fake_loss, g_fake = E.bce(disc_fake, 0.0, from_logits, disc_scale, key="dfake")   # :95
+    seeds_g += [(disc_fake, g_adv), (gen_output, dgen)]
+
+    E.backward([(disc_real, g_real), (disc_fake, g_fake)], "d")        # :112
+    E.backward(seeds_g, "g")                                            # :111
+
+    scale = 1.0
+    if model.comm is not None:
+        model.comm.allreduce_grads(model)
+        scale = 1.0 / model.world_size
+    model.gen_optimizer.apply(E, model.gen_params, scale)               # :115
+    model.disc_optimizer.apply(E, model.disc_params, scale)             # :116
+    model.iterations += 1
+
+    adv = 1e-3 * adv_raw[0]
+    mae, mse, var = out3[0], out3[1], 1e-5 * out3[2]
+    gen_loss = content + adv + mae * w_mae + mse * w_mse + var * (w_tv / 1e-5 if w_tv else 0.0)
+    disc_loss = disc_scale * (real_loss[0] + fake_loss[0])
+    return dict(gen_loss=gen_loss, adv_loss=adv, mae_loss=mae, mse_loss=mse, content_loss=content, disc_loss=disc_loss,
+                var_loss=var, gen_output=gen_output, disc_real=disc_real, disc_fake=disc_fake)

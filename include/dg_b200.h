@@ -1,0 +1,163 @@
+/*
+ * dg_b200 — C ABI of the B200-native convolutional hot path of pmcbride/denoise-gan.
+ *
+ * The reference has no FFI: its lower seam is "Keras layer call -> TensorFlow op" (SURVEY.md §8b).
+ * Every entry point below replaces one of those op call sites; the citation after each prototype is
+ * the reference file:line whose arithmetic it reproduces.  Conventions:
+ *   - plain C, no exceptions; return 0 on success, non-zero on error with text in dg_last_error();
+ *     invalid shapes/alignments are errors, never a fallback path;
+ *   - all tensors are caller-allocated DEVICE memory, NHWC; the library allocates nothing per call
+ *     (workspaces are passed in, sized by the *_workspace_bytes helpers);
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*), no hidden syncs,
+ *     so whole train steps can be captured into CUDA graphs;
+ *   - Keras kernel layouts: Conv2D [kh,kw,Cin,Cout] fp32; Conv2DTranspose [kh,kw,Cout,Cin];
+ *     DepthwiseConv2D [kh,kw,C,1].
+ */
+#ifndef DG_B200_H
+#define DG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dg_ctx dg_ctx;
+
+enum { DG_F32 = 0, DG_BF16 = 1 };
+enum { DG_ACT_NONE = 0, DG_ACT_RELU = 1, DG_ACT_LRELU = 2, DG_ACT_TANH = 3, DG_ACT_SIGMOID = 4, DG_ACT_PRELU = 5 };
+
+/* NHWC tensor view: logical channels `c` stored at channel offset `coff` inside pixels of
+ * `cpitch` elements (cpitch == c, coff == 0 for a dense tensor; a U-Net concat slice otherwise). */
+typedef struct {
+  void* ptr;
+  int32_t dtype;
+  int32_t n, h, w, c;
+  int32_t cpitch, coff;
+} dg_tensor;
+
+/* Forward-convolution geometry.  pad_t / pad_l are the zero rows/cols BEFORE the image (TF 'SAME':
+ * total//2, host computes; pix2pix ZeroPadding2D+VALID: 1). */
+typedef struct {
+  int32_t kh, kw, stride, pad_t, pad_l;
+  int32_t act;      /* epilogue activation applied after bias */
+  float act_alpha;  /* LeakyReLU slope */
+} dg_conv_params;
+
+int dg_init(int device, dg_ctx** out);
+void dg_destroy(dg_ctx* ctx);
+const char* dg_last_error(void);
+int dg_version(void);
+/* 1 if the library was built with tcgen05 kernels and `device` is sm_100. */
+int dg_has_umma(dg_ctx* ctx);
+
+/* ---- convolution, CUDA-core implicit GEMM (fp32 accumulate; any channel count; fp32 or bf16 I/O).
+ * Used for the fp32 parity tier and for the <16-channel first/last layers. */
+/* y = act(conv(x, w) + bias).  keras Conv2D: srgan.py:154,246; autoencoder.py:95; pix2pix.py:115,207 */
+int dg_conv2d_fwd(dg_ctx*, const dg_tensor* x, const float* w_hwio, const float* bias, const dg_tensor* y,
+                  const dg_conv_params* p, void* stream);
+/* dx = input-gradient of the forward conv described by p (autodiff of the call sites above,
+ * train_srgan.py:111-112); also Conv2DTranspose forward with w = [kh,kw,Cout,Cin] (pix2pix.py:130,169):
+ * then `dy` is the transposed conv's input, `dx` its output, bias/act apply to the output. */
+int dg_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const float* w_hwio, const float* bias, const dg_tensor* dx,
+                    const dg_conv_params* p, void* stream);
+/* dw[kh,kw,Cin,Cout] (+)= sum x * dy ; dbias[Cout] (+)= sum dy (dbias may be NULL).  workspace:
+ * dg_conv2d_wgrad_workspace_bytes().  accumulate != 0 adds into dw/dbias. */
+size_t dg_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
+int dg_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw_hwio, float* dbias,
+                    const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- convolution on tcgen05 tensor cores (bf16 in, fp32 TMEM accumulate, bf16/fp32 out).
+ * Requires Cin % 16 == 0 and Cout % 16 == 0.  Weights are pre-packed by dg_umma_pack_weights. */
+/* packed size in bytes for a conv with the given geometry; mode 0 = forward, 1 = dgrad */
+size_t dg_umma_packed_bytes(int kh, int kw, int cin, int cout, int mode);
+int dg_umma_pack_weights(dg_ctx*, const float* w_hwio, void* packed, int kh, int kw, int cin, int cout,
+                         int mode, void* stream);
+int dg_umma_conv2d_fwd(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias,
+                       const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream);
+int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,
+                         const dg_tensor* dx, const dg_conv_params* p, void* stream);
+size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
+int dg_umma_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw_hwio, float* dbias,
+                         const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- depthwise 3x3 s1 SAME (fsrgan.py:149-154) */
+int dg_dwconv3x3_fwd(dg_ctx*, const dg_tensor* x, const float* w, const float* bias, const dg_tensor* y, void* stream);
+int dg_dwconv3x3_dgrad(dg_ctx*, const dg_tensor* dy, const float* w, const dg_tensor* dx, void* stream);
+size_t dg_dwconv3x3_wgrad_workspace_bytes(const dg_tensor* x);
+int dg_dwconv3x3_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- BatchNormalization (srgan.py:155,248; fsrgan.py:140-172; pix2pix.py:119,135,211) */
+size_t dg_bn_workspace_bytes(const dg_tensor* x);
+/* batch statistics -> per-channel scale/shift (y = x*scale+shift), saved mean / invstd, moving-stat update */
+int dg_bn_stats(dg_ctx*, const dg_tensor* x, const float* gamma, const float* beta, float eps, float momentum,
+                float* moving_mean, float* moving_var, float* scale, float* shift, float* save_mean,
+                float* save_invstd, void* workspace, size_t workspace_bytes, void* stream);
+/* inference: scale/shift from the moving statistics */
+int dg_bn_infer_affine(dg_ctx*, int c, const float* gamma, const float* beta, const float* moving_mean,
+                       const float* moving_var, float eps, float* scale, float* shift, void* stream);
+/* y = act(drop(x*scale+shift)) + residual ; drop: keep-mask from (seed, offset), kept units x2 (pix2pix.py:138) */
+int dg_bn_act_fwd(dg_ctx*, const dg_tensor* x, const float* scale, const float* shift, int act, float act_alpha,
+                  const float* prelu_alpha, const dg_tensor* residual, int dropout, uint32_t seed, uint32_t offset,
+                  const dg_tensor* y, void* stream);
+/* backward of the above: dx, dgamma, dbeta (and dprelu_alpha when act == PRELU) */
+int dg_bn_act_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const float* scale, const float* shift,
+                  const float* gamma, const float* save_mean, const float* save_invstd, int act, float act_alpha,
+                  const float* prelu_alpha, int dropout, uint32_t seed, uint32_t offset, const dg_tensor* dx,
+                  float* dgamma, float* dbeta, float* dprelu_alpha, int accumulate, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---- activations / structural ops */
+/* dpre = dy * act'(.) from the saved OUTPUT y (relu, lrelu, tanh, sigmoid) */
+int dg_act_bwd_from_output(dg_ctx*, const dg_tensor* dy, const dg_tensor* y, int act, float act_alpha,
+                           const dg_tensor* dpre, void* stream);
+/* tf.nn.depth_to_space(u, 2) followed by PReLU(shared_axes=[1,2]) (srgan.py:145-146, fsrgan.py:188-189);
+ * prelu_alpha == NULL: plain depth_to_space */
+int dg_d2s_prelu_fwd(dg_ctx*, const dg_tensor* u, const float* prelu_alpha, const dg_tensor* y, void* stream);
+int dg_d2s_prelu_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* u, const float* prelu_alpha, const dg_tensor* du,
+                     float* dprelu_alpha, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* out = a + b */
+int dg_add(dg_ctx*, const dg_tensor* a, const dg_tensor* b, const dg_tensor* out, void* stream);
+/* out (+)= src, with dtype conversion and view (concat-slice) support; accumulate != 0 adds */
+int dg_copy(dg_ctx*, const dg_tensor* src, const dg_tensor* out, int accumulate, void* stream);
+/* MaxPool2D(2,2) (autoencoder.py:110) and its gradient (first max in window order gets the gradient) */
+int dg_maxpool2x2_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
+int dg_maxpool2x2_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y, const dg_tensor* dx, void* stream);
+/* UpSampling2D(2,'nearest') + relu into a concat slice (autoencoder.py:113-136) and its gradient */
+int dg_upsample2x_relu_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
+int dg_upsample2x_relu_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* dx, void* stream);
+
+/* vgg19.preprocess_input(((x+1)*255)/2), 'caffe' mode: RGB->BGR, subtract (103.939,116.779,123.68) (srgan.py:71-72) */
+int dg_vgg_preprocess_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
+int dg_vgg_preprocess_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, void* stream);
+
+/* ---- losses: value sums and upstream gradients in one pass */
+size_t dg_loss_workspace_bytes(const dg_tensor* t);
+/* out3 = {mean|t-g|, mean(t-g)^2, mean_b TV(t-g)};  dgen (+)= w_mae*dMAE + w_mse*dMSE + w_tv*dTV
+ * (train_srgan.py:88-90, pix2pix.py:78-84); dgen may be NULL */
+int dg_image_losses(dg_ctx*, const dg_tensor* gen, const dg_tensor* target, float w_mae, float w_mse, float w_tv,
+                    float* out3, const dg_tensor* dgen, int accumulate, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* BinaryCrossentropy against a constant target. from_logits=1: train_srgan.py:71; 0: clipped-probability
+ * form, train_autoencoder.py:79.  loss_out = mean BCE ; dx = grad_scale * dBCE/dx (dx may be NULL) */
+int dg_bce_const_target(dg_ctx*, const dg_tensor* x, float target, int from_logits, float grad_scale,
+                        float* loss_out, const dg_tensor* dx, void* workspace, size_t workspace_bytes, void* stream);
+/* feature MSE for the VGG content loss (srgan.py:73-75): mean((a-b)^2 / 12.75^2), da = grad wrt a */
+int dg_feature_mse(dg_ctx*, const dg_tensor* a, const dg_tensor* b, float inv_div, float* loss_out,
+                   const dg_tensor* da, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused Keras Adam over a flat parameter arena (srgan.py:35-50, pix2pix.py:30-31) */
+/* state: int64 iterations at state[0]; advances it and updates theta/m/v for `numel` elements.
+ * grad_scale multiplies the gradient first (1/world_size after an all-reduce sum). */
+int dg_adam_step(dg_ctx*, float* theta, const float* grad, float* m, float* v, int64_t numel, float lr0,
+                 float beta1, float beta2, float eps, int64_t decay_steps, float decay_rate, float grad_scale,
+                 int64_t* iterations_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DG_B200_H */

@@ -1,0 +1,424 @@
+"""GPU parity tests, kernel by kernel, THROUGH THE C ABI (ctypes -> libdg_b200.so), against the
+CPU oracle (oracle/ops_torch.py in float64 + autograd) on identical seeded inputs.
+
+Tolerances (north star): fp32 path 1e-5 relative to the tensor's max magnitude; bf16 tensor-core
+path 2e-2 (inputs are pre-rounded to bf16 so only accumulation order and output rounding differ)."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ops_np as ON  # noqa: E402
+from oracle import ops_torch as OT  # noqa: E402
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def L():
+    from denoise_gan_b200 import _lib
+    _lib.load()
+    _lib.ctx(0)
+    return _lib
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def dev(t, dtype=torch.float32):
+    return t.to(dtype).cuda().contiguous()
+
+
+def ws(nbytes):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device="cuda")
+
+
+def conv_params(L, kh, kw, stride, H, W, padding, act=0, alpha=0.0):
+    if padding == "same":
+        pt, pl = ON.same_pads(H, kh, stride)[0], ON.same_pads(W, kw, stride)[0]
+    elif padding == "valid":
+        pt = pl = 0
+    else:
+        pt, pl = padding[0][0], padding[1][0]
+    return L.DgConvParams(kh, kw, stride, pt, pl, act, alpha)
+
+
+CONV_CASES = [  # (k, stride, padding, cin, cout, N, H, W)
+    (3, 1, "same", 3, 32, 2, 12, 10),
+    (3, 1, "same", 67, 44, 1, 9, 11),
+    (3, 2, "same", 32, 32, 2, 12, 10),
+    (4, 2, "same", 6, 64, 2, 8, 8),
+    (1, 1, "same", 64, 3, 2, 7, 9),
+    (4, 1, ((1, 1), (1, 1)), 16, 1, 1, 10, 10),
+    (3, 2, "same", 5, 7, 1, 7, 9),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_simt_conv_fwd_dgrad_wgrad_fp32(L, case):
+    k, s, padding, cin, cout, N, H, W = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = torch.randn(N, H, W, cin, generator=g, dtype=torch.float64)
+    w = torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * 0.2
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    y_ref = OT.conv2d(xr, wr, br, stride=s, padding=padding)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    (y_ref * gy).sum().backward()
+
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, s, H, W, padding)
+    xd, wd, bd, gyd = dev(x), dev(w), dev(b), dev(gy)
+    y = torch.empty(y_ref.shape, device="cuda")
+    tx, ty = L.tensor(xd), L.tensor(y)
+    L.check(lib.dg_conv2d_fwd(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), st))
+    assert relerr(y, y_ref) < FP32_TOL
+    dx = torch.empty_like(xd)
+    tgy, tdx = L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_conv2d_dgrad(ctx, C.byref(tgy), wd.data_ptr(), None, C.byref(tdx), C.byref(cp), st))
+    assert relerr(dx, xr.grad) < FP32_TOL
+    dw = torch.empty_like(wd); db = torch.empty_like(bd)
+    nb = lib.dg_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tgy), C.byref(cp))
+    wk = ws(nb)
+    L.check(lib.dg_conv2d_wgrad(ctx, C.byref(tx), C.byref(tgy), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, st))
+    assert relerr(dw, wr.grad) < FP32_TOL
+    assert relerr(db, br.grad) < FP32_TOL
+    # accumulate flag
+    L.check(lib.dg_conv2d_wgrad(ctx, C.byref(tx), C.byref(tgy), dw.data_ptr(), db.data_ptr(), C.byref(cp), 1, wk.data_ptr(), nb, st))
+    assert relerr(dw, 2 * wr.grad) < FP32_TOL
+
+
+def test_simt_conv_epilogue_activations_and_views(L):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 6, 8, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, 8, 4, generator=g, dtype=torch.float64) * 0.3
+    b = torch.randn(4, generator=g, dtype=torch.float64)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    ref = OT.conv2d(x, w, b)
+    for act, f in [(1, torch.relu), (2, lambda t: OT.leaky_relu(t, 0.2)), (3, torch.tanh), (4, torch.sigmoid)]:
+        cp = conv_params(L, 3, 3, 1, 6, 6, "same", act, 0.2)
+        # write into channels [4, 8) of a 12-channel buffer (concat slice), read x from a slice too
+        xin = torch.zeros(2, 6, 6, 10, device="cuda"); xin[..., 2:] = dev(x)
+        out = torch.full((2, 6, 6, 12), 7.0, device="cuda")
+        tx, ty = L.tensor(xin, c=8, coff=2), L.tensor(out, c=4, coff=4)
+        L.check(lib.dg_conv2d_fwd(ctx, C.byref(tx), dev(w).data_ptr(), dev(b).data_ptr(), C.byref(ty), C.byref(cp), st))
+        assert relerr(out[..., 4:8], f(ref)) < FP32_TOL
+        assert (out[..., :4] == 7).all() and (out[..., 8:] == 7).all()
+
+
+@pytest.mark.parametrize("k,s,cin,cout", [(4, 2, 8, 6), (3, 2, 5, 4), (4, 2, 16, 3)])
+def test_simt_conv_transpose_forward(L, k, s, cin, cout):
+    g = torch.Generator().manual_seed(k * 10 + s)
+    x = torch.randn(2, 5, 4, cin, generator=g, dtype=torch.float64)
+    w = torch.randn(k, k, cout, cin, generator=g, dtype=torch.float64) * 0.3
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    ref = torch.tanh(OT.conv2d_transpose(x, w, b, stride=s))
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    Ho, Wo = 5 * s, 4 * s
+    cp = conv_params(L, k, k, s, Ho, Wo, "same", 3, 0.0)
+    y = torch.empty(2, Ho, Wo, cout, device="cuda")
+    tx, ty = L.tensor(dev(x)), L.tensor(y)
+    L.check(lib.dg_conv2d_dgrad(ctx, C.byref(tx), dev(w).data_ptr(), dev(b).data_ptr(), C.byref(ty), C.byref(cp), st))
+    assert relerr(y, ref) < FP32_TOL
+
+
+UMMA_CASES = [  # (k, stride, padding, cin, cout, N, H, W)
+    (3, 1, "same", 64, 64, 2, 24, 20),
+    (3, 1, "same", 64, 64, 1, 48, 32),
+    (3, 1, "same", 32, 32, 2, 24, 24),
+    (3, 1, "same", 32, 64, 1, 16, 8),
+    (3, 1, "same", 64, 256, 1, 32, 16),
+    (3, 1, "same", 256, 64, 1, 32, 16),
+    (3, 1, "same", 16, 48, 1, 20, 12),
+    (3, 1, "same", 192, 32, 1, 16, 16),
+    (1, 1, "same", 32, 192, 1, 16, 16),
+    (3, 2, "same", 32, 32, 2, 24, 24),
+    (3, 2, "same", 64, 64, 1, 48, 16),
+    (4, 2, "same", 64, 128, 1, 32, 32),
+    (4, 1, ((1, 1), (1, 1)), 64, 32, 1, 18, 18),
+    (3, 1, "same", 256, 256, 1, 40, 24),
+    (3, 1, "same", 128, 512, 1, 16, 16),
+]
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+@pytest.mark.parametrize("case", UMMA_CASES)
+def test_umma_conv_fwd_dgrad_bf16(L, case):
+    k, s, padding, cin, cout, N, H, W = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * (1.0 / (k * np.sqrt(cin))))
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    y_ref = OT.conv2d(xr, w, b, stride=s, padding=padding)
+    gy = _bf16_round(torch.randn(y_ref.shape, generator=g, dtype=torch.float64))
+    (y_ref * gy).sum().backward()
+
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    assert lib.dg_has_umma(ctx) == 1
+    cp = conv_params(L, k, k, s, H, W, padding)
+    xd, wd, bd, gyd = dev(x, torch.bfloat16), dev(w), dev(b), dev(gy, torch.bfloat16)
+    pk_f = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    pk_d = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk_f.data_ptr(), k, k, cin, cout, 0, st))
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk_d.data_ptr(), k, k, cin, cout, 1, st))
+    for out_dtype in (torch.bfloat16, torch.float32):
+        y = torch.full(y_ref.shape, float("nan"), device="cuda", dtype=out_dtype)
+        tx, ty = L.tensor(xd), L.tensor(y)
+        L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk_f.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), None, st))
+        torch.cuda.synchronize()
+        e = relerr(y, y_ref)
+        assert e < (BF16_TOL if out_dtype == torch.bfloat16 else 1e-4), f"fwd relerr {e}"
+    dx = torch.full(x.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+    tgy, tdx = L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tgy), pk_d.data_ptr(), None, C.byref(tdx), C.byref(cp), st))
+    torch.cuda.synchronize()
+    e = relerr(dx, xr.grad)
+    assert e < BF16_TOL, f"dgrad relerr {e}"
+
+
+def test_umma_conv_transpose_forward_bf16(L):
+    g = torch.Generator().manual_seed(3)
+    cin, cout, k, s = 128, 64, 4, 2
+    x = _bf16_round(torch.randn(2, 16, 8, cin, generator=g, dtype=torch.float64))
+    w = _bf16_round(torch.randn(k, k, cout, cin, generator=g, dtype=torch.float64) * 0.02)
+    ref = OT.conv2d_transpose(x, w, None, stride=s)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    # as the forward conv f the kernel is HWIO with I = cout, O = cin; Conv2DTranspose forward = dgrad of f
+    cp = conv_params(L, k, k, s, 32, 16, "same")
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, dev(w).data_ptr(), pk.data_ptr(), k, k, cout, cin, 1, st))
+    y = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+    tx, ty = L.tensor(dev(x, torch.bfloat16)), L.tensor(y)
+    L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), st))
+    torch.cuda.synchronize()
+    assert relerr(y, ref) < BF16_TOL
+
+
+def test_umma_rejects_bad_shapes(L):
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    x = torch.zeros(1, 8, 8, 3, device="cuda", dtype=torch.bfloat16)
+    y = torch.zeros(1, 8, 8, 16, device="cuda", dtype=torch.bfloat16)
+    cp = conv_params(L, 3, 3, 1, 8, 8, "same")
+    tx, ty = L.tensor(x), L.tensor(y)
+    rc = lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), y.data_ptr(), None, C.byref(ty), C.byref(cp), None, st)
+    assert rc != 0 and b"multiples of 16" in lib.dg_last_error()
+
+
+@pytest.mark.parametrize("C_,act,with_res,dropout", [(64, "relu", False, False), (100, "prelu", False, False),
+                                                     (32, "lrelu", False, False), (64, None, True, False),
+                                                     (512, "relu", False, True), (48, "tanh", False, False)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_act_fwd_bwd(L, C_, act, with_res, dropout, dtype):
+    g = torch.Generator().manual_seed(C_)
+    N, H, W = 2, 6, 5
+    rnd = (lambda t: t) if dtype == torch.float32 else _bf16_round
+    x = rnd(torch.randn(N, H, W, C_, generator=g, dtype=torch.float64) * 1.5 + 0.3)
+    gamma = torch.randn(C_, generator=g, dtype=torch.float64) * 0.2 + 1
+    beta = torch.randn(C_, generator=g, dtype=torch.float64) * 0.2
+    alpha = torch.randn(C_, generator=g, dtype=torch.float64) * 0.3
+    res = rnd(torch.randn(N, H, W, C_, generator=g, dtype=torch.float64)) if with_res else None
+    gy = rnd(torch.randn(N, H, W, C_, generator=g, dtype=torch.float64))
+    xr, gr, br, ar = [t.clone().requires_grad_(True) for t in (x, gamma, beta, alpha)]
+    p = {"bn/gamma": gr, "bn/beta": br, "bn/moving_mean": torch.zeros(C_, dtype=torch.float64), "bn/moving_variance": torch.ones(C_, dtype=torch.float64)}
+    stt = {}
+    t = OT.batch_norm(xr, p, "bn", True, stt, momentum=0.8, eps=1e-3)
+    seed, off = 7, 11
+    if dropout:
+        keep = torch.from_numpy(ON.dropout_keep_mask(seed, off, x.numel())).view(x.shape).double()
+        t = t * keep * 2.0
+    a_code = {None: 0, "relu": 1, "lrelu": 2, "tanh": 3, "prelu": 5}[act]
+    if act == "relu": t = torch.relu(t)
+    elif act == "lrelu": t = OT.leaky_relu(t, 0.2)
+    elif act == "tanh": t = torch.tanh(t)
+    elif act == "prelu": t = OT.prelu(t, ar)
+    if with_res: t = t + res
+    (t * gy).sum().backward()
+
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    xd, gyd = dev(x, dtype), dev(gy, dtype)
+    gd, bd, ad = dev(gamma), dev(beta), dev(alpha)
+    mm, mv = torch.zeros(C_, device="cuda"), torch.ones(C_, device="cuda")
+    scale, shift, mean, invstd = [torch.empty(C_, device="cuda") for _ in range(4)]
+    tx = L.tensor(xd)
+    nb = lib.dg_bn_workspace_bytes(C.byref(tx)); wk = ws(nb)
+    L.check(lib.dg_bn_stats(ctx, C.byref(tx), gd.data_ptr(), bd.data_ptr(), 1e-3, 0.8, mm.data_ptr(), mv.data_ptr(), scale.data_ptr(),
+                            shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), wk.data_ptr(), nb, st))
+    y = torch.empty_like(xd)
+    ty = L.tensor(y)
+    resd = dev(res, dtype) if with_res else None
+    tres = L.tensor(resd) if with_res else None
+    L.check(lib.dg_bn_act_fwd(ctx, C.byref(tx), scale.data_ptr(), shift.data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None,
+                              C.byref(tres) if with_res else None, 1 if dropout else 0, seed, off, C.byref(ty), st))
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert relerr(y, t) < tol
+    assert relerr(mm, stt["bn/moving_mean"]) < 1e-5 and relerr(mv, stt["bn/moving_variance"]) < 1e-5
+    dx = torch.empty_like(xd); dgam, dbet, dalp = [torch.empty(C_, device="cuda") for _ in range(3)]
+    tgy, tdx = L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_bn_act_bwd(ctx, C.byref(tgy), C.byref(tx), scale.data_ptr(), shift.data_ptr(), gd.data_ptr(), mean.data_ptr(),
+                              invstd.data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None, 1 if dropout else 0, seed, off,
+                              C.byref(tdx), dgam.data_ptr(), dbet.data_ptr(), dalp.data_ptr(), 0, wk.data_ptr(), nb, st))
+    gtol = 2e-5 if dtype == torch.float32 else BF16_TOL
+    assert relerr(dx, xr.grad) < gtol
+    assert relerr(dgam, gr.grad) < gtol and relerr(dbet, br.grad) < gtol
+    if act == "prelu":
+        assert relerr(dalp, ar.grad) < gtol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_d2s_prelu_fwd_bwd(L, dtype):
+    g = torch.Generator().manual_seed(2)
+    rnd = (lambda t: t) if dtype == torch.float32 else _bf16_round
+    u = rnd(torch.randn(2, 5, 4, 32, generator=g, dtype=torch.float64))
+    alpha = torch.randn(8, generator=g, dtype=torch.float64) * 0.4
+    gy = rnd(torch.randn(2, 10, 8, 8, generator=g, dtype=torch.float64))
+    ur, ar = u.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    ref = OT.prelu(OT.depth_to_space(ur, 2), ar)
+    (ref * gy).sum().backward()
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    ud, gyd, ad = dev(u, dtype), dev(gy, dtype), dev(alpha)
+    y = torch.empty(2, 10, 8, 8, device="cuda", dtype=dtype)
+    tu, ty = L.tensor(ud), L.tensor(y)
+    L.check(lib.dg_d2s_prelu_fwd(ctx, C.byref(tu), ad.data_ptr(), C.byref(ty), st))
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert relerr(y, ref) < tol
+    du = torch.empty_like(ud); da = torch.empty(8, device="cuda")
+    tgy, tdu = L.tensor(gyd), L.tensor(du)
+    nb = lib.dg_bn_workspace_bytes(C.byref(tgy)); wk = ws(nb)
+    L.check(lib.dg_d2s_prelu_bwd(ctx, C.byref(tgy), C.byref(tu), ad.data_ptr(), C.byref(tdu), da.data_ptr(), 0, wk.data_ptr(), nb, st))
+    assert relerr(du, ur.grad) < tol and relerr(da, ar.grad) < (2e-5 if dtype == torch.float32 else BF16_TOL)
+
+
+def test_structural_ops(L):
+    g = torch.Generator().manual_seed(4)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    x = torch.randn(2, 6, 8, 5, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    # max pool
+    ref = OT.max_pool2x2(xr); gy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * gy).sum().backward()
+    xd, gyd = dev(x), dev(gy)
+    y = torch.empty(ref.shape, device="cuda"); dx = torch.empty_like(xd)
+    tx, ty, tg, tdx = L.tensor(xd), L.tensor(y), L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_maxpool2x2_fwd(ctx, C.byref(tx), C.byref(ty), st))
+    L.check(lib.dg_maxpool2x2_bwd(ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), st))
+    assert relerr(y, ref) == 0 and relerr(dx, xr.grad) < 1e-6
+    # upsample + relu into a concat slice
+    xr.grad = None
+    ref = torch.relu(OT.upsample2x_nearest(xr)); gy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * gy).sum().backward()
+    wide = torch.zeros(2, 12, 16, 9, device="cuda")
+    tw = L.tensor(wide, c=5, coff=0)
+    L.check(lib.dg_upsample2x_relu_fwd(ctx, C.byref(tx), C.byref(tw), st))
+    assert relerr(wide[..., :5], ref) == 0 and (wide[..., 5:] == 0).all()
+    gyd = dev(gy); tg = L.tensor(gyd)
+    L.check(lib.dg_upsample2x_relu_bwd(ctx, C.byref(tg), C.byref(tx), C.byref(tdx), st))
+    assert relerr(dx, xr.grad) < 1e-6
+    # add, copy with accumulate + dtype conversion
+    a, b = dev(torch.randn(2, 3, 3, 4, generator=g)), dev(torch.randn(2, 3, 3, 4, generator=g))
+    o = torch.empty_like(a)
+    ta, tb, to = L.tensor(a), L.tensor(b), L.tensor(o)
+    L.check(lib.dg_add(ctx, C.byref(ta), C.byref(tb), C.byref(to), st))
+    assert torch.equal(o, a + b)
+    ob = torch.ones(2, 3, 3, 4, device="cuda", dtype=torch.bfloat16)
+    tob = L.tensor(ob)
+    L.check(lib.dg_copy(ctx, C.byref(ta), C.byref(tob), 1, st))
+    assert relerr(ob, a + 1) < 1e-2
+    # vgg preprocess
+    img = dev(torch.rand(2, 4, 4, 3, generator=g) * 2 - 1)
+    pre = torch.empty_like(img); tp, ti = L.tensor(pre), L.tensor(img)
+    L.check(lib.dg_vgg_preprocess_fwd(ctx, C.byref(ti), C.byref(tp), st))
+    from oracle.models import vgg_preprocess
+    assert relerr(pre, vgg_preprocess(img.cpu().double())) < 1e-6
+
+
+@pytest.mark.parametrize("C_", [32, 192])
+def test_depthwise(L, C_):
+    g = torch.Generator().manual_seed(C_)
+    x = torch.randn(2, 7, 6, C_, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, C_, 1, generator=g, dtype=torch.float64); b = torch.randn(C_, generator=g, dtype=torch.float64)
+    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
+    ref = OT.depthwise_conv2d(xr, wr, br); gy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * gy).sum().backward()
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    xd, wd, bd, gyd = dev(x), dev(w), dev(b), dev(gy)
+    y = torch.empty_like(xd); dx = torch.empty_like(xd); dw = torch.empty_like(wd); db = torch.empty_like(bd)
+    tx, ty, tg, tdx = L.tensor(xd), L.tensor(y), L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_dwconv3x3_fwd(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), C.byref(ty), st))
+    L.check(lib.dg_dwconv3x3_dgrad(ctx, C.byref(tg), wd.data_ptr(), C.byref(tdx), st))
+    nb = lib.dg_dwconv3x3_wgrad_workspace_bytes(C.byref(tx)); wk = ws(nb)
+    L.check(lib.dg_dwconv3x3_wgrad(ctx, C.byref(tx), C.byref(tg), dw.data_ptr(), db.data_ptr(), 0, wk.data_ptr(), nb, st))
+    assert relerr(y, ref) < FP32_TOL and relerr(dx, xr.grad) < FP32_TOL
+    assert relerr(dw, wr.grad) < FP32_TOL and relerr(db, br.grad) < FP32_TOL
+
+
+def test_losses_and_grads(L):
+    g = torch.Generator().manual_seed(9)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    gen = (torch.rand(2, 6, 5, 3, generator=g, dtype=torch.float64) * 2 - 1)
+    tgt = (torch.rand(2, 6, 5, 3, generator=g, dtype=torch.float64) * 2 - 1).float().double()
+    gen = gen.float().double()
+    gr = gen.clone().requires_grad_(True)
+    w_mae, w_mse, w_tv = 1.0, 0.5, 1e-5
+    loss = w_mae * OT.mae(tgt, gr) + w_mse * OT.mse(tgt, gr) + w_tv * OT.total_variation_mean(tgt - gr)
+    loss.backward()
+    out3 = torch.empty(3, device="cuda"); dgen = torch.empty(2, 6, 5, 3, device="cuda")
+    tg, tt, td = L.tensor(dev(gen)), L.tensor(dev(tgt)), L.tensor(dgen)
+    nb = lib.dg_loss_workspace_bytes(C.byref(tg)); wk = ws(nb)
+    L.check(lib.dg_image_losses(ctx, C.byref(tg), C.byref(tt), w_mae, w_mse, w_tv, out3.data_ptr(), C.byref(td), 0, wk.data_ptr(), nb, st))
+    ref3 = torch.tensor([OT.mae(tgt, gen), OT.mse(tgt, gen), OT.total_variation_mean(tgt - gen)])
+    assert relerr(out3, ref3) < FP32_TOL
+    assert relerr(dgen, gr.grad) < FP32_TOL
+    # BCE, both forms
+    x = torch.randn(2, 3, 3, 1, generator=g, dtype=torch.float64) * 2
+    for from_logits in (1, 0):
+        for z in (0.0, 1.0):
+            xin = x if from_logits else torch.sigmoid(x)
+            xin = xin.float().double()
+            xr = xin.clone().requires_grad_(True)
+            l = OT.bce_from_logits(xr, z) if from_logits else OT.bce_from_probs(xr, z)
+            (l * 1e-3).backward()
+            lo = torch.empty(1, device="cuda"); dx = torch.empty(2, 3, 3, 1, device="cuda")
+            tx, tdx = L.tensor(dev(xin)), L.tensor(dx)
+            L.check(lib.dg_bce_const_target(ctx, C.byref(tx), z, from_logits, 1e-3, lo.data_ptr(), C.byref(tdx), wk.data_ptr(), nb, st))
+            assert relerr(lo, l.detach().view(1)) < 2e-5
+            assert relerr(dx, xr.grad) < 2e-5
+    # feature MSE
+    a = torch.randn(2, 3, 3, 16, generator=g, dtype=torch.float64).float().double(); b = torch.randn(2, 3, 3, 16, generator=g, dtype=torch.float64).float().double()
+    ar = a.clone().requires_grad_(True)
+    l = OT.mse(b / 12.75, ar / 12.75); l.backward()
+    lo = torch.empty(1, device="cuda"); da = torch.empty(2, 3, 3, 16, device="cuda")
+    ta, tb, tda = L.tensor(dev(a)), L.tensor(dev(b)), L.tensor(da)
+    L.check(lib.dg_feature_mse(ctx, C.byref(ta), C.byref(tb), 1.0 / 12.75, lo.data_ptr(), C.byref(tda), wk.data_ptr(), nb, st))
+    assert relerr(lo, l.detach().view(1)) < FP32_TOL and relerr(da, ar.grad) < FP32_TOL
+
+
+def test_adam_matches_keras_definition(L):
+    g = torch.Generator().manual_seed(1)
+    n = 1000 + 3
+    th = torch.randn(n, generator=g, dtype=torch.float64).float().double()
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    npad = 1024
+    theta = torch.zeros(npad, device="cuda"); theta[:n] = dev(th)
+    m = torch.zeros(npad, device="cuda"); v = torch.zeros(npad, device="cuda")
+    state = torch.zeros(2, dtype=torch.int64, device="cuda")
+    opt = OT.KerasAdam(1e-3, beta1=0.5, decay_steps=2, decay_rate=0.1)
+    p = {"w": th.clone()}
+    for step in range(4):
+        gr = torch.randn(n, generator=g, dtype=torch.float64).float().double()
+        gd = torch.zeros(npad, device="cuda"); gd[:n] = dev(gr) * 2.0   # grad_scale 0.5 undoes the x2
+        L.check(lib.dg_adam_step(ctx, theta.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), npad, 1e-3, 0.5, 0.999, 1e-7, 2, 0.1,
+                                 0.5, state.data_ptr(), st))
+        opt.apply(p, {"w": gr})
+        assert relerr(theta[:n], p["w"]) < 1e-6, f"step {step}"
+    assert state[0].item() == 4

@@ -1,0 +1,130 @@
+"""GPU: whole-model parity of the SRGAN train step (the north-star workload) against the oracle's
+restatement of train_srgan.py:61-118 on identical weights and synthetic inputs — per-layer
+activations, every generator / discriminator gradient, the 7 returned losses, the parameters
+after the update, and a short loss curve."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import models as OM  # noqa: E402
+from oracle import ops_torch as OT  # noqa: E402
+from oracle import steps as OS  # noqa: E402
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def make(fp16, vgg, crop=32, batch=2, seed=0):
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.srgan import SRGAN
+    args = SimpleNamespace(crop_size=crop, scale=4, lr=1e-3, fp16=fp16, vgg=vgg, seed=seed)
+    model = SRGAN(args)
+    g0 = P.init_srgan_generator(seed=seed, scale=4)
+    d0 = P.init_patch_discriminator(seed=seed + 1)
+    # give the zero-initialised parameters non-trivial values so every gradient path is exercised
+    gen = torch.Generator().manual_seed(99)
+    for p in (g0, d0):
+        for k in p:
+            if k.endswith(("bias", "beta", "alpha")):
+                p[k] = torch.randn(p[k].shape, generator=gen) * 0.1
+    model.gen_params.load(g0); model.disc_params.load(d0)
+    v0 = P.init_vgg19_synthetic() if vgg else None
+    x, y = synthetic_pair(batch, crop, 4, step=0)
+    return model, g0, d0, v0, x, y
+
+
+def oracle_step(g0, d0, v0, x, y, dtype=torch.float64, steps=1):
+    g = {k: v.to(dtype).clone() for k, v in g0.items()}
+    d = {k: v.to(dtype).clone() for k, v in d0.items()}
+    vgg = {k: v.to(dtype) for k, v in v0.items()} if v0 is not None else None
+    go = OT.KerasAdam(1e-3, decay_steps=100000); do = OT.KerasAdam(5e-3, decay_steps=100000)
+    outs = []
+    for s in range(steps):
+        acts, out = {}, {}
+        losses = OS.srgan_train_step(g, d, vgg, go, do, x[s].to(dtype), y[s].to(dtype), acts=acts, out=out)
+        outs.append((losses, acts, out))
+    return g, d, outs
+
+
+@pytest.mark.parametrize("vgg", [False, True])
+def test_srgan_step_fp32_layers_grads_losses(vgg):
+    from denoise_gan_b200.train_common import gan_step
+    model, g0, d0, v0, x, y = make(fp16=0, vgg=vgg)
+    rec = {}
+    model.engine.record = rec
+    r = gan_step(model, x.cuda(), y.cuda(), from_logits=True, disc_scale=1.0)
+    torch.cuda.synchronize()
+    g1, d1, outs = oracle_step(g0, d0, v0, [x], [y])
+    losses, acts, out = outs[0]
+    worst = 0.0
+    for name, ref in acts.items():
+        if name in rec:
+            e = relerr(rec[name].t, ref)
+            worst = max(worst, e)
+            assert e < 1e-5, f"activation {name}: {e}"
+    assert relerr(r["gen_output"].t, out["gen_output"]) < 1e-5
+    assert relerr(r["disc_real"].t, out["disc_real"]) < 1e-5
+    assert relerr(r["disc_fake"].t, out["disc_fake"]) < 1e-5
+    gg = model.gen_params.grads(); dg = model.disc_params.grads()
+    for name, ref in out["gen_grads"].items():
+        e = relerr(gg[name], ref)
+        assert e < 1e-4, f"gen grad {name}: {e}"
+    for name, ref in out["disc_grads"].items():
+        e = relerr(dg[name], ref)
+        assert e < 1e-4, f"disc grad {name}: {e}"
+    names = ["gen_loss", "adv_loss", "mae_loss", "mse_loss", "content_loss", "disc_loss", "var_loss"]
+    for n, ref in zip(names, losses):
+        assert abs(r[n].item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item())), f"{n}: {r[n].item()} vs {ref.item()}"
+    # parameters and BN moving statistics after the Adam step
+    ge, de = model.gen_params.export(), model.disc_params.export()
+    for k, ref in g1.items():
+        assert relerr(ge[k], ref) < 1e-4, f"param {k}"
+    for k, ref in d1.items():
+        assert relerr(de[k], ref) < 1e-4, f"param {k}"
+
+
+def test_srgan_step_bf16_tensor_core_path():
+    from denoise_gan_b200.train_common import gan_step
+    model, g0, d0, v0, x, y = make(fp16=1, vgg=False)
+    assert model.engine.use_umma
+    rec = {}
+    model.engine.record = rec
+    r = gan_step(model, x.cuda(), y.cuda(), from_logits=True, disc_scale=1.0)
+    torch.cuda.synchronize()
+    _, _, outs = oracle_step(g0, d0, v0, [x], [y])
+    losses, acts, out = outs[0]
+    for name, ref in acts.items():
+        if name in rec:
+            e = relerr(rec[name].t, ref)
+            assert e < 2e-2, f"activation {name}: {e}"
+    assert relerr(r["gen_output"].t, out["gen_output"]) < 2e-2
+    assert relerr(r["disc_fake"].t, out["disc_fake"]) < 5e-2
+    gg = model.gen_params.grads()
+    bad = [(n, relerr(gg[n], ref)) for n, ref in out["gen_grads"].items() if relerr(gg[n], ref) > 0.15]
+    assert not bad, bad[:5]
+    names = ["gen_loss", "adv_loss", "mae_loss", "mse_loss", "content_loss", "disc_loss", "var_loss"]
+    for n, ref in zip(names, losses):
+        assert abs(r[n].item() - ref.item()) <= 2e-2 * max(1.0, abs(ref.item())), f"{n}: {r[n].item()} vs {ref.item()}"
+
+
+def test_srgan_loss_curve_fp32_20_steps():
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.train_srgan import train_step
+    model, g0, d0, v0, _, _ = make(fp16=0, vgg=False, crop=32, batch=2)
+    steps = 20
+    xs, ys = zip(*[synthetic_pair(2, 32, 4, step=s) for s in range(steps)])
+    ours = []
+    for s in range(steps):
+        out = train_step(model, xs[s].cuda(), ys[s].cuda())
+        ours.append([v.item() for v in out])
+    _, _, outs = oracle_step(g0, d0, v0, xs, ys, steps=steps)
+    for s in range(steps):
+        ref = [v.item() for v in outs[s][0]]
+        for a, b in zip(ours[s], ref):
+            assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), f"step {s}: {ours[s]} vs {ref}"
