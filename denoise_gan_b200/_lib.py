@@ -113,7 +113,12 @@ def ctx(device: int | None = None):
     return _ctx[device]
 
 
+CALLS = 0  # number of C-ABI compute calls issued (each enqueues >= 1 kernel)
+
+
 def check(rc: int):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         raise DgError(_lib.dg_last_error().decode())
 

@@ -1,13 +1,449 @@
-// Tensor-core weight gradient (placeholder until the tcgen05 kernel lands): reports an error so
-// callers never silently take another path.
+// Tensor-core weight gradient for sm_100a:
+//      dW[t][c][o] (+)= sum_{n,h,w} S_t[n, h+dh_t, w+dw_t, c] * dy[n,h,w,o]        db[o] (+)= sum dy[n,h,w,o]
+// with the same sources/taps as the forward "multi-source halo conv" (conv_umma.cu).
+//
+// GEMM view: per tap D_t[M = Cin, N = Cout] = X_t^T dY with the PIXELS as the contraction.  Both
+// operands are pixel-major in NHWC, i.e. "MN-major" for tcgen05: the halo box of x and the dense
+// 16x8 tile of dy are TMA-loaded exactly as in the forward kernel and consumed in place through
+// MN-major shared-memory descriptors (a_major = b_major = 1) -- no transpose anywhere.  A tap is a
+// row-shifted window of the halo box (start address += shift * pixel_bytes).  UMMA wants M = 128:
+//   * Cin >= 128: the two 64-channel chunk boxes of a tap form one M=128 operand (LBO = box pitch);
+//   * Cin <= 64 : several TAPS are stacked along M instead; their windows differ by a constant
+//     number of pixels, which is simply the descriptor's leading-dimension byte offset (LBO).
+// Every CTA keeps all its [128 x Nblk] accumulators in TMEM (<= 512 columns) across ALL of its
+// pixel tiles and writes one fp32 partial at the end; a second kernel sums the partials in CTA
+// order (deterministic split-K).  The bias gradient is one more accumulator whose A operand is a
+// constant tile of ones.
+//
+// Reference: tape.gradient(..., trainable_variables) train_srgan.py:111-112 for every Conv2D /
+// Conv2DTranspose kernel and bias.
+#include <cuda.h>
+#include <string.h>
+
 #include "dg_common.cuh"
+#include "sm100.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int MAX_SRC = 4;
+constexpr int MAX_TAPS = 16;
+constexpr int MAX_GROUPS = 24;
+constexpr int MAX_ATOMS = 8;
+constexpr int MAX_STAGES = 6;
+constexpr int WG_THREADS = 192;
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+
+struct WgradParams {
+  CUtensorMap src[MAX_SRC];
+  CUtensorMap dymap;
+  int n_src, kc, kco, nb, n_groups, groups_per_cta, chunks, chunk0;
+  int tiles_h, tiles_w, n_img;
+  int src_h0[MAX_SRC], src_w0[MAX_SRC];
+  uint32_t src_off[MAX_SRC], chunk_bytes[MAX_SRC], a_sbo[MAX_SRC], a_kstep[MAX_SRC];
+  uint32_t g_off[MAX_GROUPS], g_lbo[MAX_GROUPS];
+  int g_src[MAX_GROUPS];
+  int g_dst[MAX_GROUPS][MAX_ATOMS];  // first dW row (t*Cin + c) of each atom, -1 = padding
+  uint32_t dy_off, dy_atom_bytes, stage_bytes, stage_tx, ones_off;
+  int n_stages, has_bias, cout_total;
+  float* part;
+  long part_stride, bias_off;
+  uint32_t a_layout, b_layout, idesc;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_done;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int nb0 = blockIdx.y * P.nb;
+  const int g_begin = blockIdx.z * P.groups_per_cta;
+  const int g_end = min(P.n_groups, g_begin + P.groups_per_cta);
+  const bool do_bias = P.has_bias && blockIdx.z == 0;
+  const int total_tiles = P.n_img * P.tiles_h * P.tiles_w;
+
+  if (tid == 0) {
+    for (int s = 0; s < P.n_stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_done), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (do_bias) {  // constant ones tile: 128 pixels x kc channels of bf16 1.0 (layout-invariant)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(base_ptr + P.ones_off);
+    for (int i = tid; i < 128 * P.kc / 2; i += WG_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
+      tma_prefetch_desc(&P.dymap);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tw = tile % P.tiles_w;
+        int t2 = tile / P.tiles_w;
+        int th = t2 % P.tiles_h;
+        int n = t2 / P.tiles_h;
+        const int h0 = th * 16, w0 = tw * 8;
+        const uint32_t full = smem_u32(&bar_full[stage]);
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        mbar_expect_tx(full, P.stage_tx);
+        const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
+        for (int s = 0; s < P.n_src; ++s)
+          for (int c = 0; c < P.chunks; ++c)
+            tma_load_4d(sa + P.src_off[s] + (uint32_t)c * P.chunk_bytes[s], &P.src[s], full, (P.chunk0 + c) * P.kc,
+                        w0 + P.src_w0[s], h0 + P.src_h0[s], n);
+        for (int a = 0; a < P.nb / P.kco; ++a)
+          tma_load_4d(sa + P.dy_off + (uint32_t)a * P.dy_atom_bytes, &P.dymap, full, nb0 + a * P.kco, w0, h0, n);
+        if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t b_sbo = 8u * (uint32_t)P.kco * 2u;      // between 8-pixel rows of the dense dy tile
+      const uint32_t b_kstep = 16u * (uint32_t)P.kco * 2u;   // 16 pixels per MMA
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t bd = make_smem_desc(sa + P.dy_off + j * b_kstep, P.dy_atom_bytes, b_sbo, P.b_layout);
+          for (int g = g_begin; g < g_end; ++g) {
+            const int s = P.g_src[g];
+            const uint64_t ad = make_smem_desc(sa + P.g_off[g] + j * P.a_kstep[s], P.g_lbo[g], P.a_sbo[s], P.a_layout);
+            umma_f16(tmem + (uint32_t)((g - g_begin) * P.nb), ad, bd, P.idesc, (first && j == 0) ? 0u : 1u);
+          }
+          if (do_bias) {
+            // ones tile: 8-pixel groups are 8*kc*2 bytes apart, channel atoms never repeat (M rows identical)
+            const uint64_t od = make_smem_desc(base + P.ones_off + j * 16u * P.kc * 2u, 0, 8u * P.kc * 2u, P.a_layout);
+            umma_f16(tmem + (uint32_t)((g_end - g_begin) * P.nb), od, bd, P.idesc, (first && j == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(&bar_done));
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(smem_u32(&bar_done), 0);
+    tc_fence_after();
+    float* part = P.part + (long)blockIdx.x * P.part_stride;
+    const int atom = m / P.kc, r = m - atom * P.kc;
+    for (int g = g_begin; g < g_end; ++g) {
+      const int dst = atom < MAX_ATOMS ? P.g_dst[g][atom] : -1;
+      for (int c0 = 0; c0 < P.nb; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_begin) * P.nb + c0), v);
+        tmem_ld_wait();
+        if (dst >= 0) {
+          float4* o = reinterpret_cast<float4*>(part + (long)(dst + r) * P.cout_total + nb0 + c0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            o[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                               __uint_as_float(v[4 * k + 3]));
+        }
+      }
+    }
+    if (do_bias) {
+      for (int c0 = 0; c0 < P.nb; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((g_end - g_begin) * P.nb + c0), v);
+        tmem_ld_wait();
+        if (m == 0) {
+          float* o = part + P.bias_off + nb0 + c0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(v[k]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// dst[i] (+)= sum_s part[s][i]  (fixed order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, long part_stride, int splits, float* __restrict__ dw,
+                                    long n_dw, float* __restrict__ dbias, int n_bias, long bias_off, int accumulate) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_dw) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long)z * part_stride + i];
+    dw[i] = accumulate ? dw[i] + s : s;
+  } else if (dbias && i < n_dw + n_bias) {
+    int o = (int)(i - n_dw);
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long)z * part_stride + bias_off + o];
+    dbias[o] = accumulate ? dbias[o] + s : s;
+  }
+}
+
+inline int kc_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+inline uint32_t layout_for(int kc) { return kc == 64 ? LAYOUT_SW128 : (kc == 32 ? LAYOUT_SW64 : LAYOUT_SW32); }
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int pymod(int a, int b) { return a - floordiv(a, b) * b; }
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode4(dg_ctx* ctx, CUtensorMap* m, void* ptr, const uint64_t* dims, const uint64_t* strides_b, const uint32_t* box,
+            int kc) {
+  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  uint32_t ones[4] = {1, 1, 1, 1};
+  CUresult r = ((EncodeFn)ctx->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, (const cuuint64_t*)dims,
+                                             (const cuuint64_t*)strides_b, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DG_FAIL("cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+struct Tap {
+  int src, dh, dw, widx;
+};
+struct Lat {
+  int step, h_first, w_first;
+};
+
+struct Plan {
+  Tap taps[MAX_TAPS];
+  Lat lat[MAX_SRC];
+  int n_taps, n_src;
+  int kc, kco, n_chunks, nb, gpc, zblocks, yblocks, splits, has_bias;
+};
+
+int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p, int has_bias,
+              Plan* pl) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(dy) && p, "%s: null argument", name);
+  DG_REQUIRE(x->dtype == DG_BF16 && dy->dtype == DG_BF16, "%s: tensor-core wgrad needs bf16 operands", name);
+  DG_REQUIRE(x->c % 16 == 0 && dy->c % 16 == 0, "%s: channels must be multiples of 16", name);
+  DG_REQUIRE(p->stride == 1 || p->stride == 2, "%s: stride must be 1 or 2", name);
+  DG_REQUIRE(p->kh * p->kw <= MAX_TAPS, "%s: kernel too large", name);
+  DG_REQUIRE(x->n == dy->n, "%s: batch mismatch", name);
+  pl->n_taps = 0; pl->n_src = 0;
+  if (p->stride == 1) {
+    pl->lat[0] = Lat{1, 0, 0};
+    pl->n_src = 1;
+    for (int r = 0; r < p->kh; ++r)
+      for (int s = 0; s < p->kw; ++s) pl->taps[pl->n_taps++] = Tap{0, r - p->pad_t, s - p->pad_l, r * p->kw + s};
+  } else {
+    DG_REQUIRE(x->h % 2 == 0 && x->w % 2 == 0, "%s: stride 2 needs even input size", name);
+    int src_of[2][2] = {{-1, -1}, {-1, -1}};
+    for (int r = 0; r < p->kh; ++r)
+      for (int s = 0; s < p->kw; ++s) {
+        int ph = pymod(r - p->pad_t, 2), pw = pymod(s - p->pad_l, 2);
+        if (src_of[ph][pw] < 0) { src_of[ph][pw] = pl->n_src; pl->lat[pl->n_src++] = Lat{2, ph, pw}; }
+        pl->taps[pl->n_taps++] = Tap{src_of[ph][pw], floordiv(r - p->pad_t - ph, 2), floordiv(s - p->pad_l - pw, 2), r * p->kw + s};
+      }
+  }
+  pl->kc = kc_for(x->c);
+  pl->kco = kc_for(dy->c);
+  pl->n_chunks = x->c / pl->kc;
+  pl->has_bias = has_bias;
+  // worst-case number of accumulator groups of one launch (all taps; chunk ranges of <= 128 channels)
+  const int atoms = 128 / pl->kc;
+  int n_groups = pl->n_taps;  // one group per tap when a launch spans several chunks
+  if (pl->n_chunks == 1) n_groups = (pl->n_taps + 1) / 2 + pl->n_src;  // upper bound for tap stacking
+  int cout = dy->c;
+  int best_nb = 0;
+  for (int nb = cout > 256 ? 256 : cout; nb >= 16; nb -= 16) {
+    if (cout % nb != 0 || nb % pl->kco != 0) continue;
+    int gpc = 512 / nb - (has_bias ? 1 : 0);
+    if (gpc >= n_groups) { best_nb = nb; break; }
+  }
+  if (!best_nb) {
+    for (int nb = cout > 64 ? 64 : cout; nb >= 16; nb -= 16)
+      if (cout % nb == 0 && nb % pl->kco == 0) { best_nb = nb; break; }
+  }
+  DG_REQUIRE(best_nb > 0, "%s: no N block for Cout=%d", name, cout);
+  pl->nb = best_nb;
+  pl->gpc = 512 / best_nb - (has_bias ? 1 : 0);
+  if (pl->gpc > MAX_GROUPS) pl->gpc = MAX_GROUPS;
+  pl->zblocks = (n_groups + pl->gpc - 1) / pl->gpc;
+  pl->yblocks = cout / best_nb;
+  const int tiles = dy->n * ((dy->h + 15) / 16) * ((dy->w + 7) / 8);
+  int splits = sm_count / (pl->zblocks * pl->yblocks);
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = tiles;
+  pl->splits = splits;
+  (void)atoms;
+  return 0;
+}
+
+}  // namespace
 
 extern "C" size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
-  return 0;
+  // one full fp32 dW (+ bias row) per pixel split; sized for devices of up to 160 SMs
+  Plan pl;
+  if (make_plan("dg_umma_conv2d_wgrad_workspace_bytes", 160, x, dy, p, 1, &pl)) return 0;
+  size_t per = (size_t)p->kh * p->kw * x->c * dy->c + dy->c;
+  return (size_t)pl.splits * per * sizeof(float);
 }
 
 extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias,
                                     const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
                                     void* stream) {
-  DG_FAIL("dg_umma_conv2d_wgrad: not built in this revision");
+  const char* name = "dg_umma_conv2d_wgrad";
+  Plan pl;
+  if (make_plan(name, ctx->sm_count < 160 ? ctx->sm_count : 160, x, dy, p, dbias != nullptr, &pl)) return 1;
+  DG_REQUIRE(dw && workspace, "%s: null output/workspace", name);
+  DG_REQUIRE(x->cpitch % 8 == 0 && x->coff % 8 == 0 && dy->cpitch % 8 == 0 && dy->coff % 8 == 0 &&
+                 ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)dy->ptr % 16) == 0, "%s: views not 16-byte aligned", name);
+  const int cin = x->c, cout = dy->c, kc = pl.kc, kco = pl.kco;
+  const long n_dw = (long)pl.n_taps * cin * cout;
+  const long part_stride = n_dw + cout;
+  DG_REQUIRE(workspace_bytes >= (size_t)pl.splits * part_stride * sizeof(float), "%s: workspace too small", name);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // halo extents per source
+  int dh_min[MAX_SRC], dh_max[MAX_SRC], dw_min[MAX_SRC], dw_max[MAX_SRC];
+  bool used[MAX_SRC] = {false, false, false, false};
+  for (int t = 0; t < pl.n_taps; ++t) {
+    const Tap& T = pl.taps[t];
+    int s = T.src;
+    if (!used[s]) { dh_min[s] = dh_max[s] = T.dh; dw_min[s] = dw_max[s] = T.dw; used[s] = true; }
+    dh_min[s] = T.dh < dh_min[s] ? T.dh : dh_min[s]; dh_max[s] = T.dh > dh_max[s] ? T.dh : dh_max[s];
+    dw_min[s] = T.dw < dw_min[s] ? T.dw : dw_min[s]; dw_max[s] = T.dw > dw_max[s] ? T.dw : dw_max[s];
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    if (e != cudaSuccess) DG_FAIL("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    attr_set = true;
+  }
+
+  const int atoms_full = 128 / kc;
+  const int chunks_per_launch = pl.n_chunks < atoms_full ? pl.n_chunks : atoms_full;
+  for (int chunk0 = 0; chunk0 < pl.n_chunks; chunk0 += chunks_per_launch) {
+    const int chunks = (pl.n_chunks - chunk0) < chunks_per_launch ? (pl.n_chunks - chunk0) : chunks_per_launch;
+    WgradParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_src = pl.n_src; P.kc = kc; P.kco = kco; P.nb = pl.nb; P.chunks = chunks; P.chunk0 = chunk0;
+    P.tiles_h = (dy->h + 15) / 16; P.tiles_w = (dy->w + 7) / 8; P.n_img = dy->n;
+    P.cout_total = cout; P.part = (float*)workspace; P.part_stride = part_stride; P.bias_off = n_dw;
+    P.has_bias = (dbias != nullptr && chunk0 == 0) ? 1 : 0;
+    P.a_layout = layout_for(kc); P.b_layout = layout_for(kco);
+    P.idesc = make_idesc_bf16(128, pl.nb, 1, 1);
+    uint32_t off = 0, tx = 0;
+    int WWs[MAX_SRC];
+    for (int s = 0; s < pl.n_src; ++s) {
+      const Lat& L = pl.lat[s];
+      const int HH = 16 + dh_max[s] - dh_min[s], WW = 8 + dw_max[s] - dw_min[s];
+      WWs[s] = WW;
+      const int vh = (x->h - L.h_first + L.step - 1) / L.step, vw = (x->w - L.w_first + L.step - 1) / L.step;
+      uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)vw, (uint64_t)vh, (uint64_t)x->n};
+      uint64_t strides[3] = {(uint64_t)x->cpitch * 2 * L.step, (uint64_t)x->cpitch * 2 * x->w * L.step,
+                             (uint64_t)x->cpitch * 2 * x->w * x->h};
+      uint32_t box[4] = {(uint32_t)kc, (uint32_t)WW, (uint32_t)HH, 1};
+      char* ptr = (char*)x->ptr + ((size_t)x->coff + ((size_t)L.h_first * x->w + L.w_first) * x->cpitch) * 2;
+      if (encode4(ctx, &P.src[s], ptr, dims, strides, box, kc)) return 1;
+      P.src_h0[s] = dh_min[s]; P.src_w0[s] = dw_min[s];
+      uint32_t hb = (uint32_t)HH * WW * kc * 2;
+      P.chunk_bytes[s] = (hb + 1023u) & ~1023u;
+      P.src_off[s] = off;
+      P.a_sbo[s] = (uint32_t)WW * kc * 2;
+      P.a_kstep[s] = 2u * WW * kc * 2;
+      off += P.chunk_bytes[s] * chunks;
+      tx += hb * chunks;
+    }
+    {  // dy tile: dense 16 x 8 pixels, nb/kco channel atoms
+      uint64_t dims[4] = {(uint64_t)dy->c, (uint64_t)dy->w, (uint64_t)dy->h, (uint64_t)dy->n};
+      uint64_t strides[3] = {(uint64_t)dy->cpitch * 2, (uint64_t)dy->cpitch * 2 * dy->w, (uint64_t)dy->cpitch * 2 * dy->w * dy->h};
+      uint32_t box[4] = {(uint32_t)kco, 8, 16, 1};
+      char* ptr = (char*)dy->ptr + (size_t)dy->coff * 2;
+      if (encode4(ctx, &P.dymap, ptr, dims, strides, box, kco)) return 1;
+      P.dy_off = off;
+      P.dy_atom_bytes = 128u * kco * 2;
+      off += P.dy_atom_bytes * (pl.nb / kco);
+      tx += P.dy_atom_bytes * (pl.nb / kco);
+    }
+    P.stage_bytes = (off + 1023u) & ~1023u;
+    P.stage_tx = tx;
+    // groups
+    int ng = 0;
+    if (pl.n_chunks > 1) {
+      for (int t = 0; t < pl.n_taps; ++t) {
+        const Tap& T = pl.taps[t];
+        int s = T.src;
+        DG_REQUIRE(ng < MAX_GROUPS, "%s: too many groups", name);
+        P.g_src[ng] = s;
+        P.g_off[ng] = P.src_off[s] + (uint32_t)((T.dh - dh_min[s]) * WWs[s] + (T.dw - dw_min[s])) * kc * 2;
+        P.g_lbo[ng] = P.chunk_bytes[s];
+        for (int a = 0; a < MAX_ATOMS; ++a) P.g_dst[ng][a] = a < chunks ? T.widx * cin + (chunk0 + a) * kc : -1;
+        ++ng;
+      }
+    } else {
+      // stack taps of the same source whose windows are uniformly spaced
+      bool done[MAX_TAPS] = {false};
+      for (int t = 0; t < pl.n_taps; ++t) {
+        if (done[t]) continue;
+        const Tap& T = pl.taps[t];
+        const int s = T.src;
+        auto row = [&](const Tap& U) { return (U.dh - dh_min[s]) * WWs[s] + (U.dw - dw_min[s]); };
+        DG_REQUIRE(ng < MAX_GROUPS, "%s: too many groups", name);
+        P.g_src[ng] = s;
+        P.g_off[ng] = P.src_off[s] + (uint32_t)row(T) * kc * 2;
+        for (int a = 0; a < MAX_ATOMS; ++a) P.g_dst[ng][a] = -1;
+        P.g_dst[ng][0] = T.widx * cin;
+        done[t] = true;
+        int delta = 0, count = 1, last = row(T);
+        for (int u = t + 1; u < pl.n_taps && count < atoms_full; ++u) {
+          if (done[u] || pl.taps[u].src != s) continue;
+          int d = row(pl.taps[u]) - last;
+          if (d <= 0) continue;
+          if (count == 1) delta = d;
+          if (d != delta) continue;
+          P.g_dst[ng][count++] = pl.taps[u].widx * cin;
+          done[u] = true;
+          last = row(pl.taps[u]);
+        }
+        P.g_lbo[ng] = (uint32_t)(delta > 0 ? delta : 1) * kc * 2;
+        ++ng;
+      }
+    }
+    P.n_groups = ng;
+    P.groups_per_cta = pl.gpc;
+    const int zblocks = (ng + pl.gpc - 1) / pl.gpc;
+    // shared memory: stages + ones tile + slack for padding atoms
+    const uint32_t ones_bytes = 128u * kc * 2;
+    uint32_t slack = 0;
+    for (int s = 0; s < pl.n_src; ++s) slack = P.chunk_bytes[s] > slack ? P.chunk_bytes[s] : slack;
+    const uint32_t budget = SMEM_LIMIT - 4096;
+    DG_REQUIRE(2 * P.stage_bytes + ones_bytes + slack <= budget, "%s: tile does not fit shared memory", name);
+    int n_stages = (int)((budget - ones_bytes - slack) / P.stage_bytes);
+    if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
+    P.n_stages = n_stages;
+    P.ones_off = (uint32_t)n_stages * P.stage_bytes;
+    const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;
+    dim3 grid(pl.splits, pl.yblocks, zblocks);
+    umma_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(P);
+    DG_CHECK_LAUNCH(name);
+  }
+  const long total = n_dw + (dbias ? cout : 0);
+  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, part_stride, pl.splits, dw, n_dw,
+                                                                      dbias, cout, n_dw, accumulate);
+  DG_CHECK_LAUNCH("dg_umma_conv2d_wgrad(reduce)");
+  return 0;
 }

@@ -58,9 +58,21 @@ class Engine:
         self._ws = None
         self.written: set = set()      # param names whose grad slice was written this step
         self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
-        self.use_umma_wgrad = False
+        self.use_umma_wgrad = self.use_umma
         self.launches = 0
         self.record = None             # dict name -> Var when a test wants per-layer activations
+        self.prof = None               # list of (kind, flops, ev0, ev1) when bench.py profiles a step
+
+    def _timed(self, kind: str, flops: float, call):
+        """Runs `call()`; when profiling, brackets it with CUDA events on the launching stream."""
+        if self.prof is None:
+            return call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = call()
+        e1.record()
+        self.prof.append((kind, flops, e0, e1))
+        return r
 
     def mark(self, name: str, v: "Var") -> "Var":
         if self.record is not None:
@@ -153,11 +165,14 @@ class Engine:
         umma = self._umma_ok(x.t, cin, cout, kh, kw, stride, H, W)
         tx, ty = tensor(x.t), tensor(y)
         bias = _lib.ptr(b.data) if b is not None else None
+        flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
         if umma:
-            check(self.lib.dg_umma_conv2d_fwd(self.ctx, C.byref(tx), self._packed(w, 0).data_ptr(), bias, C.byref(ty),
-                                              C.byref(cp), None, self.st))
+            pk = self._packed(w, 0)
+            self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+                self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), None, self.st)))
         else:
-            check(self.lib.dg_conv2d_fwd(self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st))
+            self._timed("simt_conv", flops, lambda: check(self.lib.dg_conv2d_fwd(
+                self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st)))
         out = Var(y, self._deps([x], w.group), seq)
         lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
 
@@ -169,21 +184,24 @@ class Engine:
                 check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
             tdp = tensor(dpre)
             if need_p:
-                self._wgrad(x.t, dpre, w, b, lin)
+                self._wgrad(x.t, dpre, w, b, lin, flops)
             dx = None
             if need_in[0]:
                 dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
                 tdx = tensor(dx)
                 if umma and dpre.dtype == torch.bfloat16:
-                    check(self.lib.dg_umma_conv2d_dgrad(self.ctx, C.byref(tdp), self._packed(w, 1).data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
+                    pk = self._packed(w, 1)
+                    self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
+                        self.ctx, C.byref(tdp), pk.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
                 else:
-                    check(self.lib.dg_conv2d_dgrad(self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
+                    self._timed("simt_conv", flops, lambda: check(self.lib.dg_conv2d_dgrad(
+                        self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
             return [dx]
 
         self._push([x], out, w.group, bwd)
         return out
 
-    def _wgrad(self, x: torch.Tensor, dy: torch.Tensor, w: Param, b: Param | None, lin: DgConvParams):
+    def _wgrad(self, x: torch.Tensor, dy: torch.Tensor, w: Param, b: Param | None, lin: DgConvParams, flops: float = 0.0):
         """dW (+ dbias) of the forward conv `lin` with input x and output-gradient dy, into the grad arena."""
         tx, tdy = tensor(x), tensor(dy)
         acc = self._acc_flag(w)
@@ -196,13 +214,13 @@ class Engine:
                 self._umma_ok(x, cin, cout, kh, kw, lin.stride, x.shape[1], x.shape[2])):
             nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))
             ws = self.workspace(nbytes)
-            check(self.lib.dg_umma_conv2d_wgrad(self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc,
-                                                ws.data_ptr(), nbytes, self.st))
+            self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
+                self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc, ws.data_ptr(), nbytes, self.st)))
         else:
             nbytes = self.lib.dg_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))
             ws = self.workspace(nbytes)
-            check(self.lib.dg_conv2d_wgrad(self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc,
-                                           ws.data_ptr(), nbytes, self.st))
+            self._timed("simt_wgrad", flops, lambda: check(self.lib.dg_conv2d_wgrad(
+                self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc, ws.data_ptr(), nbytes, self.st)))
 
     def conv2d_transpose(self, x: Var, w: Param, b: Param | None = None, *, stride=2, act=None, alpha=0.0,
                          out_dtype=None) -> Var:

@@ -33,11 +33,14 @@ def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: flo
     seeds_g += [(disc_fake, g_adv), (gen_output, dgen)]
 
     E.backward([(disc_real, g_real), (disc_fake, g_fake)], "d")        # :112
+    if model.comm is not None:
+        model.comm.start(model.disc_params.grad)    # overlaps the generator backward pass below
     E.backward(seeds_g, "g")                                            # :111
 
     scale = 1.0
     if model.comm is not None:
-        model.comm.allreduce_grads(model)
+        model.comm.start(model.gen_params.grad)
+        model.comm.wait()
         scale = 1.0 / model.world_size
     model.gen_optimizer.apply(E, model.gen_params, scale)               # :115
     model.disc_optimizer.apply(E, model.disc_params, scale)             # :116

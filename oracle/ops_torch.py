@@ -33,7 +33,7 @@ def conv2d(x, w, b=None, stride=1, padding="same"):
     else:
         (pt, pb), (pl, pr) = padding
     xn = F.pad(_nchw(x), (pl, pr, pt, pb))
-    y = F.conv2d(xn, w.permute(3, 2, 0, 1), b, stride=stride)
+    y = F.conv2d(xn, w.permute(3, 2, 0, 1).contiguous(), b, stride=stride)
     return _nhwc(y)
 
 
@@ -44,7 +44,7 @@ def conv2d_transpose(x, w, b=None, stride=2):
     ho, wo = h * stride, wd * stride
     pt, _ = same_pads(ho, kh, stride)
     pl, _ = same_pads(wo, kw, stride)
-    full = F.conv_transpose2d(_nchw(x), w.permute(3, 2, 0, 1), None, stride=stride)
+    full = F.conv_transpose2d(_nchw(x), w.permute(3, 2, 0, 1).contiguous(), None, stride=stride)
     y = full[:, :, pt:pt + ho, pl:pl + wo]
     if b is not None:
         y = y + b.view(1, -1, 1, 1)
@@ -57,7 +57,7 @@ def depthwise_conv2d(x, w, b=None):
     kh, kw = w.shape[0], w.shape[1]
     (pt, pb), (pl, pr) = same_pads(h, kh, 1), same_pads(wd, kw, 1)
     xn = F.pad(_nchw(x), (pl, pr, pt, pb))
-    y = F.conv2d(xn, w.permute(2, 3, 0, 1), b, groups=c)
+    y = F.conv2d(xn, w.permute(2, 3, 0, 1).contiguous(), b, groups=c)
     return _nhwc(y)
 
 

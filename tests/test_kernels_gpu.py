@@ -108,7 +108,8 @@ def test_simt_conv_epilogue_activations_and_views(L):
         xin = torch.zeros(2, 6, 6, 10, device="cuda"); xin[..., 2:] = dev(x)
         out = torch.full((2, 6, 6, 12), 7.0, device="cuda")
         tx, ty = L.tensor(xin, c=8, coff=2), L.tensor(out, c=4, coff=4)
-        L.check(lib.dg_conv2d_fwd(ctx, C.byref(tx), dev(w).data_ptr(), dev(b).data_ptr(), C.byref(ty), C.byref(cp), st))
+        wd, bd = dev(w), dev(b)
+        L.check(lib.dg_conv2d_fwd(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), st))
         assert relerr(out[..., 4:8], f(ref)) < FP32_TOL
         assert (out[..., :4] == 7).all() and (out[..., 8:] == 7).all()
 
@@ -124,8 +125,9 @@ def test_simt_conv_transpose_forward(L, k, s, cin, cout):
     Ho, Wo = 5 * s, 4 * s
     cp = conv_params(L, k, k, s, Ho, Wo, "same", 3, 0.0)
     y = torch.empty(2, Ho, Wo, cout, device="cuda")
-    tx, ty = L.tensor(dev(x)), L.tensor(y)
-    L.check(lib.dg_conv2d_dgrad(ctx, C.byref(tx), dev(w).data_ptr(), dev(b).data_ptr(), C.byref(ty), C.byref(cp), st))
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    tx, ty = L.tensor(xd), L.tensor(y)
+    L.check(lib.dg_conv2d_dgrad(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), st))
     assert relerr(y, ref) < FP32_TOL
 
 
@@ -197,9 +199,10 @@ def test_umma_conv_transpose_forward_bf16(L):
     # as the forward conv f the kernel is HWIO with I = cout, O = cin; Conv2DTranspose forward = dgrad of f
     cp = conv_params(L, k, k, s, 32, 16, "same")
     pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
-    L.check(lib.dg_umma_pack_weights(ctx, dev(w).data_ptr(), pk.data_ptr(), k, k, cout, cin, 1, st))
+    wd, xd = dev(w), dev(x, torch.bfloat16)
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cout, cin, 1, st))
     y = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
-    tx, ty = L.tensor(dev(x, torch.bfloat16)), L.tensor(y)
+    tx, ty = L.tensor(xd), L.tensor(y)
     L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), st))
     torch.cuda.synchronize()
     assert relerr(y, ref) < BF16_TOL
@@ -312,7 +315,7 @@ def test_structural_ops(L):
     tx, ty, tg, tdx = L.tensor(xd), L.tensor(y), L.tensor(gyd), L.tensor(dx)
     L.check(lib.dg_maxpool2x2_fwd(ctx, C.byref(tx), C.byref(ty), st))
     L.check(lib.dg_maxpool2x2_bwd(ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), st))
-    assert relerr(y, ref) == 0 and relerr(dx, xr.grad) < 1e-6
+    assert relerr(y, ref) < 1e-6 and relerr(dx, xr.grad) < 1e-6
     # upsample + relu into a concat slice
     xr.grad = None
     ref = torch.relu(OT.upsample2x_nearest(xr)); gy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
@@ -320,7 +323,7 @@ def test_structural_ops(L):
     wide = torch.zeros(2, 12, 16, 9, device="cuda")
     tw = L.tensor(wide, c=5, coff=0)
     L.check(lib.dg_upsample2x_relu_fwd(ctx, C.byref(tx), C.byref(tw), st))
-    assert relerr(wide[..., :5], ref) == 0 and (wide[..., 5:] == 0).all()
+    assert relerr(wide[..., :5], ref) < 1e-6 and (wide[..., 5:] == 0).all()
     gyd = dev(gy); tg = L.tensor(gyd)
     L.check(lib.dg_upsample2x_relu_bwd(ctx, C.byref(tg), C.byref(tx), C.byref(tdx), st))
     assert relerr(dx, xr.grad) < 1e-6
@@ -373,7 +376,8 @@ def test_losses_and_grads(L):
     loss = w_mae * OT.mae(tgt, gr) + w_mse * OT.mse(tgt, gr) + w_tv * OT.total_variation_mean(tgt - gr)
     loss.backward()
     out3 = torch.empty(3, device="cuda"); dgen = torch.empty(2, 6, 5, 3, device="cuda")
-    tg, tt, td = L.tensor(dev(gen)), L.tensor(dev(tgt)), L.tensor(dgen)
+    gend, tgtd = dev(gen), dev(tgt)
+    tg, tt, td = L.tensor(gend), L.tensor(tgtd), L.tensor(dgen)
     nb = lib.dg_loss_workspace_bytes(C.byref(tg)); wk = ws(nb)
     L.check(lib.dg_image_losses(ctx, C.byref(tg), C.byref(tt), w_mae, w_mse, w_tv, out3.data_ptr(), C.byref(td), 0, wk.data_ptr(), nb, st))
     ref3 = torch.tensor([OT.mae(tgt, gen), OT.mse(tgt, gen), OT.total_variation_mean(tgt - gen)])
@@ -389,7 +393,8 @@ def test_losses_and_grads(L):
             l = OT.bce_from_logits(xr, z) if from_logits else OT.bce_from_probs(xr, z)
             (l * 1e-3).backward()
             lo = torch.empty(1, device="cuda"); dx = torch.empty(2, 3, 3, 1, device="cuda")
-            tx, tdx = L.tensor(dev(xin)), L.tensor(dx)
+            xind = dev(xin)
+            tx, tdx = L.tensor(xind), L.tensor(dx)
             L.check(lib.dg_bce_const_target(ctx, C.byref(tx), z, from_logits, 1e-3, lo.data_ptr(), C.byref(tdx), wk.data_ptr(), nb, st))
             assert relerr(lo, l.detach().view(1)) < 2e-5
             assert relerr(dx, xr.grad) < 2e-5
@@ -398,7 +403,8 @@ def test_losses_and_grads(L):
     ar = a.clone().requires_grad_(True)
     l = OT.mse(b / 12.75, ar / 12.75); l.backward()
     lo = torch.empty(1, device="cuda"); da = torch.empty(2, 3, 3, 16, device="cuda")
-    ta, tb, tda = L.tensor(dev(a)), L.tensor(dev(b)), L.tensor(da)
+    a_d, b_d = dev(a), dev(b)
+    ta, tb, tda = L.tensor(a_d), L.tensor(b_d), L.tensor(da)
     L.check(lib.dg_feature_mse(ctx, C.byref(ta), C.byref(tb), 1.0 / 12.75, lo.data_ptr(), C.byref(tda), wk.data_ptr(), nb, st))
     assert relerr(lo, l.detach().view(1)) < FP32_TOL and relerr(da, ar.grad) < FP32_TOL
 
@@ -422,3 +428,52 @@ def test_adam_matches_keras_definition(L):
         opt.apply(p, {"w": gr})
         assert relerr(theta[:n], p["w"]) < 1e-6, f"step {step}"
     assert state[0].item() == 4
+
+
+WGRAD_CASES = [  # (k, stride, padding, cin, cout, N, H, W, bias)
+    (3, 1, "same", 64, 64, 2, 24, 20, False),
+    (3, 1, "same", 64, 64, 1, 48, 32, True),
+    (3, 1, "same", 32, 32, 2, 24, 24, True),
+    (3, 1, "same", 32, 64, 1, 16, 8, True),
+    (3, 1, "same", 64, 256, 1, 32, 16, True),
+    (3, 1, "same", 256, 64, 1, 32, 16, False),
+    (3, 1, "same", 16, 48, 1, 20, 12, True),
+    (3, 1, "same", 192, 32, 1, 16, 16, True),
+    (1, 1, "same", 32, 192, 1, 16, 16, True),
+    (3, 2, "same", 32, 32, 2, 24, 24, True),
+    (3, 2, "same", 64, 64, 1, 48, 16, True),
+    (4, 2, "same", 64, 128, 1, 32, 32, False),
+    (4, 1, ((1, 1), (1, 1)), 64, 32, 1, 18, 18, False),
+    (3, 1, "same", 128, 128, 2, 40, 24, True),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_umma_conv_wgrad_bf16(L, case):
+    k, s, padding, cin, cout, N, H, W, bias = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64).requires_grad_(True)
+    b = torch.randn(cout, generator=g, dtype=torch.float64).requires_grad_(True)
+    y_ref = OT.conv2d(x, w, b, stride=s, padding=padding)
+    gy = _bf16_round(torch.randn(y_ref.shape, generator=g, dtype=torch.float64))
+    (y_ref * gy).sum().backward()
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, s, H, W, padding)
+    xd, gyd = dev(x, torch.bfloat16), dev(gy, torch.bfloat16)
+    tx, tg = L.tensor(xd), L.tensor(gyd)
+    nb = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tg), C.byref(cp))
+    assert nb > 0
+    wk = ws(nb)
+    dw = torch.full(w.shape, float("nan"), device="cuda"); db = torch.full((cout,), float("nan"), device="cuda")
+    L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(tg), dw.data_ptr(), db.data_ptr() if bias else None, C.byref(cp), 0,
+                                     wk.data_ptr(), nb, st))
+    torch.cuda.synchronize()
+    e = relerr(dw, w.grad)
+    assert e < 1e-4, f"dW relerr {e}"        # bf16 inputs are exact here; only fp32 accumulation order differs
+    if bias:
+        assert relerr(db, b.grad) < 1e-4
+    L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(tg), dw.data_ptr(), db.data_ptr() if bias else None, C.byref(cp), 1,
+                                     wk.data_ptr(), nb, st))
+    torch.cuda.synchronize()
+    assert relerr(dw, 2 * w.grad) < 1e-4
