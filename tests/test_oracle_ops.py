@@ -7,7 +7,6 @@ import torch
 from oracle import ops_np as N
 from oracle import ops_torch as T
 
-torch.set_default_dtype(torch.float64)
 rng = np.random.default_rng(0)
 
 
@@ -45,7 +44,8 @@ def test_conv2d_transpose(k, s):
 
 def test_conv2d_transpose_is_conv_input_gradient():
     # definition check: <conv(y, W), x> == <y, convT(x, W)> for the SAME stride-2 conv
-    y = torch.randn(1, 8, 8, 6, requires_grad=True); w = torch.randn(4, 4, 6, 5); x = torch.randn(1, 4, 4, 5)
+    y = torch.randn(1, 8, 8, 6, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(4, 4, 6, 5, dtype=torch.float64); x = torch.randn(1, 4, 4, 5, dtype=torch.float64)
     (T.conv2d(y, w, None, stride=2) * x).sum().backward()
     np.testing.assert_allclose(y.grad.numpy(), T.conv2d_transpose(x, w, None, stride=2).numpy(), atol=1e-10)
 
@@ -67,7 +67,8 @@ def test_depth_to_space_dcr_order():
 
 def test_batch_norm_train_and_moving():
     x = rng.standard_normal((3, 4, 5, 6)) * 2 + 1; g = rng.standard_normal(6); b = rng.standard_normal(6)
-    p = {"bn/gamma": t(g), "bn/beta": t(b), "bn/moving_mean": torch.zeros(6), "bn/moving_variance": torch.ones(6)}
+    p = {"bn/gamma": t(g), "bn/beta": t(b), "bn/moving_mean": torch.zeros(6, dtype=torch.float64),
+         "bn/moving_variance": torch.ones(6, dtype=torch.float64)}
     st = {}
     y = T.batch_norm(t(x), p, "bn", True, st, momentum=0.8, eps=1e-3).numpy()
     yn, mean, var = N.batch_norm_train(x, g, b, 1e-3)
