@@ -9,6 +9,7 @@
 // Reference call sites: keras Conv2D srgan.py:154,246, autoencoder.py:95, pix2pix.py:115,207;
 // Conv2DTranspose pix2pix.py:130,169; gradients via tape.gradient train_srgan.py:111-112.
 #include "dg_common.cuh"
+#include "conv_thin.cuh"
 
 namespace {
 
@@ -276,6 +277,16 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
   dst[i] = accumulate ? dst[i] + s : s;
 }
 
+// dst[i] (+)= sum_z part[z*stride + offset + i]
+__global__ void reduce_strided_kernel(const float* __restrict__ part, long stride, long offset, float* __restrict__ dst, long numel,
+                                      int splits, int accumulate) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(long)z * stride + offset + i];
+  dst[i] = accumulate ? dst[i] + s : s;
+}
+
 int fill_geom(const char* name, const dg_tensor* img, const dg_tensor* out, const dg_conv_params* p, Geom* g) {
   DG_REQUIRE(dg_valid(img) && dg_valid(out) && p, "%s: invalid tensor", name);
   DG_REQUIRE(p->kh >= 1 && p->kw >= 1 && p->stride >= 1, "%s: bad kernel geometry", name);
@@ -288,6 +299,115 @@ int fill_geom(const char* name, const dg_tensor* img, const dg_tensor* out, cons
   // every output position must read a window that starts inside the padded image
   DG_REQUIRE((g->Ho - 1) * g->stride - g->pad_t < g->H && (g->Wo - 1) * g->stride - g->pad_l < g->W,
              "%s: output size %dx%d inconsistent with input %dx%d", name, g->Ho, g->Wo, g->H, g->W);
+  return 0;
+}
+
+
+// ------------------------------------------------------------------ thin-layer dispatch (conv_thin.cuh)
+using dgthin::ThinGeom;
+
+bool thin_shape_ok(const dg_tensor* img, const dg_tensor* out, const dg_conv_params* p) {
+  return p->stride == 1 && img->h == out->h && img->w == out->w && p->kh * p->kw <= 16 && p->kw <= dgthin::OUT_MAX_KW;
+}
+bool fat_ok(const dg_tensor* t, int mult) { return dgvec::vec_ok(t) && t->c % mult == 0; }
+
+ThinGeom thin_geom(const dg_tensor* img, const dg_conv_params* p, int cin, int cout) {
+  ThinGeom g;
+  g.N = img->n; g.H = img->h; g.W = img->w; g.kh = p->kh; g.kw = p->kw;
+  g.dh0 = p->pad_t; g.dw0 = p->pad_l; g.dsign = 1;
+  g.w_st = cin * cout;
+  g.act = p->act; g.alpha = p->act_alpha;
+  return g;
+}
+
+// returns -1 when the layer is not "thin", else 0/1 like the public entry points
+template <int MODE>  // 0 forward (in=x, out=y), 1 dgrad (in=dy, out=dx)
+int try_thin(dg_ctx* ctx, const char* name, const dg_tensor* in, const float* w, const float* bias, const dg_tensor* out,
+             const dg_conv_params* p, cudaStream_t st) {
+  const dg_tensor* img = MODE == 0 ? in : out;   // x-side tensor
+  const dg_tensor* oth = MODE == 0 ? out : in;   // y-side tensor
+  if (!thin_shape_ok(img, oth, p)) return -1;
+  const int cin = img->c, cout = oth->c;
+  ThinGeom g = thin_geom(img, p, cin, cout);
+  g.dsign = MODE == 0 ? 1 : -1;
+  const long P = dg_pixels(in);
+  const int in_c = in->c, out_c = out->c;
+  // weight strides (tap, thin, fat) for W[t][ci][co]
+  const int s_ci = cout, s_co = 1;
+  if (in_c <= 4 && fat_ok(out, 16)) {           // expand: thin input -> fat output
+    g.CT = in_c; g.CF = out_c; g.tp = in->cpitch; g.to = in->coff; g.fp = out->cpitch; g.fo = out->coff;
+    g.w_sthin = MODE == 0 ? s_ci : s_co; g.w_sfat = MODE == 0 ? s_co : s_ci;
+    dim3 grid((unsigned)((P + dgthin::EXP_THREADS - 1) / dgthin::EXP_THREADS), out_c / dgthin::EXP_OG);
+    DG_DISPATCH_2(in->dtype, out->dtype, name,
+                  dgthin::thin_expand_kernel<TI, TO><<<grid, dgthin::EXP_THREADS, 0, st>>>((const TI*)in->ptr, (TO*)out->ptr, w, bias, g););
+    DG_CHECK_LAUNCH(name);
+    return 0;
+  }
+  if (out_c <= 4 && fat_ok(in, 8)) {            // contract: fat input -> thin output
+    g.CT = out_c; g.CF = in_c; g.tp = out->cpitch; g.to = out->coff; g.fp = in->cpitch; g.fo = in->coff;
+    g.w_sthin = MODE == 0 ? s_co : s_ci; g.w_sfat = MODE == 0 ? s_ci : s_co;
+    size_t smem = (size_t)g.kh * g.kw * g.CF * sizeof(float4);
+    if (smem > 40 * 1024) return -1;
+    unsigned grid = (unsigned)((P + dgthin::CON_THREADS - 1) / dgthin::CON_THREADS);
+    DG_DISPATCH_2(in->dtype, out->dtype, name,
+                  dgthin::thin_contract_kernel<TI, TO><<<grid, dgthin::CON_THREADS, smem, st>>>((const TI*)in->ptr, (TO*)out->ptr, w, bias, g););
+    DG_CHECK_LAUNCH(name);
+    return 0;
+  }
+  return -1;
+}
+
+constexpr int THIN_WGRAD_BLOCKS = 592;  // 4 x 148 partial blocks
+
+bool thin_wgrad_applicable(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
+  if (!thin_shape_ok(x, dy, p)) return false;
+  const dg_tensor* fat = x->c <= 4 ? dy : x;
+  const dg_tensor* thin = x->c <= 4 ? x : dy;
+  if (thin->c > 4 || thin->c < 1) return false;
+  if (!fat_ok(fat, 8)) return false;
+  int warps = (fat->c / 8) * p->kh;
+  return warps >= 1 && warps <= 32;
+}
+
+int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, const dg_conv_params* p,
+               int accumulate, void* workspace, cudaStream_t st) {
+  const char* name = "dg_conv2d_wgrad(thin)";
+  const bool thin_in = x->c <= 4;
+  const dg_tensor* fat = thin_in ? dy : x;
+  const dg_tensor* thin = thin_in ? x : dy;
+  const int cin = x->c, cout = dy->c;
+  ThinGeom g = thin_geom(x, p, cin, cout);
+  g.CT = thin->c; g.CF = fat->c; g.tp = thin->cpitch; g.to = thin->coff; g.fp = fat->cpitch; g.fo = fat->coff;
+  g.dsign = thin_in ? 1 : -1;
+  g.w_sthin = thin_in ? cout : 1;
+  g.w_sfat = thin_in ? 1 : cout;
+  const long P = dg_pixels(x);
+  const long n_dw = (long)p->kh * p->kw * cin * cout;
+  const long part_stride = n_dw + cout;
+  long per = (P + THIN_WGRAD_BLOCKS - 1) / THIN_WGRAD_BLOCKS;
+  per = (per + 31) / 32 * 32;
+  const int blocks = (int)((P + per - 1) / per);
+  const int threads = 32 * (fat->c / 8) * p->kh;
+  float* part = (float*)workspace;
+  const int want_bias = dbias != nullptr;
+#define THIN_OUTER(CTN)                                                                                                   \
+  DG_DISPATCH_2(fat->dtype, thin->dtype, name,                                                                            \
+                dgthin::thin_outer_kernel<TI, TO, CTN><<<blocks, threads, 0, st>>>((const TI*)fat->ptr, (const TO*)thin->ptr, part, \
+                                                                                  part_stride, n_dw, thin_in ? 1 : 0, want_bias, g, per);)
+  switch (thin->c) {
+    case 1: THIN_OUTER(1); break;
+    case 2: THIN_OUTER(2); break;
+    case 3: THIN_OUTER(3); break;
+    default: THIN_OUTER(4); break;
+  }
+#undef THIN_OUTER
+  DG_CHECK_LAUNCH(name);
+  reduce_strided_kernel<<<(unsigned)((n_dw + 255) / 256), 256, 0, st>>>(part, part_stride, 0, dw, n_dw, blocks, accumulate);
+  if (dbias) {
+    const int nbias = cout;
+    reduce_strided_kernel<<<(nbias + 255) / 256, 256, 0, st>>>(part, part_stride, n_dw, dbias, nbias, blocks, accumulate);
+  }
+  DG_CHECK_LAUNCH(name);
   return 0;
 }
 
@@ -306,6 +426,10 @@ extern "C" int dg_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const float* w, co
   if (fill_geom("dg_conv2d_fwd", x, y, p, &g)) return 1;
   DG_REQUIRE(w, "dg_conv2d_fwd: null weights");
   DG_REQUIRE(p->act != DG_ACT_PRELU, "dg_conv2d_fwd: PReLU is not a conv epilogue");
+  {
+    int r = try_thin<0>(ctx, "dg_conv2d_fwd(thin)", x, w, bias, y, p, (cudaStream_t)stream);
+    if (r >= 0) return r;
+  }
   long M = (long)g.N * g.Ho * g.Wo;
   dim3 grid((unsigned)((M + TM - 1) / TM), (g.Cout + TN - 1) / TN);
   DG_DISPATCH_2(x->dtype, y->dtype, "dg_conv2d_fwd",
@@ -320,6 +444,10 @@ extern "C" int dg_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const float* w,
   if (fill_geom("dg_conv2d_dgrad", dx, dy, p, &g)) return 1;
   DG_REQUIRE(w, "dg_conv2d_dgrad: null weights");
   DG_REQUIRE(p->act != DG_ACT_PRELU, "dg_conv2d_dgrad: PReLU is not a conv epilogue");
+  {
+    int r = try_thin<1>(ctx, "dg_conv2d_dgrad(thin)", dy, w, bias, dx, p, (cudaStream_t)stream);
+    if (r >= 0) return r;
+  }
   long M = (long)g.N * g.H * g.W;
   dim3 grid((unsigned)((M + TM - 1) / TM), (g.Cin + TN - 1) / TN);
   DG_DISPATCH_2(dy->dtype, dx->dtype, "dg_conv2d_dgrad",
@@ -331,6 +459,7 @@ extern "C" int dg_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const float* w,
 extern "C" size_t dg_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
   long P = (long)dy->n * dy->h * dy->w;
   int splits = wgrad_splits(P);
+  if (splits < THIN_WGRAD_BLOCKS) splits = THIN_WGRAD_BLOCKS;  // the thin-layer path writes up to this many partials
   return (size_t)splits * ((size_t)p->kh * p->kw * x->c * dy->c + dy->c) * sizeof(float);
 }
 
@@ -341,6 +470,7 @@ extern "C" int dg_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor*
   if (fill_geom("dg_conv2d_wgrad", x, dy, p, &g)) return 1;
   DG_REQUIRE(dw && workspace, "dg_conv2d_wgrad: null output/workspace");
   DG_REQUIRE(workspace_bytes >= dg_conv2d_wgrad_workspace_bytes(x, dy, p), "dg_conv2d_wgrad: workspace too small");
+  if (thin_wgrad_applicable(x, dy, p)) return thin_wgrad(ctx, x, dy, dw, dbias, p, accumulate, workspace, (cudaStream_t)stream);
   long P = (long)g.N * g.Ho * g.Wo;
   int splits = wgrad_splits(P);
   long per = ((P + splits - 1) / splits + TK - 1) / TK * TK;

@@ -261,22 +261,39 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   pl->kco = kc_for(dy->c);
   pl->n_chunks = x->c / pl->kc;
   pl->has_bias = has_bias;
-  // worst-case number of accumulator groups of one launch (all taps; chunk ranges of <= 128 channels)
   const int atoms = 128 / pl->kc;
+  const int chunks_per_launch = pl->n_chunks < atoms ? pl->n_chunks : atoms;
+  // halo bytes of one launch stage (all sources, the launch's chunks)
+  uint32_t halo = 0, max_chunk = 0;
+  for (int s = 0; s < pl->n_src; ++s) {
+    int dh0 = 1 << 30, dh1 = -(1 << 30), dw0 = 1 << 30, dw1 = -(1 << 30);
+    for (int t = 0; t < pl->n_taps; ++t)
+      if (pl->taps[t].src == s) {
+        dh0 = pl->taps[t].dh < dh0 ? pl->taps[t].dh : dh0; dh1 = pl->taps[t].dh > dh1 ? pl->taps[t].dh : dh1;
+        dw0 = pl->taps[t].dw < dw0 ? pl->taps[t].dw : dw0; dw1 = pl->taps[t].dw > dw1 ? pl->taps[t].dw : dw1;
+      }
+    uint32_t cb = ((uint32_t)(16 + dh1 - dh0) * (8 + dw1 - dw0) * pl->kc * 2 + 1023u) & ~1023u;
+    halo += cb * chunks_per_launch;
+    max_chunk = cb > max_chunk ? cb : max_chunk;
+  }
+  // worst-case number of accumulator groups of one launch
   int n_groups = pl->n_taps;  // one group per tap when a launch spans several chunks
   if (pl->n_chunks == 1) n_groups = (pl->n_taps + 1) / 2 + pl->n_src;  // upper bound for tap stacking
-  int cout = dy->c;
+  const int cout = dy->c;
+  const uint32_t budget = SMEM_LIMIT - 4096;
+  const uint32_t fixed = (has_bias ? 128u * pl->kc * 2 : 0u) + max_chunk;  // ones tile + slack for padding atoms
+  auto fits = [&](int nb) { return 2 * ((halo + 128u * nb * 2 + 1023u) & ~1023u) + fixed <= budget; };
   int best_nb = 0;
   for (int nb = cout > 256 ? 256 : cout; nb >= 16; nb -= 16) {
-    if (cout % nb != 0 || nb % pl->kco != 0) continue;
+    if (cout % nb != 0 || nb % pl->kco != 0 || !fits(nb)) continue;
     int gpc = 512 / nb - (has_bias ? 1 : 0);
     if (gpc >= n_groups) { best_nb = nb; break; }
   }
   if (!best_nb) {
     for (int nb = cout > 64 ? 64 : cout; nb >= 16; nb -= 16)
-      if (cout % nb == 0 && nb % pl->kco == 0) { best_nb = nb; break; }
+      if (cout % nb == 0 && nb % pl->kco == 0 && fits(nb)) { best_nb = nb; break; }
   }
-  DG_REQUIRE(best_nb > 0, "%s: no N block for Cout=%d", name, cout);
+  DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d)", name, x->c, cout);
   pl->nb = best_nb;
   pl->gpc = 512 / best_nb - (has_bias ? 1 : 0);
   if (pl->gpc > MAX_GROUPS) pl->gpc = MAX_GROUPS;

@@ -8,6 +8,7 @@
 // Dropout pix2pix.py:138; Add srgan.py:169,175.
 #include "dg_common.cuh"
 #include "reduce.cuh"
+#include "pointwise_vec.cuh"
 
 namespace {
 
@@ -16,6 +17,35 @@ struct View {
 };
 
 using namespace dgred;
+
+
+// Sums NV per-channel partials over `nblocks` blocks (layout [block][NV][C]) for the 8 channels owned by
+// this thread block: 256 threads = 32 block-lanes x 8 channels; result valid in threads with lane == 0.
+template <int NV>
+__device__ __forceinline__ bool sum_partials8(const float* __restrict__ partial, int nblocks, int C, double (&out)[NV], int* c_out) {
+  __shared__ double sm_part[NV][32][8];
+  const int cl = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  if (c < C)
+    for (int b = lane; b < nblocks; b += 32)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] += (double)partial[((long)b * NV + v) * C + c];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sm_part[v][lane][cl] = acc[v];
+  __syncthreads();
+  *c_out = c;
+  if (lane != 0 || c >= C) return false;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double t = 0.0;
+    for (int l = 0; l < 32; ++l) t += sm_part[v][l][cl];
+    out[v] = t;
+  }
+  return true;
+}
 
 // ------------------------------------------------------------------ BN statistics
 template <typename T>
@@ -33,15 +63,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    float momentum, float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += partial[(long)b * 2 * C + c];
-    ss += partial[(long)b * 2 * C + C + c];
-  }
-  double mean = s / (double)P;
-  double var = ss / (double)P - mean * mean;
+  double sums[2];
+  int c;
+  if (!sum_partials8<2>(partial, nblocks, C, sums, &c)) return;
+  double mean = sums[0] / (double)P;
+  double var = sums[1] / (double)P - mean * mean;
   if (var < 0.0) var = 0.0;
   float invstd = (float)(1.0 / sqrt(var + (double)eps));
   float g = gamma[c], b = beta[c];
@@ -134,14 +160,10 @@ bn_bwd_reduce_kernel(const TG* __restrict__ dy, View dv, const TX* __restrict__ 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, long P, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ dalpha, int accumulate, float* __restrict__ coef) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s0 = 0, s1 = 0, s2 = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    s0 += partial[(long)b * 3 * C + c];
-    s1 += partial[(long)b * 3 * C + C + c];
-    s2 += partial[(long)b * 3 * C + 2 * C + c];
-  }
+  double sums[3];
+  int c;
+  if (!sum_partials8<3>(partial, nblocks, C, sums, &c)) return;
+  const double s0 = sums[0], s1 = sums[1], s2 = sums[2];
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
   if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
@@ -255,11 +277,10 @@ d2s_prelu_dalpha_kernel(const T* __restrict__ dy, View dv, const T* __restrict__
 
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out,
                                     int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(long)b * C + c];
-  out[c] = (accumulate ? out[c] : 0.f) + (float)s;
+  double sums[1];
+  int c;
+  if (!sum_partials8<1>(partial, nblocks, C, sums, &c)) return;
+  out[c] = (accumulate ? out[c] : 0.f) + (float)sums[0];
 }
 
 // ------------------------------------------------------------------ add / copy
@@ -430,9 +451,16 @@ extern "C" int dg_bn_stats(dg_ctx* ctx, const dg_tensor* x, const float* gamma, 
   int R = RED_THREADS / red_lanes(C);
   size_t smem = (size_t)R * 2 * C * sizeof(float);
   float* partial = (float*)workspace;
-  DG_DISPATCH_1(x->dtype, "dg_bn_stats",
-                bn_stats_kernel<T><<<blocks, RED_THREADS, smem, ST>>>((const T*)x->ptr, view_of(x), P, C, partial););
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partial, blocks, P, C, gamma, beta, eps, momentum, moving_mean,
+  if (dgvec::vec_ok(x)) {
+    blocks = dgvec::red8_blocks(P, C, ctx->sm_count);
+    DG_DISPATCH_1(x->dtype, "dg_bn_stats",
+                  dgvec::bn_stats8_kernel<T><<<blocks, dgvec::VT, dgvec::red8_smem(C, 2), ST>>>(
+                      (const T*)x->ptr, dgvec::VView{x->cpitch, x->coff}, P, C, partial););
+  } else {
+    DG_DISPATCH_1(x->dtype, "dg_bn_stats",
+                  bn_stats_kernel<T><<<blocks, RED_THREADS, smem, ST>>>((const T*)x->ptr, view_of(x), P, C, partial););
+  }
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, blocks, P, C, gamma, beta, eps, momentum, moving_mean,
                                                       moving_var, scale, shift, save_mean, save_invstd);
   DG_CHECK_LAUNCH("dg_bn_stats");
   return 0;
@@ -457,6 +485,15 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
   long P = dg_pixels(x);
   int C = x->c;
   View rv = residual ? view_of(residual) : View{0, 0};
+  if (dgvec::vec_ok(x) && dgvec::vec_ok(y) && (!residual || dgvec::vec_ok(residual))) {
+    DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
+                  dgvec::bn_act_fwd8_kernel<TI, TO><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const TI*)x->ptr, dgvec::VView{x->cpitch, x->coff}, scale, shift, act, act_alpha, prelu_alpha,
+                      residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset,
+                      (TO*)y->ptr, dgvec::VView{y->cpitch, y->coff}, P, C););
+    DG_CHECK_LAUNCH("dg_bn_act_fwd");
+    return 0;
+  }
   DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
                 bn_act_fwd_kernel<TI, TO><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
                     (const TI*)x->ptr, view_of(x), scale, shift, act, act_alpha, prelu_alpha,
@@ -483,11 +520,27 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
   size_t smem = (size_t)R * 3 * C * sizeof(float);
   float* partial = (float*)workspace;
   float* coef = partial + (size_t)256 * 8 * 3 * C;
+  if (dgvec::vec_ok(dy) && dgvec::vec_ok(x) && dgvec::vec_ok(dx)) {
+    const int vblocks = dgvec::red8_blocks(P, C, ctx->sm_count);
+    const dgvec::VView vdy{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vdx{dx->cpitch, dx->coff};
+    DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
+      dgvec::bn_bwd_reduce8_kernel<TI, TO><<<vblocks, dgvec::VT, dgvec::red8_smem(C, 3), ST>>>(
+          (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout,
+          seed, offset, P, C, partial);
+      bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, vblocks, P, C, dgamma, dbeta,
+                                                              act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
+      dgvec::bn_bwd_dx8_kernel<TI, TO, TI><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
+          (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,
+          dropout, seed, offset, coef, (TI*)dx->ptr, vdx, P, C);
+    });
+    DG_CHECK_LAUNCH("dg_bn_act_bwd");
+    return 0;
+  }
   DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
     bn_bwd_reduce_kernel<TI, TO><<<blocks, RED_THREADS, smem, ST>>>(
         (const TI*)dy->ptr, view_of(dy), (const TO*)x->ptr, view_of(x), scale, shift, save_mean, save_invstd, act,
         act_alpha, prelu_alpha, dropout, seed, offset, P, C, partial);
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partial, blocks, P, C, dgamma, dbeta,
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, blocks, P, C, dgamma, dbeta,
                                                             act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
     bn_bwd_dx_kernel<TI, TO, TI><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
         (const TI*)dy->ptr, view_of(dy), (const TO*)x->ptr, view_of(x), scale, shift, gamma, save_mean, save_invstd,
@@ -505,6 +558,14 @@ extern "C" int dg_act_bwd_from_output(dg_ctx* ctx, const dg_tensor* dy, const dg
   DG_REQUIRE(act != DG_ACT_PRELU, "dg_act_bwd_from_output: PReLU needs the pre-activation");
   long P = dg_pixels(y);
   int C = y->c;
+  if (dgvec::vec_ok(dy) && dgvec::vec_ok(y) && dgvec::vec_ok(dpre)) {
+    DG_DISPATCH_2(dy->dtype, y->dtype, "dg_act_bwd_from_output",
+                  dgvec::act_bwd8_kernel<TI, TO, TI><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const TI*)dy->ptr, dgvec::VView{dy->cpitch, dy->coff}, (const TO*)y->ptr, dgvec::VView{y->cpitch, y->coff}, act,
+                      act_alpha, (TI*)dpre->ptr, dgvec::VView{dpre->cpitch, dpre->coff}, P, C););
+    DG_CHECK_LAUNCH("dg_act_bwd_from_output");
+    return 0;
+  }
   DG_DISPATCH_2(dy->dtype, y->dtype, "dg_act_bwd_from_output",
                 act_bwd_kernel<TI, TO, TI><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
                     (const TI*)dy->ptr, view_of(dy), (const TO*)y->ptr, view_of(y), act, act_alpha, (TI*)dpre->ptr,
@@ -520,6 +581,14 @@ extern "C" int dg_d2s_prelu_fwd(dg_ctx* ctx, const dg_tensor* u, const float* pr
              "dg_d2s_prelu_fwd: shape mismatch");
   DG_REQUIRE(u->dtype == y->dtype, "dg_d2s_prelu_fwd: dtype mismatch");
   long total = dg_pixels(u) * u->c;
+  if (dgvec::vec_ok(u) && dgvec::vec_ok(y)) {
+    DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_fwd",
+                  dgvec::d2s_prelu8_kernel<T, false><<<dgvec::ew8_blocks(total / 8, ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const T*)u->ptr, dgvec::VView{u->cpitch, u->coff}, nullptr, dgvec::VView{0, 0}, prelu_alpha, (T*)y->ptr,
+                      dgvec::VView{y->cpitch, y->coff}, u->n, u->h, u->w, y->c););
+    DG_CHECK_LAUNCH("dg_d2s_prelu_fwd");
+    return 0;
+  }
   DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_fwd",
                 d2s_prelu_fwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
                     (const T*)u->ptr, view_of(u), prelu_alpha, (T*)y->ptr, view_of(y), u->n, u->h, u->w, y->c););
@@ -536,11 +605,26 @@ extern "C" int dg_d2s_prelu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tenso
   DG_REQUIRE(dy->dtype == u->dtype && du->dtype == u->dtype, "dg_d2s_prelu_bwd: dtype mismatch");
   long total = dg_pixels(u) * u->c;
   int Co = dy->c;
+  const bool vec = dgvec::vec_ok(dy) && dgvec::vec_ok(u) && dgvec::vec_ok(du);
   DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_bwd", {
-    d2s_prelu_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
-        (const T*)dy->ptr, view_of(dy), (const T*)u->ptr, view_of(u), prelu_alpha, (T*)du->ptr, view_of(du), u->n, u->h,
-        u->w, Co);
-    if (prelu_alpha && dprelu_alpha) {
+    if (vec)
+      dgvec::d2s_prelu8_kernel<T, true><<<dgvec::ew8_blocks(total / 8, ctx->sm_count), dgvec::VT, 0, ST>>>(
+          (const T*)dy->ptr, dgvec::VView{dy->cpitch, dy->coff}, (const T*)u->ptr, dgvec::VView{u->cpitch, u->coff}, prelu_alpha,
+          (T*)du->ptr, dgvec::VView{du->cpitch, du->coff}, u->n, u->h, u->w, Co);
+    else
+      d2s_prelu_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
+          (const T*)dy->ptr, view_of(dy), (const T*)u->ptr, view_of(u), prelu_alpha, (T*)du->ptr, view_of(du), u->n, u->h,
+          u->w, Co);
+    if (prelu_alpha && dprelu_alpha && vec) {
+      DG_REQUIRE(workspace && workspace_bytes >= dg_bn_workspace_bytes(dy), "dg_d2s_prelu_bwd: workspace too small");
+      long Pout = dg_pixels(dy);
+      int vblocks = dgvec::red8_blocks(Pout, Co, ctx->sm_count);
+      float* partial = (float*)workspace;
+      dgvec::d2s_dalpha8_kernel<T><<<vblocks, dgvec::VT, dgvec::red8_smem(Co, 1), ST>>>(
+          (const T*)dy->ptr, dgvec::VView{dy->cpitch, dy->coff}, (const T*)u->ptr, dgvec::VView{u->cpitch, u->coff}, Pout, dy->h,
+          dy->w, Co, partial);
+      sum_partials_kernel<<<(Co + 7) / 8, 256, 0, ST>>>(partial, vblocks, Co, dprelu_alpha, accumulate);
+    } else if (prelu_alpha && dprelu_alpha) {
       DG_REQUIRE(workspace && workspace_bytes >= dg_bn_workspace_bytes(dy), "dg_d2s_prelu_bwd: workspace too small");
       long Pout = dg_pixels(dy);
       int blocks = red_blocks(Pout, Co, ctx->sm_count);
@@ -548,7 +632,7 @@ extern "C" int dg_d2s_prelu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tenso
       float* partial = (float*)workspace;
       d2s_prelu_dalpha_kernel<T><<<blocks, RED_THREADS, (size_t)R * Co * sizeof(float), ST>>>(
           (const T*)dy->ptr, view_of(dy), (const T*)u->ptr, view_of(u), Pout, dy->h, dy->w, Co, partial);
-      sum_partials_kernel<<<(Co + 127) / 128, 128, 0, ST>>>(partial, blocks, Co, dprelu_alpha, accumulate);
+      sum_partials_kernel<<<(Co + 7) / 8, 256, 0, ST>>>(partial, blocks, Co, dprelu_alpha, accumulate);
     }
   });
   DG_CHECK_LAUNCH("dg_d2s_prelu_bwd");
@@ -559,6 +643,14 @@ extern "C" int dg_add(dg_ctx* ctx, const dg_tensor* a, const dg_tensor* b, const
   DG_REQUIRE(dg_valid(a) && dg_valid(b) && dg_valid(out), "dg_add: null argument");
   DG_REQUIRE(dg_same_shape(a, b) && dg_same_shape(a, out) && a->dtype == b->dtype, "dg_add: shape/dtype mismatch");
   long P = dg_pixels(a);
+  if (dgvec::vec_ok(a) && dgvec::vec_ok(b) && dgvec::vec_ok(out)) {
+    DG_DISPATCH_2(a->dtype, out->dtype, "dg_add",
+                  dgvec::ew8_kernel<TI, TO, 1><<<dgvec::ew8_blocks(P * (a->c / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const TI*)a->ptr, dgvec::VView{a->cpitch, a->coff}, (const TI*)b->ptr, dgvec::VView{b->cpitch, b->coff},
+                      (TO*)out->ptr, dgvec::VView{out->cpitch, out->coff}, P, a->c););
+    DG_CHECK_LAUNCH("dg_add");
+    return 0;
+  }
   DG_DISPATCH_2(a->dtype, out->dtype, "dg_add",
                 add_kernel<TI, TO><<<ew_blocks(P * a->c, ctx->sm_count), 256, 0, ST>>>(
                     (const TI*)a->ptr, view_of(a), (const TI*)b->ptr, view_of(b), (TO*)out->ptr, view_of(out), P, a->c););
@@ -570,6 +662,18 @@ extern "C" int dg_copy(dg_ctx* ctx, const dg_tensor* src, const dg_tensor* out, 
   DG_REQUIRE(dg_valid(src) && dg_valid(out), "dg_copy: null argument");
   DG_REQUIRE(dg_same_shape(src, out), "dg_copy: shape mismatch");
   long P = dg_pixels(src);
+  if (dgvec::vec_ok(src) && dgvec::vec_ok(out)) {
+    const dgvec::VView vs{src->cpitch, src->coff}, vo{out->cpitch, out->coff};
+    const unsigned nblk = dgvec::ew8_blocks(P * (src->c / 8), ctx->sm_count);
+    DG_DISPATCH_2(src->dtype, out->dtype, "dg_copy", {
+      if (accumulate)
+        dgvec::ew8_kernel<TI, TO, 2><<<nblk, dgvec::VT, 0, ST>>>((const TI*)src->ptr, vs, nullptr, vs, (TO*)out->ptr, vo, P, src->c);
+      else
+        dgvec::ew8_kernel<TI, TO, 0><<<nblk, dgvec::VT, 0, ST>>>((const TI*)src->ptr, vs, nullptr, vs, (TO*)out->ptr, vo, P, src->c);
+    });
+    DG_CHECK_LAUNCH("dg_copy");
+    return 0;
+  }
   DG_DISPATCH_2(src->dtype, out->dtype, "dg_copy",
                 copy_kernel<TI, TO><<<ew_blocks(P * src->c, ctx->sm_count), 256, 0, ST>>>(
                     (const TI*)src->ptr, view_of(src), (TO*)out->ptr, view_of(out), P, src->c, accumulate););

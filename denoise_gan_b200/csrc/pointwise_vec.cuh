@@ -1,0 +1,338 @@
+// 8-channel-vector versions of the HBM-bound kernels in pointwise.cu: every thread moves 16 bytes
+// (bf16) or 32 bytes (fp32) per tensor per step, so a warp touches fully used 128-byte lines.
+// Used whenever channel count, pitch and offset are multiples of 8 (all 16/32/64/256-channel
+// activations of the networks); the scalar kernels in pointwise.cu remain for odd shapes (RGB images,
+// the autoencoder's 44/56/76/100-channel layers).
+#pragma once
+#include "dg_common.cuh"
+
+namespace dgvec {
+
+constexpr int VT = 256;
+
+template <typename T>
+struct V8;
+template <>
+struct V8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ void ldc8(const float* __restrict__ p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+struct VView {
+  int pitch, off;
+};
+
+// ---------------------------------------------------------------- per-channel reduction skeleton (8 channels / thread)
+// F(p, c0, acc[NV][8]); partial layout [block][NV][C]
+template <int NV, typename F>
+__device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict__ partial, F f) {
+  extern __shared__ float red8[];
+  const int CV = C >> 3, R = VT / CV;
+  const int lane = threadIdx.x % CV, row = threadIdx.x / CV;
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  if (row < R)
+    for (long p = (long)blockIdx.x * R + row; p < P; p += (long)gridDim.x * R) f(p, lane * 8, acc);
+  if (row < R) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red8[(row * NV + v) * C + lane * 8 + j] = acc[v][j];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NV * C; e += VT) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += red8[r * NV * C + e];
+    partial[(long)blockIdx.x * NV * C + e] = s;
+  }
+}
+
+static inline int red8_blocks(long P, int C, int sm_count) {
+  int R = VT / (C >> 3);
+  long want = (P + R - 1) / R, cap = (long)sm_count * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+static inline size_t red8_smem(int C, int NV) { return (size_t)(VT / (C >> 3)) * NV * C * sizeof(float); }
+
+static inline bool vec_ok(const dg_tensor* t) {
+  int esz = t->dtype == DG_F32 ? 4 : 2;
+  return t->c % 8 == 0 && t->cpitch % 8 == 0 && t->coff % 8 == 0 && t->c <= 1024 && ((uintptr_t)t->ptr % 16) == 0 &&
+         (t->cpitch * esz) % 16 == 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(VT) bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __restrict__ partial) {
+  channel_reduce8<2>(P, C, partial, [&](long p, int c0, float (&a)[2][8]) {
+    float v[8];
+    V8<T>::ld(x + (p * xv.pitch + xv.off + c0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[0][j] += v[j]; a[1][j] += v[j] * v[j]; }
+  });
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(VT)
+bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                   float alpha, const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, int dropout,
+                   uint32_t seed, uint32_t offset, TO* __restrict__ y, VView yv, long P, int C) {
+  const int CV = C >> 3;
+  const long total = P * CV;
+  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
+    const long p = i / CV;
+    const int c0 = (int)(i - p * CV) * 8;
+    float v[8], sc[8], sh[8];
+    V8<TI>::ld(x + (p * xv.pitch + xv.off + c0), v);
+    ldc8(scale + c0, sc); ldc8(shift + c0, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+    if (dropout) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j)) ? 2.f * v[j] : 0.f;
+    }
+    if (act == DG_ACT_PRELU) {
+      float al[8];
+      ldc8(prelu_alpha + c0, al);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : al[j] * v[j];
+    } else if (act != DG_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, alpha);
+    }
+    if (res) {
+      float r[8];
+      V8<TO>::ld(res + (p * rv.pitch + rv.off + c0), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    V8<TO>::st(y + (p * yv.pitch + yv.off + c0), v);
+  }
+}
+
+// g[j] = dL/d(bn output); t[j] = activation input (after dropout)
+template <typename TG, typename TX>
+__device__ __forceinline__ void bn_bwd_g8(const TG* dy, VView dv, const TX* x, VView xv, const float* scale, const float* shift,
+                                          int act, float alpha, const float* prelu_alpha, int dropout, uint32_t seed,
+                                          uint32_t offset, long p, int c0, int C, float (&g)[8], float (&t)[8], float (&xin)[8],
+                                          float (&gy)[8]) {
+  float sc[8], sh[8];
+  V8<TX>::ld(x + (p * xv.pitch + xv.off + c0), xin);
+  V8<TG>::ld(dy + (p * dv.pitch + dv.off + c0), gy);
+  ldc8(scale + c0, sc); ldc8(shift + c0, sh);
+  float al[8];
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float tt = xin[j] * sc[j] + sh[j];
+    float dm = 1.f;
+    if (dropout) {
+      bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
+      tt = keep ? 2.f * tt : 0.f;
+      dm = keep ? 2.f : 0.f;
+    }
+    float d;
+    switch (act) {
+      case DG_ACT_RELU: d = tt > 0.f ? 1.f : 0.f; break;
+      case DG_ACT_LRELU: d = tt >= 0.f ? 1.f : alpha; break;
+      case DG_ACT_PRELU: d = tt > 0.f ? 1.f : al[j]; break;
+      case DG_ACT_TANH: { float yy = tanhf(tt); d = 1.f - yy * yy; break; }
+      case DG_ACT_SIGMOID: { float yy = 1.f / (1.f + expf(-tt)); d = yy * (1.f - yy); break; }
+      default: d = 1.f;
+    }
+    t[j] = tt;
+    g[j] = gy[j] * d * dm;
+  }
+}
+
+template <typename TG, typename TX>
+__global__ void __launch_bounds__(VT)
+bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
+                      const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                      float alpha, const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset, long P, int C,
+                      float* __restrict__ partial) {
+  channel_reduce8<3>(P, C, partial, [&](long p, int c0, float (&a)[3][8]) {
+    float g[8], t[8], xin[8], gy[8], mu[8], is[8];
+    bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
+    ldc8(mean + c0, mu); ldc8(invstd + c0, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[0][j] += g[j];
+      a[1][j] += g[j] * (xin[j] - mu[j]) * is[j];
+      if (act == DG_ACT_PRELU) a[2][j] += gy[j] * fminf(t[j], 0.f);
+    }
+  });
+}
+
+// dx = gamma*invstd*(g - mean_g - xhat*mean_gxhat)  [+ extra: gradient arriving through a skip connection]
+template <typename TG, typename TX, typename TO>
+__global__ void __launch_bounds__(VT)
+bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, int act, float alpha, const float* __restrict__ prelu_alpha, int dropout,
+                  uint32_t seed, uint32_t offset, const float* __restrict__ coef, TO* __restrict__ dx, VView ov, long P, int C) {
+  const int CV = C >> 3;
+  const long total = P * CV;
+  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
+    const long p = i / CV;
+    const int c0 = (int)(i - p * CV) * 8;
+    float g[8], t[8], xin[8], gy[8], mu[8], is[8], ga[8], k0[8], k1[8], o[8];
+    bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
+    ldc8(mean + c0, mu); ldc8(invstd + c0, is); ldc8(gamma + c0, ga); ldc8(coef + c0, k0); ldc8(coef + C + c0, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = ga[j] * is[j] * (g[j] - k0[j] - (xin[j] - mu[j]) * is[j] * k1[j]);
+    V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);
+  }
+}
+
+template <typename TG, typename TY, typename TO>
+__global__ void __launch_bounds__(VT)
+act_bwd8_kernel(const TG* __restrict__ dy, VView dv, const TY* __restrict__ y, VView yv, int act, float alpha, TO* __restrict__ dpre,
+                VView ov, long P, int C) {
+  const int CV = C >> 3;
+  const long total = P * CV;
+  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
+    const long p = i / CV;
+    const int c0 = (int)(i - p * CV) * 8;
+    float g[8], yo[8];
+    V8<TG>::ld(dy + (p * dv.pitch + dv.off + c0), g);
+    V8<TY>::ld(y + (p * yv.pitch + yv.off + c0), yo);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d;
+      switch (act) {
+        case DG_ACT_RELU: d = yo[j] > 0.f ? 1.f : 0.f; break;
+        case DG_ACT_LRELU: d = yo[j] >= 0.f ? 1.f : alpha; break;
+        case DG_ACT_TANH: d = 1.f - yo[j] * yo[j]; break;
+        case DG_ACT_SIGMOID: d = yo[j] * (1.f - yo[j]); break;
+        default: d = 1.f;
+      }
+      g[j] *= d;
+    }
+    V8<TO>::st(dpre + (p * ov.pitch + ov.off + c0), g);
+  }
+}
+
+// depth_to_space(2)+PReLU: one thread = 8 consecutive input channels (all in one sub-pixel block since Co % 8 == 0)
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(VT)
+d2s_prelu8_kernel(const T* __restrict__ a, VView av, const T* __restrict__ u, VView uv, const float* __restrict__ alpha,
+                  T* __restrict__ o, VView ov, int N, int H, int W, int Co) {
+  // FWD: a = u (input), o = y.   BWD: a = dy (output-sized), u = saved input, o = du.
+  const int CV = (4 * Co) >> 3;
+  const long total = (long)N * H * W * CV;
+  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
+    const long p = i / CV;
+    const int ch0 = (int)(i - p * CV) * 8;
+    const int w = (int)(p % W);
+    const long t = p / W;
+    const int h = (int)(t % H);
+    const long n = t / H;
+    const int sub = ch0 / Co, c0 = ch0 - sub * Co;
+    const long q = ((long)n * 2 * H + 2 * h + (sub >> 1)) * 2 * W + 2 * w + (sub & 1);
+    float v[8], al[8];
+    if (alpha) ldc8(alpha + c0, al);
+    if (!BWD) {
+      V8<T>::ld(a + (p * av.pitch + av.off + ch0), v);
+      if (alpha) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : al[j] * v[j];
+      }
+      V8<T>::st(o + (q * ov.pitch + ov.off + c0), v);
+    } else {
+      V8<T>::ld(a + (q * av.pitch + av.off + c0), v);
+      if (alpha) {
+        float uu[8];
+        V8<T>::ld(u + (p * uv.pitch + uv.off + ch0), uu);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = uu[j] > 0.f ? v[j] : al[j] * v[j];
+      }
+      V8<T>::st(o + (p * ov.pitch + ov.off + ch0), v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(VT)
+d2s_dalpha8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ u, VView uv, long Pout, int H2, int W2, int Co,
+                   float* __restrict__ partial) {
+  channel_reduce8<1>(Pout, Co, partial, [&](long q, int c0, float (&a)[1][8]) {
+    int w2 = (int)(q % W2);
+    long t = q / W2;
+    int h2 = (int)(t % H2);
+    long n = t / H2;
+    long p = (n * (H2 / 2) + h2 / 2) * (W2 / 2) + w2 / 2;
+    int sub = (h2 & 1) * 2 + (w2 & 1);
+    float g[8], uu[8];
+    V8<T>::ld(dy + (q * dv.pitch + dv.off + c0), g);
+    V8<T>::ld(u + (p * uv.pitch + uv.off + sub * Co + c0), uu);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[0][j] += g[j] * fminf(uu[j], 0.f);
+  });
+}
+
+// out = a (+ b) with dtype conversion; ACC: out += a
+template <typename TA, typename TO, int MODE>  // MODE 0: out = a ; 1: out = a + b ; 2: out += a
+__global__ void __launch_bounds__(VT)
+ew8_kernel(const TA* __restrict__ a, VView av, const TA* __restrict__ b, VView bv, TO* __restrict__ o, VView ov, long P, int C) {
+  const int CV = C >> 3;
+  const long total = P * CV;
+  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
+    const long p = i / CV;
+    const int c0 = (int)(i - p * CV) * 8;
+    float v[8];
+    V8<TA>::ld(a + (p * av.pitch + av.off + c0), v);
+    if (MODE == 1) {
+      float w[8];
+      V8<TA>::ld(b + (p * bv.pitch + bv.off + c0), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += w[j];
+    } else if (MODE == 2) {
+      float w[8];
+      V8<TO>::ld(o + (p * ov.pitch + ov.off + c0), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += w[j];
+    }
+    V8<TO>::st(o + (p * ov.pitch + ov.off + c0), v);
+  }
+}
+
+static inline unsigned ew8_blocks(long total_vec, int sm_count) {
+  long b = (total_vec + VT - 1) / VT, cap = (long)sm_count * 32;
+  return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace dgvec

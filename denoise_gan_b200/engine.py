@@ -61,6 +61,7 @@ class Engine:
         self.use_umma_wgrad = self.use_umma
         self.launches = 0
         self.record = None             # dict name -> Var when a test wants per-layer activations
+        self.grad_record = None        # dict seq -> dL/dVar of the generator pass when a test wants per-layer gradients
         self.prof = None               # list of (kind, flops, ev0, ev1) when bench.py profiles a step
 
     def _timed(self, kind: str, flops: float, call):

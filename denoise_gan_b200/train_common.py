@@ -35,7 +35,7 @@ def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: flo
     E.backward([(disc_real, g_real), (disc_fake, g_fake)], "d")        # :112
     if model.comm is not None:
         model.comm.start(model.disc_params.grad)    # overlaps the generator backward pass below
-    E.backward(seeds_g, "g")                                            # :111
+    E.backward(seeds_g, "g", collect=E.grad_record)                                            # :111
 
     scale = 1.0
     if model.comm is not None:

@@ -68,6 +68,10 @@ def srgan_train_step(g, d, vgg, gen_opt, disc_opt, x, y, *, fsrgan=False, acts=N
     if out is not None:
         out.update(gen_output=gen_output.detach(), disc_real=disc_real.detach(), disc_fake=disc_fake.detach(),
                    gen_grads=gen_grads, disc_grads=disc_grads)
+        if acts:
+            names = [k for k, v in acts.items() if v.requires_grad]
+            gs = torch.autograd.grad(gen_loss, [acts[k] for k in names], retain_graph=True, allow_unused=True)
+            out["act_grads"] = {k: v for k, v in zip(names, gs) if v is not None}
     _finish(g, d, g_state, d_state, gen_grads, disc_grads, gen_opt, disc_opt)        # :115-116
     vals = [v.detach() for v in (gen_loss, adv, mae, mse, content, disc_loss, var)]
     gl, adv_, mae_, mse_, content_, dl, var_ = vals
