@@ -366,7 +366,7 @@ bool thin_wgrad_applicable(const dg_tensor* x, const dg_tensor* dy, const dg_con
   if (thin->c > 4 || thin->c < 1) return false;
   if (!fat_ok(fat, 8)) return false;
   int warps = (fat->c / 8) * p->kh;
-  return warps >= 1 && warps <= 32;
+  return warps >= 1 && warps <= 16;
 }
 
 int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, const dg_conv_params* p,
@@ -390,10 +390,17 @@ int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, 
   const int threads = 32 * (fat->c / 8) * p->kh;
   float* part = (float*)workspace;
   const int want_bias = dbias != nullptr;
-#define THIN_OUTER(CTN)                                                                                                   \
+#define THIN_OUTER_KW(CTN, KWN)                                                                                           \
   DG_DISPATCH_2(fat->dtype, thin->dtype, name,                                                                            \
-                dgthin::thin_outer_kernel<TI, TO, CTN><<<blocks, threads, 0, st>>>((const TI*)fat->ptr, (const TO*)thin->ptr, part, \
-                                                                                  part_stride, n_dw, thin_in ? 1 : 0, want_bias, g, per);)
+                dgthin::thin_outer_kernel<TI, TO, CTN, KWN><<<blocks, threads, 0, st>>>((const TI*)fat->ptr, (const TO*)thin->ptr, part, \
+                                                                                       part_stride, n_dw, thin_in ? 1 : 0, want_bias, g, per);)
+#define THIN_OUTER(CTN)                   \
+  switch (p->kw) {                        \
+    case 1: THIN_OUTER_KW(CTN, 1); break; \
+    case 2: THIN_OUTER_KW(CTN, 2); break; \
+    case 3: THIN_OUTER_KW(CTN, 3); break; \
+    default: THIN_OUTER_KW(CTN, 4); break; \
+  }
   switch (thin->c) {
     case 1: THIN_OUTER(1); break;
     case 2: THIN_OUTER(2); break;
@@ -401,6 +408,7 @@ int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, 
     default: THIN_OUTER(4); break;
   }
 #undef THIN_OUTER
+#undef THIN_OUTER_KW
   DG_CHECK_LAUNCH(name);
   reduce_strided_kernel<<<(unsigned)((n_dw + 255) / 256), 256, 0, st>>>(part, part_stride, 0, dw, n_dw, blocks, accumulate);
   if (dbias) {

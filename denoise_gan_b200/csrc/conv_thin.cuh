@@ -143,8 +143,8 @@ thin_contract_kernel(const TF* __restrict__ fat, TT* __restrict__ thin, const fl
 // part layout per block: dW as HWIO strides (same as w) + bias slots behind it.
 constexpr int OUT_MAX_KW = 4;
 
-template <typename TF, typename TT, int CT>
-__global__ void thin_outer_kernel(const TF* __restrict__ fat, const TT* __restrict__ thin, float* __restrict__ part, long part_stride,
+template <typename TF, typename TT, int CT, int KW>
+__global__ void __launch_bounds__(512, 1) thin_outer_kernel(const TF* __restrict__ fat, const TT* __restrict__ thin, float* __restrict__ part, long part_stride,
                                   long bias_off, int bias_on_fat, int want_bias, ThinGeom g, long pix_per_block) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CV = g.CF >> 3;
@@ -152,11 +152,11 @@ __global__ void thin_outer_kernel(const TF* __restrict__ fat, const TT* __restri
   const long P = (long)g.N * g.H * g.W;
   const long f_beg = (long)blockIdx.x * pix_per_block;
   const long f_end = min(P, f_beg + pix_per_block);
-  float acc[OUT_MAX_KW][CT][8];
+  float acc[KW][CT][8];
   float bsum[8];
   float tsum[CT];
 #pragma unroll
-  for (int s = 0; s < OUT_MAX_KW; ++s)
+  for (int s = 0; s < KW; ++s)
 #pragma unroll
     for (int c = 0; c < CT; ++c)
 #pragma unroll
@@ -183,8 +183,7 @@ __global__ void thin_outer_kernel(const TF* __restrict__ fat, const TT* __restri
     const int hh = h + g.dsign * (r - g.dh0);
     if (hh < 0 || hh >= g.H) continue;
 #pragma unroll
-    for (int s = 0; s < OUT_MAX_KW; ++s) {
-      if (s >= g.kw) break;
+    for (int s = 0; s < KW; ++s) {
       const int ww = wq + g.dsign * (s - g.dw0);
       if (ww < 0 || ww >= g.W) continue;
       const TT* tp = thin + (((n * g.H + hh) * g.W + ww) * g.tp + g.to);
@@ -198,8 +197,7 @@ __global__ void thin_outer_kernel(const TF* __restrict__ fat, const TT* __restri
   }
   float* out = part + (long)blockIdx.x * part_stride;
 #pragma unroll
-  for (int s = 0; s < OUT_MAX_KW; ++s) {
-    if (s >= g.kw) break;
+  for (int s = 0; s < KW; ++s) {
 #pragma unroll
     for (int c = 0; c < CT; ++c)
 #pragma unroll

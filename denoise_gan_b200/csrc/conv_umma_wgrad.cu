@@ -231,6 +231,7 @@ struct Plan {
   Lat lat[MAX_SRC];
   int n_taps, n_src;
   int kc, kco, n_chunks, nb, gpc, zblocks, yblocks, splits, has_bias;
+  uint32_t slack;
 };
 
 int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p, int has_bias,
@@ -281,7 +282,18 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   if (pl->n_chunks == 1) n_groups = (pl->n_taps + 1) / 2 + pl->n_src;  // upper bound for tap stacking
   const int cout = dy->c;
   const uint32_t budget = SMEM_LIMIT - 4096;
-  const uint32_t fixed = (has_bias ? 128u * pl->kc * 2 : 0u) + max_chunk;  // ones tile + slack for padding atoms
+  // padding atoms (M rows beyond the valid taps/chunks) read shared memory past their group: keep a slack region
+  bool padding = false;
+  if (pl->n_chunks > 1) padding = (pl->n_chunks % atoms) != 0;
+  else if (atoms > 2) padding = true;
+  else
+    for (int s = 0; s < pl->n_src; ++s) {
+      int cnt = 0;
+      for (int t = 0; t < pl->n_taps; ++t) cnt += pl->taps[t].src == s;
+      padding = padding || (cnt % atoms) != 0;
+    }
+  pl->slack = padding ? max_chunk : 0;
+  const uint32_t fixed = (has_bias ? 128u * pl->kc * 2 : 0u) + pl->slack;  // ones tile + slack
   auto fits = [&](int nb) { return 2 * ((halo + 128u * nb * 2 + 1023u) & ~1023u) + fixed <= budget; };
   int best_nb = 0;
   for (int nb = cout > 256 ? 256 : cout; nb >= 16; nb -= 16) {
@@ -444,9 +456,8 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     P.groups_per_cta = pl.gpc;
     const int zblocks = (ng + pl.gpc - 1) / pl.gpc;
     // shared memory: stages + ones tile + slack for padding atoms
-    const uint32_t ones_bytes = 128u * kc * 2;
-    uint32_t slack = 0;
-    for (int s = 0; s < pl.n_src; ++s) slack = P.chunk_bytes[s] > slack ? P.chunk_bytes[s] : slack;
+    const uint32_t ones_bytes = P.has_bias ? 128u * kc * 2 : 0u;
+    const uint32_t slack = pl.slack;
     const uint32_t budget = SMEM_LIMIT - 4096;
     DG_REQUIRE(2 * P.stage_bytes + ones_bytes + slack <= budget, "%s: tile does not fit shared memory", name);
     int n_stages = (int)((budget - ones_bytes - slack) / P.stage_bytes);

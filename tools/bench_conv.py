@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Micro-benchmark of single convolution launches through the C ABI (CUDA-event timing; inputs rotate
+through enough buffers to exceed the 126 MB L2).  Used to fill the per-kernel roofline table in
+DESIGN.md and as the short command for `ncu --set full` captures.
+
+    python tools/bench_conv.py [--only body_fwd] [--iters 20]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from denoise_gan_b200 import _lib as L  # noqa: E402
+
+CASES = {
+    # name: (kind, N, H, W, cin, cout, k, stride)
+    "body_fwd": ("fwd", 16, 96, 96, 64, 64, 3, 1),
+    "body_dgrad": ("dgrad", 16, 96, 96, 64, 64, 3, 1),
+    "body_wgrad": ("wgrad", 16, 96, 96, 64, 64, 3, 1),
+    "up1_fwd": ("fwd", 16, 96, 96, 64, 256, 3, 1),
+    "up2_fwd": ("fwd", 16, 192, 192, 64, 256, 3, 1),
+    "up2_dgrad": ("dgrad", 16, 192, 192, 64, 256, 3, 1),
+    "up2_wgrad": ("wgrad", 16, 192, 192, 64, 256, 3, 1),
+    "d3_fwd": ("fwd", 16, 192, 192, 32, 32, 3, 1),
+    "d2_fwd_s2": ("fwd", 16, 384, 384, 32, 32, 3, 2),
+    "d3_wgrad": ("wgrad", 16, 192, 192, 32, 32, 3, 1),
+    "vgg_256": ("fwd", 16, 96, 96, 256, 256, 3, 1),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--sets", type=int, default=6)
+    args = ap.parse_args()
+    lib = L.load(); ctx = L.ctx(0); st = L.stream_ptr()
+    peak = 1393.4
+    if os.path.exists("MEASURED_PEAKS.json"):
+        peak = json.load(open("MEASURED_PEAKS.json"))["bf16_tflops"]
+    for name, (kind, N, H, W, cin, cout, k, s) in CASES.items():
+        if args.only and name not in args.only.split(","):
+            continue
+        Ho, Wo = H // s, W // s
+        pt = max((Ho - 1) * s + k - H, 0) // 2
+        cp = L.DgConvParams(k, k, s, pt, pt, 0, 0.0)
+        xs = [torch.randn(N, H, W, cin, device="cuda").to(torch.bfloat16) for _ in range(args.sets)]
+        ys = [torch.randn(N, Ho, Wo, cout, device="cuda").to(torch.bfloat16) for _ in range(args.sets)]
+        w = torch.randn(k, k, cin, cout, device="cuda") * 0.05
+        pk0 = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda"); pk1 = torch.empty_like(pk0)
+        L.check(lib.dg_umma_pack_weights(ctx, w.data_ptr(), pk0.data_ptr(), k, k, cin, cout, 0, st))
+        L.check(lib.dg_umma_pack_weights(ctx, w.data_ptr(), pk1.data_ptr(), k, k, cin, cout, 1, st))
+        dw = torch.empty_like(w); db = torch.empty(cout, device="cuda")
+        tx0, ty0 = L.tensor(xs[0]), L.tensor(ys[0])
+        nb = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx0), C.byref(ty0), C.byref(cp))
+        wk = torch.empty(max(nb, 16), dtype=torch.uint8, device="cuda")
+
+        def run(i):
+            tx, ty = L.tensor(xs[i % args.sets]), L.tensor(ys[i % args.sets])
+            if kind == "fwd":
+                L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk0.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
+            elif kind == "dgrad":
+                L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(ty), pk1.data_ptr(), None, C.byref(tx), C.byref(cp), st))
+            else:
+                L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(ty), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, st))
+
+        for i in range(3):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.iters):
+            run(i)
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / args.iters
+        flops = 2.0 * N * Ho * Wo * k * k * cin * cout
+        byts = 2.0 * N * (H * W * cin + Ho * Wo * cout)
+        print(json.dumps({"case": name, "us": round(us, 2), "tflops": round(flops / us / 1e6, 1), "frac_of_bf16_peak": round(flops / us / 1e6 / peak, 3),
+                          "algo_GBs": round(byts / us / 1e3, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
