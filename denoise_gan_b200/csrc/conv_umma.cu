@@ -65,11 +65,89 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v, float alpha) {
+  if (ACT == DG_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (ACT == DG_ACT_LRELU) return v >= 0.f ? v : alpha * v;
+  if (ACT == DG_ACT_TANH) return tanhf(v);
+  if (ACT == DG_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+// one 16-column group of one accumulator row: + bias, activation, store
+template <int ACT, bool F32>
+__device__ __forceinline__ void epi_store16(const uint32_t (&v)[16], const float* __restrict__ bs, float alpha, void* out, long elem) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (bs) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] += bs[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = act_fn<ACT>(f[j], alpha);
+  if (F32) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  } else {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + elem);
+    dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+  }
+}
+
+template <int ACT, bool F32>
+__device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t tmem, int q, int lane, int nb0, int total_tiles,
+                                              const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty) {
+  const int m_idx = q * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+    const int tw = tile % P.tiles_w;
+    const int t2 = tile / P.tiles_w;
+    const int th = t2 % P.tiles_h;
+    const int n = t2 / P.tiles_h;
+    mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
+    tc_fence_after();
+    for (int m = 0; m < P.mt; ++m) {
+      const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
+      const int pw = tw * 8 + (m_idx & 7);
+      const bool valid = ph < P.out_h && pw < P.out_w;
+      const long pix = (long)n * P.out_sn + (long)ph * P.out_sh + (long)pw * P.out_sw + nb0;
+      const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.mt + m) * P.nb);
+      int c0 = 0;
+      for (; c0 + 32 <= P.nb; c0 += 32) {   // two 16-column loads in flight per wait
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x16(acc + c0, v0);
+        tmem_ld_32x16(acc + c0 + 16, v1);
+        tmem_ld_wait();
+        if (valid) {
+          epi_store16<ACT, F32>(v0, bs ? bs + c0 : nullptr, P.alpha, P.out, pix + c0);
+          epi_store16<ACT, F32>(v1, bs ? bs + c0 + 16 : nullptr, P.alpha, P.out, pix + c0 + 16);
+        }
+      }
+      if (c0 < P.nb) {
+        uint32_t v0[16];
+        tmem_ld_32x16(acc + c0, v0);
+        tmem_ld_wait();
+        if (valid) epi_store16<ACT, F32>(v0, bs ? bs + c0 : nullptr, P.alpha, P.out, pix + c0);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
+  }
+}
+
 __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_w;
   __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -178,53 +256,24 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
+    // activation / output type are resolved ONCE per kernel (warp-uniform switch) so the per-element code is
+    // straight-line: TMEM -> registers, + bias (from shared memory), activation, pack, 16-byte stores.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int m_idx = q * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int b = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      int tw = tile % P.tiles_w;
-      int t2 = tile / P.tiles_w;
-      int th = t2 % P.tiles_h;
-      int n = t2 / P.tiles_h;
-      mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
-      tc_fence_after();
-      for (int m = 0; m < P.mt; ++m) {
-        const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
-        const int pw = tw * 8 + (m_idx & 7);
-        const bool valid = ph < P.out_h && pw < P.out_w;
-        const long pix = (long)n * P.out_sn + (long)ph * P.out_sh + (long)pw * P.out_sw + nb0;
-        for (int c0 = 0; c0 < P.nb; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * P.mt + m) * P.nb + c0), v);
-          tmem_ld_wait();
-          if (valid) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = __uint_as_float(v[j]);
-              if (P.bias) x += __ldg(P.bias + nb0 + c0 + j);
-              f[j] = apply_act(x, P.act, P.alpha);
-            }
-            if (P.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix + c0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix + c0);
-              dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                  pack_bf16x2(f[6], f[7]));
-              dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                                  pack_bf16x2(f[14], f[15]));
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
+    if (P.bias)
+      for (int i = tid - 64; i < P.nb; i += 128) bias_s[i] = __ldg(P.bias + nb0 + i);
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    const float* bs = P.bias ? bias_s : nullptr;
+#define DG_EPI(ACT)                                                                                     \
+  if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty); \
+  else epilogue_role<ACT, false>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty);
+    switch (P.act) {
+      case DG_ACT_RELU: DG_EPI(DG_ACT_RELU) break;
+      case DG_ACT_LRELU: DG_EPI(DG_ACT_LRELU) break;
+      case DG_ACT_TANH: DG_EPI(DG_ACT_TANH) break;
+      case DG_ACT_SIGMOID: DG_EPI(DG_ACT_SIGMOID) break;
+      default: DG_EPI(DG_ACT_NONE) break;
     }
+#undef DG_EPI
   }
   tc_fence_before();
   __syncthreads();
@@ -409,7 +458,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);
     if (e != cudaSuccess) DG_FAIL("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     attr_set = true;
   }
