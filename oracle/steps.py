@@ -52,7 +52,7 @@ def srgan_train_step(g, d, vgg, gen_opt, disc_opt, x, y, *, fsrgan=False, acts=N
     gen = M.fsrgan_generator if fsrgan else M.srgan_generator
     gen_output = gen(g, x, True, g_state, acts)                                      # :75
     disc_real = M.patch_discriminator(d, y, True, d_state)                           # :78
-    disc_fake = M.patch_discriminator(d, gen_output, True, d_state)                  # :79
+    disc_fake = M.patch_discriminator(d, gen_output, True, d_state, acts)            # :79 (acts: the FAKE call's layers)
     zero = torch.zeros((), dtype=x.dtype)
     content = M.content_loss(vgg, y, gen_output) if vgg is not None else zero        # :86
     adv = 1e-3 * T.bce_from_logits(disc_fake, 1.0)                                   # :87

@@ -58,6 +58,10 @@ CONV_CASES = [  # (k, stride, padding, cin, cout, N, H, W)
     (1, 1, "same", 64, 3, 2, 7, 9),
     (4, 1, ((1, 1), (1, 1)), 16, 1, 1, 10, 10),
     (3, 2, "same", 5, 7, 1, 7, 9),
+    (3, 1, "same", 3, 32, 4, 64, 64),      # thin-Cin layer at a size that spans many blocks
+    (1, 1, "same", 64, 3, 4, 64, 64),      # thin-Cout head
+    (1, 1, "same", 64, 1, 4, 8, 8),        # logits head
+    (3, 1, "same", 32, 3, 2, 24, 40),      # Fast-SRGAN 3x3 head
 ]
 
 
@@ -477,3 +481,35 @@ def test_umma_conv_wgrad_bf16(L, case):
                                      wk.data_ptr(), nb, st))
     torch.cuda.synchronize()
     assert relerr(dw, 2 * w.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,k", [(3, 32, 3), (64, 3, 1), (64, 1, 1)])
+def test_thin_layers_mixed_dtypes(L, cin, cout, k):
+    """bf16 model: the RGB / logits side of a thin layer is fp32, the wide side bf16 (srgan.py:183,270)."""
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    N, H, W = 3, 40, 24
+    x_dt = torch.float32 if cin <= 4 else torch.bfloat16
+    y_dt = torch.float32 if cout <= 4 else torch.bfloat16
+    rx = (lambda t: t.float().double()) if x_dt == torch.float32 else _bf16_round
+    ry = (lambda t: t.float().double()) if y_dt == torch.float32 else _bf16_round
+    x = rx(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = (torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * 0.2).float().double()
+    b = torch.randn(cout, generator=g, dtype=torch.float64).float().double()
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = OT.conv2d(xr, wr, br)
+    gy = ry(torch.randn(y_ref.shape, generator=g, dtype=torch.float64))
+    (y_ref * gy).sum().backward()
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same")
+    xd, wd, bd, gyd = dev(x, x_dt), dev(w), dev(b), dev(gy, y_dt)
+    y = torch.empty(y_ref.shape, device="cuda", dtype=y_dt)
+    tx, ty, tg = L.tensor(xd), L.tensor(y), L.tensor(gyd)
+    L.check(lib.dg_conv2d_fwd(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), st))
+    assert relerr(y, y_ref) < (1e-5 if y_dt == torch.float32 else 1e-2)
+    dx = torch.empty_like(xd); tdx = L.tensor(dx)
+    L.check(lib.dg_conv2d_dgrad(ctx, C.byref(tg), wd.data_ptr(), None, C.byref(tdx), C.byref(cp), st))
+    assert relerr(dx, xr.grad) < (1e-5 if x_dt == torch.float32 else 1e-2)
+    dw = torch.empty_like(wd); db = torch.empty_like(bd)
+    nb = lib.dg_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tg), C.byref(cp)); wk = ws(nb)
+    L.check(lib.dg_conv2d_wgrad(ctx, C.byref(tx), C.byref(tg), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, st))
+    assert relerr(dw, wr.grad) < 1e-5 and relerr(db, br.grad) < 1e-5

@@ -75,21 +75,25 @@ def test_srgan_step_fp32_layers_grads_losses(vgg):
     torch.cuda.synchronize()
     g1, d1, outs = oracle_steps(g0, d0, v0, [x], [y])
     losses, acts, out = outs[0]
-    # per-layer gradients of the generator loss w.r.t. activations (backward order: last layer first)
-    n_g = 0
-    for name in reversed(list(out["act_grads"].keys())):
-        if name in rec and rec[name].seq in grec:
-            e = relerr(grec[rec[name].seq], out["act_grads"][name])
-            assert e < 1e-4, f"activation gradient {name}: {e}"
-            n_g += 1
-    assert n_g >= 15
     checked = 0
+    act_report = []
     for name, ref in acts.items():
         if name in rec:
-            e = relerr(rec[name].t, ref)
-            assert e < 1e-5, f"activation {name}: {e}"
+            act_report.append((name, relerr(rec[name].t, ref)))
             checked += 1
+    print("fp32 activation errors:", [(n, float(f"{e:.2e}")) for n, e in act_report])
+    # per-layer gradients of the generator loss w.r.t. activations (backward order: last layer first)
+    grad_report = []
+    for name in reversed(list(out["act_grads"].keys())):
+        if name in rec and rec[name].seq in grec:
+            grad_report.append((name, relerr(grec[rec[name].seq], out["act_grads"][name])))
+    print("fp32 activation-gradient errors (backward order):", [(n, float(f"{e:.2e}")) for n, e in grad_report])
+    for name, e in act_report:
+        assert e < 1e-5, f"activation {name}: {e}"
     assert checked >= 20
+    for name, e in grad_report:
+        assert e < 1e-4, f"activation gradient {name}: {e}"
+    assert len(grad_report) >= 15
     assert relerr(r["gen_output"].t, out["gen_output"]) < 1e-5
     assert relerr(r["disc_real"].t, out["disc_real"]) < 1e-5
     assert relerr(r["disc_fake"].t, out["disc_fake"]) < 1e-5
@@ -134,6 +138,7 @@ def test_srgan_step_bf16_tensor_core_path():
         if name in rec and name.startswith("g/"):
             e = relerr(rec[name].t, ref)
             assert e < 2e-2, f"activation {name}: {e}"
+    print("bf16 activation errors:", [(n, round(relerr(rec[n].t, ref), 4)) for n, ref in acts.items() if n in rec])
     assert relerr(r["gen_output"].t, out["gen_output"]) < 2e-2
     # 8 more bf16 layers with batch-2 BatchNorm on top of the generator error
     assert relerr(r["disc_fake"].t, out["disc_fake"]) < 0.1
