@@ -23,40 +23,58 @@ def _rec(acts, name, x):
 
 
 # ----------------------------------------------------------------------------- SRGAN
-def srgan_generator(p, x, training=True, state_out=None, acts=None, scale=4):
-    """srgan.py:129-185."""
+def bf16_quant(t):
+    """Storage rounding of the bf16 path (straight-through for autograd): what the CUDA kernels do when
+    they write an activation to HBM.  Used to build a bf16-EMULATING oracle whose only differences from
+    the tensor-core path are accumulation order and gradient storage rounding."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _ident(t):
+    return t
+
+
+def _wq(w, q):
+    """tensor-core layers consume bf16 copies of the kernels (Cin and Cout multiples of 16)."""
+    return q(w) if (w.shape[2] % 16 == 0 and w.shape[3] % 16 == 0) else w
+
+
+def srgan_generator(p, x, training=True, state_out=None, acts=None, scale=4, q=None):
+    """srgan.py:129-185.  `q` (optional) rounds every stored activation, emulating the bf16 path."""
+    q = q or _ident
     bn = lambda t, name: T.batch_norm(t, p, name, training, state_out, momentum=0.99, eps=1e-3)
-    n = T.conv2d(x, p["g/conv_in/kernel"])                                   # :154
+    n = q(T.conv2d(x, p["g/conv_in/kernel"]))                                # :154
     n = bn(n, "g/bn_in")                                                     # :155
-    n = T.prelu(n, p["g/prelu_in/alpha"])                                    # :157
+    n = q(T.prelu(n, p["g/prelu_in/alpha"]))                                 # :157
     temp = _rec(acts, "g/prelu_in", n)
     for i in range(16):                                                      # :161-170
-        nn = T.conv2d(n, p[f"g/res{i}/conv1/kernel"])
-        nn = torch.relu(bn(nn, f"g/res{i}/bn1"))
-        nn = T.conv2d(nn, p[f"g/res{i}/conv2/kernel"])
+        nn = q(T.conv2d(n, _wq(p[f"g/res{i}/conv1/kernel"], q)))
+        nn = q(torch.relu(bn(nn, f"g/res{i}/bn1")))
+        nn = q(T.conv2d(nn, _wq(p[f"g/res{i}/conv2/kernel"], q)))
         nn = bn(nn, f"g/res{i}/bn2")
-        n = _rec(acts, f"g/res{i}/add", n + nn)
-    n = T.conv2d(n, p["g/conv_post/kernel"])                                 # :172
-    n = bn(n, "g/bn_post")
-    n = _rec(acts, "g/post_add", n + temp)                                   # :175
+        n = _rec(acts, f"g/res{i}/add", q(n + nn))
+    n2 = q(T.conv2d(n, _wq(p["g/conv_post/kernel"], q)))                     # :172
+    n2 = bn(n2, "g/bn_post")
+    n = _rec(acts, "g/post_add", q(n2 + temp))                               # :175
     for j in range(scale // 2):                                              # :179-180, deconv2d :134-147
-        u = T.conv2d(n, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"])
+        u = q(T.conv2d(n, _wq(p[f"g/up{j}/conv/kernel"], q), p[f"g/up{j}/conv/bias"]))
         u = T.depth_to_space(u, 2)
-        n = _rec(acts, f"g/up{j}/prelu", T.prelu(u, p[f"g/up{j}/prelu/alpha"]))
+        n = _rec(acts, f"g/up{j}/prelu", q(T.prelu(u, p[f"g/up{j}/prelu/alpha"])))
     out = T.conv2d(n, p["g/conv_out/kernel"], p["g/conv_out/bias"])          # :182 (1x1)
-    return _rec(acts, "g/tanh", torch.tanh(out))                             # :183
+    return _rec(acts, "g/tanh", torch.tanh(out))                             # :183 (fp32 output)
 
 
-def patch_discriminator(p, x, training=True, state_out=None, acts=None, sigmoid=False, prefix="d"):
+def patch_discriminator(p, x, training=True, state_out=None, acts=None, sigmoid=False, prefix="d", q=None):
     """The 9-conv discriminator shared by srgan.py:232-272, fsrgan.py:222-258 (logits) and
     autoencoder.py:190-229 (sigmoid)."""
+    q = q or _ident
     filters_strides = [(32, 1), (32, 2), (32, 1), (32, 2), (64, 1), (64, 2), (64, 1), (64, 2)]
     d = x
     for i, (_, s) in enumerate(filters_strides, start=1):
-        d = T.conv2d(d, p[f"{prefix}/conv{i}/kernel"], p[f"{prefix}/conv{i}/bias"], stride=s)
+        d = T.conv2d(d, _wq(p[f"{prefix}/conv{i}/kernel"], q), p[f"{prefix}/conv{i}/bias"], stride=s)
         if i > 1:
-            d = T.batch_norm(d, p, f"{prefix}/bn{i}", training, state_out, momentum=0.8, eps=1e-3)
-        d = _rec(acts, f"{prefix}/lrelu{i}", T.leaky_relu(d, 0.2))
+            d = T.batch_norm(q(d), p, f"{prefix}/bn{i}", training, state_out, momentum=0.8, eps=1e-3)
+        d = _rec(acts, f"{prefix}/lrelu{i}", q(T.leaky_relu(d, 0.2)))
     logits = T.conv2d(d, p[f"{prefix}/logits/kernel"], p[f"{prefix}/logits/bias"])
     if sigmoid:
         logits = torch.sigmoid(logits)

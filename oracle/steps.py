@@ -44,15 +44,16 @@ def _finish(g, d, g_state, d_state, gen_grads, disc_grads, gen_opt, disc_opt):
             d[k].copy_(v)
 
 
-def srgan_train_step(g, d, vgg, gen_opt, disc_opt, x, y, *, fsrgan=False, acts=None, out=None):
+def srgan_train_step(g, d, vgg, gen_opt, disc_opt, x, y, *, fsrgan=False, acts=None, out=None, q=None):
     """train_srgan.py:61-118 (fsrgan=False) and train_fsrgan.py:61-120 (fsrgan=True).
     D's BN moving statistics are updated twice (real call, then fake call)."""
     _prep(g); _prep(d)
     g_state, d_state = {}, {}
     gen = M.fsrgan_generator if fsrgan else M.srgan_generator
-    gen_output = gen(g, x, True, g_state, acts)                                      # :75
-    disc_real = M.patch_discriminator(d, y, True, d_state)                           # :78
-    disc_fake = M.patch_discriminator(d, gen_output, True, d_state, acts)            # :79 (acts: the FAKE call's layers)
+    qkw = {} if (q is None or fsrgan) else {"q": q}
+    gen_output = gen(g, x, True, g_state, acts, **qkw)                               # :75
+    disc_real = M.patch_discriminator(d, y, True, d_state, q=q)                      # :78
+    disc_fake = M.patch_discriminator(d, gen_output, True, d_state, acts, q=q)       # :79 (acts: the FAKE call's layers)
     zero = torch.zeros((), dtype=x.dtype)
     content = M.content_loss(vgg, y, gen_output) if vgg is not None else zero        # :86
     adv = 1e-3 * T.bce_from_logits(disc_fake, 1.0)                                   # :87

@@ -50,6 +50,7 @@ struct ProbeCase {
   uint32_t idesc;
   int n_cols;
   uint32_t dump_bytes;
+  int repeat;  // timing mode: issue the MMA list this many times and report cycles
 };
 
 constexpr int SMEM_DATA = 160 * 1024;
@@ -106,19 +107,26 @@ probe_kernel(const __grid_constant__ Maps maps, const ProbeCase* __restrict__ pc
       status[0] = 1;  // TMA never completed (tx byte mismatch?)
     } else {
       tc_fence_after();
+      const int reps = pc.repeat > 0 ? pc.repeat : 1;
+      long long t0 = clock64();
+      for (int rep = 0; rep < reps; ++rep)
       for (int i = 0; i < pc.n_mma; ++i) {
         uint32_t a_addr = base + pc.mma[i].a_off, b_addr = base + pc.mma[i].b_off;
         uint32_t a_bo = pc.a_bo_mode ? ((a_addr >> 7) & 7) : 0;
         uint32_t b_bo = pc.b_bo_mode ? ((b_addr >> 7) & 7) : 0;
         uint64_t ad = make_smem_desc(a_addr, pc.a_lbo, pc.a_sbo, pc.a_layout, a_bo);
         uint64_t bd = make_smem_desc(b_addr, pc.b_lbo, pc.b_sbo, pc.b_layout, b_bo);
-        umma_f16(tmem, ad, bd, pc.idesc, i > 0 ? 1u : 0u);
+        umma_f16(tmem, ad, bd, pc.idesc, (i > 0 || rep > 0) ? 1u : 0u);
       }
+      long long t1 = clock64();
       umma_commit(bar_mma);
       if (!bounded_wait(bar_mma, 0)) {
         ok_flag = 0;
         status[0] = 2;  // MMA never committed
       }
+      long long t2 = clock64();
+      status[1] = (int)(t1 - t0);
+      status[2] = (int)(t2 - t0);
     }
   }
   __syncthreads();
@@ -158,8 +166,9 @@ static CUtensorMap make_map(void* ptr, int rank, const uint64_t* dims, const uin
 }
 
 static float gen(int salt, long r, int c) {
-  long v = (r * 7 + c * 13 + (r * (c + salt)) % 5 + salt * 3) % 7;
-  return (float)(v - 3);
+  uint64_t x = (uint64_t)r * 0x9E3779B97F4A7C15ull + (uint64_t)c * 0xC2B2AE3D27D4EB4Full + (uint64_t)salt * 0x165667B19E3779F9ull;
+  x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+  return (float)((long)(x % 7) - 3);
 }
 
 struct HostTensor {
@@ -246,7 +255,7 @@ int main() {
   float* d_out; uint32_t* d_dump; int* d_status; ProbeCase* d_pc;
   CK(cudaMalloc(&d_out, 128 * 256 * 4));
   CK(cudaMalloc(&d_dump, SMEM_DATA));
-  CK(cudaMalloc(&d_status, 4));
+  CK(cudaMalloc(&d_status, 16));
   CK(cudaMalloc(&d_pc, sizeof(ProbeCase)));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DATA + 1024));
 
@@ -257,7 +266,7 @@ int main() {
   auto run = [&](const std::string& name, ProbeCase pc, int M, std::function<float(int, int)> expect,
                  const Maps& mp, bool lane_search = false) {
     CK(cudaMemset(d_out, 0xff, 128 * 256 * 4));
-    CK(cudaMemset(d_status, 0, 4));
+    CK(cudaMemset(d_status, 0, 16));
     CK(cudaMemcpy(d_pc, &pc, sizeof(pc), cudaMemcpyHostToDevice));
     probe_kernel<<<1, 128, SMEM_DATA + 1024>>>(mp, d_pc, d_out, d_dump, d_status);
     cudaError_t e = cudaDeviceSynchronize();
@@ -449,6 +458,42 @@ int main() {
           for (int k = 0; k < 64; ++k) acc += img(0, 2 * h - 1, 2 * w - 1, k) * Bm.at(n, k);
           return acc;
         }, m2);
+  }
+
+  // ---- T: tensor-pipe throughput for the descriptor styles the conv kernels use (cycles per MMA, single CTA)
+  {
+    struct TCase { const char* name; int N; int a_mn, b_mn; uint32_t a_off0, a_kstep, a_sbo, a_lbo, b_kstep, b_sbo, b_lbo; int nk; };
+    const TCase tc[] = {
+        {"t_kmajor_aligned_N64", 64, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4},
+        {"t_kmajor_shift1_N64", 64, 0, 0, 128, 32, 1024, 16, 32, 1024, 16, 4},
+        {"t_kmajor_halo10_tap11_N64", 64, 0, 0, 11 * 128, 32, 1280, 16, 32, 1024, 16, 4},
+        {"t_kmajor_aligned_N128", 128, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4},
+        {"t_kmajor_halo10_tap11_N128", 128, 0, 0, 11 * 128, 32, 1280, 16, 32, 1024, 16, 4},
+        {"t_kmajor_aligned_N256", 256, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4},
+        {"t_mnmajor_aligned_N64", 64, 1, 1, 0, 2048, 1024, 24576, 2048, 1024, 32768, 8},
+        {"t_mnmajor_shift11_N64", 64, 1, 1, 11 * 128, 2560, 1280, 128, 2048, 1024, 32768, 8},
+    };
+    for (const TCase& T : tc) {
+      ProbeCase pc = base_case();
+      pc.loads[pc.n_loads++] = {0, 2, 0, 0, 0, 0, 0};
+      pc.tx_bytes = 256 * 128;
+      add_B64(pc, 5, 0, 256 * 128);
+      pc.n_cols = T.N;
+      pc.idesc = sm100::make_idesc_bf16(128, T.N, T.a_mn, T.b_mn);
+      pc.a_sbo = T.a_sbo; pc.a_lbo = T.a_lbo; pc.b_sbo = T.b_sbo; pc.b_lbo = T.b_lbo;
+      for (int k = 0; k < T.nk; ++k) pc.mma[pc.n_mma++] = {T.a_off0 + (uint32_t)k * T.a_kstep, B_OFF + (uint32_t)k * T.b_kstep};
+      pc.repeat = 256;
+      CK(cudaMemset(d_status, 0, 16));
+      CK(cudaMemcpy(d_pc, &pc, sizeof(pc), cudaMemcpyHostToDevice));
+      probe_kernel<<<1, 128, SMEM_DATA + 1024>>>(maps, d_pc, d_out, d_dump, d_status);
+      CK(cudaDeviceSynchronize());
+      int st[4];
+      CK(cudaMemcpy(st, d_status, 16, cudaMemcpyDeviceToHost));
+      int n = pc.n_mma * pc.repeat;
+      printf("{\"timing\": \"%s\", \"status\": %d, \"mmas\": %d, \"issue_cycles_per_mma\": %.1f, \"total_cycles_per_mma\": %.1f}\n", T.name, st[0], n,
+             (double)st[1] / n, (double)st[2] / n);
+      fflush(stdout);
+    }
   }
   printf("{\"summary\": {\"pass\": %d, \"fail\": %d}}\n", n_pass, n_fail);
   return 0;

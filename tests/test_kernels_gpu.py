@@ -62,6 +62,8 @@ CONV_CASES = [  # (k, stride, padding, cin, cout, N, H, W)
     (1, 1, "same", 64, 3, 4, 64, 64),      # thin-Cout head
     (1, 1, "same", 64, 1, 4, 8, 8),        # logits head
     (3, 1, "same", 32, 3, 2, 24, 40),      # Fast-SRGAN 3x3 head
+    (3, 1, "same", 32, 64, 4, 16, 16),     # discriminator conv5 shape (Cin < tile width)
+    (3, 2, "same", 64, 64, 4, 16, 16),
 ]
 
 
@@ -226,9 +228,9 @@ def test_umma_rejects_bad_shapes(L):
                                                      (32, "lrelu", False, False), (64, None, True, False),
                                                      (512, "relu", False, True), (48, "tanh", False, False)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_bn_act_fwd_bwd(L, C_, act, with_res, dropout, dtype):
+@pytest.mark.parametrize("N,H,W", [(2, 6, 5), (4, 16, 16), (3, 40, 33)])
+def test_bn_act_fwd_bwd(L, C_, act, with_res, dropout, dtype, N, H, W):
     g = torch.Generator().manual_seed(C_)
-    N, H, W = 2, 6, 5
     rnd = (lambda t: t) if dtype == torch.float32 else _bf16_round
     x = rnd(torch.randn(N, H, W, C_, generator=g, dtype=torch.float64) * 1.5 + 0.3)
     gamma = torch.randn(C_, generator=g, dtype=torch.float64) * 0.2 + 1

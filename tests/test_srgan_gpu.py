@@ -51,7 +51,7 @@ def make(fp16, vgg, crop=32, batch=2, seed=0):
     return model, g0, d0, v0, x, y
 
 
-def oracle_steps(g0, d0, v0, xs, ys, dtype=torch.float64):
+def oracle_steps(g0, d0, v0, xs, ys, dtype=torch.float64, q=None):
     g = {k: v.to(dtype).clone() for k, v in g0.items()}
     d = {k: v.to(dtype).clone() for k, v in d0.items()}
     vgg = {k: v.to(dtype) for k, v in v0.items()} if v0 is not None else None
@@ -59,7 +59,7 @@ def oracle_steps(g0, d0, v0, xs, ys, dtype=torch.float64):
     outs = []
     for x, y in zip(xs, ys):
         acts, out = {}, {}
-        losses = OS.srgan_train_step(g, d, vgg, go, do, x.to(dtype), y.to(dtype), acts=acts, out=out)
+        losses = OS.srgan_train_step(g, d, vgg, go, do, x.to(dtype), y.to(dtype), acts=acts, out=out, q=q)
         outs.append((losses, acts, out))
     return g, d, outs
 
@@ -117,9 +117,11 @@ def test_srgan_step_fp32_layers_grads_losses(vgg):
 
 
 def test_srgan_step_bf16_tensor_core_path():
+    """bf16 path against (a) the float64 oracle — the north-star 2e-2 bound on generator activations — and
+    (b) a bf16-EMULATING oracle (same storage-rounding points, float64 arithmetic in between), which
+    separates kernel errors from the rounding noise that 45 bf16 layers legitimately accumulate."""
     from denoise_gan_b200.train_common import gan_step
-    # bf16 needs well-conditioned BatchNorm statistics: at crop 32 / batch 2 the last D layers normalise over 8
-    # samples and amplify rounding ~1000x (the fp32 test shows the same factor); crop 128 / batch 4 gives >= 256.
+    from oracle.models import bf16_quant
     model, g0, d0, v0, x, y = make(fp16=1, vgg=False, crop=128, batch=4)
     assert model.engine.use_umma
     rec, grec = {}, {}
@@ -128,24 +130,34 @@ def test_srgan_step_bf16_tensor_core_path():
     r = gan_step(model, x.cuda(), y.cuda(), from_logits=True, disc_scale=1.0)
     torch.cuda.synchronize()
     _, _, outs = oracle_steps(g0, d0, v0, [x], [y])
+    _, _, outs_q = oracle_steps(g0, d0, v0, [x], [y], q=bf16_quant)
     losses, acts, out = outs[0]
-    report = []
-    for name in reversed(list(out["act_grads"].keys())):
-        if name in rec and rec[name].seq in grec:
-            report.append((name, round(relerr(grec[rec[name].seq], out["act_grads"][name]), 4)))
-    print("bf16 activation-gradient errors (backward order):", report)
-    for name, ref in acts.items():
-        if name in rec and name.startswith("g/"):
-            e = relerr(rec[name].t, ref)
-            assert e < 2e-2, f"activation {name}: {e}"
-    print("bf16 activation errors:", [(n, round(relerr(rec[n].t, ref), 4)) for n, ref in acts.items() if n in rec])
+    losses_q, acts_q, out_q = outs_q[0]
+    act64 = [(n, relerr(rec[n].t, ref)) for n, ref in acts.items() if n in rec]
+    actq = [(n, relerr(rec[n].t, ref)) for n, ref in acts_q.items() if n in rec]
+    gq = [(n, relerr(grec[rec[n].seq], out_q["act_grads"][n])) for n in reversed(list(out_q["act_grads"].keys()))
+          if n in rec and rec[n].seq in grec]
+    g64 = [(n, relerr(grec[rec[n].seq], out["act_grads"][n])) for n in reversed(list(out["act_grads"].keys()))
+           if n in rec and rec[n].seq in grec]
+    print("bf16 activations vs fp64 oracle:", [(n, round(e, 4)) for n, e in act64])
+    print("bf16 activations vs bf16-emulating oracle:", [(n, round(e, 4)) for n, e in actq])
+    print("bf16 activation gradients vs bf16-emulating oracle (backward order):", [(n, round(e, 4)) for n, e in gq])
+    print("bf16 activation gradients vs fp64 oracle (backward order):", [(n, round(e, 4)) for n, e in g64])
+    for n, e in act64:
+        if n.startswith("g/"):
+            assert e < 2e-2, f"activation {n} vs fp64 oracle: {e}"
+    for n, e in actq:
+        assert e < 2e-2, f"activation {n} vs bf16-emulating oracle: {e}"
     assert relerr(r["gen_output"].t, out["gen_output"]) < 2e-2
-    # 8 more bf16 layers with batch-2 BatchNorm on top of the generator error
-    assert relerr(r["disc_fake"].t, out["disc_fake"]) < 0.1
+    assert relerr(r["disc_fake"].t, out_q["disc_fake"]) < 2e-2
+    for n, e in gq:
+        assert e < 5e-2, f"activation gradient {n} vs bf16-emulating oracle: {e}"
     gg = model.gen_params.grads()
-    bad = [(n, relerr(gg[n], ref)) for n, ref in out["gen_grads"].items() if relerr(gg[n], ref) > 0.15]
-    assert not bad, bad[:5]
-    for n, ref in zip(LOSS_NAMES, losses):
+    pg = [(n, relerr(gg[n], ref)) for n, ref in out_q["gen_grads"].items()]
+    print("bf16 generator parameter-gradient errors vs bf16-emulating oracle (worst 8):", sorted(pg, key=lambda t: -t[1])[:8])
+    for n, e in pg:
+        assert e < 0.1, f"gen grad {n}: {e}"
+    for n, ref in zip(LOSS_NAMES, losses_q):
         assert abs(r[n].item() - ref.item()) <= 2e-2 * max(1.0, abs(ref.item())), f"{n}: {r[n].item()} vs {ref.item()}"
 
 
