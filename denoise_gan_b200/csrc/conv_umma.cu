@@ -58,11 +58,16 @@ struct UmmaConvParams {
   int act;
   float alpha;
   uint32_t layout, idesc;
+  long long* dbg;  // optional per-role timeline of CTA 0 (tools/conv_timeline.py); nullptr in production
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void dbg_mark(const UmmaConvParams& P, int role, int it, int slot) {
+  if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 16) P.dbg[(role * 16 + it) * 4 + slot] = clock64();
 }
 
 template <int ACT>
@@ -110,8 +115,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
     const int t2 = tile / P.tiles_w;
     const int th = t2 % P.tiles_h;
     const int n = t2 / P.tiles_h;
+    if (q == 0 && lane == 0) dbg_mark(P, 2, it, 0);
     mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
     tc_fence_after();
+    if (q == 0 && lane == 0) dbg_mark(P, 2, it, 1);
     for (int m = 0; m < P.mt; ++m) {
       const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
       const int pw = tw * 8 + (m_idx & 7);
@@ -139,6 +146,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
+    if (q == 0 && lane == 0) dbg_mark(P, 2, it, 2);
   }
 }
 
@@ -201,9 +209,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
         int th = t2 % P.tiles_h;
         int n = t2 / P.tiles_h;
         const int h0 = th * 16 * P.mt, w0 = tw * 8;
+        const int pit = (tile - (int)blockIdx.x) / (int)gridDim.x;
+        dbg_mark(P, 0, pit, 0);
         for (int kc = 0; kc < P.n_chunks; ++kc) {
           const uint32_t full = smem_u32(&bar_a_full[stage]);
           mbar_wait(smem_u32(&bar_a_empty[stage]), phase ^ 1u);
+          if (kc == 0) dbg_mark(P, 0, pit, 1);
           mbar_expect_tx(full, P.stage_tx);
           const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
           for (int s = 0; s < P.n_src; ++s)
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
                           (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
           if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
         }
+        dbg_mark(P, 0, pit, 2);
       }
     }
   } else if (warp == 1) {
@@ -248,13 +260,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        dbg_mark(P, 1, it, 0);
         mbar_wait(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
         tc_fence_after();
+        dbg_mark(P, 1, it, 1);
         const uint32_t acc0 = tmem + (uint32_t)(b * mt) * nb;
         uint32_t accf = 0;
         for (int kc = 0; kc < n_chunks; ++kc) {
           mbar_wait(smem_u32(&bar_a_full[stage]), phase);
           tc_fence_after();
+          if (kc == 0) dbg_mark(P, 1, it, 2);
           const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;
           uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
           const uint32_t b_step = resident ? (uint32_t)n_chunks * wblk16 : wblk16;
@@ -275,6 +290,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(smem_u32(&bar_acc_full[b]));
+        dbg_mark(P, 1, it, 3);
       }
     }
   } else {
@@ -324,6 +340,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     dst[i] = __float2bfloat16(v);
   }
 }
+
+static long long* g_dbg_timeline = nullptr;
 
 inline int kc_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
@@ -477,6 +495,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.out_sn = (long)out->cpitch * out->w * out->h;
   P.out_f32 = out->dtype == DG_F32;
   P.bias = bias; P.act = act; P.alpha = alpha;
+  P.dbg = g_dbg_timeline;
 
   const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + 1024;
   static bool attr_set = false;
@@ -500,6 +519,10 @@ inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 inline int pymod(int a, int b) { return a - floordiv(a, b) * b; }
 
 }  // namespace
+
+// Debug aid: when set to a device buffer of 3*16*4 int64, CTA 0 of every conv launch records clock64() marks
+// (role, tile, slot); pass NULL to switch off.  Not part of the hot path.
+extern "C" void dg_debug_conv_timeline(void* dev_buffer) { g_dbg_timeline = (long long*)dev_buffer; }
 
 extern "C" size_t dg_umma_packed_bytes(int kh, int kw, int cin, int cout, int mode) {
   return (size_t)kh * kw * cin * cout * 2;
