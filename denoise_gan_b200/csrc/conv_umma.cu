@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[256];
-  __shared__ uint32_t tap_a_lo[MAX_TAPS], tap_a_hi[MAX_TAPS], tap_ms[MAX_TAPS];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -229,22 +228,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    // Everything that does not change per tile is folded into per-tap 32-bit descriptor words kept in
-    // shared memory, so issuing one tcgen05.mma costs a handful of integer instructions: the issue rate
-    // of this single thread, not the tensor pipe, was the limiter of the first version (profiles/).
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // The WHOLE warp runs this loop with warp-uniform values (kernel parameters, loop counters) and only
+    // the tcgen05 instructions sit under elect_one(): UTCHMMA takes its descriptors from UNIFORM registers,
+    // and when the loop ran under `if (lane == 0)` every operand went through R2UR with a scoreboard wait
+    // (~200 cycles per MMA measured with tools/conv_timeline.py; the tensor pipe needs one per 32).
+    {
       const int n_taps = P.n_taps, n_chunks = P.n_chunks, mt = P.mt, nbk = P.kc / 16, n_stages = P.n_stages;
       const uint32_t nb = (uint32_t)P.nb, idesc = P.idesc;
       const uint32_t w_sbo = 8u * (uint32_t)P.kc * 2u;
-      const uint32_t b_hi = (uint32_t)make_smem_desc_hi(w_sbo, P.layout);
+      const uint64_t b_hi = make_smem_desc_hi(w_sbo, P.layout) << 32;
       const uint32_t lbo16 = 1u << 16;  // LBO field (ignored for swizzled K-major), 16 bytes
-      for (int t = 0; t < n_taps; ++t) {
-        const int s = P.tap_src[t];
-        tap_a_lo[t] = (P.tap_off[t] >> 4) | lbo16;
-        tap_a_hi[t] = (uint32_t)make_smem_desc_hi(P.a_sbo[s], P.layout);
-        tap_ms[t] = P.mt_stride[s] >> 4;
-      }
       const uint32_t wblk16 = P.w_block_bytes >> 4;
       const uint32_t wres16 = (w_base >> 4) | lbo16;
       const uint32_t wstage16 = (P.w_stage_off >> 4) | lbo16;
@@ -260,37 +254,38 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        dbg_mark(P, 1, it, 0);
+        if (lane == 0) dbg_mark(P, 1, it, 0);
         mbar_wait(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
         tc_fence_after();
-        dbg_mark(P, 1, it, 1);
+        if (lane == 0) dbg_mark(P, 1, it, 1);
         const uint32_t acc0 = tmem + (uint32_t)(b * mt) * nb;
-        uint32_t accf = 0;
         for (int kc = 0; kc < n_chunks; ++kc) {
           mbar_wait(smem_u32(&bar_a_full[stage]), phase);
           tc_fence_after();
-          if (kc == 0) dbg_mark(P, 1, it, 2);
+          if (kc == 0 && lane == 0) dbg_mark(P, 1, it, 2);
           const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;
-          uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
-          const uint32_t b_step = resident ? (uint32_t)n_chunks * wblk16 : wblk16;
-          for (int t = 0; t < n_taps; ++t, b_lo += b_step) {
-            const uint32_t a_lo = sa16 + tap_a_lo[t];
-            const uint64_t a_hi = (uint64_t)tap_a_hi[t] << 32, bh = (uint64_t)b_hi << 32;
-            const uint32_t ms = tap_ms[t];
-            for (int k16 = 0; k16 < nbk; ++k16) {
-              const uint64_t bd = bh | (uint64_t)(b_lo + 2u * k16);
-              uint32_t al = a_lo + 2u * k16;
-              for (int m = 0; m < mt; ++m, al += ms) {
-                umma_f16(acc0 + (uint32_t)m * nb, a_hi | (uint64_t)al, bd, idesc, accf);
+          if (elect_one()) {
+            uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
+            const uint32_t b_step = resident ? (uint32_t)n_chunks * wblk16 : wblk16;
+            for (int t = 0; t < n_taps; ++t, b_lo += b_step) {
+              const int s = P.tap_src[t];
+              const uint32_t a_lo = sa16 + ((P.tap_off[t] >> 4) | lbo16);
+              const uint64_t a_hi = make_smem_desc_hi(P.a_sbo[s], P.layout) << 32;
+              const uint32_t ms = P.mt_stride[s] >> 4;
+              for (int k16 = 0; k16 < nbk; ++k16) {
+                const uint64_t bd = b_hi | (uint64_t)(b_lo + 2u * k16);
+                uint32_t al = a_lo + 2u * k16;
+                const uint32_t accf = (kc | t | k16) != 0 ? 1u : 0u;
+                for (int m = 0; m < mt; ++m, al += ms) umma_f16(acc0 + (uint32_t)m * nb, a_hi | (uint64_t)al, bd, idesc, accf);
               }
-              accf = 1u;
             }
+            umma_commit(smem_u32(&bar_a_empty[stage]));
+            if (kc == n_chunks - 1) umma_commit(smem_u32(&bar_acc_full[b]));
           }
-          umma_commit(smem_u32(&bar_a_empty[stage]));
+          __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&bar_acc_full[b]));
-        dbg_mark(P, 1, it, 3);
+        if (lane == 0) dbg_mark(P, 1, it, 3);
       }
     }
   } else {

@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t grp_lo[MAX_GROUPS], grp_hi[MAX_GROUPS], grp_ks[MAX_GROUPS];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -115,48 +114,55 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // per-group descriptor words are precomputed once (single-thread issue rate is the limiter otherwise)
+    // Whole warp, warp-uniform values, tcgen05 under elect_one(): UTCHMMA reads its descriptors from uniform
+    // registers (see conv_umma.cu).
+    {
       const uint32_t b_sbo = 8u * (uint32_t)P.kco * 2u;      // between 8-pixel rows of the dense dy tile
       const uint32_t b_kstep16 = (16u * (uint32_t)P.kco * 2u) >> 4;   // 16 pixels per MMA
-      const uint32_t b_hi = (uint32_t)make_smem_desc_hi(b_sbo, P.b_layout);
+      const uint64_t b_hi = make_smem_desc_hi(b_sbo, P.b_layout) << 32;
       const uint32_t b_lo0 = ((P.dy_off >> 4) & 0x3FFFu) | (((P.dy_atom_bytes >> 4) & 0x3FFFu) << 16);
       const int ng = g_end - g_begin;
-      for (int g = 0; g < ng; ++g) {
-        const int s = P.g_src[g_begin + g];
-        grp_lo[g] = ((P.g_off[g_begin + g] >> 4) & 0x3FFFu) | (((P.g_lbo[g_begin + g] >> 4) & 0x3FFFu) << 16);
-        grp_hi[g] = (uint32_t)make_smem_desc_hi(P.a_sbo[s], P.a_layout);
-        grp_ks[g] = P.a_kstep[s] >> 4;
-      }
-      const uint32_t ones_hi = (uint32_t)make_smem_desc_hi(8u * P.kc * 2u, P.a_layout);
+      const uint64_t ones_hi = make_smem_desc_hi(8u * P.kc * 2u, P.a_layout) << 32;
       const uint32_t ones_lo0 = (base + P.ones_off) >> 4;
       const uint32_t ones_ks = (16u * P.kc * 2u) >> 4;
       const uint32_t nb = (uint32_t)P.nb, idesc = P.idesc, stage16 = P.stage_bytes >> 4, base16 = base >> 4;
       const int n_stages = P.n_stages;
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t accf = 0;
+      uint32_t first = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         const uint32_t sa16 = base16 + (uint32_t)stage * stage16;
-        for (int j = 0; j < 8; ++j) {
-          const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(sa16 + b_lo0 + (uint32_t)j * b_kstep16);
+        if (elect_one()) {
           for (int g = 0; g < ng; ++g) {
-            const uint64_t ad = ((uint64_t)grp_hi[g] << 32) | (uint64_t)(sa16 + grp_lo[g] + (uint32_t)j * grp_ks[g]);
-            umma_f16(tmem + (uint32_t)g * nb, ad, bd, idesc, accf);
+            const int s = P.g_src[g_begin + g];
+            const uint32_t a_lo = sa16 + (((P.g_off[g_begin + g] >> 4) & 0x3FFFu) | (((P.g_lbo[g_begin + g] >> 4) & 0x3FFFu) << 16));
+            const uint64_t a_hi = make_smem_desc_hi(P.a_sbo[s], P.a_layout) << 32;
+            const uint32_t ks = P.a_kstep[s] >> 4;
+            const uint32_t acc = tmem + (uint32_t)g * nb;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t bd = b_hi | (uint64_t)(sa16 + b_lo0 + (uint32_t)j * b_kstep16);
+              umma_f16(acc, a_hi | (uint64_t)(a_lo + (uint32_t)j * ks), bd, idesc, (first && j == 0) ? 0u : 1u);
+            }
           }
           if (do_bias) {
             // ones tile: 8-pixel groups are 8*kc*2 bytes apart; LBO 0 => every M row reads the same data
-            const uint64_t od = ((uint64_t)ones_hi << 32) | (uint64_t)(ones_lo0 + (uint32_t)j * ones_ks);
-            umma_f16(tmem + (uint32_t)ng * nb, od, bd, idesc, accf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t bd = b_hi | (uint64_t)(sa16 + b_lo0 + (uint32_t)j * b_kstep16);
+              umma_f16(tmem + (uint32_t)ng * nb, ones_hi | (uint64_t)(ones_lo0 + (uint32_t)j * ones_ks), bd, idesc, (first && j == 0) ? 0u : 1u);
+            }
           }
-          accf = 1u;
+          umma_commit(smem_u32(&bar_empty[stage]));
         }
-        umma_commit(smem_u32(&bar_empty[stage]));
+        __syncwarp();
+        first = 0;
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(&bar_done));
+      if (elect_one()) umma_commit(smem_u32(&bar_done));
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -19,6 +19,7 @@ x, y = synthetic_pair(batch, crop, 4, step=0)
 E = model.engine
 rec, grec = {}, {}
 E.record, E.grad_record = rec, grec
+snap = {k: v.cuda().double() for k, v in model.disc_params.export().items()}   # weights BEFORE the Adam update
 gan_step(model, x.cuda(), y.cuda(), from_logits=True, disc_scale=1.0)
 torch.cuda.synchronize()
 by_out = {n.seq: n for n in E.tape}
@@ -36,12 +37,12 @@ for i in range(8, 1, -1):
     g_act = grec[rec[f"d/lrelu{i}"].seq]          # dL/d(lrelu_i)
     g_conv = grec.get(conv_out.seq)                # dL/d(conv_i raw) = bn backward output
     g_in = grec.get(xin.seq)                       # dL/d(conv_i input) = conv dgrad output
-    w = model.disc_params[f"d/conv{i}/kernel"].data.double()
-    gamma = model.disc_params[f"d/bn{i}/gamma"].data.double()
+    w = snap[f"d/conv{i}/kernel"]
+    gamma = snap[f"d/bn{i}/gamma"]
     # reference BN backward in float64 from our own inputs
     xr = conv_out.t.double().requires_grad_(True)
     mean = xr.mean(dim=(0, 1, 2)); var = xr.var(dim=(0, 1, 2), unbiased=False)
-    t = gamma * (xr - mean) * torch.rsqrt(var + 1e-3) + model.disc_params[f"d/bn{i}/beta"].data.double()
+    t = gamma * (xr - mean) * torch.rsqrt(var + 1e-3) + snap[f"d/bn{i}/beta"]
     out = torch.where(t >= 0, t, 0.2 * t)
     (out * g_act.double()).sum().backward()
     e_bn = rel(g_conv, xr.grad) if g_conv is not None else None
