@@ -58,6 +58,7 @@ struct UmmaConvParams {
   int act;
   float alpha;
   uint32_t layout, idesc;
+  int dbg_flags;   // debug experiments (tools/conv_timeline.py): 1 no stores, 2 no epilogue work, 4 no TMA reloads, 8 unshifted taps
   long long* dbg;  // optional per-role timeline of CTA 0 (tools/conv_timeline.py); nullptr in production
 };
 
@@ -128,10 +129,11 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
       int c0 = 0;
       for (; c0 + 32 <= P.nb; c0 += 32) {   // two 16-column loads in flight per wait
         uint32_t v0[16], v1[16];
+        if (P.dbg_flags & 2) continue;
         tmem_ld_32x16(acc + c0, v0);
         tmem_ld_32x16(acc + c0 + 16, v1);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(P.dbg_flags & 1)) {
           epi_store16<ACT, F32>(v0, bs ? bs + c0 : nullptr, P.alpha, P.out, pix + c0);
           epi_store16<ACT, F32>(v1, bs ? bs + c0 + 16 : nullptr, P.alpha, P.out, pix + c0 + 16);
         }
@@ -147,6 +149,29 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
     if (q == 0 && lane == 0) dbg_mark(P, 2, it, 2);
+  }
+}
+
+// Issues the MMAs of one pipeline stage (all taps of one channel chunk).  MT and NBK (= chunk/16) are
+// compile-time so the body is straight-line: one descriptor add per operand per tcgen05.mma.
+template <int MT, int NBK>
+__device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int n_taps, uint32_t sa16, uint32_t lbo16, uint32_t b_lo,
+                                            uint32_t b_step, uint64_t b_hi, uint32_t acc0, uint32_t nb, uint32_t idesc,
+                                            bool not_first_chunk) {
+  for (int t = 0; t < n_taps; ++t, b_lo += b_step) {
+    const int s = P.tap_src[t];
+    const uint32_t a_lo = sa16 + ((((P.dbg_flags & 8) ? 0u : P.tap_off[t]) >> 4) | lbo16);
+    const uint64_t a_hi = make_smem_desc_hi(P.a_sbo[s], P.layout) << 32;
+    const uint32_t ms = P.mt_stride[s] >> 4;
+    const uint32_t acc_rest = (not_first_chunk || t != 0) ? 1u : 0u;
+#pragma unroll
+    for (int k16 = 0; k16 < NBK; ++k16) {
+      const uint64_t bd = b_hi | (uint64_t)(b_lo + 2u * k16);
+      const uint32_t accf = k16 == 0 ? acc_rest : 1u;
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        umma_f16(acc0 + (uint32_t)m * nb, a_hi | (uint64_t)(a_lo + (uint32_t)m * ms + 2u * k16), bd, idesc, accf);
+    }
   }
 }
 
@@ -214,6 +239,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
           const uint32_t full = smem_u32(&bar_a_full[stage]);
           mbar_wait(smem_u32(&bar_a_empty[stage]), phase ^ 1u);
           if (kc == 0) dbg_mark(P, 0, pit, 1);
+          if ((P.dbg_flags & 4) && pit >= P.n_stages) { mbar_arrive(full); if (++stage == P.n_stages) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(full, P.stage_tx);
           const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
           for (int s = 0; s < P.n_src; ++s)
@@ -265,20 +291,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
           if (kc == 0 && lane == 0) dbg_mark(P, 1, it, 2);
           const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;
           if (elect_one()) {
-            uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
+            const uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
             const uint32_t b_step = resident ? (uint32_t)n_chunks * wblk16 : wblk16;
-            for (int t = 0; t < n_taps; ++t, b_lo += b_step) {
-              const int s = P.tap_src[t];
-              const uint32_t a_lo = sa16 + ((P.tap_off[t] >> 4) | lbo16);
-              const uint64_t a_hi = make_smem_desc_hi(P.a_sbo[s], P.layout) << 32;
-              const uint32_t ms = P.mt_stride[s] >> 4;
-              for (int k16 = 0; k16 < nbk; ++k16) {
-                const uint64_t bd = b_hi | (uint64_t)(b_lo + 2u * k16);
-                uint32_t al = a_lo + 2u * k16;
-                const uint32_t accf = (kc | t | k16) != 0 ? 1u : 0u;
-                for (int m = 0; m < mt; ++m, al += ms) umma_f16(acc0 + (uint32_t)m * nb, a_hi | (uint64_t)al, bd, idesc, accf);
-              }
+#define DG_ISSUE(MT_, NBK_) issue_stage<MT_, NBK_>(P, n_taps, sa16, lbo16, b_lo, b_step, b_hi, acc0, nb, idesc, kc != 0)
+            if (mt == 1) {
+              if (nbk == 4) DG_ISSUE(1, 4); else if (nbk == 2) DG_ISSUE(1, 2); else DG_ISSUE(1, 1);
+            } else {
+              if (nbk == 4) DG_ISSUE(2, 4); else if (nbk == 2) DG_ISSUE(2, 2); else DG_ISSUE(2, 1);
             }
+#undef DG_ISSUE
             umma_commit(smem_u32(&bar_a_empty[stage]));
             if (kc == n_chunks - 1) umma_commit(smem_u32(&bar_acc_full[b]));
           }
@@ -337,6 +358,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 static long long* g_dbg_timeline = nullptr;
+static int g_dbg_flags = 0;
 
 inline int kc_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
@@ -491,6 +513,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.out_f32 = out->dtype == DG_F32;
   P.bias = bias; P.act = act; P.alpha = alpha;
   P.dbg = g_dbg_timeline;
+  P.dbg_flags = g_dbg_flags;
 
   const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + 1024;
   static bool attr_set = false;
@@ -518,6 +541,7 @@ inline int pymod(int a, int b) { return a - floordiv(a, b) * b; }
 // Debug aid: when set to a device buffer of 3*16*4 int64, CTA 0 of every conv launch records clock64() marks
 // (role, tile, slot); pass NULL to switch off.  Not part of the hot path.
 extern "C" void dg_debug_conv_timeline(void* dev_buffer) { g_dbg_timeline = (long long*)dev_buffer; }
+extern "C" void dg_debug_conv_flags(int flags) { g_dbg_flags = flags; }
 
 extern "C" size_t dg_umma_packed_bytes(int kh, int kw, int cin, int cout, int mode) {
   return (size_t)kh * kw * cin * cout * 2;

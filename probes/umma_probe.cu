@@ -109,6 +109,24 @@ probe_kernel(const __grid_constant__ Maps maps, const ProbeCase* __restrict__ pc
       tc_fence_after();
       const int reps = pc.repeat > 0 ? pc.repeat : 1;
       long long t0 = clock64();
+      if (pc.repeat > 0) {
+        // timing mode: descriptors live in registers, the issue loop is nothing but tcgen05.mma
+        uint64_t adq[8], bdq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int k = i < pc.n_mma ? i : 0;
+          adq[i] = make_smem_desc(base + pc.mma[k].a_off, pc.a_lbo, pc.a_sbo, pc.a_layout, 0);
+          bdq[i] = make_smem_desc(base + pc.mma[k].b_off, pc.b_lbo, pc.b_sbo, pc.b_layout, 0);
+        }
+        const uint32_t idesc = pc.idesc;
+        const int nm = pc.n_mma;
+        t0 = clock64();
+        for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nm) umma_f16(tmem, adq[i], bdq[i], idesc, 1u);
+        }
+      } else
       for (int rep = 0; rep < reps; ++rep)
       for (int i = 0; i < pc.n_mma; ++i) {
         uint32_t a_addr = base + pc.mma[i].a_off, b_addr = base + pc.mma[i].b_off;
@@ -462,8 +480,14 @@ int main() {
 
   // ---- T: tensor-pipe throughput for the descriptor styles the conv kernels use (cycles per MMA, single CTA)
   {
-    struct TCase { const char* name; int N; int a_mn, b_mn; uint32_t a_off0, a_kstep, a_sbo, a_lbo, b_kstep, b_sbo, b_lbo; int nk; };
+    struct TCase { const char* name; int N; int a_mn, b_mn; uint32_t a_off0, a_kstep, a_sbo, a_lbo, b_kstep, b_sbo, b_lbo; int nk; int M = 128; };
     const TCase tc[] = {
+        {"t_M64_N64", 64, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4, 64},
+        {"t_M64_N128", 128, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4, 64},
+        {"t_M64_N256", 256, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4, 64},
+        {"t_M64_N256_Bhalo10", 256, 0, 0, 0, 32, 1024, 16, 32, 1280, 16, 4, 64},
+        {"t_M128_N256_Bhalo10", 256, 0, 0, 0, 32, 1024, 16, 32, 1280, 16, 4, 128},
+        {"t_M64_N192_mn", 192, 1, 1, 0, 2048, 1024, 16384, 2560, 1280, 128, 8, 64},
         {"t_kmajor_aligned_N64", 64, 0, 0, 0, 32, 1024, 16, 32, 1024, 16, 4},
         {"t_kmajor_shift1_N64", 64, 0, 0, 128, 32, 1024, 16, 32, 1024, 16, 4},
         {"t_kmajor_halo10_tap11_N64", 64, 0, 0, 11 * 128, 32, 1280, 16, 32, 1024, 16, 4},
@@ -479,7 +503,7 @@ int main() {
       pc.tx_bytes = 256 * 128;
       add_B64(pc, 5, 0, 256 * 128);
       pc.n_cols = T.N;
-      pc.idesc = sm100::make_idesc_bf16(128, T.N, T.a_mn, T.b_mn);
+      pc.idesc = sm100::make_idesc_bf16(T.M, T.N, T.a_mn, T.b_mn);
       pc.a_sbo = T.a_sbo; pc.a_lbo = T.a_lbo; pc.b_sbo = T.b_sbo; pc.b_lbo = T.b_lbo;
       for (int k = 0; k < T.nk; ++k) pc.mma[pc.n_mma++] = {T.a_off0 + (uint32_t)k * T.a_kstep, B_OFF + (uint32_t)k * T.b_kstep};
       pc.repeat = 256;

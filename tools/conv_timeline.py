@@ -22,6 +22,10 @@ cp = L.DgConvParams(k, k, 1, 1, 1, 0, 0.0)
 tx, ty = L.tensor(x), L.tensor(y)
 for _ in range(3):
     L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
+import os as _os
+flags = int(_os.environ.get("DG_FLAGS", "0"))
+lib.dg_debug_conv_flags(flags)
+print("flags", flags)
 dbg = torch.zeros(3 * 16 * 4, dtype=torch.int64, device="cuda")
 lib.dg_debug_conv_timeline(dbg.data_ptr())
 L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
@@ -31,8 +35,11 @@ t = dbg.cpu().view(3, 16, 4)
 t0 = int(t[t > 0].min())
 names = {0: ["tile start", "slot free", "loads issued", ""], 1: ["tile start", "acc free", "operands landed", "mma issued+commit"],
          2: ["tile start", "acc full", "stored+released", ""]}
+lib.dg_debug_conv_flags(0)
 for role, rn in enumerate(["producer", "mma", "epilogue"]):
     print(rn)
+    if role != 1:
+        continue
     for it in range(16):
         row = t[role, it]
         if int(row.max()) == 0:
