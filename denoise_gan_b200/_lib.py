@@ -51,6 +51,7 @@ SIGNATURES = {
     "dg_conv2d_wgrad": (_i, [_P, _T, _T, _P, _P, _CP, _i, _P, _sz, _P]),
     "dg_umma_packed_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dg_umma_pack_weights": (_i, [_P, _P, _P, _i, _i, _i, _i, _i, _P]),
+    "dg_umma_pack_weights_batch": (_i, [_P, _P, _i, _P]),
     "dg_umma_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_debug_conv_timeline": (None, [_P]),

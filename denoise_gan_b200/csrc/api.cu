@@ -42,10 +42,17 @@ extern "C" int dg_init(int device, dg_ctx** out) {
     delete c;
     DG_FAIL("dg_init: cuTensorMapEncodeTiled not available from the driver");
   }
+  if (cudaMalloc(&c->tickets, 256) != cudaSuccess || cudaMemset(c->tickets, 0, 256) != cudaSuccess) {
+    delete c;
+    DG_FAIL("dg_init: cannot allocate the ticket scratch");
+  }
   *out = c;
   return 0;
 }
 
-extern "C" void dg_destroy(dg_ctx* ctx) { delete ctx; }
+extern "C" void dg_destroy(dg_ctx* ctx) {
+  if (ctx) cudaFree(ctx->tickets);
+  delete ctx;
+}
 
 extern "C" int dg_has_umma(dg_ctx* ctx) { return ctx && ctx->cc_major == 10 && ctx->encode_tiled ? 1 : 0; }

@@ -307,6 +307,7 @@ int fill_geom(const char* name, const dg_tensor* img, const dg_tensor* out, cons
 using dgthin::ThinGeom;
 
 bool thin_shape_ok(const dg_tensor* img, const dg_tensor* out, const dg_conv_params* p) {
+  if ((long)img->n * img->h * img->w >= (1L << 31)) return false;
   return p->stride == 1 && img->h == out->h && img->w == out->w && p->kh * p->kw <= 16 && p->kw <= dgthin::OUT_MAX_KW;
 }
 bool fat_ok(const dg_tensor* t, int mult) { return dgvec::vec_ok(t) && t->c % mult == 0; }
@@ -365,8 +366,8 @@ bool thin_wgrad_applicable(const dg_tensor* x, const dg_tensor* dy, const dg_con
   const dg_tensor* thin = x->c <= 4 ? x : dy;
   if (thin->c > 4 || thin->c < 1) return false;
   if (!fat_ok(fat, 8)) return false;
-  int warps = (fat->c / 8) * p->kh;
-  return warps >= 1 && warps <= 16;
+  int warps = fat->c / 8;
+  return warps >= 1 && warps <= 16 && (long)x->n * x->h * x->w < (1L << 31);
 }
 
 int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, const dg_conv_params* p,
@@ -387,12 +388,13 @@ int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, 
   long per = (P + THIN_WGRAD_BLOCKS - 1) / THIN_WGRAD_BLOCKS;
   per = (per + 31) / 32 * 32;
   const int blocks = (int)((P + per - 1) / per);
-  const int threads = 32 * (fat->c / 8) * p->kh;
+  const int threads = 32 * (fat->c / 8);
+  const dim3 grid_o(blocks, p->kh);
   float* part = (float*)workspace;
   const int want_bias = dbias != nullptr;
 #define THIN_OUTER_KW(CTN, KWN)                                                                                           \
   DG_DISPATCH_2(fat->dtype, thin->dtype, name,                                                                            \
-                dgthin::thin_outer_kernel<TI, TO, CTN, KWN><<<blocks, threads, 0, st>>>((const TI*)fat->ptr, (const TO*)thin->ptr, part, \
+                dgthin::thin_outer_kernel<TI, TO, CTN, KWN><<<grid_o, threads, 0, st>>>((const TI*)fat->ptr, (const TO*)thin->ptr, part, \
                                                                                        part_stride, n_dw, thin_in ? 1 : 0, want_bias, g, per);)
 #define THIN_OUTER(CTN)                   \
   switch (p->kw) {                        \

@@ -45,13 +45,13 @@ thin_expand_kernel(const TT* __restrict__ thin, TF* __restrict__ fat, const floa
     ws[k][j] = w[(long)t * g.w_st + (long)c * g.w_sthin + (long)(o0 + j) * g.w_sfat];
   }
   __syncthreads();
-  const long P = (long)g.N * g.H * g.W;
-  const long p = (long)blockIdx.x * EXP_THREADS + threadIdx.x;
+  const uint32_t P = (uint32_t)g.N * g.H * g.W;
+  const uint32_t p = blockIdx.x * EXP_THREADS + threadIdx.x;
   if (p >= P) return;
-  const int wq = (int)(p % g.W);
-  const long t2 = p / g.W;
-  const int h = (int)(t2 % g.H);
-  const long n = t2 / g.H;
+  const uint32_t t2 = p / (uint32_t)g.W;
+  const int wq = (int)(p - t2 * (uint32_t)g.W);
+  const long n = t2 / (uint32_t)g.H;
+  const int h = (int)(t2 - (uint32_t)n * (uint32_t)g.H);
   float acc[EXP_OG];
 #pragma unroll
   for (int j = 0; j < EXP_OG; ++j) acc[j] = bias ? __ldg(bias + o0 + j) : 0.f;
@@ -61,7 +61,7 @@ thin_expand_kernel(const TT* __restrict__ thin, TF* __restrict__ fat, const floa
     for (int s = 0; s < g.kw; ++s) {
       const int ww = wq + g.dsign * (s - g.dw0);
       if (ww < 0 || ww >= g.W) continue;
-      const TT* src = thin + (((n * g.H + hh) * g.W + ww) * g.tp + g.to);
+      const TT* src = thin + ((long)((n * g.H + hh) * g.W + ww) * g.tp + g.to);
       const int kb = (r * g.kw + s) * g.CT;
       for (int c = 0; c < g.CT; ++c) {
         const float v = ld_f(src + c);
@@ -78,7 +78,7 @@ thin_expand_kernel(const TT* __restrict__ thin, TF* __restrict__ fat, const floa
     }
   }
   float o8[8];
-  TF* dst = fat + (p * g.fp + g.fo + o0);
+  TF* dst = fat + ((long)p * g.fp + g.fo + o0);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -103,13 +103,13 @@ thin_contract_kernel(const TF* __restrict__ fat, TT* __restrict__ thin, const fl
     w4s[e] = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
-  const long P = (long)g.N * g.H * g.W;
-  const long p = (long)blockIdx.x * CON_THREADS + threadIdx.x;
+  const uint32_t P = (uint32_t)g.N * g.H * g.W;
+  const uint32_t p = blockIdx.x * CON_THREADS + threadIdx.x;
   if (p >= P) return;
-  const int wq = (int)(p % g.W);
-  const long t2 = p / g.W;
-  const int h = (int)(t2 % g.H);
-  const long n = t2 / g.H;
+  const uint32_t t2 = p / (uint32_t)g.W;
+  const int wq = (int)(p - t2 * (uint32_t)g.W);
+  const long n = t2 / (uint32_t)g.H;
+  const int h = (int)(t2 - (uint32_t)n * (uint32_t)g.H);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < g.CT; ++j) acc[j] = bias ? __ldg(bias + j) : 0.f;
   for (int r = 0; r < g.kh; ++r) {
@@ -118,7 +118,7 @@ thin_contract_kernel(const TF* __restrict__ fat, TT* __restrict__ thin, const fl
     for (int s = 0; s < g.kw; ++s) {
       const int ww = wq + g.dsign * (s - g.dw0);
       if (ww < 0 || ww >= g.W) continue;
-      const TF* src = fat + (((n * g.H + hh) * g.W + ww) * g.fp + g.fo);
+      const TF* src = fat + ((long)((n * g.H + hh) * g.W + ww) * g.fp + g.fo);
       const float4* wt = w4s + (r * g.kw + s) * g.CF;
       for (int c0 = 0; c0 < g.CF; c0 += 8) {
         float v[8];
@@ -134,7 +134,7 @@ thin_contract_kernel(const TF* __restrict__ fat, TT* __restrict__ thin, const fl
       }
     }
   }
-  TT* dst = thin + (p * g.tp + g.to);
+  TT* dst = thin + ((long)p * g.tp + g.to);
   for (int j = 0; j < g.CT; ++j) st_f(dst + j, apply_act(acc[j], g.act, g.alpha));
 }
 
@@ -147,8 +147,7 @@ template <typename TF, typename TT, int CT, int KW>
 __global__ void __launch_bounds__(512, 1) thin_outer_kernel(const TF* __restrict__ fat, const TT* __restrict__ thin, float* __restrict__ part, long part_stride,
                                   long bias_off, int bias_on_fat, int want_bias, ThinGeom g, long pix_per_block) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int CV = g.CF >> 3;
-  const int cv = warp % CV, r = warp / CV;  // blockDim = 32 * CV * kh
+  const int cv = warp, r = blockIdx.y;  // blockDim = 32 * CF/8 ; gridDim.y = kh
   const long P = (long)g.N * g.H * g.W;
   const long f_beg = (long)blockIdx.x * pix_per_block;
   const long f_end = min(P, f_beg + pix_per_block);
@@ -165,11 +164,17 @@ __global__ void __launch_bounds__(512, 1) thin_outer_kernel(const TF* __restrict
   for (int k = 0; k < 8; ++k) bsum[k] = 0.f;
 #pragma unroll
   for (int c = 0; c < CT; ++c) tsum[c] = 0.f;
-  for (long f = f_beg + lane; f < f_end; f += 32) {
-    const int wq = (int)(f % g.W);
-    const long t2 = f / g.W;
-    const int h = (int)(t2 % g.H);
-    const long n = t2 / g.H;
+  // pixel coordinates advance incrementally (no division in the loop)
+  int wq, h, n;
+  {
+    const uint32_t f0 = (uint32_t)(f_beg + lane);
+    const uint32_t t2 = f0 / (uint32_t)g.W;
+    wq = (int)(f0 - t2 * (uint32_t)g.W);
+    n = (int)(t2 / (uint32_t)g.H);
+    h = (int)(t2 - (uint32_t)n * (uint32_t)g.H);
+  }
+  for (long f = f_beg + lane; f < f_end; f += 32, wq += 32) {
+    while (wq >= g.W) { wq -= g.W; if (++h == g.H) { h = 0; ++n; } }
     float v[8];
     V8<TF>::ld(fat + (f * g.fp + g.fo + cv * 8), v);
     if (r == 0) {
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(512, 1) thin_outer_kernel(const TF* __restrict
     for (int s = 0; s < KW; ++s) {
       const int ww = wq + g.dsign * (s - g.dw0);
       if (ww < 0 || ww >= g.W) continue;
-      const TT* tp = thin + (((n * g.H + hh) * g.W + ww) * g.tp + g.to);
+      const TT* tp = thin + ((long)((n * g.H + hh) * g.W + ww) * g.tp + g.to);
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
         const float tv = ld_f(tp + c);

@@ -360,6 +360,28 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 static long long* g_dbg_timeline = nullptr;
 static int g_dbg_flags = 0;
 
+struct PackEntry {   // mirrored by denoise_gan_b200/params.py (48 bytes)
+  const float* src;
+  __nv_bfloat16* dst;
+  int taps, cin, cout, kc, mode, pad0;
+  long pad1;
+};
+
+// all kernels of a network in ONE launch: blockIdx.y selects the table entry
+__global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry E = table[blockIdx.y];
+  const int rows = E.mode == 0 ? E.cout : E.cin, kdim = E.mode == 0 ? E.cin : E.cout, nch = kdim / E.kc;
+  const unsigned total = (unsigned)E.taps * E.cin * E.cout;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned j = i % E.kc, r1 = i / E.kc;
+    unsigned row = r1 % rows, r2 = r1 / rows;
+    unsigned ch = r2 % nch, t = r2 / nch;
+    unsigned k = ch * E.kc + j;
+    float v = E.mode == 0 ? E.src[((long)t * E.cin + k) * E.cout + row] : E.src[((long)t * E.cin + row) * E.cout + k];
+    E.dst[i] = __float2bfloat16(v);
+  }
+}
+
 inline int kc_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -558,6 +580,14 @@ extern "C" int dg_umma_pack_weights(dg_ctx* ctx, const float* w, void* packed, i
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin, cout, kc, mode);
   DG_CHECK_LAUNCH("dg_umma_pack_weights");
+  return 0;
+}
+
+extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, int n_entries, void* stream) {
+  DG_REQUIRE(table_dev && n_entries > 0, "dg_umma_pack_weights_batch: empty table");
+  dim3 grid(16, n_entries);
+  pack_weights_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackEntry*)table_dev);
+  DG_CHECK_LAUNCH("dg_umma_pack_weights_batch");
   return 0;
 }
 

@@ -12,6 +12,7 @@ struct dg_ctx {
   int sm_count;
   int cc_major, cc_minor;
   void* encode_tiled;  // cuTensorMapEncodeTiled entry point (driver API, resolved at init)
+  unsigned* tickets;   // device scratch: 'last block finishes the reduction' counters (zero between kernels; one stream per ctx)
 };
 
 void dg_set_error(const char* fmt, ...);

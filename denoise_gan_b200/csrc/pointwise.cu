@@ -455,7 +455,10 @@ extern "C" int dg_bn_stats(dg_ctx* ctx, const dg_tensor* x, const float* gamma, 
     blocks = dgvec::red8_blocks(P, C, ctx->sm_count);
     DG_DISPATCH_1(x->dtype, "dg_bn_stats",
                   dgvec::bn_stats8_kernel<T><<<blocks, dgvec::VT, dgvec::red8_smem(C, 2), ST>>>(
-                      (const T*)x->ptr, dgvec::VView{x->cpitch, x->coff}, P, C, partial););
+                      (const T*)x->ptr, dgvec::VView{x->cpitch, x->coff}, P, C, partial, ctx->tickets, gamma, beta, eps, momentum,
+                      moving_mean, moving_var, scale, shift, save_mean, save_invstd););
+    DG_CHECK_LAUNCH("dg_bn_stats");
+    return 0;
   } else {
     DG_DISPATCH_1(x->dtype, "dg_bn_stats",
                   bn_stats_kernel<T><<<blocks, RED_THREADS, smem, ST>>>((const T*)x->ptr, view_of(x), P, C, partial););
@@ -526,9 +529,7 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
       dgvec::bn_bwd_reduce8_kernel<TI, TO><<<vblocks, dgvec::VT, dgvec::red8_smem(C, 3), ST>>>(
           (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout,
-          seed, offset, P, C, partial);
-      bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, vblocks, P, C, dgamma, dbeta,
-                                                              act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
+          seed, offset, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
       dgvec::bn_bwd_dx8_kernel<TI, TO, TI><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
           (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,
           dropout, seed, offset, coef, (TI*)dx->ptr, vdx, P, C);
@@ -622,8 +623,7 @@ extern "C" int dg_d2s_prelu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tenso
       float* partial = (float*)workspace;
       dgvec::d2s_dalpha8_kernel<T><<<vblocks, dgvec::VT, dgvec::red8_smem(Co, 1), ST>>>(
           (const T*)dy->ptr, dgvec::VView{dy->cpitch, dy->coff}, (const T*)u->ptr, dgvec::VView{u->cpitch, u->coff}, Pout, dy->h,
-          dy->w, Co, partial);
-      sum_partials_kernel<<<(Co + 7) / 8, 256, 0, ST>>>(partial, vblocks, Co, dprelu_alpha, accumulate);
+          dy->w, Co, partial, ctx->tickets, dprelu_alpha, accumulate);
     } else if (prelu_alpha && dprelu_alpha) {
       DG_REQUIRE(workspace && workspace_bytes >= dg_bn_workspace_bytes(dy), "dg_d2s_prelu_bwd: workspace too small");
       long Pout = dg_pixels(dy);

@@ -55,10 +55,13 @@ struct VView {
 };
 
 // ---------------------------------------------------------------- per-channel reduction skeleton (8 channels / thread)
-// F(p, c0, acc[NV][8]); partial layout [block][NV][C]
-template <int NV, typename F>
-__device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict__ partial, F f) {
-  extern __shared__ float red8[];
+// F(p, c0, acc[NV][8]) accumulates; every block writes one partial [NV][C]; the LAST block to finish (ticket
+// counter) sums the partials in block order in double precision and calls Fin(c, sums) per channel, so no
+// separate finalize launch is needed and the result does not depend on block scheduling (deterministic).
+template <int NV, typename F, typename Fin>
+__device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, F f, Fin fin) {
+  extern __shared__ __align__(16) float red8[];
+  __shared__ int is_last;
   const int CV = C >> 3, R = VT / CV;
   const int lane = threadIdx.x % CV, row = threadIdx.x / CV;
   float acc[NV][8];
@@ -66,9 +69,14 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
-  if (row < R)
-    for (long p = (long)blockIdx.x * R + row; p < P; p += (long)gridDim.x * R) f(p, lane * 8, acc);
   if (row < R) {
+    const long stride = (long)gridDim.x * R;
+    long p = (long)blockIdx.x * R + row;
+    for (; p + stride < P; p += 2 * stride) {  // two pixels in flight per thread
+      f(p, lane * 8, acc);
+      f(p + stride, lane * 8, acc);
+    }
+    if (p < P) f(p, lane * 8, acc);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -80,29 +88,77 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
     for (int r = 0; r < R; ++r) s += red8[r * NV * C + e];
     partial[(long)blockIdx.x * NV * C + e] = s;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double* fsum = reinterpret_cast<double*>(red8);  // NV*C doubles fit: the block had R >= 2 rows of NV*C floats
+  const int nb = (int)gridDim.x;
+  for (int e = threadIdx.x; e < NV * C; e += VT) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int bI = 0;
+    for (; bI + 3 < nb; bI += 4) {
+      s0 += (double)__ldcg(partial + (long)bI * NV * C + e);
+      s1 += (double)__ldcg(partial + (long)(bI + 1) * NV * C + e);
+      s2 += (double)__ldcg(partial + (long)(bI + 2) * NV * C + e);
+      s3 += (double)__ldcg(partial + (long)(bI + 3) * NV * C + e);
+    }
+    for (; bI < nb; ++bI) s0 += (double)__ldcg(partial + (long)bI * NV * C + e);
+    fsum[e] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += VT) fin(c, fsum);
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 static inline int red8_blocks(long P, int C, int sm_count) {
   int R = VT / (C >> 3);
-  long want = (P + R - 1) / R, cap = (long)sm_count * 8;
+  long want = (P + R - 1) / R, cap = (long)sm_count * 4;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
-static inline size_t red8_smem(int C, int NV) { return (size_t)(VT / (C >> 3)) * NV * C * sizeof(float); }
+static inline size_t red8_smem(int C, int NV) {
+  size_t a = (size_t)(VT / (C >> 3)) * NV * C * sizeof(float), b = (size_t)NV * C * sizeof(double);
+  return a > b ? a : b;
+}
 
 static inline bool vec_ok(const dg_tensor* t) {
   int esz = t->dtype == DG_F32 ? 4 : 2;
+  if ((long)t->n * t->h * t->w * t->cpitch >= (1L << 31)) return false;  // kernels index with 32 bits
   return t->c % 8 == 0 && t->cpitch % 8 == 0 && t->coff % 8 == 0 && t->c <= 1024 && ((uintptr_t)t->ptr % 16) == 0 &&
          (t->cpitch * esz) % 16 == 0;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(VT) bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __restrict__ partial) {
-  channel_reduce8<2>(P, C, partial, [&](long p, int c0, float (&a)[2][8]) {
-    float v[8];
-    V8<T>::ld(x + (p * xv.pitch + xv.off + c0), v);
+__global__ void __launch_bounds__(VT)
+bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                 float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
+                 float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  channel_reduce8<2>(
+      P, C, partial, ticket,
+      [&](long p, int c0, float (&a)[2][8]) {
+        float v[8];
+        V8<T>::ld(x + (p * xv.pitch + xv.off + c0), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[0][j] += v[j]; a[1][j] += v[j] * v[j]; }
-  });
+        for (int j = 0; j < 8; ++j) { a[0][j] += v[j]; a[1][j] += v[j] * v[j]; }
+      },
+      [&](int c, const double* sums) {
+        double mean = sums[c] / (double)P;
+        double var = sums[C + c] / (double)P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        float g = gamma[c], b = beta[c];
+        scale[c] = g * invstd;
+        shift[c] = b - (float)mean * g * invstd;
+        save_mean[c] = (float)mean;
+        save_invstd[c] = invstd;
+        if (moving_mean) {
+          moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+          moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+        }
+      });
 }
 
 template <typename TI, typename TO>
@@ -110,10 +166,10 @@ __global__ void __launch_bounds__(VT)
 bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                    float alpha, const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, int dropout,
                    uint32_t seed, uint32_t offset, TO* __restrict__ y, VView yv, long P, int C) {
-  const int CV = C >> 3;
-  const long total = P * CV;
-  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
-    const long p = i / CV;
+  const uint32_t CV = (uint32_t)C >> 3;
+  const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV;
     const int c0 = (int)(i - p * CV) * 8;
     float v[8], sc[8], sh[8];
     V8<TI>::ld(x + (p * xv.pitch + xv.off + c0), v);
@@ -183,8 +239,9 @@ __global__ void __launch_bounds__(VT)
 bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                       const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                       float alpha, const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset, long P, int C,
-                      float* __restrict__ partial) {
-  channel_reduce8<3>(P, C, partial, [&](long p, int c0, float (&a)[3][8]) {
+                      float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                      float* __restrict__ dalpha, int accumulate, float* __restrict__ coef) {
+  channel_reduce8<3>(P, C, partial, ticket, [&](long p, int c0, float (&a)[3][8]) {
     float g[8], t[8], xin[8], gy[8], mu[8], is[8];
     bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
     ldc8(mean + c0, mu); ldc8(invstd + c0, is);
@@ -194,6 +251,13 @@ bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict_
       a[1][j] += g[j] * (xin[j] - mu[j]) * is[j];
       if (act == DG_ACT_PRELU) a[2][j] += gy[j] * fminf(t[j], 0.f);
     }
+  }, [&](int c, const double* sums) {
+    const double s0 = sums[c], s1 = sums[C + c], s2 = sums[2 * C + c];
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+    if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
+    coef[c] = (float)(s0 / (double)P);
+    coef[C + c] = (float)(s1 / (double)P);
   });
 }
 
@@ -204,10 +268,10 @@ bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x,
                   const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ invstd, int act, float alpha, const float* __restrict__ prelu_alpha, int dropout,
                   uint32_t seed, uint32_t offset, const float* __restrict__ coef, TO* __restrict__ dx, VView ov, long P, int C) {
-  const int CV = C >> 3;
-  const long total = P * CV;
-  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
-    const long p = i / CV;
+  const uint32_t CV = (uint32_t)C >> 3;
+  const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV;
     const int c0 = (int)(i - p * CV) * 8;
     float g[8], t[8], xin[8], gy[8], mu[8], is[8], ga[8], k0[8], k1[8], o[8];
     bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
@@ -222,10 +286,10 @@ template <typename TG, typename TY, typename TO>
 __global__ void __launch_bounds__(VT)
 act_bwd8_kernel(const TG* __restrict__ dy, VView dv, const TY* __restrict__ y, VView yv, int act, float alpha, TO* __restrict__ dpre,
                 VView ov, long P, int C) {
-  const int CV = C >> 3;
-  const long total = P * CV;
-  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
-    const long p = i / CV;
+  const uint32_t CV = (uint32_t)C >> 3;
+  const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV;
     const int c0 = (int)(i - p * CV) * 8;
     float g[8], yo[8];
     V8<TG>::ld(dy + (p * dv.pitch + dv.off + c0), g);
@@ -252,15 +316,15 @@ __global__ void __launch_bounds__(VT)
 d2s_prelu8_kernel(const T* __restrict__ a, VView av, const T* __restrict__ u, VView uv, const float* __restrict__ alpha,
                   T* __restrict__ o, VView ov, int N, int H, int W, int Co) {
   // FWD: a = u (input), o = y.   BWD: a = dy (output-sized), u = saved input, o = du.
-  const int CV = (4 * Co) >> 3;
-  const long total = (long)N * H * W * CV;
-  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
-    const long p = i / CV;
+  const uint32_t CV = (uint32_t)(4 * Co) >> 3;
+  const uint32_t total = (uint32_t)N * H * W * CV;
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV;
     const int ch0 = (int)(i - p * CV) * 8;
-    const int w = (int)(p % W);
-    const long t = p / W;
-    const int h = (int)(t % H);
-    const long n = t / H;
+    const uint32_t t = p / (uint32_t)W;
+    const int w = (int)(p - t * (uint32_t)W);
+    const uint32_t n = t / (uint32_t)H;
+    const int h = (int)(t - n * (uint32_t)H);
     const int sub = ch0 / Co, c0 = ch0 - sub * Co;
     const long q = ((long)n * 2 * H + 2 * h + (sub >> 1)) * 2 * W + 2 * w + (sub & 1);
     float v[8], al[8];
@@ -288,8 +352,8 @@ d2s_prelu8_kernel(const T* __restrict__ a, VView av, const T* __restrict__ u, VV
 template <typename T>
 __global__ void __launch_bounds__(VT)
 d2s_dalpha8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ u, VView uv, long Pout, int H2, int W2, int Co,
-                   float* __restrict__ partial) {
-  channel_reduce8<1>(Pout, Co, partial, [&](long q, int c0, float (&a)[1][8]) {
+                   float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ dalpha, int accumulate) {
+  channel_reduce8<1>(Pout, Co, partial, ticket, [&](long q, int c0, float (&a)[1][8]) {
     int w2 = (int)(q % W2);
     long t = q / W2;
     int h2 = (int)(t % H2);
@@ -301,17 +365,17 @@ d2s_dalpha8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ u, 
     V8<T>::ld(u + (p * uv.pitch + uv.off + sub * Co + c0), uu);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[0][j] += g[j] * fminf(uu[j], 0.f);
-  });
+  }, [&](int c, const double* sums) { dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)sums[c]; });
 }
 
 // out = a (+ b) with dtype conversion; ACC: out += a
 template <typename TA, typename TO, int MODE>  // MODE 0: out = a ; 1: out = a + b ; 2: out += a
 __global__ void __launch_bounds__(VT)
 ew8_kernel(const TA* __restrict__ a, VView av, const TA* __restrict__ b, VView bv, TO* __restrict__ o, VView ov, long P, int C) {
-  const int CV = C >> 3;
-  const long total = P * CV;
-  for (long i = (long)blockIdx.x * VT + threadIdx.x; i < total; i += (long)gridDim.x * VT) {
-    const long p = i / CV;
+  const uint32_t CV = (uint32_t)C >> 3;
+  const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV;
     const int c0 = (int)(i - p * CV) * 8;
     float v[8];
     V8<TA>::ld(a + (p * av.pitch + av.off + c0), v);

@@ -92,15 +92,26 @@ class ParamSet:
         return OrderedDict((n, p.grad.detach().clone().cpu()) for n, p in self.params.items())
 
     def repack(self, lib, ctx, stream):
-        """Refreshes the bf16 K-major copies of every conv kernel the tensor-core path consumes."""
+        """Refreshes the bf16 K-major copies of every conv kernel the tensor-core path consumes — one launch
+        for the whole network (device table of (src, dst, geometry) entries, rebuilt when the set changes)."""
+        import struct
+        ents = []
         for p in self.params.values():
-            if p.packed_fwd is None and p.packed_dgrad is None:
-                continue
-            kh, kw, cin, cout = p.shape
-            if p.packed_fwd is not None:
-                _lib.check(lib.dg_umma_pack_weights(ctx, p.data.data_ptr(), p.packed_fwd.data_ptr(), kh, kw, cin, cout, 0, stream))
-            if p.packed_dgrad is not None:
-                _lib.check(lib.dg_umma_pack_weights(ctx, p.data.data_ptr(), p.packed_dgrad.data_ptr(), kh, kw, cin, cout, 1, stream))
+            for mode, t in ((0, p.packed_fwd), (1, p.packed_dgrad)):
+                if t is None:
+                    continue
+                kh, kw, cin, cout = p.shape
+                kdim = cin if mode == 0 else cout
+                kc = 64 if kdim % 64 == 0 else (32 if kdim % 32 == 0 else 16)
+                ents.append((p.data.data_ptr(), t.data_ptr(), kh * kw, cin, cout, kc, mode))
+        if not ents:
+            return
+        key = tuple(ents)
+        if getattr(self, "_pack_key", None) != key:
+            blob = b"".join(struct.pack("<QQiiiiiiq", s, d, taps, cin, cout, kc, mode, 0, 0) for s, d, taps, cin, cout, kc, mode in ents)
+            self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.theta.device)
+            self._pack_key = key
+        _lib.check(lib.dg_umma_pack_weights_batch(ctx, self._pack_table.data_ptr(), len(ents), stream))
 
 
 # ------------------------------------------------------------------------------------------------

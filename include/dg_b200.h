@@ -75,6 +75,10 @@ int dg_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw_
 size_t dg_umma_packed_bytes(int kh, int kw, int cin, int cout, int mode);
 int dg_umma_pack_weights(dg_ctx*, const float* w_hwio, void* packed, int kh, int kw, int cin, int cout,
                          int mode, void* stream);
+/* same for a whole network in one launch: device table of n 48-byte entries
+ * {const float* src; bf16* dst; int32 taps, cin, cout, kc, mode, pad; int64 pad} with kc = 64/32/16 = largest of
+ * those dividing the contraction channel count (Cin for mode 0, Cout for mode 1) */
+int dg_umma_pack_weights_batch(dg_ctx*, const void* table_dev, int n_entries, void* stream);
 int dg_umma_conv2d_fwd(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias,
                        const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream);
 int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,

@@ -1,0 +1,106 @@
+"""GPU: one train step of the Autoencoder (train_autoencoder.py:66-112) and Fast-SRGAN
+(train_fsrgan.py:61-120) surfaces against the oracle, fp32 path: generator output, discriminator
+outputs, every parameter gradient (relative L2, see test_srgan_gpu.relerr_l2), returned losses."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ops_torch as OT  # noqa: E402
+from oracle import steps as OS  # noqa: E402
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def relerr_l2(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def perturb(p, seed=99):
+    gen = torch.Generator().manual_seed(seed)
+    for k in p:
+        if k.endswith(("bias", "beta", "alpha")):
+            p[k] = torch.randn(p[k].shape, generator=gen) * 0.1
+    return p
+
+
+def check(model, r, out, losses, names, bn_bias_prefixes):
+    assert relerr(r["gen_output"].t, out["gen_output"]) < 2e-5
+    assert relerr(r["disc_real"].t, out["disc_real"]) < 5e-5
+    assert relerr(r["disc_fake"].t, out["disc_fake"]) < 5e-5
+    worst = []
+    for ours, refs in ((model.gen_params.grads(), out["gen_grads"]), (model.disc_params.grads(), out["disc_grads"])):
+        for name, ref in refs.items():
+            if name.endswith("/bias") and name.startswith(bn_bias_prefixes):
+                assert ours[name].abs().max().item() < 1e-3, f"grad {name} should vanish"
+                continue
+            worst.append((relerr_l2(ours[name], ref), name))
+    worst.sort(reverse=True)
+    print("worst gradient L2 errors:", worst[:5])
+    assert worst[0][0] < 2e-4, worst[:5]
+    for n, ref in zip(names, losses):
+        assert abs(r[n].item() - ref.item()) <= 2e-5 * max(1.0, abs(ref.item())), f"{n}: {r[n].item()} vs {ref.item()}"
+
+
+def test_autoencoder_step_fp32():
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.autoencoder import Autoencoder
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.train_common import gan_step
+    model = Autoencoder(SimpleNamespace(crop_size=64, lr=1e-3, fp16=0, vgg=0, retrain=0, seed=0))
+    g0 = perturb(P.init_autoencoder_generator(0)); d0 = perturb(P.init_patch_discriminator(1))
+    model.gen_params.load(g0); model.disc_params.load(d0)
+    x, y = synthetic_pair(2, 64, 1, step=0)
+    r = gan_step(model, x.cuda(), y.cuda(), from_logits=False, disc_scale=1.0)
+    torch.cuda.synchronize()
+    g = {k: v.double().clone() for k, v in g0.items()}; d = {k: v.double().clone() for k, v in d0.items()}
+    out = {}
+    losses = OS.autoencoder_train_step(g, d, None, OT.KerasAdam(1e-3, decay_steps=100000), OT.KerasAdam(5e-3, decay_steps=100000),
+                                       x.double(), y.double(), out=out)
+    # oracle order: (disc_loss, adv, content, mse, mae)
+    check(model, r, out, losses, ["disc_loss", "adv_loss", "content_loss", "mse_loss", "mae_loss"],
+          bn_bias_prefixes=tuple(f"d/conv{i}/" for i in range(2, 9)))
+
+
+def test_fsrgan_step_fp32():
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.fsrgan import FastSRGAN
+    from denoise_gan_b200.train_common import gan_step
+    model = FastSRGAN(SimpleNamespace(crop_size=64, scale=4, lr=1e-3, fp16=0, vgg=0, seed=0))
+    g0 = perturb(P.init_fsrgan_generator(0)); d0 = perturb(P.init_patch_discriminator(1))
+    model.gen_params.load(g0); model.disc_params.load(d0)
+    x, y = synthetic_pair(2, 64, 4, step=0)
+    r = gan_step(model, x.cuda(), y.cuda(), from_logits=True, disc_scale=0.5)
+    torch.cuda.synchronize()
+    g = {k: v.double().clone() for k, v in g0.items()}; d = {k: v.double().clone() for k, v in d0.items()}
+    out = {}
+    losses = OS.srgan_train_step(g, d, None, OT.KerasAdam(1e-3, decay_steps=100000), OT.KerasAdam(5e-3, decay_steps=100000),
+                                 x.double(), y.double(), fsrgan=True, out=out)
+    # oracle order (train_fsrgan.py:120): gen, gen, disc, adv, content, mse, mae, var
+    names = ["gen_loss", "gen_loss", "disc_loss", "adv_loss", "content_loss", "mse_loss", "mae_loss", "var_loss"]
+    bn_prefixes = tuple(f"d/conv{i}/" for i in range(2, 9)) + ("g/c1/", "g/c2/") + tuple(f"g/b{i}/" for i in range(6))
+    check(model, r, out, losses, names, bn_bias_prefixes=bn_prefixes)
+
+
+def test_fsrgan_step_bf16_runs_and_tracks_fp32():
+    """bf16 tensor-core path of the Fast-SRGAN step: losses within 2e-2 of the float64 oracle."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.fsrgan import FastSRGAN
+    from denoise_gan_b200.train_fsrgan import train_step
+    model = FastSRGAN(SimpleNamespace(crop_size=128, scale=4, lr=1e-3, fp16=1, vgg=0, seed=0))
+    g0 = P.init_fsrgan_generator(0); d0 = P.init_patch_discriminator(1)
+    x, y = synthetic_pair(4, 128, 4, step=0)
+    ours = [float(v) for v in train_step(model, x.cuda(), y.cuda())]
+    g = {k: v.double().clone() for k, v in g0.items()}; d = {k: v.double().clone() for k, v in d0.items()}
+    ref = OS.srgan_train_step(g, d, None, OT.KerasAdam(1e-3, decay_steps=100000), OT.KerasAdam(5e-3, decay_steps=100000),
+                              x.double(), y.double(), fsrgan=True)
+    for a, b in zip(ours, ref):
+        assert abs(a - float(b)) <= 2e-2 * max(1.0, abs(float(b))), (ours, [float(v) for v in ref])
