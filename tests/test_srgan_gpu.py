@@ -83,7 +83,7 @@ def test_srgan_step_fp32_layers_grads_losses(vgg):
     r = gan_step(model, x.cuda(), y.cuda(), from_logits=True, disc_scale=1.0)
     torch.cuda.synchronize()
     g1, d1, outs = oracle_steps(g0, d0, v0, [x], [y])
-    _, _, outs32 = oracle_steps(g0, d0, v0, [x], [y], dtype=torch.float32)     # fp32 noise yard-stick (tests/_parity.py)
+    g1_32, d1_32, outs32 = oracle_steps(g0, d0, v0, [x], [y], dtype=torch.float32)     # fp32 noise yard-stick (tests/_parity.py)
     losses, acts, out = outs[0]
     out32 = outs32[0][2]
     checked = 0
@@ -124,11 +124,14 @@ def test_srgan_step_fp32_layers_grads_losses(vgg):
         assert abs(r[n].item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item())), f"{n}: {r[n].item()} vs {ref.item()}"
     # parameters and BN moving statistics after the Adam step
     ge, de = model.gen_params.export(), model.disc_params.export()
-    for exp, ref in ((ge, g1), (de, d1)):
+    # the first Adam step moves every weight by ~lr*sign(g): elements whose tiny gradient changes sign under fp32
+    # rounding move by 2*lr, so the bound is again expressed in units of the fp32 oracle's own deviation
+    for exp, ref, ref32 in ((ge, g1, g1_32), (de, d1, d1_32)):
         for k, v in ref.items():
             if feeds_bn(k):
                 continue
-            assert relerr_l2(exp[k], v) < 1e-3, f"param {k}"   # Adam normalises: a flipped derivative moves a weight by ~lr
+            bound = 1e-4 + 3.0 * relerr_l2(ref32[k], v)
+            assert relerr_l2(exp[k], v) <= bound, f"param {k}: {relerr_l2(exp[k], v)} > {bound}"
 
 
 def test_srgan_step_bf16_tensor_core_path():
