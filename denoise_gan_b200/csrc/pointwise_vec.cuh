@@ -72,11 +72,13 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   if (row < R) {
     const long stride = (long)gridDim.x * R;
     long p = (long)blockIdx.x * R + row;
-    for (; p + stride < P; p += 2 * stride) {  // two pixels in flight per thread
+    for (; p + 3 * stride < P; p += 4 * stride) {  // four pixels in flight per thread
       f(p, lane * 8, acc);
       f(p + stride, lane * 8, acc);
+      f(p + 2 * stride, lane * 8, acc);
+      f(p + 3 * stride, lane * 8, acc);
     }
-    if (p < P) f(p, lane * 8, acc);
+    for (; p < P; p += stride) f(p, lane * 8, acc);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -94,19 +96,27 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  double* fsum = reinterpret_cast<double*>(red8);  // NV*C doubles fit: the block had R >= 2 rows of NV*C floats
+  // all 256 threads share the final sum: thread = (4-element vector of the partial, group of blocks)
+  double* fsum = reinterpret_cast<double*>(red8);   // [E] doubles (E = NV*C); group partials live behind it
   const int nb = (int)gridDim.x;
-  for (int e = threadIdx.x; e < NV * C; e += VT) {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int bI = 0;
-    for (; bI + 3 < nb; bI += 4) {
-      s0 += (double)__ldcg(partial + (long)bI * NV * C + e);
-      s1 += (double)__ldcg(partial + (long)(bI + 1) * NV * C + e);
-      s2 += (double)__ldcg(partial + (long)(bI + 2) * NV * C + e);
-      s3 += (double)__ldcg(partial + (long)(bI + 3) * NV * C + e);
+  const int E4 = (NV * C) >> 2;
+  const int G = E4 < VT ? VT / E4 : 1;
+  double* gsum = fsum + NV * C;                      // [G][E]
+  for (int idx = threadIdx.x; idx < E4 * G; idx += VT) {
+    const int e4 = idx % E4, grp = idx / E4;
+    double s[4] = {0, 0, 0, 0};
+    for (int bI = grp; bI < nb; bI += G) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (long)bI * NV * C) + e4);
+      s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
     }
-    for (; bI < nb; ++bI) s0 += (double)__ldcg(partial + (long)bI * NV * C + e);
-    fsum[e] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gsum[(long)grp * NV * C + e4 * 4 + k] = s[k];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NV * C; e += VT) {
+    double t = 0;
+    for (int g2 = 0; g2 < G; ++g2) t += gsum[(long)g2 * NV * C + e];
+    fsum[e] = t;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += VT) fin(c, fsum);
@@ -115,11 +125,12 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
 
 static inline int red8_blocks(long P, int C, int sm_count) {
   int R = VT / (C >> 3);
-  long want = (P + R - 1) / R, cap = (long)sm_count * 4;
+  long want = (P + R - 1) / R, cap = (long)sm_count * 2;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 static inline size_t red8_smem(int C, int NV) {
-  size_t a = (size_t)(VT / (C >> 3)) * NV * C * sizeof(float), b = (size_t)NV * C * sizeof(double);
+  const int E = NV * C, E4 = E >> 2, G = E4 < VT ? VT / E4 : 1;
+  size_t a = (size_t)(VT / (C >> 3)) * NV * C * sizeof(float), b = (size_t)(E + (size_t)G * E) * sizeof(double);
   return a > b ? a : b;
 }
 
