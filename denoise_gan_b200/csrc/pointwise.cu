@@ -95,8 +95,9 @@ template <typename TI, typename TO>
 __global__ void bn_act_fwd_kernel(const TI* __restrict__ x, View xv, const float* __restrict__ scale,
                                   const float* __restrict__ shift, int act, float alpha,
                                   const float* __restrict__ prelu_alpha, const TO* __restrict__ res, View rv,
-                                  int dropout, uint32_t seed, uint32_t offset, TO* __restrict__ y, View yv, long P,
+                                  int dropout, uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, TO* __restrict__ y, View yv, long P,
                                   int C) {
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   long total = P * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long p = i / C;
@@ -144,8 +145,9 @@ __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_reduce_kernel(const TG* __restrict__ dy, View dv, const TX* __restrict__ x, View xv,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int act, float alpha,
-                     const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset, long P, int C,
+                     const float* __restrict__ prelu_alpha, int dropout, uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, long P, int C,
                      float* __restrict__ partial) {
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   channel_reduce<3>(P, C, partial, [&](long p, int c, float* a) {
     float t;
     float g = bn_bwd_g(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c, C, &t);
@@ -176,8 +178,9 @@ __global__ void bn_bwd_dx_kernel(const TG* __restrict__ dy, View dv, const TX* _
                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ gamma, const float* __restrict__ mean,
                                  const float* __restrict__ invstd, int act, float alpha,
-                                 const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset,
+                                 const float* __restrict__ prelu_alpha, int dropout, uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr,
                                  const float* __restrict__ coef, TO* __restrict__ dx, View ov, long P, int C) {
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   long total = P * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long p = i / C;
@@ -479,7 +482,7 @@ extern "C" int dg_bn_infer_affine(dg_ctx* ctx, int c, const float* gamma, const 
 
 extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale, const float* shift, int act,
                              float act_alpha, const float* prelu_alpha, const dg_tensor* residual, int dropout,
-                             uint32_t seed, uint32_t offset, const dg_tensor* y, void* stream) {
+                             uint32_t seed, uint32_t offset, const int64_t* step_counter, const dg_tensor* y, void* stream) {
   DG_REQUIRE(dg_valid(x) && dg_valid(y) && scale && shift, "dg_bn_act_fwd: null argument");
   DG_REQUIRE(dg_same_shape(x, y), "dg_bn_act_fwd: shape mismatch");
   DG_REQUIRE(act != DG_ACT_PRELU || prelu_alpha, "dg_bn_act_fwd: PReLU needs alpha");
@@ -492,7 +495,7 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
     DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
                   dgvec::bn_act_fwd8_kernel<TI, TO><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
                       (const TI*)x->ptr, dgvec::VView{x->cpitch, x->coff}, scale, shift, act, act_alpha, prelu_alpha,
-                      residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset,
+                      residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset, step_counter,
                       (TO*)y->ptr, dgvec::VView{y->cpitch, y->coff}, P, C););
     DG_CHECK_LAUNCH("dg_bn_act_fwd");
     return 0;
@@ -500,7 +503,7 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
   DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
                 bn_act_fwd_kernel<TI, TO><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
                     (const TI*)x->ptr, view_of(x), scale, shift, act, act_alpha, prelu_alpha,
-                    residual ? (const TO*)residual->ptr : nullptr, rv, dropout, seed, offset, (TO*)y->ptr, view_of(y), P, C););
+                    residual ? (const TO*)residual->ptr : nullptr, rv, dropout, seed, offset, step_counter, (TO*)y->ptr, view_of(y), P, C););
   DG_CHECK_LAUNCH("dg_bn_act_fwd");
   return 0;
 }
@@ -508,7 +511,7 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
 extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const float* scale,
                              const float* shift, const float* gamma, const float* save_mean, const float* save_invstd,
                              int act, float act_alpha, const float* prelu_alpha, int dropout, uint32_t seed,
-                             uint32_t offset, const dg_tensor* dx, float* dgamma, float* dbeta, float* dprelu_alpha,
+                             uint32_t offset, const int64_t* step_counter, const dg_tensor* dx, float* dgamma, float* dbeta, float* dprelu_alpha,
                              int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(dx) && scale && shift && gamma && save_mean && save_invstd &&
                  workspace, "dg_bn_act_bwd: null argument");
@@ -529,10 +532,10 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
       dgvec::bn_bwd_reduce8_kernel<TI, TO><<<vblocks, dgvec::VT, dgvec::red8_smem(C, 3), ST>>>(
           (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout,
-          seed, offset, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
+          seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
       dgvec::bn_bwd_dx8_kernel<TI, TO, TI><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
           (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,
-          dropout, seed, offset, coef, (TI*)dx->ptr, vdx, P, C);
+          dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);
     });
     DG_CHECK_LAUNCH("dg_bn_act_bwd");
     return 0;
@@ -540,12 +543,12 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
   DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
     bn_bwd_reduce_kernel<TI, TO><<<blocks, RED_THREADS, smem, ST>>>(
         (const TI*)dy->ptr, view_of(dy), (const TO*)x->ptr, view_of(x), scale, shift, save_mean, save_invstd, act,
-        act_alpha, prelu_alpha, dropout, seed, offset, P, C, partial);
+        act_alpha, prelu_alpha, dropout, seed, offset, step_counter, P, C, partial);
     bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, blocks, P, C, dgamma, dbeta,
                                                             act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
     bn_bwd_dx_kernel<TI, TO, TI><<<ew_blocks(P * C, ctx->sm_count), 256, 0, ST>>>(
         (const TI*)dy->ptr, view_of(dy), (const TO*)x->ptr, view_of(x), scale, shift, gamma, save_mean, save_invstd,
-        act, act_alpha, prelu_alpha, dropout, seed, offset, coef, (TI*)dx->ptr, view_of(dx), P, C);
+        act, act_alpha, prelu_alpha, dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, view_of(dx), P, C);
   });
   DG_CHECK_LAUNCH("dg_bn_act_bwd");
   return 0;

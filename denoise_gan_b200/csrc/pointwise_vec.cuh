@@ -176,7 +176,8 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(VT)
 bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                    float alpha, const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, int dropout,
-                   uint32_t seed, uint32_t offset, TO* __restrict__ y, VView yv, long P, int C) {
+                   uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, TO* __restrict__ y, VView yv, long P, int C) {
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   const uint32_t CV = (uint32_t)C >> 3;
   const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
   for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
@@ -249,9 +250,10 @@ template <typename TG, typename TX>
 __global__ void __launch_bounds__(VT)
 bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                       const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
-                      float alpha, const float* __restrict__ prelu_alpha, int dropout, uint32_t seed, uint32_t offset, long P, int C,
+                      float alpha, const float* __restrict__ prelu_alpha, int dropout, uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, long P, int C,
                       float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ dgamma, float* __restrict__ dbeta,
                       float* __restrict__ dalpha, int accumulate, float* __restrict__ coef) {
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   channel_reduce8<3>(P, C, partial, ticket, [&](long p, int c0, float (&a)[3][8]) {
     float g[8], t[8], xin[8], gy[8], mu[8], is[8];
     bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
@@ -278,7 +280,8 @@ __global__ void __launch_bounds__(VT)
 bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ invstd, int act, float alpha, const float* __restrict__ prelu_alpha, int dropout,
-                  uint32_t seed, uint32_t offset, const float* __restrict__ coef, TO* __restrict__ dx, VView ov, long P, int C) {
+                  uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, const float* __restrict__ coef, TO* __restrict__ dx, VView ov, long P, int C) {
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   const uint32_t CV = (uint32_t)C >> 3;
   const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
   for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {

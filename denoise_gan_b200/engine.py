@@ -301,7 +301,8 @@ class Engine:
 
     # ------------------------------------------------------------------ batch norm (+act, +residual, +dropout)
     def bn_act(self, x: Var, pset, name: str, *, training: bool, momentum=0.99, eps=1e-3, act=None, alpha=0.0,
-               prelu: Param | None = None, residual: Var | None = None, dropout_seed=None, dropout_offset=0) -> Var:
+               prelu: Param | None = None, residual: Var | None = None, dropout_seed=None, dropout_offset=0,
+               step_counter: torch.Tensor | None = None) -> Var:
         gamma, beta = pset[name + "/gamma"], pset[name + "/beta"]
         mm, mv = pset[name + "/moving_mean"], pset[name + "/moving_variance"]
         Cc = x.shape[3]
@@ -328,7 +329,7 @@ class Engine:
         check(self.lib.dg_bn_act_fwd(self.ctx, C.byref(tx), scale.data_ptr(), shift.data_ptr(), a_code, float(alpha),
                                      _lib.ptr(prelu.data) if prelu is not None else None,
                                      C.byref(tres) if tres is not None else None, drop, int(dropout_seed or 0), int(dropout_offset),
-                                     C.byref(ty), self.st))
+                                     _lib.ptr(step_counter), C.byref(ty), self.st))
         inputs = [x] + ([residual] if residual is not None else [])
         out = Var(y, self._deps(inputs, gamma.group), seq)
 
@@ -348,7 +349,8 @@ class Engine:
             check(self.lib.dg_bn_act_bwd(self.ctx, C.byref(tg), C.byref(tx), scale.data_ptr(), shift.data_ptr(), gamma.data.data_ptr(),
                                          mean.data_ptr(), invstd.data_ptr(), a_code, float(alpha),
                                          _lib.ptr(prelu.data) if prelu is not None else None, drop, int(dropout_seed or 0),
-                                         int(dropout_offset), C.byref(tdx), dg, db, da, acc, ws.data_ptr(), nbytes, self.st))
+                                         int(dropout_offset), _lib.ptr(step_counter), C.byref(tdx), dg, db, da, acc, ws.data_ptr(), nbytes,
+                                         self.st))
             res = [dx if need_in[0] else None]
             if residual is not None:
                 res.append(gy if need_in[1] else None)

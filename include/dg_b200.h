@@ -107,14 +107,17 @@ int dg_bn_stats(dg_ctx*, const dg_tensor* x, const float* gamma, const float* be
 /* inference: scale/shift from the moving statistics */
 int dg_bn_infer_affine(dg_ctx*, int c, const float* gamma, const float* beta, const float* moving_mean,
                        const float* moving_var, float eps, float* scale, float* shift, void* stream);
-/* y = act(drop(x*scale+shift)) + residual ; drop: keep-mask from (seed, offset), kept units x2 (pix2pix.py:138) */
+/* y = act(drop(x*scale+shift)) + residual ; drop: keep-mask from (seed, offset), kept units x2 (pix2pix.py:138).
+ * step_counter (device int64, may be NULL) is mixed into the seed so that every optimiser step draws a new mask
+ * even when the step is replayed from a CUDA graph: seed_eff = seed + (uint32)(*step_counter) * 0x9E3779B9. */
 int dg_bn_act_fwd(dg_ctx*, const dg_tensor* x, const float* scale, const float* shift, int act, float act_alpha,
                   const float* prelu_alpha, const dg_tensor* residual, int dropout, uint32_t seed, uint32_t offset,
-                  const dg_tensor* y, void* stream);
+                  const int64_t* step_counter, const dg_tensor* y, void* stream);
 /* backward of the above: dx, dgamma, dbeta (and dprelu_alpha when act == PRELU) */
 int dg_bn_act_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const float* scale, const float* shift,
                   const float* gamma, const float* save_mean, const float* save_invstd, int act, float act_alpha,
-                  const float* prelu_alpha, int dropout, uint32_t seed, uint32_t offset, const dg_tensor* dx,
+                  const float* prelu_alpha, int dropout, uint32_t seed, uint32_t offset, const int64_t* step_counter,
+                  const dg_tensor* dx,
                   float* dgamma, float* dbeta, float* dprelu_alpha, int accumulate, void* workspace,
                   size_t workspace_bytes, void* stream);
 

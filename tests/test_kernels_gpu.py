@@ -268,14 +268,14 @@ def test_bn_act_fwd_bwd(L, C_, act, with_res, dropout, dtype, N, H, W):
     resd = dev(res, dtype) if with_res else None
     tres = L.tensor(resd) if with_res else None
     L.check(lib.dg_bn_act_fwd(ctx, C.byref(tx), scale.data_ptr(), shift.data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None,
-                              C.byref(tres) if with_res else None, 1 if dropout else 0, seed, off, C.byref(ty), st))
+                              C.byref(tres) if with_res else None, 1 if dropout else 0, seed, off, None, C.byref(ty), st))
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     assert relerr(y, t) < tol
     assert relerr(mm, stt["bn/moving_mean"]) < 1e-5 and relerr(mv, stt["bn/moving_variance"]) < 1e-5
     dx = torch.empty_like(xd); dgam, dbet, dalp = [torch.empty(C_, device="cuda") for _ in range(3)]
     tgy, tdx = L.tensor(gyd), L.tensor(dx)
     L.check(lib.dg_bn_act_bwd(ctx, C.byref(tgy), C.byref(tx), scale.data_ptr(), shift.data_ptr(), gd.data_ptr(), mean.data_ptr(),
-                              invstd.data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None, 1 if dropout else 0, seed, off,
+                              invstd.data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None, 1 if dropout else 0, seed, off, None,
                               C.byref(tdx), dgam.data_ptr(), dbet.data_ptr(), dalp.data_ptr(), 0, wk.data_ptr(), nb, st))
     gtol = 2e-5 if dtype == torch.float32 else BF16_TOL
     assert relerr(dx, xr.grad) < gtol
