@@ -54,6 +54,9 @@ SIGNATURES = {
     "dg_umma_pack_weights_batch": (_i, [_P, _P, _i, _P]),
     "dg_umma_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
+    "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
+    "dg_umma_conv2d_dgrad_supported": (_i, [_P, _T, _T, _CP]),
+    "dg_bias_grad": (_i, [_P, _T, _P, _i, _P, _sz, _P]),
     "dg_debug_conv_timeline": (None, [_P]),
     "dg_debug_conv_flags": (None, [_i]),
     "dg_umma_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),

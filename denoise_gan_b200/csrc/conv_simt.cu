@@ -469,7 +469,7 @@ extern "C" int dg_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const float* w,
 extern "C" size_t dg_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
   long P = (long)dy->n * dy->h * dy->w;
   int splits = wgrad_splits(P);
-  if (splits < THIN_WGRAD_BLOCKS) splits = THIN_WGRAD_BLOCKS;  // the thin-layer path writes up to this many partials
+  if (thin_wgrad_applicable(x, dy, p)) splits = THIN_WGRAD_BLOCKS;  // the thin-layer path writes up to this many partials
   return (size_t)splits * ((size_t)p->kh * p->kw * x->c * dy->c + dy->c) * sizeof(float);
 }
 

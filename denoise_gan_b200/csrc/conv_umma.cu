@@ -412,7 +412,7 @@ struct TapSpec {
 // Builds the launch description and runs the kernel.
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
                 const TapSpec* taps, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
-                const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st) {
+                const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
   DG_REQUIRE(in->cpitch % 8 == 0 && in->coff % 8 == 0 && ((uintptr_t)in->ptr % 16) == 0, "%s: input view not 16-byte aligned", name);
@@ -472,6 +472,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
         if (need <= budget) { best_nb = nb; best_mt = mt; best_res = res; }
       }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d taps=%d)", name, in->c, cout, n_taps);
+  if (dry) return 0;   // capability query: a tile configuration exists
   const int nb = best_nb, mt = best_mt;
   P.nb = nb; P.mt = mt; P.resident = best_res;
   P.w_block_bytes = (uint32_t)nb * kc * 2;
@@ -591,10 +592,9 @@ extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, in
   return 0;
 }
 
-extern "C" int dg_umma_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias,
-                                  const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream) {
+static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                         const dg_conv_params* p, void* stream, bool dry) {
   DG_REQUIRE(dg_valid(x) && dg_valid(y) && w_packed && p, "dg_umma_conv2d_fwd: null argument");
-  DG_REQUIRE(bn_partials == nullptr, "dg_umma_conv2d_fwd: fused BN partials not available in this build");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
   DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
   DG_REQUIRE(p->kh * p->kw <= MAX_TAPS, "dg_umma_conv2d_fwd: kernel too large");
@@ -617,11 +617,22 @@ extern "C" int dg_umma_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const void* w
       }
   }
   return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
-                     p->act, p->act_alpha, (cudaStream_t)stream);
+                     p->act, p->act_alpha, (cudaStream_t)stream, dry);
 }
 
-extern "C" int dg_umma_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const float* bias,
-                                    const dg_tensor* dx, const dg_conv_params* p, void* stream) {
+extern "C" int dg_umma_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias,
+                                  const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream) {
+  DG_REQUIRE(bn_partials == nullptr, "dg_umma_conv2d_fwd: fused BN partials not available in this build");
+  return conv_fwd_impl(ctx, x, w_packed, bias, y, p, stream, false);
+}
+
+// 1 when the tensor-core kernel has a tile configuration for this layer (shared-memory fit), else 0
+extern "C" int dg_umma_conv2d_fwd_supported(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p) {
+  return conv_fwd_impl(ctx, x, (const void*)1, nullptr, y, p, nullptr, true) == 0 ? 1 : 0;
+}
+
+static int conv_dgrad_impl(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const float* bias, const dg_tensor* dx,
+                           const dg_conv_params* p, void* stream, bool dry) {
   DG_REQUIRE(dg_valid(dy) && dg_valid(dx) && w_packed && p, "dg_umma_conv2d_dgrad: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_dgrad: stride must be 1 or 2");
   DG_REQUIRE(dx->n == dy->n, "dg_umma_conv2d_dgrad: batch mismatch");
@@ -633,7 +644,7 @@ extern "C" int dg_umma_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const void
     for (int r = 0; r < p->kh; ++r)
       for (int s = 0; s < p->kw; ++s) taps[n_taps++] = TapSpec{0, p->pad_t - r, p->pad_l - s, r * p->kw + s};
     return launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_taps, w_packed, dx->c, dx, dense, bias,
-                       p->act, p->act_alpha, (cudaStream_t)stream);
+                       p->act, p->act_alpha, (cudaStream_t)stream, dry);
   }
   DG_REQUIRE(dx->h % 2 == 0 && dx->w % 2 == 0, "dg_umma_conv2d_dgrad: stride 2 needs even image size");
   for (int a = 0; a < 2; ++a)
@@ -648,10 +659,19 @@ extern "C" int dg_umma_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const void
       }
       DG_REQUIRE(n_taps > 0, "dg_umma_conv2d_dgrad: output phase without taps (kernel smaller than stride)");
       if (launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_taps, w_packed, dx->c, dx, Lattice{2, a, b},
-                      bias, p->act, p->act_alpha, (cudaStream_t)stream))
+                      bias, p->act, p->act_alpha, (cudaStream_t)stream, dry))
         return 1;
     }
   return 0;
+}
+
+extern "C" int dg_umma_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const float* bias,
+                                    const dg_tensor* dx, const dg_conv_params* p, void* stream) {
+  return conv_dgrad_impl(ctx, dy, w_packed, bias, dx, p, stream, false);
+}
+
+extern "C" int dg_umma_conv2d_dgrad_supported(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p) {
+  return conv_dgrad_impl(ctx, dy, (const void*)1, nullptr, dx, p, nullptr, true) == 0 ? 1 : 0;
 }
 
 // wgrad on tensor cores: see conv_umma_wgrad.cu

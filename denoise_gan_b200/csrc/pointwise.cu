@@ -424,6 +424,11 @@ __global__ void vgg_pre_bwd_kernel(const TI* __restrict__ dy, View dv, TO* __res
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) bias_grad_kernel(const T* __restrict__ dy, View dv, long P, int C, float* __restrict__ partial) {
+  channel_reduce<1>(P, C, partial, [&](long p, int c, float* a) { a[0] += ld_f(dy + (p * dv.pitch + dv.off + c)); });
+}
+
 inline View view_of(const dg_tensor* t) { return View{t->cpitch, t->coff}; }
 inline unsigned ew_blocks(long total, int sm_count) {
   long b = (total + 255) / 256;
@@ -756,5 +761,23 @@ extern "C" int dg_vgg_preprocess_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_
                 vgg_pre_bwd_kernel<TI, TO><<<ew_blocks(P * 3, ctx->sm_count), 256, 0, ST>>>(
                     (const TI*)dy->ptr, view_of(dy), (TO*)dx->ptr, view_of(dx), P););
   DG_CHECK_LAUNCH("dg_vgg_preprocess_bwd");
+  return 0;
+}
+
+// dbias[c] (+)= sum over pixels of dy[.., c]  (bias gradient of Conv2DTranspose, pix2pix.py:169-173)
+extern "C" int dg_bias_grad(dg_ctx* ctx, const dg_tensor* dy, float* dbias, int accumulate, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dbias && workspace, "dg_bias_grad: null argument");
+  DG_REQUIRE(dy->c <= RED_THREADS * MAX_CPT, "dg_bias_grad: C too large");
+  DG_REQUIRE(workspace_bytes >= dg_bn_workspace_bytes(dy), "dg_bias_grad: workspace too small");
+  long P = dg_pixels(dy);
+  int C = dy->c;
+  int blocks = red_blocks(P, C, ctx->sm_count);
+  int R = RED_THREADS / red_lanes(C);
+  float* partial = (float*)workspace;
+  DG_DISPATCH_1(dy->dtype, "dg_bias_grad",
+                bias_grad_kernel<T><<<blocks, RED_THREADS, (size_t)R * C * sizeof(float), ST>>>((const T*)dy->ptr, view_of(dy), P, C, partial););
+  sum_partials_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, blocks, C, dbias, accumulate);
+  DG_CHECK_LAUNCH("dg_bias_grad");
   return 0;
 }

@@ -61,6 +61,7 @@ class Engine:
         self.use_umma_wgrad = self.use_umma
         self.launches = 0
         self.record = None             # dict name -> Var when a test wants per-layer activations
+        self._cap: dict = {}
         self.grad_record = None        # dict seq -> dL/dVar of the generator pass when a test wants per-layer gradients
         self.prof = None               # list of (kind, flops, ev0, ev1) when bench.py profiles a step
 
@@ -143,6 +144,19 @@ class Engine:
         return (self.use_umma and x.dtype == torch.bfloat16 and cin % 16 == 0 and cout % 16 == 0 and kh * kw <= 16
                 and stride in (1, 2) and (stride == 1 or (H % 2 == 0 and W % 2 == 0)))
 
+    def _umma_supported(self, kind: str, a: torch.Tensor, b: torch.Tensor, cp: DgConvParams) -> bool:
+        """Asks the library whether the tensor-core kernel has a tile configuration for this layer (shared-memory
+        fit); layers it cannot take yet (e.g. pix2pix's 4x4 stride-2 convs with >= 128 channels) are routed to the
+        CUDA-core kernels EXPLICITLY here -- the C ABI itself never falls back."""
+        key = (kind, tuple(a.shape), tuple(b.shape), cp.kh, cp.kw, cp.stride, cp.pad_t, cp.pad_l)
+        r = self._cap.get(key)
+        if r is None:
+            ta, tb = tensor(a), tensor(b)
+            fn = self.lib.dg_umma_conv2d_fwd_supported if kind == "fwd" else self.lib.dg_umma_conv2d_dgrad_supported
+            r = bool(fn(self.ctx, C.byref(ta), C.byref(tb), C.byref(cp)))
+            self._cap[key] = r
+        return r
+
     def _packed(self, p: Param, mode: int) -> torch.Tensor:
         attr = "packed_fwd" if mode == 0 else "packed_dgrad"
         t = getattr(p, attr)
@@ -163,11 +177,14 @@ class Engine:
         seq = self._next()
         y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
         cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
+        lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
         umma = self._umma_ok(x.t, cin, cout, kh, kw, stride, H, W)
+        umma_f = umma and self._umma_supported("fwd", x.t, y, lin)
+        umma_d = umma and self._umma_supported("dgrad", y, x.t, lin)
         tx, ty = tensor(x.t), tensor(y)
         bias = _lib.ptr(b.data) if b is not None else None
         flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
-        if umma:
+        if umma_f:
             pk = self._packed(w, 0)
             self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
                 self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), None, self.st)))
@@ -175,7 +192,6 @@ class Engine:
             self._timed("simt_conv", flops, lambda: check(self.lib.dg_conv2d_fwd(
                 self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st)))
         out = Var(y, self._deps([x], w.group), seq)
-        lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag):
             dpre = gy
@@ -190,7 +206,7 @@ class Engine:
             if need_in[0]:
                 dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
                 tdx = tensor(dx)
-                if umma and dpre.dtype == torch.bfloat16:
+                if umma_d and dpre.dtype == torch.bfloat16:
                     pk = self._packed(w, 1)
                     self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
                         self.ctx, C.byref(tdp), pk.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
@@ -214,6 +230,9 @@ class Engine:
         if (self.use_umma_wgrad and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and
                 self._umma_ok(x, cin, cout, kh, kw, lin.stride, x.shape[1], x.shape[2])):
             nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))
+        else:
+            nbytes = 0
+        if nbytes > 0:     # 0 = the tensor-core wgrad has no tile configuration for this layer
             ws = self.workspace(nbytes)
             self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
                 self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc, ws.data_ptr(), nbytes, self.st)))
@@ -239,9 +258,11 @@ class Engine:
         lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
         # as a forward conv f, the kernel is HWIO with I = cout (of the transposed conv), O = cin
         umma = self._umma_ok(x.t, cin, cout, kh, kw, stride, Ho, Wo)
+        umma_up = umma and self._umma_supported("dgrad", x.t, y, lin)     # y = dgrad_f(x)
+        umma_dn = umma and self._umma_supported("fwd", y, x.t, lin)       # dx = f(dy)
         tx, ty = tensor(x.t), tensor(y)
         bias = _lib.ptr(b.data) if b is not None else None
-        if umma:
+        if umma_up:
             check(self.lib.dg_umma_conv2d_dgrad(self.ctx, C.byref(tx), self._packed(w, 1).data_ptr(), bias, C.byref(ty), C.byref(cp), self.st))
         else:
             check(self.lib.dg_conv2d_dgrad(self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st))
@@ -257,12 +278,15 @@ class Engine:
                 # dWt = wgrad of f with "input" = dY (large image) and "output grad" = x (small image)
                 self._wgrad(dpre, x.t, w, None, lin)
                 if b is not None:
-                    raise NotImplementedError("bias gradient of Conv2DTranspose handled by caller")
+                    tdp2 = tensor(dpre)
+                    nb2 = self.lib.dg_bn_workspace_bytes(C.byref(tdp2))
+                    ws2 = self.workspace(nb2)
+                    check(self.lib.dg_bias_grad(self.ctx, C.byref(tdp2), b.grad.data_ptr(), self._acc_flag(b), ws2.data_ptr(), nb2, self.st))
             dx = None
             if need_in[0]:
                 dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
                 tdp, tdx = tensor(dpre), tensor(dx)
-                if umma and dpre.dtype == torch.bfloat16:
+                if umma_dn and dpre.dtype == torch.bfloat16:
                     check(self.lib.dg_umma_conv2d_fwd(self.ctx, C.byref(tdp), self._packed(w, 0).data_ptr(), None, C.byref(tdx), C.byref(lin), None, self.st))
                 else:
                     check(self.lib.dg_conv2d_fwd(self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))

@@ -141,3 +141,53 @@ class VGG19Features(_Net):
             if blk < 5:
                 t = E.maxpool2x2(t)
         return t
+
+
+class Pix2PixGenerator(_Net):
+    """pix2pix.py:144-192: 8 x (Conv 4x4 s2 [+BN] + LeakyReLU(0.3)) down, 7 x (Conv2DTranspose 4x4 s2 + BN
+    [+Dropout 0.5 on the first three] + ReLU, concat skip) up, Conv2DTranspose -> 3 + tanh."""
+    DOWN = [64, 128, 256, 512, 512, 512, 512, 512]
+    UP = [512, 512, 512, 512, 256, 128, 64]
+
+    def __init__(self, engine, pset, dropout_seed=7):
+        super().__init__(engine, pset)
+        self.dropout_seed = dropout_seed
+
+    def __call__(self, x, training=True, pass_id=0) -> Var:
+        """`pass_id` separates the dropout streams of the two generator passes of one train step
+        (gen_output and the identity term, pix2pix.py:90)."""
+        E, p = self.E, self.p
+        t = E.cast(self._in(x), E.act_dtype)
+        skips = []
+        for i in range(len(self.DOWN)):
+            w = p[f"g/down{i}/conv/kernel"]
+            if i == 0:
+                t = E.conv2d(t, w, None, stride=2, act="lrelu", alpha=0.3)
+            else:
+                t = E.conv2d(t, w, None, stride=2)
+                t = E.bn_act(t, p, f"g/down{i}/bn", training=training, act="lrelu", alpha=0.3)
+            skips.append(t)
+        skips = list(reversed(skips[:-1]))
+        for i in range(len(self.UP)):
+            t = E.conv2d_transpose(t, p[f"g/up{i}/convt/kernel"], None, stride=2)
+            drop = self.dropout_seed if (i < 3 and training) else None
+            t = E.bn_act(t, p, f"g/up{i}/bn", training=training, act="relu", dropout_seed=drop,
+                         dropout_offset=(pass_id * 3 + i) << 24, step_counter=p.opt_state if p.trainable else None)
+            t = E.concat([t, skips[i]])
+        return E.conv2d_transpose(t, p["g/last/kernel"], p["g/last/bias"], stride=2, act="tanh", out_dtype=torch.float32)
+
+
+class Pix2PixDiscriminator(_Net):
+    """pix2pix.py:194-220: PatchGAN on concat(input, target); ZeroPadding2D + VALID 4x4 convs at the end."""
+
+    def __call__(self, inputs, training=True) -> Var:
+        E, p = self.E, self.p
+        inp, tar = inputs
+        t = E.concat([E.cast(self._in(inp), E.act_dtype), E.cast(self._in(tar), E.act_dtype)])
+        t = E.conv2d(t, p["d/down1/conv/kernel"], None, stride=2, act="lrelu", alpha=0.3)
+        for i in (2, 3):
+            t = E.conv2d(t, p[f"d/down{i}/conv/kernel"], None, stride=2)
+            t = E.bn_act(t, p, f"d/down{i}/bn", training=training, act="lrelu", alpha=0.3)
+        t = E.conv2d(t, p["d/conv4/kernel"], None, stride=1, padding=((1, 1), (1, 1)))
+        t = E.bn_act(t, p, "d/bn4", training=training, act="lrelu", alpha=0.3)
+        return E.conv2d(t, p["d/last/kernel"], p["d/last/bias"], stride=1, padding=((1, 1), (1, 1)), out_dtype=torch.float32)

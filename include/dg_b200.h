@@ -83,6 +83,10 @@ int dg_umma_conv2d_fwd(dg_ctx*, const dg_tensor* x, const void* w_packed, const 
                        const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream);
 int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,
                          const dg_tensor* dx, const dg_conv_params* p, void* stream);
+/* capability queries: 1 when the tensor-core kernels have a tile configuration for the layer (shared-memory fit);
+ * callers route the remaining layers to the CUDA-core kernels explicitly */
+int dg_umma_conv2d_fwd_supported(dg_ctx*, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p);
+int dg_umma_conv2d_dgrad_supported(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p);
 /* debug aid (tools/conv_timeline.py): device buffer of 3*16*4 int64 receiving clock64() marks of CTA 0, or NULL */
 void dg_debug_conv_timeline(void* dev_buffer);
 void dg_debug_conv_flags(int flags); /* debug experiments only: results are WRONG when non-zero */
@@ -141,6 +145,8 @@ int dg_maxpool2x2_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg
 int dg_upsample2x_relu_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
 int dg_upsample2x_relu_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* dx, void* stream);
 
+/* dbias[c] (+)= sum_pixels dy[..,c]: bias gradient of Conv2DTranspose (pix2pix.py:169-173) */
+int dg_bias_grad(dg_ctx*, const dg_tensor* dy, float* dbias, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 /* vgg19.preprocess_input(((x+1)*255)/2), 'caffe' mode: RGB->BGR, subtract (103.939,116.779,123.68) (srgan.py:71-72) */
 int dg_vgg_preprocess_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
 int dg_vgg_preprocess_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, void* stream);

@@ -108,3 +108,56 @@ def test_fsrgan_step_bf16_runs_and_tracks_fp32():
                               x.double(), y.double(), fsrgan=True)
     for a, b in zip(ours, ref):
         assert abs(a - float(b)) <= 2e-2 * max(1.0, abs(float(b))), (ours, [float(v) for v in ref])
+
+
+def test_pix2pix_step_fp32():
+    """train_pix2pix.py:33-71 at the reference's hard-coded 256x256 (batch 1): 8-down/8-up U-Net with
+    Conv2DTranspose, dropout (shared counter-based mask), PatchGAN on concat(input, target), identity pass."""
+    import numpy as np
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.pix2pix import Pix2Pix
+    from denoise_gan_b200.train_pix2pix import train_step
+    from oracle import ops_np as ON
+    model = Pix2Pix(SimpleNamespace(crop_size=256, lr=2e-4, fp16=0, vgg=0, retrain=0, seed=0, dropout_seed=7))
+    g0, d0 = P.init_pix2pix(0)
+    g0, d0 = perturb(g0), perturb(d0)
+    model.gen_params.load(g0); model.disc_params.load(d0)
+    x, y = synthetic_pair(1, 256, 1, step=0)
+    ours = [float(v) for v in train_step(model, x.cuda(), y.cuda())]
+    torch.cuda.synchronize()
+
+    def masks(pass_id):
+        out = []
+        for i in range(3):
+            hw = 2 ** (i + 1)
+            shape = (1, hw, hw, 512)
+            m = ON.dropout_keep_mask(7, (pass_id * 3 + i) << 24, int(np.prod(shape)))
+            out.append(torch.from_numpy(m).view(shape))
+        return out
+
+    res = []
+    for dt in (torch.float64, torch.float32):
+        g = {k: v.to(dt).clone() for k, v in g0.items()}; d = {k: v.to(dt).clone() for k, v in d0.items()}
+        out = {}
+        losses = OS.pix2pix_train_step(g, d, None, OT.KerasAdam(2e-4, beta1=0.5), OT.KerasAdam(2e-4, beta1=0.5), x.to(dt), y.to(dt),
+                                       masks(0), masks(1), out=out)
+        res.append((losses, out))
+    (l64, out), (l32, out32) = res
+    from _parity import noise_bound
+    e, bnd = noise_bound(model.last["gen_output"].t, out["gen_output"], out32["gen_output"], 5e-5, metric=relerr)
+    assert e <= bnd, f"gen_output {e} > {bnd}"
+    e, bnd = noise_bound(model.last["disc_fake"].t, out["disc_fake"], out32["disc_fake"], 1e-4, metric=relerr)
+    assert e <= bnd, f"disc_fake {e} > {bnd}"
+    worst = []
+    for ours_g, refs, refs32 in ((model.gen_params.grads(), out["gen_grads"], out32["gen_grads"]),
+                                 (model.disc_params.grads(), out["disc_grads"], out32["disc_grads"])):
+        for name, ref in refs.items():
+            e, bnd = noise_bound(ours_g[name], ref, refs32[name], 2e-4, k=6.0)
+            worst.append((e / bnd, e, bnd, name))
+    worst.sort(reverse=True)
+    print("pix2pix worst gradient errors (err/bound, err, bound, name):", worst[:5])
+    assert worst[0][0] <= 1.0, worst[:5]
+    for n, a, ref, ref32 in zip(["total", "gan", "l1", "l2", "content", "disc", "var", "identity"], ours, l64, l32):
+        tol = 5e-5 * max(1.0, abs(ref.item())) + 3.0 * abs(ref32.item() - ref.item())
+        assert abs(a - ref.item()) <= tol, f"{n}: {a} vs {ref.item()}"
