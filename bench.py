@@ -143,6 +143,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("DG_BENCH_WATCHDOG_S", "420")), exit=True)   # a hung rank reports where, then dies
+
+    def trace(msg):
+        if os.environ.get("DG_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -159,6 +165,7 @@ def main():
         from denoise_gan_b200.parallel import GradAllReduce
         model.comm = GradAllReduce(model.device)
         model.world_size = world
+    trace("model built")
     x_h, y_h = synthetic_pair(batch, crop, scale, step=0, rank=rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -173,6 +180,7 @@ def main():
         step = GraphedStep(model, train_step, x_h, y_h, warmup=2, debug_dot=dot)
         run = step
         kernel_nodes = step.kernel_nodes
+    trace("step captured")
 
     def barrier():
         if world > 1:
@@ -181,6 +189,7 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         run()
+    trace("warmup enqueued")
     # ---- device-resident throughput (inputs already in HBM)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -193,6 +202,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    trace(f"device-resident timing done: {ms:.3f} ms/step")
     # ---- end-to-end through train_step with HOST batches: H2D of the batch + D2H of the 7 losses every step
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -205,6 +215,7 @@ def main():
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    trace("e2e timing done")
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -260,8 +271,15 @@ def main():
             line["cpu_baseline"] = {"value": args.cpu_batch / t_cpu, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"2 timed steps of batch {args.cpu_batch} (of the {batch}-image step), torch-CPU oracle restatement"}
         print(json.dumps(line), flush=True)
+    trace("done")
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
-        dist.destroy_process_group()
+        # The captured step graph holds NCCL kernels; tearing the communicator down underneath it can block
+        # forever.  Everything is synchronised and printed: leave without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
