@@ -1,0 +1,144 @@
+"""Inference entry points: the generator forward with `training=False` (BatchNorm on its moving statistics,
+dropout off) wrapped in the reference's frame arithmetic.
+
+Reference: infer_video.py:92-97 (model re-wrapped on Input((None,None,3)), training=False), :138-159 (per-frame
+pre/post), :79-83 (padded size); infer.py:38-68 (still images); unit_test.py:56-86 (256x256 crops).
+
+Only uint8 frames cross PCIe: the crop-or-pad, scaling and channel flip run on the device
+(csrc/frames.cu) next to the forward; host staging buffers are pinned and double-buffered so the copy of frame
+i+1 overlaps the forward of frame i.  Frames shard round-robin across ranks with no collective
+(`frames_for_rank`).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def padded_size(fh: int, fw: int, block: int = 256, model_scale: int = 1):
+    """infer_video.py:79-83."""
+    m = block * model_scale
+    return (fh + m) - fh % m, (fw + m) - fw % m
+
+
+def frames_for_rank(num_frames: int, rank: int, world: int, start: int = 0):
+    """Round-robin frame shard of one rank (inference: no exchange step)."""
+    return range(start + rank, num_frames, world)
+
+
+def _u8(frame) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame.contiguous()
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+        raise ValueError(f"expected a uint8 [H, W, 3] frame, got {t.dtype} {tuple(t.shape)}")
+    return t
+
+
+class FrameRunner:
+    """Runs `model.generator(x, training=False)` on uint8 frames.  `model` is any of Autoencoder / SRGAN /
+    FastSRGAN / Pix2Pix; `upscale` is the generator's output/input size ratio (4 for the SR models at scale 4)."""
+
+    def __init__(self, model, upscale: int | None = None):
+        self.model, self.E = model, model.engine
+        self.upscale = int(upscale if upscale is not None else getattr(model, "scale", 1))
+        self.copy_stream = torch.cuda.Stream(device=self.E.device)
+        self._pin: dict = {}
+
+    # ---- device-side pieces
+    def _to_float(self, frame_dev: torch.Tensor, out_h: int, out_w: int, flip: bool, norm_mode: int, scale: float, offset: float):
+        E = self.E
+        h, w = frame_dev.shape[:2]
+        x = E.buf(("infer_in",), (1, out_h, out_w, 3), torch.float32)
+        _lib.check(E.lib.dg_frame_to_float(E.ctx, frame_dev.data_ptr(), h, w, int(flip), norm_mode, scale, offset, _lib.tensor(x), E.st))
+        return x
+
+    def _to_frame(self, y: torch.Tensor, out_h: int, out_w: int, scale: float, offset: float, clip: bool, flip: bool, slot=0):
+        E = self.E
+        out = E.buf(("infer_out", slot), (out_h, out_w, 3), torch.uint8)
+        _lib.check(E.lib.dg_float_to_frame(E.ctx, _lib.tensor(y), scale, offset, int(clip), int(flip), out.data_ptr(), out_h, out_w, E.st))
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """NHWC float [-1,1] (or [0,1] for infer.py / unit_test.py callers) -> generator output, training=False."""
+        self.E.new_step()
+        return self.model.generator(x, training=False).t
+
+    def _pinned(self, key, shape):
+        k = (key, tuple(shape))
+        if k not in self._pin:
+            self._pin[k] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+        return self._pin[k]
+
+    def _h2d(self, frame: torch.Tensor, slot=0) -> torch.Tensor:
+        if frame.is_cuda:
+            return frame
+        stage = self._pinned(("in", slot), frame.shape)
+        stage.copy_(frame)
+        dev = self.E.buf(("infer_u8", slot), tuple(frame.shape), torch.uint8)
+        dev.copy_(stage, non_blocking=True)
+        return dev
+
+    # ---- the three reference call sites
+    def video_frame(self, frame_bgr, to_host: bool = True):
+        """infer_video.py:138-159: BGR uint8 [fh,fw,3] -> RGB uint8 [fh*s, fw*s, 3]."""
+        f = _u8(frame_bgr)
+        fh, fw = f.shape[:2]
+        nh, nw = padded_size(fh, fw)
+        x = self._to_float(self._h2d(f), nh, nw, flip=True, norm_mode=0, scale=2.0, offset=-1.0)
+        y = self.forward(x)
+        out = self._to_frame(y, fh * self.upscale, fw * self.upscale, 0.5, 0.5, clip=True, flip=False)
+        return self._d2h(out) if to_host else out
+
+    def still_image(self, img_bgr, to_host: bool = True):
+        """infer.py:50-68: BGR uint8 -> [0,1] RGB (float64 division) -> forward -> ((sr+1)/2)*255 -> BGR uint8."""
+        f = _u8(img_bgr)
+        h, w = f.shape[:2]
+        y = self.forward(self._to_float(self._h2d(f), h, w, flip=True, norm_mode=1, scale=1.0, offset=0.0))
+        out = self._to_frame(y, y.shape[1], y.shape[2], 0.5, 0.5, clip=False, flip=True)
+        return self._d2h(out) if to_host else out
+
+    def unit_image(self, img_bgr, to_host: bool = True):
+        """unit_test.py:67-86: top-left 256x256 crop, float32 / 255, forward, np.uint8(((sr+1)/2)*255) (RGB)."""
+        f = _u8(img_bgr)[:256, :256].contiguous()
+        h, w = f.shape[:2]
+        y = self.forward(self._to_float(self._h2d(f), h, w, flip=True, norm_mode=2, scale=1.0, offset=0.0))
+        out = self._to_frame(y, y.shape[1], y.shape[2], 0.5, 0.5, clip=False, flip=False)
+        return self._d2h(out) if to_host else out
+
+    def _d2h(self, out_dev: torch.Tensor, slot=0) -> torch.Tensor:
+        host = self._pinned(("out", slot), out_dev.shape)
+        host.copy_(out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.clone()
+
+    def video(self, frames, rank: int = 0, world: int = 1):
+        """Generator over (index, RGB uint8 frame) for this rank's round-robin shard of `frames` (a sequence of BGR
+        uint8 frames).  The upload of the next frame runs on a copy stream under the current forward."""
+        idx = list(frames_for_rank(len(frames), rank, world))
+        if not idx:
+            return
+        main = torch.cuda.current_stream()
+
+        def upload(k):
+            f = _u8(frames[idx[k]])
+            slot = k & 1
+            stage = self._pinned(("in", slot), f.shape)
+            stage.copy_(f)
+            dev = self.E.buf(("infer_u8", slot), tuple(f.shape), torch.uint8)
+            with torch.cuda.stream(self.copy_stream):
+                dev.copy_(stage, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record()
+            return dev, ev
+
+        nxt = upload(0)
+        for k in range(len(idx)):
+            dev, ev = nxt
+            main.wait_event(ev)
+            out = self.video_frame(dev, to_host=False)
+            if k + 1 < len(idx):
+                nxt = upload(k + 1)          # other slot; its last reader (frame k-1) finished before the previous yield
+            host = self._pinned(("out", 0), out.shape)
+            host.copy_(out, non_blocking=True)
+            main.synchronize()
+            yield idx[k], host.clone()

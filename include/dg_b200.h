@@ -151,6 +151,19 @@ int dg_bias_grad(dg_ctx*, const dg_tensor* dy, float* dbias, int accumulate, voi
 int dg_vgg_preprocess_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
 int dg_vgg_preprocess_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, void* stream);
 
+/* ---- frame pre/post-processing around the inference forward (infer_video.py:138-159, infer.py:50-68,
+ * unit_test.py:67-86).  src/dst frames are packed uint8 [n, h, w, 3] in DEVICE memory.
+ * dg_frame_to_float: centre crop-or-pad (tf.image.resize_with_crop_or_pad, infer_video.py:142) of the frame to
+ *   dst's h x w, u8 -> [0,1] (norm_mode 0: float32 * (1/255) as tf.image.convert_image_dtype, infer_video.py:141;
+ *   1: float64 '/ 255.0' then cast, infer.py:58; 2: float32 '/ 255', unit_test.py:74), padding pixels = 0,
+ *   then v*scale + offset (infer_video.py:145 uses 2,-1), optional BGR<->RGB flip (cv2.cvtColor, :140).
+ * dg_float_to_frame: v = src*scale + offset (infer_video.py:149 uses 0.5,0.5), centre crop-or-pad to dst_h x dst_w
+ *   with zeros (:156), optional clip to [0,1] (:156), *255 and truncation to uint8 (:158-159), optional flip. */
+int dg_frame_to_float(dg_ctx*, const uint8_t* src, int src_h, int src_w, int flip_channels, int norm_mode, float scale, float offset,
+                      const dg_tensor* dst, void* stream);
+int dg_float_to_frame(dg_ctx*, const dg_tensor* src, float scale, float offset, int clip01, int flip_channels, uint8_t* dst,
+                      int dst_h, int dst_w, void* stream);
+
 /* ---- losses: value sums and upstream gradients in one pass */
 size_t dg_loss_workspace_bytes(const dg_tensor* t);
 /* out3 = {mean|t-g|, mean(t-g)^2, mean_b TV(t-g)};  dgen (+)= w_mae*dMAE + w_mse*dMSE + w_tv*dTV
