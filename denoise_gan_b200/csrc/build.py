@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SOURCES = ["api.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_wgrad.cu", "pointwise.cu", "dwconv.cu", "frames.cu", "loss_adam.cu"]
-HEADERS = ["dg_common.cuh", "reduce.cuh", "sm100.cuh", "../../include/dg_b200.h"]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + ["../../include/dg_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -277,14 +277,34 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
   dst[i] = accumulate ? dst[i] + s : s;
 }
 
-// dst[i] (+)= sum_z part[z*stride + offset + i]
-__global__ void reduce_strided_kernel(const float* __restrict__ part, long stride, long offset, float* __restrict__ dst, long numel,
-                                      int splits, int accumulate) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= numel) return;
+// dst[i] (+)= sum_z part[z*stride + i] for i < n0 (dst0) and n0 <= i < n0+n1 (dst1): block = 32 elements x 32 groups of
+// splits, four independent loads in flight per thread, fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024)
+reduce_strided_kernel(const float* __restrict__ part, long stride, float* __restrict__ dst0, long n0, float* __restrict__ dst1,
+                      long n1, int splits, int accumulate) {
+  __shared__ float sm[32][33];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long i = (long)blockIdx.x * 32 + e;
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[(long)z * stride + offset + i];
-  dst[i] = accumulate ? dst[i] + s : s;
+  if (i < n0 + n1) {
+    const float* src = part + i;
+    int z = g;
+    for (; z + 96 < splits; z += 128) {
+      const float a = __ldg(src + (long)z * stride), b = __ldg(src + (long)(z + 32) * stride);
+      const float c = __ldg(src + (long)(z + 64) * stride), d = __ldg(src + (long)(z + 96) * stride);
+      s += a; s += b; s += c; s += d;
+    }
+    for (; z < splits; z += 32) s += __ldg(src + (long)z * stride);
+  }
+  sm[g][e] = s;
+  __syncthreads();
+  if (g == 0 && i < n0 + n1) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][e];
+    float* d = i < n0 ? dst0 + i : dst1 + (i - n0);
+    *d = accumulate ? *d + t : t;
+  }
 }
 
 int fill_geom(const char* name, const dg_tensor* img, const dg_tensor* out, const dg_conv_params* p, Geom* g) {
@@ -412,11 +432,8 @@ int thin_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, 
 #undef THIN_OUTER
 #undef THIN_OUTER_KW
   DG_CHECK_LAUNCH(name);
-  reduce_strided_kernel<<<(unsigned)((n_dw + 255) / 256), 256, 0, st>>>(part, part_stride, 0, dw, n_dw, blocks, accumulate);
-  if (dbias) {
-    const int nbias = cout;
-    reduce_strided_kernel<<<(nbias + 255) / 256, 256, 0, st>>>(part, part_stride, n_dw, dbias, nbias, blocks, accumulate);
-  }
+  const long n_bias = dbias ? cout : 0;
+  reduce_strided_kernel<<<(unsigned)((n_dw + n_bias + 31) / 32), 1024, 0, st>>>(part, part_stride, dw, n_dw, dbias, n_bias, blocks, accumulate);
   DG_CHECK_LAUNCH(name);
   return 0;
 }

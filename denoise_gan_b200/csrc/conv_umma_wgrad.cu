@@ -204,19 +204,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// dst[i] (+)= sum_s part[s][i]  (fixed order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, long part_stride, int splits, float* __restrict__ dw,
-                                    long n_dw, float* __restrict__ dbias, int n_bias, long bias_off, int accumulate) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_dw) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(long)z * part_stride + i];
-    dw[i] = accumulate ? dw[i] + s : s;
-  } else if (dbias && i < n_dw + n_bias) {
-    int o = (int)(i - n_dw);
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(long)z * part_stride + bias_off + o];
-    dbias[o] = accumulate ? dbias[o] + s : s;
+// dst[i] (+)= sum_s part[s][i] over the [dw | dbias] rows of the per-CTA partials (fixed order, deterministic).
+// Block = 32 float4 columns x 8 groups of splits; every thread keeps eight independent 16-byte loads in flight.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, long part_stride, int splits, float* __restrict__ dw, long n_dw,
+                    float* __restrict__ dbias, int n_bias, int accumulate) {
+  __shared__ float4 sm[8][32];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long col = (long)blockIdx.x * 32 + e;          // float4 column
+  const long total4 = (n_dw + n_bias) >> 2;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < total4) {
+    const float4* src = reinterpret_cast<const float4*>(part) + col;
+    const long st4 = part_stride >> 2;
+    int z = g;
+    for (; z + 56 < splits; z += 64) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + (long)(z + 8 * k) * st4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+    }
+    for (; z < splits; z += 8) {
+      const float4 v = __ldcg(src + (long)z * st4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sm[g][e] = s;
+  __syncthreads();
+  if (g == 0 && col < total4) {
+    float4 t = sm[0][e];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { t.x += sm[k][e].x; t.y += sm[k][e].y; t.z += sm[k][e].z; t.w += sm[k][e].w; }
+    const long i = col * 4;
+    float4* d = reinterpret_cast<float4*>(i < n_dw ? dw + i : dbias + (i - n_dw));
+    if (accumulate) { const float4 o = *d; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+    *d = t;
   }
 }
 
@@ -491,8 +514,10 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     DG_CHECK_LAUNCH(name);
   }
   const long total = n_dw + (dbias ? cout : 0);
-  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, part_stride, pl.splits, dw, n_dw,
-                                                                      dbias, cout, n_dw, accumulate);
+  DG_REQUIRE(n_dw % 4 == 0 && total % 4 == 0 && part_stride % 4 == 0 && ((uintptr_t)dw % 16) == 0 && (!dbias || ((uintptr_t)dbias % 16) == 0),
+             "dg_umma_conv2d_wgrad: gradient buffers must be 16-byte aligned");
+  wgrad_reduce_kernel<<<(unsigned)((total / 4 + 31) / 32), 256, 0, st>>>((const float*)workspace, part_stride, pl.splits, dw, n_dw,
+                                                                        dbias, dbias ? cout : 0, accumulate);
   DG_CHECK_LAUNCH("dg_umma_conv2d_wgrad(reduce)");
   return 0;
 }

@@ -440,6 +440,12 @@ inline unsigned ew_blocks(long total, int sm_count) {
 
 #define ST ((cudaStream_t)stream)
 
+// the per-channel reductions need a little over 48 KB of dynamic shared memory at C >= 512
+template <typename K>
+static inline void red8_optin(K kernel, size_t smem) {
+  if (smem + 64 > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+}
+
 extern "C" size_t dg_bn_workspace_bytes(const dg_tensor* x) {
   // partials [blocks][3][C] + coef [2][C]; blocks <= 148*8 (sized for any device <= 256 SMs)
   return ((size_t)256 * 8 * 3 * x->c + 2 * (size_t)x->c) * sizeof(float);
@@ -462,7 +468,8 @@ extern "C" int dg_bn_stats(dg_ctx* ctx, const dg_tensor* x, const float* gamma, 
   if (dgvec::vec_ok(x)) {
     blocks = dgvec::red8_blocks(P, C, ctx->sm_count);
     DG_DISPATCH_1(x->dtype, "dg_bn_stats",
-                  dgvec::bn_stats8_kernel<T><<<blocks, dgvec::VT, dgvec::red8_smem(C, 2), ST>>>(
+                  red8_optin(dgvec::bn_stats8_kernel<T>, dgvec::red8_smem(C, 2));
+                  dgvec::bn_stats8_kernel<T><<<blocks, dgvec::RT, dgvec::red8_smem(C, 2), ST>>>(
                       (const T*)x->ptr, dgvec::VView{x->cpitch, x->coff}, P, C, partial, ctx->tickets, gamma, beta, eps, momentum,
                       moving_mean, moving_var, scale, shift, save_mean, save_invstd););
     DG_CHECK_LAUNCH("dg_bn_stats");
@@ -498,7 +505,7 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
   View rv = residual ? view_of(residual) : View{0, 0};
   if (dgvec::vec_ok(x) && dgvec::vec_ok(y) && (!residual || dgvec::vec_ok(residual))) {
     DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
-                  dgvec::bn_act_fwd8_kernel<TI, TO><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
+                  dgvec::bn_act_fwd8_kernel<TI, TO><<<dgvec::ewc_blocks(P, C, ctx->sm_count), dgvec::ET, 0, ST>>>(
                       (const TI*)x->ptr, dgvec::VView{x->cpitch, x->coff}, scale, shift, act, act_alpha, prelu_alpha,
                       residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset, step_counter,
                       (TO*)y->ptr, dgvec::VView{y->cpitch, y->coff}, P, C););
@@ -535,10 +542,11 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
     const int vblocks = dgvec::red8_blocks(P, C, ctx->sm_count);
     const dgvec::VView vdy{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vdx{dx->cpitch, dx->coff};
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
-      dgvec::bn_bwd_reduce8_kernel<TI, TO><<<vblocks, dgvec::VT, dgvec::red8_smem(C, 3), ST>>>(
+      red8_optin(dgvec::bn_bwd_reduce8_kernel<TI, TO>, dgvec::red8_smem(C, 3));
+      dgvec::bn_bwd_reduce8_kernel<TI, TO><<<vblocks, dgvec::RT, dgvec::red8_smem(C, 3), ST>>>(
           (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout,
           seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
-      dgvec::bn_bwd_dx8_kernel<TI, TO, TI><<<dgvec::ew8_blocks(P * (C / 8), ctx->sm_count), dgvec::VT, 0, ST>>>(
+      dgvec::bn_bwd_dx8_kernel<TI, TO, TI><<<dgvec::ewc_blocks(P, C, ctx->sm_count), dgvec::ET, 0, ST>>>(
           (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,
           dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);
     });
@@ -615,6 +623,18 @@ extern "C" int dg_d2s_prelu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tenso
   long total = dg_pixels(u) * u->c;
   int Co = dy->c;
   const bool vec = dgvec::vec_ok(dy) && dgvec::vec_ok(u) && dgvec::vec_ok(du);
+  if (vec && prelu_alpha && dprelu_alpha) {   // one pass: du and the slope gradient together
+    DG_REQUIRE(workspace && workspace_bytes >= dg_bn_workspace_bytes(dy), "dg_d2s_prelu_bwd: workspace too small");
+    long Pout = dg_pixels(dy);
+    int vblocks = dgvec::red8_blocks(Pout, Co, ctx->sm_count);
+    DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_bwd",
+                  dgvec::d2s_prelu_bwd_fused8_kernel<T><<<vblocks, dgvec::RT, dgvec::red8_smem(Co, 1), ST>>>(
+                      (const T*)dy->ptr, dgvec::VView{dy->cpitch, dy->coff}, (const T*)u->ptr, dgvec::VView{u->cpitch, u->coff},
+                      prelu_alpha, (T*)du->ptr, dgvec::VView{du->cpitch, du->coff}, Pout, dy->h, dy->w, Co, (float*)workspace,
+                      ctx->tickets, dprelu_alpha, accumulate););
+    DG_CHECK_LAUNCH("dg_d2s_prelu_bwd");
+    return 0;
+  }
   DG_DISPATCH_1(u->dtype, "dg_d2s_prelu_bwd", {
     if (vec)
       dgvec::d2s_prelu8_kernel<T, true><<<dgvec::ew8_blocks(total / 8, ctx->sm_count), dgvec::VT, 0, ST>>>(
@@ -629,7 +649,7 @@ extern "C" int dg_d2s_prelu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tenso
       long Pout = dg_pixels(dy);
       int vblocks = dgvec::red8_blocks(Pout, Co, ctx->sm_count);
       float* partial = (float*)workspace;
-      dgvec::d2s_dalpha8_kernel<T><<<vblocks, dgvec::VT, dgvec::red8_smem(Co, 1), ST>>>(
+      dgvec::d2s_dalpha8_kernel<T><<<vblocks, dgvec::RT, dgvec::red8_smem(Co, 1), ST>>>(
           (const T*)dy->ptr, dgvec::VView{dy->cpitch, dy->coff}, (const T*)u->ptr, dgvec::VView{u->cpitch, u->coff}, Pout, dy->h,
           dy->w, Co, partial, ctx->tickets, dprelu_alpha, accumulate);
     } else if (prelu_alpha && dprelu_alpha) {

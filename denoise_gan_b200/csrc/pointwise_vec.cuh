@@ -12,8 +12,21 @@ constexpr int VT = 256;
 
 template <typename T>
 struct V8;
+struct RawF32 {
+  float4 a, b;
+};
 template <>
 struct V8<float> {
+  typedef RawF32 raw;
+  static __device__ __forceinline__ raw ldraw(const float* p) {
+    raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  static __device__ __forceinline__ void cvt(const raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
     float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -25,6 +38,16 @@ struct V8<float> {
 };
 template <>
 struct V8<__nv_bfloat16> {
+  typedef uint4 raw;
+  static __device__ __forceinline__ raw ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void cvt(const raw& u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -55,15 +78,22 @@ struct VView {
 };
 
 // ---------------------------------------------------------------- per-channel reduction skeleton (8 channels / thread)
-// F(p, c0, acc[NV][8]) accumulates; every block writes one partial [NV][C]; the LAST block to finish (ticket
-// counter) sums the partials in block order in double precision and calls Fin(c, sums) per channel, so no
-// separate finalize launch is needed and the result does not depend on block scheduling (deterministic).
-template <int NV, typename F, typename Fin>
-__device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, F f, Fin fin) {
+// One block of RT threads per SM.  A thread owns 8 fixed channels (so per-channel constants live in registers) and walks
+// pixels with U independent 16-byte loads per tensor in flight: `load(p, c0)` only fetches, `accum(raw, p, c0, acc)`
+// only computes.  Every block writes one partial [NV][C]; the LAST block to finish (ticket counter) sums the partials
+// in a fixed order in double precision and calls fin(c, sums) per channel: no finalize launch, and the result does
+// not depend on block scheduling (deterministic).
+constexpr int RT = 512;
+
+template <int NV, int U, typename Raw, typename L, typename A, typename Fin>
+__device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, L load,
+                                                A accum, Fin fin) {
   extern __shared__ __align__(16) float red8[];
   __shared__ int is_last;
-  const int CV = C >> 3, R = VT / CV;
+  const int CV = C >> 3, R = RT / CV;
   const int lane = threadIdx.x % CV, row = threadIdx.x / CV;
+  const int c0 = lane * 8;
+  const int E = NV * C;
   float acc[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -72,23 +102,48 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   if (row < R) {
     const long stride = (long)gridDim.x * R;
     long p = (long)blockIdx.x * R + row;
-    for (; p + 3 * stride < P; p += 4 * stride) {  // four pixels in flight per thread
-      f(p, lane * 8, acc);
-      f(p + stride, lane * 8, acc);
-      f(p + 2 * stride, lane * 8, acc);
-      f(p + 3 * stride, lane * 8, acc);
+    for (; p + (U - 1) * stride < P; p += U * stride) {
+      Raw r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = load(p + u * stride, c0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) accum(r[u], p + u * stride, c0, acc);
     }
-    for (; p < P; p += stride) f(p, lane * 8, acc);
+    for (; p < P; p += stride) {
+      Raw r = load(p, c0);
+      accum(r, p, c0, acc);
+    }
+  }
+  // ---- block reduce: rows sharing a warp first (shuffles), then across warps through shared memory
+  int rows_out;
+  if (CV <= 32 && (CV & (CV - 1)) == 0) {       // RT % CV == 0: every thread is active, warps hold 32/CV whole rows
+    for (int o = CV; o < 32; o <<= 1)
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
+      for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red8[(row * NV + v) * C + lane * 8 + j] = acc[v][j];
+        for (int j = 0; j < 8; ++j) acc[v][j] += __shfl_xor_sync(0xffffffffu, acc[v][j], o);
+    if ((int)(threadIdx.x & 31) < CV) {
+      const int wp = threadIdx.x >> 5;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red8[wp * E + v * C + c0 + j] = acc[v][j];
+    }
+    rows_out = RT / 32;
+  } else {
+    if (row < R) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red8[row * E + v * C + c0 + j] = acc[v][j];
+    }
+    rows_out = R;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < NV * C; e += VT) {
+  for (int e = threadIdx.x; e < E; e += RT) {
     float s = 0.f;
-    for (int r = 0; r < R; ++r) s += red8[r * NV * C + e];
-    partial[(long)blockIdx.x * NV * C + e] = s;
+    for (int r = 0; r < rows_out; ++r) s += red8[r * E + e];
+    partial[(long)blockIdx.x * E + e] = s;
   }
   __threadfence();
   __syncthreads();
@@ -96,42 +151,63 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // all 256 threads share the final sum: thread = (4-element vector of the partial, group of blocks)
-  double* fsum = reinterpret_cast<double*>(red8);   // [E] doubles (E = NV*C); group partials live behind it
+  // ---- last block: thread = (float4 column of the partial, group of blocks); four independent loads in flight
+  double* fsum = reinterpret_cast<double*>(red8);   // [E]; group sums [G][E] live behind it
+  double* gsum = fsum + E;
   const int nb = (int)gridDim.x;
-  const int E4 = (NV * C) >> 2;
-  const int G = E4 < VT ? VT / E4 : 1;
-  double* gsum = fsum + NV * C;                      // [G][E]
-  for (int idx = threadIdx.x; idx < E4 * G; idx += VT) {
+  const int E4 = E >> 2;
+  const int G = E4 < RT ? RT / E4 : 1;
+  const float4* part4 = reinterpret_cast<const float4*>(partial);
+  for (int idx = threadIdx.x; idx < E4 * G; idx += RT) {
     const int e4 = idx % E4, grp = idx / E4;
     double s[4] = {0, 0, 0, 0};
-    for (int bI = grp; bI < nb; bI += G) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (long)bI * NV * C) + e4);
+    int bI = grp;
+    for (; bI + 3 * G < nb; bI += 4 * G) {
+      const float4 v0 = __ldcg(part4 + (long)bI * E4 + e4), v1 = __ldcg(part4 + (long)(bI + G) * E4 + e4);
+      const float4 v2 = __ldcg(part4 + (long)(bI + 2 * G) * E4 + e4), v3 = __ldcg(part4 + (long)(bI + 3 * G) * E4 + e4);
+      s[0] += (double)v0.x; s[1] += (double)v0.y; s[2] += (double)v0.z; s[3] += (double)v0.w;
+      s[0] += (double)v1.x; s[1] += (double)v1.y; s[2] += (double)v1.z; s[3] += (double)v1.w;
+      s[0] += (double)v2.x; s[1] += (double)v2.y; s[2] += (double)v2.z; s[3] += (double)v2.w;
+      s[0] += (double)v3.x; s[1] += (double)v3.y; s[2] += (double)v3.z; s[3] += (double)v3.w;
+    }
+    for (; bI < nb; bI += G) {
+      const float4 v = __ldcg(part4 + (long)bI * E4 + e4);
       s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) gsum[(long)grp * NV * C + e4 * 4 + k] = s[k];
+    for (int k = 0; k < 4; ++k) gsum[(long)grp * E + e4 * 4 + k] = s[k];
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < NV * C; e += VT) {
+  for (int e = threadIdx.x; e < E; e += RT) {
     double t = 0;
-    for (int g2 = 0; g2 < G; ++g2) t += gsum[(long)g2 * NV * C + e];
+    for (int g2 = 0; g2 < G; ++g2) t += gsum[(long)g2 * E + e];
     fsum[e] = t;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += VT) fin(c, fsum);
+  for (int c = threadIdx.x; c < C; c += RT) fin(c, fsum);
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
 static inline int red8_blocks(long P, int C, int sm_count) {
-  int R = VT / (C >> 3);
-  long want = (P + R - 1) / R, cap = (long)sm_count * 2;
+  int R = RT / (C >> 3);
+  long want = (P + R - 1) / R, cap = (long)sm_count;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 static inline size_t red8_smem(int C, int NV) {
-  const int E = NV * C, E4 = E >> 2, G = E4 < VT ? VT / E4 : 1;
-  size_t a = (size_t)(VT / (C >> 3)) * NV * C * sizeof(float), b = (size_t)(E + (size_t)G * E) * sizeof(double);
+  const int CV = C >> 3, E = NV * C, E4 = E >> 2, G = E4 < RT ? RT / E4 : 1;
+  const int rows = (CV <= 32 && (CV & (CV - 1)) == 0) ? RT / 32 : RT / CV;
+  size_t a = (size_t)rows * E * sizeof(float), b = (size_t)(E + (size_t)G * E) * sizeof(double);
   return a > b ? a : b;
+}
+
+// ---------------------------------------------------------------- element-wise skeleton with the same thread->channel map
+// `body(p, c0)`-style kernels below use ET threads; a thread keeps its 8 channels and walks pixels EU at a time.
+constexpr int ET = 256;
+constexpr int EU = 4;
+static inline unsigned ewc_blocks(long P, int C, int sm_count) {
+  int R = ET / (C >> 3);
+  long want = (P + (long)R * EU - 1) / ((long)R * EU), cap = (long)sm_count * 4;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 static inline bool vec_ok(const dg_tensor* t) {
@@ -142,18 +218,20 @@ static inline bool vec_ok(const dg_tensor* t) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(VT)
+__global__ void __launch_bounds__(RT, 1)
 bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                  float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
                  float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  channel_reduce8<2>(
+  typedef typename V8<T>::raw Raw;
+  channel_reduce8<2, (sizeof(Raw) <= 16 ? 16 : 8), Raw>(
       P, C, partial, ticket,
-      [&](long p, int c0, float (&a)[2][8]) {
+      [&](long p, int c0) { return V8<T>::ldraw(x + (p * xv.pitch + xv.off + c0)); },
+      [&](const Raw& r, long, int, float (&a)[2][8]) {
         float v[8];
-        V8<T>::ld(x + (p * xv.pitch + xv.off + c0), v);
+        V8<T>::cvt(r, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a[0][j] += v[j]; a[1][j] += v[j] * v[j]; }
+        for (int j = 0; j < 8; ++j) { a[0][j] += v[j]; a[1][j] = fmaf(v[j], v[j], a[1][j]); }
       },
       [&](int c, const double* sums) {
         double mean = sums[c] / (double)P;
@@ -172,127 +250,200 @@ bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __rest
       });
 }
 
+// activation applied to t = bn(x) (after dropout); shared by forward and backward
+__device__ __forceinline__ float act_deriv(float tt, int act, float alpha, float al) {
+  switch (act) {
+    case DG_ACT_RELU: return tt > 0.f ? 1.f : 0.f;
+    case DG_ACT_LRELU: return tt >= 0.f ? 1.f : alpha;
+    case DG_ACT_PRELU: return tt > 0.f ? 1.f : al;
+    case DG_ACT_TANH: { float yy = tanhf(tt); return 1.f - yy * yy; }
+    case DG_ACT_SIGMOID: { float yy = 1.f / (1.f + expf(-tt)); return yy * (1.f - yy); }
+    default: return 1.f;
+  }
+}
+
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(VT)
+__global__ void __launch_bounds__(ET)
 bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                    float alpha, const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, int dropout,
                    uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, TO* __restrict__ y, VView yv, long P, int C) {
   const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
-  const uint32_t CV = (uint32_t)C >> 3;
-  const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
-  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
-    const uint32_t p = i / CV;
-    const int c0 = (int)(i - p * CV) * 8;
-    float v[8], sc[8], sh[8];
-    V8<TI>::ld(x + (p * xv.pitch + xv.off + c0), v);
-    ldc8(scale + c0, sc); ldc8(shift + c0, sh);
+  const int CV = C >> 3, R = ET / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  if (row >= R) return;
+  float sc[8], sh[8], al[8];
+  ldc8(scale + c0, sc); ldc8(shift + c0, sh);
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+  const long stride = (long)gridDim.x * R;
+  typedef typename V8<TI>::raw RawI;
+  typedef typename V8<TO>::raw RawO;
+  auto one = [&](const RawI& rx, const RawO& rr, long p) {
+    float v[8];
+    V8<TI>::cvt(rx, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
     if (dropout) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j)) ? 2.f * v[j] : 0.f;
     }
     if (act == DG_ACT_PRELU) {
-      float al[8];
-      ldc8(prelu_alpha + c0, al);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : al[j] * v[j];
+    } else if (act == DG_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == DG_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] >= 0.f ? v[j] : alpha * v[j];
     } else if (act != DG_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, alpha);
     }
     if (res) {
       float r[8];
-      V8<TO>::ld(res + (p * rv.pitch + rv.off + c0), r);
+      V8<TO>::cvt(rr, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += r[j];
     }
     V8<TO>::st(y + (p * yv.pitch + yv.off + c0), v);
-  }
-}
-
-// g[j] = dL/d(bn output); t[j] = activation input (after dropout)
-template <typename TG, typename TX>
-__device__ __forceinline__ void bn_bwd_g8(const TG* dy, VView dv, const TX* x, VView xv, const float* scale, const float* shift,
-                                          int act, float alpha, const float* prelu_alpha, int dropout, uint32_t seed,
-                                          uint32_t offset, long p, int c0, int C, float (&g)[8], float (&t)[8], float (&xin)[8],
-                                          float (&gy)[8]) {
-  float sc[8], sh[8];
-  V8<TX>::ld(x + (p * xv.pitch + xv.off + c0), xin);
-  V8<TG>::ld(dy + (p * dv.pitch + dv.off + c0), gy);
-  ldc8(scale + c0, sc); ldc8(shift + c0, sh);
-  float al[8];
-  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+  };
+  long p = (long)blockIdx.x * R + row;
+  for (; p + (EU - 1) * stride < P; p += EU * stride) {
+    RawI rx[EU];
+    RawO rr[EU];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float tt = xin[j] * sc[j] + sh[j];
-    float dm = 1.f;
-    if (dropout) {
-      bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
-      tt = keep ? 2.f * tt : 0.f;
-      dm = keep ? 2.f : 0.f;
+    for (int u = 0; u < EU; ++u) {
+      rx[u] = V8<TI>::ldraw(x + ((p + u * stride) * xv.pitch + xv.off + c0));
+      if (res) rr[u] = V8<TO>::ldraw(res + ((p + u * stride) * rv.pitch + rv.off + c0));
     }
-    float d;
-    switch (act) {
-      case DG_ACT_RELU: d = tt > 0.f ? 1.f : 0.f; break;
-      case DG_ACT_LRELU: d = tt >= 0.f ? 1.f : alpha; break;
-      case DG_ACT_PRELU: d = tt > 0.f ? 1.f : al[j]; break;
-      case DG_ACT_TANH: { float yy = tanhf(tt); d = 1.f - yy * yy; break; }
-      case DG_ACT_SIGMOID: { float yy = 1.f / (1.f + expf(-tt)); d = yy * (1.f - yy); break; }
-      default: d = 1.f;
-    }
-    t[j] = tt;
-    g[j] = gy[j] * d * dm;
+#pragma unroll
+    for (int u = 0; u < EU; ++u) one(rx[u], rr[u], p + u * stride);
+  }
+  for (; p < P; p += stride) {
+    RawI rx = V8<TI>::ldraw(x + (p * xv.pitch + xv.off + c0));
+    RawO rr;
+    if (res) rr = V8<TO>::ldraw(res + (p * rv.pitch + rv.off + c0));
+    one(rx, rr, p);
   }
 }
 
 template <typename TG, typename TX>
-__global__ void __launch_bounds__(VT)
+struct RawPair {
+  typename V8<TG>::raw g;
+  typename V8<TX>::raw x;
+};
+
+// Sums for the BatchNorm backward pass: s0 = sum g, s1 = invstd * sum g*(x-mean), s2 = sum dy*min(t,0) (PReLU slope), with
+// g = dL/d(bn output) = dy * act'(t) * dropout, t = bn(x).  Finalize also leaves coef = {s0/P, s1/P} for the dx kernel.
+template <typename TG, typename TX>
+__global__ void __launch_bounds__(RT, 1)
 bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                       const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                       float alpha, const float* __restrict__ prelu_alpha, int dropout, uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, long P, int C,
                       float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ dgamma, float* __restrict__ dbeta,
                       float* __restrict__ dalpha, int accumulate, float* __restrict__ coef) {
   const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
-  channel_reduce8<3>(P, C, partial, ticket, [&](long p, int c0, float (&a)[3][8]) {
-    float g[8], t[8], xin[8], gy[8], mu[8], is[8];
-    bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
-    ldc8(mean + c0, mu); ldc8(invstd + c0, is);
+  typedef RawPair<TG, TX> Raw;
+  const int c0k = (threadIdx.x % (C >> 3)) * 8;
+  float sc[8], sh[8], mu[8], al[8];
+  ldc8(scale + c0k, sc); ldc8(shift + c0k, sh); ldc8(mean + c0k, mu);
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0k, al);
+  channel_reduce8<3, (sizeof(Raw) <= 32 ? 4 : 2), Raw>(
+      P, C, partial, ticket,
+      [&](long p, int c0) {
+        Raw r;
+        r.g = V8<TG>::ldraw(dy + (p * dv.pitch + dv.off + c0));
+        r.x = V8<TX>::ldraw(x + (p * xv.pitch + xv.off + c0));
+        return r;
+      },
+      [&](const Raw& r, long p, int c0, float (&a)[3][8]) {
+        float gy[8], xin[8];
+        V8<TG>::cvt(r.g, gy);
+        V8<TX>::cvt(r.x, xin);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[0][j] += g[j];
-      a[1][j] += g[j] * (xin[j] - mu[j]) * is[j];
-      if (act == DG_ACT_PRELU) a[2][j] += gy[j] * fminf(t[j], 0.f);
-    }
-  }, [&](int c, const double* sums) {
-    const double s0 = sums[c], s1 = sums[C + c], s2 = sums[2 * C + c];
-    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
-    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
-    if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
-    coef[c] = (float)(s0 / (double)P);
-    coef[C + c] = (float)(s1 / (double)P);
-  });
+        for (int j = 0; j < 8; ++j) {
+          float tt = fmaf(xin[j], sc[j], sh[j]);
+          float g = gy[j];
+          if (dropout) {
+            const bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
+            tt = keep ? 2.f * tt : 0.f;
+            g = keep ? 2.f * g : 0.f;
+          }
+          g = __fmul_rn(g, act_deriv(tt, act, alpha, act == DG_ACT_PRELU ? al[j] : 0.f));   // rounded product: the reduce and dx kernels must agree bit for bit
+          a[0][j] += g;
+          a[1][j] = fmaf(g, xin[j] - mu[j], a[1][j]);
+          if (act == DG_ACT_PRELU) a[2][j] = fmaf(gy[j], fminf(tt, 0.f), a[2][j]);
+        }
+      },
+      [&](int c, const double* sums) {
+        const double s0 = sums[c], s1 = sums[C + c] * (double)invstd[c], s2 = sums[2 * C + c];
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+        if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
+        coef[c] = (float)(s0 / (double)P);
+        coef[C + c] = (float)(s1 / (double)P);
+      });
 }
 
-// dx = gamma*invstd*(g - mean_g - xhat*mean_gxhat)  [+ extra: gradient arriving through a skip connection]
+// dx = gamma*invstd*(g - mean_g - xhat*mean_gxhat) = A*(g - mean_g) + B*(x - mean) with per-channel constants in registers
 template <typename TG, typename TX, typename TO>
-__global__ void __launch_bounds__(VT)
+__global__ void __launch_bounds__(ET)
 bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ invstd, int act, float alpha, const float* __restrict__ prelu_alpha, int dropout,
                   uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, const float* __restrict__ coef, TO* __restrict__ dx, VView ov, long P, int C) {
   const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
-  const uint32_t CV = (uint32_t)C >> 3;
-  const uint32_t total = (uint32_t)P * CV;   // vec_ok() guarantees < 2^31 elements
-  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
-    const uint32_t p = i / CV;
-    const int c0 = (int)(i - p * CV) * 8;
-    float g[8], t[8], xin[8], gy[8], mu[8], is[8], ga[8], k0[8], k1[8], o[8];
-    bn_bwd_g8(dy, dv, x, xv, scale, shift, act, alpha, prelu_alpha, dropout, seed, offset, p, c0, C, g, t, xin, gy);
-    ldc8(mean + c0, mu); ldc8(invstd + c0, is); ldc8(gamma + c0, ga); ldc8(coef + c0, k0); ldc8(coef + C + c0, k1);
+  const int CV = C >> 3, R = ET / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  if (row >= R) return;
+  float sc[8], sh[8], al[8], A[8], B[8], mu[8], k0[8];
+  ldc8(scale + c0, sc); ldc8(shift + c0, sh); ldc8(mean + c0, mu); ldc8(coef + c0, k0);
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+  {
+    float ga[8], is[8], k1[8];
+    ldc8(gamma + c0, ga); ldc8(invstd + c0, is); ldc8(coef + C + c0, k1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = ga[j] * is[j] * (g[j] - k0[j] - (xin[j] - mu[j]) * is[j] * k1[j]);
+    for (int j = 0; j < 8; ++j) {
+      A[j] = ga[j] * is[j];
+      B[j] = -A[j] * is[j] * k1[j];
+    }
+  }
+  typedef RawPair<TG, TX> Raw;
+  const long stride = (long)gridDim.x * R;
+  auto one = [&](const Raw& r, long p) {
+    float gy[8], xin[8], o[8];
+    V8<TG>::cvt(r.g, gy);
+    V8<TX>::cvt(r.x, xin);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float tt = fmaf(xin[j], sc[j], sh[j]);
+      float g = gy[j];
+      if (dropout) {
+        const bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
+        tt = keep ? 2.f * tt : 0.f;
+        g = keep ? 2.f * g : 0.f;
+      }
+      g = __fmul_rn(g, act_deriv(tt, act, alpha, act == DG_ACT_PRELU ? al[j] : 0.f));   // rounded product: the reduce and dx kernels must agree bit for bit
+      o[j] = fmaf(A[j], g - k0[j], B[j] * (xin[j] - mu[j]));   // differences first: exact zero when the batch is one pixel
+    }
     V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);
+  };
+  long p = (long)blockIdx.x * R + row;
+  for (; p + (EU - 1) * stride < P; p += EU * stride) {
+    Raw r[EU];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      r[u].g = V8<TG>::ldraw(dy + ((p + u * stride) * dv.pitch + dv.off + c0));
+      r[u].x = V8<TX>::ldraw(x + ((p + u * stride) * xv.pitch + xv.off + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u) one(r[u], p + u * stride);
+  }
+  for (; p < P; p += stride) {
+    Raw r;
+    r.g = V8<TG>::ldraw(dy + (p * dv.pitch + dv.off + c0));
+    r.x = V8<TX>::ldraw(x + (p * xv.pitch + xv.off + c0));
+    one(r, p);
   }
 }
 
@@ -364,22 +515,76 @@ d2s_prelu8_kernel(const T* __restrict__ a, VView av, const T* __restrict__ u, VV
 }
 
 template <typename T>
-__global__ void __launch_bounds__(VT)
+__global__ void __launch_bounds__(RT, 1)
 d2s_dalpha8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ u, VView uv, long Pout, int H2, int W2, int Co,
                    float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ dalpha, int accumulate) {
-  channel_reduce8<1>(Pout, Co, partial, ticket, [&](long q, int c0, float (&a)[1][8]) {
+  typedef RawPair<T, T> Raw;
+  channel_reduce8<1, (sizeof(Raw) <= 32 ? 8 : 4), Raw>(
+      Pout, Co, partial, ticket,
+      [&](long q, int c0) {
+        int w2 = (int)(q % W2);
+        long t = q / W2;
+        int h2 = (int)(t % H2);
+        long n = t / H2;
+        long p = (n * (H2 / 2) + h2 / 2) * (W2 / 2) + w2 / 2;
+        int sub = (h2 & 1) * 2 + (w2 & 1);
+        Raw r;
+        r.g = V8<T>::ldraw(dy + (q * dv.pitch + dv.off + c0));
+        r.x = V8<T>::ldraw(u + (p * uv.pitch + uv.off + sub * Co + c0));
+        return r;
+      },
+      [&](const Raw& r, long, int, float (&a)[1][8]) {
+        float g[8], uu[8];
+        V8<T>::cvt(r.g, g);
+        V8<T>::cvt(r.x, uu);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[0][j] = fmaf(g[j], fminf(uu[j], 0.f), a[0][j]);
+      },
+      [&](int c, const double* sums) { dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)sums[c]; });
+}
+
+// depth_to_space(2)+PReLU backward with the slope gradient in the same pass: walks OUTPUT pixels q (thread = 8 fixed
+// output channels), du[p, sub*Co + c] = u > 0 ? dy : alpha*dy and dalpha[c] += dy * min(u, 0); dy and u are read once.
+template <typename T>
+__global__ void __launch_bounds__(RT, 1)
+d2s_prelu_bwd_fused8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ u, VView uv, const float* __restrict__ alpha,
+                            T* __restrict__ du, VView ov, long Pout, int H2, int W2, int Co, float* __restrict__ partial,
+                            unsigned* __restrict__ ticket, float* __restrict__ dalpha, int accumulate) {
+  typedef RawPair<T, T> Raw;
+  float al[8];
+  ldc8(alpha + (threadIdx.x % (Co >> 3)) * 8, al);
+  auto src = [&](long q, long& p, int& sub) {
     int w2 = (int)(q % W2);
     long t = q / W2;
     int h2 = (int)(t % H2);
     long n = t / H2;
-    long p = (n * (H2 / 2) + h2 / 2) * (W2 / 2) + w2 / 2;
-    int sub = (h2 & 1) * 2 + (w2 & 1);
-    float g[8], uu[8];
-    V8<T>::ld(dy + (q * dv.pitch + dv.off + c0), g);
-    V8<T>::ld(u + (p * uv.pitch + uv.off + sub * Co + c0), uu);
+    p = (n * (H2 / 2) + h2 / 2) * (W2 / 2) + w2 / 2;
+    sub = (h2 & 1) * 2 + (w2 & 1);
+  };
+  channel_reduce8<1, (sizeof(Raw) <= 32 ? 8 : 4), Raw>(
+      Pout, Co, partial, ticket,
+      [&](long q, int c0) {
+        long p; int sub;
+        src(q, p, sub);
+        Raw r;
+        r.g = V8<T>::ldraw(dy + (q * dv.pitch + dv.off + c0));
+        r.x = V8<T>::ldraw(u + (p * uv.pitch + uv.off + sub * Co + c0));
+        return r;
+      },
+      [&](const Raw& r, long q, int c0, float (&a)[1][8]) {
+        long p; int sub;
+        src(q, p, sub);
+        float g[8], uu[8], o[8];
+        V8<T>::cvt(r.g, g);
+        V8<T>::cvt(r.x, uu);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[0][j] += g[j] * fminf(uu[j], 0.f);
-  }, [&](int c, const double* sums) { dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)sums[c]; });
+        for (int j = 0; j < 8; ++j) {
+          a[0][j] = fmaf(g[j], fminf(uu[j], 0.f), a[0][j]);
+          o[j] = uu[j] > 0.f ? g[j] : al[j] * g[j];
+        }
+        V8<T>::st(du + (p * ov.pitch + ov.off + sub * Co + c0), o);
+      },
+      [&](int c, const double* sums) { dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)sums[c]; });
 }
 
 // out = a (+ b) with dtype conversion; ACC: out += a

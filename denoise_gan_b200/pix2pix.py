@@ -29,3 +29,15 @@ class Pix2Pix(_GanBase):
         self.disc_params = ParamSet("d", d_init, self.device)
         self.generator = Pix2PixGenerator(self.engine, self.gen_params, dropout_seed=getattr(args, "dropout_seed", 7))
         self.discriminator = Pix2PixDiscriminator(self.engine, self.disc_params)
+
+    def generator_loss(self, disc_generated_output, gen_output, target):
+        """pix2pix.py:74-94: total = 1e-3*BCE(1, D) + mse + content + 1e-5*mean(TV(target-gen)) + mae + identity, where the
+        identity term runs the generator again on `target` with training=True (BN moving statistics and dropout advance, as
+        in the reference).  Value-only; train_pix2pix.train_step computes the same terms fused with their gradients.
+        Returns (total, gan, l1, l2, content, var, identity) device scalars."""
+        E = self.engine
+        adv, l1, l2, cont, var = self._loss_terms(disc_generated_output, gen_output, target)
+        tgt = target.t if hasattr(target, "deps") else target
+        ident_out = self.generator(tgt, training=True, pass_id=1)
+        ident = E.image_losses(ident_out, tgt, 0.0, 0.0, 0.0, key="api_ident")[0][0]
+        return adv + l2 + cont + var + l1 + ident, adv, l1, l2, cont, var, ident

@@ -55,6 +55,27 @@ class _GanBase:
         return loss, dgf, gf
 
 
+    # ---- value-only loss methods kept for API completeness: the train steps compute the same
+    # terms fused with their gradients (train_common.gan_step / train_pix2pix.train_step).
+    def _var(self, t):
+        return t if hasattr(t, "deps") else self.engine.input(t)
+
+    def discriminator_loss(self, disc_real_output, disc_generated_output):
+        """srgan.py:120-127 / pix2pix.py:96-103: BCE_logits(1, D(real)) + BCE_logits(0, D(fake)); device scalar."""
+        E = self.engine
+        real, _ = E.bce(self._var(disc_real_output), 1.0, True, 0.0, key="api_real")
+        fake, _ = E.bce(self._var(disc_generated_output), 0.0, True, 0.0, key="api_fake")
+        return real + fake
+
+    def _loss_terms(self, disc_generated_output, gen_output, target):
+        E = self.engine
+        adv, _ = E.bce(self._var(disc_generated_output), 1.0, True, 0.0, key="api_adv")
+        tgt = target.t if hasattr(target, "deps") else target
+        out3, _ = E.image_losses(self._var(gen_output), tgt, 0.0, 0.0, 0.0, key="api_img")
+        cont = self.content_loss(target, self._var(gen_output), key="api_content")[0] if self.vgg is not None else torch.zeros(1, device=self.device)
+        return 1e-3 * adv[0], out3[0], out3[1], cont.reshape(()), 1e-5 * out3[2]
+
+
 class SRGAN(_GanBase):
     """SRGAN for super resolution (reference: srgan.py:8-67)."""
 
@@ -76,3 +97,9 @@ class SRGAN(_GanBase):
         self.disc_params = ParamSet("d", d_init, self.device)
         self.generator = SRGANGenerator(self.engine, self.gen_params, self.scale)
         self.discriminator = PatchDiscriminator(self.engine, self.disc_params, sigmoid=False)
+
+    def generator_loss(self, disc_generated_output, gen_output, target):
+        """srgan.py:97-117 (not called by train_srgan.py, whose inline loss is authoritative): total = adv + l2 + content.
+        Returns (total, adv, l1, l2, content, var) device scalars."""
+        adv, l1, l2, cont, var = self._loss_terms(disc_generated_output, gen_output, target)
+        return adv + l2 + cont, adv, l1, l2, cont, var

@@ -161,3 +161,25 @@ def test_pix2pix_step_fp32():
     for n, a, ref, ref32 in zip(["total", "gan", "l1", "l2", "content", "disc", "var", "identity"], ours, l64, l32):
         tol = 5e-5 * max(1.0, abs(ref.item())) + 3.0 * abs(ref32.item() - ref.item())
         assert abs(a - ref.item()) <= tol, f"{n}: {a} vs {ref.item()}"
+
+
+def test_loss_api_methods_match_oracle_terms():
+    """srgan.py:97-127 / pix2pix.py:74-103 value-only loss methods."""
+    from denoise_gan_b200.srgan import SRGAN
+    from oracle import ops_torch as OT
+    model = SRGAN(SimpleNamespace(crop_size=64, scale=4, lr=1e-3, fp16=0, vgg=0, seed=0))
+    g = torch.Generator().manual_seed(0)
+    gen = torch.rand((2, 64, 64, 3), generator=g) * 2 - 1
+    tgt = torch.rand((2, 64, 64, 3), generator=g) * 2 - 1
+    dr, df = torch.randn((2, 4, 4, 1), generator=g), torch.randn((2, 4, 4, 1), generator=g)
+    total, adv, l1, l2, cont, var = [float(v) for v in model.generator_loss(df.cuda(), gen.cuda(), tgt.cuda())]
+    d = float(model.discriminator_loss(dr.cuda(), df.cuda()))
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    diff = (tgt - gen).double()
+    tv = (diff[:, 1:] - diff[:, :-1]).abs().sum((1, 2, 3)) + (diff[:, :, 1:] - diff[:, :, :-1]).abs().sum((1, 2, 3))
+    ref = {"adv": 1e-3 * bce(df.double(), torch.ones_like(df).double()).item(), "l1": diff.abs().mean().item(),
+           "l2": (diff ** 2).mean().item(), "var": 1e-5 * tv.mean().item(),
+           "d": (bce(dr.double(), torch.ones_like(dr).double()) + bce(df.double(), torch.zeros_like(df).double())).item()}
+    for name, ours in (("adv", adv), ("l1", l1), ("l2", l2), ("var", var), ("d", d)):
+        assert abs(ours - ref[name]) <= 2e-6 * max(1.0, abs(ref[name])), (name, ours, ref[name])
+    assert cont == 0.0 and abs(total - (adv + l2)) < 1e-6

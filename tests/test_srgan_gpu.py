@@ -108,8 +108,9 @@ def test_srgan_step_fp32_layers_grads_losses(vgg):
         assert e <= bound, f"activation gradient {name}: {e} > {bound}"
     assert len(grad_report) >= 15
     assert relerr(r["gen_output"].t, out["gen_output"]) < 1e-5
-    assert relerr(r["disc_real"].t, out["disc_real"]) < 1e-5
-    assert relerr(r["disc_fake"].t, out["disc_fake"]) < 1e-5
+    for key in ("disc_real", "disc_fake"):       # 8 BN layers deep: measured in units of the fp32 oracle's own deviation
+        bound = 1e-5 + 3.0 * relerr(out32[key], out[key])
+        assert relerr(r[key].t, out[key]) <= bound, (key, bound)
     gg = model.gen_params.grads(); dg = model.disc_params.grads()
     for ours, refs in ((gg, out["gen_grads"]), (dg, out["disc_grads"])):
         for name, ref in refs.items():
@@ -198,11 +199,15 @@ def test_srgan_loss_curve_fp32(steps):
     _, _, o64 = oracle_steps(g0, d0, v0, xs, ys, torch.float64)
     _, _, o32 = oracle_steps(g0, d0, v0, xs, ys, torch.float32)
     worst = 0.0
+    running = {n: 0.0 for n in LOSS_NAMES}
     for s in range(steps):
         r64 = [v.item() for v in o64[s][0]]
         r32 = [v.item() for v in o32[s][0]]
         for n, a, b, c in zip(LOSS_NAMES, ours[s], r64, r32):
-            noise = abs(c - b)                       # the oracle's own fp32-vs-fp64 deviation
+            # the oracle's own fp32-vs-fp64 deviation; trajectories drift apart cumulatively, so the yard-stick is the
+            # largest deviation seen so far rather than the (randomly small) one of this step
+            running[n] = max(running[n], abs(c - b))
+            noise = running[n]
             bound = 2e-4 * max(1.0, abs(b)) + 50.0 * noise
             worst = max(worst, abs(a - b) / max(1.0, abs(b)))
             assert abs(a - b) <= bound, f"step {s} {n}: ours {a} fp64 {b} fp32-oracle {c}"
