@@ -541,15 +541,27 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
   if (dgvec::vec_ok(dy) && dgvec::vec_ok(x) && dgvec::vec_ok(dx)) {
     const int vblocks = dgvec::red8_blocks(P, C, ctx->sm_count);
     const dgvec::VView vdy{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vdx{dx->cpitch, dx->coff};
+#define DG_BN_BWD_VEC(AM)                                                                                                        \
+  {                                                                                                                              \
+    red8_optin(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dgvec::red8_smem(C, 3));                                                  \
+    dgvec::bn_bwd_reduce8_kernel<TI, TO, AM><<<vblocks, dgvec::RT, dgvec::red8_smem(C, 3), ST>>>(                                 \
+        (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout, \
+        seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr,   \
+        accumulate, coef);                                                                                                       \
+    dgvec::bn_bwd_dx8_kernel<TI, TO, TI, AM><<<dgvec::ewc_blocks(P, C, ctx->sm_count), dgvec::ET, 0, ST>>>(                       \
+        (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
+        dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);                                                     \
+  }
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
-      red8_optin(dgvec::bn_bwd_reduce8_kernel<TI, TO>, dgvec::red8_smem(C, 3));
-      dgvec::bn_bwd_reduce8_kernel<TI, TO><<<vblocks, dgvec::RT, dgvec::red8_smem(C, 3), ST>>>(
-          (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout,
-          seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef);
-      dgvec::bn_bwd_dx8_kernel<TI, TO, TI><<<dgvec::ewc_blocks(P, C, ctx->sm_count), dgvec::ET, 0, ST>>>(
-          (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,
-          dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);
+      switch (dgvec::act_mode(act, dropout)) {
+        case 0: DG_BN_BWD_VEC(0) break;
+        case 1: DG_BN_BWD_VEC(1) break;
+        case 2: DG_BN_BWD_VEC(2) break;
+        case 3: DG_BN_BWD_VEC(3) break;
+        default: DG_BN_BWD_VEC(4) break;
+      }
     });
+#undef DG_BN_BWD_VEC
     DG_CHECK_LAUNCH("dg_bn_act_bwd");
     return 0;
   }

@@ -262,6 +262,27 @@ __device__ __forceinline__ float act_deriv(float tt, int act, float alpha, float
   }
 }
 
+// AM = compile-time activation mode of the backward kernels: 0 none, 1 relu, 2 leaky relu, 3 prelu (straight-line code,
+// no dropout); 4 = anything else decided at run time (tanh, sigmoid, dropout)
+template <int AM>
+__device__ __forceinline__ float act_deriv_t(float tt, int act, float alpha, float al) {
+  if (AM == 0) return 1.f;
+  if (AM == 1) return tt > 0.f ? 1.f : 0.f;
+  if (AM == 2) return tt >= 0.f ? 1.f : alpha;
+  if (AM == 3) return tt > 0.f ? 1.f : al;
+  return act_deriv(tt, act, alpha, al);
+}
+static inline int act_mode(int act, int dropout) {
+  if (dropout) return 4;
+  switch (act) {
+    case DG_ACT_NONE: return 0;
+    case DG_ACT_RELU: return 1;
+    case DG_ACT_LRELU: return 2;
+    case DG_ACT_PRELU: return 3;
+    default: return 4;
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(ET)
 bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__ scale, const float* __restrict__ shift, int act,
@@ -335,7 +356,7 @@ struct RawPair {
 
 // Sums for the BatchNorm backward pass: s0 = sum g, s1 = invstd * sum g*(x-mean), s2 = sum dy*min(t,0) (PReLU slope), with
 // g = dL/d(bn output) = dy * act'(t) * dropout, t = bn(x).  Finalize also leaves coef = {s0/P, s1/P} for the dx kernel.
-template <typename TG, typename TX>
+template <typename TG, typename TX, int AM>
 __global__ void __launch_bounds__(RT, 1)
 bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                       const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
@@ -364,15 +385,16 @@ bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict_
         for (int j = 0; j < 8; ++j) {
           float tt = fmaf(xin[j], sc[j], sh[j]);
           float g = gy[j];
-          if (dropout) {
+          if (AM == 4 && dropout) {
             const bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
             tt = keep ? 2.f * tt : 0.f;
             g = keep ? 2.f * g : 0.f;
           }
-          g = __fmul_rn(g, act_deriv(tt, act, alpha, act == DG_ACT_PRELU ? al[j] : 0.f));   // rounded product: the reduce and dx kernels must agree bit for bit
+          // rounded product: the reduce and dx kernels must agree bit for bit
+          g = __fmul_rn(g, act_deriv_t<AM>(tt, act, alpha, (AM == 3 || (AM == 4 && act == DG_ACT_PRELU)) ? al[j] : 0.f));
           a[0][j] += g;
           a[1][j] = fmaf(g, xin[j] - mu[j], a[1][j]);
-          if (act == DG_ACT_PRELU) a[2][j] = fmaf(gy[j], fminf(tt, 0.f), a[2][j]);
+          if (AM == 3 || (AM == 4 && act == DG_ACT_PRELU)) a[2][j] = fmaf(gy[j], fminf(tt, 0.f), a[2][j]);
         }
       },
       [&](int c, const double* sums) {
@@ -386,7 +408,7 @@ bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict_
 }
 
 // dx = gamma*invstd*(g - mean_g - xhat*mean_gxhat) = A*(g - mean_g) + B*(x - mean) with per-channel constants in registers
-template <typename TG, typename TX, typename TO>
+template <typename TG, typename TX, typename TO, int AM>
 __global__ void __launch_bounds__(ET)
 bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -418,12 +440,12 @@ bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x,
     for (int j = 0; j < 8; ++j) {
       float tt = fmaf(xin[j], sc[j], sh[j]);
       float g = gy[j];
-      if (dropout) {
+      if (AM == 4 && dropout) {
         const bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
         tt = keep ? 2.f * tt : 0.f;
         g = keep ? 2.f * g : 0.f;
       }
-      g = __fmul_rn(g, act_deriv(tt, act, alpha, act == DG_ACT_PRELU ? al[j] : 0.f));   // rounded product: the reduce and dx kernels must agree bit for bit
+      g = __fmul_rn(g, act_deriv_t<AM>(tt, act, alpha, (AM == 3 || (AM == 4 && act == DG_ACT_PRELU)) ? al[j] : 0.f));
       o[j] = fmaf(A[j], g - k0[j], B[j] * (xin[j] - mu[j]));   // differences first: exact zero when the batch is one pixel
     }
     V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);

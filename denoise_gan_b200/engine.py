@@ -45,9 +45,35 @@ class Node:
         self.seq, self.inputs, self.out, self.group, self.bwd = seq, inputs, out, group, bwd
 
 
+class _ProfLib:
+    """Pass-through to the C library that, when `engine.prof_calls` is a list, brackets every dg_* call with CUDA
+    events (tools/step_profile.py: warm, in-order timing of a whole step by entry point)."""
+
+    def __init__(self, lib, engine):
+        self._lib, self._engine = lib, engine
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        eng = self._engine
+
+        def call(*a):
+            rec = eng.prof_calls
+            if rec is None or name.endswith(("_bytes", "_supported")) or not name.startswith("dg_"):
+                return fn(*a)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a)
+            e1.record()
+            rec.append((name, e0, e1))
+            return r
+
+        return call
+
+
 class Engine:
     def __init__(self, device=None, bf16: bool = False):
-        self.lib = _lib.load()
+        self.prof_calls = None
+        self.lib = _ProfLib(_lib.load(), self)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.ctx = _lib.ctx(self.device.index)
         self.bf16 = bool(bf16)
