@@ -57,6 +57,9 @@ SIGNATURES = {
     "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_dgrad_supported": (_i, [_P, _T, _T, _CP]),
     "dg_bias_grad": (_i, [_P, _T, _P, _i, _P, _sz, _P]),
+    "dg_pad_channels": (_i, [_P, _T, _T, _P]),
+    "dg_umma_pack_weights_padded": (_i, [_P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "dg_unpad_weight_grad": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
     "dg_frame_to_float": (_i, [_P, _P, _i, _i, _i, _i, _f, _f, _T, _P]),
     "dg_float_to_frame": (_i, [_P, _T, _f, _f, _i, _i, _P, _i, _i, _P]),
     "dg_debug_conv_timeline": (None, [_P]),

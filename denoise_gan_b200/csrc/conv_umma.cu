@@ -338,8 +338,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
 // ------------------------------------------------------------------ weight packing
 // mode 0 (forward): dst[((t*nch+kc)*Cout + o)*KC + j] = w[t][kc*KC + j][o]      (KC chunks over Cin)
 // mode 1 (dgrad)  : dst[((t*nch+kc)*Cin  + c)*KC + j] = w[t][c][kc*KC + j]      (KC chunks over Cout)
+// cin/cout are the PACKED (possibly zero-padded) dims, cin_s/cout_s the dims of the fp32 source.
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int taps, int cin,
-                                    int cout, int kc, int mode) {
+                                    int cout, int kc, int mode, int cin_s, int cout_s) {
   long total = (long)taps * cin * cout;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int rows = mode == 0 ? cout : cin;  // rows of a block
@@ -352,7 +353,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     int ch = (int)(r2 % nch);
     int t = (int)(r2 / nch);
     int k = ch * kc + j;
-    float v = mode == 0 ? w[((long)t * cin + k) * cout + row] : w[((long)t * cin + row) * cout + k];
+    const int ci = mode == 0 ? k : row, co = mode == 0 ? row : k;
+    float v = (ci < cin_s && co < cout_s) ? w[((long)t * cin_s + ci) * cout_s + co] : 0.f;
     dst[i] = __float2bfloat16(v);
   }
 }
@@ -363,8 +365,8 @@ static int g_dbg_flags = 0;
 struct PackEntry {   // mirrored by denoise_gan_b200/params.py (48 bytes)
   const float* src;
   __nv_bfloat16* dst;
-  int taps, cin, cout, kc, mode, pad0;
-  long pad1;
+  int taps, cin, cout, kc, mode, cin_src;   // cin/cout: packed (padded) dims; *_src: dims of the fp32 source (0 = same)
+  int cout_src, pad1;
 };
 
 // all kernels of a network in ONE launch: blockIdx.y selects the table entry
@@ -377,7 +379,9 @@ __global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
     unsigned row = r1 % rows, r2 = r1 / rows;
     unsigned ch = r2 % nch, t = r2 / nch;
     unsigned k = ch * E.kc + j;
-    float v = E.mode == 0 ? E.src[((long)t * E.cin + k) * E.cout + row] : E.src[((long)t * E.cin + row) * E.cout + k];
+    const unsigned ci = E.mode == 0 ? k : row, co = E.mode == 0 ? row : k;
+    const unsigned cis = E.cin_src ? E.cin_src : E.cin, cos = E.cout_src ? E.cout_src : E.cout;
+    float v = (ci < cis && co < cos) ? E.src[((long)t * cis + ci) * cos + co] : 0.f;
     E.dst[i] = __float2bfloat16(v);
   }
 }
@@ -579,8 +583,23 @@ extern "C" int dg_umma_pack_weights(dg_ctx* ctx, const float* w, void* packed, i
   long total = (long)kh * kw * cin * cout;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin, cout, kc, mode);
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin, cout, kc, mode, cin, cout);
   DG_CHECK_LAUNCH("dg_umma_pack_weights");
+  return 0;
+}
+
+extern "C" int dg_umma_pack_weights_padded(dg_ctx* ctx, const float* w, void* packed, int kh, int kw, int cin, int cout, int cin_pad,
+                                           int cout_pad, int mode, void* stream) {
+  DG_REQUIRE(w && packed, "dg_umma_pack_weights_padded: null argument");
+  DG_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0 && cin <= cin_pad && cout <= cout_pad && (mode == 0 || mode == 1),
+             "dg_umma_pack_weights_padded: padded channels must be multiples of 16");
+  int kc = kc_for(mode == 0 ? cin_pad : cout_pad);
+  long total = (long)kh * kw * cin_pad * cout_pad;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin_pad, cout_pad, kc, mode,
+                                                                          cin, cout);
+  DG_CHECK_LAUNCH("dg_umma_pack_weights_padded");
   return 0;
 }
 

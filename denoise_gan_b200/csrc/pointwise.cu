@@ -813,3 +813,85 @@ extern "C" int dg_bias_grad(dg_ctx* ctx, const dg_tensor* dy, float* dbias, int 
   DG_CHECK_LAUNCH("dg_bias_grad");
   return 0;
 }
+
+// ------------------------------------------------------------------ channel padding for the tensor-core path
+// Layers with 3 (RGB) channels on one side run on the tensor cores through a zero-padded 16-channel bf16 copy of
+// that side (srgan.py:154 conv 3->64, :182 conv 64->3, :236-246 discriminator conv 3->32).
+namespace {
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+pad_channels_kernel(const TI* __restrict__ src, View sv, TO* __restrict__ dst, View dv, long P, int cs, int cd) {
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
+    const TI* s = src + p * sv.pitch + sv.off;
+    TO* d = dst + p * dv.pitch + dv.off;
+    for (int c = 0; c < cd; ++c) st_f<TO>(d + c, c < cs ? ld_f<TI>(s + c) : 0.f);
+  }
+}
+
+// 16 bf16 output channels per pixel written as two 16-byte stores
+template <typename TI>
+__global__ void __launch_bounds__(256)
+pad_channels16_kernel(const TI* __restrict__ src, View sv, __nv_bfloat16* __restrict__ dst, long P, int cs) {
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
+    const TI* s = src + p * sv.pitch + sv.off;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = c < cs ? ld_f<TI>(s + c) : 0.f;
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+      w[c] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst + p * 16);
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// dst[t][c][o] (+)= src[t][c][o] for c < cin, o < cout  (src rows are cin_p x cout_p);  dbias likewise
+__global__ void unpad_weight_grad_kernel(const float* __restrict__ src, const float* __restrict__ bsrc, float* __restrict__ dst,
+                                         float* __restrict__ bdst, int taps, int cin, int cout, int cin_p, int cout_p,
+                                         int accumulate) {
+  const long n = (long)taps * cin * cout;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n + (bdst ? cout : 0); i += (long)gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int o = (int)(i % cout);
+      const long r = i / cout;
+      const int c = (int)(r % cin), t = (int)(r / cin);
+      const float v = src[((long)t * cin_p + c) * cout_p + o];
+      dst[i] = accumulate ? dst[i] + v : v;
+    } else {
+      const int o = (int)(i - n);
+      bdst[o] = accumulate ? bdst[o] + bsrc[o] : bsrc[o];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int dg_pad_channels(dg_ctx* ctx, const dg_tensor* src, const dg_tensor* dst, void* stream) {
+  DG_REQUIRE(dg_valid(src) && dg_valid(dst), "dg_pad_channels: null argument");
+  DG_REQUIRE(src->n == dst->n && src->h == dst->h && src->w == dst->w && src->c <= dst->c, "dg_pad_channels: shape mismatch");
+  const long P = dg_pixels(src);
+  if (dst->dtype == DG_BF16 && dst->c == 16 && dst->cpitch == 16 && dst->coff == 0 && ((uintptr_t)dst->ptr % 16) == 0) {
+    DG_DISPATCH_1(src->dtype, "dg_pad_channels",
+                  pad_channels16_kernel<T><<<ew_blocks(P, ctx->sm_count), 256, 0, ST>>>((const T*)src->ptr, view_of(src),
+                                                                                        (__nv_bfloat16*)dst->ptr, P, src->c););
+  } else {
+    DG_DISPATCH_2(src->dtype, dst->dtype, "dg_pad_channels",
+                  pad_channels_kernel<TI, TO><<<ew_blocks(P, ctx->sm_count), 256, 0, ST>>>(
+                      (const TI*)src->ptr, view_of(src), (TO*)dst->ptr, view_of(dst), P, src->c, dst->c););
+  }
+  DG_CHECK_LAUNCH("dg_pad_channels");
+  return 0;
+}
+
+extern "C" int dg_unpad_weight_grad(dg_ctx* ctx, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh,
+                                    int kw, int cin, int cout, int cin_pad, int cout_pad, int accumulate, void* stream) {
+  DG_REQUIRE(dw_padded && dw && cin <= cin_pad && cout <= cout_pad && (!dbias || dbias_padded), "dg_unpad_weight_grad: bad argument");
+  const long n = (long)kh * kw * cin * cout + (dbias ? cout : 0);
+  unpad_weight_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(dw_padded, dbias_padded, dw, dbias, kh * kw, cin, cout,
+                                                                        cin_pad, cout_pad, accumulate);
+  DG_CHECK_LAUNCH("dg_unpad_weight_grad");
+  return 0;
+}

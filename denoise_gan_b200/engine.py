@@ -85,6 +85,7 @@ class Engine:
         self.written: set = set()      # param names whose grad slice was written this step
         self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
         self.use_umma_wgrad = self.use_umma
+        self.pad_rgb = True            # 3-channel-sided convs on the tensor cores through 16-channel zero padding
         self.launches = 0
         self.record = None             # dict name -> Var when a test wants per-layer activations
         self._cap: dict = {}
@@ -188,10 +189,116 @@ class Engine:
         t = getattr(p, attr)
         if t is None:
             kh, kw, cin, cout = p.shape
-            t = torch.empty(p.numel, dtype=torch.bfloat16, device=self.device)
+            cin_p, cout_p = p.pack_pad or (cin, cout)
+            t = torch.empty(kh * kw * cin_p * cout_p, dtype=torch.bfloat16, device=self.device)
             setattr(p, attr, t)
-            check(self.lib.dg_umma_pack_weights(self.ctx, p.data.data_ptr(), t.data_ptr(), kh, kw, cin, cout, mode, self.st))
+            check(self.lib.dg_umma_pack_weights_padded(self.ctx, p.data.data_ptr(), t.data_ptr(), kh, kw, cin, cout, cin_p, cout_p,
+                                                       mode, self.st))
         return t
+
+    # ---- RGB-sided layers on the tensor cores through zero-padded 16-channel bf16 copies
+    def _zeros(self, key, shape, dtype) -> torch.Tensor:
+        k = (key, tuple(shape), dtype)
+        t = self.pool.get(k)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self.pool[k] = t
+        return t
+
+    def _conv2d_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype):
+        """conv2d when Cin or Cout is not a multiple of 16 (the 3-channel image side of srgan.py:154,182,236): operands are
+        zero-padded to 16 channels in bf16 (dg_pad_channels / dg_umma_pack_weights_padded), the tcgen05 kernels run on the
+        padded shapes, and results are sliced back (dg_copy views, dg_unpad_weight_grad).  Returns None when the tensor-core
+        kernels have no tile configuration for the padded layer (the caller then uses the CUDA-core kernels)."""
+        N, H, W, cin = x.shape
+        kh, kw, _, cout = w.shape
+        cin_p, cout_p = -(-cin // 16) * 16, -(-cout // 16) * 16
+        ydt = out_dtype or self.act_dtype
+        lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
+        cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
+        BF = _lib.DG_BF16
+        dummy = x.t.data_ptr()
+        d_x = _lib.DgTensor(dummy, BF, N, H, W, cin_p, cin_p, 0)
+        d_y = _lib.DgTensor(dummy, BF, N, Ho, Wo, cout_p, cout_p, 0)
+        key = ("padded", N, H, W, cin_p, Ho, Wo, cout_p, kh, kw, stride, pt, pl)
+        ok = self._cap.get(key)
+        if ok is None:
+            ok = (bool(self.lib.dg_umma_conv2d_fwd_supported(self.ctx, C.byref(d_x), C.byref(d_y), C.byref(lin))) and
+                  bool(self.lib.dg_umma_conv2d_dgrad_supported(self.ctx, C.byref(d_y), C.byref(d_x), C.byref(lin))) and
+                  self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(d_x), C.byref(d_y), C.byref(lin)) > 0)
+            self._cap[key] = ok
+        if not ok:
+            return None
+        seq = self._next()
+        w.pack_pad = (cin_p, cout_p)
+        y = self.buf((seq, "y"), (N, Ho, Wo, cout), ydt)
+        pad_in = cin_p != cin or x.t.dtype != torch.bfloat16
+        if pad_in:
+            xin = self.buf((seq, "xpad"), (N, H, W, cin_p), torch.bfloat16)
+            tsrc, tdst = tensor(x.t), tensor(xin)
+            check(self.lib.dg_pad_channels(self.ctx, C.byref(tsrc), C.byref(tdst), self.st))
+        else:
+            xin = x.t
+        yp = y if cout_p == cout else self.buf((seq, "ypad"), (N, Ho, Wo, cout_p), ydt)
+        bias = None
+        if b is not None:
+            if cout_p == cout:
+                bias = b.data.data_ptr()
+            else:
+                bp = self._zeros((seq, "bias_p"), (cout_p,), torch.float32)
+                bp[:cout].copy_(b.data)
+                bias = bp.data_ptr()
+        txi, typ = tensor(xin), tensor(yp)
+        flops = 2.0 * N * Ho * Wo * kh * kw * cin_p * cout_p
+        pk = self._packed(w, 0)
+        self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+            self.ctx, C.byref(txi), pk.data_ptr(), bias, C.byref(typ), C.byref(cp), None, self.st)))
+        if yp is not y:
+            tv, ty = tensor(yp, c=cout), tensor(y)
+            check(self.lib.dg_copy(self.ctx, C.byref(tv), C.byref(ty), 0, self.st))
+        out = Var(y, self._deps([x], w.group), seq)
+
+        def bwd(gy: torch.Tensor, need_in, need_p, tag):
+            dpre = gy
+            if ACT[act]:
+                dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
+                tg, tyy, td = tensor(gy), tensor(y), tensor(dpre)
+                check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
+            if cout_p != cout or dpre.dtype != torch.bfloat16:
+                dpp = self.buf((seq, "dpad", tag), (N, Ho, Wo, cout_p), torch.bfloat16)
+                ts, td = tensor(dpre), tensor(dpp)
+                check(self.lib.dg_pad_channels(self.ctx, C.byref(ts), C.byref(td), self.st))
+            else:
+                dpp = dpre
+            tdp = tensor(dpp)
+            if need_p:
+                acc = self._acc_flag(w)
+                if b is not None:
+                    assert self._acc_flag(b) == acc
+                nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(txi), C.byref(tdp), C.byref(lin))
+                ws = self.workspace(nbytes)
+                dwp = self.buf((seq, "dw_pad", tag), (kh * kw * cin_p * cout_p,), torch.float32)
+                dbp = self.buf((seq, "db_pad", tag), (cout_p,), torch.float32) if b is not None else None
+                self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
+                    self.ctx, C.byref(txi), C.byref(tdp), dwp.data_ptr(), _lib.ptr(dbp), C.byref(lin), 0, ws.data_ptr(), nbytes, self.st)))
+                check(self.lib.dg_unpad_weight_grad(self.ctx, dwp.data_ptr(), _lib.ptr(dbp), w.grad.data_ptr(),
+                                                    b.grad.data_ptr() if b is not None else None, kh, kw, cin, cout, cin_p, cout_p,
+                                                    acc, self.st))
+            dx = None
+            if need_in[0]:
+                dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                dxp = self.buf((seq, "dx_pad", tag), (N, H, W, cin_p), torch.bfloat16) if pad_in else dx
+                tdx = tensor(dxp)
+                pkd = self._packed(w, 1)
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
+                    self.ctx, C.byref(tdp), pkd.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
+                if dxp is not dx:
+                    tv, td = tensor(dxp, c=cin), tensor(dx)
+                    check(self.lib.dg_copy(self.ctx, C.byref(tv), C.byref(td), 0, self.st))
+            return [dx]
+
+        self._push([x], out, w.group, bwd)
+        return out
 
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
                out_dtype=None) -> Var:
@@ -200,6 +307,11 @@ class Engine:
         kh, kw, cin, cout = w.shape
         assert cin == Cin, f"{w.name}: Cin {cin} != input {Cin}"
         pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, stride, padding)
+        if (self.use_umma and self.pad_rgb and min(cin, cout) < 16 and max(cin, cout) % 16 == 0 and kh * kw <= 16 and
+                stride in (1, 2) and (stride == 1 or (H % 2 == 0 and W % 2 == 0))):
+            r = self._conv2d_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype)
+            if r is not None:
+                return r
         seq = self._next()
         y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
         cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))

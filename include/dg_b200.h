@@ -151,6 +151,17 @@ int dg_bias_grad(dg_ctx*, const dg_tensor* dy, float* dbias, int accumulate, voi
 int dg_vgg_preprocess_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
 int dg_vgg_preprocess_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, void* stream);
 
+/* ---- zero-padded channels for the tensor-core path: RGB-sided layers (srgan.py:154 conv 3->64, :182 conv 64->3,
+ * :236-246 discriminator conv 3->32; same in the other models) run on tcgen05 through a 16-channel bf16 copy.
+ * dg_pad_channels: dst[..., :src.c] = src (dtype conversion), dst[..., src.c:] = 0.
+ * dg_umma_pack_weights_padded: dg_umma_pack_weights of the kernel zero-padded to [kh,kw,cin_pad,cout_pad].
+ * dg_unpad_weight_grad: dw[t,c,o] (+)= dw_padded[t,c,o] (c < cin, o < cout), dbias likewise (may be NULL). */
+int dg_pad_channels(dg_ctx*, const dg_tensor* src, const dg_tensor* dst, void* stream);
+int dg_umma_pack_weights_padded(dg_ctx*, const float* w, void* packed, int kh, int kw, int cin, int cout, int cin_pad, int cout_pad,
+                                int mode, void* stream);
+int dg_unpad_weight_grad(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw, int cin,
+                         int cout, int cin_pad, int cout_pad, int accumulate, void* stream);
+
 /* ---- frame pre/post-processing around the inference forward (infer_video.py:138-159, infer.py:50-68,
  * unit_test.py:67-86).  src/dst frames are packed uint8 [n, h, w, 3] in DEVICE memory.
  * dg_frame_to_float: centre crop-or-pad (tf.image.resize_with_crop_or_pad, infer_video.py:142) of the frame to

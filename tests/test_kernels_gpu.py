@@ -515,3 +515,44 @@ def test_thin_layers_mixed_dtypes(L, cin, cout, k):
     nb = lib.dg_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tg), C.byref(cp)); wk = ws(nb)
     L.check(lib.dg_conv2d_wgrad(ctx, C.byref(tx), C.byref(tg), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, st))
     assert relerr(dw, wr.grad) < 1e-5 and relerr(db, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,act,out_f32", [(3, 32, 3, 1, "lrelu", False), (3, 64, 3, 1, None, False),
+                                                          (64, 3, 1, 1, "tanh", True), (3, 64, 4, 2, "lrelu", False)])
+def test_rgb_sided_conv_on_tensor_cores(cin, cout, k, stride, act, out_f32):
+    """3-channel-sided convs (srgan.py:154,182,236; pix2pix.py:147) through the zero-padded 16-channel tcgen05 path:
+    forward, input gradient, kernel and bias gradients against a float64 conv on the same bf16-rounded operands."""
+    from collections import OrderedDict
+    from denoise_gan_b200 import _lib
+    from denoise_gan_b200.engine import Engine
+    from denoise_gan_b200.params import ParamSet
+    from oracle import ops_torch as OT
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    N, H, W = 2, 40, 24
+    w0 = torch.randn((k, k, cin, cout), generator=g) * 0.2
+    b0 = torch.randn((cout,), generator=g) * 0.1
+    x0 = torch.randn((N, H, W, cin), generator=g)
+    E = Engine(bf16=True)
+    ps = ParamSet("g", OrderedDict([("k", w0), ("b", b0)]), E.device)
+    xin = x0.cuda() if cin == 3 else x0.cuda().to(torch.bfloat16)
+    from denoise_gan_b200.engine import Var
+    xv = Var(xin, frozenset({"g"}), E._next())      # depends on group "g": ask for the input gradient as well
+    y = E.conv2d(xv, ps["k"], ps["b"], stride=stride, act=act, alpha=0.2, out_dtype=torch.float32 if out_f32 else None)
+    assert E._cap and any(k_[0] == "padded" and v for k_, v in E._cap.items()), "padded tensor-core path was not taken"
+    gy0 = torch.randn(y.shape, generator=g)
+    gy = gy0.cuda().to(y.t.dtype)
+    coll = {}
+    E.backward([(y, gy)], "g", collect=coll)
+    torch.cuda.synchronize()
+    q = lambda t: t.to(torch.bfloat16).double()
+    xq, wq = q(x0), q(w0)
+    xr = xq.clone().requires_grad_(True); wr = wq.clone().requires_grad_(True); br = b0.double().clone().requires_grad_(True)
+    pre = OT.conv2d(xr, wr, br, stride=stride)
+    ref = {"lrelu": lambda t: torch.nn.functional.leaky_relu(t, 0.2), "tanh": torch.tanh, None: lambda t: t}[act](pre)
+    ref.backward(gy.double().cpu())
+    tol = 2e-2
+    assert relerr(y.t.float().cpu(), ref.detach().float()) < tol
+    dx = E.pool[[kk for kk in E.pool if isinstance(kk[0], tuple) and len(kk[0]) >= 2 and kk[0][0] == y.seq and kk[0][1] == "dx"][0]]
+    assert relerr(dx.float().cpu(), xr.grad.float()) < tol
+    assert relerr(ps["k"].grad.cpu(), wr.grad.float()) < tol
+    assert relerr(ps["b"].grad.cpu(), br.grad.float()) < tol
