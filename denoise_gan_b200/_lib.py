@@ -64,6 +64,7 @@ SIGNATURES = {
     "dg_float_to_frame": (_i, [_P, _T, _f, _f, _i, _i, _P, _i, _i, _P]),
     "dg_debug_conv_timeline": (None, [_P]),
     "dg_debug_conv_flags": (None, [_i]),
+    "dg_debug_wgrad_timeline": (None, [_P]),
     "dg_umma_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),
     "dg_umma_conv2d_wgrad": (_i, [_P, _T, _T, _P, _P, _CP, _i, _P, _sz, _P]),
     "dg_dwconv3x3_fwd": (_i, [_P, _T, _P, _P, _T, _P]),

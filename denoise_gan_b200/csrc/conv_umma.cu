@@ -49,6 +49,8 @@ struct UmmaConvParams {
   uint32_t a_sbo[MAX_SRC], mt_stride[MAX_SRC];
   uint32_t tap_off[MAX_TAPS];
   int tap_src[MAX_TAPS], tap_w[MAX_TAPS];
+  uint64_t tap_adesc[MAX_TAPS];   // complete A descriptor of the tap's window minus the stage base (added to the low word)
+  uint32_t tap_ms16[MAX_TAPS];    // descriptor step between the m sub-tiles of the tap's source
   uint32_t stage_bytes, stage_tx, w_stage_off, w_block_bytes, w_res_bytes, w_res_tx;
   int n_stages, resident, cout_total;
   void* out;
@@ -154,23 +156,24 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
 
 // Issues the MMAs of one pipeline stage (all taps of one channel chunk).  MT and NBK (= chunk/16) are
 // compile-time so the body is straight-line: one descriptor add per operand per tcgen05.mma.
-template <int MT, int NBK>
-__device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int n_taps, uint32_t sa16, uint32_t lbo16, uint32_t b_lo,
-                                            uint32_t b_step, uint64_t b_hi, uint32_t acc0, uint32_t nb, uint32_t idesc,
-                                            bool not_first_chunk) {
-  for (int t = 0; t < n_taps; ++t, b_lo += b_step) {
-    const int s = P.tap_src[t];
-    const uint32_t a_lo = sa16 + ((((P.dbg_flags & 8) ? 0u : P.tap_off[t]) >> 4) | lbo16);
-    const uint64_t a_hi = make_smem_desc_hi(P.a_sbo[s], P.layout) << 32;
-    const uint32_t ms = P.mt_stride[s] >> 4;
+// NT > 0 additionally fixes the tap count, so every per-tap descriptor is a constant-bank load at a static offset and the
+// whole stage is one straight line of tcgen05.mma (the issue thread must stay well under the ~48 cycles a
+// 128 x 64 x 16 MMA occupies the tensor pipe: probes/umma_probe.cu "t2_*").
+template <int MT, int NBK, int NT>
+__device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int n_taps, uint32_t sa16, uint32_t b_lo, uint32_t b_step,
+                                            uint64_t b_hi, uint32_t acc0, uint32_t nb, uint32_t idesc, bool not_first_chunk) {
+  const int nt = NT > 0 ? NT : n_taps;
+#pragma unroll
+  for (int t = 0; t < nt; ++t) {
+    const uint64_t ad = P.tap_adesc[t] + (uint64_t)sa16;
+    const uint32_t ms = P.tap_ms16[t];
     const uint32_t acc_rest = (not_first_chunk || t != 0) ? 1u : 0u;
 #pragma unroll
     for (int k16 = 0; k16 < NBK; ++k16) {
-      const uint64_t bd = b_hi | (uint64_t)(b_lo + 2u * k16);
+      const uint64_t bd = b_hi | (uint64_t)(b_lo + (uint32_t)t * b_step + 2u * k16);
       const uint32_t accf = k16 == 0 ? acc_rest : 1u;
 #pragma unroll
-      for (int m = 0; m < MT; ++m)
-        umma_f16(acc0 + (uint32_t)m * nb, a_hi | (uint64_t)(a_lo + (uint32_t)m * ms + 2u * k16), bd, idesc, accf);
+      for (int m = 0; m < MT; ++m) umma_f16(acc0 + (uint32_t)m * nb, ad + (uint64_t)((uint32_t)m * ms + 2u * k16), bd, idesc, accf);
     }
   }
 }
@@ -293,12 +296,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
           if (elect_one()) {
             const uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
             const uint32_t b_step = resident ? (uint32_t)n_chunks * wblk16 : wblk16;
-#define DG_ISSUE(MT_, NBK_) issue_stage<MT_, NBK_>(P, n_taps, sa16, lbo16, b_lo, b_step, b_hi, acc0, nb, idesc, kc != 0)
+#define DG_ISSUE(MT_, NBK_, NT_) issue_stage<MT_, NBK_, NT_>(P, n_taps, sa16, b_lo, b_step, b_hi, acc0, nb, idesc, kc != 0)
+#define DG_ISSUE_NT(MT_, NBK_) \
+  { if (n_taps == 9) DG_ISSUE(MT_, NBK_, 9); else if (n_taps == 4) DG_ISSUE(MT_, NBK_, 4); else if (n_taps == 1) DG_ISSUE(MT_, NBK_, 1); else DG_ISSUE(MT_, NBK_, 0); }
             if (mt == 1) {
-              if (nbk == 4) DG_ISSUE(1, 4); else if (nbk == 2) DG_ISSUE(1, 2); else DG_ISSUE(1, 1);
+              if (nbk == 4) DG_ISSUE_NT(1, 4) else if (nbk == 2) DG_ISSUE_NT(1, 2) else DG_ISSUE_NT(1, 1)
             } else {
-              if (nbk == 4) DG_ISSUE(2, 4); else if (nbk == 2) DG_ISSUE(2, 2); else DG_ISSUE(2, 1);
+              if (nbk == 4) DG_ISSUE_NT(2, 4) else if (nbk == 2) DG_ISSUE_NT(2, 2) else DG_ISSUE_NT(2, 1)
             }
+#undef DG_ISSUE_NT
 #undef DG_ISSUE
             umma_commit(smem_u32(&bar_a_empty[stage]));
             if (kc == n_chunks - 1) umma_commit(smem_u32(&bar_acc_full[b]));
@@ -465,14 +471,19 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     return tot;
   };
   int best_nb = 0, best_mt = 0, best_res = 0;
+  const long tiles_mt2 = (long)in->n * ((out_h + 31) / 32) * ((out_w + 7) / 8);
   for (int res = 1; res >= 0 && !best_nb; --res)
-    for (int mt = (res ? 1 : 2); mt >= 1 && !best_nb; --mt)
+    for (int mt = 2; mt >= 1 && !best_nb; --mt)
       for (int nb = cout > 256 ? 256 : cout; nb >= 16 && !best_nb; nb -= 16) {
         if (cout % nb != 0 || 2 * mt * nb > 512) continue;
         uint32_t wblk = (uint32_t)nb * kc * 2;
         uint32_t wres = (uint32_t)n_taps * n_chunks * wblk;
         uint32_t stage = halo_bytes(mt) + (res ? 0 : (uint32_t)n_taps * wblk);
-        uint32_t need = (res ? ((wres + 1023u) & ~1023u) : 0) + 2 * ((stage + 1023u) & ~1023u);
+        // resident weights: the taller (32-row) tile halves the per-tile issue bubble, worth it with >= 3 stages in
+        // flight, enough tiles to fill the SMs about three times, and no half-empty bottom tile row
+        const int min_stages = (res && mt == 2) ? 3 : 2;
+        if (res && mt == 2 && (cout > 32 || n_src > 1 || tiles_mt2 < 3L * ctx->sm_count || out_h % 32 != 0)) continue;   // measured: only narrow stride-1 layers gain
+        uint32_t need = (res ? ((wres + 1023u) & ~1023u) : 0) + min_stages * ((stage + 1023u) & ~1023u);
         if (need <= budget) { best_nb = nb; best_mt = mt; best_res = res; }
       }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d taps=%d)", name, in->c, cout, n_taps);
@@ -522,6 +533,8 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     P.tap_src[t] = s;
     P.tap_w[t] = taps[t].widx;
     P.tap_off[t] = P.src_off[s] + (uint32_t)((taps[t].dh - dh_min[s]) * WW + (taps[t].dw - dw_min[s])) * kc * 2;
+    P.tap_adesc[t] = (make_smem_desc_hi(P.a_sbo[s], P.layout) << 32) | (uint64_t)((P.tap_off[t] >> 4) | (1u << 16));
+    P.tap_ms16[t] = P.mt_stride[s] >> 4;
   }
   // weights: 2D [rows][kc]
   {

@@ -47,10 +47,16 @@ struct WgradParams {
   int g_dst[MAX_GROUPS][MAX_ATOMS];  // first dW row (t*Cin + c) of each atom, -1 = padding
   uint32_t dy_off, dy_atom_bytes, stage_bytes, stage_tx, ones_off;
   int n_stages, has_bias, cout_total;
+  long long* dbg;   // optional clock64 timeline of CTA 0 (tools/wgrad_timeline.py); nullptr in production
+  int dump_cw;   // columns staged per pass of the coalesced partial dump (0: direct strided stores)
   float* part;
   long part_stride, bias_off;
   uint32_t a_layout, b_layout, idesc;
 };
+
+__device__ __forceinline__ void wdbg(const WgradParams& P, int role, int it, int slot) {
+  if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 16) P.dbg[(role * 16 + it) * 4 + slot] = clock64();
+}
 
 __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -130,9 +136,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t first = 1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if (lane == 0) wdbg(P, 1, it, 0);
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
+        if (lane == 0) wdbg(P, 1, it, 1);
         const uint32_t sa16 = base16 + (uint32_t)stage * stage16;
         if (elect_one()) {
           for (int g = 0; g < ng; ++g) {
@@ -158,6 +167,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
           umma_commit(smem_u32(&bar_empty[stage]));
         }
         __syncwarp();
+        if (lane == 0) wdbg(P, 1, it, 2);
         first = 0;
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
@@ -167,10 +177,53 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    if (q == 0 && lane == 0) wdbg(P, 2, 0, 0);
     mbar_wait(smem_u32(&bar_done), 0);
     tc_fence_after();
+    if (q == 0 && lane == 0) wdbg(P, 2, 0, 1);
     float* part = P.part + (long)blockIdx.x * P.part_stride;
     const int atom = m / P.kc, r = m - atom * P.kc;
+    if (P.dump_cw > 0) {
+      // Coalesced dump: each warp stages its 32 accumulator rows x cw columns in the (now idle) pipeline buffers and
+      // writes them back as whole float4 rows, so a store instruction covers contiguous 512 bytes instead of 32 lines.
+      const int cw = P.dump_cw, ld = cw + 4, cw4 = cw >> 2;
+      const int cw4_shift = cw4 == 16 ? 4 : (cw4 == 8 ? 3 : 2);
+      const int kc_shift = P.kc == 64 ? 6 : (P.kc == 32 ? 5 : 4);
+      const int at_lo = (q * 32) >> kc_shift, at_hi = (q * 32 + 16) >> kc_shift;   // the (at most two) atoms of this warp's rows
+      float* stg = reinterpret_cast<float*>(base_ptr) + (size_t)q * 32 * ld;
+      for (int g = g_begin; g < g_end; ++g) {
+        for (int cb = 0; cb < P.nb; cb += cw) {
+          for (int c0 = 0; c0 < cw; c0 += 32) {      // two 16-column loads in flight per wait
+            uint32_t v0[16], v1[16];
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_begin) * P.nb + cb + c0);
+            tmem_ld_32x16(ta, v0);
+            if (c0 + 16 < cw) tmem_ld_32x16(ta + 16, v1);
+            tmem_ld_wait();
+            float4* o = reinterpret_cast<float4*>(stg + lane * ld + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = make_float4(__uint_as_float(v0[4 * k]), __uint_as_float(v0[4 * k + 1]),
+                                                         __uint_as_float(v0[4 * k + 2]), __uint_as_float(v0[4 * k + 3]));
+            if (c0 + 16 < cw) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[4 + k] = make_float4(__uint_as_float(v1[4 * k]), __uint_as_float(v1[4 * k + 1]),
+                                                               __uint_as_float(v1[4 * k + 2]), __uint_as_float(v1[4 * k + 3]));
+            }
+          }
+          __syncwarp();
+          // cw4 is 4, 8 or 16 (power of two): rows per store instruction = 32 / cw4
+          const int rstep = 32 >> cw4_shift, row0 = lane >> cw4_shift, c4 = lane & (cw4 - 1);
+          const int dlo = at_lo < MAX_ATOMS ? P.g_dst[g][at_lo] : -1, dhi = at_hi < MAX_ATOMS ? P.g_dst[g][at_hi] : -1;
+          for (int row = row0; row < 32; row += rstep) {
+            const int mm = q * 32 + row;
+            const int dst = row < 16 ? dlo : dhi;
+            if (dst >= 0)
+              *reinterpret_cast<float4*>(part + (long)(dst + (mm & (P.kc - 1))) * P.cout_total + nb0 + cb + c4 * 4) =
+                  *reinterpret_cast<const float4*>(stg + row * ld + c4 * 4);
+          }
+          __syncwarp();
+        }
+      }
+    } else
     for (int g = g_begin; g < g_end; ++g) {
       const int dst = atom < MAX_ATOMS ? P.g_dst[g][atom] : -1;
       for (int c0 = 0; c0 < P.nb; c0 += 16) {
@@ -199,6 +252,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       }
     }
   }
+  if (warp == 2 && lane == 0) wdbg(P, 2, 0, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
@@ -351,7 +405,7 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d)", name, x->c, cout);
   pl->nb = best_nb;
-  pl->gpc = 512 / best_nb - (has_bias ? 1 : 0);
+  pl->gpc = 512 / best_nb - (has_bias ? 1 : 0);      // accumulator groups that fit TMEM
   if (pl->gpc > MAX_GROUPS) pl->gpc = MAX_GROUPS;
   pl->zblocks = (n_groups + pl->gpc - 1) / pl->gpc;
   pl->yblocks = cout / best_nb;
@@ -364,7 +418,11 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   return 0;
 }
 
+static long long* g_wgrad_dbg = nullptr;
+
 }  // namespace
+
+extern "C" void dg_debug_wgrad_timeline(void* dev_buffer) { g_wgrad_dbg = (long long*)dev_buffer; }
 
 extern "C" size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
   // one full fp32 dW (+ bias row) per pixel split; sized for devices of up to 160 SMs
@@ -507,7 +565,12 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     int n_stages = (int)((budget - ones_bytes - slack) / P.stage_bytes);
     if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
     P.n_stages = n_stages;
+    P.dbg = g_wgrad_dbg;
     P.ones_off = (uint32_t)n_stages * P.stage_bytes;
+    {
+      int cw = pl.nb >= 64 ? 64 : (pl.nb >= 32 && pl.nb % 32 == 0 ? 32 : 16);
+      P.dump_cw = (size_t)4 * 32 * (cw + 4) * sizeof(float) <= (size_t)n_stages * P.stage_bytes ? cw : 0;
+    }
     const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;
     dim3 grid(pl.splits, pl.yblocks, zblocks);
     umma_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(P);

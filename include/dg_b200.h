@@ -89,7 +89,8 @@ int dg_umma_conv2d_fwd_supported(dg_ctx*, const dg_tensor* x, const dg_tensor* y
 int dg_umma_conv2d_dgrad_supported(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p);
 /* debug aid (tools/conv_timeline.py): device buffer of 3*16*4 int64 receiving clock64() marks of CTA 0, or NULL */
 void dg_debug_conv_timeline(void* dev_buffer);
-void dg_debug_conv_flags(int flags); /* debug experiments only: results are WRONG when non-zero */
+void dg_debug_conv_flags(int flags);
+void dg_debug_wgrad_timeline(void* dev_buffer);   /* same for the weight-gradient kernel */ /* debug experiments only: results are WRONG when non-zero */
 size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
 int dg_umma_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw_hwio, float* dbias,
                          const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,

@@ -51,6 +51,8 @@ struct ProbeCase {
   int n_cols;
   uint32_t dump_bytes;
   int repeat;  // timing mode: issue the MMA list this many times and report cycles
+  int n_acc;   // timing mode: round-robin over this many independent accumulators (0/1 = one dependent chain)
+  uint32_t acc_stride;
 };
 
 constexpr int SMEM_DATA = 160 * 1024;
@@ -120,11 +122,20 @@ probe_kernel(const __grid_constant__ Maps maps, const ProbeCase* __restrict__ pc
         }
         const uint32_t idesc = pc.idesc;
         const int nm = pc.n_mma;
-        t0 = clock64();
-        for (int rep = 0; rep < reps; ++rep) {
+        uint32_t dq[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nm) umma_f16(tmem, adq[i], bdq[i], idesc, 1u);
+        for (int i = 0; i < 8; ++i) dq[i] = tmem + (pc.n_acc > 1 ? (uint32_t)(i % pc.n_acc) * pc.acc_stride : 0u);
+        t0 = clock64();
+        if (nm == 8) {
+          for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) umma_f16(dq[i], adq[i], bdq[i], idesc, 1u);
+          }
+        } else {
+          for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) umma_f16(dq[i], adq[i], bdq[i], idesc, 1u);
+          }
         }
       } else
       for (int rep = 0; rep < reps; ++rep)
@@ -518,6 +529,61 @@ int main() {
              (double)st[1] / n, (double)st[2] / n);
       fflush(stdout);
     }
+  }
+  // ---- T2: is the ~98-cycle K-major floor a dependent-accumulator chain or operand fetch?  Independent accumulators
+  //          and the narrower swizzles (a K=16 slice is a whole 32-byte row under SW32).
+  {
+    struct Off { uint32_t a, b; };
+    auto timing2 = [&](const char* name, int M, int N, int a_mn, int b_mn, uint32_t layout, uint32_t a_sbo, uint32_t a_lbo,
+                       uint32_t b_sbo, uint32_t b_lbo, std::vector<Off> offs, int n_acc) {
+      ProbeCase pc = base_case();
+      pc.loads[pc.n_loads++] = {0, 2, 0, 0, 0, 0, 0};
+      pc.tx_bytes = 256 * 128;
+      add_B64(pc, 5, 0, 256 * 128);
+      pc.n_cols = N * (n_acc > 1 ? n_acc : 1);
+      pc.idesc = sm100::make_idesc_bf16(M, N, a_mn, b_mn);
+      pc.a_layout = pc.b_layout = layout;
+      pc.a_sbo = a_sbo; pc.a_lbo = a_lbo; pc.b_sbo = b_sbo; pc.b_lbo = b_lbo;
+      for (auto& o : offs) pc.mma[pc.n_mma++] = {o.a, B_OFF + o.b};
+      pc.repeat = 256; pc.n_acc = n_acc; pc.acc_stride = (uint32_t)N;
+      CK(cudaMemset(d_status, 0, 16));
+      CK(cudaMemcpy(d_pc, &pc, sizeof(pc), cudaMemcpyHostToDevice));
+      probe_kernel<<<1, 128, SMEM_DATA + 1024>>>(maps, d_pc, d_out, d_dump, d_status);
+      CK(cudaDeviceSynchronize());
+      int st[4];
+      CK(cudaMemcpy(st, d_status, 16, cudaMemcpyDeviceToHost));
+      int n = pc.n_mma * pc.repeat;
+      printf("{\"timing\": \"%s\", \"status\": %d, \"mmas\": %d, \"issue_cycles_per_mma\": %.1f, \"total_cycles_per_mma\": %.1f}\n", name, st[0], n,
+             (double)st[1] / n, (double)st[2] / n);
+      fflush(stdout);
+    };
+    using sm100::LAYOUT_SW128; using sm100::LAYOUT_SW64; using sm100::LAYOUT_SW32;
+    std::vector<Off> k128 = {{0, 0}, {32, 32}, {64, 64}, {96, 96}};
+    std::vector<Off> k128x8 = {{0, 0}, {32, 32}, {64, 64}, {96, 96}, {0, 0}, {32, 32}, {64, 64}, {96, 96}};
+    timing2("t2_k128_N64_acc1", 128, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1);
+    timing2("t2_k128_N64_acc2", 128, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 2);
+    timing2("t2_k128_N64_acc4", 128, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
+    timing2("t2_k128_N128_acc2", 128, 128, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 2);
+    timing2("t2_k128_N32_acc4", 128, 32, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
+    timing2("t2_k128_M64_N256_acc2", 64, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 2);
+    std::vector<Off> k32 = {{0, 0}, {4096, 8192}, {8192, 16384}, {12288, 24576}, {0, 0}, {4096, 8192}, {8192, 16384}, {12288, 24576}};
+    timing2("t2_ksw32_N64_acc1", 128, 64, 0, 0, LAYOUT_SW32, 256, 16, 256, 16, k32, 1);
+    timing2("t2_ksw32_N64_acc2", 128, 64, 0, 0, LAYOUT_SW32, 256, 16, 256, 16, k32, 2);
+    std::vector<Off> k64 = {{0, 0}, {32, 32}, {8192, 16384}, {8224, 16416}, {0, 0}, {32, 32}, {8192, 16384}, {8224, 16416}};
+    timing2("t2_ksw64_N64_acc1", 128, 64, 0, 0, LAYOUT_SW64, 512, 16, 512, 16, k64, 1);
+    timing2("t2_ksw64_N64_acc2", 128, 64, 0, 0, LAYOUT_SW64, 512, 16, 512, 16, k64, 2);
+    std::vector<Off> mn8;
+    for (uint32_t k = 0; k < 8; ++k) mn8.push_back({k * 2048, k * 2048});
+    timing2("t2_mn_N64_acc1", 128, 64, 1, 1, LAYOUT_SW128, 1024, 24576, 1024, 32768, mn8, 1);
+    timing2("t2_mn_N64_acc2", 128, 64, 1, 1, LAYOUT_SW128, 1024, 24576, 1024, 32768, mn8, 2);
+    timing2("t2_mn_N64_acc4", 128, 64, 1, 1, LAYOUT_SW128, 1024, 24576, 1024, 32768, mn8, 4);
+    timing2("t2_mn_N128_acc2", 128, 128, 1, 1, LAYOUT_SW128, 1024, 24576, 1024, 32768, mn8, 2);
+    timing2("t2_k128_N128_acc1", 128, 128, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1);
+    timing2("t2_k128_N256_acc1", 128, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1);
+    timing2("t2_k128_N256_acc2", 128, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 2);
+    timing2("t2_k128_N16_acc4", 128, 16, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
+    timing2("t2_k128_M64_N64_acc4", 64, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
+    timing2("t2_k128_M64_N256_acc1", 64, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1);
   }
   printf("{\"summary\": {\"pass\": %d, \"fail\": %d}}\n", n_pass, n_fail);
   return 0;
