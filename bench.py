@@ -71,6 +71,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant family's most frequent launch (64->64 3x3 conv of the
+# generator body, 66 of the 141 umma_conv launches of a step) from the `ncu --set full` capture in
+# profiles/ncu_body_conv_wgrad_r1c_details.csv; the algorithmic bytes of that launch are 37.8 MB (18.9 in + 18.9 out):
+# the output stays in the 126 MB L2 for the next kernel, the input is read from DRAM exactly once.
+CONV_TRAFFIC_BYTES = {"srgan_c3": 19.03e6}
+
+
 def make_model(wl, fp16=1, vgg=0):
     from denoise_gan_b200.srgan import SRGAN
     _, crop, scale, _, _, _ = WORKLOADS[wl]
@@ -257,7 +264,7 @@ def main():
             "step_tflops": images_s * gf_img / 1e3 / world,
             "step_frac_of_bf16_burst": images_s * gf_img / 1e3 / world / burst,
             "roofline": {"bound": "tensor", "kernel": top[0], "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": ach / sustained, "traffic": None, "peak_source": peak_src + ", sustained figure (kernel timed inside a step)",
+                         "frac": ach / sustained, "traffic": CONV_TRAFFIC_BYTES.get(wl), "peak_source": peak_src + ", sustained figure (kernel timed inside a step)",
                          "conv_families": kinds, "conv_share_of_step": conv_ms / ms if args.no_graph else None},
             "e2e": {"value": world * batch / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_h.numel() * 4 + y_h.numel() * 4,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},

@@ -25,6 +25,7 @@
 // Reference call sites: Conv2D srgan.py:154-182,246-268, fsrgan.py:134-217, autoencoder.py:95-104,
 // pix2pix.py:115,207-218; Conv2DTranspose pix2pix.py:130,169; gradients train_srgan.py:111-112.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "dg_common.cuh"
 #include "sm100.cuh"
@@ -482,7 +483,9 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
         // resident weights: the taller (32-row) tile halves the per-tile issue bubble, worth it with >= 3 stages in
         // flight, enough tiles to fill the SMs about three times, and no half-empty bottom tile row
         const int min_stages = (res && mt == 2) ? 3 : 2;
-        if (res && mt == 2 && (cout > 32 || n_src > 1 || tiles_mt2 < 3L * ctx->sm_count || out_h % 32 != 0)) continue;   // measured: only narrow stride-1 layers gain
+        static const char* dbg_mt = getenv("DG_DEBUG_MT");   // experiments only
+        if (dbg_mt && res && nb == cout) { if (mt != atoi(dbg_mt)) continue; }
+        else if (res && mt == 2 && (cout > 32 || n_src > 1 || tiles_mt2 < 3L * ctx->sm_count || out_h % 32 != 0)) continue;   // measured: only narrow stride-1 layers gain
         uint32_t need = (res ? ((wres + 1023u) & ~1023u) : 0) + min_stages * ((stage + 1023u) & ~1023u);
         if (need <= budget) { best_nb = nb; best_mt = mt; best_res = res; }
       }
