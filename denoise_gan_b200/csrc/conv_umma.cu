@@ -37,7 +37,7 @@ using namespace sm100;
 constexpr int MAX_SRC = 4;
 constexpr int MAX_TAPS = 16;
 constexpr int MAX_STAGES = 6;
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 224;   // TMA producer, MMA issuer, 4 epilogue warps, second MMA issuer
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 
 struct UmmaConvParams {
@@ -54,6 +54,7 @@ struct UmmaConvParams {
   uint32_t tap_ms16[MAX_TAPS];    // descriptor step between the m sub-tiles of the tap's source
   uint32_t stage_bytes, stage_tx, w_stage_off, w_block_bytes, w_res_bytes, w_res_tx;
   int n_stages, resident, cout_total;
+  int nbuf_shift;   // log2 of the TMEM accumulator buffers: 2 (four buffers, TWO issuing warps on alternate tiles) or 1
   void* out;
   long out_sn, out_sh, out_sw;
   int out_f32;
@@ -113,14 +114,14 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-    const int b = it & 1;
-    const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+    const int b = it & ((1 << P.nbuf_shift) - 1);
+    const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
     const int tw = tile % P.tiles_w;
     const int t2 = tile / P.tiles_w;
     const int th = t2 % P.tiles_h;
     const int n = t2 / P.tiles_h;
     if (q == 0 && lane == 0) dbg_mark(P, 2, it, 0);
-    mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
+    mbar_wait_warp<0>(smem_u32(&bar_acc_full[b]), acc_phase);
     tc_fence_after();
     if (q == 0 && lane == 0) dbg_mark(P, 2, it, 1);
     for (int m = 0; m < P.mt; ++m) {
@@ -182,11 +183,17 @@ __device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int n_taps,
 __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
-  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_w;
+  __shared__ __align__(8) uint64_t bar_acc_full[4], bar_acc_empty[4], bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (P.dbg && tid == 0 && blockIdx.y == 0) {   // kernel-lifetime marks: [CTA][0] entry clock, [1] exit clock, [2]/[3] globaltimer ns
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.dbg[256 + blockIdx.x * 4 + 0] = clock64();
+    P.dbg[256 + blockIdx.x * 4 + 2] = (long long)gt;
+  }
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
   const uint32_t stage_base = base + (P.resident ? P.w_res_bytes : 0u);
@@ -198,12 +205,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       mbar_init(smem_u32(&bar_a_full[s]), 1);
       mbar_init(smem_u32(&bar_a_empty[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
       mbar_init(smem_u32(&bar_acc_empty[b]), 4);
     }
     mbar_init(smem_u32(&bar_w), 1);
     fence_mbar_init();
+    // the resident weights start loading before the CTA-wide sync, under the TMEM allocation of warp 1
+    for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
+    tma_prefetch_desc(&P.wmap);
+    if (P.resident) {
+      const uint32_t bw = smem_u32(&bar_w);
+      mbar_expect_tx(bw, P.w_res_tx);
+      for (int b = 0; b < P.n_taps * P.n_chunks; ++b) {
+        // resident block b = tap_slot * n_chunks + chunk; source rows come from the tap's weight index
+        int t = b / P.n_chunks, kc = b - t * P.n_chunks;
+        tma_load_2d(w_base + (uint32_t)b * P.w_block_bytes, &P.wmap, bw, 0,
+                    (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
+      }
+    }
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(&tmem_slot), 512);
@@ -217,33 +237,28 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
-      tma_prefetch_desc(&P.wmap);
-      if (P.resident) {
-        const uint32_t bw = smem_u32(&bar_w);
-        mbar_expect_tx(bw, P.w_res_tx);
-        for (int b = 0; b < P.n_taps * P.n_chunks; ++b) {
-          // resident block b = tap_slot * n_chunks + chunk; source rows come from the tap's weight index
-          int t = b / P.n_chunks, kc = b - t * P.n_chunks;
-          tma_load_2d(w_base + (uint32_t)b * P.w_block_bytes, &P.wmap, bw, 0,
-                      (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
-        }
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // Pipeline slots form one ring per issuing warp (slot s belongs to issuer s % n_issuers), so every mbarrier has
+      // exactly one producer/consumer pair walking consecutive phases.
+      const int n_iss = P.nbuf_shift == 2 ? 2 : 1, half = P.n_stages / n_iss;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         int tw = tile % P.tiles_w;
         int t2 = tile / P.tiles_w;
         int th = t2 % P.tiles_h;
         int n = t2 / P.tiles_h;
         const int h0 = th * 16 * P.mt, w0 = tw * 8;
-        const int pit = (tile - (int)blockIdx.x) / (int)gridDim.x;
+        const int pit = it;
+        const int wi = it % n_iss;
+        const uint32_t j0 = (uint32_t)(it / n_iss) * (uint32_t)P.n_chunks;
         dbg_mark(P, 0, pit, 0);
         for (int kc = 0; kc < P.n_chunks; ++kc) {
+          const uint32_t j = j0 + (uint32_t)kc;
+          const int stage = (int)(j % (uint32_t)half) * n_iss + wi;
+          const uint32_t phase = (j / (uint32_t)half) & 1u;
           const uint32_t full = smem_u32(&bar_a_full[stage]);
           mbar_wait(smem_u32(&bar_a_empty[stage]), phase ^ 1u);
           if (kc == 0) dbg_mark(P, 0, pit, 1);
-          if ((P.dbg_flags & 4) && pit >= P.n_stages) { mbar_arrive(full); if (++stage == P.n_stages) { stage = 0; phase ^= 1u; } continue; }
+          if ((P.dbg_flags & 4) && pit >= P.n_stages) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, P.stage_tx);
           const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
           for (int s = 0; s < P.n_src; ++s)
@@ -252,13 +267,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
             for (int t = 0; t < P.n_taps; ++t)
               tma_load_2d(sa + P.w_stage_off + (uint32_t)t * P.w_block_bytes, &P.wmap, full, 0,
                           (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
-          if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
         }
         dbg_mark(P, 0, pit, 2);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 6) {
+    // ------------------------------------------------------------------ MMA issuer(s)
     // The WHOLE warp runs this loop with warp-uniform values (kernel parameters, loop counters) and only
     // the tcgen05 instructions sit under elect_one(): UTCHMMA takes its descriptors from UNIFORM registers,
     // and when the loop ran under `if (lane == 0)` every operand went through R2UR with a scoreboard wait
@@ -275,24 +289,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       const uint32_t stage16 = P.stage_bytes >> 4, sbase16 = stage_base >> 4;
       const bool resident = P.resident != 0;
       if (resident) {
-        mbar_wait(smem_u32(&bar_w), 0);
+        mbar_wait_warp<0>(smem_u32(&bar_w), 0);
         tc_fence_after();
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        if (lane == 0) dbg_mark(P, 1, it, 0);
-        mbar_wait(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
+      // With four accumulator buffers two warps issue alternate tiles, so the tensor pipe always has the other
+      // warp's MMAs queued while one warp walks its barriers between tiles (a single issuer let the pipe drain and
+      // refill every 128-pixel tile: ~500 of 2700 cycles on the 64-channel layers, tools/conv_timeline.py).
+      const int n_issuers = P.nbuf_shift == 2 ? 2 : 1;
+      const int me = warp == 1 ? 0 : 1;
+      if (me < n_issuers)
+      for (int it = me, tile = blockIdx.x + me * (int)gridDim.x; tile < total_tiles; tile += n_issuers * (int)gridDim.x, it += n_issuers) {
+        const int b = it & ((1 << P.nbuf_shift) - 1);
+        const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
+        const uint32_t half = (uint32_t)(n_stages / n_issuers);
+        const uint32_t j0 = (uint32_t)(it / n_issuers) * (uint32_t)n_chunks;   // this issuer's slot sequence number
+        if (lane == 0 && me == 0) dbg_mark(P, 1, it, 0);
+        mbar_wait_warp<0>(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0) dbg_mark(P, 1, it, 1);
+        if (lane == 0 && me == 0) dbg_mark(P, 1, it, 1);
         const uint32_t acc0 = tmem + (uint32_t)(b * mt) * nb;
         for (int kc = 0; kc < n_chunks; ++kc) {
-          mbar_wait(smem_u32(&bar_a_full[stage]), phase);
+          const uint32_t j = j0 + (uint32_t)kc;
+          const int stage = (int)(j % half) * n_issuers + me;
+          const uint32_t phase = (j / half) & 1u;
+          mbar_wait_warp<0>(smem_u32(&bar_a_full[stage]), phase);
           tc_fence_after();
-          if (kc == 0 && lane == 0) dbg_mark(P, 1, it, 2);
+          if (kc == 0 && lane == 0 && me == 0) dbg_mark(P, 1, it, 2);
           const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;
           if (elect_one()) {
             const uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
@@ -311,9 +333,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
             if (kc == n_chunks - 1) umma_commit(smem_u32(&bar_acc_full[b]));
           }
           __syncwarp();
-          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        if (lane == 0) dbg_mark(P, 1, it, 3);
+        if (lane == 0 && me == 0) dbg_mark(P, 1, it, 3);
       }
     }
   } else {
@@ -340,6 +361,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (P.dbg && tid == 0 && blockIdx.y == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.dbg[256 + blockIdx.x * 4 + 1] = clock64();
+    P.dbg[256 + blockIdx.x * 4 + 3] = (long long)gt;
+  }
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -493,6 +520,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   if (dry) return 0;   // capability query: a tile configuration exists
   const int nb = best_nb, mt = best_mt;
   P.nb = nb; P.mt = mt; P.resident = best_res;
+
   P.w_block_bytes = (uint32_t)nb * kc * 2;
   P.w_res_tx = best_res ? (uint32_t)n_taps * n_chunks * P.w_block_bytes : 0;
   P.w_res_bytes = (P.w_res_tx + 1023u) & ~1023u;
@@ -529,6 +557,12 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   int n_stages = (int)((budget - P.w_res_bytes) / P.stage_bytes);
   if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
   DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
+  {
+    // two issuing warps need four TMEM accumulator buffers and at least two pipeline slots each
+    static const char* dbg_single = getenv("DG_DEBUG_SINGLE_ISSUER");   // experiments only
+    P.nbuf_shift = (4 * mt * nb <= 512 && n_stages >= 4 && !dbg_single) ? 2 : 1;
+    if (P.nbuf_shift == 2) n_stages &= ~1;
+  }
   P.n_stages = n_stages;
   for (int t = 0; t < n_taps; ++t) {
     int s = taps[t].src;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         if (lane == 0) wdbg(P, 1, it, 0);
-        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        mbar_wait_warp<0>(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         if (lane == 0) wdbg(P, 1, it, 1);
         const uint32_t sa16 = base16 + (uint32_t)stage * stage16;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
     const int q = warp & 3;
     const int m = q * 32 + lane;
     if (q == 0 && lane == 0) wdbg(P, 2, 0, 0);
-    mbar_wait(smem_u32(&bar_done), 0);
+    mbar_wait_warp<256>(smem_u32(&bar_done), 0);
     tc_fence_after();
     if (q == 0 && lane == 0) wdbg(P, 2, 0, 1);
     float* part = P.part + (long)blockIdx.x * P.part_stride;

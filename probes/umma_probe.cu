@@ -535,7 +535,7 @@ int main() {
   {
     struct Off { uint32_t a, b; };
     auto timing2 = [&](const char* name, int M, int N, int a_mn, int b_mn, uint32_t layout, uint32_t a_sbo, uint32_t a_lbo,
-                       uint32_t b_sbo, uint32_t b_lbo, std::vector<Off> offs, int n_acc) {
+                       uint32_t b_sbo, uint32_t b_lbo, std::vector<Off> offs, int n_acc, int grid = 1) {
       ProbeCase pc = base_case();
       pc.loads[pc.n_loads++] = {0, 2, 0, 0, 0, 0, 0};
       pc.tx_bytes = 256 * 128;
@@ -548,12 +548,14 @@ int main() {
       pc.repeat = 256; pc.n_acc = n_acc; pc.acc_stride = (uint32_t)N;
       CK(cudaMemset(d_status, 0, 16));
       CK(cudaMemcpy(d_pc, &pc, sizeof(pc), cudaMemcpyHostToDevice));
-      probe_kernel<<<1, 128, SMEM_DATA + 1024>>>(maps, d_pc, d_out, d_dump, d_status);
+      pc.repeat = grid > 1 ? 2048 : 256;     // long enough for chip-level power management to act
+      CK(cudaMemcpy(d_pc, &pc, sizeof(pc), cudaMemcpyHostToDevice));
+      probe_kernel<<<grid, 128, SMEM_DATA + 1024>>>(maps, d_pc, d_out, d_dump, d_status);
       CK(cudaDeviceSynchronize());
       int st[4];
       CK(cudaMemcpy(st, d_status, 16, cudaMemcpyDeviceToHost));
       int n = pc.n_mma * pc.repeat;
-      printf("{\"timing\": \"%s\", \"status\": %d, \"mmas\": %d, \"issue_cycles_per_mma\": %.1f, \"total_cycles_per_mma\": %.1f}\n", name, st[0], n,
+      printf("{\"timing\": \"%s\", \"ctas\": %d, \"status\": %d, \"mmas\": %d, \"issue_cycles_per_mma\": %.1f, \"total_cycles_per_mma\": %.1f}\n", name, grid, st[0], n,
              (double)st[1] / n, (double)st[2] / n);
       fflush(stdout);
     };
@@ -584,6 +586,12 @@ int main() {
     timing2("t2_k128_N16_acc4", 128, 16, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
     timing2("t2_k128_M64_N64_acc4", 64, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
     timing2("t2_k128_M64_N256_acc1", 64, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1);
+    // the same loops on every SM at once: chip-level (power) limits on the tensor pipe
+    timing2("t3_allsm_k128_N64", 128, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1, 148);
+    timing2("t3_allsm_k128_N128", 128, 128, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1, 148);
+    timing2("t3_allsm_k128_N256", 128, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1, 148);
+    timing2("t3_allsm_mn_N64", 128, 64, 1, 1, LAYOUT_SW128, 1024, 24576, 1024, 32768, mn8, 1, 148);
+    timing2("t3_allsm_k128_N32", 128, 32, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4, 148);
   }
   printf("{\"summary\": {\"pass\": %d, \"fail\": %d}}\n", n_pass, n_fail);
   return 0;

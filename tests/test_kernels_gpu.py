@@ -556,3 +556,41 @@ def test_rgb_sided_conv_on_tensor_cores(cin, cout, k, stride, act, out_f32):
     assert relerr(dx.float().cpu(), xr.grad.float()) < tol
     assert relerr(ps["k"].grad.cpu(), wr.grad.float()) < tol
     assert relerr(ps["b"].grad.cpu(), br.grad.float()) < tol
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,kind", [(8, 96, 96, 64, 64, 3, "fwd"), (4, 96, 96, 256, 64, 3, "fwd"),
+                                                   (8, 96, 96, 32, 32, 3, "dgrad"), (6, 64, 64, 128, 128, 3, "fwd")])
+def test_umma_conv_many_tiles_per_cta(N, H, W, cin, cout, k, kind):
+    """Several tiles per persistent CTA: exercises the two alternating MMA-issuing warps, their per-issuer pipeline
+    rings (multi-chunk K with streamed weights included) and the four TMEM accumulator buffers."""
+    from denoise_gan_b200 import _lib as L
+    lib, ctx, st = L.load(), L.ctx(), L.stream_ptr()
+    g = torch.Generator().manual_seed(N * 1000 + cin)
+    x0 = torch.randn((N, H, W, cin), generator=g).to(torch.bfloat16)
+    w0 = (torch.randn((k, k, cin, cout), generator=g) * 0.05)
+    xd = x0.cuda()
+    wd = w0.cuda()
+    pk = torch.empty(w0.numel(), dtype=torch.bfloat16, device="cuda")
+    cp = L.DgConvParams(k, k, 1, k // 2, k // 2, 0, 0.0)
+    wq = w0.to(torch.bfloat16).float()
+    if kind == "fwd":
+        L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 0, st))
+        y = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device="cuda")
+        tx, ty = L.tensor(xd), L.tensor(y)
+        L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
+        ref = OT.conv2d(x0.float(), wq)
+        out = y
+    else:   # dgrad: x0 plays dy [N,H,W,cin->"cout" of the conv]; conv is cout_conv=cin, cin_conv=cout
+        wconv = (torch.randn((k, k, cout, cin), generator=g) * 0.05)
+        pk = torch.empty(wconv.numel(), dtype=torch.bfloat16, device="cuda")
+        wcd = wconv.cuda()
+        L.check(lib.dg_umma_pack_weights(ctx, wcd.data_ptr(), pk.data_ptr(), k, k, cout, cin, 1, st))
+        dx = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device="cuda")
+        tdy, tdx = L.tensor(xd), L.tensor(dx)
+        L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tdy), pk.data_ptr(), None, C.byref(tdx), C.byref(cp), st))
+        xin = torch.zeros((N, H, W, cout), dtype=torch.float32, requires_grad=True)
+        OT.conv2d(xin, wconv.to(torch.bfloat16).float()).backward(x0.float())
+        ref = xin.grad
+        out = dx
+    torch.cuda.synchronize()
+    assert relerr(out.float().cpu(), ref) < 2e-2

@@ -26,12 +26,13 @@ import os as _os
 flags = int(_os.environ.get("DG_FLAGS", "0"))
 lib.dg_debug_conv_flags(flags)
 print("flags", flags)
-dbg = torch.zeros(3 * 16 * 4, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(256 + 148 * 4, dtype=torch.int64, device="cuda")
 lib.dg_debug_conv_timeline(dbg.data_ptr())
 L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
 torch.cuda.synchronize()
 lib.dg_debug_conv_timeline(None)
-t = dbg.cpu().view(3, 16, 4)
+life = dbg.cpu()[256:].view(148, 4)
+t = dbg.cpu()[:192].view(3, 16, 4)
 t0 = int(t[t > 0].min())
 names = {0: ["tile start", "slot free", "loads issued", ""], 1: ["tile start", "acc free", "operands landed", "mma issued+commit"],
          2: ["tile start", "acc full", "stored+released", ""]}
@@ -45,3 +46,8 @@ for role, rn in enumerate(["producer", "mma", "epilogue"]):
         if int(row.max()) == 0:
             continue
         print("  tile", it, "  ".join(f"{names[role][s]}={int(row[s]) - t0}" for s in range(4) if int(row[s]) > 0))
+
+cyc = (life[:, 1] - life[:, 0]).float()
+ns0, ns1 = life[:, 2].min().item(), life[:, 3].max().item()
+print(f"CTA lifetimes: min {cyc.min().item():.0f} mean {cyc.mean().item():.0f} max {cyc.max().item():.0f} cycles; "
+      f"first entry -> last exit {ns1 - ns0} ns; entry spread {life[:, 2].max().item() - ns0} ns; CTA0 entry->first mark {t0 - int(life[0, 0])} cycles")
