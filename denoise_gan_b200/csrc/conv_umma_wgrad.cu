@@ -425,11 +425,17 @@ static long long* g_wgrad_dbg = nullptr;
 extern "C" void dg_debug_wgrad_timeline(void* dev_buffer) { g_wgrad_dbg = (long long*)dev_buffer; }
 
 extern "C" size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
-  // one full fp32 dW (+ bias row) per pixel split; sized for devices of up to 160 SMs
-  Plan pl;
-  if (make_plan("dg_umma_conv2d_wgrad_workspace_bytes", 160, x, dy, p, 1, &pl)) return 0;
+  // one full fp32 dW (+ bias row) per pixel split; sized for devices of up to 160 SMs and for a call with or without a
+  // bias gradient (the bias accumulator changes how many groups fit TMEM, hence the split count)
   size_t per = (size_t)p->kh * p->kw * x->c * dy->c + dy->c;
-  return (size_t)pl.splits * per * sizeof(float);
+  int splits = 0;
+  for (int has_bias = 0; has_bias < 2; ++has_bias)
+    for (int sms = 132; sms <= 160; sms += 4) {
+      Plan pl;
+      if (make_plan("dg_umma_conv2d_wgrad_workspace_bytes", sms, x, dy, p, has_bias, &pl)) return 0;
+      splits = pl.splits > splits ? pl.splits : splits;
+    }
+  return (size_t)splits * per * sizeof(float);
 }
 
 extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias,
@@ -568,7 +574,7 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     P.dbg = g_wgrad_dbg;
     P.ones_off = (uint32_t)n_stages * P.stage_bytes;
     {
-      int cw = pl.nb >= 64 ? 64 : (pl.nb >= 32 && pl.nb % 32 == 0 ? 32 : 16);
+      int cw = pl.nb % 64 == 0 ? 64 : (pl.nb % 32 == 0 ? 32 : 16);   // must divide the N block (e.g. 112 = 7 x 16)
       P.dump_cw = (size_t)4 * 32 * (cw + 4) * sizeof(float) <= (size_t)n_stages * P.stage_bytes ? cw : 0;
     }
     const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;

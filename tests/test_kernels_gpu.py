@@ -558,6 +558,31 @@ def test_rgb_sided_conv_on_tensor_cores(cin, cout, k, stride, act, out_f32):
     assert relerr(ps["b"].grad.cpu(), br.grad.float()) < tol
 
 
+def test_umma_wgrad_odd_multiples_of_16():
+    """autoencoder.py conv7: 208 -> 112 channels (13 and 7 chunks of 16): N block 112, padding atoms, partial dump."""
+    from denoise_gan_b200 import _lib as L
+    lib, ctx, st = L.load(), L.ctx(), L.stream_ptr()
+    g = torch.Generator().manual_seed(5)
+    N, H, W, cin, cout, k = 4, 32, 32, 208, 112, 3
+    x0 = torch.randn((N, H, W, cin), generator=g).to(torch.bfloat16)
+    dy0 = torch.randn((N, H, W, cout), generator=g).to(torch.bfloat16)
+    xd, dyd = x0.cuda(), dy0.cuda()
+    cp = L.DgConvParams(k, k, 1, 1, 1, 0, 0.0)
+    tx, tdy = L.tensor(xd), L.tensor(dyd)
+    nbytes = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(cp))
+    assert nbytes > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dw = torch.empty((k, k, cin, cout), device="cuda"); db = torch.empty(cout, device="cuda")
+    guard = torch.full((1 << 16,), 7.0, device="cuda")      # canary right after the outputs in allocation order
+    L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(tdy), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, ws.data_ptr(), nbytes, st))
+    torch.cuda.synchronize()
+    w = torch.zeros((k, k, cin, cout), dtype=torch.float32, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    OT.conv2d(x0.float(), w, b).backward(dy0.float())
+    assert relerr(dw.cpu(), w.grad) < 2e-2 and relerr(db.cpu(), b.grad) < 2e-2
+    assert bool((guard == 7.0).all())
+
+
 @pytest.mark.parametrize("N,H,W,cin,cout,k,kind", [(8, 96, 96, 64, 64, 3, "fwd"), (4, 96, 96, 256, 64, 3, "fwd"),
                                                    (8, 96, 96, 32, 32, 3, "dgrad"), (6, 64, 64, 128, 128, 3, "fwd")])
 def test_umma_conv_many_tiles_per_cta(N, H, W, cin, cout, k, kind):
