@@ -390,7 +390,9 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
       for (int t = 0; t < pl->n_taps; ++t) cnt += pl->taps[t].src == s;
       padding = padding || (cnt % atoms) != 0;
     }
-  pl->slack = padding ? max_chunk : 0;
+  // Padding atoms read (and discard) shared memory BEHIND the last real chunk box of the stage: with several chunks per
+  // M=128 operand that is (missing atoms) x (chunk pitch) past the end of the last stage, which must still be mapped.
+  pl->slack = !padding ? 0 : (pl->n_chunks > 1 ? (uint32_t)(atoms - pl->n_chunks % atoms) * max_chunk : max_chunk);
   const uint32_t fixed = (has_bias ? 128u * pl->kc * 2 : 0u) + pl->slack;  // ones tile + slack
   auto fits = [&](int nb) { return 2 * ((halo + 128u * nb * 2 + 1023u) & ~1023u) + fixed <= budget; };
   int best_nb = 0;

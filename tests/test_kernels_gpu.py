@@ -563,7 +563,7 @@ def test_umma_wgrad_odd_multiples_of_16():
     from denoise_gan_b200 import _lib as L
     lib, ctx, st = L.load(), L.ctx(), L.stream_ptr()
     g = torch.Generator().manual_seed(5)
-    N, H, W, cin, cout, k = 4, 32, 32, 208, 112, 3
+    N, H, W, cin, cout, k = 12, 32, 32, 208, 112, 3       # several tiles per CTA: the second pipeline stage is used too
     x0 = torch.randn((N, H, W, cin), generator=g).to(torch.bfloat16)
     dy0 = torch.randn((N, H, W, cout), generator=g).to(torch.bfloat16)
     xd, dyd = x0.cuda(), dy0.cuda()
