@@ -85,7 +85,8 @@ class Engine:
         self.written: set = set()      # param names whose grad slice was written this step
         self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
         self.use_umma_wgrad = self.use_umma
-        self.pad_rgb = True            # 3-channel-sided convs on the tensor cores through 16-channel zero padding
+        self.pad_rgb = True            # channel counts that are not multiples of 16 (RGB sides, the autoencoder's 44/56/76/100/67/...)
+                                       # run on the tensor cores through zero padding to the next multiple of 16
         self.launches = 0
         self.record = None             # dict name -> Var when a test wants per-layer activations
         self._cap: dict = {}
@@ -307,7 +308,7 @@ class Engine:
         kh, kw, cin, cout = w.shape
         assert cin == Cin, f"{w.name}: Cin {cin} != input {Cin}"
         pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, stride, padding)
-        if (self.use_umma and self.pad_rgb and min(cin, cout) < 16 and max(cin, cout) % 16 == 0 and kh * kw <= 16 and
+        if (self.use_umma and self.pad_rgb and (cin % 16 != 0 or cout % 16 != 0) and kh * kw <= 16 and
                 stride in (1, 2) and (stride == 1 or (H % 2 == 0 and W % 2 == 0))):
             r = self._conv2d_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype)
             if r is not None:

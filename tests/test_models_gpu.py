@@ -110,6 +110,70 @@ def test_fsrgan_step_bf16_runs_and_tracks_fp32():
         assert abs(a - float(b)) <= 2e-2 * max(1.0, abs(float(b))), (ours, [float(v) for v in ref])
 
 
+def test_autoencoder_step_bf16_tracks_fp64():
+    """bf16 tensor-core path of the autoencoder step (odd channel counts zero-padded to multiples of 16): generator
+    output and losses against the float64 oracle."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.autoencoder import Autoencoder
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.train_common import gan_step
+    model = Autoencoder(SimpleNamespace(crop_size=64, lr=1e-3, fp16=1, vgg=0, retrain=0, seed=0))
+    g0 = perturb(P.init_autoencoder_generator(0)); d0 = perturb(P.init_patch_discriminator(1))
+    model.gen_params.load(g0); model.disc_params.load(d0)
+    x, y = synthetic_pair(2, 64, 1, step=0)
+    r = gan_step(model, x.cuda(), y.cuda(), from_logits=False, disc_scale=1.0)
+    torch.cuda.synchronize()
+    assert any(k[0] == "padded" and v for k, v in model.engine._cap.items() if isinstance(k, tuple)), "padded tensor-core path unused"
+    g = {k: v.double().clone() for k, v in g0.items()}; d = {k: v.double().clone() for k, v in d0.items()}
+    out = {}
+    ref = OS.autoencoder_train_step(g, d, None, OT.KerasAdam(1e-3, decay_steps=100000), OT.KerasAdam(5e-3, decay_steps=100000),
+                                    x.double(), y.double(), out=out)
+    # 22 convolutions deep with no normalisation layer: bf16 storage noise (2^-9 per layer) adds up to ~1 % in the
+    # L2 norm and a few % on the worst pixel of the tanh output
+    assert relerr_l2(r["gen_output"].t.float(), out["gen_output"]) < 2e-2
+    assert relerr(r["gen_output"].t.float(), out["gen_output"]) < 8e-2
+    gg = model.gen_params.grads()
+    # Gradients reach the early layers through the 9-layer discriminator and ~20 generator layers in bf16; the
+    # discriminator at initialisation doubles a rounding perturbation per layer (test_srgan_gpu.py measures ~0.5 relative
+    # noise on what it sends back even in the bf16-emulating ORACLE), so deep layers are checked for direction (cosine)
+    # and the layers next to the loss for magnitude.  The same graph is checked to fp32 accuracy in
+    # test_autoencoder_step_fp32 and every kernel to 2e-2 in test_kernels_gpu.py.
+    def cosine(a, b):
+        a, b = a.double().flatten(), b.double().flatten()
+        return float((a @ b) / (a.norm() * b.norm()))
+    assert relerr_l2(gg["g/conv11/kernel"], out["gen_grads"]["g/conv11/kernel"]) < 6e-2
+    for name in ("g/conv11/kernel", "g/conv9/kernel", "g/conv7/kernel", "g/conv4/kernel", "g/conv2/kernel", "g/conv1/kernel"):
+        assert cosine(gg[name], out["gen_grads"][name]) > 0.95, (name, cosine(gg[name], out["gen_grads"][name]))
+    for n, b in zip(["disc_loss", "adv_loss", "content_loss", "mse_loss", "mae_loss"], ref):
+        assert abs(r[n].item() - float(b)) <= 2e-2 * max(1.0, abs(float(b))), (n, r[n].item(), float(b))
+
+
+def test_pix2pix_step_bf16_tracks_fp64():
+    """bf16 path of the pix2pix step at 256x256: losses against the float64 oracle (same dropout masks)."""
+    import numpy as np
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.pix2pix import Pix2Pix
+    from denoise_gan_b200.train_pix2pix import train_step
+    from oracle import ops_np as ON
+    model = Pix2Pix(SimpleNamespace(crop_size=256, lr=2e-4, fp16=1, vgg=0, retrain=0, seed=0, dropout_seed=7))
+    g0, d0 = P.init_pix2pix(0)
+    g0, d0 = perturb(g0), perturb(d0)
+    model.gen_params.load(g0); model.disc_params.load(d0)
+    x, y = synthetic_pair(1, 256, 1, step=0)
+    ours = [float(v) for v in train_step(model, x.cuda(), y.cuda())]
+
+    def masks(pass_id):
+        return [torch.from_numpy(ON.dropout_keep_mask(7, (pass_id * 3 + i) << 24, 2 ** (i + 1) * 2 ** (i + 1) * 512)).view(1, 2 ** (i + 1), 2 ** (i + 1), 512)
+                for i in range(3)]
+
+    g = {k: v.double().clone() for k, v in g0.items()}; d = {k: v.double().clone() for k, v in d0.items()}
+    ref = OS.pix2pix_train_step(g, d, None, OT.KerasAdam(2e-4, beta1=0.5), OT.KerasAdam(2e-4, beta1=0.5), x.double(), y.double(),
+                                masks(0), masks(1))
+    for n, a, b in zip(["total", "gan", "l1", "l2", "content", "disc", "var", "identity"], ours, ref):
+        assert abs(a - float(b)) <= 3e-2 * max(1.0, abs(float(b))), (n, a, float(b))
+
+
 def test_pix2pix_step_fp32():
     """train_pix2pix.py:33-71 at the reference's hard-coded 256x256 (batch 1): 8-down/8-up U-Net with
     Conv2DTranspose, dropout (shared counter-based mask), PatchGAN on concat(input, target), identity pass."""
