@@ -391,6 +391,11 @@ class Engine:
         Ho, Wo = H * stride, W * stride
         pt, _ = same_pads(Ho, kh, stride)
         pl, _ = same_pads(Wo, kw, stride)
+        if (self.use_umma and self.pad_rgb and cout % 16 != 0 and cin % 16 == 0 and x.t.dtype == torch.bfloat16 and kh * kw <= 16
+                and stride == 2):
+            r = self._conv2d_transpose_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype)
+            if r is not None:
+                return r
         seq = self._next()
         y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
         cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
@@ -429,6 +434,81 @@ class Engine:
                     check(self.lib.dg_umma_conv2d_fwd(self.ctx, C.byref(tdp), self._packed(w, 0).data_ptr(), None, C.byref(tdx), C.byref(lin), None, self.st))
                 else:
                     check(self.lib.dg_conv2d_fwd(self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
+            return [dx]
+
+        self._push([x], out, w.group, bwd)
+        return out
+
+    def _conv2d_transpose_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype):
+        """Conv2DTranspose whose OUTPUT channel count is not a multiple of 16 (pix2pix.py:169-173, 128 -> 3 + tanh) on the
+        tensor cores: the output side is zero-padded to 16 channels exactly as in _conv2d_padded (the transposed conv is the
+        input-gradient of a forward conv f: [N,Ho,Wo,cout] -> [N,H,W,cin], so the padded side is f's INPUT)."""
+        N, H, W, cin = x.shape
+        kh, kw, cout, _ = w.shape
+        cout_p = -(-cout // 16) * 16
+        ydt = out_dtype or self.act_dtype
+        lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
+        cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
+        dummy = x.t.data_ptr()
+        d_big = _lib.DgTensor(dummy, _lib.DG_BF16, N, Ho, Wo, cout_p, cout_p, 0)
+        d_small = _lib.DgTensor(dummy, _lib.DG_BF16, N, H, W, cin, cin, 0)
+        key = ("padded_T", N, H, W, cin, Ho, Wo, cout_p, kh, kw, stride, pt, pl)
+        ok = self._cap.get(key)
+        if ok is None:
+            ok = (bool(self.lib.dg_umma_conv2d_dgrad_supported(self.ctx, C.byref(d_small), C.byref(d_big), C.byref(lin))) and
+                  bool(self.lib.dg_umma_conv2d_fwd_supported(self.ctx, C.byref(d_big), C.byref(d_small), C.byref(lin))) and
+                  self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(d_big), C.byref(d_small), C.byref(lin)) > 0)
+            self._cap[key] = ok
+        if not ok:
+            return None
+        seq = self._next()
+        w.pack_pad = (cout_p, cin)          # HWIO of f: I = cout of the transposed conv (padded), O = cin
+        y = self.buf((seq, "y"), (N, Ho, Wo, cout), ydt)
+        yp = self.buf((seq, "ypad"), (N, Ho, Wo, cout_p), ydt)
+        bias = None
+        if b is not None:
+            bp = self._zeros((seq, "bias_p"), (cout_p,), torch.float32)
+            bp[:cout].copy_(b.data)
+            bias = bp.data_ptr()
+        tx, typ = tensor(x.t), tensor(yp)
+        flops = 2.0 * N * H * W * kh * kw * cin * cout_p
+        pk1 = self._packed(w, 1)
+        self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
+            self.ctx, C.byref(tx), pk1.data_ptr(), bias, C.byref(typ), C.byref(cp), self.st)))
+        tv, ty = tensor(yp, c=cout), tensor(y)
+        check(self.lib.dg_copy(self.ctx, C.byref(tv), C.byref(ty), 0, self.st))
+        out = Var(y, self._deps([x], w.group), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            dpre = gy
+            if ACT[act]:
+                dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
+                tg, tyy, td = tensor(gy), tensor(y), tensor(dpre)
+                check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
+            dpp = self.buf((seq, "dpad", tag), (N, Ho, Wo, cout_p), torch.bfloat16)
+            ts, tdp = tensor(dpre), tensor(dpp)
+            check(self.lib.dg_pad_channels(self.ctx, C.byref(ts), C.byref(tdp), self.st))
+            if need_p:
+                acc = self._acc_flag(w)
+                nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tdp), C.byref(tx), C.byref(lin))
+                ws = self.workspace(nbytes)
+                dwp = self.buf((seq, "dw_pad", tag), (kh * kw * cout_p * cin,), torch.float32)
+                self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
+                    self.ctx, C.byref(tdp), C.byref(tx), dwp.data_ptr(), None, C.byref(lin), 0, ws.data_ptr(), nbytes, self.st)))
+                check(self.lib.dg_unpad_weight_grad(self.ctx, dwp.data_ptr(), None, w.grad.data_ptr(), None, kh, kw, cout, cin,
+                                                    cout_p, cin, acc, self.st))
+                if b is not None:
+                    tdp2 = tensor(dpre)
+                    nb2 = self.lib.dg_bn_workspace_bytes(C.byref(tdp2))
+                    ws2 = self.workspace(nb2)
+                    check(self.lib.dg_bias_grad(self.ctx, C.byref(tdp2), b.grad.data_ptr(), self._acc_flag(b), ws2.data_ptr(), nb2, self.st))
+            dx = None
+            if need_in[0]:
+                dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                tdx = tensor(dx)
+                pk0 = self._packed(w, 0)
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+                    self.ctx, C.byref(tdp), pk0.data_ptr(), None, C.byref(tdx), C.byref(lin), None, self.st)))
             return [dx]
 
         self._push([x], out, w.group, bwd)

@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--fp16", type=int, default=1)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--crop", type=int, default=384)
-ap.add_argument("--model", default="srgan", choices=["srgan", "fsrgan", "autoencoder"])
+ap.add_argument("--model", default="srgan", choices=["srgan", "fsrgan", "autoencoder", "pix2pix"])
 args = ap.parse_args()
 
 from denoise_gan_b200.dataloader import synthetic_pair  # noqa: E402
@@ -30,6 +30,10 @@ elif args.model == "fsrgan":
     from denoise_gan_b200.fsrgan import FastSRGAN as M
     from denoise_gan_b200.train_fsrgan import train_step
     scale = 4
+elif args.model == "pix2pix":
+    from denoise_gan_b200.pix2pix import Pix2Pix as M
+    from denoise_gan_b200.train_pix2pix import train_step
+    scale = 1
 else:
     from denoise_gan_b200.autoencoder import Autoencoder as M
     from denoise_gan_b200.train_autoencoder import train_step
