@@ -54,6 +54,9 @@ struct UmmaConvParams {
   uint32_t tap_ms16[MAX_TAPS];    // descriptor step between the m sub-tiles of the tap's source
   uint32_t stage_bytes, stage_tx, w_stage_off, w_block_bytes, w_res_bytes, w_res_tx;
   int n_stages, resident, cout_total;
+  int split;        // 1: one SOURCE per pipeline stage (halo box + the weights of that source's taps): big stride-2 layers
+  int src_tap0[MAX_SRC], src_ntaps[MAX_SRC];   // taps are sorted by source
+  uint32_t src_tx[MAX_SRC];
   int nbuf_shift;   // log2 of the TMEM accumulator buffers: 2 (four buffers, TWO issuing warps on alternate tiles) or 1
   void* out;
   long out_sn, out_sh, out_sw;
@@ -162,13 +165,14 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
 // whole stage is one straight line of tcgen05.mma (the issue thread must stay well under the ~48 cycles a
 // 128 x 64 x 16 MMA occupies the tensor pipe: probes/umma_probe.cu "t2_*").
 template <int MT, int NBK, int NT>
-__device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int n_taps, uint32_t sa16, uint32_t b_lo, uint32_t b_step,
+__device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int t0, int n_taps, uint32_t sa16, uint32_t b_lo, uint32_t b_step,
                                             uint64_t b_hi, uint32_t acc0, uint32_t nb, uint32_t idesc, bool not_first_chunk) {
   const int nt = NT > 0 ? NT : n_taps;
 #pragma unroll
   for (int t = 0; t < nt; ++t) {
-    const uint64_t ad = P.tap_adesc[t] + (uint64_t)sa16;
-    const uint32_t ms = P.tap_ms16[t];
+    const int tt = NT > 0 ? t : t0 + t;      // (t0 != 0 only in split-source mode, which uses the generic instance)
+    const uint64_t ad = P.tap_adesc[tt] + (uint64_t)sa16;
+    const uint32_t ms = P.tap_ms16[tt];
     const uint32_t acc_rest = (not_first_chunk || t != 0) ? 1u : 0u;
 #pragma unroll
     for (int k16 = 0; k16 < NBK; ++k16) {
@@ -249,18 +253,29 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
         const int h0 = th * 16 * P.mt, w0 = tw * 8;
         const int pit = it;
         const int wi = it % n_iss;
-        const uint32_t j0 = (uint32_t)(it / n_iss) * (uint32_t)P.n_chunks;
+        const int n_steps = P.split ? P.n_chunks * P.n_src : P.n_chunks;
+        const uint32_t j0 = (uint32_t)(it / n_iss) * (uint32_t)n_steps;
         dbg_mark(P, 0, pit, 0);
-        for (int kc = 0; kc < P.n_chunks; ++kc) {
-          const uint32_t j = j0 + (uint32_t)kc;
+        for (int step = 0; step < n_steps; ++step) {
+          const int kc = P.split ? step / P.n_src : step;
+          const int so = P.split ? step - kc * P.n_src : 0;
+          const uint32_t j = j0 + (uint32_t)step;
           const int stage = (int)(j % (uint32_t)half) * n_iss + wi;
           const uint32_t phase = (j / (uint32_t)half) & 1u;
           const uint32_t full = smem_u32(&bar_a_full[stage]);
           mbar_wait(smem_u32(&bar_a_empty[stage]), phase ^ 1u);
-          if (kc == 0) dbg_mark(P, 0, pit, 1);
+          if (step == 0) dbg_mark(P, 0, pit, 1);
           if ((P.dbg_flags & 4) && pit >= P.n_stages) { mbar_arrive(full); continue; }
-          mbar_expect_tx(full, P.stage_tx);
           const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
+          if (P.split) {
+            mbar_expect_tx(full, P.src_tx[so]);
+            tma_load_4d(sa, &P.src[so], full, kc * P.kc, w0 + P.src_w0[so], h0 + P.src_h0[so], n);
+            for (int t = 0; t < P.src_ntaps[so]; ++t)
+              tma_load_2d(sa + P.w_stage_off + (uint32_t)t * P.w_block_bytes, &P.wmap, full, 0,
+                          (P.tap_w[P.src_tap0[so] + t] * P.n_chunks + kc) * P.cout_total + nb0);
+            continue;
+          }
+          mbar_expect_tx(full, P.stage_tx);
           for (int s = 0; s < P.n_src; ++s)
             tma_load_4d(sa + P.src_off[s], &P.src[s], full, kc * P.kc, w0 + P.src_w0[s], h0 + P.src_h0[s], n);
           if (!P.resident)
@@ -302,26 +317,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
         const int b = it & ((1 << P.nbuf_shift) - 1);
         const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
         const uint32_t half = (uint32_t)(n_stages / n_issuers);
-        const uint32_t j0 = (uint32_t)(it / n_issuers) * (uint32_t)n_chunks;   // this issuer's slot sequence number
+        const int n_steps = P.split ? n_chunks * P.n_src : n_chunks;
+        const uint32_t j0 = (uint32_t)(it / n_issuers) * (uint32_t)n_steps;   // this issuer's slot sequence number
         if (lane == 0 && me == 0) dbg_mark(P, 1, it, 0);
         mbar_wait_warp<0>(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
         tc_fence_after();
         if (lane == 0 && me == 0) dbg_mark(P, 1, it, 1);
         const uint32_t acc0 = tmem + (uint32_t)(b * mt) * nb;
-        for (int kc = 0; kc < n_chunks; ++kc) {
-          const uint32_t j = j0 + (uint32_t)kc;
+        for (int step = 0; step < n_steps; ++step) {
+          const int kc = P.split ? step / P.n_src : step;
+          const int so = P.split ? step - kc * P.n_src : 0;
+          const uint32_t j = j0 + (uint32_t)step;
           const int stage = (int)(j % half) * n_issuers + me;
           const uint32_t phase = (j / half) & 1u;
           mbar_wait_warp<0>(smem_u32(&bar_a_full[stage]), phase);
           tc_fence_after();
-          if (kc == 0 && lane == 0 && me == 0) dbg_mark(P, 1, it, 2);
+          if (step == 0 && lane == 0 && me == 0) dbg_mark(P, 1, it, 2);
           const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;
           if (elect_one()) {
             const uint32_t b_lo = resident ? wres16 + (uint32_t)kc * wblk16 : sa16 + wstage16;
             const uint32_t b_step = resident ? (uint32_t)n_chunks * wblk16 : wblk16;
-#define DG_ISSUE(MT_, NBK_, NT_) issue_stage<MT_, NBK_, NT_>(P, n_taps, sa16, b_lo, b_step, b_hi, acc0, nb, idesc, kc != 0)
+            const int t0 = P.split ? P.src_tap0[so] : 0, ntp = P.split ? P.src_ntaps[so] : n_taps;
+#define DG_ISSUE(MT_, NBK_, NT_) issue_stage<MT_, NBK_, NT_>(P, t0, ntp, sa16, b_lo, b_step, b_hi, acc0, nb, idesc, step != 0)
 #define DG_ISSUE_NT(MT_, NBK_) \
-  { if (n_taps == 9) DG_ISSUE(MT_, NBK_, 9); else if (n_taps == 4) DG_ISSUE(MT_, NBK_, 4); else if (n_taps == 1) DG_ISSUE(MT_, NBK_, 1); else DG_ISSUE(MT_, NBK_, 0); }
+  { if (P.split) DG_ISSUE(MT_, NBK_, 0); else if (n_taps == 9) DG_ISSUE(MT_, NBK_, 9); else if (n_taps == 4) DG_ISSUE(MT_, NBK_, 4); else if (n_taps == 1) DG_ISSUE(MT_, NBK_, 1); else DG_ISSUE(MT_, NBK_, 0); }
             if (mt == 1) {
               if (nbk == 4) DG_ISSUE_NT(1, 4) else if (nbk == 2) DG_ISSUE_NT(1, 2) else DG_ISSUE_NT(1, 1)
             } else {
@@ -330,7 +349,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
 #undef DG_ISSUE_NT
 #undef DG_ISSUE
             umma_commit(smem_u32(&bar_a_empty[stage]));
-            if (kc == n_chunks - 1) umma_commit(smem_u32(&bar_acc_full[b]));
+            if (step == n_steps - 1) umma_commit(smem_u32(&bar_acc_full[b]));
           }
           __syncwarp();
         }
@@ -449,7 +468,7 @@ struct TapSpec {
 
 // Builds the launch description and runs the kernel.
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
-                const TapSpec* taps, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
+                const TapSpec* taps_in, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
@@ -459,6 +478,17 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
              "%s: output view not 16-byte aligned", name);
   DG_REQUIRE(n_src >= 1 && n_src <= MAX_SRC && n_taps >= 1 && n_taps <= MAX_TAPS, "%s: too many sources/taps", name);
   DG_REQUIRE(act != DG_ACT_PRELU, "%s: PReLU is not a conv epilogue", name);
+
+  // taps grouped by source (stable), so that a stage can carry the taps of one source only (split mode)
+  TapSpec taps_sorted[MAX_TAPS];
+  {
+    int k = 0;
+    for (int s = 0; s < n_src; ++s)
+      for (int t = 0; t < n_taps; ++t)
+        if (taps_in[t].src == s) taps_sorted[k++] = taps_in[t];
+    DG_REQUIRE(k == n_taps, "%s: tap with an invalid source", name);
+  }
+  const TapSpec* taps = taps_sorted;
 
   UmmaConvParams P;
   memset(&P, 0, sizeof(P));
@@ -516,10 +546,34 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
         uint32_t need = (res ? ((wres + 1023u) & ~1023u) : 0) + min_stages * ((stage + 1023u) & ~1023u);
         if (need <= budget) { best_nb = nb; best_mt = mt; best_res = res; }
       }
+  // Fallback for many-tap, many-channel layers (pix2pix 4x4 stride 2 with >= 128 channels): one SOURCE per pipeline stage
+  // (its halo box + the weights of its taps), so a stage is 1/n_src of the halo and of the streamed weights.
+  int split = 0;
+  int src_ntaps[MAX_SRC] = {0, 0, 0, 0}, max_ntaps = 0;
+  for (int t = 0; t < n_taps; ++t) ++src_ntaps[taps[t].src];
+  for (int s = 0; s < n_src; ++s) max_ntaps = src_ntaps[s] > max_ntaps ? src_ntaps[s] : max_ntaps;
+  auto max_halo = [&](int mt) {
+    uint32_t m = 0;
+    for (int s = 0; s < n_src; ++s) {
+      uint32_t hb = (uint32_t)(16 * mt + dh_max[s] - dh_min[s]) * (uint32_t)(8 + dw_max[s] - dw_min[s]) * kc * 2;
+      hb = (hb + 1023u) & ~1023u;
+      m = hb > m ? hb : m;
+    }
+    return m;
+  };
+  if (!best_nb && n_src > 1) {
+    for (int min_stages = 3; min_stages >= 2 && !best_nb; --min_stages)
+      for (int nb = cout > 256 ? 256 : cout; nb >= 16 && !best_nb; nb -= 16)
+        for (int mt = 2; mt >= 1 && !best_nb; --mt) {
+          if (cout % nb != 0 || 2 * mt * nb > 512) continue;
+          uint32_t stage = max_halo(mt) + (uint32_t)max_ntaps * nb * kc * 2;
+          if ((uint32_t)min_stages * ((stage + 1023u) & ~1023u) <= budget) { best_nb = nb; best_mt = mt; best_res = 0; split = 1; }
+        }
+  }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d taps=%d)", name, in->c, cout, n_taps);
   if (dry) return 0;   // capability query: a tile configuration exists
   const int nb = best_nb, mt = best_mt;
-  P.nb = nb; P.mt = mt; P.resident = best_res;
+  P.nb = nb; P.mt = mt; P.resident = best_res; P.split = split;
 
   P.w_block_bytes = (uint32_t)nb * kc * 2;
   P.w_res_tx = best_res ? (uint32_t)n_taps * n_chunks * P.w_block_bytes : 0;
@@ -543,7 +597,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     char* p = (char*)in->ptr + ((size_t)in->coff + ((size_t)L.h_first * in->w + L.w_first) * in->cpitch) * 2;
     if (encode_map(ctx, &P.src[s], p, 4, dims, strides, box, kc)) return 1;
     P.src_h0[s] = dh_min[s]; P.src_w0[s] = dw_min[s];
-    P.src_off[s] = off;
+    P.src_off[s] = split ? 0u : off;
     P.a_sbo[s] = (uint32_t)WW * kc * 2;
     P.mt_stride[s] = (uint32_t)16 * WW * kc * 2;
     uint32_t hb = (uint32_t)HH * WW * kc * 2;
@@ -554,6 +608,17 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   if (!best_res) { off += (uint32_t)n_taps * P.w_block_bytes; tx += (uint32_t)n_taps * P.w_block_bytes; }
   P.stage_bytes = (off + 1023u) & ~1023u;
   P.stage_tx = tx;
+  if (split) {
+    P.w_stage_off = max_halo(mt);
+    P.stage_bytes = (P.w_stage_off + (uint32_t)max_ntaps * P.w_block_bytes + 1023u) & ~1023u;
+    int t0 = 0;
+    for (int s = 0; s < n_src; ++s) {
+      const uint32_t hb = (uint32_t)(16 * mt + dh_max[s] - dh_min[s]) * (uint32_t)(8 + dw_max[s] - dw_min[s]) * kc * 2;
+      P.src_tap0[s] = t0; P.src_ntaps[s] = src_ntaps[s];
+      P.src_tx[s] = hb + (uint32_t)src_ntaps[s] * P.w_block_bytes;
+      t0 += src_ntaps[s];
+    }
+  }
   int n_stages = (int)((budget - P.w_res_bytes) / P.stage_bytes);
   if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
   DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);

@@ -329,6 +329,7 @@ struct Plan {
   Lat lat[MAX_SRC];
   int n_taps, n_src;
   int kc, kco, n_chunks, nb, gpc, zblocks, yblocks, splits, has_bias;
+  int src_split;   // 1: one launch per source (big stride-2 layers whose four halo boxes do not fit one stage)
   uint32_t slack;
 };
 
@@ -363,21 +364,22 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   const int atoms = 128 / pl->kc;
   const int chunks_per_launch = pl->n_chunks < atoms ? pl->n_chunks : atoms;
   // halo bytes of one launch stage (all sources, the launch's chunks)
-  uint32_t halo = 0, max_chunk = 0;
+  uint32_t halo_all = 0, halo_max = 0, max_chunk = 0;
+  int taps_of[MAX_SRC] = {0, 0, 0, 0}, max_taps_src = 0;
   for (int s = 0; s < pl->n_src; ++s) {
     int dh0 = 1 << 30, dh1 = -(1 << 30), dw0 = 1 << 30, dw1 = -(1 << 30);
     for (int t = 0; t < pl->n_taps; ++t)
       if (pl->taps[t].src == s) {
+        ++taps_of[s];
         dh0 = pl->taps[t].dh < dh0 ? pl->taps[t].dh : dh0; dh1 = pl->taps[t].dh > dh1 ? pl->taps[t].dh : dh1;
         dw0 = pl->taps[t].dw < dw0 ? pl->taps[t].dw : dw0; dw1 = pl->taps[t].dw > dw1 ? pl->taps[t].dw : dw1;
       }
+    max_taps_src = taps_of[s] > max_taps_src ? taps_of[s] : max_taps_src;
     uint32_t cb = ((uint32_t)(16 + dh1 - dh0) * (8 + dw1 - dw0) * pl->kc * 2 + 1023u) & ~1023u;
-    halo += cb * chunks_per_launch;
+    halo_all += cb * chunks_per_launch;
+    halo_max = cb * chunks_per_launch > halo_max ? cb * chunks_per_launch : halo_max;
     max_chunk = cb > max_chunk ? cb : max_chunk;
   }
-  // worst-case number of accumulator groups of one launch
-  int n_groups = pl->n_taps;  // one group per tap when a launch spans several chunks
-  if (pl->n_chunks == 1) n_groups = (pl->n_taps + 1) / 2 + pl->n_src;  // upper bound for tap stacking
   const int cout = dy->c;
   const uint32_t budget = SMEM_LIMIT - 4096;
   // padding atoms (M rows beyond the valid taps/chunks) read shared memory past their group: keep a slack region
@@ -394,16 +396,24 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   // M=128 operand that is (missing atoms) x (chunk pitch) past the end of the last stage, which must still be mapped.
   pl->slack = !padding ? 0 : (pl->n_chunks > 1 ? (uint32_t)(atoms - pl->n_chunks % atoms) * max_chunk : max_chunk);
   const uint32_t fixed = (has_bias ? 128u * pl->kc * 2 : 0u) + pl->slack;  // ones tile + slack
-  auto fits = [&](int nb) { return 2 * ((halo + 128u * nb * 2 + 1023u) & ~1023u) + fixed <= budget; };
-  int best_nb = 0;
-  for (int nb = cout > 256 ? 256 : cout; nb >= 16; nb -= 16) {
-    if (cout % nb != 0 || nb % pl->kco != 0 || !fits(nb)) continue;
-    int gpc = 512 / nb - (has_bias ? 1 : 0);
-    if (gpc >= n_groups) { best_nb = nb; break; }
-  }
-  if (!best_nb) {
-    for (int nb = cout > 64 ? 64 : cout; nb >= 16; nb -= 16)
-      if (cout % nb == 0 && nb % pl->kco == 0 && fits(nb)) { best_nb = nb; break; }
+  int best_nb = 0, n_groups = 0;
+  for (int split = 0; split < 2 && !best_nb; ++split) {
+    if (split && pl->n_src == 1) break;
+    const uint32_t halo = split ? halo_max : halo_all;
+    // worst-case number of accumulator groups of one launch
+    n_groups = split ? max_taps_src : pl->n_taps;  // one group per tap when a launch spans several chunks
+    if (pl->n_chunks == 1) n_groups = split ? (max_taps_src + 1) / 2 + 1 : (pl->n_taps + 1) / 2 + pl->n_src;  // upper bound for tap stacking
+    auto fits = [&](int nb) { return 2 * ((halo + 128u * nb * 2 + 1023u) & ~1023u) + fixed <= budget; };
+    for (int nb = cout > 256 ? 256 : cout; nb >= 16; nb -= 16) {
+      if (cout % nb != 0 || nb % pl->kco != 0 || !fits(nb)) continue;
+      int gpc = 512 / nb - (has_bias ? 1 : 0);
+      if (gpc >= n_groups) { best_nb = nb; break; }
+    }
+    if (!best_nb) {
+      for (int nb = cout > 64 ? 64 : cout; nb >= 16; nb -= 16)
+        if (cout % nb == 0 && nb % pl->kco == 0 && fits(nb)) { best_nb = nb; break; }
+    }
+    pl->src_split = split;
   }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d)", name, x->c, cout);
   pl->nb = best_nb;
@@ -475,19 +485,26 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
 
   const int atoms_full = 128 / kc;
   const int chunks_per_launch = pl.n_chunks < atoms_full ? pl.n_chunks : atoms_full;
-  for (int chunk0 = 0; chunk0 < pl.n_chunks; chunk0 += chunks_per_launch) {
+  bool first_launch = true;
+  for (int chunk0 = 0; chunk0 < pl.n_chunks; chunk0 += chunks_per_launch)
+  for (int ssel = pl.src_split ? 0 : -1; ssel < (pl.src_split ? pl.n_src : 0); ++ssel) {   // -1: all sources in one launch
     const int chunks = (pl.n_chunks - chunk0) < chunks_per_launch ? (pl.n_chunks - chunk0) : chunks_per_launch;
     WgradParams P;
     memset(&P, 0, sizeof(P));
-    P.n_src = pl.n_src; P.kc = kc; P.kco = kco; P.nb = pl.nb; P.chunks = chunks; P.chunk0 = chunk0;
+    P.n_src = ssel < 0 ? pl.n_src : 1; P.kc = kc; P.kco = kco; P.nb = pl.nb; P.chunks = chunks; P.chunk0 = chunk0;
     P.tiles_h = (dy->h + 15) / 16; P.tiles_w = (dy->w + 7) / 8; P.n_img = dy->n;
     P.cout_total = cout; P.part = (float*)workspace; P.part_stride = part_stride; P.bias_off = n_dw;
-    P.has_bias = (dbias != nullptr && chunk0 == 0) ? 1 : 0;
+    P.has_bias = (dbias != nullptr && first_launch) ? 1 : 0;
+    first_launch = false;
     P.a_layout = layout_for(kc); P.b_layout = layout_for(kco);
     P.idesc = make_idesc_bf16(128, pl.nb, 1, 1);
     uint32_t off = 0, tx = 0;
-    int WWs[MAX_SRC];
+    int WWs[MAX_SRC], slot_of[MAX_SRC] = {-1, -1, -1, -1};
+    int n_slots = 0;
     for (int s = 0; s < pl.n_src; ++s) {
+      if (ssel >= 0 && s != ssel) continue;
+      const int si = n_slots++;      // slot of this source in the launch's parameter arrays
+      slot_of[s] = si;
       const Lat& L = pl.lat[s];
       const int HH = 16 + dh_max[s] - dh_min[s], WW = 8 + dw_max[s] - dw_min[s];
       WWs[s] = WW;
@@ -497,14 +514,14 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
                              (uint64_t)x->cpitch * 2 * x->w * x->h};
       uint32_t box[4] = {(uint32_t)kc, (uint32_t)WW, (uint32_t)HH, 1};
       char* ptr = (char*)x->ptr + ((size_t)x->coff + ((size_t)L.h_first * x->w + L.w_first) * x->cpitch) * 2;
-      if (encode4(ctx, &P.src[s], ptr, dims, strides, box, kc)) return 1;
-      P.src_h0[s] = dh_min[s]; P.src_w0[s] = dw_min[s];
+      if (encode4(ctx, &P.src[si], ptr, dims, strides, box, kc)) return 1;
+      P.src_h0[si] = dh_min[s]; P.src_w0[si] = dw_min[s];
       uint32_t hb = (uint32_t)HH * WW * kc * 2;
-      P.chunk_bytes[s] = (hb + 1023u) & ~1023u;
-      P.src_off[s] = off;
-      P.a_sbo[s] = (uint32_t)WW * kc * 2;
-      P.a_kstep[s] = 2u * WW * kc * 2;
-      off += P.chunk_bytes[s] * chunks;
+      P.chunk_bytes[si] = (hb + 1023u) & ~1023u;
+      P.src_off[si] = off;
+      P.a_sbo[si] = (uint32_t)WW * kc * 2;
+      P.a_kstep[si] = 2u * WW * kc * 2;
+      off += P.chunk_bytes[si] * chunks;
       tx += hb * chunks;
     }
     {  // dy tile: dense 16 x 8 pixels, nb/kco channel atoms
@@ -526,10 +543,11 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
       for (int t = 0; t < pl.n_taps; ++t) {
         const Tap& T = pl.taps[t];
         int s = T.src;
+        if (slot_of[s] < 0) continue;
         DG_REQUIRE(ng < MAX_GROUPS, "%s: too many groups", name);
-        P.g_src[ng] = s;
-        P.g_off[ng] = P.src_off[s] + (uint32_t)((T.dh - dh_min[s]) * WWs[s] + (T.dw - dw_min[s])) * kc * 2;
-        P.g_lbo[ng] = P.chunk_bytes[s];
+        P.g_src[ng] = slot_of[s];
+        P.g_off[ng] = P.src_off[slot_of[s]] + (uint32_t)((T.dh - dh_min[s]) * WWs[s] + (T.dw - dw_min[s])) * kc * 2;
+        P.g_lbo[ng] = P.chunk_bytes[slot_of[s]];
         for (int a = 0; a < MAX_ATOMS; ++a) P.g_dst[ng][a] = a < chunks ? T.widx * cin + (chunk0 + a) * kc : -1;
         ++ng;
       }
@@ -540,10 +558,11 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
         if (done[t]) continue;
         const Tap& T = pl.taps[t];
         const int s = T.src;
+        if (slot_of[s] < 0) continue;
         auto row = [&](const Tap& U) { return (U.dh - dh_min[s]) * WWs[s] + (U.dw - dw_min[s]); };
         DG_REQUIRE(ng < MAX_GROUPS, "%s: too many groups", name);
-        P.g_src[ng] = s;
-        P.g_off[ng] = P.src_off[s] + (uint32_t)row(T) * kc * 2;
+        P.g_src[ng] = slot_of[s];
+        P.g_off[ng] = P.src_off[slot_of[s]] + (uint32_t)row(T) * kc * 2;
         for (int a = 0; a < MAX_ATOMS; ++a) P.g_dst[ng][a] = -1;
         P.g_dst[ng][0] = T.widx * cin;
         done[t] = true;

@@ -619,3 +619,49 @@ def test_umma_conv_many_tiles_per_cta(N, H, W, cin, cout, k, kind):
         out = dx
     torch.cuda.synchronize()
     assert relerr(out.float().cpu(), ref) < 2e-2
+
+
+@pytest.mark.parametrize("N,H,cin,cout", [(4, 64, 128, 256), (2, 32, 256, 512), (8, 16, 512, 512), (3, 2, 512, 512)])
+def test_umma_conv_k4s2_split_source_stages(N, H, cin, cout):
+    """pix2pix.py:110-123 downsample convs (4x4, stride 2, SAME) with >= 128 channels: the forward kernel stages one
+    parity source (halo + its four taps' weights) per pipeline slot."""
+    from denoise_gan_b200 import _lib as L
+    lib, ctx, st = L.load(), L.ctx(), L.stream_ptr()
+    g = torch.Generator().manual_seed(H * 7 + cin)
+    x0 = torch.randn((N, H, H, cin), generator=g).to(torch.bfloat16)
+    w0 = torch.randn((4, 4, cin, cout), generator=g) * 0.03
+    xd, wd = x0.cuda(), w0.cuda()
+    pk = torch.empty(w0.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), 4, 4, cin, cout, 0, st))
+    cp = L.DgConvParams(4, 4, 2, 1, 1, 0, 0.0)
+    y = torch.empty((N, H // 2, H // 2, cout), dtype=torch.bfloat16, device="cuda")
+    tx, ty = L.tensor(xd), L.tensor(y)
+    assert lib.dg_umma_conv2d_fwd_supported(ctx, C.byref(tx), C.byref(ty), C.byref(cp))
+    L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
+    torch.cuda.synchronize()
+    ref = OT.conv2d(x0.float(), w0.to(torch.bfloat16).float(), stride=2)
+    assert relerr(y.float().cpu(), ref) < 2e-2
+
+
+@pytest.mark.parametrize("N,H,cin,cout", [(4, 64, 128, 256), (2, 32, 256, 512), (8, 16, 512, 512), (3, 4, 512, 512)])
+def test_umma_wgrad_k4s2_one_launch_per_source(N, H, cin, cout):
+    """Weight gradient of the pix2pix 4x4 stride-2 convs with >= 128 channels: the four parity sources are processed by
+    separate launches (their halo boxes do not fit one pipeline stage together)."""
+    from denoise_gan_b200 import _lib as L
+    lib, ctx, st = L.load(), L.ctx(), L.stream_ptr()
+    g = torch.Generator().manual_seed(H * 11 + cin)
+    x0 = torch.randn((N, H, H, cin), generator=g).to(torch.bfloat16)
+    dy0 = torch.randn((N, H // 2, H // 2, cout), generator=g).to(torch.bfloat16)
+    xd, dyd = x0.cuda(), dy0.cuda()
+    cp = L.DgConvParams(4, 4, 2, 1, 1, 0, 0.0)
+    tx, tdy = L.tensor(xd), L.tensor(dyd)
+    nbytes = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(cp))
+    assert nbytes > 0, lib.dg_last_error().decode()
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dw = torch.empty((4, 4, cin, cout), device="cuda"); db = torch.empty(cout, device="cuda")
+    L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(tdy), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, ws.data_ptr(), nbytes, st))
+    torch.cuda.synchronize()
+    w = torch.zeros((4, 4, cin, cout), dtype=torch.float32, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    OT.conv2d(x0.float(), w, b, stride=2).backward(dy0.float())
+    assert relerr(dw.cpu(), w.grad) < 2e-2 and relerr(db.cpu(), b.grad) < 2e-2
