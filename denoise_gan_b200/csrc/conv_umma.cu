@@ -124,7 +124,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
     const int th = t2 % P.tiles_h;
     const int n = t2 / P.tiles_h;
     if (q == 0 && lane == 0) dbg_mark(P, 2, it, 0);
-    mbar_wait_warp<0>(smem_u32(&bar_acc_full[b]), acc_phase);
+    mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
     tc_fence_after();
     if (q == 0 && lane == 0) dbg_mark(P, 2, it, 1);
     for (int m = 0; m < P.mt; ++m) {
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       const uint32_t stage16 = P.stage_bytes >> 4, sbase16 = stage_base >> 4;
       const bool resident = P.resident != 0;
       if (resident) {
-        mbar_wait_warp<0>(smem_u32(&bar_w), 0);
+        mbar_wait(smem_u32(&bar_w), 0);
         tc_fence_after();
       }
       // With four accumulator buffers two warps issue alternate tiles, so the tensor pipe always has the other
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
         const int n_steps = P.split ? n_chunks * P.n_src : n_chunks;
         const uint32_t j0 = (uint32_t)(it / n_issuers) * (uint32_t)n_steps;   // this issuer's slot sequence number
         if (lane == 0 && me == 0) dbg_mark(P, 1, it, 0);
-        mbar_wait_warp<0>(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
+        mbar_wait(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
         tc_fence_after();
         if (lane == 0 && me == 0) dbg_mark(P, 1, it, 1);
         const uint32_t acc0 = tmem + (uint32_t)(b * mt) * nb;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
           const uint32_t j = j0 + (uint32_t)step;
           const int stage = (int)(j % half) * n_issuers + me;
           const uint32_t phase = (j / half) & 1u;
-          mbar_wait_warp<0>(smem_u32(&bar_a_full[stage]), phase);
+          mbar_wait(smem_u32(&bar_a_full[stage]), phase);
           tc_fence_after();
           if (step == 0 && lane == 0 && me == 0) dbg_mark(P, 1, it, 2);
           const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;

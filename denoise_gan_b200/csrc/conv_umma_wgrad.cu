@@ -18,6 +18,7 @@
 // Reference: tape.gradient(..., trainable_variables) train_srgan.py:111-112 for every Conv2D /
 // Conv2DTranspose kernel and bias.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dg_common.cuh"
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         if (lane == 0) wdbg(P, 1, it, 0);
-        mbar_wait_warp<0>(smem_u32(&bar_full[stage]), phase);
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         if (lane == 0) wdbg(P, 1, it, 1);
         const uint32_t sa16 = base16 + (uint32_t)stage * stage16;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
     const int q = warp & 3;
     const int m = q * 32 + lane;
     if (q == 0 && lane == 0) wdbg(P, 2, 0, 0);
-    mbar_wait_warp<256>(smem_u32(&bar_done), 0);
+    mbar_wait(smem_u32(&bar_done), 0);
     tc_fence_after();
     if (q == 0 && lane == 0) wdbg(P, 2, 0, 1);
     float* part = P.part + (long)blockIdx.x * P.part_stride;
@@ -596,7 +597,8 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     P.ones_off = (uint32_t)n_stages * P.stage_bytes;
     {
       int cw = pl.nb % 64 == 0 ? 64 : (pl.nb % 32 == 0 ? 32 : 16);   // must divide the N block (e.g. 112 = 7 x 16)
-      P.dump_cw = (size_t)4 * 32 * (cw + 4) * sizeof(float) <= (size_t)n_stages * P.stage_bytes ? cw : 0;
+      static const char* dbg_direct = getenv("DG_DEBUG_WGRAD_DIRECT");   // experiments only
+      P.dump_cw = (!dbg_direct && (size_t)4 * 32 * (cw + 4) * sizeof(float) <= (size_t)n_stages * P.stage_bytes) ? cw : 0;
     }
     const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;
     dim3 grid(pl.splits, pl.yblocks, zblocks);

@@ -55,18 +55,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// Whole-warp wait with ONE polling lane (32 lanes spinning on mbarrier.try_wait are 32x the shared-memory traffic of
-// one, on the memory the tensor pipe fetches its operands from).  SLEEP_NS > 0 adds a back-off for waits that are off
-// the critical path.
-template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) {
-    while (!mbar_try_wait(bar, parity)) {
-      if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
-    }
-  }
-  __syncwarp();
-}
+// (A variant that polled with one lane per warp and __syncwarp()ed the rest was measured SLOWER: +3 % on the whole SRGAN
+// step, the wake-up of the issuing warp is on the critical path of every 128-pixel tile.)
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
