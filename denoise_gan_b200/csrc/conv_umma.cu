@@ -720,7 +720,8 @@ extern "C" int dg_umma_pack_weights_padded(dg_ctx* ctx, const float* w, void* pa
 
 extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, int n_entries, void* stream) {
   DG_REQUIRE(table_dev && n_entries > 0, "dg_umma_pack_weights_batch: empty table");
-  dim3 grid(16, n_entries);
+  // blockIdx.x strides over one kernel: enough blocks that a 4x4x512x512 kernel (pix2pix) is spread over all SMs
+  dim3 grid(ctx && ctx->sm_count > 0 ? 2 * ctx->sm_count : 296, n_entries);
   pack_weights_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackEntry*)table_dev);
   DG_CHECK_LAUNCH("dg_umma_pack_weights_batch");
   return 0;
