@@ -1,10 +1,13 @@
 // Context management and error reporting of the dg_b200 C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dg_common.cuh"
 
 static thread_local char g_err[1024] = "";
+
+int g_dg_pdl = []() { const char* e = getenv("DG_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // default OFF: inside the step's CUDA graph the early-launched CTAs cost more than the hidden launch latency (A/B: 8.43 vs 8.34 ms)
 
 void dg_set_error(const char* fmt, ...) {
   va_list ap;

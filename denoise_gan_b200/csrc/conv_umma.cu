@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   __shared__ float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (P.dbg && tid == 0 && blockIdx.y == 0) {   // kernel-lifetime marks: [CTA][0] entry clock, [1] exit clock, [2]/[3] globaltimer ns
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();   // everything above (barriers, TMEM, the constant weights) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -670,7 +672,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   if (ctas < 1) ctas = 1;
   if (ctas > total_tiles) ctas = total_tiles;
   dim3 grid(ctas, n_blocks);
-  umma_conv_kernel<<<grid, CONV_THREADS, smem, st>>>(P);
+  dg_pdl_launch(umma_conv_kernel, grid, dim3(CONV_THREADS), smem, st, P);
   DG_CHECK_LAUNCH(name);
   return 0;
 }

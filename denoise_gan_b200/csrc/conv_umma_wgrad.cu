@@ -14,6 +14,9 @@
 // pixel tiles and writes one fp32 partial at the end; a second kernel sums the partials in CTA
 // order (deterministic split-K).  The bias gradient is one more accumulator whose A operand is a
 // constant tile of ones.
+// (Tried and dropped in round 1: summing the partials of 4-CTA clusters through distributed shared memory with
+// per-thread st.shared::cluster stores took 20 K cycles per CTA against 12.7 K for the plain per-CTA dump; a bulk-copy
+// version is the follow-up)
 //
 // Reference: tape.gradient(..., trainable_variables) train_srgan.py:111-112 for every Conv2D /
 // Conv2DTranspose kernel and bias.
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const int nb0 = blockIdx.y * P.nb;
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -265,6 +270,8 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, long part_stride, int splits, float* __restrict__ dw, long n_dw,
                     float* __restrict__ dbias, int n_bias, int accumulate) {
   __shared__ float4 sm[8][32];
+  pdl_trigger();
+  pdl_wait();
   const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
   const long col = (long)blockIdx.x * 32 + e;          // float4 column
   const long total4 = (n_dw + n_bias) >> 2;
@@ -602,14 +609,14 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     }
     const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;
     dim3 grid(pl.splits, pl.yblocks, zblocks);
-    umma_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(P);
+    dg_pdl_launch(umma_wgrad_kernel, grid, dim3(WG_THREADS), smem, st, P);
     DG_CHECK_LAUNCH(name);
   }
   const long total = n_dw + (dbias ? cout : 0);
   DG_REQUIRE(n_dw % 4 == 0 && total % 4 == 0 && part_stride % 4 == 0 && ((uintptr_t)dw % 16) == 0 && (!dbias || ((uintptr_t)dbias % 16) == 0),
              "dg_umma_conv2d_wgrad: gradient buffers must be 16-byte aligned");
-  wgrad_reduce_kernel<<<(unsigned)((total / 4 + 31) / 32), 256, 0, st>>>((const float*)workspace, part_stride, pl.splits, dw, n_dw,
-                                                                        dbias, dbias ? cout : 0, accumulate);
+  dg_pdl_launch(wgrad_reduce_kernel, dim3((unsigned)((total / 4 + 31) / 32)), dim3(256), 0, st, (const float*)workspace, part_stride,
+                pl.splits, dw, n_dw, dbias, dbias ? cout : 0, accumulate);
   DG_CHECK_LAUNCH("dg_umma_conv2d_wgrad(reduce)");
   return 0;
 }

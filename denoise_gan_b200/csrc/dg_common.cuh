@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/dg_b200.h"
 
@@ -33,6 +34,30 @@ void dg_set_error(const char* fmt, ...);
   do {                              \
     if (!(cond)) DG_FAIL(__VA_ARGS__); \
   } while (0)
+
+// ---- programmatic dependent launch (PDL): a kernel launched through dg_pdl_launch() may be scheduled while its
+// predecessor in the stream is still draining; it must execute pdl_wait() before touching global memory (this waits
+// for the predecessor's completion and memory flush, so ordering is exactly stream order) and should call
+// pdl_trigger() at its top so that ITS successor can be scheduled early.  Launch latency and the kernel prologue
+// (barrier init, TMEM allocation, weight loads) then overlap the predecessor's tail; ~500 kernels per train step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+extern int g_dg_pdl;   // 1 enables the launch attribute (DG_PDL=1, default off: measured slower inside the step graph), api.cu
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dg_pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_dg_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---- element access for the two storage types
 template <typename T>

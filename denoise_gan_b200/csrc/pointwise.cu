@@ -469,7 +469,7 @@ extern "C" int dg_bn_stats(dg_ctx* ctx, const dg_tensor* x, const float* gamma, 
     blocks = dgvec::red8_blocks(P, C, ctx->sm_count);
     DG_DISPATCH_1(x->dtype, "dg_bn_stats",
                   red8_optin(dgvec::bn_stats8_kernel<T>, dgvec::red8_smem(C, 2));
-                  dgvec::bn_stats8_kernel<T><<<blocks, dgvec::RT, dgvec::red8_smem(C, 2), ST>>>(
+                  dg_pdl_launch(dgvec::bn_stats8_kernel<T>, dim3(blocks), dim3(dgvec::RT), dgvec::red8_smem(C, 2), ST,
                       (const T*)x->ptr, dgvec::VView{x->cpitch, x->coff}, P, C, partial, ctx->tickets, gamma, beta, eps, momentum,
                       moving_mean, moving_var, scale, shift, save_mean, save_invstd););
     DG_CHECK_LAUNCH("dg_bn_stats");
@@ -505,7 +505,7 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
   View rv = residual ? view_of(residual) : View{0, 0};
   if (dgvec::vec_ok(x) && dgvec::vec_ok(y) && (!residual || dgvec::vec_ok(residual))) {
     DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd",
-                  dgvec::bn_act_fwd8_kernel<TI, TO><<<dgvec::ewc_blocks(P, C, ctx->sm_count), dgvec::ET, 0, ST>>>(
+                  dg_pdl_launch(dgvec::bn_act_fwd8_kernel<TI, TO>, dim3(dgvec::ewc_blocks(P, C, ctx->sm_count)), dim3(dgvec::ET), 0, ST,
                       (const TI*)x->ptr, dgvec::VView{x->cpitch, x->coff}, scale, shift, act, act_alpha, prelu_alpha,
                       residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset, step_counter,
                       (TO*)y->ptr, dgvec::VView{y->cpitch, y->coff}, P, C););
@@ -544,11 +544,11 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
 #define DG_BN_BWD_VEC(AM)                                                                                                        \
   {                                                                                                                              \
     red8_optin(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dgvec::red8_smem(C, 3));                                                  \
-    dgvec::bn_bwd_reduce8_kernel<TI, TO, AM><<<vblocks, dgvec::RT, dgvec::red8_smem(C, 3), ST>>>(                                 \
+    dg_pdl_launch(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,           \
         (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout, \
         seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr,   \
         accumulate, coef);                                                                                                       \
-    dgvec::bn_bwd_dx8_kernel<TI, TO, TI, AM><<<dgvec::ewc_blocks(P, C, ctx->sm_count), dgvec::ET, 0, ST>>>(                       \
+    dg_pdl_launch(dgvec::bn_bwd_dx8_kernel<TI, TO, TI, AM>, dim3(dgvec::ewc_blocks(P, C, ctx->sm_count)), dim3(dgvec::ET), 0, ST, \
         (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
         dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);                                                     \
   }

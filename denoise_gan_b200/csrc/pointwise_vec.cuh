@@ -223,6 +223,8 @@ bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __rest
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                  float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
                  float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  pdl_trigger();
+  pdl_wait();
   typedef typename V8<T>::raw Raw;
   channel_reduce8<2, (sizeof(Raw) <= 16 ? 16 : 8), Raw>(
       P, C, partial, ticket,
@@ -288,6 +290,8 @@ __global__ void __launch_bounds__(ET)
 bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                    float alpha, const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, int dropout,
                    uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, TO* __restrict__ y, VView yv, long P, int C) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   const int CV = C >> 3, R = ET / CV;
   const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
@@ -363,6 +367,8 @@ bn_bwd_reduce8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict_
                       float alpha, const float* __restrict__ prelu_alpha, int dropout, uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, long P, int C,
                       float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ dgamma, float* __restrict__ dbeta,
                       float* __restrict__ dalpha, int accumulate, float* __restrict__ coef) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   typedef RawPair<TG, TX> Raw;
   const int c0k = (threadIdx.x % (C >> 3)) * 8;
@@ -414,6 +420,8 @@ bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x,
                   const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ invstd, int act, float alpha, const float* __restrict__ prelu_alpha, int dropout,
                   uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, const float* __restrict__ coef, TO* __restrict__ dx, VView ov, long P, int C) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);  // a new mask every optimiser step, graph-replay safe
   const int CV = C >> 3, R = ET / CV;
   const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
