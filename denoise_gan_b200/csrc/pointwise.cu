@@ -543,14 +543,11 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
     const dgvec::VView vdy{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vdx{dx->cpitch, dx->coff};
 #define DG_BN_BWD_VEC(AM)                                                                                                        \
   {                                                                                                                              \
-    red8_optin(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dgvec::red8_smem(C, 3));                                                  \
-    dg_pdl_launch(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,           \
-        (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout, \
-        seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr,   \
-        accumulate, coef);                                                                                                       \
-    dg_pdl_launch(dgvec::bn_bwd_dx8_kernel<TI, TO, TI, AM>, dim3(dgvec::ewc_blocks(P, C, ctx->sm_count)), dim3(dgvec::ET), 0, ST, \
+    red8_optin(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dgvec::red8_smem(C, 3));                                               \
+    dg_pdl_launch(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,        \
         (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
-        dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);                                                     \
+        dropout, seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta,                                         \
+        act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef, (TI*)dx->ptr, vdx);                                      \
   }
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
       switch (dgvec::act_mode(act, dropout)) {

@@ -86,7 +86,7 @@ struct VView {
 constexpr int RT = 512;
 
 template <int NV, int U, typename Raw, typename L, typename A, typename Fin>
-__device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, L load,
+__device__ __forceinline__ bool channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, L load,
                                                 A accum, Fin fin) {
   extern __shared__ __align__(16) float red8[];
   __shared__ int is_last;
@@ -149,7 +149,7 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   // ---- last block: thread = (float4 column of the partial, group of blocks); four independent loads in flight
   double* fsum = reinterpret_cast<double*>(red8);   // [E]; group sums [G][E] live behind it
@@ -186,6 +186,36 @@ __device__ __forceinline__ void channel_reduce8(long P, int C, float* __restrict
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += RT) fin(c, fsum);
   if (threadIdx.x == 0) *ticket = 0u;
+  return true;
+}
+
+// Grid-wide "results are ready" barrier for kernels whose blocks are all co-resident (grid <= SM count, one block per
+// SM): the block that finished the reduction (`last`) raises `flag`, everybody waits for it, and the last block to
+// pass lowers it again for the next kernel.  Lets a reduction and the element-wise pass that consumes its result be
+// ONE launch: on the 19 MB generator tensors a kernel boundary (launch + ramp + tail) costs as much as the pass itself.
+__device__ __forceinline__ void grid_flag_barrier(bool last, unsigned* flag, unsigned* passed) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (last) {
+      __threadfence();
+      atomicExch(flag, 1u);
+    }
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    } while (v == 0u);
+    __threadfence();
+    if (atomicAdd(passed, 1u) == gridDim.x - 1) {
+      atomicExch(passed, 0u);
+      atomicExch(flag, 0u);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void ldcg8(const float* __restrict__ p, float (&v)[8]) {   // values written earlier in this kernel
+  float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 static inline int red8_blocks(long P, int C, int sm_count) {
@@ -455,6 +485,109 @@ bn_bwd_dx8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x,
       }
       g = __fmul_rn(g, act_deriv_t<AM>(tt, act, alpha, (AM == 3 || (AM == 4 && act == DG_ACT_PRELU)) ? al[j] : 0.f));
       o[j] = fmaf(A[j], g - k0[j], B[j] * (xin[j] - mu[j]));   // differences first: exact zero when the batch is one pixel
+    }
+    V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);
+  };
+  long p = (long)blockIdx.x * R + row;
+  for (; p + (EU - 1) * stride < P; p += EU * stride) {
+    Raw r[EU];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      r[u].g = V8<TG>::ldraw(dy + ((p + u * stride) * dv.pitch + dv.off + c0));
+      r[u].x = V8<TX>::ldraw(x + ((p + u * stride) * xv.pitch + xv.off + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u) one(r[u], p + u * stride);
+  }
+  for (; p < P; p += stride) {
+    Raw r;
+    r.g = V8<TG>::ldraw(dy + (p * dv.pitch + dv.off + c0));
+    r.x = V8<TX>::ldraw(x + (p * xv.pitch + xv.off + c0));
+    one(r, p);
+  }
+}
+
+// BatchNorm backward in ONE launch: the per-channel sums (as bn_bwd_reduce8_kernel), a grid barrier, then dx (as
+// bn_bwd_dx8_kernel) by the same 148 blocks while dy and x are still in L2.
+template <typename TG, typename TX, typename TO, int AM>
+__global__ void __launch_bounds__(RT, 1)
+bn_bwd_fused8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, int act, float alpha, const float* __restrict__ prelu_alpha, int dropout,
+                     uint32_t seed0, uint32_t offset, const int64_t* __restrict__ ctr, long P, int C, float* __restrict__ partial,
+                     unsigned* __restrict__ ticket, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dalpha,
+                     int accumulate, float* __restrict__ coef, TO* __restrict__ dx, VView ov) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);
+  typedef RawPair<TG, TX> Raw;
+  const int CV = C >> 3, R = RT / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  float sc[8], sh[8], mu[8], al[8];
+  ldc8(scale + c0, sc); ldc8(shift + c0, sh); ldc8(mean + c0, mu);
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+  auto gterm = [&](float gyj, float xj, int j, long p, float& tt) {
+    tt = fmaf(xj, sc[j], sh[j]);
+    float g = gyj;
+    if (AM == 4 && dropout) {
+      const bool keep = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j));
+      tt = keep ? 2.f * tt : 0.f;
+      g = keep ? 2.f * g : 0.f;
+    }
+    return __fmul_rn(g, act_deriv_t<AM>(tt, act, alpha, (AM == 3 || (AM == 4 && act == DG_ACT_PRELU)) ? al[j] : 0.f));
+  };
+  const bool last = channel_reduce8<3, (sizeof(Raw) <= 32 ? 4 : 2), Raw>(
+      P, C, partial, ticket,
+      [&](long p, int cc) {
+        Raw r;
+        r.g = V8<TG>::ldraw(dy + (p * dv.pitch + dv.off + cc));
+        r.x = V8<TX>::ldraw(x + (p * xv.pitch + xv.off + cc));
+        return r;
+      },
+      [&](const Raw& r, long p, int, float (&a)[3][8]) {
+        float gy[8], xin[8];
+        V8<TG>::cvt(r.g, gy);
+        V8<TX>::cvt(r.x, xin);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float tt;
+          const float g = gterm(gy[j], xin[j], j, p, tt);
+          a[0][j] += g;
+          a[1][j] = fmaf(g, xin[j] - mu[j], a[1][j]);
+          if (AM == 3 || (AM == 4 && act == DG_ACT_PRELU)) a[2][j] = fmaf(gy[j], fminf(tt, 0.f), a[2][j]);
+        }
+      },
+      [&](int c, const double* sums) {
+        const double s0 = sums[c], s1 = sums[C + c] * (double)invstd[c], s2 = sums[2 * C + c];
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+        if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
+        coef[c] = (float)(s0 / (double)P);
+        coef[C + c] = (float)(s1 / (double)P);
+      });
+  grid_flag_barrier(last, ticket + 1, ticket + 2);
+  if (row >= R) return;
+  float A[8], B[8], k0[8];
+  {
+    float ga[8], is[8], k1[8];
+    ldc8(gamma + c0, ga); ldc8(invstd + c0, is);
+    ldcg8(coef + c0, k0); ldcg8(coef + C + c0, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      A[j] = ga[j] * is[j];
+      B[j] = -A[j] * is[j] * k1[j];
+    }
+  }
+  const long stride = (long)gridDim.x * R;
+  auto one = [&](const Raw& r, long p) {
+    float gy[8], xin[8], o[8];
+    V8<TG>::cvt(r.g, gy);
+    V8<TX>::cvt(r.x, xin);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float tt;
+      const float g = gterm(gy[j], xin[j], j, p, tt);
+      o[j] = fmaf(A[j], g - k0[j], B[j] * (xin[j] - mu[j]));
     }
     V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);
   };
