@@ -75,6 +75,7 @@ SIGNATURES = {
     "dg_bn_stats": (_i, [_P, _T, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "dg_bn_infer_affine": (_i, [_P, _i, _P, _P, _P, _P, _f, _P, _P, _P]),
     "dg_bn_act_fwd": (_i, [_P, _T, _P, _P, _i, _f, _P, _T, _i, _u32, _u32, _P, _T, _P]),
+    "dg_bn_train_fwd": (_i, [_P, _T, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _i, _f, _P, _T, _i, _u32, _u32, _P, _T, _P, _sz, _P]),
     "dg_bn_act_bwd": (_i, [_P, _T, _T, _P, _P, _P, _P, _P, _i, _f, _P, _i, _u32, _u32, _P, _T, _P, _P, _P, _i, _P, _sz, _P]),
     "dg_act_bwd_from_output": (_i, [_P, _T, _T, _i, _f, _T, _P]),
     "dg_d2s_prelu_fwd": (_i, [_P, _T, _P, _T, _P]),

@@ -6,6 +6,8 @@
 // Reference call sites: BatchNormalization srgan.py:155,248, fsrgan.py:140-172, pix2pix.py:119,135,211;
 // tf.nn.depth_to_space + PReLU srgan.py:145-146; MaxPool2D / UpSampling2D autoencoder.py:110,122-124;
 // Dropout pix2pix.py:138; Add srgan.py:169,175.
+#include <stdlib.h>
+
 #include "dg_common.cuh"
 #include "reduce.cuh"
 #include "pointwise_vec.cuh"
@@ -520,6 +522,37 @@ extern "C" int dg_bn_act_fwd(dg_ctx* ctx, const dg_tensor* x, const float* scale
   return 0;
 }
 
+// dg_bn_stats + dg_bn_act_fwd in one launch (training mode).  Returns 2 when the tensors do not qualify for the fused
+// vector kernel: the caller then issues the two calls (never a silent fallback inside the library).
+extern "C" int dg_bn_train_fwd(dg_ctx* ctx, const dg_tensor* x, const float* gamma, const float* beta, float eps, float momentum,
+                               float* moving_mean, float* moving_var, float* scale, float* shift, float* save_mean,
+                               float* save_invstd, int act, float act_alpha, const float* prelu_alpha, const dg_tensor* residual,
+                               int dropout, uint32_t seed, uint32_t offset, const int64_t* step_counter, const dg_tensor* y,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y) && gamma && beta && scale && shift && save_mean && save_invstd && workspace,
+             "dg_bn_train_fwd: null argument");
+  DG_REQUIRE(dg_same_shape(x, y), "dg_bn_train_fwd: shape mismatch");
+  DG_REQUIRE(act != DG_ACT_PRELU || prelu_alpha, "dg_bn_train_fwd: PReLU needs alpha");
+  if (residual) DG_REQUIRE(dg_valid(residual) && dg_same_shape(residual, y) && residual->dtype == y->dtype,
+                           "dg_bn_train_fwd: residual mismatch");
+  DG_REQUIRE(workspace_bytes >= dg_bn_workspace_bytes(x), "dg_bn_train_fwd: workspace too small");
+  if (!(dgvec::vec_ok(x) && dgvec::vec_ok(y) && (!residual || dgvec::vec_ok(residual)))) return 2;
+  const long P = dg_pixels(x);
+  const int C = x->c;
+  const int blocks = dgvec::red8_blocks(P, C, ctx->sm_count);
+  View rv = residual ? view_of(residual) : View{0, 0};
+  DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_train_fwd", {
+    red8_optin(dgvec::bn_fwd_fused8_kernel<TI, TO>, dgvec::red8_smem(C, 2));
+    dg_pdl_launch(dgvec::bn_fwd_fused8_kernel<TI, TO>, dim3(blocks), dim3(dgvec::RT), dgvec::red8_smem(C, 2), ST, (const TI*)x->ptr,
+                  dgvec::VView{x->cpitch, x->coff}, P, C, (float*)workspace, ctx->tickets, gamma, beta, eps, momentum, moving_mean,
+                  moving_var, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha,
+                  residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset, step_counter,
+                  (TO*)y->ptr, dgvec::VView{y->cpitch, y->coff});
+  });
+  DG_CHECK_LAUNCH("dg_bn_train_fwd");
+  return 0;
+}
+
 extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const float* scale,
                              const float* shift, const float* gamma, const float* save_mean, const float* save_invstd,
                              int act, float act_alpha, const float* prelu_alpha, int dropout, uint32_t seed,
@@ -541,13 +574,24 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
   if (dgvec::vec_ok(dy) && dgvec::vec_ok(x) && dgvec::vec_ok(dx)) {
     const int vblocks = dgvec::red8_blocks(P, C, ctx->sm_count);
     const dgvec::VView vdy{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vdx{dx->cpitch, dx->coff};
+    static const char* env_fused = getenv("DG_BN_FUSED_BWD");
+    const bool fused_bwd = !(env_fused && env_fused[0] == '0');
 #define DG_BN_BWD_VEC(AM)                                                                                                        \
-  {                                                                                                                              \
+  if (fused_bwd) {                                                                                                               \
     red8_optin(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dgvec::red8_smem(C, 3));                                               \
     dg_pdl_launch(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,        \
         (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
         dropout, seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta,                                         \
         act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef, (TI*)dx->ptr, vdx);                                      \
+  } else {                                                                                                                       \
+    red8_optin(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dgvec::red8_smem(C, 3));                                                  \
+    dg_pdl_launch(dgvec::bn_bwd_reduce8_kernel<TI, TO, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,           \
+        (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha, dropout, \
+        seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr,   \
+        accumulate, coef);                                                                                                       \
+    dg_pdl_launch(dgvec::bn_bwd_dx8_kernel<TI, TO, TI, AM>, dim3(dgvec::ewc_blocks(P, C, ctx->sm_count)), dim3(dgvec::ET), 0, ST, \
+        (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
+        dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);                                                     \
   }
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
       switch (dgvec::act_mode(act, dropout)) {

@@ -382,6 +382,103 @@ bn_act_fwd8_kernel(const TI* __restrict__ x, VView xv, const float* __restrict__
   }
 }
 
+// Training-mode BatchNorm forward in ONE launch: batch statistics (as bn_stats8_kernel, incl. the moving-statistics
+// update), grid flag barrier, then normalise + dropout + activation + skip-add (as bn_act_fwd8_kernel) by the same blocks.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(RT, 1)
+bn_fwd_fused8_kernel(const TI* __restrict__ x, VView xv, long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                     float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
+                     float* __restrict__ save_mean, float* __restrict__ save_invstd, int act, float alpha,
+                     const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, int dropout, uint32_t seed0,
+                     uint32_t offset, const int64_t* __restrict__ ctr, TO* __restrict__ y, VView yv) {
+  pdl_trigger();
+  pdl_wait();
+  typedef typename V8<TI>::raw Raw;
+  const bool last = channel_reduce8<2, (sizeof(Raw) <= 16 ? 16 : 8), Raw>(
+      P, C, partial, ticket,
+      [&](long p, int c0) { return V8<TI>::ldraw(x + (p * xv.pitch + xv.off + c0)); },
+      [&](const Raw& r, long, int, float (&a)[2][8]) {
+        float v[8];
+        V8<TI>::cvt(r, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[0][j] += v[j]; a[1][j] = fmaf(v[j], v[j], a[1][j]); }
+      },
+      [&](int c, const double* sums) {
+        double mean = sums[c] / (double)P;
+        double var = sums[C + c] / (double)P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        float g = gamma[c], b = beta[c];
+        scale[c] = g * invstd;
+        shift[c] = b - (float)mean * g * invstd;
+        save_mean[c] = (float)mean;
+        save_invstd[c] = invstd;
+        if (moving_mean) {
+          moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+          moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+        }
+      });
+  grid_flag_barrier(last, ticket + 1, ticket + 2);
+  const uint32_t seed = seed0 + (ctr ? (uint32_t)(*ctr) * 0x9E3779B9u : 0u);
+  const int CV = C >> 3, R = RT / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  if (row >= R) return;
+  float sc[8], sh[8], al[8];
+  ldcg8(scale + c0, sc); ldcg8(shift + c0, sh);
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+  const long stride = (long)gridDim.x * R;
+  typedef typename V8<TO>::raw RawO;
+  auto one = [&](const Raw& rx, const RawO& rr, long p) {
+    float v[8];
+    V8<TI>::cvt(rx, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (dropout) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = dropout_keep(seed, offset + (uint32_t)(p * C + c0 + j)) ? 2.f * v[j] : 0.f;
+    }
+    if (act == DG_ACT_PRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : al[j] * v[j];
+    } else if (act == DG_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == DG_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] >= 0.f ? v[j] : alpha * v[j];
+    } else if (act != DG_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, alpha);
+    }
+    if (res) {
+      float r[8];
+      V8<TO>::cvt(rr, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    V8<TO>::st(y + (p * yv.pitch + yv.off + c0), v);
+  };
+  long p = (long)blockIdx.x * R + row;
+  for (; p + (EU - 1) * stride < P; p += EU * stride) {
+    Raw rx[EU];
+    RawO rr[EU];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      rx[u] = V8<TI>::ldraw(x + ((p + u * stride) * xv.pitch + xv.off + c0));
+      if (res) rr[u] = V8<TO>::ldraw(res + ((p + u * stride) * rv.pitch + rv.off + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u) one(rx[u], rr[u], p + u * stride);
+  }
+  for (; p < P; p += stride) {
+    Raw rx = V8<TI>::ldraw(x + (p * xv.pitch + xv.off + c0));
+    RawO rr;
+    if (res) rr = V8<TO>::ldraw(res + (p * rv.pitch + rv.off + c0));
+    one(rx, rr, p);
+  }
+}
+
 template <typename TG, typename TX>
 struct RawPair {
   typename V8<TG>::raw g;

@@ -11,6 +11,7 @@ captured into one CUDA graph.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -85,6 +86,7 @@ class Engine:
         self.written: set = set()      # param names whose grad slice was written this step
         self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
         self.use_umma_wgrad = self.use_umma
+        self.fuse_bn_fwd = os.environ.get("DG_BN_FUSED_FWD", "1") != "0"   # A/B switch for the one-launch BN forward
         self.pad_rgb = True            # channel counts that are not multiples of 16 (RGB sides, the autoencoder's 44/56/76/100/67/...)
                                        # run on the tensor cores through zero padding to the next multiple of 16
         self.launches = 0
@@ -557,22 +559,38 @@ class Engine:
         tx = tensor(x.t)
         nbytes = self.lib.dg_bn_workspace_bytes(C.byref(tx))
         ws = self.workspace(nbytes)
-        if training:
-            check(self.lib.dg_bn_stats(self.ctx, C.byref(tx), gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
-                                       mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
-                                       invstd.data_ptr(), ws.data_ptr(), nbytes, self.st))
-        else:
-            check(self.lib.dg_bn_infer_affine(self.ctx, Cc, gamma.data.data_ptr(), beta.data.data_ptr(), mm.data.data_ptr(),
-                                              mv.data.data_ptr(), float(eps), scale.data_ptr(), shift.data_ptr(), self.st))
         y = self.buf((seq, "y"), x.shape, x.t.dtype)
         ty = tensor(y)
         tres = tensor(residual.t) if residual is not None else None
         drop = 1 if (dropout_seed is not None and training) else 0
         a_code = ACT["prelu"] if prelu is not None else ACT[act]
-        check(self.lib.dg_bn_act_fwd(self.ctx, C.byref(tx), scale.data_ptr(), shift.data_ptr(), a_code, float(alpha),
-                                     _lib.ptr(prelu.data) if prelu is not None else None,
-                                     C.byref(tres) if tres is not None else None, drop, int(dropout_seed or 0), int(dropout_offset),
-                                     _lib.ptr(step_counter), C.byref(ty), self.st))
+        fused = False
+        if training and not self.fuse_bn_fwd:
+            check(self.lib.dg_bn_stats(self.ctx, C.byref(tx), gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
+                                       mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                       invstd.data_ptr(), ws.data_ptr(), nbytes, self.st))
+        elif training:
+            # statistics + apply as ONE launch when the tensors qualify (rc 2: they do not, issue the two calls)
+            rc = self.lib.dg_bn_train_fwd(self.ctx, C.byref(tx), gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
+                                          mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                          invstd.data_ptr(), a_code, float(alpha), _lib.ptr(prelu.data) if prelu is not None else None,
+                                          C.byref(tres) if tres is not None else None, drop, int(dropout_seed or 0), int(dropout_offset),
+                                          _lib.ptr(step_counter), C.byref(ty), ws.data_ptr(), nbytes, self.st)
+            if rc == 2:
+                check(self.lib.dg_bn_stats(self.ctx, C.byref(tx), gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
+                                           mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                           invstd.data_ptr(), ws.data_ptr(), nbytes, self.st))
+            else:
+                check(rc)
+                fused = True
+        else:
+            check(self.lib.dg_bn_infer_affine(self.ctx, Cc, gamma.data.data_ptr(), beta.data.data_ptr(), mm.data.data_ptr(),
+                                              mv.data.data_ptr(), float(eps), scale.data_ptr(), shift.data_ptr(), self.st))
+        if not fused:
+            check(self.lib.dg_bn_act_fwd(self.ctx, C.byref(tx), scale.data_ptr(), shift.data_ptr(), a_code, float(alpha),
+                                         _lib.ptr(prelu.data) if prelu is not None else None,
+                                         C.byref(tres) if tres is not None else None, drop, int(dropout_seed or 0), int(dropout_offset),
+                                         _lib.ptr(step_counter), C.byref(ty), self.st))
         inputs = [x] + ([residual] if residual is not None else [])
         out = Var(y, self._deps(inputs, gamma.group), seq)
 

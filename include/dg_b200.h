@@ -118,6 +118,14 @@ int dg_bn_infer_affine(dg_ctx*, int c, const float* gamma, const float* beta, co
 int dg_bn_act_fwd(dg_ctx*, const dg_tensor* x, const float* scale, const float* shift, int act, float act_alpha,
                   const float* prelu_alpha, const dg_tensor* residual, int dropout, uint32_t seed, uint32_t offset,
                   const int64_t* step_counter, const dg_tensor* y, void* stream);
+/* dg_bn_stats followed by dg_bn_act_fwd as ONE launch (statistics, grid barrier, apply): training-mode BatchNormalization
+ * + activation of srgan.py:155-157 etc.  Returns 0 on success, 1 on error, 2 when the tensors do not qualify for the
+ * fused kernel (channels/pitch not multiples of 8, > 2^31 elements): issue the two calls instead. */
+int dg_bn_train_fwd(dg_ctx*, const dg_tensor* x, const float* gamma, const float* beta, float eps, float momentum,
+                    float* moving_mean, float* moving_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                    int act, float act_alpha, const float* prelu_alpha, const dg_tensor* residual, int dropout, uint32_t seed,
+                    uint32_t offset, const int64_t* step_counter, const dg_tensor* y, void* workspace, size_t workspace_bytes,
+                    void* stream);
 /* backward of the above: dx, dgamma, dbeta (and dprelu_alpha when act == PRELU) */
 int dg_bn_act_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const float* scale, const float* shift,
                   const float* gamma, const float* save_mean, const float* save_invstd, int act, float act_alpha,
