@@ -126,6 +126,16 @@ def ctx(device: int | None = None):
     return _ctx[device]
 
 
+def new_ctx(device: int):
+    """A second, private context (own reduction scratch) for launches on a second stream of the same device."""
+    lib = load()
+    h = C.c_void_p()
+    rc = lib.dg_init(int(device), C.byref(h))
+    if rc != 0:
+        raise DgError(lib.dg_last_error().decode())
+    return h
+
+
 CALLS = 0  # number of C-ABI compute calls issued (each enqueues >= 1 kernel)
 
 

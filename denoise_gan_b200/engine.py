@@ -77,7 +77,9 @@ class Engine:
         self.prof_calls = None
         self.lib = _ProfLib(_lib.load(), self)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self.ctx = _lib.ctx(self.device.index)
+        self._in_side = False
+        self._ctx_main = _lib.ctx(self.device.index)
+        self._ctx_side = None          # private context (reduction scratch) of the side stream, created on first use
         self.bf16 = bool(bf16)
         self.act_dtype = torch.bfloat16 if bf16 else torch.float32
         self.pool: dict = {}
@@ -142,6 +144,22 @@ class Engine:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
         return self._ws
+
+    @property
+    def ctx(self):
+        if self._in_side:
+            if self._ctx_side is None:
+                self._ctx_side = _lib.new_ctx(self.device.index)
+            return self._ctx_side
+        return self._ctx_main
+
+    def branch(self):
+        """`with E.branch(): ...` runs an independent part of the forward graph (e.g. D(real) next to the generator) on
+        the side stream; call E.join() before its results are consumed."""
+        return self._side()
+
+    def join(self):
+        self._join_side()
 
     @contextlib.contextmanager
     def _side(self):

@@ -15,8 +15,12 @@ def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: flo
     E.new_step()
     x = E.input(img_input)
     y = E.input(img_target)
-    gen_output = model.generator(x, training=True)                     # train_srgan.py:75
-    disc_real = model.discriminator(y, training=True)                  # :78
+    # D(real) does not depend on the generator: it runs on the side stream next to the generator forward and is joined
+    # before D(fake), which keeps the reference's order of the two BatchNorm moving-statistics updates (real, then fake)
+    with E.branch():
+        disc_real = model.discriminator(y, training=True)              # train_srgan.py:78
+    gen_output = model.generator(x, training=True)                     # :75
+    E.join()
     disc_fake = model.discriminator(gen_output, training=True)         # :79
 
     seeds_g = []
