@@ -662,6 +662,7 @@ class Engine:
                 da = prelu.grad.data_ptr() if prelu is not None else None
             else:
                 acc, dg, db, da = 0, None, None, None
+            ws = self.workspace(nbytes)     # the workspace of the stream this runs on (not the forward pass's: side-stream branches)
             check(self.lib.dg_bn_act_bwd(self.ctx, C.byref(tg), C.byref(tx), scale.data_ptr(), shift.data_ptr(), gamma.data.data_ptr(),
                                          mean.data_ptr(), invstd.data_ptr(), a_code, float(alpha),
                                          _lib.ptr(prelu.data) if prelu is not None else None, drop, int(dropout_seed or 0),

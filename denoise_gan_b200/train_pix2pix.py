@@ -14,8 +14,15 @@ def train_step(model, x, y):
     E = model.engine
     E.new_step()
     xv, yv = E.input(x), E.input(y)
-    gen_output = model.generator(xv, training=True, pass_id=0)                   # train_pix2pix.py:44
-    disc_real = model.discriminator([xv, yv], training=True)                     # :47
+    # Independent sub-graphs run on the engine's side stream: D(real) next to the first generator pass, and the identity
+    # generator pass next to D(fake) and the image losses.  Joins keep the reference's order of the BatchNorm
+    # moving-statistics updates (D: real then fake; G: pass 0 then the identity pass).
+    with E.branch():
+        disc_real = model.discriminator([xv, yv], training=True)                 # train_pix2pix.py:47
+    gen_output = model.generator(xv, training=True, pass_id=0)                   # :44
+    E.join()
+    with E.branch():
+        ident_out = model.generator(yv, training=True, pass_id=1)                # pix2pix.py:90
     disc_fake = model.discriminator([xv, gen_output], training=True)             # :48
 
     seeds_g = []
@@ -27,7 +34,7 @@ def train_step(model, x, y):
         content = torch.zeros((), dtype=torch.float32, device=E.device)
     gan_raw, g_adv = E.bce(disc_fake, 1.0, True, 1e-3, key="adv")                # pix2pix.py:75
     out3, dgen = E.image_losses(gen_output, y, 1.0, 1.0, 1e-5, key="img")         # :78-84 (mae, mse, 1e-5*TV)
-    ident_out = model.generator(yv, training=True, pass_id=1)                    # :90
+    E.join()
     id3, dident = E.image_losses(ident_out, y, 1.0, 0.0, 0.0, key="ident")
     real_loss, g_real = E.bce(disc_real, 1.0, True, 1.0, key="dreal")             # :97
     fake_loss, g_fake = E.bce(disc_fake, 0.0, True, 1.0, key="dfake")             # :99
