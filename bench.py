@@ -237,9 +237,11 @@ def main():
         from denoise_gan_b200 import _lib as _L
         calls0 = _L.CALLS
         comm, model.comm = model.comm, None      # profile step is rank-0 only: no exchange, or the other ranks would be missed
+        overlap, E.wgrad_overlap = E.wgrad_overlap, False   # one stream: per-kernel times are not stretched by a concurrent kernel
         train_step(model, run.x if not args.no_graph else x_h.cuda(), run.y if not args.no_graph else y_h.cuda())
         torch.cuda.synchronize()
         model.comm = comm
+        E.wgrad_overlap = overlap
         fam = {}
         for kind, flops, a, b in E.prof:
             f = fam.setdefault(kind, [0.0, 0.0, 0])
