@@ -8,6 +8,62 @@ from __future__ import annotations
 import torch
 
 
+class DevicePrefetcher:
+    """Hands out the batches of a host `(input, target)` iterable as device tensors whose host->device copy was
+    enqueued ONE BATCH AHEAD on a copy stream, so the transfer of batch k+1 runs under train step k — the role of
+    `dataset.prefetch(AUTOTUNE)` in the reference input pipeline (dataloader.py:204-221).  Two device buffers per
+    tensor; pinned host batches are copied asynchronously as they are, pageable ones through pinned staging."""
+
+    def __init__(self, dataset, device):
+        self.it = iter(dataset)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]     # per slot: (x_dev, y_dev, x_pin, y_pin)
+        self.k = 0
+        self.pending = None           # (x_dev, y_dev, event) of the batch whose copy is in flight
+        self.h2d_bytes = 0
+
+    def _enqueue(self):
+        try:
+            x, y = next(self.it)
+        except StopIteration:
+            self.pending = None
+            return
+        i = self.k & 1
+        self.k += 1
+        if self.slots[i] is None or self.slots[i][0].shape != x.shape or self.slots[i][1].shape != y.shape:
+            self.slots[i] = (torch.empty(x.shape, dtype=x.dtype, device=self.device), torch.empty(y.shape, dtype=y.dtype, device=self.device),
+                             None if x.is_pinned() else torch.empty(x.shape, dtype=x.dtype).pin_memory(),
+                             None if y.is_pinned() else torch.empty(y.shape, dtype=y.dtype).pin_memory())
+        xd, yd, xp, yp = self.slots[i]
+        # the slot was consumed by work already enqueued on the caller's stream (the step before last)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if xp is not None:
+            self.stream.synchronize()             # the previous copy out of the pinned staging must have left it
+            xp.copy_(x); yp.copy_(y)
+            x, y = xp, yp
+        with torch.cuda.stream(self.stream):
+            xd.copy_(x, non_blocking=True)
+            yd.copy_(y, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.h2d_bytes += x.numel() * x.element_size() + y.numel() * y.element_size()
+        self.pending = (xd, yd, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.k == 0 and self.pending is None:
+            self._enqueue()
+        cur = self.pending
+        if cur is None:
+            raise StopIteration
+        self._enqueue()                            # start the next transfer before the caller launches this step
+        torch.cuda.current_stream(self.device).wait_event(cur[2])
+        return cur[0], cur[1]
+
+
 class GraphedStep:
     def __init__(self, model, step_fn, x_example: torch.Tensor, y_example: torch.Tensor, warmup: int = 2, debug_dot: str | None = None):
         self.model = model
@@ -22,20 +78,31 @@ class GraphedStep:
                 self.out = step_fn(model, self.x, self.y)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        if debug_dot:
-            self.graph.enable_debug_mode()
+        try:
+            self.graph = torch.cuda.CUDAGraph(keep_graph=True)      # keeps the cudaGraph_t so that its nodes can be counted
+        except TypeError:
+            self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = step_fn(model, self.x, self.y)
-        self.kernel_nodes = None
-        if debug_dot:
-            try:
-                self.graph.debug_dump(debug_dot)
-                with open(debug_dot) as f:
-                    txt = f.read()
-                self.kernel_nodes = txt.count("KERNEL") or None
-            except Exception:
-                self.kernel_nodes = None
+        self.kernel_nodes = self._count_kernel_nodes()
+
+    def _count_kernel_nodes(self):
+        """Number of kernel nodes of the captured step (bench.py's `gpu_launches`), through the CUDA runtime bindings."""
+        try:
+            from cuda.bindings import runtime as cudart
+            raw = self.graph.raw_cuda_graph()
+            err, _, n = cudart.cudaGraphGetNodes(raw, 0)
+            if int(err) != 0 or n == 0:
+                return None
+            err, nodes, n = cudart.cudaGraphGetNodes(raw, n)
+            count = 0
+            for nd in nodes[:n]:
+                err, ty = cudart.cudaGraphNodeGetType(nd)
+                if int(err) == 0 and ty == cudart.cudaGraphNodeType.cudaGraphNodeTypeKernel:
+                    count += 1
+            return count or None
+        except Exception:
+            return None
 
     def __call__(self, x: torch.Tensor | None = None, y: torch.Tensor | None = None):
         if x is not None:

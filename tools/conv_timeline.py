@@ -39,7 +39,7 @@ names = {0: ["tile start", "slot free", "loads issued", ""], 1: ["tile start", "
 lib.dg_debug_conv_flags(0)
 for role, rn in enumerate(["producer", "mma", "epilogue"]):
     print(rn)
-    if role != 1:
+    if role != 1 and not _os.environ.get('DG_ALL_ROLES'):
         continue
     for it in range(16):
         row = t[role, it]
