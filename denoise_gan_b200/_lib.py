@@ -55,6 +55,8 @@ SIGNATURES = {
     "dg_umma_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
+    "dg_umma_conv2d_fwd_bn_blocks": (_i, [_P, _T, _T, _CP]),
+    "dg_bn_finalize": (_i, [_P, _P, _i, C.c_longlong, _i, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _P]),
     "dg_umma_conv2d_dgrad_supported": (_i, [_P, _T, _T, _CP]),
     "dg_bias_grad": (_i, [_P, _T, _P, _i, _P, _sz, _P]),
     "dg_pad_channels": (_i, [_P, _T, _T, _P]),

@@ -61,6 +61,13 @@ struct UmmaConvParams {
   void* out;
   long out_sn, out_sh, out_sw;
   int out_f32;
+  // staged epilogue: the tile is written to shared memory in the TMA swizzle and leaves through ONE bulk tensor store
+  // (dense bf16 output views with a 16/32/64-channel N block); optionally the BatchNorm batch-statistics partials
+  // (per-channel sum and sum of squares of the STORED values) are accumulated from the staged tile
+  CUtensorMap omap;
+  int tstore;
+  uint32_t stg_off, stg_bytes, stg_mask;
+  float* bn_partials;   // [gridDim.x][2][cout_total] or nullptr
   const float* bias;
   int act;
   float alpha;
@@ -159,6 +166,138 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
   }
 }
 
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// one 16-column group of one accumulator row: + bias, activation, bf16, two 16-byte chunks of the staged row
+template <int ACT>
+__device__ __forceinline__ void epi_stage16(const uint32_t (&v)[16], const float* __restrict__ bs, float alpha, bool valid, uint32_t stg,
+                                            uint32_t off, uint32_t mask) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (bs) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] += bs[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = valid ? act_fn<ACT>(f[j], alpha) : 0.f;   // rows outside the image: zeros (clipped by the store, neutral in the sums)
+  st_shared_v4(stg + swz(off, mask), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  st_shared_v4(stg + swz(off + 16u, mask), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+               pack_bf16x2(f[14], f[15]));
+}
+
+// Epilogue through shared memory: TMEM -> registers -> bias/activation -> bf16 rows in the TMA swizzle (conflict-free
+// 16-byte stores) -> one cp.async.bulk.tensor store per tile (full 128-byte lines instead of 32 scattered 16-byte
+// segments per warp instruction), double-buffered so the store of tile i drains under the epilogue of tile i+1.
+// With P.bn_partials the same staged tile feeds the BatchNorm batch statistics: a thread owns one channel pair and
+// walks the rows of its warp's quarter (one 4-byte word per lane: conflict-free), so the statistics cost no extra
+// pass over the tensor and no launch (srgan.py:155 BatchNormalization after every conv of the residual trunk).
+template <int ACT>
+__device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int nb0,
+                                                 int total_tiles, const float* __restrict__ bs, uint64_t* bar_acc_full,
+                                                 uint64_t* bar_acc_empty, float* red_s) {
+  const int m_idx = q * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t RB = (uint32_t)P.nb * 2u, mask = P.stg_mask;
+  const int WPR = P.nb >> 1, RPR = 32 / WPR;          // 4-byte words per staged row, rows per warp-wide read
+  const int sub = lane / WPR, w = lane - sub * WPR;
+  const bool leader = q == 0 && lane == 0;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int b = it & ((1 << P.nbuf_shift) - 1);
+    const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
+    const int tw = tile % P.tiles_w;
+    const int t2 = tile / P.tiles_w;
+    const int th = t2 % P.tiles_h;
+    const int n = t2 / P.tiles_h;
+    const uint32_t stg = stg_base + (uint32_t)(it & 1) * P.stg_bytes;
+    if (leader) {
+      dbg_mark(P, 2, it, 0);
+      tma_store_wait_read<1>();     // the store that read this buffer two tiles ago has left shared memory
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
+    tc_fence_after();
+    if (leader) dbg_mark(P, 2, it, 1);
+    for (int m = 0; m < P.mt; ++m) {
+      const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
+      const int pw = tw * 8 + (m_idx & 7);
+      const bool valid = ph < P.out_h && pw < P.out_w;
+      const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.mt + m) * P.nb);
+      const uint32_t row_off = (uint32_t)(m * 128 + m_idx) * RB;
+      int c0 = 0;
+      for (; c0 + 32 <= P.nb; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x16(acc + c0, v0);
+        tmem_ld_32x16(acc + c0 + 16, v1);
+        tmem_ld_wait();
+        epi_stage16<ACT>(v0, bs ? bs + c0 : nullptr, P.alpha, valid, stg, row_off + 2u * c0, mask);
+        epi_stage16<ACT>(v1, bs ? bs + c0 + 16 : nullptr, P.alpha, valid, stg, row_off + 2u * c0 + 32u, mask);
+      }
+      if (c0 < P.nb) {
+        uint32_t v0[16];
+        tmem_ld_32x16(acc + c0, v0);
+        tmem_ld_wait();
+        epi_stage16<ACT>(v0, bs ? bs + c0 : nullptr, P.alpha, valid, stg, row_off + 2u * c0, mask);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));   // the accumulator is free as soon as it is in registers
+    fence_proxy_async();                                         // generic-proxy writes -> visible to the bulk store
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (leader) {
+      if (!(P.dbg_flags & 1)) tma_store_4d(&P.omap, stg, nb0, tw * 8, th * 16 * P.mt, n);
+      tma_store_commit();
+      dbg_mark(P, 2, it, 2);
+    }
+    if (P.bn_partials) {
+      const int iters = 32 / RPR;
+      for (int m = 0; m < P.mt; ++m) {
+        const uint32_t r0 = (uint32_t)(m * 128 + q * 32 + sub);
+#pragma unroll 8
+        for (int i = 0; i < iters; ++i) {
+          const uint32_t off = (r0 + (uint32_t)(i * RPR)) * RB + 4u * (uint32_t)w;
+          const uint32_t word = ld_shared_u32(stg + swz(off, mask));
+          const float a = __uint_as_float(word << 16), c = __uint_as_float(word & 0xffff0000u);
+          s0 += a; q0 = fmaf(a, a, q0);
+          s1 += c; q1 = fmaf(c, c, q1);
+        }
+      }
+    }
+  }
+  if (leader) tma_store_wait<0>();
+  if (P.bn_partials) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // all stores have left the staging buffers: buffer 0 is the scratch of the final sum
+    for (int o = WPR; o < 32; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    if (lane < WPR) {
+      red_s[(q * 4 + 0) * 32 + lane] = s0; red_s[(q * 4 + 1) * 32 + lane] = s1;
+      red_s[(q * 4 + 2) * 32 + lane] = q0; red_s[(q * 4 + 3) * 32 + lane] = q1;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (q == 0 && lane < WPR) {
+      float t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = red_s[(0 * 4 + k) * 32 + lane] + red_s[(1 * 4 + k) * 32 + lane] + red_s[(2 * 4 + k) * 32 + lane] + red_s[(3 * 4 + k) * 32 + lane];
+      float* dst = P.bn_partials + (size_t)blockIdx.x * 2 * P.cout_total + nb0 + 2 * lane;
+      dst[0] = t[0]; dst[1] = t[1];
+      dst[P.cout_total] = t[2]; dst[P.cout_total + 1] = t[3];
+    }
+  }
+}
+
 // Issues the MMAs of one pipeline stage (all taps of one channel chunk).  MT and NBK (= chunk/16) are
 // compile-time so the body is straight-line: one descriptor add per operand per tcgen05.mma.
 // NT > 0 additionally fixes the tap count, so every per-tap descriptor is a constant-bank load at a static offset and the
@@ -219,6 +358,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     // the resident weights start loading before the CTA-wide sync, under the TMEM allocation of warp 1
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
     tma_prefetch_desc(&P.wmap);
+    if (P.tstore) tma_prefetch_desc(&P.omap);
     if (P.resident) {
       const uint32_t bw = smem_u32(&bar_w);
       mbar_expect_tx(bw, P.w_res_tx);
@@ -368,7 +508,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     const float* bs = P.bias ? bias_s : nullptr;
 #define DG_EPI(ACT)                                                                                     \
-  if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty); \
+  if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
+                                      reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off)); \
+  else if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty); \
   else epilogue_role<ACT, false>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty);
     switch (P.act) {
       case DG_ACT_RELU: DG_EPI(DG_ACT_RELU) break;
@@ -471,7 +613,8 @@ struct TapSpec {
 // Builds the launch description and runs the kernel.
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
                 const TapSpec* taps_in, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
-                const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false) {
+                const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
+                float* bn_partials = nullptr, int* bn_blocks = nullptr) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
   DG_REQUIRE(in->cpitch % 8 == 0 && in->coff % 8 == 0 && ((uintptr_t)in->ptr % 16) == 0, "%s: input view not 16-byte aligned", name);
@@ -573,9 +716,36 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
         }
   }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d taps=%d)", name, in->c, cout, n_taps);
-  if (dry) return 0;   // capability query: a tile configuration exists
   const int nb = best_nb, mt = best_mt;
   P.nb = nb; P.mt = mt; P.resident = best_res; P.split = split;
+
+  // pipeline depth, and whether the staged (shared memory + TMA store) epilogue fits next to it
+  auto r1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  const uint32_t stage_bytes_pre = split ? r1k(max_halo(mt) + (uint32_t)max_ntaps * nb * kc * 2)
+                                         : r1k(halo_bytes(mt) + (best_res ? 0u : (uint32_t)n_taps * nb * kc * 2));
+  const uint32_t w_res_pre = best_res ? r1k((uint32_t)n_taps * n_chunks * nb * kc * 2) : 0u;
+  int n_stages = (int)((budget - w_res_pre) / stage_bytes_pre);
+  if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
+  DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
+  static const char* dbg_no_ts = getenv("DG_DEBUG_NO_TSTORE");   // experiments only
+  bool ts = (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64);
+  const uint32_t stg_bytes = (uint32_t)mt * 128u * (uint32_t)nb * 2u;
+  if (ts) {
+    const long room = (long)budget - (long)w_res_pre - 2L * (long)stg_bytes;
+    int ns = room > 0 ? (int)(room / (long)stage_bytes_pre) : 0;
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    // keep the two-issuer configuration (>= 4 slots and four TMEM buffers) when the layer had it without the staging buffers
+    const bool had_two = 4 * mt * nb <= 512 && n_stages >= 4;
+    if (ns >= 2 && (!had_two || ns >= 4)) n_stages = ns; else ts = false;
+  }
+  const int out_h_ = (out->h - out_lat.h_first + out_lat.step - 1) / out_lat.step, out_w_ = (out->w - out_lat.w_first + out_lat.step - 1) / out_lat.step;
+  const int total_tiles_pre = out->n * ((out_h_ + 16 * mt - 1) / (16 * mt)) * ((out_w_ + 7) / 8);
+  int ctas_pre = ctx->sm_count / (cout / nb);
+  if (ctas_pre < 1) ctas_pre = 1;
+  if (ctas_pre > total_tiles_pre) ctas_pre = total_tiles_pre;
+  if (bn_blocks) *bn_blocks = ts ? ctas_pre : 0;
+  if (dry) return 0;   // capability query: a tile configuration exists
+  DG_REQUIRE(!bn_partials || ts, "%s: fused BatchNorm statistics need the staged epilogue (dense bf16 output, N block of 16/32/64)", name);
 
   P.w_block_bytes = (uint32_t)nb * kc * 2;
   P.w_res_tx = best_res ? (uint32_t)n_taps * n_chunks * P.w_block_bytes : 0;
@@ -621,9 +791,11 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
       t0 += src_ntaps[s];
     }
   }
-  int n_stages = (int)((budget - P.w_res_bytes) / P.stage_bytes);
-  if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
-  DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
+  DG_REQUIRE(P.stage_bytes == stage_bytes_pre && P.w_res_bytes == w_res_pre, "%s: internal: stage accounting mismatch", name);
+  P.tstore = ts ? 1 : 0;
+  P.stg_bytes = stg_bytes;
+  P.stg_mask = nb == 64 ? 7u : (nb == 32 ? 3u : 1u);
+  P.bn_partials = bn_partials;
   {
     // two issuing warps need four TMEM accumulator buffers and at least two pipeline slots each
     static const char* dbg_single = getenv("DG_DEBUG_SINGLE_ISSUER");   // experiments only
@@ -659,7 +831,15 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.dbg = g_dbg_timeline;
   P.dbg_flags = g_dbg_flags;
 
-  const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + 1024;
+  P.stg_off = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes;
+  if (ts) {
+    // output view as a 4-D tensor map (C, W, H, N); one box = the CTA's tile, clipped at the image border by the TMA unit
+    uint64_t dims[4] = {(uint64_t)out->c, (uint64_t)out->w, (uint64_t)out->h, (uint64_t)out->n};
+    uint64_t strides[3] = {(uint64_t)out->cpitch * 2, (uint64_t)out->cpitch * 2 * out->w, (uint64_t)out->cpitch * 2 * out->w * out->h};
+    uint32_t box[4] = {(uint32_t)nb, 8u, (uint32_t)(16 * mt), 1u};
+    if (encode_map(ctx, &P.omap, (char*)out->ptr + (size_t)out->coff * 2, 4, dims, strides, box, nb)) return 1;
+  }
+  const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + (ts ? 2u * stg_bytes : 0u) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);
@@ -730,7 +910,7 @@ extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, in
 }
 
 static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
-                         const dg_conv_params* p, void* stream, bool dry) {
+                         const dg_conv_params* p, void* stream, bool dry, float* bn_partials = nullptr, int* bn_blocks = nullptr) {
   DG_REQUIRE(dg_valid(x) && dg_valid(y) && w_packed && p, "dg_umma_conv2d_fwd: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
   DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
@@ -754,13 +934,20 @@ static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, 
       }
   }
   return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
-                     p->act, p->act_alpha, (cudaStream_t)stream, dry);
+                     p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks);
 }
 
 extern "C" int dg_umma_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias,
                                   const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream) {
-  DG_REQUIRE(bn_partials == nullptr, "dg_umma_conv2d_fwd: fused BN partials not available in this build");
-  return conv_fwd_impl(ctx, x, w_packed, bias, y, p, stream, false);
+  return conv_fwd_impl(ctx, x, w_packed, bias, y, p, stream, false, bn_partials);
+}
+
+// Number of per-CTA partial rows ([rows][2][Cout] floats) dg_umma_conv2d_fwd writes into `bn_partials` for this layer,
+// or 0 when the layer does not run the staged epilogue (the caller then issues dg_bn_stats).
+extern "C" int dg_umma_conv2d_fwd_bn_blocks(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p) {
+  int blocks = 0;
+  if (conv_fwd_impl(ctx, x, (const void*)1, nullptr, y, p, nullptr, true, nullptr, &blocks) != 0) return 0;
+  return blocks;
 }
 
 // 1 when the tensor-core kernel has a tile configuration for this layer (shared-memory fit), else 0

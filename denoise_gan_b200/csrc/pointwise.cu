@@ -486,6 +486,20 @@ extern "C" int dg_bn_stats(dg_ctx* ctx, const dg_tensor* x, const float* gamma, 
   return 0;
 }
 
+// Second half of dg_bn_stats for statistics whose per-block partials [nblocks][2][C] (sum, sum of squares) were produced
+// by the convolution epilogue (dg_umma_conv2d_fwd with bn_partials): fixed-order double-precision sum, scale/shift,
+// saved mean / invstd and the moving-statistics update.  `pixels` = N*H*W of the normalised tensor.
+extern "C" int dg_bn_finalize(dg_ctx* ctx, const float* partials, int nblocks, long long pixels, int c, const float* gamma,
+                              const float* beta, float eps, float momentum, float* moving_mean, float* moving_var, float* scale,
+                              float* shift, float* save_mean, float* save_invstd, void* stream) {
+  DG_REQUIRE(partials && nblocks > 0 && pixels > 0 && c > 0 && gamma && beta && scale && shift && save_mean && save_invstd,
+             "dg_bn_finalize: null argument");
+  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, ST>>>(partials, nblocks, (long)pixels, c, gamma, beta, eps, momentum, moving_mean,
+                                                     moving_var, scale, shift, save_mean, save_invstd);
+  DG_CHECK_LAUNCH("dg_bn_finalize");
+  return 0;
+}
+
 extern "C" int dg_bn_infer_affine(dg_ctx* ctx, int c, const float* gamma, const float* beta, const float* moving_mean,
                                   const float* moving_var, float eps, float* scale, float* shift, void* stream) {
   DG_REQUIRE(c > 0 && gamma && beta && moving_mean && moving_var && scale && shift, "dg_bn_infer_affine: null argument");

@@ -30,10 +30,11 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq")
+    __slots__ = ("t", "deps", "seq", "bn_part")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
+        self.bn_part = None     # (partials [blocks,2,C], blocks) when the producing conv reduced the BatchNorm statistics
 
     @property
     def shape(self):
@@ -90,6 +91,7 @@ class Engine:
         self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
         self.use_umma_wgrad = self.use_umma
         self.fuse_bn_fwd = os.environ.get("DG_BN_FUSED_FWD", "0") == "1"   # one-launch BN forward: measured 1 % slower in the step graph
+        self.fuse_conv_bn_stats = os.environ.get("DG_CONV_BN_STATS", "1") != "0"   # BN batch statistics from the conv epilogue
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
         # dgrad / BatchNorm chain of the backward pass (joined at the end of backward())
         self.wgrad_overlap = os.environ.get("DG_WGRAD_OVERLAP", "1") != "0"
@@ -356,8 +358,9 @@ class Engine:
         return out
 
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
-               out_dtype=None) -> Var:
-        """keras Conv2D (+bias, +activation epilogue)."""
+               out_dtype=None, bn: bool = False) -> Var:
+        """keras Conv2D (+bias, +activation epilogue).  `bn=True`: a training-mode BatchNormalization consumes the result
+        next, so the tensor-core epilogue also produces its batch-statistics partials (picked up by bn_act)."""
         N, H, W, Cin = x.shape
         kh, kw, cin, cout = w.shape
         assert cin == Cin, f"{w.name}: Cin {cin} != input {Cin}"
@@ -377,14 +380,24 @@ class Engine:
         tx, ty = tensor(x.t), tensor(y)
         bias = _lib.ptr(b.data) if b is not None else None
         flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
+        bn_part = None
         if umma_f:
             pk = self._packed(w, 0)
+            if bn and self.fuse_conv_bn_stats and act is None:
+                key = ("bnblk", N, H, W, cin, Ho, Wo, cout, kh, kw, stride, pt, pl)
+                blocks = self._cap.get(key)
+                if blocks is None:
+                    blocks = int(self.lib.dg_umma_conv2d_fwd_bn_blocks(self.ctx, C.byref(tx), C.byref(ty), C.byref(cp)))
+                    self._cap[key] = blocks
+                if blocks > 0:
+                    bn_part = (self.buf((seq, "bn_part"), (blocks, 2, cout), torch.float32), blocks)
             self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
-                self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), None, self.st)))
+                self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), _lib.ptr(bn_part[0]) if bn_part else None, self.st)))
         else:
             self._timed("simt_conv", flops, lambda: check(self.lib.dg_conv2d_fwd(
                 self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st)))
         out = Var(y, self._deps([x], w.group), seq)
+        out.bn_part = bn_part
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag):
             dpre = gy
@@ -620,7 +633,13 @@ class Engine:
         drop = 1 if (dropout_seed is not None and training) else 0
         a_code = ACT["prelu"] if prelu is not None else ACT[act]
         fused = False
-        if training and not self.fuse_bn_fwd:
+        bn_part = getattr(x, "bn_part", None)
+        if training and bn_part is not None:
+            # the producing convolution already reduced the batch statistics to per-CTA partials
+            check(self.lib.dg_bn_finalize(self.ctx, bn_part[0].data_ptr(), bn_part[1], x.shape[0] * x.shape[1] * x.shape[2], Cc,
+                                          gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum), mm.data.data_ptr(),
+                                          mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), self.st))
+        elif training and not self.fuse_bn_fwd:
             check(self.lib.dg_bn_stats(self.ctx, C.byref(tx), gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
                                        mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                                        invstd.data_ptr(), ws.data_ptr(), nbytes, self.st))

@@ -31,15 +31,15 @@ class SRGANGenerator(_Net):
 
     def __call__(self, x, training=True) -> Var:
         E, p = self.E, self.p
-        n = E.conv2d(self._in(x), p["g/conv_in/kernel"])
+        n = E.conv2d(self._in(x), p["g/conv_in/kernel"], bn=training)
         n = E.bn_act(n, p, "g/bn_in", training=training, prelu=p["g/prelu_in/alpha"])
         temp = E.mark("g/prelu_in", n)
         for i in range(16):
-            nn = E.conv2d(n, p[f"g/res{i}/conv1/kernel"])
+            nn = E.conv2d(n, p[f"g/res{i}/conv1/kernel"], bn=training)
             nn = E.bn_act(nn, p, f"g/res{i}/bn1", training=training, act="relu")
-            nn = E.conv2d(nn, p[f"g/res{i}/conv2/kernel"])
+            nn = E.conv2d(nn, p[f"g/res{i}/conv2/kernel"], bn=training)
             n = E.mark(f"g/res{i}/add", E.bn_act(nn, p, f"g/res{i}/bn2", training=training, residual=n))
-        n2 = E.conv2d(n, p["g/conv_post/kernel"])
+        n2 = E.conv2d(n, p["g/conv_post/kernel"], bn=training)
         n = E.mark("g/post_add", E.bn_act(n2, p, "g/bn_post", training=training, residual=temp))
         for j in range(self.scale // 2):
             u = E.conv2d(n, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"])
@@ -64,7 +64,7 @@ class PatchDiscriminator(_Net):
             if i == 1:
                 d = E.conv2d(d, w, b, stride=s, act="lrelu", alpha=0.2)
             else:
-                d = E.conv2d(d, w, b, stride=s)
+                d = E.conv2d(d, w, b, stride=s, bn=training)
                 d = E.bn_act(d, p, f"{px}/bn{i}", training=training, momentum=0.8, act="lrelu", alpha=0.2)
             E.mark(f"{px}/lrelu{i}", d)
         return E.conv2d(d, p[f"{px}/logits/kernel"], p[f"{px}/logits/bias"], act="sigmoid" if self.sigmoid else None,

@@ -81,6 +81,11 @@ int dg_umma_pack_weights(dg_ctx*, const float* w_hwio, void* packed, int kh, int
 int dg_umma_pack_weights_batch(dg_ctx*, const void* table_dev, int n_entries, void* stream);
 int dg_umma_conv2d_fwd(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias,
                        const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream);
+/* bn_partials (may be NULL): when a BatchNormalization follows the conv (srgan.py:154-155,162-163,247-248), the conv
+ * epilogue also accumulates the batch statistics of the values it stores and writes one row [2][Cout] (sum, sum of
+ * squares) per CTA; dg_umma_conv2d_fwd_bn_blocks() gives the row count (0: layer not eligible, call dg_bn_stats),
+ * dg_bn_finalize() turns the rows into scale/shift/mean/invstd and updates the moving statistics. */
+int dg_umma_conv2d_fwd_bn_blocks(dg_ctx*, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p);
 int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,
                          const dg_tensor* dx, const dg_conv_params* p, void* stream);
 /* capability queries: 1 when the tensor-core kernels have a tile configuration for the layer (shared-memory fit);
@@ -109,6 +114,9 @@ size_t dg_bn_workspace_bytes(const dg_tensor* x);
 int dg_bn_stats(dg_ctx*, const dg_tensor* x, const float* gamma, const float* beta, float eps, float momentum,
                 float* moving_mean, float* moving_var, float* scale, float* shift, float* save_mean,
                 float* save_invstd, void* workspace, size_t workspace_bytes, void* stream);
+int dg_bn_finalize(dg_ctx*, const float* partials, int nblocks, long long pixels, int c, const float* gamma, const float* beta,
+                   float eps, float momentum, float* moving_mean, float* moving_var, float* scale, float* shift,
+                   float* save_mean, float* save_invstd, void* stream);
 /* inference: scale/shift from the moving statistics */
 int dg_bn_infer_affine(dg_ctx*, int c, const float* gamma, const float* beta, const float* moving_mean,
                        const float* moving_var, float eps, float* scale, float* shift, void* stream);

@@ -665,3 +665,60 @@ def test_umma_wgrad_k4s2_one_launch_per_source(N, H, cin, cout):
     b = torch.zeros(cout, requires_grad=True)
     OT.conv2d(x0.float(), w, b, stride=2).backward(dy0.float())
     assert relerr(dw.cpu(), w.grad) < 2e-2 and relerr(db.cpu(), b.grad) < 2e-2
+
+
+# ---------------------------------------------------------------- staged (TMA-store) epilogue + fused BatchNorm statistics
+@pytest.mark.parametrize("case", [(3, 1, 64, 64, 2, 24, 20), (3, 1, 64, 64, 16, 96, 96), (3, 1, 32, 32, 3, 40, 24), (3, 2, 32, 32, 2, 48, 40),
+                                  (3, 1, 32, 64, 2, 33, 19), (3, 2, 64, 64, 2, 48, 16), (3, 1, 64, 16, 1, 20, 12), (1, 1, 192, 32, 2, 16, 16)])
+def test_umma_conv_fused_bn_partials_and_slice_output(L, case):
+    """dg_umma_conv2d_fwd with bn_partials: the per-CTA rows sum to the per-channel sum / sum of squares of the STORED
+    bf16 output (what dg_bn_stats would read), dg_bn_finalize reproduces dg_bn_stats, and the staged epilogue writes a
+    channel-slice view without touching its neighbours (srgan.py:154-155,247-248: Conv2D followed by BatchNormalization)."""
+    k, s, cin, cout, N, H, W = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * (1.0 / (k * np.sqrt(cin))))
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    y_ref = OT.conv2d(x, w, b, stride=s, padding="same")
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, s, H, W, "same")
+    xd, wd, bd = dev(x, torch.bfloat16), dev(w), dev(b)
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 0, st))
+    Ho, Wo = y_ref.shape[1], y_ref.shape[2]
+    # output = channels [16, 16+cout) of a wider tensor pre-filled with a sentinel
+    ybig = torch.full((N, Ho, Wo, cout + 32), 7.0, device="cuda", dtype=torch.bfloat16)
+    tx, ty = L.tensor(xd), L.tensor(ybig, c=cout, coff=16)
+    blocks = lib.dg_umma_conv2d_fwd_bn_blocks(ctx, C.byref(tx), C.byref(ty), C.byref(cp))
+    if blocks == 0:
+        assert (k, s, cin, cout) == (3, 2, 64, 64), "this layer is expected to run the staged epilogue"
+        pytest.skip("four parity halos + resident weights leave no room for the staging buffers: the engine calls dg_bn_stats")
+    part = torch.full((blocks, 2, cout), float("nan"), device="cuda")
+    L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), part.data_ptr(), st))
+    torch.cuda.synchronize()
+    y = ybig[..., 16:16 + cout]
+    assert relerr(y, y_ref) < BF16_TOL
+    assert torch.all(ybig[..., :16] == 7.0) and torch.all(ybig[..., 16 + cout:] == 7.0), "staged store wrote outside its channel slice"
+    yd = y.double()
+    sums = part.double().sum(0).cpu()
+    ref_s, ref_q = yd.sum((0, 1, 2)).cpu(), (yd * yd).sum((0, 1, 2)).cpu()
+    assert ((sums[0] - ref_s).abs().max() / ref_q.sqrt().max()).item() < 1e-5
+    assert ((sums[1] - ref_q).abs().max() / ref_q.max()).item() < 1e-5
+    # finalize == dg_bn_stats on the stored tensor
+    gamma, beta = dev(torch.rand(cout, generator=g) + 0.5), dev(torch.randn(cout, generator=g))
+    outs = []
+    for fused in (True, False):
+        mm, mv = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+        sc, sh, mean, inv = (torch.empty(cout, device="cuda") for _ in range(4))
+        if fused:
+            L.check(lib.dg_bn_finalize(ctx, part.data_ptr(), blocks, N * Ho * Wo, cout, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
+                                       mm.data_ptr(), mv.data_ptr(), sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), inv.data_ptr(), st))
+        else:
+            yc = y.contiguous(); tyc = L.tensor(yc)
+            nb = lib.dg_bn_workspace_bytes(C.byref(tyc)); wk = ws(nb)
+            L.check(lib.dg_bn_stats(ctx, C.byref(tyc), gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99, mm.data_ptr(), mv.data_ptr(),
+                                    sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), inv.data_ptr(), wk.data_ptr(), nb, st))
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (sc, sh, mean, inv, mm, mv)])
+    for a, b_ in zip(*outs):
+        assert relerr(a, b_) < 1e-5
