@@ -40,35 +40,64 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: in-process NVML (initialised BEFORE the timed
+    region; a query costs microseconds), falling back to spawning nvidia-smi.  Spawning nvidia-smi inside the region was
+    measured to disturb it: each start-up initialises NVML against the driver and stalled the host-synchronous
+    end-to-end loop by milliseconds per step on some boxes."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+        for n, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(n)
+
+    def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant family's most frequent launch (64->64 3x3 conv of the

@@ -57,6 +57,11 @@ struct UmmaConvParams {
   int split;        // 1: one SOURCE per pipeline stage (halo box + the weights of that source's taps): big stride-2 layers
   int src_tap0[MAX_SRC], src_ntaps[MAX_SRC];   // taps are sorted by source
   uint32_t src_tx[MAX_SRC];
+  // K-outer mode for streamed weights: an output tile is P.mt sub-tiles of 16x8 pixels, each with its OWN halo stage, and
+  // the loop order is chunk-outer / sub-tile-inner, so that a weight chunk (all taps), streamed through a two-slot ring
+  // of its own, is loaded once per P.mt sub-tiles instead of once per 128 pixels
+  int kouter;
+  uint32_t wslot_bytes, wslot_tx;
   int nbuf_shift;   // log2 of the TMEM accumulator buffers: 2 (four buffers, TWO issuing warps on alternate tiles) or 1
   void* out;
   long out_sn, out_sh, out_sw;
@@ -72,7 +77,7 @@ struct UmmaConvParams {
   int act;
   float alpha;
   uint32_t layout, idesc;
-  int dbg_flags;   // debug experiments (tools/conv_timeline.py): 1 no stores, 2 no epilogue work, 4 no TMA reloads, 8 unshifted taps
+  int dbg_flags;   // debug experiments (tools/conv_timeline.py): 1 no stores, 2 no epilogue work, 4 no TMA reloads, 8 unshifted taps; 16 (host) force K-outer
   long long* dbg;  // optional per-role timeline of CTA 0 (tools/conv_timeline.py); nullptr in production
 };
 
@@ -326,7 +331,7 @@ __device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int t0, int
 __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
-  __shared__ __align__(8) uint64_t bar_acc_full[4], bar_acc_empty[4], bar_w;
+  __shared__ __align__(8) uint64_t bar_acc_full[4], bar_acc_empty[4], bar_w, bar_wf[2], bar_we[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[256];
 
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   }
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
-  const uint32_t stage_base = base + (P.resident ? P.w_res_bytes : 0u);
+  const uint32_t stage_base = base + (P.resident ? P.w_res_bytes : (P.kouter ? 2u * P.wslot_bytes : 0u));
   const int nb0 = blockIdx.y * P.nb;
   const int total_tiles = P.n_img * P.tiles_h * P.tiles_w;
 
@@ -354,6 +359,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       mbar_init(smem_u32(&bar_acc_empty[b]), 4);
     }
     mbar_init(smem_u32(&bar_w), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_wf[b]), 1);
+      mbar_init(smem_u32(&bar_we[b]), 1);
+    }
     fence_mbar_init();
     // the resident weights start loading before the CTA-wide sync, under the TMEM allocation of warp 1
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
@@ -387,6 +396,31 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       // exactly one producer/consumer pair walking consecutive phases.
       const int n_iss = P.nbuf_shift == 2 ? 2 : 1, half = P.n_stages / n_iss;
       int it = 0;
+      if (P.kouter) {
+        uint32_t wj = 0, aj = 0;     // weight-slot and halo-stage sequence numbers
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h, n = t2 / P.tiles_h;
+          const int h0 = th * 16 * P.mt, w0 = tw * 8;
+          for (int kc = 0; kc < P.n_chunks; ++kc) {
+            const uint32_t ws = wj & 1u, wfull = smem_u32(&bar_wf[ws]);
+            mbar_wait(smem_u32(&bar_we[ws]), ((wj >> 1) & 1u) ^ 1u);
+            mbar_expect_tx(wfull, P.wslot_tx);
+            for (int t = 0; t < P.n_taps; ++t)
+              tma_load_2d(w_base + ws * P.wslot_bytes + (uint32_t)t * P.w_block_bytes, &P.wmap, wfull, 0,
+                          (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
+            ++wj;
+            for (int m = 0; m < P.mt; ++m, ++aj) {
+              const int stage = (int)(aj % (uint32_t)P.n_stages);
+              const uint32_t full = smem_u32(&bar_a_full[stage]);
+              mbar_wait(smem_u32(&bar_a_empty[stage]), ((aj / (uint32_t)P.n_stages) & 1u) ^ 1u);
+              mbar_expect_tx(full, P.stage_tx);
+              const uint32_t sa = stage_base + (uint32_t)stage * P.stage_bytes;
+              for (int s = 0; s < P.n_src; ++s)
+                tma_load_4d(sa + P.src_off[s], &P.src[s], full, kc * P.kc, w0 + P.src_w0[s], h0 + 16 * m + P.src_h0[s], n);
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         int tw = tile % P.tiles_w;
         int t2 = tile / P.tiles_w;
@@ -454,6 +488,42 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       // refill every 128-pixel tile: ~500 of 2700 cycles on the 64-channel layers, tools/conv_timeline.py).
       const int n_issuers = P.nbuf_shift == 2 ? 2 : 1;
       const int me = warp == 1 ? 0 : 1;
+      if (P.kouter) {
+        if (me == 0) {
+          uint32_t wj = 0, aj = 0;
+          const uint32_t wslot16 = P.wslot_bytes >> 4;
+          int it = 0;
+          for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            mbar_wait(smem_u32(&bar_acc_empty[b]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            for (int kc = 0; kc < n_chunks; ++kc, ++wj) {
+              const uint32_t ws = wj & 1u;
+              mbar_wait(smem_u32(&bar_wf[ws]), (wj >> 1) & 1u);
+              const uint32_t b_lo = wres16 + ws * wslot16;
+              for (int m = 0; m < mt; ++m, ++aj) {
+                const int stage = (int)(aj % (uint32_t)n_stages);
+                mbar_wait(smem_u32(&bar_a_full[stage]), (aj / (uint32_t)n_stages) & 1u);
+                tc_fence_after();
+                const uint32_t sa16 = sbase16 + (uint32_t)stage * stage16;
+                const uint32_t acc0 = tmem + (uint32_t)(b * mt + m) * nb;
+                if (elect_one()) {
+#define DG_ISSUE_K(NBK_) \
+  { if (n_taps == 9) issue_stage<1, NBK_, 9>(P, 0, 9, sa16, b_lo, wblk16, b_hi, acc0, nb, idesc, kc != 0); \
+    else if (n_taps == 4) issue_stage<1, NBK_, 4>(P, 0, 4, sa16, b_lo, wblk16, b_hi, acc0, nb, idesc, kc != 0); \
+    else issue_stage<1, NBK_, 0>(P, 0, n_taps, sa16, b_lo, wblk16, b_hi, acc0, nb, idesc, kc != 0); }
+                  if (nbk == 4) DG_ISSUE_K(4) else if (nbk == 2) DG_ISSUE_K(2) else DG_ISSUE_K(1)
+#undef DG_ISSUE_K
+                  umma_commit(smem_u32(&bar_a_empty[stage]));
+                  if (m == mt - 1) umma_commit(smem_u32(&bar_we[ws]));
+                  if (m == mt - 1 && kc == n_chunks - 1) umma_commit(smem_u32(&bar_acc_full[b]));
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+      } else
       if (me < n_issuers)
       for (int it = me, tile = blockIdx.x + me * (int)gridDim.x; tile < total_tiles; tile += n_issuers * (int)gridDim.x, it += n_issuers) {
         const int b = it & ((1 << P.nbuf_shift) - 1);
@@ -716,19 +786,61 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
         }
   }
   DG_REQUIRE(best_nb > 0, "%s: no tile configuration fits shared memory (Cin=%d Cout=%d taps=%d)", name, in->c, cout, n_taps);
+  auto r1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  // K-outer mode (streamed weights, several chunks): weight chunks go through a two-slot ring of their own and are reused
+  // by `kouter` 16x8 sub-tiles; chosen when the predicted shared-memory fill traffic per CTA drops by >= 10 %
+  int kouter = 0;
+  {
+    // Cost model (cycles per CTA, MMA issue + shared-memory fill, shallow pipelines make them roughly additive):
+    // a 128 x nb x 16 MMA occupies the tensor pipe max(nb/2, 32 + nb/4, 44) cycles (probes/umma_probe.cu t2_*), and with
+    // every SM pulling at once L2 delivers ~19 B/clk/SM (5.6 TB/s).  The streamed K-outer configuration competes with
+    // whatever the search above picked -- including RESIDENT weights bought with a narrow N block (256->64 dgrad ran as
+    // two 32-channel blocks: 44-cycle MMAs for half the work and the input read twice).
+    static const char* dbg_no_ko = getenv("DG_DEBUG_NO_KOUTER");   // experiments only
+    if (!split && n_chunks >= 2 && !dbg_no_ko) {
+      auto cyc = [](int nb_) { int c = nb_ / 2 > 32 + nb_ / 4 ? nb_ / 2 : 32 + nb_ / 4; return (double)(c < 44 ? 44 : c); };
+      auto rounds = [&](int mt_, int nb_) {
+        long t = (long)in->n * ((out_h + 16 * mt_ - 1) / (16 * mt_)) * ((out_w + 7) / 8), c = ctx->sm_count / (cout / nb_);
+        c = c < 1 ? 1 : (c > t ? t : c);
+        return (double)((t + c - 1) / c);
+      };
+      const double kk = (double)n_chunks * n_taps * (kc / 16);
+      const uint32_t h1 = halo_bytes(1);
+      const double cur = rounds(best_mt, best_nb) * (best_mt * kk * cyc(best_nb) +
+                                                     n_chunks * ((double)halo_bytes(best_mt) + (best_res ? 0.0 : (double)n_taps * best_nb * kc * 2)) / 19.0);
+      double best_cost = (g_dbg_flags & 16) ? 1e30 : 0.85 * cur;   // flag 16 (tests): K-outer whenever it fits
+      int k_nb = 0;
+      for (int nbk = cout > 256 ? 256 : cout; nbk >= best_nb && nbk >= 16; nbk -= 16) {
+        if (cout % nbk != 0) continue;
+        const uint32_t wchunk = (uint32_t)n_taps * nbk * kc * 2;
+        if (2 * r1k(wchunk) + 3 * r1k(h1) > budget) continue;
+        for (int mtk = 4; mtk >= 2; mtk -= 2) {
+          if (2 * mtk * nbk > 512) continue;
+          // three halo stages + the weight ring overlap fill and issue: measured ~1.2 x max(issue, fill) (256->64 dgrad at 192^2)
+          const double mma = mtk * kk * cyc(nbk), fill = n_chunks * ((double)wchunk + (double)mtk * h1) / 19.0;
+          const double c = rounds(mtk, nbk) * 1.2 * (mma > fill ? mma : fill);
+          if (c < best_cost) { best_cost = c; kouter = mtk; k_nb = nbk; }
+        }
+      }
+      if (kouter) { best_mt = kouter; best_nb = k_nb; best_res = 0; }
+    }
+  }
   const int nb = best_nb, mt = best_mt;
-  P.nb = nb; P.mt = mt; P.resident = best_res; P.split = split;
+  const int hmt = kouter ? 1 : mt;     // sub-tiles covered by ONE halo box
+  P.nb = nb; P.mt = mt; P.resident = best_res; P.split = split; P.kouter = kouter;
+  P.wslot_tx = (uint32_t)n_taps * nb * kc * 2;
+  P.wslot_bytes = r1k(P.wslot_tx);
+  const uint32_t ring_bytes = kouter ? 2u * P.wslot_bytes : 0u;
 
   // pipeline depth, and whether the staged (shared memory + TMA store) epilogue fits next to it
-  auto r1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
   const uint32_t stage_bytes_pre = split ? r1k(max_halo(mt) + (uint32_t)max_ntaps * nb * kc * 2)
-                                         : r1k(halo_bytes(mt) + (best_res ? 0u : (uint32_t)n_taps * nb * kc * 2));
+                                         : r1k(halo_bytes(hmt) + ((best_res || kouter) ? 0u : (uint32_t)n_taps * nb * kc * 2));
   const uint32_t w_res_pre = best_res ? r1k((uint32_t)n_taps * n_chunks * nb * kc * 2) : 0u;
-  int n_stages = (int)((budget - w_res_pre) / stage_bytes_pre);
+  int n_stages = (int)((budget - w_res_pre - ring_bytes) / stage_bytes_pre);
   if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
   DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
   static const char* dbg_no_ts = getenv("DG_DEBUG_NO_TSTORE");   // experiments only
-  bool ts = (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64);
+  bool ts = !kouter && (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64);
   const uint32_t stg_bytes = (uint32_t)mt * 128u * (uint32_t)nb * 2u;
   if (ts) {
     const long room = (long)budget - (long)w_res_pre - 2L * (long)stg_bytes;
@@ -758,7 +870,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   uint32_t off = 0, tx = 0;
   for (int s = 0; s < n_src; ++s) {
     const Lattice& L = src_lat[s];
-    const int HH = 16 * mt + dh_max[s] - dh_min[s], WW = 8 + dw_max[s] - dw_min[s];
+    const int HH = 16 * hmt + dh_max[s] - dh_min[s], WW = 8 + dw_max[s] - dw_min[s];
     DG_REQUIRE(HH <= 256 && WW <= 256, "%s: halo box too large", name);
     const int vh = (in->h - L.h_first + L.step - 1) / L.step, vw = (in->w - L.w_first + L.step - 1) / L.step;
     DG_REQUIRE(vh > 0 && vw > 0, "%s: empty source view", name);
@@ -777,7 +889,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     off += (hb + 1023u) & ~1023u;
   }
   P.w_stage_off = off;
-  if (!best_res) { off += (uint32_t)n_taps * P.w_block_bytes; tx += (uint32_t)n_taps * P.w_block_bytes; }
+  if (!best_res && !kouter) { off += (uint32_t)n_taps * P.w_block_bytes; tx += (uint32_t)n_taps * P.w_block_bytes; }
   P.stage_bytes = (off + 1023u) & ~1023u;
   P.stage_tx = tx;
   if (split) {
@@ -799,7 +911,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   {
     // two issuing warps need four TMEM accumulator buffers and at least two pipeline slots each
     static const char* dbg_single = getenv("DG_DEBUG_SINGLE_ISSUER");   // experiments only
-    P.nbuf_shift = (4 * mt * nb <= 512 && n_stages >= 4 && !dbg_single) ? 2 : 1;
+    P.nbuf_shift = (4 * mt * nb <= 512 && n_stages >= 4 && !dbg_single && !kouter) ? 2 : 1;
     if (P.nbuf_shift == 2) n_stages &= ~1;
   }
   P.n_stages = n_stages;
@@ -831,7 +943,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.dbg = g_dbg_timeline;
   P.dbg_flags = g_dbg_flags;
 
-  P.stg_off = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes;
+  P.stg_off = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes;
   if (ts) {
     // output view as a 4-D tensor map (C, W, H, N); one box = the CTA's tile, clipped at the image border by the TMA unit
     uint64_t dims[4] = {(uint64_t)out->c, (uint64_t)out->w, (uint64_t)out->h, (uint64_t)out->n};
@@ -839,7 +951,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     uint32_t box[4] = {(uint32_t)nb, 8u, (uint32_t)(16 * mt), 1u};
     if (encode_map(ctx, &P.omap, (char*)out->ptr + (size_t)out->coff * 2, 4, dims, strides, box, nb)) return 1;
   }
-  const uint32_t smem = P.w_res_bytes + (uint32_t)n_stages * P.stage_bytes + (ts ? 2u * stg_bytes : 0u) + 1024;
+  const uint32_t smem = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes + (ts ? 2u * stg_bytes : 0u) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);
@@ -848,6 +960,13 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   }
   const int n_blocks = cout / nb;
   const int total_tiles = P.n_img * P.tiles_h * P.tiles_w;
+  {
+    static const char* dbg_cfg = getenv("DG_DEBUG_CONFIG");   // prints the tile configuration of every launch
+    if (dbg_cfg)
+      fprintf(stderr, "[%s] %dx%dx%d c%d->%d taps %d src %d: nb %d mt %d kc %d chunks %d resident %d split %d kouter %d stages %d x %u B, issuers %d, tstore %d, smem %u\n",
+              name, out->n, out_h, out_w, in->c, cout, n_taps, n_src, nb, mt, kc, n_chunks, best_res, split, kouter, n_stages, P.stage_bytes,
+              P.nbuf_shift == 2 ? 2 : 1, P.tstore, smem);
+  }
   int ctas = ctx->sm_count / n_blocks;
   if (ctas < 1) ctas = 1;
   if (ctas > total_tiles) ctas = total_tiles;

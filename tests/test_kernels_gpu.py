@@ -722,3 +722,45 @@ def test_umma_conv_fused_bn_partials_and_slice_output(L, case):
         outs.append([t.clone() for t in (sc, sh, mean, inv, mm, mv)])
     for a, b_ in zip(*outs):
         assert relerr(a, b_) < 1e-5
+
+
+# ---------------------------------------------------------------- K-outer mode (streamed weights reused by several sub-tiles)
+@pytest.mark.parametrize("case", [(3, 256, 64, 2, 70, 20, "dgrad"), (3, 256, 64, 1, 64, 24, "fwd"), (3, 128, 256, 2, 40, 17, "fwd"),
+                                  (3, 256, 256, 1, 48, 16, "fwd"), (1, 512, 64, 2, 33, 9, "fwd"), (3, 192, 96, 1, 30, 30, "dgrad")])
+def test_umma_conv_k_outer_weight_ring(L, case):
+    """The chunk-outer / sub-tile-inner loop order with its two-slot weight ring (conv_umma.cu `kouter`), forced through
+    the debug flag so that small shapes take it: partial tiles in both directions, several N blocks, 2-8 chunks.
+    (In production the cost model picks it for e.g. the 256->64 dgrad of the generator's upsampling conv, srgan.py:144.)"""
+    k, cin, cout, N, H, W, kind = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * (1.0 / (k * np.sqrt(cin))))
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same")
+    wd = dev(w)
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 0 if kind == "fwd" else 1, st))
+    lib.dg_debug_conv_flags(16)
+    try:
+        if kind == "fwd":
+            x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+            b = torch.randn(cout, generator=g, dtype=torch.float64)
+            ref = OT.conv2d(x, w, b, stride=1, padding="same")
+            y = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+            xd, bd = dev(x, torch.bfloat16), dev(b)
+            tx, ty = L.tensor(xd), L.tensor(y)
+            L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), None, st))
+            out = y
+        else:
+            xr = torch.zeros(N, H, W, cin, dtype=torch.float64, requires_grad=True)
+            gy = _bf16_round(torch.randn(N, H, W, cout, generator=g, dtype=torch.float64))
+            (OT.conv2d(xr, w, None, stride=1, padding="same") * gy).sum().backward()
+            ref = xr.grad
+            dx = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+            gyd = dev(gy, torch.bfloat16)
+            tg, tdx = L.tensor(gyd), L.tensor(dx)
+            L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tg), pk.data_ptr(), None, C.byref(tdx), C.byref(cp), st))
+            out = dx
+        torch.cuda.synchronize()
+    finally:
+        lib.dg_debug_conv_flags(0)
+    assert relerr(out, ref) < BF16_TOL

@@ -29,6 +29,25 @@ CASES = {
     "d2_fwd_s2": ("fwd", 16, 384, 384, 32, 32, 3, 2),
     "d3_wgrad": ("wgrad", 16, 192, 192, 32, 32, 3, 1),
     "vgg_256": ("fwd", 16, 96, 96, 256, 256, 3, 1),
+    "up1_dgrad": ("dgrad", 16, 96, 96, 64, 256, 3, 1),
+    "up1_wgrad": ("wgrad", 16, 96, 96, 64, 256, 3, 1),
+    "d3_dgrad": ("dgrad", 16, 192, 192, 32, 32, 3, 1),
+    "d2_dgrad_s2": ("dgrad", 16, 384, 384, 32, 32, 3, 2),
+    "d2_wgrad_s2": ("wgrad", 16, 384, 384, 32, 32, 3, 2),
+    "d5_fwd": ("fwd", 16, 96, 96, 32, 64, 3, 1),
+    "d1_fwd": ("fwd", 16, 384, 384, 16, 32, 3, 1),
+    "d1_dgrad": ("dgrad", 16, 384, 384, 16, 32, 3, 1),
+    "d1_wgrad": ("wgrad", 16, 384, 384, 16, 32, 3, 1),
+    "gout_fwd": ("fwd", 16, 384, 384, 64, 16, 1, 1),
+    "gout_dgrad": ("dgrad", 16, 384, 384, 64, 16, 1, 1),
+    "gout_wgrad": ("wgrad", 16, 384, 384, 64, 16, 1, 1),
+    "gin_fwd": ("fwd", 16, 96, 96, 16, 64, 3, 1),
+    "gin_wgrad": ("wgrad", 16, 96, 96, 16, 64, 3, 1),
+    "d4_fwd_s2": ("fwd", 16, 192, 192, 32, 32, 3, 2),
+    "d4_dgrad_s2": ("dgrad", 16, 192, 192, 32, 32, 3, 2),
+    "d7_fwd": ("fwd", 16, 48, 48, 64, 64, 3, 1),
+    "d7_wgrad": ("wgrad", 16, 48, 48, 64, 64, 3, 1),
+    "d6_fwd_s2": ("fwd", 16, 96, 96, 64, 64, 3, 2),
 }
 
 
@@ -37,6 +56,7 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sets", type=int, default=6)
+    ap.add_argument("--graph", type=int, default=1, help="1: time a CUDA graph of the launches (no host launch gaps), 0: eager launches")
     args = ap.parse_args()
     lib = L.load(); ctx = L.ctx(0); st = L.stream_ptr()
     peak = 1393.4
@@ -62,21 +82,38 @@ def main():
         def run(i):
             tx, ty = L.tensor(xs[i % args.sets]), L.tensor(ys[i % args.sets])
             if kind == "fwd":
-                L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk0.data_ptr(), None, C.byref(ty), C.byref(cp), None, st))
+                L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk0.data_ptr(), None, C.byref(ty), C.byref(cp), None, L.stream_ptr()))
             elif kind == "dgrad":
-                L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(ty), pk1.data_ptr(), None, C.byref(tx), C.byref(cp), st))
+                L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(ty), pk1.data_ptr(), None, C.byref(tx), C.byref(cp), L.stream_ptr()))
             else:
-                L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(ty), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, st))
+                L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(ty), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, L.stream_ptr()))
 
         for i in range(3):
             run(i)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.iters):
-            run(i)
-        e1.record(); torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / args.iters
+        if args.graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run(0)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    for i in range(args.iters):
+                        run(i)
+            torch.cuda.current_stream().wait_stream(side)
+            gr.replay(); torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                gr.replay()
+            e1.record(); torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (5 * args.iters)
+        else:
+            e0.record()
+            for i in range(args.iters):
+                run(i)
+            e1.record(); torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / args.iters
         flops = 2.0 * N * Ho * Wo * k * k * cin * cout
         byts = 2.0 * N * (H * W * cin + Ho * Wo * cout)
         print(json.dumps({"case": name, "us": round(us, 2), "tflops": round(flops / us / 1e6, 1), "frac_of_bf16_peak": round(flops / us / 1e6 / peak, 3),
