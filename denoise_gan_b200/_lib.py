@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdg_b200.so")
+LIB_PATH = os.environ.get("DG_LIB_PATH") or os.path.join(_HERE, "libdg_b200.so")   # DG_LIB_PATH: A/B experiments against another build
 
 DG_F32, DG_BF16 = 0, 1
 ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4, "prelu": 5}

@@ -113,13 +113,13 @@ class FastSRGANGenerator(_Net):
         for i in range(self.n_blocks):
             t = r
             if i:
-                t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"])
+                t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"], bn=training)
                 t = E.bn_act(t, p, f"g/b{i}/expand_bn", training=training, momentum=0.999, act="relu")
             t = E.dwconv3x3(t, p[f"g/b{i}/dw/kernel"], p[f"g/b{i}/dw/bias"])
             t = E.bn_act(t, p, f"g/b{i}/dw_bn", training=training, momentum=0.999, act="relu")
-            t = E.conv2d(t, p[f"g/b{i}/project/kernel"], p[f"g/b{i}/project/bias"])
+            t = E.conv2d(t, p[f"g/b{i}/project/kernel"], p[f"g/b{i}/project/bias"], bn=training)
             r = E.bn_act(t, p, f"g/b{i}/project_bn", training=training, momentum=0.999, residual=r)
-        c2 = E.conv2d(r, p["g/c2/kernel"], p["g/c2/bias"])
+        c2 = E.conv2d(r, p["g/c2/kernel"], p["g/c2/bias"], bn=training)
         u = E.bn_act(c2, p, "g/c2_bn", training=training, residual=c1)
         for j in range(2):
             u = E.d2s_prelu(E.conv2d(u, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"]), p[f"g/up{j}/prelu/alpha"])
@@ -164,7 +164,7 @@ class Pix2PixGenerator(_Net):
             if i == 0:
                 t = E.conv2d(t, w, None, stride=2, act="lrelu", alpha=0.3)
             else:
-                t = E.conv2d(t, w, None, stride=2)
+                t = E.conv2d(t, w, None, stride=2, bn=training)
                 t = E.bn_act(t, p, f"g/down{i}/bn", training=training, act="lrelu", alpha=0.3)
             skips.append(t)
         skips = list(reversed(skips[:-1]))
@@ -186,8 +186,8 @@ class Pix2PixDiscriminator(_Net):
         t = E.concat([E.cast(self._in(inp), E.act_dtype), E.cast(self._in(tar), E.act_dtype)])
         t = E.conv2d(t, p["d/down1/conv/kernel"], None, stride=2, act="lrelu", alpha=0.3)
         for i in (2, 3):
-            t = E.conv2d(t, p[f"d/down{i}/conv/kernel"], None, stride=2)
+            t = E.conv2d(t, p[f"d/down{i}/conv/kernel"], None, stride=2, bn=training)
             t = E.bn_act(t, p, f"d/down{i}/bn", training=training, act="lrelu", alpha=0.3)
-        t = E.conv2d(t, p["d/conv4/kernel"], None, stride=1, padding=((1, 1), (1, 1)))
+        t = E.conv2d(t, p["d/conv4/kernel"], None, stride=1, padding=((1, 1), (1, 1)), bn=training)
         t = E.bn_act(t, p, "d/bn4", training=training, act="lrelu", alpha=0.3)
         return E.conv2d(t, p["d/last/kernel"], p["d/last/bias"], stride=1, padding=((1, 1), (1, 1)), out_dtype=torch.float32)
