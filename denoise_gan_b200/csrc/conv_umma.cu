@@ -37,7 +37,9 @@ using namespace sm100;
 constexpr int MAX_SRC = 4;
 constexpr int MAX_TAPS = 16;
 constexpr int MAX_STAGES = 6;
-constexpr int CONV_THREADS = 224;   // TMA producer, MMA issuer, 4 epilogue warps, second MMA issuer
+constexpr int CONV_THREADS = 352;   // TMA producer, MMA issuer, 4 epilogue warps (group 0), second MMA issuer, 4 epilogue warps (group 1)
+// The two epilogue groups take ALTERNATE tiles: one tile's TMEM -> registers -> shared memory -> store chain is a serial
+// latency chain of ~1500 cycles per 128 x 64 tile, longer than the MMAs of thin layers (1x1, 16/32-channel, K = 16 layers)
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 
 struct UmmaConvParams {
@@ -52,6 +54,11 @@ struct UmmaConvParams {
   int tap_src[MAX_TAPS], tap_w[MAX_TAPS];
   uint64_t tap_adesc[MAX_TAPS];   // complete A descriptor of the tap's window minus the stage base (added to the low word)
   uint32_t tap_ms16[MAX_TAPS];    // descriptor step between the m sub-tiles of the tap's source
+  // Output phases: a stride-2 dgrad / Conv2DTranspose computes its four output parity phases in ONE launch.  Every tap
+  // belongs to one phase; a phase has its own accumulator (column offset tap_acc) and its own output lattice offset.
+  int n_phase;
+  uint32_t tap_acc[MAX_TAPS], tap_first[MAX_TAPS];
+  long ph_off[4];
   uint32_t stage_bytes, stage_tx, w_stage_off, w_block_bytes, w_res_bytes, w_res_tx;
   int n_stages, resident, cout_total;
   int split;        // 1: one SOURCE per pipeline stage (halo box + the weights of that source's taps): big stride-2 layers
@@ -124,27 +131,28 @@ __device__ __forceinline__ void epi_store16(const uint32_t (&v)[16], const float
 
 template <int ACT, bool F32>
 __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t tmem, int q, int lane, int nb0, int total_tiles,
-                                              const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty) {
+                                              const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, int grp) {
   const int m_idx = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+  int it = grp;
+  for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     const int b = it & ((1 << P.nbuf_shift) - 1);
     const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
     const int tw = tile % P.tiles_w;
     const int t2 = tile / P.tiles_w;
     const int th = t2 % P.tiles_h;
     const int n = t2 / P.tiles_h;
-    if (q == 0 && lane == 0) dbg_mark(P, 2, it, 0);
+    if (q == 0 && lane == 0 && grp == 0) dbg_mark(P, 2, it >> 1, 0);
     mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
     tc_fence_after();
-    if (q == 0 && lane == 0) dbg_mark(P, 2, it, 1);
-    for (int m = 0; m < P.mt; ++m) {
+    if (q == 0 && lane == 0 && grp == 0) dbg_mark(P, 2, it >> 1, 1);
+    for (int pm = 0; pm < P.n_phase * P.mt; ++pm) {
+      const int phs = pm / P.mt, m = pm - phs * P.mt;
       const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
       const int pw = tw * 8 + (m_idx & 7);
       const bool valid = ph < P.out_h && pw < P.out_w;
-      const long pix = (long)n * P.out_sn + (long)ph * P.out_sh + (long)pw * P.out_sw + nb0;
-      const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.mt + m) * P.nb);
+      const long pix = (long)n * P.out_sn + (long)ph * P.out_sh + (long)pw * P.out_sw + nb0 + P.ph_off[phs];
+      const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.n_phase * P.mt + pm) * P.nb);
       int c0 = 0;
       for (; c0 + 32 <= P.nb; c0 += 32) {   // two 16-column loads in flight per wait
         uint32_t v0[16], v1[16];
@@ -167,7 +175,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
-    if (q == 0 && lane == 0) dbg_mark(P, 2, it, 2);
+    if (q == 0 && lane == 0 && grp == 0) dbg_mark(P, 2, it >> 1, 2);
   }
 }
 
@@ -208,7 +216,9 @@ __device__ __forceinline__ void epi_stage16(const uint32_t (&v)[16], const float
 template <int ACT>
 __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int nb0,
                                                  int total_tiles, const float* __restrict__ bs, uint64_t* bar_acc_full,
-                                                 uint64_t* bar_acc_empty, float* red_s) {
+                                                 uint64_t* bar_acc_empty, float* red_s, int grp) {
+  const uint32_t bar_id = 1u + (uint32_t)grp;   // named barrier of this group's 128 threads (3: both groups)
+#define DG_GROUP_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory")
   const int m_idx = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t RB = (uint32_t)P.nb * 2u, mask = P.stg_mask;
@@ -216,23 +226,23 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
   const int sub = lane / WPR, w = lane - sub * WPR;
   const bool leader = q == 0 && lane == 0;
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+  const uint32_t stg = stg_base + (uint32_t)grp * P.stg_bytes;   // one staging buffer per group
+  int it = grp;
+  for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     const int b = it & ((1 << P.nbuf_shift) - 1);
     const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
     const int tw = tile % P.tiles_w;
     const int t2 = tile / P.tiles_w;
     const int th = t2 % P.tiles_h;
     const int n = t2 / P.tiles_h;
-    const uint32_t stg = stg_base + (uint32_t)(it & 1) * P.stg_bytes;
     if (leader) {
-      dbg_mark(P, 2, it, 0);
-      tma_store_wait_read<1>();     // the store that read this buffer two tiles ago has left shared memory
+      if (grp == 0) dbg_mark(P, 2, it >> 1, 0);
+      tma_store_wait_read<0>();     // this group's previous store has left the buffer (it drained under the other group's tile)
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    DG_GROUP_SYNC();
     mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
     tc_fence_after();
-    if (leader) dbg_mark(P, 2, it, 1);
+    if (leader && grp == 0) dbg_mark(P, 2, it >> 1, 1);
     for (int m = 0; m < P.mt; ++m) {
       const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
       const int pw = tw * 8 + (m_idx & 7);
@@ -259,11 +269,11 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));   // the accumulator is free as soon as it is in registers
     fence_proxy_async();                                         // generic-proxy writes -> visible to the bulk store
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    DG_GROUP_SYNC();
     if (leader) {
       if (!(P.dbg_flags & 1)) tma_store_4d(&P.omap, stg, nb0, tw * 8, th * 16 * P.mt, n);
       tma_store_commit();
-      dbg_mark(P, 2, it, 2);
+      if (grp == 0) dbg_mark(P, 2, it >> 1, 2);
     }
     if (P.bn_partials) {
       const int iters = 32 / RPR;
@@ -282,26 +292,33 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
   }
   if (leader) tma_store_wait<0>();
   if (P.bn_partials) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // all stores have left the staging buffers: buffer 0 is the scratch of the final sum
+    asm volatile("bar.sync 3, 256;" ::: "memory");   // both groups: all stores have left the staging buffers, buffer 0 is the scratch of the final sum
     for (int o = WPR; o < 32; o <<= 1) {
       s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
     }
+    const int gw = grp * 4 + q;     // one row of the scratch per epilogue warp: [8][4][32] floats = 4 KB <= one staging buffer
     if (lane < WPR) {
-      red_s[(q * 4 + 0) * 32 + lane] = s0; red_s[(q * 4 + 1) * 32 + lane] = s1;
-      red_s[(q * 4 + 2) * 32 + lane] = q0; red_s[(q * 4 + 3) * 32 + lane] = q1;
+      red_s[(gw * 4 + 0) * 32 + lane] = s0; red_s[(gw * 4 + 1) * 32 + lane] = s1;
+      red_s[(gw * 4 + 2) * 32 + lane] = q0; red_s[(gw * 4 + 3) * 32 + lane] = q1;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (q == 0 && lane < WPR) {
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    if (grp == 0 && q == 0 && lane < WPR) {
       float t[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t[k] = red_s[(0 * 4 + k) * 32 + lane] + red_s[(1 * 4 + k) * 32 + lane] + red_s[(2 * 4 + k) * 32 + lane] + red_s[(3 * 4 + k) * 32 + lane];
+      for (int k = 0; k < 4; ++k) {
+        t[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[k] += red_s[(r * 4 + k) * 32 + lane];
+      }
       float* dst = P.bn_partials + (size_t)blockIdx.x * 2 * P.cout_total + nb0 + 2 * lane;
       dst[0] = t[0]; dst[1] = t[1];
       dst[P.cout_total] = t[2]; dst[P.cout_total + 1] = t[3];
     }
   }
 }
+
+#undef DG_GROUP_SYNC
 
 // Issues the MMAs of one pipeline stage (all taps of one channel chunk).  MT and NBK (= chunk/16) are
 // compile-time so the body is straight-line: one descriptor add per operand per tcgen05.mma.
@@ -317,13 +334,14 @@ __device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int t0, int
     const int tt = NT > 0 ? t : t0 + t;      // (t0 != 0 only in split-source mode, which uses the generic instance)
     const uint64_t ad = P.tap_adesc[tt] + (uint64_t)sa16;
     const uint32_t ms = P.tap_ms16[tt];
-    const uint32_t acc_rest = (not_first_chunk || t != 0) ? 1u : 0u;
+    const uint32_t acc_rest = (not_first_chunk || P.tap_first[tt] == 0u) ? 1u : 0u;
+    const uint32_t acc_t = acc0 + P.tap_acc[tt];
 #pragma unroll
     for (int k16 = 0; k16 < NBK; ++k16) {
       const uint64_t bd = b_hi | (uint64_t)(b_lo + (uint32_t)t * b_step + 2u * k16);
       const uint32_t accf = k16 == 0 ? acc_rest : 1u;
 #pragma unroll
-      for (int m = 0; m < MT; ++m) umma_f16(acc0 + (uint32_t)m * nb, ad + (uint64_t)((uint32_t)m * ms + 2u * k16), bd, idesc, accf);
+      for (int m = 0; m < MT; ++m) umma_f16(acc_t + (uint32_t)m * nb, ad + (uint64_t)((uint32_t)m * ms + 2u * k16), bd, idesc, accf);
     }
   }
 }
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
         mbar_wait(smem_u32(&bar_acc_empty[b]), acc_phase ^ 1u);
         tc_fence_after();
         if (lane == 0 && me == 0) dbg_mark(P, 1, it, 1);
-        const uint32_t acc0 = tmem + (uint32_t)(b * mt) * nb;
+        const uint32_t acc0 = tmem + (uint32_t)(b * P.n_phase * mt) * nb;
         for (int step = 0; step < n_steps; ++step) {
           const int kc = P.split ? step / P.n_src : step;
           const int so = P.split ? step - kc * P.n_src : 0;
@@ -572,16 +590,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     // ------------------------------------------------------------------ epilogue (4 warps)
     // activation / output type are resolved ONCE per kernel (warp-uniform switch) so the per-element code is
     // straight-line: TMEM -> registers, + bias (from shared memory), activation, pack, 16-byte stores.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;  // TMEM lane quarter this warp may access (any four consecutive warps cover the four quarters)
+    const int grp = warp >= 7 ? 1 : 0;
+    const int etid = grp * 128 + (warp - (grp ? 7 : 2)) * 32 + lane;   // 0..255 over both epilogue groups
     if (P.bias)
-      for (int i = tid - 64; i < P.nb; i += 128) bias_s[i] = __ldg(P.bias + nb0 + i);
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      for (int i = etid; i < P.nb; i += 256) bias_s[i] = __ldg(P.bias + nb0 + i);
+    asm volatile("bar.sync 3, 256;" ::: "memory");  // epilogue warps only
     const float* bs = P.bias ? bias_s : nullptr;
 #define DG_EPI(ACT)                                                                                     \
   if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
-                                      reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off)); \
-  else if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty); \
-  else epilogue_role<ACT, false>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty);
+                                      reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp); \
+  else if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, grp); \
+  else epilogue_role<ACT, false>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, grp);
     switch (P.act) {
       case DG_ACT_RELU: DG_EPI(DG_ACT_RELU) break;
       case DG_ACT_LRELU: DG_EPI(DG_ACT_LRELU) break;
@@ -678,14 +698,16 @@ struct Lattice {
 
 struct TapSpec {
   int src, dh, dw, widx;
+  int phase = 0;   // output parity phase the tap contributes to (fused stride-2 dgrad), 0 otherwise
 };
 
 // Builds the launch description and runs the kernel.
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
                 const TapSpec* taps_in, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
-                float* bn_partials = nullptr, int* bn_blocks = nullptr) {
+                float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
+  DG_REQUIRE(n_phase == 1 || (n_phase == 4 && phase_lat && n_src == 1), "%s: bad output-phase description", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
   DG_REQUIRE(in->cpitch % 8 == 0 && in->coff % 8 == 0 && ((uintptr_t)in->ptr % 16) == 0, "%s: input view not 16-byte aligned", name);
   const int out_esz = out->dtype == DG_F32 ? 4 : 2;
@@ -748,7 +770,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   for (int res = 1; res >= 0 && !best_nb; --res)
     for (int mt = 2; mt >= 1 && !best_nb; --mt)
       for (int nb = cout > 256 ? 256 : cout; nb >= 16 && !best_nb; nb -= 16) {
-        if (cout % nb != 0 || 2 * mt * nb > 512) continue;
+        if (cout % nb != 0 || 2 * n_phase * mt * nb > 512) continue;
         uint32_t wblk = (uint32_t)nb * kc * 2;
         uint32_t wres = (uint32_t)n_taps * n_chunks * wblk;
         uint32_t stage = halo_bytes(mt) + (res ? 0 : (uint32_t)n_taps * wblk);
@@ -780,7 +802,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     for (int min_stages = 3; min_stages >= 2 && !best_nb; --min_stages)
       for (int nb = cout > 256 ? 256 : cout; nb >= 16 && !best_nb; nb -= 16)
         for (int mt = 2; mt >= 1 && !best_nb; --mt) {
-          if (cout % nb != 0 || 2 * mt * nb > 512) continue;
+          if (cout % nb != 0 || 2 * n_phase * mt * nb > 512) continue;
           uint32_t stage = max_halo(mt) + (uint32_t)max_ntaps * nb * kc * 2;
           if ((uint32_t)min_stages * ((stage + 1023u) & ~1023u) <= budget) { best_nb = nb; best_mt = mt; best_res = 0; split = 1; }
         }
@@ -797,7 +819,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     // whatever the search above picked -- including RESIDENT weights bought with a narrow N block (256->64 dgrad ran as
     // two 32-channel blocks: 44-cycle MMAs for half the work and the input read twice).
     static const char* dbg_no_ko = getenv("DG_DEBUG_NO_KOUTER");   // experiments only
-    if (!split && n_chunks >= 2 && !dbg_no_ko) {
+    if (!split && n_chunks >= 2 && !dbg_no_ko && n_phase == 1) {
       auto cyc = [](int nb_) { int c = nb_ / 2 > 32 + nb_ / 4 ? nb_ / 2 : 32 + nb_ / 4; return (double)(c < 44 ? 44 : c); };
       auto rounds = [&](int mt_, int nb_) {
         long t = (long)in->n * ((out_h + 16 * mt_ - 1) / (16 * mt_)) * ((out_w + 7) / 8), c = ctx->sm_count / (cout / nb_);
@@ -840,14 +862,14 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
   DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
   static const char* dbg_no_ts = getenv("DG_DEBUG_NO_TSTORE");   // experiments only
-  bool ts = !kouter && (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64);
+  bool ts = !kouter && n_phase == 1 && (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64);
   const uint32_t stg_bytes = (uint32_t)mt * 128u * (uint32_t)nb * 2u;
   if (ts) {
     const long room = (long)budget - (long)w_res_pre - 2L * (long)stg_bytes;
     int ns = room > 0 ? (int)(room / (long)stage_bytes_pre) : 0;
     if (ns > MAX_STAGES) ns = MAX_STAGES;
     // keep the two-issuer configuration (>= 4 slots and four TMEM buffers) when the layer had it without the staging buffers
-    const bool had_two = 4 * mt * nb <= 512 && n_stages >= 4;
+    const bool had_two = 4 * n_phase * mt * nb <= 512 && n_stages >= 4;
     if (ns >= 2 && (!had_two || ns >= 4)) n_stages = ns; else ts = false;
   }
   const int out_h_ = (out->h - out_lat.h_first + out_lat.step - 1) / out_lat.step, out_w_ = (out->w - out_lat.w_first + out_lat.step - 1) / out_lat.step;
@@ -911,7 +933,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   {
     // two issuing warps need four TMEM accumulator buffers and at least two pipeline slots each
     static const char* dbg_single = getenv("DG_DEBUG_SINGLE_ISSUER");   // experiments only
-    P.nbuf_shift = (4 * mt * nb <= 512 && n_stages >= 4 && !dbg_single && !kouter) ? 2 : 1;
+    P.nbuf_shift = (4 * n_phase * mt * nb <= 512 && n_stages >= 4 && !dbg_single && !kouter) ? 2 : 1;
     if (P.nbuf_shift == 2) n_stages &= ~1;
   }
   P.n_stages = n_stages;
@@ -923,6 +945,21 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     P.tap_off[t] = P.src_off[s] + (uint32_t)((taps[t].dh - dh_min[s]) * WW + (taps[t].dw - dw_min[s])) * kc * 2;
     P.tap_adesc[t] = (make_smem_desc_hi(P.a_sbo[s], P.layout) << 32) | (uint64_t)((P.tap_off[t] >> 4) | (1u << 16));
     P.tap_ms16[t] = P.mt_stride[s] >> 4;
+  }
+  P.n_phase = n_phase;
+  {
+    bool seen[4] = {false, false, false, false};
+    for (int t = 0; t < n_taps; ++t) {
+      const int ph = n_phase == 1 ? 0 : taps[t].phase;
+      DG_REQUIRE(ph >= 0 && ph < n_phase, "%s: bad tap phase", name);
+      P.tap_acc[t] = (uint32_t)(ph * mt * nb);
+      P.tap_first[t] = seen[ph] ? 0u : 1u;
+      seen[ph] = true;
+    }
+    for (int ph = 0; ph < n_phase; ++ph) {
+      DG_REQUIRE(seen[ph], "%s: output phase without taps", name);
+      P.ph_off[ph] = n_phase == 1 ? 0L : ((long)phase_lat[ph].h_first * out->w + phase_lat[ph].w_first) * (long)out->cpitch;
+    }
   }
   // weights: 2D [rows][kc]
   {
@@ -963,9 +1000,9 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   {
     static const char* dbg_cfg = getenv("DG_DEBUG_CONFIG");   // prints the tile configuration of every launch
     if (dbg_cfg)
-      fprintf(stderr, "[%s] %dx%dx%d c%d->%d taps %d src %d: nb %d mt %d kc %d chunks %d resident %d split %d kouter %d stages %d x %u B, issuers %d, tstore %d, smem %u\n",
-              name, out->n, out_h, out_w, in->c, cout, n_taps, n_src, nb, mt, kc, n_chunks, best_res, split, kouter, n_stages, P.stage_bytes,
-              P.nbuf_shift == 2 ? 2 : 1, P.tstore, smem);
+      fprintf(stderr, "[%s] %dx%dx%d c%d->%d taps %d src %d: nb %d mt %d kc %d chunks %d resident %d split %d kouter %d phases %d stages %d x %u B, issuers %d, tstore %d, smem %u\n",
+              name, out->n, out_h, out_w, in->c, cout, n_taps, n_src, nb, mt, kc, n_chunks, best_res, split, kouter, n_phase, n_stages,
+              P.stage_bytes, P.nbuf_shift == 2 ? 2 : 1, P.tstore, smem);
   }
   int ctas = ctx->sm_count / n_blocks;
   if (ctas < 1) ctas = 1;
@@ -1090,6 +1127,35 @@ static int conv_dgrad_impl(dg_ctx* ctx, const dg_tensor* dy, const void* w_packe
                        p->act, p->act_alpha, (cudaStream_t)stream, dry);
   }
   DG_REQUIRE(dx->h % 2 == 0 && dx->w % 2 == 0, "dg_umma_conv2d_dgrad: stride 2 needs even image size");
+  {
+    // All four output parity phases in ONE launch when their accumulators fit TMEM together (2 buffers x 4 phases x mt x nb
+    // <= 512 columns: the 32/64-channel discriminator layers): dy is read once instead of four times and one prologue /
+    // tail is paid instead of four.  Otherwise (wide layers, pix2pix) one launch per phase below.
+    static const char* no_fuse = getenv("DG_DEBUG_NO_PHASE_FUSION");   // experiments only
+    Lattice plat[4];
+    int n_all = 0;
+    bool ok = !no_fuse;
+    for (int a = 0; a < 2 && ok; ++a)
+      for (int b = 0; b < 2 && ok; ++b) {
+        plat[a * 2 + b] = Lattice{2, a, b};
+        int cnt = 0;
+        for (int r = 0; r < p->kh; ++r) {
+          if (pymod(a + p->pad_t - r, 2) != 0) continue;
+          for (int s = 0; s < p->kw; ++s) {
+            if (pymod(b + p->pad_l - s, 2) != 0) continue;
+            taps[n_all++] = TapSpec{0, floordiv(a + p->pad_t - r, 2), floordiv(b + p->pad_l - s, 2), r * p->kw + s, a * 2 + b};
+            ++cnt;
+          }
+        }
+        if (cnt == 0) ok = false;
+      }
+    if (ok && launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_all, w_packed, dx->c, dx, Lattice{2, 0, 0}, bias, p->act,
+                          p->act_alpha, (cudaStream_t)stream, true, nullptr, nullptr, 4, plat) == 0) {
+      if (dry) return 0;
+      return launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_all, w_packed, dx->c, dx, Lattice{2, 0, 0}, bias, p->act,
+                         p->act_alpha, (cudaStream_t)stream, false, nullptr, nullptr, 4, plat);
+    }
+  }
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       int n_taps = 0;

@@ -764,3 +764,38 @@ def test_umma_conv_k_outer_weight_ring(L, case):
     finally:
         lib.dg_debug_conv_flags(0)
     assert relerr(out, ref) < BF16_TOL
+
+
+# ---------------------------------------------------------------- stride-2 dgrad: four output phases in one launch
+@pytest.mark.parametrize("case", [(3, 32, 32, 2, 40, 24), (3, 64, 64, 2, 24, 36), (4, 64, 32, 1, 32, 16), (3, 32, 64, 3, 18, 10), (4, 128, 64, 1, 16, 16)])
+def test_umma_dgrad_stride2_fused_phases(L, case):
+    """dx of a stride-2 Conv2D (= Conv2DTranspose forward, pix2pix.py:130) with all four output parity phases computed by ONE
+    launch when their accumulators fit TMEM (conv_umma.cu `n_phase`), against the oracle and against the one-launch-per-phase
+    path it replaces; odd tile counts in both directions, bias + LeakyReLU epilogue on the transposed-conv output."""
+    k, cin, cout, N, H, W = case          # forward conv: [N,H,W,cin] -> [N,H/2,W/2,cout]
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * (1.0 / (k * np.sqrt(cout))))
+    gy = _bf16_round(torch.randn(N, H // 2, W // 2, cout, generator=g, dtype=torch.float64))
+    xr = torch.zeros(N, H, W, cin, dtype=torch.float64, requires_grad=True)
+    (OT.conv2d(xr, w, None, stride=2, padding="same") * gy).sum().backward()
+    ref = xr.grad
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 2, H, W, "same")
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    wd = dev(w)
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 1, st))
+    gyd = dev(gy, torch.bfloat16)
+    dx = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+    tg, tdx = L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tg), pk.data_ptr(), None, C.byref(tdx), C.byref(cp), st))
+    torch.cuda.synchronize()
+    assert relerr(dx, ref) < BF16_TOL
+    # bias + activation epilogue (Conv2DTranspose forward with bias, fp32 output)
+    b = torch.randn(cin, generator=g, dtype=torch.float64)
+    cpa = conv_params(L, k, k, 2, H, W, "same", act=2, alpha=0.3)
+    out = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.float32)
+    bd = dev(b); to = L.tensor(out)
+    L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tg), pk.data_ptr(), bd.data_ptr(), C.byref(to), C.byref(cpa), st))
+    torch.cuda.synchronize()
+    pre = ref + b
+    assert relerr(out, torch.where(pre >= 0, pre, 0.3 * pre)) < 1e-4
