@@ -607,6 +607,37 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
         (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
         dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, vdx, P, C);                                                     \
   }
+    // on-chip variant: bf16 tensors, no dropout, every thread's pixel walk fits K = 16 cached iterations.  OFF by default
+    // (DG_BN_BWD_CACHED=1 enables): measured SLOWER inside the SRGAN step, 7.76 vs 7.44 ms -- 128 registers with the x cache
+    // leave four loads in flight per thread and 200 KB of shared memory keep every other kernel off the SM.
+    {
+      static const char* env_cached = getenv("DG_BN_BWD_CACHED");
+      constexpr int KC = 16;
+      const int Rr = dgvec::RT / (C >> 3);
+      const long walk = ((long)P + (long)vblocks * Rr - 1) / ((long)vblocks * Rr);
+      const int am = dgvec::act_mode(act, dropout);
+      const size_t red = (dgvec::red8_smem(C, 3) + 15) & ~(size_t)15, smem_c = red + (size_t)KC * dgvec::RT * 16;
+      if (fused_bwd && (env_cached && env_cached[0] == '1') && dy->dtype == DG_BF16 && x->dtype == DG_BF16 && am <= 3 && walk <= KC &&
+          dgvec::RT % (C >> 3) == 0 && smem_c <= 200 * 1024) {
+#define DG_BN_BWD_CACHED(AM)                                                                                                      \
+  {                                                                                                                              \
+    cudaFuncSetAttribute(dgvec::bn_bwd_cached8_kernel<AM, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);          \
+    dg_pdl_launch(dgvec::bn_bwd_cached8_kernel<AM, KC>, dim3(vblocks), dim3(dgvec::RT), smem_c, ST,                                \
+        (const __nv_bfloat16*)dy->ptr, vdy, (const __nv_bfloat16*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act,    \
+        act_alpha, prelu_alpha, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr,        \
+        accumulate, coef, (__nv_bfloat16*)dx->ptr, vdx, (unsigned)red);                                                          \
+  }
+        switch (am) {
+          case 0: DG_BN_BWD_CACHED(0) break;
+          case 1: DG_BN_BWD_CACHED(1) break;
+          case 2: DG_BN_BWD_CACHED(2) break;
+          default: DG_BN_BWD_CACHED(3) break;
+        }
+#undef DG_BN_BWD_CACHED
+        DG_CHECK_LAUNCH("dg_bn_act_bwd");
+        return 0;
+      }
+    }
     DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_act_bwd", {
       switch (dgvec::act_mode(act, dropout)) {
         case 0: DG_BN_BWD_VEC(0) break;

@@ -85,35 +85,16 @@ struct VView {
 // not depend on block scheduling (deterministic).
 constexpr int RT = 512;
 
-template <int NV, int U, typename Raw, typename L, typename A, typename Fin>
-__device__ __forceinline__ bool channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, L load,
-                                                A accum, Fin fin) {
+// Second half of channel_reduce8: block reduce of the per-thread sums, per-block partial, last-block finalize.
+template <int NV, typename Fin>
+__device__ __forceinline__ bool channel_reduce8_finish(float (&acc)[NV][8], long P, int C, float* __restrict__ partial,
+                                                       unsigned* __restrict__ ticket, Fin fin) {
   extern __shared__ __align__(16) float red8[];
   __shared__ int is_last;
   const int CV = C >> 3, R = RT / CV;
   const int lane = threadIdx.x % CV, row = threadIdx.x / CV;
   const int c0 = lane * 8;
   const int E = NV * C;
-  float acc[NV][8];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
-  if (row < R) {
-    const long stride = (long)gridDim.x * R;
-    long p = (long)blockIdx.x * R + row;
-    for (; p + (U - 1) * stride < P; p += U * stride) {
-      Raw r[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) r[u] = load(p + u * stride, c0);
-#pragma unroll
-      for (int u = 0; u < U; ++u) accum(r[u], p + u * stride, c0, acc);
-    }
-    for (; p < P; p += stride) {
-      Raw r = load(p, c0);
-      accum(r, p, c0, acc);
-    }
-  }
   // ---- block reduce: rows sharing a warp first (shuffles), then across warps through shared memory
   int rows_out;
   if (CV <= 32 && (CV & (CV - 1)) == 0) {       // RT % CV == 0: every thread is active, warps hold 32/CV whole rows
@@ -187,6 +168,35 @@ __device__ __forceinline__ bool channel_reduce8(long P, int C, float* __restrict
   for (int c = threadIdx.x; c < C; c += RT) fin(c, fsum);
   if (threadIdx.x == 0) *ticket = 0u;
   return true;
+}
+
+template <int NV, int U, typename Raw, typename L, typename A, typename Fin>
+__device__ __forceinline__ bool channel_reduce8(long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket, L load,
+                                                A accum, Fin fin) {
+  const int CV = C >> 3, R = RT / CV;
+  const int lane = threadIdx.x % CV, row = threadIdx.x / CV;
+  const int c0 = lane * 8;
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  if (row < R) {
+    const long stride = (long)gridDim.x * R;
+    long p = (long)blockIdx.x * R + row;
+    for (; p + (U - 1) * stride < P; p += U * stride) {
+      Raw r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = load(p + u * stride, c0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) accum(r[u], p + u * stride, c0, acc);
+    }
+    for (; p < P; p += stride) {
+      Raw r = load(p, c0);
+      accum(r, p, c0, acc);
+    }
+  }
+  return channel_reduce8_finish<NV>(acc, P, C, partial, ticket, fin);
 }
 
 // Grid-wide "results are ready" barrier for kernels whose blocks are all co-resident (grid <= SM count, one block per
@@ -704,6 +714,113 @@ bn_bwd_fused8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__
     r.g = V8<TG>::ldraw(dy + (p * dv.pitch + dv.off + c0));
     r.x = V8<TX>::ldraw(x + (p * xv.pitch + xv.off + c0));
     one(r, p);
+  }
+}
+
+// bn_bwd_fused8_kernel for bf16 tensors whose per-block slice fits ON CHIP: in the statistics pass a thread keeps the x
+// values it loaded in registers (K x 16 bytes) and parks the dy values in shared memory (K x 512 x 16 bytes), so the dx pass
+// after the grid barrier touches no global memory except its store.  The 19 MB tensors of the generator trunk are 128 KB of
+// x and 128 KB of dy per SM: the register file and the shared memory of a B200 SM hold exactly one of each.
+template <int AM, int K>
+__global__ void __launch_bounds__(RT, 1)
+bn_bwd_cached8_kernel(const __nv_bfloat16* __restrict__ dy, VView dv, const __nv_bfloat16* __restrict__ x, VView xv,
+                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ gamma,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, int act, float alpha,
+                      const float* __restrict__ prelu_alpha, long P, int C, float* __restrict__ partial, unsigned* __restrict__ ticket,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dalpha, int accumulate,
+                      float* __restrict__ coef, __nv_bfloat16* __restrict__ dx, VView ov, unsigned cache_off) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float red8[];
+  uint4* dyc = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(red8) + cache_off);
+  typedef V8<__nv_bfloat16> V;
+  const int CV = C >> 3, R = RT / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  float sc[8], sh[8], mu[8], al[8];
+  ldc8(scale + c0, sc); ldc8(shift + c0, sh); ldc8(mean + c0, mu);
+  if (AM == 3) ldc8(prelu_alpha + c0, al);
+  auto gterm = [&](float gyj, float xj, int j, float& tt) {
+    tt = fmaf(xj, sc[j], sh[j]);
+    return __fmul_rn(gyj, act_deriv_t<AM>(tt, act, alpha, AM == 3 ? al[j] : 0.f));
+  };
+  const long stride = (long)gridDim.x * R;
+  const long p0 = (long)blockIdx.x * R + row;
+  uint4 xc[K];
+  float acc[3][8];
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  if (row < R) {
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      uint4 g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long p = p0 + (long)(k0 + u) * stride;
+        if (p < P) {
+          g[u] = V::ldraw(dy + (p * dv.pitch + dv.off + c0));
+          xc[k0 + u] = V::ldraw(x + (p * xv.pitch + xv.off + c0));
+        } else {
+          g[u] = make_uint4(0u, 0u, 0u, 0u);
+          xc[k0 + u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dyc[(k0 + u) * RT + threadIdx.x] = g[u];
+        if (p0 + (long)(k0 + u) * stride < P) {
+          float gy[8], xin[8];
+          V::cvt(g[u], gy);
+          V::cvt(xc[k0 + u], xin);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float tt;
+            const float gg = gterm(gy[j], xin[j], j, tt);
+            acc[0][j] += gg;
+            acc[1][j] = fmaf(gg, xin[j] - mu[j], acc[1][j]);
+            if (AM == 3) acc[2][j] = fmaf(gy[j], fminf(tt, 0.f), acc[2][j]);
+          }
+        }
+      }
+    }
+  }
+  const bool last = channel_reduce8_finish<3>(acc, P, C, partial, ticket, [&](int c, const double* sums) {
+    const double s0 = sums[c], s1 = sums[C + c] * (double)invstd[c], s2 = sums[2 * C + c];
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+    if (dalpha) dalpha[c] = (accumulate ? dalpha[c] : 0.f) + (float)s2;
+    coef[c] = (float)(s0 / (double)P);
+    coef[C + c] = (float)(s1 / (double)P);
+  });
+  grid_flag_barrier(last, ticket + 1, ticket + 2);
+  if (row >= R) return;
+  float A[8], B[8], k0v[8];
+  {
+    float ga[8], is[8], k1[8];
+    ldc8(gamma + c0, ga); ldc8(invstd + c0, is);
+    ldcg8(coef + c0, k0v); ldcg8(coef + C + c0, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      A[j] = ga[j] * is[j];
+      B[j] = -A[j] * is[j] * k1[j];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const long p = p0 + (long)k * stride;
+    if (p < P) {
+      float gy[8], xin[8], o[8];
+      V::cvt(dyc[k * RT + threadIdx.x], gy);
+      V::cvt(xc[k], xin);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float tt;
+        const float gg = gterm(gy[j], xin[j], j, tt);
+        o[j] = fmaf(A[j], gg - k0v[j], B[j] * (xin[j] - mu[j]));
+      }
+      V::st(dx + (p * ov.pitch + ov.off + c0), o);
+    }
   }
 }
 
