@@ -53,12 +53,16 @@ image_losses_kernel(const TG* __restrict__ gen, int gp, int go, const TT* __rest
                     int accumulate, float* __restrict__ partial) {
   const long total = (long)N * H * W * C;
   float acc[3] = {0.f, 0.f, 0.f};
+  const bool idx32 = total < (1L << 31);    // 32-bit index arithmetic when the tensor allows it (three divisions per element)
   for (long i = (long)blockIdx.x * LT + threadIdx.x; i < total; i += (long)gridDim.x * LT) {
-    int c = (int)(i % C);
-    long p = i / C;
-    int w = (int)(p % W);
-    long t = p / W;
-    int h = (int)(t % H);
+    int c, w, h;
+    long p;
+    if (idx32) {
+      const unsigned iu = (unsigned)i, pu = iu / (unsigned)C, tu = pu / (unsigned)W;
+      c = (int)(iu - pu * (unsigned)C); w = (int)(pu - tu * (unsigned)W); h = (int)(tu % (unsigned)H); p = (long)pu;
+    } else {
+      c = (int)(i % C); p = i / C; w = (int)(p % W); h = (int)((p / W) % H);
+    }
     auto diff = [&](long pp) { return ld_f(tgt + (pp * tp + to + c)) - ld_f(gen + (pp * gp + go + c)); };
     float d = diff(p);
     acc[0] += fabsf(d);

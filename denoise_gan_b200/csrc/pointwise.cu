@@ -49,6 +49,23 @@ __device__ __forceinline__ bool sum_partials8(const float* __restrict__ partial,
   return true;
 }
 
+
+// Element loop of the scalar (any channel count) kernels: 32-bit index arithmetic whenever the tensor allows it -- the
+// 64-bit division per element made these kernels run at ~1 TB/s on the 3-channel fp32 images around the generator output.
+#define DG_ELEM_LOOP(total, C, body)                                                                                   \
+  if ((total) < (1L << 31)) {                                                                                          \
+    const unsigned total32_ = (unsigned)(total), C32_ = (unsigned)(C), step32_ = gridDim.x * blockDim.x;                \
+    for (unsigned i_ = blockIdx.x * blockDim.x + threadIdx.x; i_ < total32_; i_ += step32_) {                           \
+      const unsigned p32_ = i_ / C32_;                                                                                 \
+      body((long)p32_, (int)(i_ - p32_ * C32_));                                                                       \
+    }                                                                                                                  \
+  } else {                                                                                                             \
+    for (long i_ = (long)blockIdx.x * blockDim.x + threadIdx.x; i_ < (total); i_ += (long)gridDim.x * blockDim.x) {     \
+      const long p64_ = i_ / (C);                                                                                      \
+      body(p64_, (int)(i_ - p64_ * (C)));                                                                              \
+    }                                                                                                                  \
+  }
+
 // ------------------------------------------------------------------ BN statistics
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) bn_stats_kernel(const T* __restrict__ x, View xv, long P, int C,
@@ -199,10 +216,8 @@ __global__ void bn_bwd_dx_kernel(const TG* __restrict__ dy, View dv, const TX* _
 template <typename TG, typename TY, typename TO>
 __global__ void act_bwd_kernel(const TG* __restrict__ dy, View dv, const TY* __restrict__ y, View yv, int act,
                                float alpha, TO* __restrict__ dpre, View ov, long P, int C) {
-  long total = P * C;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long p = i / C;
-    int c = (int)(i - p * C);
+  const long total = P * C;
+  auto body = [&](long p, int c) {
     float yo = ld_f(y + (p * yv.pitch + yv.off + c));
     float g = ld_f(dy + (p * dv.pitch + dv.off + c));
     float d;
@@ -214,7 +229,8 @@ __global__ void act_bwd_kernel(const TG* __restrict__ dy, View dv, const TY* __r
       default: d = 1.f;
     }
     st_f(dpre + (p * ov.pitch + ov.off + c), g * d);
-  }
+  };
+  DG_ELEM_LOOP(total, C, body)
 }
 
 // ------------------------------------------------------------------ depth_to_space(2) + PReLU
@@ -292,27 +308,25 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int nbloc
 template <typename TA, typename TO>
 __global__ void add_kernel(const TA* __restrict__ a, View av, const TA* __restrict__ b, View bv, TO* __restrict__ o,
                            View ov, long P, int C) {
-  long total = P * C;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long p = i / C;
-    int c = (int)(i - p * C);
+  const long total = P * C;
+  auto body = [&](long p, int c) {
     st_f(o + (p * ov.pitch + ov.off + c),
          ld_f(a + (p * av.pitch + av.off + c)) + ld_f(b + (p * bv.pitch + bv.off + c)));
-  }
+  };
+  DG_ELEM_LOOP(total, C, body)
 }
 
 template <typename TI, typename TO>
 __global__ void copy_kernel(const TI* __restrict__ s, View sv, TO* __restrict__ o, View ov, long P, int C,
                             int accumulate) {
-  long total = P * C;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long p = i / C;
-    int c = (int)(i - p * C);
+  const long total = P * C;
+  auto body = [&](long p, int c) {
     float v = ld_f(s + (p * sv.pitch + sv.off + c));
     TO* dst = o + (p * ov.pitch + ov.off + c);
     if (accumulate) v += ld_f(dst);
     st_f(dst, v);
-  }
+  };
+  DG_ELEM_LOOP(total, C, body)
 }
 
 // ------------------------------------------------------------------ max-pool 2x2 / upsample 2x
