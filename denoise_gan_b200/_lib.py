@@ -28,6 +28,12 @@ class DgConvParams(C.Structure):
                 ("pad_l", C.c_int32), ("act", C.c_int32), ("act_alpha", C.c_float)]
 
 
+class DgBnFused(C.Structure):      # include/dg_b200.h: dg_bn_fused
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
+                ("moving_mean", C.c_void_p), ("moving_var", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p), ("pixels", C.c_longlong)]
+
+
 class DgError(RuntimeError):
     pass
 
@@ -56,6 +62,7 @@ SIGNATURES = {
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_fwd_bn_blocks": (_i, [_P, _T, _T, _CP]),
+    "dg_umma_conv2d_fwd_bn": (_i, [_P, _T, _P, _P, _T, _CP, _P, C.POINTER(DgBnFused), _P]),
     "dg_bn_finalize": (_i, [_P, _P, _i, C.c_longlong, _i, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _P]),
     "dg_umma_conv2d_dgrad_supported": (_i, [_P, _T, _T, _CP]),
     "dg_bias_grad": (_i, [_P, _T, _P, _i, _P, _sz, _P]),

@@ -80,6 +80,9 @@ struct UmmaConvParams {
   int tstore;
   uint32_t stg_off, stg_bytes, stg_mask;
   float* bn_partials;   // [gridDim.x][2][cout_total] or nullptr
+  int bn_fin;           // the last CTA (ticket) turns the partial rows into scale/shift/mean/invstd + moving statistics
+  dg_bn_fused bnf;
+  unsigned* ticket;
   const float* bias;
   int act;
   float alpha;
@@ -314,6 +317,61 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
       float* dst = P.bn_partials + (size_t)blockIdx.x * 2 * P.cout_total + nb0 + 2 * lane;
       dst[0] = t[0]; dst[1] = t[1];
       dst[P.cout_total] = t[2]; dst[P.cout_total + 1] = t[3];
+    }
+    if (P.bn_fin) {
+      // ---- last CTA of the grid: fixed-order double-precision sum of the rows, then the BatchNorm coefficients
+      __shared__ int s_last;
+      const int etid = grp * 128 + q * 32 + lane;     // any bijection onto 0..255
+      __threadfence();
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (etid == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        const int C = P.cout_total, E = 2 * C, E4 = E >> 2, nblk = (int)gridDim.x;
+        const int G = E4 < 256 ? 256 / E4 : 1;
+        double* gsum = reinterpret_cast<double*>(red_s);          // [G][E] doubles <= 8 KB = the two staging buffers
+        const float4* part4 = reinterpret_cast<const float4*>(P.bn_partials);
+        for (int idx = etid; idx < E4 * G; idx += 256) {
+          const int e4 = idx % E4, g2 = idx / E4;
+          double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+          int bI = g2;
+          for (; bI + 3 * G < nblk; bI += 4 * G) {     // four independent loads in flight
+            const float4 v0 = __ldcg(part4 + (long)bI * E4 + e4), v1 = __ldcg(part4 + (long)(bI + G) * E4 + e4);
+            const float4 v2 = __ldcg(part4 + (long)(bI + 2 * G) * E4 + e4), v3 = __ldcg(part4 + (long)(bI + 3 * G) * E4 + e4);
+            sacc[0] += (double)v0.x; sacc[1] += (double)v0.y; sacc[2] += (double)v0.z; sacc[3] += (double)v0.w;
+            sacc[0] += (double)v1.x; sacc[1] += (double)v1.y; sacc[2] += (double)v1.z; sacc[3] += (double)v1.w;
+            sacc[0] += (double)v2.x; sacc[1] += (double)v2.y; sacc[2] += (double)v2.z; sacc[3] += (double)v2.w;
+            sacc[0] += (double)v3.x; sacc[1] += (double)v3.y; sacc[2] += (double)v3.z; sacc[3] += (double)v3.w;
+          }
+          for (; bI < nblk; bI += G) {
+            const float4 v = __ldcg(part4 + (long)bI * E4 + e4);
+            sacc[0] += (double)v.x; sacc[1] += (double)v.y; sacc[2] += (double)v.z; sacc[3] += (double)v.w;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gsum[(long)g2 * E + e4 * 4 + k] = sacc[k];
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const dg_bn_fused& B = P.bnf;
+        for (int c = etid; c < C; c += 256) {
+          double s0d = 0.0, s1d = 0.0;
+          for (int g2 = 0; g2 < G; ++g2) { s0d += gsum[(long)g2 * E + c]; s1d += gsum[(long)g2 * E + C + c]; }
+          const double mean = s0d / (double)B.pixels;
+          double var = s1d / (double)B.pixels - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float invstd = (float)(1.0 / sqrt(var + (double)B.eps));
+          const float ga = B.gamma[c], be = B.beta[c];
+          B.scale[c] = ga * invstd;
+          B.shift[c] = be - (float)mean * ga * invstd;
+          B.save_mean[c] = (float)mean;
+          B.save_invstd[c] = invstd;
+          if (B.moving_mean) {
+            B.moving_mean[c] = B.moving_mean[c] * B.momentum + (float)mean * (1.f - B.momentum);
+            B.moving_var[c] = B.moving_var[c] * B.momentum + (float)var * (1.f - B.momentum);
+          }
+        }
+        if (etid == 0) *P.ticket = 0u;
+      }
     }
   }
 }
@@ -705,7 +763,8 @@ struct TapSpec {
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
                 const TapSpec* taps_in, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
-                float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr) {
+                float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr,
+                const dg_bn_fused* bn_fin = nullptr) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
   DG_REQUIRE(n_phase == 1 || (n_phase == 4 && phase_lat && n_src == 1), "%s: bad output-phase description", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
@@ -930,6 +989,14 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.stg_bytes = stg_bytes;
   P.stg_mask = nb == 64 ? 7u : (nb == 32 ? 3u : 1u);
   P.bn_partials = bn_partials;
+  if (bn_fin) {
+    DG_REQUIRE(bn_partials && cout <= 512 && cout % 8 == 0, "%s: in-kernel BatchNorm finalize needs bn_partials and Cout <= 512", name);
+    DG_REQUIRE(bn_fin->gamma && bn_fin->beta && bn_fin->scale && bn_fin->shift && bn_fin->save_mean && bn_fin->save_invstd &&
+                   bn_fin->pixels == (long long)out->n * out_h * out_w, "%s: bad dg_bn_fused", name);
+    P.bn_fin = 1;
+    P.bnf = *bn_fin;
+    P.ticket = ctx->tickets + 8;     // own counter: the reduction kernels of this context use tickets[0..2]
+  }
   {
     // two issuing warps need four TMEM accumulator buffers and at least two pipeline slots each
     static const char* dbg_single = getenv("DG_DEBUG_SINGLE_ISSUER");   // experiments only
@@ -1066,7 +1133,8 @@ extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, in
 }
 
 static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
-                         const dg_conv_params* p, void* stream, bool dry, float* bn_partials = nullptr, int* bn_blocks = nullptr) {
+                         const dg_conv_params* p, void* stream, bool dry, float* bn_partials = nullptr, int* bn_blocks = nullptr,
+                         const dg_bn_fused* bn_fin = nullptr) {
   DG_REQUIRE(dg_valid(x) && dg_valid(y) && w_packed && p, "dg_umma_conv2d_fwd: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
   DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
@@ -1090,12 +1158,18 @@ static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, 
       }
   }
   return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
-                     p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks);
+                     p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks, 1, nullptr, bn_fin);
 }
 
 extern "C" int dg_umma_conv2d_fwd(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias,
                                   const dg_tensor* y, const dg_conv_params* p, float* bn_partials, void* stream) {
   return conv_fwd_impl(ctx, x, w_packed, bias, y, p, stream, false, bn_partials);
+}
+
+extern "C" int dg_umma_conv2d_fwd_bn(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                                     const dg_conv_params* p, float* bn_partials, const dg_bn_fused* bn, void* stream) {
+  DG_REQUIRE(bn_partials && bn, "dg_umma_conv2d_fwd_bn: null argument");
+  return conv_fwd_impl(ctx, x, w_packed, bias, y, p, stream, false, bn_partials, nullptr, bn);
 }
 
 // Number of per-CTA partial rows ([rows][2][Cout] floats) dg_umma_conv2d_fwd writes into `bn_partials` for this layer,

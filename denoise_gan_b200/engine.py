@@ -30,11 +30,12 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq", "bn_part")
+    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
         self.bn_part = None     # (partials [blocks,2,C], blocks) when the producing conv reduced the BatchNorm statistics
+        self.bn_done = None     # (name, scale, shift, mean, invstd) when the producing conv ALSO finalised them (last-CTA ticket)
 
     @property
     def shape(self):
@@ -92,6 +93,9 @@ class Engine:
         self.use_umma_wgrad = self.use_umma
         self.fuse_bn_fwd = os.environ.get("DG_BN_FUSED_FWD", "0") == "1"   # one-launch BN forward: measured 1 % slower in the step graph
         self.fuse_conv_bn_stats = os.environ.get("DG_CONV_BN_STATS", "1") != "0"   # BN batch statistics from the conv epilogue
+        # ... and their finalize by the conv's last CTA (dg_umma_conv2d_fwd_bn): OFF by default, measured slower in the step graph
+        # (7.54 vs 7.45 ms, 403 vs 446 kernel nodes): the serial tail on one CTA costs more than the 8-block finalize launch
+        self.fuse_conv_bn_finalize = os.environ.get("DG_CONV_BN_FINALIZE", "0") == "1"
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
         # dgrad / BatchNorm chain of the backward pass (joined at the end of backward())
         self.wgrad_overlap = os.environ.get("DG_WGRAD_OVERLAP", "1") != "0"
@@ -380,7 +384,7 @@ class Engine:
         tx, ty = tensor(x.t), tensor(y)
         bias = _lib.ptr(b.data) if b is not None else None
         flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
-        bn_part = None
+        bn_part = bn_done = None
         if umma_f:
             pk = self._packed(w, 0)
             if bn and self.fuse_conv_bn_stats and act is None:
@@ -391,13 +395,26 @@ class Engine:
                     self._cap[key] = blocks
                 if blocks > 0:
                     bn_part = (self.buf((seq, "bn_part"), (blocks, 2, cout), torch.float32), blocks)
-            self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
-                self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), _lib.ptr(bn_part[0]) if bn_part else None, self.st)))
+            if bn_part and isinstance(bn, tuple) and self.fuse_conv_bn_finalize and cout <= 512:
+                # (pset, name, momentum, eps): the conv's last CTA also turns the partial rows into the BatchNorm coefficients
+                bp, bname, bmom, beps = bn
+                coef = [self.buf((seq, "bn_" + k), (cout,), torch.float32) for k in ("scale", "shift", "mean", "invstd")]
+                fz = _lib.DgBnFused(bp[bname + "/gamma"].data.data_ptr(), bp[bname + "/beta"].data.data_ptr(), float(beps), float(bmom),
+                                    bp[bname + "/moving_mean"].data.data_ptr(), bp[bname + "/moving_variance"].data.data_ptr(),
+                                    coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), N * Ho * Wo)
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd_bn(
+                    self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), bn_part[0].data_ptr(), C.byref(fz), self.st)))
+                bn_done = (bname, *coef)
+                bn_part = None
+            else:
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+                    self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), _lib.ptr(bn_part[0]) if bn_part else None, self.st)))
         else:
             self._timed("simt_conv", flops, lambda: check(self.lib.dg_conv2d_fwd(
                 self.ctx, C.byref(tx), w.data.data_ptr(), bias, C.byref(ty), C.byref(cp), self.st)))
         out = Var(y, self._deps([x], w.group), seq)
         out.bn_part = bn_part
+        out.bn_done = bn_done
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag):
             dpre = gy
@@ -620,10 +637,15 @@ class Engine:
         mm, mv = pset[name + "/moving_mean"], pset[name + "/moving_variance"]
         Cc = x.shape[3]
         seq = self._next()
-        scale = self.buf((seq, "scale"), (Cc,), torch.float32)
-        shift = self.buf((seq, "shift"), (Cc,), torch.float32)
-        mean = self.buf((seq, "mean"), (Cc,), torch.float32)
-        invstd = self.buf((seq, "invstd"), (Cc,), torch.float32)
+        bn_done = getattr(x, "bn_done", None) if training else None
+        if bn_done is not None:
+            assert bn_done[0] == name, f"conv finalised the statistics of {bn_done[0]}, consumed by {name}"
+            _, scale, shift, mean, invstd = bn_done
+        else:
+            scale = self.buf((seq, "scale"), (Cc,), torch.float32)
+            shift = self.buf((seq, "shift"), (Cc,), torch.float32)
+            mean = self.buf((seq, "mean"), (Cc,), torch.float32)
+            invstd = self.buf((seq, "invstd"), (Cc,), torch.float32)
         tx = tensor(x.t)
         nbytes = self.lib.dg_bn_workspace_bytes(C.byref(tx))
         ws = self.workspace(nbytes)
@@ -634,7 +656,9 @@ class Engine:
         a_code = ACT["prelu"] if prelu is not None else ACT[act]
         fused = False
         bn_part = getattr(x, "bn_part", None)
-        if training and bn_part is not None:
+        if bn_done is not None:
+            pass    # scale/shift/mean/invstd and the moving statistics were written by the producing convolution
+        elif training and bn_part is not None:
             # the producing convolution already reduced the batch statistics to per-CTA partials
             check(self.lib.dg_bn_finalize(self.ctx, bn_part[0].data_ptr(), bn_part[1], x.shape[0] * x.shape[1] * x.shape[2], Cc,
                                           gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum), mm.data.data_ptr(),

@@ -86,6 +86,18 @@ int dg_umma_conv2d_fwd(dg_ctx*, const dg_tensor* x, const void* w_packed, const 
  * squares) per CTA; dg_umma_conv2d_fwd_bn_blocks() gives the row count (0: layer not eligible, call dg_bn_stats),
  * dg_bn_finalize() turns the rows into scale/shift/mean/invstd and updates the moving statistics. */
 int dg_umma_conv2d_fwd_bn_blocks(dg_ctx*, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p);
+/* Conv2D + the statistics half of the BatchNormalization that follows it, in ONE launch: as dg_umma_conv2d_fwd with
+ * bn_partials, and the LAST CTA to finish (ticket counter) sums the per-CTA rows in a fixed order in double precision and
+ * does what dg_bn_finalize does (scale/shift, saved mean/invstd, moving-statistics update). */
+typedef struct {
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  float* moving_mean; float* moving_var;          /* may be NULL */
+  float* scale; float* shift; float* save_mean; float* save_invstd;
+  long long pixels;                               /* N*H*W of the conv output */
+} dg_bn_fused;
+int dg_umma_conv2d_fwd_bn(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                          const dg_conv_params* p, float* bn_partials, const dg_bn_fused* bn, void* stream);
 int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,
                          const dg_tensor* dx, const dg_conv_params* p, void* stream);
 /* capability queries: 1 when the tensor-core kernels have a tile configuration for the layer (shared-memory fit);

@@ -707,10 +707,21 @@ def test_umma_conv_fused_bn_partials_and_slice_output(L, case):
     # finalize == dg_bn_stats on the stored tensor
     gamma, beta = dev(torch.rand(cout, generator=g) + 0.5), dev(torch.randn(cout, generator=g))
     outs = []
-    for fused in (True, False):
+    for fused in ("in-kernel", True, False):
         mm, mv = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
         sc, sh, mean, inv = (torch.empty(cout, device="cuda") for _ in range(4))
-        if fused:
+        if fused == "in-kernel":
+            # the conv launch itself finalises (last-CTA ticket); run it twice: the ticket must come back to zero
+            fz = L.DgBnFused(gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99, mm.data_ptr(), mv.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                             mean.data_ptr(), inv.data_ptr(), N * Ho * Wo)
+            for rep in range(2):
+                mm.zero_(); mv.fill_(1.0)
+                part.fill_(float("nan"))
+                L.check(lib.dg_umma_conv2d_fwd_bn(ctx, C.byref(tx), pk.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp), part.data_ptr(),
+                                                  C.byref(fz), st))
+            torch.cuda.synchronize()
+            assert relerr(ybig[..., 16:16 + cout], y_ref) < BF16_TOL
+        elif fused:
             L.check(lib.dg_bn_finalize(ctx, part.data_ptr(), blocks, N * Ho * Wo, cout, gamma.data_ptr(), beta.data_ptr(), 1e-3, 0.99,
                                        mm.data_ptr(), mv.data_ptr(), sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), inv.data_ptr(), st))
         else:
@@ -720,8 +731,8 @@ def test_umma_conv_fused_bn_partials_and_slice_output(L, case):
                                     sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), inv.data_ptr(), wk.data_ptr(), nb, st))
         torch.cuda.synchronize()
         outs.append([t.clone() for t in (sc, sh, mean, inv, mm, mv)])
-    for a, b_ in zip(*outs):
-        assert relerr(a, b_) < 1e-5
+    for a, b_, c_ in zip(*outs):
+        assert relerr(a, c_) < 1e-5 and relerr(b_, c_) < 1e-5
 
 
 # ---------------------------------------------------------------- K-outer mode (streamed weights reused by several sub-tiles)
