@@ -243,6 +243,14 @@ def main():
     from denoise_gan_b200.graph import DevicePrefetcher
     for xd_, yd_ in DevicePrefetcher(((x_h, y_h) for _ in range(3)), torch.device("cuda", local)):   # untimed: first-use costs of the feed path
         torch.stack([v.detach().float().reshape(()) for v in run(xd_, yd_)]).tolist()
+    # diagnostic (untimed): one batch over PCIe with the GPU otherwise idle
+    hx0, hx1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xs_, ys_ = torch.empty_like(x_h, device="cuda"), torch.empty_like(y_h, device="cuda")
+    torch.cuda.synchronize()
+    hx0.record(); xs_.copy_(x_h, non_blocking=True); ys_.copy_(y_h, non_blocking=True); hx1.record()
+    torch.cuda.synchronize()
+    h2d_ms_idle = hx0.elapsed_time(hx1)
+    del xs_, ys_
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -251,22 +259,26 @@ def main():
     # dataset.prefetch); every one of the K host->device copies is enqueued and completed inside the timed region
     feed = DevicePrefetcher(((x_h, y_h) for _ in range(args.steps)), torch.device("cuda", local))
     # Losses come back through two pinned host buffers: the copy of step k's seven scalars is enqueued behind step k and
-    # the host consumes it after it has launched step k+1 (every step's result is read on the host inside the timed
+    # the host consumes it after it has launched step k+2 (every step's result is read on the host inside the timed
     # region; the last one before the closing event), so neither PCIe direction nor the graph launch idles the GPU.
     n_out = len(run.out) if not args.no_graph else 7
-    host_bufs = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(2)]
-    evs = [torch.cuda.Event(), torch.cuda.Event()]
-    pending, host_losses = None, []
+    LAG = 2                                     # the host reads step k's losses after it has launched step k+LAG
+    host_bufs = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    evs = [torch.cuda.Event() for _ in range(LAG + 1)]
+    inflight, host_losses = [], []
     for k, (xd_, yd_) in enumerate(feed):
         out = run(xd_, yd_)
-        host_bufs[k & 1].copy_(torch.stack([v.detach().float().reshape(()) for v in out]), non_blocking=True)
-        evs[k & 1].record()
-        if pending is not None:
-            evs[pending].synchronize()
-            host_losses.append(host_bufs[pending].tolist())
-        pending = k & 1
-    evs[pending].synchronize()
-    host_losses.append(host_bufs[pending].tolist())
+        s_ = k % (LAG + 1)
+        host_bufs[s_].copy_(torch.stack([v.detach().float().reshape(()) for v in out]), non_blocking=True)
+        evs[s_].record()
+        inflight.append(s_)
+        if len(inflight) > LAG:
+            o_ = inflight.pop(0)
+            evs[o_].synchronize()
+            host_losses.append(host_bufs[o_].tolist())
+    for o_ in inflight:
+        evs[o_].synchronize()
+        host_losses.append(host_bufs[o_].tolist())
     d2h = 4 * n_out
     assert len(host_losses) == args.steps and all(len(h) == n_out for h in host_losses)
     assert feed.h2d_bytes == args.steps * (x_h.numel() * 4 + y_h.numel() * 4)
@@ -320,7 +332,7 @@ def main():
                          "frac": ach / sustained, "traffic": CONV_TRAFFIC_BYTES.get(wl), "peak_source": peak_src + ", sustained figure (kernel timed inside a step)",
                          "conv_families": kinds, "conv_share_of_step": conv_ms / ms if args.no_graph else None},
             "e2e": {"value": world * batch / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_h.numel() * 4 + y_h.numel() * 4,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "h2d_ms_per_batch_gpu_idle": h2d_ms_idle},
             "gpu_launches": (kernel_nodes if kernel_nodes else abi_calls) * args.steps,
             "abi_calls_per_step": abi_calls,
             "kernel_nodes_per_step": kernel_nodes,

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < P.n_stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), do_bias ? 5 : 1);   // MMA commit (+ the four bias-summing warps)
     }
     mbar_init(smem_u32(&bar_done), 1);
     fence_mbar_init();
@@ -88,11 +88,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   if (warp == 1) {
     tmem_alloc(smem_u32(&tmem_slot), 512);
     tmem_relinquish();
-  }
-  if (do_bias) {  // constant ones tile: 128 pixels x kc channels of bf16 1.0 (layout-invariant)
-    uint32_t* ones = reinterpret_cast<uint32_t*>(base_ptr + P.ones_off);
-    for (int i = tid; i < 128 * P.kc / 2; i += WG_THREADS) ones[i] = 0x3F803F80u;
-    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -134,9 +129,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       const uint64_t b_hi = make_smem_desc_hi(b_sbo, P.b_layout) << 32;
       const uint32_t b_lo0 = ((P.dy_off >> 4) & 0x3FFFu) | (((P.dy_atom_bytes >> 4) & 0x3FFFu) << 16);
       const int ng = g_end - g_begin;
-      const uint64_t ones_hi = make_smem_desc_hi(8u * P.kc * 2u, P.a_layout) << 32;
-      const uint32_t ones_lo0 = (base + P.ones_off) >> 4;
-      const uint32_t ones_ks = (16u * P.kc * 2u) >> 4;
       const uint32_t nb = (uint32_t)P.nb, idesc = P.idesc, stage16 = P.stage_bytes >> 4, base16 = base >> 4;
       const int n_stages = P.n_stages;
       int stage = 0;
@@ -162,14 +154,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
               umma_f16(acc, a_hi | (uint64_t)(a_lo + (uint32_t)j * ks), bd, idesc, (first && j == 0) ? 0u : 1u);
             }
           }
-          if (do_bias) {
-            // ones tile: 8-pixel groups are 8*kc*2 bytes apart; LBO 0 => every M row reads the same data
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint64_t bd = b_hi | (uint64_t)(sa16 + b_lo0 + (uint32_t)j * b_kstep16);
-              umma_f16(tmem + (uint32_t)ng * nb, ones_hi | (uint64_t)(ones_lo0 + (uint32_t)j * ones_ks), bd, idesc, (first && j == 0) ? 0u : 1u);
-            }
-          }
           umma_commit(smem_u32(&bar_empty[stage]));
         }
         __syncwarp();
@@ -184,9 +168,62 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
     const int q = warp & 3;
     const int m = q * 32 + lane;
     if (q == 0 && lane == 0) wdbg(P, 2, 0, 0);
+    // db[o] = sum over pixels of dy: the four epilogue warps, idle until the accumulators are final, sum the columns of
+    // every dy tile straight from its pipeline stage (TMA swizzle undone in the address, one 16-byte load = 8 channels of
+    // one pixel) while the MMAs consume it.  This replaced an extra accumulator against a constant tile of ones.
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int et = tid - 64;                     // 0..127
+    const int CH = P.nb >> 3;                    // 8-channel chunks of the N block
+    const int RG = CH <= 128 ? 128 / CH : 1;     // row groups
+    const int chunk = et % CH, rg = et / CH;
+    const bool b_active = do_bias && rg < RG;
+    if (do_bias) {
+      const int c0 = 8 * chunk, atom_i = c0 / P.kco, cc = c0 - atom_i * P.kco;
+      const uint32_t row_pitch = (uint32_t)P.kco * 2u, mask = P.kco == 64 ? 7u : (P.kco == 32 ? 3u : 1u);
+      const uint32_t col_off = P.dy_off + (uint32_t)atom_i * P.dy_atom_bytes + (uint32_t)cc * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        if (b_active) {
+          const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
+#pragma unroll 4
+          for (int r = rg; r < 128; r += RG) {
+            const uint32_t off = col_off + (uint32_t)r * row_pitch;      // col_off is a multiple of 1024 plus < row_pitch bytes
+            const uint32_t rel = off - (P.dy_off + (uint32_t)atom_i * P.dy_atom_bytes);
+            const uint32_t addr = sa + P.dy_off + (uint32_t)atom_i * P.dy_atom_bytes + (rel ^ (((rel >> 7) & mask) << 4));
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr) : "memory");
+            bsum[0] += __uint_as_float(w0 << 16); bsum[1] += __uint_as_float(w0 & 0xFFFF0000u);
+            bsum[2] += __uint_as_float(w1 << 16); bsum[3] += __uint_as_float(w1 & 0xFFFF0000u);
+            bsum[4] += __uint_as_float(w2 << 16); bsum[5] += __uint_as_float(w2 & 0xFFFF0000u);
+            bsum[6] += __uint_as_float(w3 << 16); bsum[7] += __uint_as_float(w3 & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
+        if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
     mbar_wait(smem_u32(&bar_done), 0);
     tc_fence_after();
     if (q == 0 && lane == 0) wdbg(P, 2, 0, 1);
+    if (do_bias) {     // all MMAs have completed: the pipeline buffers are free, [128][8] floats of scratch
+      float* red = reinterpret_cast<float*>(base_ptr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[et * 8 + k] = bsum[k];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (b_active && rg == 0) {
+        float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t[k] += red[(g * CH + chunk) * 8 + k];
+        float* o = P.part + (long)blockIdx.x * P.part_stride + P.bias_off + nb0 + 8 * chunk;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = t[k];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the dump below stages through the same buffers
+    }
     float* part = P.part + (long)blockIdx.x * P.part_stride;
     const int atom = m / P.kc, r = m - atom * P.kc;
     if (P.dump_cw > 0) {
@@ -242,18 +279,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
           for (int k = 0; k < 4; ++k)
             o[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
                                __uint_as_float(v[4 * k + 3]));
-        }
-      }
-    }
-    if (do_bias) {
-      for (int c0 = 0; c0 < P.nb; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((g_end - g_begin) * P.nb + c0), v);
-        tmem_ld_wait();
-        if (m == 0) {
-          float* o = part + P.bias_off + nb0 + c0;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(v[k]);
         }
       }
     }

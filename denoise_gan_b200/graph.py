@@ -10,33 +10,36 @@ import torch
 
 class DevicePrefetcher:
     """Hands out the batches of a host `(input, target)` iterable as device tensors whose host->device copy was
-    enqueued ONE BATCH AHEAD on a copy stream, so the transfer of batch k+1 runs under train step k — the role of
-    `dataset.prefetch(AUTOTUNE)` in the reference input pipeline (dataloader.py:204-221).  Two device buffers per
-    tensor; pinned host batches are copied asynchronously as they are, pageable ones through pinned staging."""
+    enqueued up to `depth` BATCHES AHEAD on a copy stream, so the transfers of batches k+1, k+2 run under train step k —
+    the role of `dataset.prefetch(AUTOTUNE)` in the reference input pipeline (dataloader.py:204-221).  `depth + 1` device
+    buffers per tensor; pinned host batches are copied asynchronously as they are, pageable ones through pinned staging.
+    (depth 2: on some boxes a transfer running next to the step graph takes longer than one step.)"""
 
-    def __init__(self, dataset, device):
+    def __init__(self, dataset, device, depth: int = 2):
         self.it = iter(dataset)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
-        self.slots = [None, None]     # per slot: (x_dev, y_dev, x_pin, y_pin)
+        self.depth = max(1, int(depth))
+        self.slots = [None] * (self.depth + 1)     # per slot: (x_dev, y_dev, x_pin, y_pin)
         self.k = 0
-        self.pending = None           # (x_dev, y_dev, event) of the batch whose copy is in flight
+        self.pending = []             # (x_dev, y_dev, event) of the batches whose copies are in flight, oldest first
+        self.exhausted = False
         self.h2d_bytes = 0
 
     def _enqueue(self):
         try:
             x, y = next(self.it)
         except StopIteration:
-            self.pending = None
+            self.exhausted = True
             return
-        i = self.k & 1
+        i = self.k % len(self.slots)
         self.k += 1
         if self.slots[i] is None or self.slots[i][0].shape != x.shape or self.slots[i][1].shape != y.shape:
             self.slots[i] = (torch.empty(x.shape, dtype=x.dtype, device=self.device), torch.empty(y.shape, dtype=y.dtype, device=self.device),
                              None if x.is_pinned() else torch.empty(x.shape, dtype=x.dtype).pin_memory(),
                              None if y.is_pinned() else torch.empty(y.shape, dtype=y.dtype).pin_memory())
         xd, yd, xp, yp = self.slots[i]
-        # the slot was consumed by work already enqueued on the caller's stream (the step before last)
+        # the slot was consumed by work already enqueued on the caller's stream (depth + 1 batches ago)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         if xp is not None:
             self.stream.synchronize()             # the previous copy out of the pinned staging must have left it
@@ -48,20 +51,20 @@ class DevicePrefetcher:
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.h2d_bytes += x.numel() * x.element_size() + y.numel() * y.element_size()
-        self.pending = (xd, yd, ev)
+        self.pending.append((xd, yd, ev))
 
     def __iter__(self):
         return self
 
     def __next__(self):
-        if self.k == 0 and self.pending is None:
+        # keep `depth` transfers in flight behind the batch handed out now
+        while not self.exhausted and len(self.pending) < self.depth + 1:
             self._enqueue()
-        cur = self.pending
-        if cur is None:
+        if not self.pending:
             raise StopIteration
-        self._enqueue()                            # start the next transfer before the caller launches this step
-        torch.cuda.current_stream(self.device).wait_event(cur[2])
-        return cur[0], cur[1]
+        xd, yd, ev = self.pending.pop(0)
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return xd, yd
 
 
 class GraphedStep:

@@ -86,7 +86,7 @@ def main():
             elif kind == "dgrad":
                 L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(ty), pk1.data_ptr(), None, C.byref(tx), C.byref(cp), L.stream_ptr()))
             else:
-                L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(ty), dw.data_ptr(), db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, L.stream_ptr()))
+                L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(ty), dw.data_ptr(), None if os.environ.get('DG_BENCH_NO_DB') else db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, L.stream_ptr()))
 
         for i in range(3):
             run(i)
