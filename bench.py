@@ -101,10 +101,10 @@ class ClockSampler(threading.Thread):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant family's most frequent launch (64->64 3x3 conv of the
-# generator body, 66 of the 141 umma_conv launches of a step) from the `ncu --set full` capture in
-# profiles/ncu_body_conv_wgrad_r1c_details.csv; the algorithmic bytes of that launch are 37.8 MB (18.9 in + 18.9 out):
-# the output stays in the 126 MB L2 for the next kernel, the input is read from DRAM exactly once.
-CONV_TRAFFIC_BYTES = {"srgan_c3": 19.03e6}
+# generator body, 66 of the 116 umma_conv calls of a step) from the `ncu --set full` capture in
+# profiles/ncu_body_conv_r1h_raw.csv: 19.04 MB read, 0 written.  The algorithmic bytes of that launch are 37.8 MB (18.9 in +
+# 18.9 out): the input is read from DRAM exactly once and the output stays in the 126 MB L2 for the next kernel.
+CONV_TRAFFIC_BYTES = {"srgan_c3": 19.04e6}
 
 
 def make_model(wl, fp16=1, vgg=0):
@@ -241,7 +241,7 @@ def main():
     trace(f"device-resident timing done: {ms:.3f} ms/step")
     # ---- end-to-end through train_step with HOST batches: H2D of the batch + D2H of the 7 losses every step
     from denoise_gan_b200.graph import DevicePrefetcher
-    for xd_, yd_ in DevicePrefetcher(((x_h, y_h) for _ in range(3)), torch.device("cuda", local)):   # untimed: first-use costs of the feed path
+    for xd_, yd_ in DevicePrefetcher(((x_h, y_h) for _ in range(5)), torch.device("cuda", local), depth=3):   # untimed: first-use costs of the feed path
         torch.stack([v.detach().float().reshape(()) for v in run(xd_, yd_)]).tolist()
     # diagnostic (untimed): one batch over PCIe with the GPU otherwise idle
     hx0, hx1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,25 +251,32 @@ def main():
     torch.cuda.synchronize()
     h2d_ms_idle = hx0.elapsed_time(hx1)
     del xs_, ys_
+    # everything the timed loop needs is allocated BEFORE the region (cudaMalloc / cudaHostAlloc may synchronise the device
+    # and take milliseconds), and the Python garbage collector is parked: a single ~100 ms host stall inside a 40-step
+    # host-driven loop showed up as +2-3 ms per step on some runs
+    import gc
+    n_out = len(run.out) if not args.no_graph else 7
+    LAG = 4                                     # the host reads step k's losses after it has launched step k+LAG
+    host_bufs = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    evs = [torch.cuda.Event() for _ in range(LAG + 1)]
+    feed = DevicePrefetcher(((x_h, y_h) for _ in range(args.steps)), torch.device("cuda", local), depth=3).preallocate(x_h, y_h)
+    gc.collect()
+    gc.disable()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     d2h = 0
     # the batch of step k+1 crosses PCIe on a copy stream while step k runs (DevicePrefetcher = the reference pipeline's
     # dataset.prefetch); every one of the K host->device copies is enqueued and completed inside the timed region
-    feed = DevicePrefetcher(((x_h, y_h) for _ in range(args.steps)), torch.device("cuda", local))
-    # Losses come back through two pinned host buffers: the copy of step k's seven scalars is enqueued behind step k and
-    # the host consumes it after it has launched step k+2 (every step's result is read on the host inside the timed
+    # Losses come back through a small ring of pinned host buffers: the copy of step k's seven scalars is enqueued behind step k and
+    # the host consumes it after it has launched step k+4 (every step's result is read on the host inside the timed
     # region; the last one before the closing event), so neither PCIe direction nor the graph launch idles the GPU.
-    n_out = len(run.out) if not args.no_graph else 7
-    LAG = 2                                     # the host reads step k's losses after it has launched step k+LAG
-    host_bufs = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
-    evs = [torch.cuda.Event() for _ in range(LAG + 1)]
     inflight, host_losses = [], []
     for k, (xd_, yd_) in enumerate(feed):
         out = run(xd_, yd_)
         s_ = k % (LAG + 1)
-        host_bufs[s_].copy_(torch.stack([v.detach().float().reshape(()) for v in out]), non_blocking=True)
+        packed = run.packed if not args.no_graph else torch.stack([v.detach().float().reshape(()) for v in out])
+        host_bufs[s_].copy_(packed, non_blocking=True)
         evs[s_].record()
         inflight.append(s_)
         if len(inflight) > LAG:
@@ -284,6 +291,7 @@ def main():
     assert feed.h2d_bytes == args.steps * (x_h.numel() * 4 + y_h.numel() * 4)
     e3.record()
     barrier()
+    gc.enable()
     ms_e2e = e2.elapsed_time(e3) / args.steps
     trace("e2e timing done")
     clocks = sampler.stop() if sampler else None

@@ -26,6 +26,20 @@ class DevicePrefetcher:
         self.exhausted = False
         self.h2d_bytes = 0
 
+    def _slot(self, i, x, y):
+        if self.slots[i] is None or self.slots[i][0].shape != x.shape or self.slots[i][1].shape != y.shape:
+            self.slots[i] = (torch.empty(x.shape, dtype=x.dtype, device=self.device), torch.empty(y.shape, dtype=y.dtype, device=self.device),
+                             None if x.is_pinned() else torch.empty(x.shape, dtype=x.dtype).pin_memory(),
+                             None if y.is_pinned() else torch.empty(y.shape, dtype=y.dtype).pin_memory())
+        return self.slots[i]
+
+    def preallocate(self, x, y):
+        """Allocates every slot for batches shaped like (x, y) now, so that no cudaMalloc / cudaHostAlloc (both may
+        synchronise the device) happens while the pipeline is running."""
+        for i in range(len(self.slots)):
+            self._slot(i, x, y)
+        return self
+
     def _enqueue(self):
         try:
             x, y = next(self.it)
@@ -34,11 +48,7 @@ class DevicePrefetcher:
             return
         i = self.k % len(self.slots)
         self.k += 1
-        if self.slots[i] is None or self.slots[i][0].shape != x.shape or self.slots[i][1].shape != y.shape:
-            self.slots[i] = (torch.empty(x.shape, dtype=x.dtype, device=self.device), torch.empty(y.shape, dtype=y.dtype, device=self.device),
-                             None if x.is_pinned() else torch.empty(x.shape, dtype=x.dtype).pin_memory(),
-                             None if y.is_pinned() else torch.empty(y.shape, dtype=y.dtype).pin_memory())
-        xd, yd, xp, yp = self.slots[i]
+        xd, yd, xp, yp = self._slot(i, x, y)
         # the slot was consumed by work already enqueued on the caller's stream (depth + 1 batches ago)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         if xp is not None:
@@ -87,6 +97,9 @@ class GraphedStep:
             self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = step_fn(model, self.x, self.y)
+            # the step's scalar results as ONE fp32 vector (same order), so that a caller reads them with a single copy
+            scal = [v for v in self.out if isinstance(v, torch.Tensor) and v.numel() == 1]
+            self.packed = torch.stack([v.detach().float().reshape(()) for v in scal]) if scal else None
         self.kernel_nodes = self._count_kernel_nodes()
 
     def _count_kernel_nodes(self):
