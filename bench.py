@@ -309,6 +309,11 @@ def main():
         calls0 = _L.CALLS
         comm, model.comm = model.comm, None      # profile step is rank-0 only: no exchange, or the other ranks would be missed
         overlap, E.wgrad_overlap = E.wgrad_overlap, False   # one stream: per-kernel times are not stretched by a concurrent kernel
+        # Park the GPU for ~25 ms first: Python needs ~12 ms to enqueue the eager step, longer than the GPU needs to run it, and
+        # an event pair around a call would otherwise include the host's launch latency.  With the queue pre-filled every
+        # event pair brackets device time only.
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(0.025 * 1.9e9))
         train_step(model, run.x if not args.no_graph else x_h.cuda(), run.y if not args.no_graph else y_h.cuda())
         torch.cuda.synchronize()
         model.comm = comm
