@@ -18,9 +18,12 @@
 // instead of taps x.  Weight blocks [Cout_blk][chunk] (K-major) stay resident in shared memory
 // when they fit, else they stream with the halo stage.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
-// warps 2-5 epilogue (TMEM -> registers -> bias/activation -> global).  Three mbarrier pipelines:
-// halo stages (full/empty), TMEM accumulators (double-buffered full/empty), resident weights.
+// Warp roles (352 threads): warp 0 TMA producer, warps 1 and 6 TMEM allocator / MMA issuers (alternate tiles when four
+// accumulator buffers fit TMEM), warps 2-5 and 7-10 two epilogue groups on alternate tiles (TMEM -> registers -> bias /
+// activation -> shared-memory staging + TMA store, or direct global stores; optional BatchNorm statistics).  mbarrier
+// pipelines: halo stages (full/empty), TMEM accumulators (full/empty), resident weights, the K-outer weight ring.
+// Modes chosen on the host (launch_conv): resident / streamed / split-source / K-outer weights, 1-4 sub-tiles per tile,
+// one or four output phases (fused stride-2 dgrad), staged or direct epilogue.
 //
 // Reference call sites: Conv2D srgan.py:154-182,246-268, fsrgan.py:134-217, autoencoder.py:95-104,
 // pix2pix.py:115,207-218; Conv2DTranspose pix2pix.py:130,169; gradients train_srgan.py:111-112.
