@@ -282,7 +282,7 @@ int main() {
   }
 
   float* d_out; uint32_t* d_dump; int* d_status; ProbeCase* d_pc;
-  CK(cudaMalloc(&d_out, 128 * 256 * 4));
+  CK(cudaMalloc(&d_out, 128 * 512 * 4));   // timing cases dump up to 512 accumulator columns; the checked cases use <= 256
   CK(cudaMalloc(&d_dump, SMEM_DATA));
   CK(cudaMalloc(&d_status, 16));
   CK(cudaMalloc(&d_pc, sizeof(ProbeCase)));
@@ -535,14 +535,15 @@ int main() {
   {
     struct Off { uint32_t a, b; };
     auto timing2 = [&](const char* name, int M, int N, int a_mn, int b_mn, uint32_t layout, uint32_t a_sbo, uint32_t a_lbo,
-                       uint32_t b_sbo, uint32_t b_lbo, std::vector<Off> offs, int n_acc, int grid = 1) {
+                       uint32_t b_sbo, uint32_t b_lbo, std::vector<Off> offs, int n_acc, int grid = 1, int b_layout = -1) {
       ProbeCase pc = base_case();
       pc.loads[pc.n_loads++] = {0, 2, 0, 0, 0, 0, 0};
       pc.tx_bytes = 256 * 128;
       add_B64(pc, 5, 0, 256 * 128);
       pc.n_cols = N * (n_acc > 1 ? n_acc : 1);
       pc.idesc = sm100::make_idesc_bf16(M, N, a_mn, b_mn);
-      pc.a_layout = pc.b_layout = layout;
+      pc.a_layout = layout;
+      pc.b_layout = b_layout < 0 ? layout : (uint32_t)b_layout;
       pc.a_sbo = a_sbo; pc.a_lbo = a_lbo; pc.b_sbo = b_sbo; pc.b_lbo = b_lbo;
       for (auto& o : offs) pc.mma[pc.n_mma++] = {o.a, B_OFF + o.b};
       pc.repeat = 256; pc.n_acc = n_acc; pc.acc_stride = (uint32_t)N;
@@ -586,6 +587,22 @@ int main() {
     timing2("t2_k128_N16_acc4", 128, 16, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
     timing2("t2_k128_M64_N64_acc4", 64, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 4);
     timing2("t2_k128_M64_N256_acc1", 64, 256, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1);
+    // ---- thin-layer weight gradients (conv_umma_wgrad.cu, 16-channel x against 32-channel dy: 3->32 at 384^2 measured ~75
+    // cycles per 128x32x16 MMA in the kernel, tools/wgrad_timeline.py).  Timing only (operand values are irrelevant):
+    //  * the kernel's operands: A = MN-major 32-byte-swizzle halo windows (pixel rows 10 x 32 B = 320 B apart, eight taps
+    //    stacked along M through LBO = one pixel), B = MN-major 64-byte-swizzle dense dy tile;
+    //  * the same with DENSE A rows (256 B apart = whole 32-byte-swizzle atoms): is the 320-byte row pitch the cost?
+    //  * the TRANSPOSED formulation: A = dy^T padded to M = 64, B = taps x Cin = 144 columns of x.
+    std::vector<Off> thin8;
+    for (uint32_t k = 0; k < 8; ++k) thin8.push_back({k * 640, k * 1024});            // 16 pixels per MMA: 2 halo rows / 2 dy rows
+    timing2("t2_thin_wgrad_M128_N32_halo320", 128, 32, 1, 1, LAYOUT_SW32, 320, 32, 512, 4096, thin8, 2, 1, (int)LAYOUT_SW64);
+    std::vector<Off> thin8d;
+    for (uint32_t k = 0; k < 8; ++k) thin8d.push_back({k * 512, k * 1024});
+    timing2("t2_thin_wgrad_M128_N32_dense256", 128, 32, 1, 1, LAYOUT_SW32, 256, 32, 512, 4096, thin8d, 2, 1, (int)LAYOUT_SW64);
+    std::vector<Off> thinT;
+    for (uint32_t k = 0; k < 8; ++k) thinT.push_back({k * 1024, k * 640});
+    timing2("t2_thin_wgradT_M64_N144", 64, 144, 1, 1, LAYOUT_SW64, 512, 4096, 320, 32, thinT, 2, 1, (int)LAYOUT_SW32);
+    timing2("t2_thin_wgradT_M64_N160", 64, 160, 1, 1, LAYOUT_SW64, 512, 4096, 320, 32, thinT, 2, 1, (int)LAYOUT_SW32);
     // the same loops on every SM at once: chip-level (power) limits on the tensor pipe
     timing2("t3_allsm_k128_N64", 128, 64, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1, 148);
     timing2("t3_allsm_k128_N128", 128, 128, 0, 0, LAYOUT_SW128, 1024, 16, 1024, 16, k128x8, 1, 148);
