@@ -63,6 +63,8 @@ SIGNATURES = {
     "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_fwd_bn_blocks": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_fwd_bn": (_i, [_P, _T, _P, _P, _T, _CP, _P, C.POINTER(DgBnFused), _P]),
+    "dg_umma_conv2d_fwd_bn_act": (_i, [_P, _T, _P, _P, _T, _CP, _P, C.POINTER(DgBnFused), _i, _f, _P, _T, _T, _P]),
+    "dg_umma_conv2d_fwd_bn_act_blocks": (_i, [_P, _T, _T, _CP]),
     "dg_bn_finalize": (_i, [_P, _P, _i, C.c_longlong, _i, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _P]),
     "dg_umma_conv2d_dgrad_supported": (_i, [_P, _T, _T, _CP]),
     "dg_bias_grad": (_i, [_P, _T, _P, _i, _P, _sz, _P]),
@@ -143,6 +145,15 @@ def new_ctx(device: int):
     if rc != 0:
         raise DgError(lib.dg_last_error().decode())
     return h
+
+
+def destroy_ctx(h):
+    """Frees a context made by new_ctx (called from the owning Engine's finalizer)."""
+    try:
+        if _lib is not None and h:
+            _lib.dg_destroy(h)
+    except Exception:
+        pass
 
 
 CALLS = 0  # number of C-ABI compute calls issued (each enqueues >= 1 kernel)

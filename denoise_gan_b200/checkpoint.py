@@ -48,47 +48,44 @@ def state_dict(model) -> "OrderedDict[str, np.ndarray]":
 
 def load_state_dict(model, sd, strict: bool = True) -> list[str]:
     """Restores `state_dict(model)` output (or a weights-only subset with strict=False).  Returns the names that were
-    expected but absent (always empty when strict).  Shapes are checked against the model's architecture."""
+    expected but absent (always empty when strict).
+
+    Two phases: (1) every key and shape of BOTH networks, the optimiser moments and the counters is validated and staged as
+    host tensors without touching the model; (2) only then is the staged state copied in.  A mismatched or partial file
+    therefore raises with the model exactly as it was (no half-loaded generator next to a stale discriminator)."""
     missing: list[str] = []
     known = set()
+    staged = []            # (destination tensor, host source tensor)
+    meta = {}
+
+    def stage(key, shape, dst, dtype=np.float32):
+        known.add(key)
+        if key not in sd:
+            missing.append(key)
+            return
+        a = np.asarray(sd[key])
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{key}: checkpoint shape {tuple(a.shape)} != model shape {tuple(shape)}")
+        staged.append((dst, torch.from_numpy(np.ascontiguousarray(a.astype(dtype, copy=False)))))
+
+    # ---- phase 1: validate + stage (no writes into the model)
     for prefix, attr in _SETS:
         ps: ParamSet = getattr(model, attr)
-        tensors = OrderedDict()
         for name in list(ps.params) + list(ps.states):
-            key = f"{prefix}/{name}"
-            known.add(key)
-            if key in sd:
-                a = np.asarray(sd[key])
-                if tuple(a.shape) != ps[name].shape:
-                    raise ValueError(f"{key}: checkpoint shape {tuple(a.shape)} != model shape {ps[name].shape}")
-                tensors[name] = torch.from_numpy(a.astype(np.float32, copy=False))
-            else:
-                missing.append(key)
-        ps.load(tensors)
+            stage(f"{prefix}/{name}", ps[name].shape, ps[name].data)
         if ps.trainable:
             for name, p in ps.params.items():
                 sl = slice(p.offset, p.offset + p.numel)
-                for mom, arena in (("m", ps.m), ("v", ps.v)):
-                    key = f"{prefix}_opt/{mom}/{name}"
-                    known.add(key)
-                    if key in sd:
-                        a = np.asarray(sd[key])
-                        if tuple(a.shape) != p.shape:
-                            raise ValueError(f"{key}: checkpoint shape {tuple(a.shape)} != model shape {p.shape}")
-                        arena[sl].view(p.shape).copy_(torch.from_numpy(a.astype(np.float32, copy=False)))
-                    else:
-                        missing.append(key)
-            key = f"{prefix}_opt/state"
-            known.add(key)
-            if key in sd:
-                ps.opt_state.copy_(torch.from_numpy(np.asarray(sd[key]).astype(np.int64, copy=False)))
-            else:
-                missing.append(key)
-        _repack_in_place(model, ps)
+                stage(f"{prefix}_opt/m/{name}", p.shape, ps.m[sl].view(p.shape))
+                stage(f"{prefix}_opt/v/{name}", p.shape, ps.v[sl].view(p.shape))
+            stage(f"{prefix}_opt/state", tuple(ps.opt_state.shape), ps.opt_state, np.int64)
     for key, attr in (("meta/iterations", "iterations"), ("meta/epochs", "epochs")):
         known.add(key)
         if key in sd:
-            setattr(model, attr, int(np.asarray(sd[key])))
+            a = np.asarray(sd[key])
+            if a.size != 1:
+                raise ValueError(f"{key}: expected a scalar, got shape {tuple(a.shape)}")
+            meta[attr] = int(a.reshape(()))
         else:
             missing.append(key)
     if strict:
@@ -96,6 +93,13 @@ def load_state_dict(model, sd, strict: bool = True) -> list[str]:
         if missing or unexpected:
             raise KeyError(f"checkpoint does not match the model: missing {missing[:5]}{'...' if len(missing) > 5 else ''}, "
                            f"unexpected {unexpected[:5]}{'...' if len(unexpected) > 5 else ''}")
+    # ---- phase 2: commit
+    for dst, src in staged:
+        dst.copy_(src)
+    for attr, v in meta.items():
+        setattr(model, attr, v)
+    for _, attr in _SETS:
+        _repack_in_place(model, getattr(model, attr))
     return missing
 
 

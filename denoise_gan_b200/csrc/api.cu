@@ -9,6 +9,8 @@ static thread_local char g_err[1024] = "";
 
 int g_dg_pdl = []() { const char* e = getenv("DG_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // default OFF: inside the step's CUDA graph the early-launched CTAs cost more than the hidden launch latency (A/B: 8.43 vs 8.34 ms)
 
+int g_dg_coop = []() { const char* e = getenv("DG_COOP"); return (e && e[0] == '0') ? 0 : 1; }();   // cooperative-launch attribute of the grid-barrier kernels
+
 void dg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

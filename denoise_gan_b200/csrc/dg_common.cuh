@@ -57,6 +57,35 @@ static inline cudaError_t dg_pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim
   cfg.numAttrs = g_dg_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// ---- cooperative launch: kernels that contain a grid-wide barrier (the one-launch BatchNorm forward / backward, the
+// convolution with a fused BatchNorm phase) need EVERY block resident at the same time.  dg_coresident() checks that the
+// grid fits the device at this block size / shared memory (an empty device: occupancy x SM count), and the launch carries
+// cudaLaunchAttributeCooperative, so that the driver schedules the grid only when all of its blocks can be resident --
+// other work sharing the device (side-stream weight gradients, another context, MPS) can delay it but cannot leave
+// part of the grid spinning on blocks that never start.  Callers fall back to their multi-kernel path when the check fails.
+extern int g_dg_coop;   // 0 drops the attribute (DG_COOP=0; debugging only), api.cu
+template <typename K>
+static inline bool dg_coresident(K kernel, int block_threads, size_t smem, long grid_blocks, int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_threads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return (long)per_sm * sm_count >= grid_blocks;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dg_coop_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_dg_coop ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
 
 // ---- element access for the two storage types

@@ -96,7 +96,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
   save_invstd[c] = invstd;
   if (moving_mean) {
     moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
-    moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + (float)(var * ((double)P / (double)(P > 1 ? P - 1 : 1))) * (1.f - momentum);   // Bessel-corrected, as Keras' fused path
   }
 }
 
@@ -571,7 +571,8 @@ extern "C" int dg_bn_train_fwd(dg_ctx* ctx, const dg_tensor* x, const float* gam
   View rv = residual ? view_of(residual) : View{0, 0};
   DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_train_fwd", {
     red8_optin(dgvec::bn_fwd_fused8_kernel<TI, TO>, dgvec::red8_smem(C, 2));
-    dg_pdl_launch(dgvec::bn_fwd_fused8_kernel<TI, TO>, dim3(blocks), dim3(dgvec::RT), dgvec::red8_smem(C, 2), ST, (const TI*)x->ptr,
+    if (!dg_coresident(dgvec::bn_fwd_fused8_kernel<TI, TO>, dgvec::RT, dgvec::red8_smem(C, 2), blocks, ctx->sm_count)) return 2;   // grid barrier inside
+    dg_coop_launch(dgvec::bn_fwd_fused8_kernel<TI, TO>, dim3(blocks), dim3(dgvec::RT), dgvec::red8_smem(C, 2), ST, (const TI*)x->ptr,
                   dgvec::VView{x->cpitch, x->coff}, P, C, (float*)workspace, ctx->tickets, gamma, beta, eps, momentum, moving_mean,
                   moving_var, scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha,
                   residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, dropout, seed, offset, step_counter,
@@ -605,9 +606,9 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
     static const char* env_fused = getenv("DG_BN_FUSED_BWD");
     const bool fused_bwd = !(env_fused && env_fused[0] == '0');
 #define DG_BN_BWD_VEC(AM)                                                                                                        \
-  if (fused_bwd) {                                                                                                               \
-    red8_optin(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dgvec::red8_smem(C, 3));                                               \
-    dg_pdl_launch(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,        \
+  if (fused_bwd && (red8_optin(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dgvec::red8_smem(C, 3)),                               \
+                    dg_coresident(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dgvec::RT, dgvec::red8_smem(C, 3), vblocks, ctx->sm_count))) { \
+    dg_coop_launch(dgvec::bn_bwd_fused8_kernel<TI, TO, TI, AM>, dim3(vblocks), dim3(dgvec::RT), dgvec::red8_smem(C, 3), ST,        \
         (const TI*)dy->ptr, vdy, (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act, act_alpha, prelu_alpha,  \
         dropout, seed, offset, step_counter, P, C, partial, ctx->tickets, dgamma, dbeta,                                         \
         act == DG_ACT_PRELU ? dprelu_alpha : nullptr, accumulate, coef, (TI*)dx->ptr, vdx);                                      \
@@ -636,7 +637,7 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
 #define DG_BN_BWD_CACHED(AM)                                                                                                      \
   {                                                                                                                              \
     cudaFuncSetAttribute(dgvec::bn_bwd_cached8_kernel<AM, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);          \
-    dg_pdl_launch(dgvec::bn_bwd_cached8_kernel<AM, KC>, dim3(vblocks), dim3(dgvec::RT), smem_c, ST,                                \
+    dg_coop_launch(dgvec::bn_bwd_cached8_kernel<AM, KC>, dim3(vblocks), dim3(dgvec::RT), smem_c, ST,                                \
         (const __nv_bfloat16*)dy->ptr, vdy, (const __nv_bfloat16*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act,    \
         act_alpha, prelu_alpha, P, C, partial, ctx->tickets, dgamma, dbeta, act == DG_ACT_PRELU ? dprelu_alpha : nullptr,        \
         accumulate, coef, (__nv_bfloat16*)dx->ptr, vdx, (unsigned)red);                                                          \

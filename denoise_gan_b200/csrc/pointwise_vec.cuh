@@ -287,7 +287,7 @@ bn_stats8_kernel(const T* __restrict__ x, VView xv, long P, int C, float* __rest
         save_invstd[c] = invstd;
         if (moving_mean) {
           moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
-          moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+          moving_var[c] = moving_var[c] * momentum + (float)(var * ((double)P / (double)(P > 1 ? P - 1 : 1))) * (1.f - momentum);   // Bessel-corrected, as Keras' fused path
         }
       });
 }
@@ -426,7 +426,7 @@ bn_fwd_fused8_kernel(const TI* __restrict__ x, VView xv, long P, int C, float* _
         save_invstd[c] = invstd;
         if (moving_mean) {
           moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
-          moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+          moving_var[c] = moving_var[c] * momentum + (float)(var * ((double)P / (double)(P > 1 ? P - 1 : 1))) * (1.f - momentum);   // Bessel-corrected, as Keras' fused path
         }
       });
   grid_flag_barrier(last, ticket + 1, ticket + 2);

@@ -13,6 +13,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -30,12 +31,13 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done")
+    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
         self.bn_part = None     # (partials [blocks,2,C], blocks) when the producing conv reduced the BatchNorm statistics
         self.bn_done = None     # (name, scale, shift, mean, invstd) when the producing conv ALSO finalised them (last-CTA ticket)
+        self.bn_applied = None  # (y_act, act, alpha, prelu, residual) when the producing conv ALSO applied BatchNorm + activation (+ skip)
 
     @property
     def shape(self):
@@ -80,7 +82,10 @@ class Engine:
         self.lib = _ProfLib(_lib.load(), self)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self._in_side = False
-        self._ctx_main = _lib.ctx(self.device.index)
+        # every Engine owns its contexts (ticket counters / reduction scratch are per context and assume ONE stream per
+        # context): two engines in a process, or an engine next to direct C-ABI callers, never share counters
+        self._ctx_main = _lib.new_ctx(self.device.index)
+        weakref.finalize(self, _lib.destroy_ctx, self._ctx_main)
         self._ctx_side = None          # private context (reduction scratch) of the side stream, created on first use
         self.bf16 = bool(bf16)
         self.act_dtype = torch.bfloat16 if bf16 else torch.float32
@@ -96,6 +101,9 @@ class Engine:
         # ... and their finalize by the conv's last CTA (dg_umma_conv2d_fwd_bn): OFF by default, measured slower in the step graph
         # (7.54 vs 7.45 ms, 403 vs 446 kernel nodes): the serial tail on one CTA costs more than the 8-block finalize launch
         self.fuse_conv_bn_finalize = os.environ.get("DG_CONV_BN_FINALIZE", "0") == "1"
+        # conv + BatchNorm(train) + activation (+ skip-add) as ONE cooperative launch where all output tiles of a CTA fit TMEM
+        # (dg_umma_conv2d_fwd_bn_act): the generator trunk and most discriminator layers lose the finalize and the apply launch
+        self.fuse_conv_bn_act = os.environ.get("DG_CONV_BN_ACT", "1") != "0"
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
         # dgrad / BatchNorm chain of the backward pass (joined at the end of backward())
         self.wgrad_overlap = os.environ.get("DG_WGRAD_OVERLAP", "1") != "0"
@@ -156,6 +164,7 @@ class Engine:
         if self._in_side:
             if self._ctx_side is None:
                 self._ctx_side = _lib.new_ctx(self.device.index)
+                weakref.finalize(self, _lib.destroy_ctx, self._ctx_side)
             return self._ctx_side
         return self._ctx_main
 
@@ -265,6 +274,12 @@ class Engine:
             self.pool[k] = t
         return t
 
+    def _copy_vec(self, src: torch.Tensor, dst: torch.Tensor, n: int):
+        """dst[:n] = src[:n] for 1-D fp32 vectors, through the C ABI (no torch kernel inside the captured step)."""
+        ts = _lib.DgTensor(src.data_ptr(), _lib.DG_F32, 1, 1, 1, n, src.numel(), 0)
+        td = _lib.DgTensor(dst.data_ptr(), _lib.DG_F32, 1, 1, 1, n, dst.numel(), 0)
+        check(self.lib.dg_copy(self.ctx, C.byref(ts), C.byref(td), 0, self.st))
+
     def _conv2d_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype):
         """conv2d when Cin or Cout is not a multiple of 16 (the 3-channel image side of srgan.py:154,182,236): operands are
         zero-padded to 16 channels in bf16 (dg_pad_channels / dg_umma_pack_weights_padded), the tcgen05 kernels run on the
@@ -306,10 +321,10 @@ class Engine:
                 bias = b.data.data_ptr()
             else:
                 bp = self._zeros((seq, "bias_p"), (cout_p,), torch.float32)
-                bp[:cout].copy_(b.data)
+                self._copy_vec(b.data, bp, cout)
                 bias = bp.data_ptr()
         txi, typ = tensor(xin), tensor(yp)
-        flops = 2.0 * N * Ho * Wo * kh * kw * cin_p * cout_p
+        flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout      # ALGORITHMIC: the zero-padded channels are not counted
         pk = self._packed(w, 0)
         self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
             self.ctx, C.byref(txi), pk.data_ptr(), bias, C.byref(typ), C.byref(cp), None, self.st)))
@@ -362,9 +377,12 @@ class Engine:
         return out
 
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
-               out_dtype=None, bn: bool = False) -> Var:
+               out_dtype=None, bn: bool = False, post: dict | None = None) -> Var:
         """keras Conv2D (+bias, +activation epilogue).  `bn=True`: a training-mode BatchNormalization consumes the result
-        next, so the tensor-core epilogue also produces its batch-statistics partials (picked up by bn_act)."""
+        next, so the tensor-core epilogue also produces its batch-statistics partials (picked up by bn_act).
+        `post` = dict(act=, alpha=, prelu=, residual=) describes what the bn_act call that FOLLOWS will do with the result; when
+        the layer qualifies, convolution, statistics, normalisation, activation and skip-add run as one cooperative launch
+        and bn_act only records the tape node."""
         N, H, W, Cin = x.shape
         kh, kw, cin, cout = w.shape
         assert cin == Cin, f"{w.name}: Cin {cin} != input {Cin}"
@@ -384,7 +402,7 @@ class Engine:
         tx, ty = tensor(x.t), tensor(y)
         bias = _lib.ptr(b.data) if b is not None else None
         flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
-        bn_part = bn_done = None
+        bn_part = bn_done = bn_applied = None
         if umma_f:
             pk = self._packed(w, 0)
             if bn and self.fuse_conv_bn_stats and act is None:
@@ -395,7 +413,35 @@ class Engine:
                     self._cap[key] = blocks
                 if blocks > 0:
                     bn_part = (self.buf((seq, "bn_part"), (blocks, 2, cout), torch.float32), blocks)
-            if bn_part and isinstance(bn, tuple) and self.fuse_conv_bn_finalize and cout <= 512:
+            fused_post = None
+            if (post is not None and isinstance(bn, tuple) and self.fuse_conv_bn_act and act is None and y.dtype == torch.bfloat16 and
+                    (post.get("residual") is None or post["residual"].t.dtype == torch.bfloat16)):
+                keyp = ("bnact", N, H, W, cin, Ho, Wo, cout, kh, kw, stride, pt, pl)
+                pblocks = self._cap.get(keyp)
+                if pblocks is None:
+                    pblocks = int(self.lib.dg_umma_conv2d_fwd_bn_act_blocks(self.ctx, C.byref(tx), C.byref(ty), C.byref(cp)))
+                    self._cap[keyp] = pblocks
+                if pblocks > 0:
+                    fused_post = pblocks
+            if fused_post:
+                bp, bname, bmom, beps = bn
+                part = self.buf((seq, "bn_part"), (fused_post, 2, cout), torch.float32)
+                coef = [self.buf((seq, "bn_" + k), (cout,), torch.float32) for k in ("scale", "shift", "mean", "invstd")]
+                y_act = self.buf((seq, "y_act"), (N, Ho, Wo, cout), torch.bfloat16)
+                fz = _lib.DgBnFused(bp[bname + "/gamma"].data.data_ptr(), bp[bname + "/beta"].data.data_ptr(), float(beps), float(bmom),
+                                    bp[bname + "/moving_mean"].data.data_ptr(), bp[bname + "/moving_variance"].data.data_ptr(),
+                                    coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), N * Ho * Wo)
+                p_act, p_alpha, p_prelu, p_res = post.get("act"), float(post.get("alpha", 0.0)), post.get("prelu"), post.get("residual")
+                a_code = ACT["prelu"] if p_prelu is not None else ACT[p_act]
+                tres = tensor(p_res.t) if p_res is not None else None
+                tya = tensor(y_act)
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd_bn_act(
+                    self.ctx, C.byref(tx), pk.data_ptr(), bias, C.byref(ty), C.byref(cp), part.data_ptr(), C.byref(fz), a_code, p_alpha,
+                    _lib.ptr(p_prelu.data) if p_prelu is not None else None, C.byref(tres) if tres is not None else None, C.byref(tya), self.st)))
+                bn_done = (bname, *coef)
+                bn_part = None
+                bn_applied = (y_act, p_act, p_alpha, p_prelu, p_res)
+            elif bn_part and isinstance(bn, tuple) and self.fuse_conv_bn_finalize and cout <= 512:
                 # (pset, name, momentum, eps): the conv's last CTA also turns the partial rows into the BatchNorm coefficients
                 bp, bname, bmom, beps = bn
                 coef = [self.buf((seq, "bn_" + k), (cout,), torch.float32) for k in ("scale", "shift", "mean", "invstd")]
@@ -415,6 +461,7 @@ class Engine:
         out = Var(y, self._deps([x], w.group), seq)
         out.bn_part = bn_part
         out.bn_done = bn_done
+        out.bn_applied = bn_applied
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag):
             dpre = gy
@@ -554,10 +601,10 @@ class Engine:
         bias = None
         if b is not None:
             bp = self._zeros((seq, "bias_p"), (cout_p,), torch.float32)
-            bp[:cout].copy_(b.data)
+            self._copy_vec(b.data, bp, cout)
             bias = bp.data_ptr()
         tx, typ = tensor(x.t), tensor(yp)
-        flops = 2.0 * N * H * W * kh * kw * cin * cout_p
+        flops = 2.0 * N * H * W * kh * kw * cin * cout        # ALGORITHMIC: the zero-padded channels are not counted
         pk1 = self._packed(w, 1)
         self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
             self.ctx, C.byref(tx), pk1.data_ptr(), bias, C.byref(typ), C.byref(cp), self.st)))
@@ -649,12 +696,19 @@ class Engine:
         tx = tensor(x.t)
         nbytes = self.lib.dg_bn_workspace_bytes(C.byref(tx))
         ws = self.workspace(nbytes)
-        y = self.buf((seq, "y"), x.shape, x.t.dtype)
+        drop = 1 if (dropout_seed is not None and training) else 0
+        applied = getattr(x, "bn_applied", None) if (training and bn_done is not None and not drop) else None
+        if applied is not None:
+            # the producing convolution already normalised, activated and added the skip connection (one cooperative launch)
+            y, f_act, f_alpha, f_prelu, f_res = applied
+            assert (f_act or None) == (act or None) and f_prelu is prelu and f_res is residual and \
+                (act != "lrelu" or abs(f_alpha - float(alpha)) < 1e-12), f"{name}: fused conv epilogue does not match this bn_act call"
+        else:
+            y = self.buf((seq, "y"), x.shape, x.t.dtype)
         ty = tensor(y)
         tres = tensor(residual.t) if residual is not None else None
-        drop = 1 if (dropout_seed is not None and training) else 0
         a_code = ACT["prelu"] if prelu is not None else ACT[act]
-        fused = False
+        fused = applied is not None
         bn_part = getattr(x, "bn_part", None)
         if bn_done is not None:
             pass    # scale/shift/mean/invstd and the moving statistics were written by the producing convolution

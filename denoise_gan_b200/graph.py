@@ -21,6 +21,7 @@ class DevicePrefetcher:
         self.stream = torch.cuda.Stream(device=self.device)
         self.depth = max(1, int(depth))
         self.slots = [None] * (self.depth + 1)     # per slot: (x_dev, y_dev, x_pin, y_pin)
+        self.copied = [None] * (self.depth + 1)    # per slot: event recorded after the copies that READ its pinned staging
         self.k = 0
         self.pending = []             # (x_dev, y_dev, event) of the batches whose copies are in flight, oldest first
         self.exhausted = False
@@ -49,17 +50,22 @@ class DevicePrefetcher:
         i = self.k % len(self.slots)
         self.k += 1
         xd, yd, xp, yp = self._slot(i, x, y)
-        # the slot was consumed by work already enqueued on the caller's stream (depth + 1 batches ago)
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         if xp is not None:
-            self.stream.synchronize()             # the previous copy out of the pinned staging must have left it
+            # pageable batch: it goes through this slot's pinned staging.  Only the copy that last READ that staging
+            # (depth + 1 batches ago) has to be finished before the host overwrites it -- not the whole copy stream,
+            # and certainly not the train step just enqueued on the caller's stream.
+            if self.copied[i] is not None:
+                self.copied[i].synchronize()
             xp.copy_(x); yp.copy_(y)
             x, y = xp, yp
+        # the slot's device buffers were consumed by work already enqueued on the caller's stream (depth + 1 batches ago)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             xd.copy_(x, non_blocking=True)
             yd.copy_(y, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self.copied[i] = ev
         self.h2d_bytes += x.numel() * x.element_size() + y.numel() * y.element_size()
         self.pending.append((xd, yd, ev))
 

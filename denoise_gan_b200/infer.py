@@ -5,8 +5,8 @@ Reference: infer_video.py:92-97 (model re-wrapped on Input((None,None,3)), train
 pre/post), :79-83 (padded size); infer.py:38-68 (still images); unit_test.py:56-86 (256x256 crops).
 
 Only uint8 frames cross PCIe: the crop-or-pad, scaling and channel flip run on the device
-(csrc/frames.cu) next to the forward; host staging buffers are pinned and double-buffered so the copy of frame
-i+1 overlaps the forward of frame i.  Frames shard round-robin across ranks with no collective
+(csrc/frames.cu) next to the forward; host staging buffers are pinned and double-buffered in BOTH directions, so the
+upload of frame i+1 and the download of frame i-1 overlap the forward of frame i (`FrameRunner.video`).  Frames shard round-robin across ranks with no collective
 (`frames_for_rank`).
 """
 from __future__ import annotations
@@ -42,8 +42,10 @@ class FrameRunner:
     def __init__(self, model, upscale: int | None = None):
         self.model, self.E = model, model.engine
         self.upscale = int(upscale if upscale is not None else getattr(model, "scale", 1))
-        self.copy_stream = torch.cuda.Stream(device=self.E.device)
+        self.copy_stream = torch.cuda.Stream(device=self.E.device)       # uploads
+        self.d2h_stream = torch.cuda.Stream(device=self.E.device)        # downloads
         self._pin: dict = {}
+        self._pin_ev: dict = {}       # pinned staging buffer -> event after the last device copy that read it
 
     # ---- device-side pieces
     def _to_float(self, frame_dev: torch.Tensor, out_h: int, out_w: int, flip: bool, norm_mode: int, scale: float, offset: float):
@@ -74,20 +76,25 @@ class FrameRunner:
         if frame.is_cuda:
             return frame
         stage = self._pinned(("in", slot), frame.shape)
+        ev = self._pin_ev.get(("in", slot))
+        if ev is not None:
+            ev.synchronize()          # the previous asynchronous copy OUT of this pinned buffer (video_frame(..., to_host=False))
         stage.copy_(frame)
         dev = self.E.buf(("infer_u8", slot), tuple(frame.shape), torch.uint8)
         dev.copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        self._pin_ev[("in", slot)] = ev
         return dev
 
     # ---- the three reference call sites
-    def video_frame(self, frame_bgr, to_host: bool = True):
+    def video_frame(self, frame_bgr, to_host: bool = True, out_slot: int = 0):
         """infer_video.py:138-159: BGR uint8 [fh,fw,3] -> RGB uint8 [fh*s, fw*s, 3]."""
         f = _u8(frame_bgr)
         fh, fw = f.shape[:2]
         nh, nw = padded_size(fh, fw)
         x = self._to_float(self._h2d(f), nh, nw, flip=True, norm_mode=0, scale=2.0, offset=-1.0)
         y = self.forward(x)
-        out = self._to_frame(y, fh * self.upscale, fw * self.upscale, 0.5, 0.5, clip=True, flip=False)
+        out = self._to_frame(y, fh * self.upscale, fw * self.upscale, 0.5, 0.5, clip=True, flip=False, slot=out_slot)
         return self._d2h(out) if to_host else out
 
     def still_image(self, img_bgr, to_host: bool = True):
@@ -112,9 +119,13 @@ class FrameRunner:
         torch.cuda.current_stream().synchronize()
         return host.clone()
 
-    def video(self, frames, rank: int = 0, world: int = 1):
+    def video(self, frames, rank: int = 0, world: int = 1, copy: bool = True):
         """Generator over (index, RGB uint8 frame) for this rank's round-robin shard of `frames` (a sequence of BGR
-        uint8 frames).  The upload of the next frame runs on a copy stream under the current forward."""
+        uint8 frames).  Three things overlap: the upload of frame k+1 (copy stream), the forward of frame k (main stream)
+        and the download of frame k-1 (second copy stream, into one of two pinned buffers); the host only ever waits for
+        the download event of the frame it is about to hand out, never for the compute stream.  With `copy=False` the
+        yielded tensor IS the pinned staging buffer: valid until the generator has been advanced twice more (the
+        reference writes each frame to its video sink immediately, infer_video.py:160-170)."""
         idx = list(frames_for_rank(len(frames), rank, world))
         if not idx:
             return
@@ -124,21 +135,37 @@ class FrameRunner:
             f = _u8(frames[idx[k]])
             slot = k & 1
             stage = self._pinned(("in", slot), f.shape)
+            ev0 = self._pin_ev.get(("in", slot))
+            if ev0 is not None:
+                ev0.synchronize()           # the copy that last read this staging buffer (frame k-2)
             stage.copy_(f)
             dev = self.E.buf(("infer_u8", slot), tuple(f.shape), torch.uint8)
             with torch.cuda.stream(self.copy_stream):
                 dev.copy_(stage, non_blocking=True)
                 ev = torch.cuda.Event(); ev.record()
+            self._pin_ev[("in", slot)] = ev
             return dev, ev
 
+        pending = None                      # (frame index, pinned host buffer, download-finished event) of frame k-1
         nxt = upload(0)
         for k in range(len(idx)):
             dev, ev = nxt
             main.wait_event(ev)
-            out = self.video_frame(dev, to_host=False)
+            slot = k & 1
+            out = self.video_frame(dev, to_host=False, out_slot=slot)     # device result slot: its previous download (frame k-2) was waited for below
+            done = torch.cuda.Event(); done.record(main)
             if k + 1 < len(idx):
-                nxt = upload(k + 1)          # other slot; its last reader (frame k-1) finished before the previous yield
-            host = self._pinned(("out", 0), out.shape)
-            host.copy_(out, non_blocking=True)
-            main.synchronize()
-            yield idx[k], host.clone()
+                nxt = upload(k + 1)         # other input slot
+            host = self._pinned(("out", slot), out.shape)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(done)
+                host.copy_(out, non_blocking=True)
+                hev = torch.cuda.Event(); hev.record()
+            if pending is not None:
+                pi, ph, pe = pending
+                pe.synchronize()
+                yield pi, (ph.clone() if copy else ph)
+            pending = (idx[k], host, hev)
+        pi, ph, pe = pending
+        pe.synchronize()
+        yield pi, (ph.clone() if copy else ph)

@@ -36,15 +36,15 @@ class SRGANGenerator(_Net):
 
     def __call__(self, x, training=True) -> Var:
         E, p = self.E, self.p
-        n = E.conv2d(self._in(x), p["g/conv_in/kernel"], bn=self._bn("g/bn_in", training))
+        n = E.conv2d(self._in(x), p["g/conv_in/kernel"], bn=self._bn("g/bn_in", training), post=dict(prelu=p["g/prelu_in/alpha"]))
         n = E.bn_act(n, p, "g/bn_in", training=training, prelu=p["g/prelu_in/alpha"])
         temp = E.mark("g/prelu_in", n)
         for i in range(16):
-            nn = E.conv2d(n, p[f"g/res{i}/conv1/kernel"], bn=self._bn(f"g/res{i}/bn1", training))
+            nn = E.conv2d(n, p[f"g/res{i}/conv1/kernel"], bn=self._bn(f"g/res{i}/bn1", training), post=dict(act="relu"))
             nn = E.bn_act(nn, p, f"g/res{i}/bn1", training=training, act="relu")
-            nn = E.conv2d(nn, p[f"g/res{i}/conv2/kernel"], bn=self._bn(f"g/res{i}/bn2", training))
+            nn = E.conv2d(nn, p[f"g/res{i}/conv2/kernel"], bn=self._bn(f"g/res{i}/bn2", training), post=dict(residual=n))
             n = E.mark(f"g/res{i}/add", E.bn_act(nn, p, f"g/res{i}/bn2", training=training, residual=n))
-        n2 = E.conv2d(n, p["g/conv_post/kernel"], bn=self._bn("g/bn_post", training))
+        n2 = E.conv2d(n, p["g/conv_post/kernel"], bn=self._bn("g/bn_post", training), post=dict(residual=temp))
         n = E.mark("g/post_add", E.bn_act(n2, p, "g/bn_post", training=training, residual=temp))
         for j in range(self.scale // 2):
             u = E.conv2d(n, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"])
@@ -69,7 +69,7 @@ class PatchDiscriminator(_Net):
             if i == 1:
                 d = E.conv2d(d, w, b, stride=s, act="lrelu", alpha=0.2)
             else:
-                d = E.conv2d(d, w, b, stride=s, bn=self._bn(f"{px}/bn{i}", training, momentum=0.8))
+                d = E.conv2d(d, w, b, stride=s, bn=self._bn(f"{px}/bn{i}", training, momentum=0.8), post=dict(act="lrelu", alpha=0.2))
                 d = E.bn_act(d, p, f"{px}/bn{i}", training=training, momentum=0.8, act="lrelu", alpha=0.2)
             E.mark(f"{px}/lrelu{i}", d)
         return E.conv2d(d, p[f"{px}/logits/kernel"], p[f"{px}/logits/bias"], act="sigmoid" if self.sigmoid else None,
@@ -118,13 +118,15 @@ class FastSRGANGenerator(_Net):
         for i in range(self.n_blocks):
             t = r
             if i:
-                t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"], bn=self._bn(f"g/b{i}/expand_bn", training, momentum=0.999))
+                t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"], bn=self._bn(f"g/b{i}/expand_bn", training, momentum=0.999),
+                             post=dict(act="relu"))
                 t = E.bn_act(t, p, f"g/b{i}/expand_bn", training=training, momentum=0.999, act="relu")
             t = E.dwconv3x3(t, p[f"g/b{i}/dw/kernel"], p[f"g/b{i}/dw/bias"])
             t = E.bn_act(t, p, f"g/b{i}/dw_bn", training=training, momentum=0.999, act="relu")
-            t = E.conv2d(t, p[f"g/b{i}/project/kernel"], p[f"g/b{i}/project/bias"], bn=self._bn(f"g/b{i}/project_bn", training, momentum=0.999))
+            t = E.conv2d(t, p[f"g/b{i}/project/kernel"], p[f"g/b{i}/project/bias"], bn=self._bn(f"g/b{i}/project_bn", training, momentum=0.999),
+                         post=dict(residual=r))
             r = E.bn_act(t, p, f"g/b{i}/project_bn", training=training, momentum=0.999, residual=r)
-        c2 = E.conv2d(r, p["g/c2/kernel"], p["g/c2/bias"], bn=self._bn("g/c2_bn", training))
+        c2 = E.conv2d(r, p["g/c2/kernel"], p["g/c2/bias"], bn=self._bn("g/c2_bn", training), post=dict(residual=c1))
         u = E.bn_act(c2, p, "g/c2_bn", training=training, residual=c1)
         for j in range(2):
             u = E.d2s_prelu(E.conv2d(u, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"]), p[f"g/up{j}/prelu/alpha"])
@@ -169,7 +171,7 @@ class Pix2PixGenerator(_Net):
             if i == 0:
                 t = E.conv2d(t, w, None, stride=2, act="lrelu", alpha=0.3)
             else:
-                t = E.conv2d(t, w, None, stride=2, bn=self._bn(f"g/down{i}/bn", training))
+                t = E.conv2d(t, w, None, stride=2, bn=self._bn(f"g/down{i}/bn", training), post=dict(act="lrelu", alpha=0.3))
                 t = E.bn_act(t, p, f"g/down{i}/bn", training=training, act="lrelu", alpha=0.3)
             skips.append(t)
         skips = list(reversed(skips[:-1]))
@@ -191,8 +193,8 @@ class Pix2PixDiscriminator(_Net):
         t = E.concat([E.cast(self._in(inp), E.act_dtype), E.cast(self._in(tar), E.act_dtype)])
         t = E.conv2d(t, p["d/down1/conv/kernel"], None, stride=2, act="lrelu", alpha=0.3)
         for i in (2, 3):
-            t = E.conv2d(t, p[f"d/down{i}/conv/kernel"], None, stride=2, bn=self._bn(f"d/down{i}/bn", training))
+            t = E.conv2d(t, p[f"d/down{i}/conv/kernel"], None, stride=2, bn=self._bn(f"d/down{i}/bn", training), post=dict(act="lrelu", alpha=0.3))
             t = E.bn_act(t, p, f"d/down{i}/bn", training=training, act="lrelu", alpha=0.3)
-        t = E.conv2d(t, p["d/conv4/kernel"], None, stride=1, padding=((1, 1), (1, 1)), bn=self._bn("d/bn4", training))
+        t = E.conv2d(t, p["d/conv4/kernel"], None, stride=1, padding=((1, 1), (1, 1)), bn=self._bn("d/bn4", training), post=dict(act="lrelu", alpha=0.3))
         t = E.bn_act(t, p, "d/bn4", training=training, act="lrelu", alpha=0.3)
         return E.conv2d(t, p["d/last/kernel"], p["d/last/bias"], stride=1, padding=((1, 1), (1, 1)), out_dtype=torch.float32)

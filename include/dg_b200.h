@@ -98,6 +98,15 @@ typedef struct {
 } dg_bn_fused;
 int dg_umma_conv2d_fwd_bn(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
                           const dg_conv_params* p, float* bn_partials, const dg_bn_fused* bn, void* stream);
+/* Conv2D + training-mode BatchNormalization + activation (+ Add) in ONE cooperative launch: srgan.py:154-157 (conv, BN,
+ * PReLU), :162-169 (conv, BN, ReLU, conv, BN, Add), :246-250 (conv, BN, LeakyReLU); fsrgan.py:208-210.  y = raw conv output
+ * (kept for the backward pass), out = act(BN_batch(y)) (+ residual); bn receives scale/shift/mean/invstd and the
+ * moving-statistics update.  dg_umma_conv2d_fwd_bn_act_blocks() = rows of the [rows][2][Cout] fp32 statistics workspace, or
+ * 0 when the fused phase does not apply to the layer (the caller then issues the three separate calls). */
+int dg_umma_conv2d_fwd_bn_act(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                              const dg_conv_params* p, float* bn_partials, const dg_bn_fused* bn, int act, float act_alpha,
+                              const float* prelu_alpha, const dg_tensor* residual, const dg_tensor* out, void* stream);
+int dg_umma_conv2d_fwd_bn_act_blocks(dg_ctx*, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p);
 int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,
                          const dg_tensor* dx, const dg_conv_params* p, void* stream);
 /* capability queries: 1 when the tensor-core kernels have a tile configuration for the layer (shared-memory fit);

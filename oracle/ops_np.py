@@ -96,8 +96,15 @@ def batch_norm_infer(x, gamma, beta, mean, var, eps=1e-3):
 
 
 def moving_update(moving, batch, momentum):
-    """Keras moving statistic: moving*m + batch*(1-m); the fused path feeds the biased variance."""
+    """Keras moving statistic: moving*m + batch*(1-m).  For the moving VARIANCE pass bessel(var, P): the fused path
+    (4-D NHWC inputs) feeds the Bessel-corrected estimate."""
     return moving * momentum + batch * (1.0 - momentum)
+
+
+def bessel(var, n_reduced):
+    """Unbiased variance from the biased one over `n_reduced` = N*H*W samples (what Keras' fused BatchNormalization
+    stores into moving_variance; `_bessels_correction_test_only = True` leaves FusedBatchNorm's correction in place)."""
+    return var * (n_reduced / max(n_reduced - 1, 1))
 
 
 def depth_to_space(x, block=2):

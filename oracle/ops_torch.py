@@ -62,8 +62,10 @@ def depthwise_conv2d(x, w, b=None):
 
 
 def batch_norm(x, p, prefix, training, state_out, momentum=0.99, eps=1e-3):
-    """BatchNormalization (srgan.py:155,248; fsrgan.py:140; pix2pix.py:119).  Training: batch mean and
-    biased variance; moving <- moving*m + batch*(1-m) (biased variance, Keras fused path)."""
+    """BatchNormalization (srgan.py:155,248; fsrgan.py:140; pix2pix.py:119).  Training: normalise with the batch mean and
+    the BIASED variance; moving <- moving*m + batch*(1-m), where the moving VARIANCE takes the Bessel-corrected estimate
+    var*P/(P-1): 4-D NHWC inputs go through Keras' fused path, whose FusedBatchNorm op returns the unbiased variance and
+    whose `_bessels_correction_test_only = True` default leaves it in place (keras/layers/normalization.py, TF 2.1-2.4)."""
     gamma, beta = p[prefix + "/gamma"], p[prefix + "/beta"]
     if training:
         mean = x.mean(dim=(0, 1, 2))
@@ -72,7 +74,9 @@ def batch_norm(x, p, prefix, training, state_out, momentum=0.99, eps=1e-3):
             mm = state_out.get(prefix + "/moving_mean", p[prefix + "/moving_mean"])
             mv = state_out.get(prefix + "/moving_variance", p[prefix + "/moving_variance"])
             state_out[prefix + "/moving_mean"] = (mm * momentum + mean.detach() * (1 - momentum)).detach()
-            state_out[prefix + "/moving_variance"] = (mv * momentum + var.detach() * (1 - momentum)).detach()
+            n = x.shape[0] * x.shape[1] * x.shape[2]
+            var_u = var.detach() * (n / max(n - 1, 1))
+            state_out[prefix + "/moving_variance"] = (mv * momentum + var_u * (1 - momentum)).detach()
     else:
         mean, var = p[prefix + "/moving_mean"], p[prefix + "/moving_variance"]
     return gamma * (x - mean) * torch.rsqrt(var + eps) + beta

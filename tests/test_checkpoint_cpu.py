@@ -70,3 +70,41 @@ def test_weights_only_and_mismatches():
     extra = CK.state_dict(a); extra["gen/not_a_layer/kernel"] = np.zeros(3, np.float32)
     with pytest.raises(KeyError):
         CK.load_state_dict(_model(2), extra, strict=True)
+
+
+def test_failed_load_leaves_the_model_untouched():
+    """load_state_dict validates every key and shape of BOTH networks before it copies anything: a file whose generator part
+    is fine but whose discriminator part is wrong (or absent under strict) must not leave the generator half-loaded."""
+    a = _model(0)
+    for make_bad in ("disc_shape", "disc_missing_strict", "unexpected_strict"):
+        b, ref = _model(9), _model(9)
+        _scramble(b, 1); _scramble(ref, 1)
+        sd = dict(CK.state_dict(a))
+        if make_bad == "disc_shape":
+            sd["disc/d/conv8/kernel"] = np.zeros((3, 3, 64, 32), np.float32)
+            with pytest.raises(ValueError):
+                CK.load_state_dict(b, sd, strict=False)
+        elif make_bad == "disc_missing_strict":
+            sd = {k: v for k, v in sd.items() if not k.startswith("disc")}
+            with pytest.raises(KeyError):
+                CK.load_state_dict(b, sd, strict=True)
+        else:
+            sd["gen/not_a_layer/kernel"] = np.zeros(3, np.float32)
+            with pytest.raises(KeyError):
+                CK.load_state_dict(b, sd, strict=True)
+        _same(b, ref)
+
+
+def test_keras_named_weights_only_file_round_trip(tmp_path):
+    """The documented path for real weights: a weights-only .npz in Keras variable layouts (what tools/h5_to_npz.py writes from
+    a Keras .h5: Conv2D kernels [kh,kw,Cin,Cout], BN gamma/beta/moving_*) loads with strict=False and leaves the optimiser cold."""
+    a = _model(3)
+    keras_like = {"gen/" + n: p.data.numpy().copy() for n, p in list(a.gen_params.params.items()) + list(a.gen_params.states.items())}
+    path = str(tmp_path / "weights_only.npz")
+    np.savez(path, **keras_like)
+    b = _model(11)
+    missing = CK.load(b, path, strict=False)
+    assert all(not k.startswith("gen/") for k in missing) and any(k.startswith("gen_opt/") for k in missing)
+    for n in list(a.gen_params.params) + list(a.gen_params.states):
+        assert torch.equal(a.gen_params[n].data, b.gen_params[n].data), n
+    assert float(b.gen_params.m.abs().sum()) == 0.0 and int(b.gen_params.opt_state[0]) == 0

@@ -735,6 +735,93 @@ def test_umma_conv_fused_bn_partials_and_slice_output(L, case):
         assert relerr(a, c_) < 1e-5 and relerr(b_, c_) < 1e-5
 
 
+# ---------------------------------------------------------------- conv + BatchNorm + activation (+ Add) in one cooperative launch
+@pytest.mark.parametrize("case", [(3, 1, 64, 64, 2, 24, 20, "relu", False, True), (3, 1, 64, 64, 16, 96, 96, "relu", False, False),
+                                  (3, 1, 64, 64, 16, 96, 96, None, True, False), (3, 1, 16, 64, 4, 32, 32, "prelu", False, False),
+                                  (3, 1, 32, 32, 3, 40, 24, "lrelu", False, True), (3, 2, 32, 32, 2, 48, 40, "lrelu", False, True),
+                                  (3, 1, 32, 64, 2, 33, 19, None, True, True), (3, 1, 64, 16, 1, 20, 12, "relu", True, False),
+                                  (1, 1, 192, 32, 2, 16, 16, None, True, False), (3, 1, 64, 64, 5, 96, 96, "relu", True, False)])
+def test_umma_conv_bn_act_one_launch(L, case):
+    """dg_umma_conv2d_fwd_bn_act (conv -> batch statistics -> grid barrier -> scale/shift -> activation (+ skip) from the
+    TMEM-resident accumulators) against the three separate calls it replaces (dg_umma_conv2d_fwd with bn_partials,
+    dg_bn_finalize, dg_bn_act_fwd): the raw conv output and the activated output must be BIT-identical, the BatchNorm
+    coefficients and moving statistics equal to fp32 rounding; and against the float64 oracle within the bf16 bound.
+    Run twice back to back: the grid-barrier counters must re-arm (srgan.py:154-157,162-169,246-250)."""
+    k, s, cin, cout, N, H, W, act, with_res, bias = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * (1.0 / (k * np.sqrt(cin))))
+    b = torch.randn(cout, generator=g, dtype=torch.float64) if bias else None
+    gamma = torch.rand(cout, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(cout, generator=g, dtype=torch.float64) * 0.3
+    alpha = torch.rand(cout, generator=g, dtype=torch.float64) * 0.4
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, s, H, W, "same")
+    Ho, Wo = -(-H // s), -(-W // s)
+    res = _bf16_round(torch.randn(N, Ho, Wo, cout, generator=g, dtype=torch.float64)) if with_res else None
+    xd, wd = dev(x, torch.bfloat16), dev(w)
+    bd = dev(b) if bias else None
+    gd, bed, ad = dev(gamma), dev(beta), dev(alpha)
+    resd = dev(res, torch.bfloat16) if with_res else None
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 0, st))
+    a_code = {None: 0, "relu": 1, "lrelu": 2, "prelu": 5}[act]
+    y0 = torch.empty(N, Ho, Wo, cout, device="cuda", dtype=torch.bfloat16); a0 = torch.empty_like(y0)
+    y1 = torch.empty_like(y0); a1 = torch.empty_like(y0)
+    tx = L.tensor(xd)
+    blocks = lib.dg_umma_conv2d_fwd_bn_act_blocks(ctx, C.byref(tx), C.byref(L.tensor(y1)), C.byref(cp))
+    if blocks == 0:
+        assert (k, s, cin, cout) != (3, 1, 64, 64), "the fused BatchNorm phase must apply to the generator trunk layers"
+        pytest.skip("no fused BatchNorm phase for this layer (tiles do not all fit TMEM, or streamed weights): the engine issues the three separate calls")
+    P_ = N * Ho * Wo
+
+    def coeffs():
+        return [torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")] + [torch.empty(cout, device="cuda") for _ in range(4)]   # mm, mv, sc, sh, mean, inv
+
+    # ---- reference: the three separate launches
+    c0 = coeffs()
+    rows = lib.dg_umma_conv2d_fwd_bn_blocks(ctx, C.byref(tx), C.byref(L.tensor(y0)), C.byref(cp))
+    assert rows > 0
+    part0 = torch.empty(rows, 2, cout, device="cuda")
+    ty0, ta0 = L.tensor(y0), L.tensor(a0)
+    L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk.data_ptr(), L.ptr(bd), C.byref(ty0), C.byref(cp), part0.data_ptr(), st))
+    L.check(lib.dg_bn_finalize(ctx, part0.data_ptr(), rows, P_, cout, gd.data_ptr(), bed.data_ptr(), 1e-3, 0.8, c0[0].data_ptr(), c0[1].data_ptr(),
+                               c0[2].data_ptr(), c0[3].data_ptr(), c0[4].data_ptr(), c0[5].data_ptr(), st))
+    tres = L.tensor(resd) if with_res else None
+    L.check(lib.dg_bn_act_fwd(ctx, C.byref(ty0), c0[2].data_ptr(), c0[3].data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None,
+                              C.byref(tres) if with_res else None, 0, 0, 0, None, C.byref(ta0), st))
+    # ---- the fused launch, twice (moving statistics reset in between)
+    part1 = torch.full((blocks, 2, cout), float("nan"), device="cuda")
+    ty1, ta1 = L.tensor(y1), L.tensor(a1)
+    for rep in range(2):
+        c1 = coeffs()
+        y1.fill_(7.0); a1.fill_(7.0)
+        fz = L.DgBnFused(gd.data_ptr(), bed.data_ptr(), 1e-3, 0.8, c1[0].data_ptr(), c1[1].data_ptr(), c1[2].data_ptr(), c1[3].data_ptr(),
+                         c1[4].data_ptr(), c1[5].data_ptr(), P_)
+        L.check(lib.dg_umma_conv2d_fwd_bn_act(ctx, C.byref(tx), pk.data_ptr(), L.ptr(bd), C.byref(ty1), C.byref(cp), part1.data_ptr(), C.byref(fz),
+                                              a_code, 0.2, ad.data_ptr() if act == "prelu" else None, C.byref(tres) if with_res else None,
+                                              C.byref(ta1), st))
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y0), "raw conv output differs from the unfused launch"
+        for u, v in zip(c1, c0):
+            assert relerr(u, v) < 1e-6
+        if all(torch.equal(u, v) for u, v in zip(c1[2:4], c0[2:4])):
+            assert torch.equal(a1, a0), "activated output differs from dg_bn_act_fwd on the stored conv output"
+        else:       # coefficients differ in the last bit (different summation grouping of the partial rows): outputs within one bf16 ulp
+            assert relerr(a1, a0) < 2 ** -7
+    # ---- oracle (float64) on the same bf16-rounded operands
+    yr = OT.conv2d(x, w, b, stride=s, padding="same")
+    p = {"bn/gamma": gamma, "bn/beta": beta, "bn/moving_mean": torch.zeros(cout, dtype=torch.float64), "bn/moving_variance": torch.ones(cout, dtype=torch.float64)}
+    stt = {}
+    t = OT.batch_norm(yr, p, "bn", True, stt, momentum=0.8, eps=1e-3)
+    if act == "relu": t = torch.relu(t)
+    elif act == "lrelu": t = OT.leaky_relu(t, 0.2)
+    elif act == "prelu": t = OT.prelu(t, alpha)
+    if with_res: t = t + res
+    assert relerr(y1, yr) < BF16_TOL and relerr(a1, t) < BF16_TOL
+    assert relerr(c1[0], stt["bn/moving_mean"]) < 2e-2 and relerr(c1[1], stt["bn/moving_variance"]) < 2e-2
+
+
 # ---------------------------------------------------------------- K-outer mode (streamed weights reused by several sub-tiles)
 @pytest.mark.parametrize("case", [(3, 256, 64, 2, 70, 20, "dgrad"), (3, 256, 64, 1, 64, 24, "fwd"), (3, 128, 256, 2, 40, 17, "fwd"),
                                   (3, 256, 256, 1, 48, 16, "fwd"), (1, 512, 64, 2, 33, 9, "fwd"), (3, 192, 96, 1, 30, 30, "dgrad")])

@@ -74,9 +74,27 @@ def test_batch_norm_train_and_moving():
     yn, mean, var = N.batch_norm_train(x, g, b, 1e-3)
     np.testing.assert_allclose(y, yn, atol=1e-10)
     np.testing.assert_allclose(st["bn/moving_mean"].numpy(), N.moving_update(0.0, mean, 0.8), atol=1e-12)
-    np.testing.assert_allclose(st["bn/moving_variance"].numpy(), N.moving_update(1.0, var, 0.8), atol=1e-12)  # biased var
+    # moving variance: Bessel-corrected batch variance (Keras fused path, `_bessels_correction_test_only = True`)
+    np.testing.assert_allclose(st["bn/moving_variance"].numpy(), N.moving_update(1.0, N.bessel(var, 3 * 4 * 5), 0.8), atol=1e-12)
     yi = T.batch_norm(t(x), p, "bn", False, None).numpy()
     np.testing.assert_allclose(yi, N.batch_norm_infer(x, g, b, 0.0, 1.0), atol=1e-10)
+
+
+def test_batch_norm_moving_variance_small_batch_keras_formula():
+    """pix2pix bottleneck maps (2x2 and 1x1 pixels at batch 1-4): the unbiased estimate differs from the biased one by
+    P/(P-1), up to 33 % at P = 4; P = 1 keeps the biased value (0) instead of dividing by zero."""
+    for shape in ((1, 2, 2, 5), (2, 1, 1, 5), (1, 1, 1, 5)):
+        x = rng.standard_normal(shape)
+        P_ = shape[0] * shape[1] * shape[2]
+        p = {"bn/gamma": torch.ones(5, dtype=torch.float64), "bn/beta": torch.zeros(5, dtype=torch.float64),
+             "bn/moving_mean": torch.zeros(5, dtype=torch.float64), "bn/moving_variance": torch.ones(5, dtype=torch.float64)}
+        st = {}
+        T.batch_norm(t(x), p, "bn", True, st, momentum=0.99, eps=1e-3)
+        var_b = x.reshape(-1, 5).var(axis=0)                       # biased
+        var_u = x.reshape(-1, 5).var(axis=0, ddof=1) if P_ > 1 else var_b
+        np.testing.assert_allclose(st["bn/moving_variance"].numpy(), 0.99 * 1.0 + 0.01 * var_u, atol=1e-12)
+        if P_ == 4:
+            np.testing.assert_allclose(var_u / np.maximum(var_b, 1e-30), 4.0 / 3.0, rtol=1e-9)
 
 
 def test_activations_pool_upsample():
