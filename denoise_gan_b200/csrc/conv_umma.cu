@@ -645,10 +645,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       mbar_init(smem_u32(&bar_we[b]), 1);
     }
     fence_mbar_init();
+    if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0) P.dbg[192] = clock64();
     // the resident weights start loading before the CTA-wide sync, under the TMEM allocation of warp 1
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
     tma_prefetch_desc(&P.wmap);
     if (P.tstore) tma_prefetch_desc(&P.omap);
+    if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0) P.dbg[193] = clock64();
     if (P.resident) {
       const uint32_t bw = smem_u32(&bar_w);
       mbar_expect_tx(bw, P.w_res_tx);
@@ -659,15 +661,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
                     (P.tap_w[t] * P.n_chunks + kc) * P.cout_total + nb0);
       }
     }
+    if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0) P.dbg[194] = clock64();
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(&tmem_slot), 512);
     tmem_relinquish();
+    if (P.dbg && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) P.dbg[195] = clock64();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (P.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { P.dbg[196] = clock64(); P.dbg[197] = P.dbg[256]; }
   pdl_wait();   // everything above (barriers, TMEM, the constant weights) overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -1173,8 +1178,9 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
     // the fused BatchNorm phase needs: the staged epilogue, ONE N block holding all output channels (<= 64), and every tile
     // of a CTA resident in TMEM at once
     const int per_cta = (total_tiles_pre + ctas_pre - 1) / ctas_pre;
+    // (the skip-connection tiles of pass 2 travel through the halo stages: a stage must hold one staged tile)
     const bool ok = ts && nb == cout && cout <= 64 && !split && !kouter && n_phase == 1 && per_cta <= MAX_ACC && per_cta * mt * nb <= 512 &&
-                    ctas_pre <= ctx->sm_count;
+                    ctas_pre <= ctx->sm_count && stage_bytes_pre >= stg_bytes;
     if (!ok) {
       if (bn_blocks) *bn_blocks = 0;
       DG_FAIL("%s: the fused BatchNorm phase does not apply to this layer (tiles per CTA %d x mt %d x nb %d columns)", name, per_cta, mt, nb);

@@ -102,8 +102,10 @@ class Engine:
         # (7.54 vs 7.45 ms, 403 vs 446 kernel nodes): the serial tail on one CTA costs more than the 8-block finalize launch
         self.fuse_conv_bn_finalize = os.environ.get("DG_CONV_BN_FINALIZE", "0") == "1"
         # conv + BatchNorm(train) + activation (+ skip-add) as ONE cooperative launch where all output tiles of a CTA fit TMEM
-        # (dg_umma_conv2d_fwd_bn_act): the generator trunk and most discriminator layers lose the finalize and the apply launch
-        self.fuse_conv_bn_act = os.environ.get("DG_CONV_BN_ACT", "1") != "0"
+        # (dg_umma_conv2d_fwd_bn_act): the generator trunk and most discriminator layers lose the finalize and the apply launch.
+        # OFF by default: measured SLOWER in the step graph (7.57 vs 7.42 ms, same box, job r2_03) -- the tensor pipe idles
+        # through the grid barrier and pass 2, and a cooperative launch cannot overlap its neighbours' tails
+        self.fuse_conv_bn_act = os.environ.get("DG_CONV_BN_ACT", "0") == "1"
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
         # dgrad / BatchNorm chain of the backward pass (joined at the end of backward())
         self.wgrad_overlap = os.environ.get("DG_WGRAD_OVERLAP", "1") != "0"
@@ -477,6 +479,13 @@ class Engine:
             if need_in[0]:
                 dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
                 tdx = tensor(dx)
+                if umma_d and dpre.dtype != torch.bfloat16 and x.t.dtype == torch.bfloat16:
+                    # fp32 output layer (VGG19 block5_conv4 feeding the fp32 feature loss, srgan.py:92): its gradient is rounded
+                    # to bf16 once so that the input gradient runs on the tensor cores like every other layer
+                    d16 = self.buf((seq, "dpre16", tag), dpre.shape, torch.bfloat16)
+                    ts_, td_ = tensor(dpre), tensor(d16)
+                    check(self.lib.dg_copy(self.ctx, C.byref(ts_), C.byref(td_), 0, self.st))
+                    dpre, tdp = d16, td_
                 if umma_d and dpre.dtype == torch.bfloat16:
                     pk = self._packed(w, 1)
                     self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(

@@ -47,6 +47,10 @@ for role, rn in enumerate(["producer", "mma", "epilogue"]):
             continue
         print("  tile", it, "  ".join(f"{names[role][s]}={int(row[s]) - t0}" for s in range(4) if int(row[s]) > 0))
 
+pro = dbg.cpu()[192:198]
+e0 = int(life[0, 0])
+print("prologue of CTA 0 (cycles after kernel entry): barriers initialised", int(pro[0]) - e0, "| descriptors prefetched", int(pro[1]) - e0,
+      "| weight loads issued", int(pro[2]) - e0, "| TMEM allocated (warp 1)", int(pro[3]) - e0, "| past the CTA-wide sync", int(pro[4]) - e0)
 cyc = (life[:, 1] - life[:, 0]).float()
 ns0, ns1 = life[:, 2].min().item(), life[:, 3].max().item()
 print(f"CTA lifetimes: min {cyc.min().item():.0f} mean {cyc.mean().item():.0f} max {cyc.max().item():.0f} cycles; "
