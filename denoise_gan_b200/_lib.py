@@ -34,6 +34,11 @@ class DgBnFused(C.Structure):      # include/dg_b200.h: dg_bn_fused
                 ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p), ("pixels", C.c_longlong)]
 
 
+class DgBnBwdStats(C.Structure):  # include/dg_b200.h: dg_bn_bwd_stats
+    _fields_ = [("y", C.POINTER(DgTensor)), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("act", C.c_int32),
+                ("alpha", C.c_float), ("partials", C.c_void_p)]
+
+
 class DgError(RuntimeError):
     pass
 
@@ -51,6 +56,13 @@ SIGNATURES = {
     "dg_last_error": (C.c_char_p, []),
     "dg_version": (_i, []),
     "dg_has_umma": (_i, [_P]),
+    "dg_comm_unique_id_bytes": (_i, []),
+    "dg_comm_unique_id": (_i, [_P]),
+    "dg_comm_init": (_i, [C.POINTER(_P), _P, _i, _i, _i]),
+    "dg_comm_allreduce": (_i, [_P, _P, C.c_longlong, _P]),
+    "dg_comm_rank": (_i, [_P]),
+    "dg_comm_world": (_i, [_P]),
+    "dg_comm_destroy": (None, [_P]),
     "dg_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),
@@ -60,12 +72,16 @@ SIGNATURES = {
     "dg_umma_pack_weights_batch": (_i, [_P, _P, _i, _P]),
     "dg_umma_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
+    "dg_umma_conv2d_dgrad_fused": (_i, [_P, _T, _P, _T, _CP, _T, C.POINTER(DgBnBwdStats), _P]),
+    "dg_umma_conv2d_dgrad_fused_blocks": (_i, [_P, _T, _T, _CP]),
+    "dg_bn_bwd_dx_from_partials": (_i, [_P, _T, _T, _P, _P, _P, _P, _P, _i, _f, _P, _i, _T, _P, _P, _i, _P]),
     "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_fwd_bn_blocks": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_fwd_bn": (_i, [_P, _T, _P, _P, _T, _CP, _P, C.POINTER(DgBnFused), _P]),
     "dg_umma_conv2d_fwd_bn_act": (_i, [_P, _T, _P, _P, _T, _CP, _P, C.POINTER(DgBnFused), _i, _f, _P, _T, _T, _P]),
     "dg_umma_conv2d_fwd_bn_act_blocks": (_i, [_P, _T, _T, _CP]),
     "dg_bn_finalize": (_i, [_P, _P, _i, C.c_longlong, _i, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _P]),
+    "dg_bn_act_fwd_from_partials": (_i, [_P, _T, _P, _i, _P, _P, _f, _f, _P, _P, _P, _P, _P, _P, _i, _f, _P, _T, _T, _P]),
     "dg_umma_conv2d_dgrad_supported": (_i, [_P, _T, _T, _CP]),
     "dg_bias_grad": (_i, [_P, _T, _P, _i, _P, _sz, _P]),
     "dg_pad_channels": (_i, [_P, _T, _T, _P]),

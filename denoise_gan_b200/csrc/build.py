@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["api.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_wgrad.cu", "pointwise.cu", "dwconv.cu", "frames.cu", "loss_adam.cu"]
+SOURCES = ["api.cu", "comm.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_wgrad.cu", "pointwise.cu", "dwconv.cu", "frames.cu", "loss_adam.cu"]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + ["../../include/dg_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -58,7 +58,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

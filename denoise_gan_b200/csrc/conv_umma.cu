@@ -98,6 +98,20 @@ struct UmmaConvParams {
   const float* bnp_prelu;
   CUtensorMap omap2, rmap;
   unsigned* gbar;       // [0] arrivals, [1] departures of the grid barrier (self-resetting)
+  // BatchNorm-backward epilogue ("bwd", kernel instance umma_conv_kernel<true>): the launch is an input-gradient convolution
+  // whose result is g = dL/da for the output a = act(BN(yb)) (+ skip) of a training-mode BatchNormalization (srgan.py:162-169:
+  // the dgrad of every trunk convolution feeds the backward pass of the BatchNorm in front of it).  The epilogue
+  //   * adds the gradient that arrives over the skip connection (bwd_res, srgan.py:169 Add) -- no separate add launch,
+  //   * stores g (bf16, staged TMA store), and
+  //   * accumulates from the rounded g the two per-channel sums of the BatchNorm backward pass, sum g' and sum g' (yb - mean)
+  //     with g' = g * act'(scale * yb + shift), into the per-CTA rows `bn_partials` ([gridDim.x][2][Cout]),
+  // so that the BatchNorm backward pass is ONE read of g and yb (dg_bn_bwd_dx_from_partials) instead of two.
+  int bwd_am;                      // -1: no statistics; 0 none / 1 relu / 2 leaky relu: activation behind the BatchNorm
+  const __nv_bfloat16* bwd_y;      // yb, the BatchNorm input (same pixel grid as the output), first channel of the view
+  const __nv_bfloat16* bwd_res;    // skip-connection gradient or nullptr
+  long bwd_y_sn, bwd_y_sh, bwd_y_sw, bwd_r_sn, bwd_r_sh, bwd_r_sw;   // element strides
+  const float *bwd_scale, *bwd_shift, *bwd_mean;
+  float bwd_alpha;
   const float* bias;
   int act;
   float alpha;
@@ -577,6 +591,151 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
 
 #undef DG_GROUP_SYNC
 
+// Sum over the 32 lanes of a warp of x[i] for each of 32 values i, transposed: lane l returns the total of x[l].  Each step
+// halves the values a lane carries (it keeps the half named by one bit of its lane index and hands the other half to its
+// partner), 31 shuffles in all instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? x[i + h] : x[i];
+      const float send = up ? x[i] : x[i + h];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return x[0];
+}
+
+__device__ __forceinline__ uint4 ldg_v4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// Epilogue of the BatchNorm-backward instance (UmmaConvParams::bwd_*).  Thread = accumulator row = one output pixel; it
+// fetches its pixel's skip gradient and BatchNorm input straight from global memory (NB x 2 bytes each, issued before the wait
+// for the accumulator), adds, rounds to bf16, stages the row for the bulk store, and feeds g' and g'(yb - mean) of 16 channels
+// at a time to the transposed warp sum: lane l < 16 ends up owning sum g' of channel 16k + l, lane l >= 16 sum g'(yb - mean) of
+// channel 16k + l - 16, for its warp's rows.
+template <int AM, int NB>
+__device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int nb0,
+                                                  int total_tiles, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, float* red_s, int grp,
+                                                  const float* __restrict__ cs) {
+  constexpr int NV = NB / 8, NG = NB / 16;
+  const uint32_t bar_id = 1u + (uint32_t)grp;
+  const int m_idx = q * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t RB = (uint32_t)NB * 2u, mask = P.stg_mask;
+  const bool leader = q == 0 && lane == 0;
+  const bool has_res = P.bwd_res != nullptr;
+  const uint32_t stg = stg_base + (uint32_t)grp * P.stg_bytes;
+  float asum[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) asum[k] = 0.f;
+  int it = grp;
+  for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
+    const int b = it & ((1 << P.nbuf_shift) - 1);
+    const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
+    const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h, n = t2 / P.tiles_h;
+    for (int m = 0; m < P.mt; ++m) {
+      const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
+      const int pw = tw * 8 + (m_idx & 7);
+      const bool valid = ph < P.out_h && pw < P.out_w;
+      uint4 ry[NV], rr[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { ry[j] = make_uint4(0u, 0u, 0u, 0u); rr[j] = make_uint4(0u, 0u, 0u, 0u); }
+      if (valid && !(P.dbg_flags & 64)) {
+        if (AM >= 0) {
+          const __nv_bfloat16* yp = P.bwd_y + ((long)n * P.bwd_y_sn + (long)ph * P.bwd_y_sh + (long)pw * P.bwd_y_sw + nb0);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) ry[j] = ldg_v4(yp + 8 * j);
+        }
+        if (has_res) {
+          const __nv_bfloat16* rp = P.bwd_res + ((long)n * P.bwd_r_sn + (long)ph * P.bwd_r_sh + (long)pw * P.bwd_r_sw + nb0);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) rr[j] = ldg_v4(rp + 8 * j);
+        }
+      }
+      if (m == 0) {
+        if (leader) { if (grp == 0) dbg_mark(P, 2, it >> 1, 0); tma_store_wait_read<0>(); }     // this group's previous store has left the staging buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
+        tc_fence_after();
+        if (leader && grp == 0) dbg_mark(P, 2, it >> 1, 1);
+      }
+      const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.mt + m) * NB);
+      const uint32_t row_off = (uint32_t)(m * 128 + m_idx) * RB;
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        uint32_t v[16];
+        tmem_ld_32x16(acc + 16 * k, v);
+        tmem_ld_wait();
+        const uint32_t rw[8] = {rr[2 * k].x, rr[2 * k].y, rr[2 * k].z, rr[2 * k].w, rr[2 * k + 1].x, rr[2 * k + 1].y, rr[2 * k + 1].z, rr[2 * k + 1].w};
+        const uint32_t yw[8] = {ry[2 * k].x, ry[2 * k].y, ry[2 * k].z, ry[2 * k].w, ry[2 * k + 1].x, ry[2 * k + 1].y, ry[2 * k + 1].z, ry[2 * k + 1].w};
+        uint32_t gw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f0 = __uint_as_float(v[2 * j]) + __uint_as_float(rw[j] << 16);
+          const float f1 = __uint_as_float(v[2 * j + 1]) + __uint_as_float(rw[j] & 0xffff0000u);
+          gw[j] = valid ? pack_bf16x2(f0, f1) : 0u;     // rows outside the image: zeros (clipped by the store, neutral in the sums)
+        }
+        st_shared_v4(stg + swz(row_off + 32u * k, mask), gw[0], gw[1], gw[2], gw[3]);
+        st_shared_v4(stg + swz(row_off + 32u * k + 16u, mask), gw[4], gw[5], gw[6], gw[7]);
+        if (AM >= 0) {
+          float x[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sc = *reinterpret_cast<const float4*>(cs + 16 * k + 4 * j4);
+            const float4 sh = *reinterpret_cast<const float4*>(cs + 64 + 16 * k + 4 * j4);
+            const float4 mu = *reinterpret_cast<const float4*>(cs + 128 + 16 * k + 4 * j4);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, muv[4] = {mu.x, mu.y, mu.z, mu.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * j4 + e;                  // channel 16k + j of this pixel
+              const uint32_t gword = gw[j >> 1], yword = yw[j >> 1];
+              const float g = (j & 1) ? __uint_as_float(gword & 0xffff0000u) : __uint_as_float(gword << 16);
+              const float yv = (j & 1) ? __uint_as_float(yword & 0xffff0000u) : __uint_as_float(yword << 16);
+              const float tt = fmaf(yv, scv[e], shv[e]);
+              float d = 1.f;
+              if (AM == 1) d = tt > 0.f ? 1.f : 0.f;
+              if (AM == 2) d = tt >= 0.f ? 1.f : P.bwd_alpha;
+              const float gp = __fmul_rn(g, d);          // the same rounded product as the dx pass (bn_bwd_dx8_kernel)
+              x[j] = gp;
+              x[16 + j] = gp * (yv - muv[e]);
+            }
+          }
+          if (P.dbg_flags & 32) asum[k] += x[0] + x[16]; else
+          asum[k] += warp_transpose_sum32(x, lane);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));   // the accumulator is free as soon as it is in registers
+    fence_proxy_async();                                         // generic-proxy writes -> visible to the bulk store
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    if (leader) {
+      tma_store_4d(&P.omap, stg, nb0, tw * 8, th * 16 * P.mt, n);
+      tma_store_commit();
+      if (grp == 0) dbg_mark(P, 2, it >> 1, 2);
+    }
+  }
+  if (leader) tma_store_wait<0>();
+  if (AM >= 0) {
+    asm volatile("bar.sync 3, 256;" ::: "memory");   // both groups: all stores have left the staging buffers, buffer 0 is the scratch of the final sum
+    const int gwarp = grp * 4 + q;                   // [8 warps][NG][32] floats <= 4 KB
+#pragma unroll
+    for (int k = 0; k < NG; ++k) red_s[(gwarp * NG + k) * 32 + lane] = asum[k];
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    const int etid = gwarp * 32 + lane;
+    if (etid < NG * 32) {
+      const int k = etid >> 5, l = etid & 31;
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += red_s[(r * NG + k) * 32 + l];
+      P.bn_partials[(size_t)blockIdx.x * 2 * P.cout_total + (size_t)(l >> 4) * P.cout_total + nb0 + 16 * k + (l & 15)] = t;
+    }
+  }
+}
+
 // Issues the MMAs of one pipeline stage (all taps of one channel chunk).  MT and NBK (= chunk/16) are
 // compile-time so the body is straight-line: one descriptor add per operand per tcgen05.mma.
 // NT > 0 additionally fixes the tap count, so every per-tap descriptor is a constant-bank load at a static offset and the
@@ -603,6 +762,7 @@ __device__ __forceinline__ void issue_stage(const UmmaConvParams& P, int t0, int
   }
 }
 
+template <bool BWD>
 __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[MAX_STAGES], bar_a_empty[MAX_STAGES];
@@ -647,6 +807,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     fence_mbar_init();
     if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0) P.dbg[192] = clock64();
     // the resident weights start loading before the CTA-wide sync, under the TMEM allocation of warp 1
+    // (Tried in round 2 and reverted, job r2_04: barrier initialisation spread over the lanes of warp 0, the producer warp only
+    // ARRIVING at the CTA-wide barrier, and the first tile's halo issued BEFORE the weights.  The first MMA moved ~800 cycles
+    // LATER (the weight loads queue behind the halo's first-use descriptor fetch), the conv family ran 6 % slower inside the
+    // step (348 vs 369 TFLOP/s) and the step 7.64 vs 7.42 ms.)
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
     tma_prefetch_desc(&P.wmap);
     if (P.tstore) tma_prefetch_desc(&P.omap);
@@ -879,8 +1043,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     const int etid = grp * 128 + (warp - (grp ? 7 : 2)) * 32 + lane;   // 0..255 over both epilogue groups
     if (P.bias)
       for (int i = etid; i < P.nb; i += 256) bias_s[i] = __ldg(P.bias + nb0 + i);
+    if (BWD && P.bwd_am >= 0)
+      for (int i = etid; i < P.nb; i += 256) {
+        bnp_s[i] = __ldg(P.bwd_scale + nb0 + i); bnp_s[64 + i] = __ldg(P.bwd_shift + nb0 + i); bnp_s[128 + i] = __ldg(P.bwd_mean + nb0 + i);
+      }
     asm volatile("bar.sync 3, 256;" ::: "memory");  // epilogue warps only
     const float* bs = P.bias ? bias_s : nullptr;
+    if (BWD) {
+      float* red = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off);
+#define DG_EPI_BWD(AM_) \
+  { if (P.nb == 64) epilogue_role_bwd<AM_, 64>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bar_acc_full, bar_acc_empty, red, grp, bnp_s); \
+    else epilogue_role_bwd<AM_, 32>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bar_acc_full, bar_acc_empty, red, grp, bnp_s); }
+      switch (P.bwd_am) {
+        case 0: DG_EPI_BWD(0) break;
+        case 1: DG_EPI_BWD(1) break;
+        case 2: DG_EPI_BWD(2) break;
+        default: DG_EPI_BWD(-1) break;
+      }
+#undef DG_EPI_BWD
+    } else {
 #define DG_EPI(ACT)                                                                                     \
   if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
                                       reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp, bnp_s, \
@@ -895,6 +1076,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       default: DG_EPI(DG_ACT_NONE) break;
     }
 #undef DG_EPI
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -997,11 +1179,18 @@ struct BnPhase {
   const dg_tensor* out2;   // act(BN(y)) (+ res)
 };
 
+// BatchNorm-backward epilogue of an input-gradient launch (UmmaConvParams::bwd_*)
+struct BwdEpi {
+  const dg_tensor* res;        // skip-connection gradient added to the result, or nullptr
+  const dg_bn_bwd_stats* bn;   // statistics of the BatchNorm in front of the convolution, or nullptr
+};
+
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
                 const TapSpec* taps_in, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
                 float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr,
-                const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false) {
+                const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, const BwdEpi* bwd = nullptr,
+                bool bwd_query = false) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
   DG_REQUIRE(n_phase == 1 || (n_phase == 4 && phase_lat && n_src == 1), "%s: bad output-phase description", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
@@ -1186,6 +1375,14 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
       DG_FAIL("%s: the fused BatchNorm phase does not apply to this layer (tiles per CTA %d x mt %d x nb %d columns)", name, per_cta, mt, nb);
     }
   }
+  if (bwd || bwd_query) {
+    // the BatchNorm-backward epilogue rides on the staged epilogue with a 32- or 64-channel N block
+    const bool ok = ts && (nb == 32 || nb == 64) && !split && !kouter && n_phase == 1 && !bias && act == DG_ACT_NONE;
+    if (!ok) {
+      if (bn_blocks) *bn_blocks = 0;
+      DG_FAIL("%s: the BatchNorm-backward epilogue does not apply to this layer (staged %d, nb %d)", name, (int)ts, nb);
+    }
+  }
   if (dry) return 0;   // capability query: a tile configuration exists
   DG_REQUIRE(!bn_partials || ts, "%s: fused BatchNorm statistics need the staged epilogue (dense bf16 output, N block of 16/32/64)", name);
 
@@ -1333,10 +1530,34 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
       P.bnp_res = 1;
     }
   }
+  P.bwd_am = -1;
+  if (bwd) {
+    DG_REQUIRE(!bnp && !bn_fin, "%s: the BatchNorm-backward epilogue excludes the forward BatchNorm modes", name);
+    if (bwd->res) {
+      const dg_tensor* r = bwd->res;
+      DG_REQUIRE(dg_valid(r) && dg_same_shape(r, out) && r->dtype == DG_BF16 && ((uintptr_t)r->ptr % 16) == 0 && r->cpitch % 8 == 0 &&
+                     r->coff % 8 == 0, "%s: bad skip-gradient view", name);
+      P.bwd_res = (const __nv_bfloat16*)r->ptr + r->coff;
+      P.bwd_r_sw = r->cpitch; P.bwd_r_sh = (long)r->cpitch * r->w; P.bwd_r_sn = (long)r->cpitch * r->w * r->h;
+    }
+    if (bwd->bn) {
+      const dg_bn_bwd_stats* b = bwd->bn;
+      const dg_tensor* yb = b->y;
+      DG_REQUIRE(bn_partials && b->scale && b->shift && b->mean && dg_valid(yb) && dg_same_shape(yb, out) && yb->dtype == DG_BF16 &&
+                     ((uintptr_t)yb->ptr % 16) == 0 && yb->cpitch % 8 == 0 && yb->coff % 8 == 0, "%s: bad BatchNorm-backward arguments", name);
+      DG_REQUIRE(b->act == DG_ACT_NONE || b->act == DG_ACT_RELU || b->act == DG_ACT_LRELU, "%s: the BatchNorm-backward epilogue takes none / relu / leaky relu", name);
+      P.bwd_am = b->act == DG_ACT_NONE ? 0 : (b->act == DG_ACT_RELU ? 1 : 2);
+      P.bwd_alpha = b->alpha;
+      P.bwd_y = (const __nv_bfloat16*)yb->ptr + yb->coff;
+      P.bwd_y_sw = yb->cpitch; P.bwd_y_sh = (long)yb->cpitch * yb->w; P.bwd_y_sn = (long)yb->cpitch * yb->w * yb->h;
+      P.bwd_scale = b->scale; P.bwd_shift = b->shift; P.bwd_mean = b->mean;
+    }
+  }
   const uint32_t smem = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes + (ts ? 2u * stg_bytes : 0u) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);
+    cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);
     if (e != cudaSuccess) DG_FAIL("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1355,11 +1576,13 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   dim3 grid(ctas, n_blocks);
   if (bnp) {
     DG_REQUIRE(n_blocks == 1 && ctas == ctas_pre, "%s: internal: BatchNorm-phase grid mismatch", name);
-    DG_REQUIRE(dg_coresident(umma_conv_kernel, CONV_THREADS, smem, ctas, ctx->sm_count), "%s: the grid does not fit the device at once", name);
-    cudaError_t e = dg_coop_launch(umma_conv_kernel, grid, dim3(CONV_THREADS), smem, st, P);
+    DG_REQUIRE(dg_coresident(umma_conv_kernel<false>, CONV_THREADS, smem, ctas, ctx->sm_count), "%s: the grid does not fit the device at once", name);
+    cudaError_t e = dg_coop_launch(umma_conv_kernel<false>, grid, dim3(CONV_THREADS), smem, st, P);
     if (e != cudaSuccess) DG_FAIL("%s: cooperative launch failed: %s", name, cudaGetErrorString(e));
+  } else if (bwd) {
+    dg_pdl_launch(umma_conv_kernel<true>, grid, dim3(CONV_THREADS), smem, st, P);
   } else {
-    dg_pdl_launch(umma_conv_kernel, grid, dim3(CONV_THREADS), smem, st, P);
+    dg_pdl_launch(umma_conv_kernel<false>, grid, dim3(CONV_THREADS), smem, st, P);
   }
   DG_CHECK_LAUNCH(name);
   return 0;
@@ -1490,7 +1713,8 @@ extern "C" int dg_umma_conv2d_fwd_supported(dg_ctx* ctx, const dg_tensor* x, con
 }
 
 static int conv_dgrad_impl(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const float* bias, const dg_tensor* dx,
-                           const dg_conv_params* p, void* stream, bool dry) {
+                           const dg_conv_params* p, void* stream, bool dry, const BwdEpi* bwd = nullptr, bool bwd_query = false,
+                           int* bwd_blocks = nullptr) {
   DG_REQUIRE(dg_valid(dy) && dg_valid(dx) && w_packed && p, "dg_umma_conv2d_dgrad: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_dgrad: stride must be 1 or 2");
   DG_REQUIRE(dx->n == dy->n, "dg_umma_conv2d_dgrad: batch mismatch");
@@ -1502,8 +1726,10 @@ static int conv_dgrad_impl(dg_ctx* ctx, const dg_tensor* dy, const void* w_packe
     for (int r = 0; r < p->kh; ++r)
       for (int s = 0; s < p->kw; ++s) taps[n_taps++] = TapSpec{0, p->pad_t - r, p->pad_l - s, r * p->kw + s};
     return launch_conv(ctx, "dg_umma_conv2d_dgrad", dy, &dense, 1, taps, n_taps, w_packed, dx->c, dx, dense, bias,
-                       p->act, p->act_alpha, (cudaStream_t)stream, dry);
+                       p->act, p->act_alpha, (cudaStream_t)stream, dry, bwd && bwd->bn ? bwd->bn->partials : nullptr, bwd_blocks, 1, nullptr,
+                       nullptr, nullptr, false, bwd, bwd_query);
   }
+  DG_REQUIRE(!bwd && !bwd_query, "dg_umma_conv2d_dgrad: the BatchNorm-backward epilogue needs a stride-1 convolution");
   DG_REQUIRE(dx->h % 2 == 0 && dx->w % 2 == 0, "dg_umma_conv2d_dgrad: stride 2 needs even image size");
   {
     // All four output parity phases in ONE launch when their accumulators fit TMEM together (2 buffers x 4 phases x mt x nb
@@ -1555,6 +1781,25 @@ static int conv_dgrad_impl(dg_ctx* ctx, const dg_tensor* dy, const void* w_packe
 extern "C" int dg_umma_conv2d_dgrad(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const float* bias,
                                     const dg_tensor* dx, const dg_conv_params* p, void* stream) {
   return conv_dgrad_impl(ctx, dy, w_packed, bias, dx, p, stream, false);
+}
+
+// Input gradient + the skip-connection add + the statistics half of the BatchNorm backward pass in front of the convolution
+// (UmmaConvParams::bwd_*): `residual` (may be NULL) is added to the result, `bn` (may be NULL) describes the BatchNormalization
+// whose OUTPUT gradient this launch produces; its partials rows come from dg_umma_conv2d_dgrad_fused_blocks().
+extern "C" int dg_umma_conv2d_dgrad_fused(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const dg_tensor* dx, const dg_conv_params* p,
+                                          const dg_tensor* residual, const dg_bn_bwd_stats* bn, void* stream) {
+  BwdEpi e{residual, bn};
+  return conv_dgrad_impl(ctx, dy, w_packed, nullptr, dx, p, stream, false, &e);
+}
+
+// Rows of the [rows][2][Cin] fp32 statistics workspace of dg_umma_conv2d_dgrad_fused, or 0 when the fused epilogue does not apply
+// to the layer (stride 2, streamed weights, N block other than 32 / 64): the caller then issues dg_umma_conv2d_dgrad, dg_add and the
+// two-pass dg_bn_act_bwd.
+extern "C" int dg_umma_conv2d_dgrad_fused_blocks(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p) {
+  int blocks = 0;
+  if (p->stride != 1) return 0;
+  if (conv_dgrad_impl(ctx, dy, (const void*)1, nullptr, dx, p, nullptr, true, nullptr, true, &blocks) != 0) return 0;
+  return blocks;
 }
 
 extern "C" int dg_umma_conv2d_dgrad_supported(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p) {

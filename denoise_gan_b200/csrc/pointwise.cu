@@ -514,6 +514,36 @@ extern "C" int dg_bn_finalize(dg_ctx* ctx, const float* partials, int nblocks, l
   return 0;
 }
 
+// dg_bn_finalize + dg_bn_act_fwd in ONE launch (no dropout): the blocks of the apply pass each reduce the per-CTA statistics rows
+// themselves.  rc 2: the tensors do not qualify for the vector kernel (the caller issues the two separate calls).
+extern "C" int dg_bn_act_fwd_from_partials(dg_ctx* ctx, const dg_tensor* x, const float* partials, int nblocks, const float* gamma,
+                                           const float* beta, float eps, float momentum, float* moving_mean, float* moving_var, float* scale,
+                                           float* shift, float* save_mean, float* save_invstd, int act, float act_alpha,
+                                           const float* prelu_alpha, const dg_tensor* residual, const dg_tensor* y, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y) && partials && nblocks > 0 && gamma && beta && scale && shift && save_mean && save_invstd,
+             "dg_bn_act_fwd_from_partials: null argument");
+  DG_REQUIRE(dg_same_shape(x, y), "dg_bn_act_fwd_from_partials: shape mismatch");
+  DG_REQUIRE(act != DG_ACT_PRELU || prelu_alpha, "dg_bn_act_fwd_from_partials: PReLU needs alpha");
+  if (residual) DG_REQUIRE(dg_valid(residual) && dg_same_shape(residual, y) && residual->dtype == y->dtype,
+                           "dg_bn_act_fwd_from_partials: residual mismatch");
+  const long P = dg_pixels(x);
+  const int C = x->c;
+  if (!(dgvec::vec_ok(x) && dgvec::vec_ok(y) && (!residual || dgvec::vec_ok(residual)) && dgvec::RT % (C >> 3) == 0)) return 2;
+  const int E = 2 * C, E4 = E >> 2, G = E4 < dgvec::RT ? dgvec::RT / E4 : 1;
+  const size_t smem = (size_t)G * E * sizeof(double) + (size_t)2 * C * sizeof(float);
+  if (smem > 48 * 1024) return 2;
+  const int vblocks = dgvec::red8_blocks(P, C, ctx->sm_count);
+  View rv = residual ? view_of(residual) : View{0, 0};
+  DG_DISPATCH_2(x->dtype, y->dtype, "dg_bn_act_fwd_from_partials",
+                dg_pdl_launch(dgvec::bn_fwd_part8_kernel<TI, TO>, dim3(vblocks), dim3(dgvec::RT), smem, ST, (const TI*)x->ptr,
+                              dgvec::VView{x->cpitch, x->coff}, P, C, partials, nblocks, gamma, beta, eps, momentum, moving_mean, moving_var,
+                              scale, shift, save_mean, save_invstd, act, act_alpha, prelu_alpha,
+                              residual ? (const TO*)residual->ptr : nullptr, dgvec::VView{rv.pitch, rv.off}, (TO*)y->ptr,
+                              dgvec::VView{y->cpitch, y->coff}););
+  DG_CHECK_LAUNCH("dg_bn_act_fwd_from_partials");
+  return 0;
+}
+
 extern "C" int dg_bn_infer_affine(dg_ctx* ctx, int c, const float* gamma, const float* beta, const float* moving_mean,
                                   const float* moving_var, float eps, float* scale, float* shift, void* stream) {
   DG_REQUIRE(c > 0 && gamma && beta && moving_mean && moving_var && scale && shift, "dg_bn_infer_affine: null argument");
@@ -677,6 +707,38 @@ extern "C" int dg_bn_act_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* 
         act, act_alpha, prelu_alpha, dropout, seed, offset, step_counter, coef, (TI*)dx->ptr, view_of(dx), P, C);
   });
   DG_CHECK_LAUNCH("dg_bn_act_bwd");
+  return 0;
+}
+
+// dx half of the BatchNorm(+activation) backward pass from the per-CTA partial sums of dg_umma_conv2d_dgrad_fused.
+extern "C" int dg_bn_bwd_dx_from_partials(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const float* scale, const float* shift,
+                                          const float* gamma, const float* save_mean, const float* save_invstd, int act, float act_alpha,
+                                          const float* partials, int rows, const dg_tensor* dx, float* dgamma, float* dbeta, int accumulate,
+                                          void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(dx) && scale && shift && gamma && save_mean && save_invstd && partials && rows > 0,
+             "dg_bn_bwd_dx_from_partials: null argument");
+  DG_REQUIRE(dg_same_shape(dy, x) && dg_same_shape(dx, x), "dg_bn_bwd_dx_from_partials: shape mismatch");
+  DG_REQUIRE(dy->dtype == dx->dtype, "dg_bn_bwd_dx_from_partials: dy/dx dtype mismatch");
+  DG_REQUIRE(act == DG_ACT_NONE || act == DG_ACT_RELU || act == DG_ACT_LRELU, "dg_bn_bwd_dx_from_partials: activation must be none / relu / leaky relu");
+  DG_REQUIRE(dgvec::vec_ok(dy) && dgvec::vec_ok(x) && dgvec::vec_ok(dx) && x->c % 8 == 0 && dgvec::RT % (x->c >> 3) == 0 && x->c <= 1024,
+             "dg_bn_bwd_dx_from_partials: needs 16-byte aligned views with a channel count dividing 4096");
+  const long P = dg_pixels(x);
+  const int C = x->c;
+  const int E = 2 * C, E4 = E >> 2, G = E4 < dgvec::RT ? dgvec::RT / E4 : 1;
+  const size_t smem = (size_t)G * E * sizeof(double) + (size_t)2 * C * sizeof(float);
+  const int vblocks = dgvec::red8_blocks(P, C, ctx->sm_count);
+  const dgvec::VView vdy{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vdx{dx->cpitch, dx->coff};
+#define DG_BN_DXP(AM)                                                                                                              \
+  dg_pdl_launch(dgvec::bn_bwd_dx_part8_kernel<TI, TO, TI, AM>, dim3(vblocks), dim3(dgvec::RT), smem, ST, (const TI*)dy->ptr, vdy,  \
+                (const TO*)x->ptr, vx, scale, shift, gamma, save_mean, save_invstd, act_alpha, partials, rows, P, C, dgamma, dbeta, \
+                accumulate, (TI*)dx->ptr, vdx)
+  DG_DISPATCH_2(dy->dtype, x->dtype, "dg_bn_bwd_dx_from_partials", {
+    if (act == DG_ACT_NONE) DG_BN_DXP(0);
+    else if (act == DG_ACT_RELU) DG_BN_DXP(1);
+    else DG_BN_DXP(2);
+  });
+#undef DG_BN_DXP
+  DG_CHECK_LAUNCH("dg_bn_bwd_dx_from_partials");
   return 0;
 }
 

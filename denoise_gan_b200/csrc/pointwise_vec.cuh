@@ -489,6 +489,125 @@ bn_fwd_fused8_kernel(const TI* __restrict__ x, VView xv, long P, int C, float* _
   }
 }
 
+// Training-mode BatchNorm forward when the convolution that produced x already reduced the batch statistics to per-CTA rows
+// ([nrows][2][C]: sum, sum of squares; dg_umma_conv2d_fwd with bn_partials): every block sums the rows in the same fixed order in
+// double precision and derives scale / shift itself (no finalize launch, no grid barrier); block 0 publishes scale / shift / mean /
+// invstd for the backward pass and updates the moving statistics; then normalise + activation + skip-add as bn_act_fwd8_kernel.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(RT, 1)
+bn_fwd_part8_kernel(const TI* __restrict__ x, VView xv, long P, int C, const float* __restrict__ partial, int nrows,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                    float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
+                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int act, float alpha,
+                    const float* __restrict__ prelu_alpha, const TO* __restrict__ res, VView rv, TO* __restrict__ y, VView yv) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float red8[];
+  const int E = 2 * C, E4 = E >> 2, G = E4 < RT ? RT / E4 : 1;
+  double* gsum = reinterpret_cast<double*>(red8);                    // [G][E]
+  float* coef_s = reinterpret_cast<float*>(gsum + (size_t)G * E);   // [2][C]: scale, shift
+  {
+    const float4* part4 = reinterpret_cast<const float4*>(partial);
+    for (int idx = threadIdx.x; idx < E4 * G; idx += RT) {
+      const int e4 = idx % E4, grp = idx / E4;
+      double s[4] = {0, 0, 0, 0};
+      int bI = grp;
+      for (; bI + 3 * G < nrows; bI += 4 * G) {     // four independent loads in flight
+        const float4 v0 = __ldg(part4 + (long)bI * E4 + e4), v1 = __ldg(part4 + (long)(bI + G) * E4 + e4);
+        const float4 v2 = __ldg(part4 + (long)(bI + 2 * G) * E4 + e4), v3 = __ldg(part4 + (long)(bI + 3 * G) * E4 + e4);
+        s[0] += (double)v0.x; s[1] += (double)v0.y; s[2] += (double)v0.z; s[3] += (double)v0.w;
+        s[0] += (double)v1.x; s[1] += (double)v1.y; s[2] += (double)v1.z; s[3] += (double)v1.w;
+        s[0] += (double)v2.x; s[1] += (double)v2.y; s[2] += (double)v2.z; s[3] += (double)v2.w;
+        s[0] += (double)v3.x; s[1] += (double)v3.y; s[2] += (double)v3.z; s[3] += (double)v3.w;
+      }
+      for (; bI < nrows; bI += G) {
+        const float4 v = __ldg(part4 + (long)bI * E4 + e4);
+        s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gsum[(long)grp * E + e4 * 4 + k] = s[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += RT) {
+      double s0 = 0, s1 = 0;
+      for (int g2 = 0; g2 < G; ++g2) { s0 += gsum[(long)g2 * E + c]; s1 += gsum[(long)g2 * E + C + c]; }
+      const double mean = s0 / (double)P;
+      double var = s1 / (double)P - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float g = gamma[c], b = beta[c];
+      const float scv = g * invstd, shv = b - (float)mean * g * invstd;
+      coef_s[c] = scv;
+      coef_s[C + c] = shv;
+      if (blockIdx.x == 0) {
+        scale[c] = scv;
+        shift[c] = shv;
+        save_mean[c] = (float)mean;
+        save_invstd[c] = invstd;
+        if (moving_mean) {
+          moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+          moving_var[c] = moving_var[c] * momentum + (float)(var * ((double)P / (double)(P > 1 ? P - 1 : 1))) * (1.f - momentum);   // Bessel-corrected
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int CV = C >> 3, R = RT / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  if (row >= R) return;
+  float sc[8], sh[8], al[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = coef_s[c0 + j]; sh[j] = coef_s[C + c0 + j]; }
+  if (act == DG_ACT_PRELU) ldc8(prelu_alpha + c0, al);
+  const long stride = (long)gridDim.x * R;
+  typedef typename V8<TI>::raw Raw;
+  typedef typename V8<TO>::raw RawO;
+  auto apply = [&](const Raw& rx, const RawO& rr, long p) {
+    float v[8];
+    V8<TI>::cvt(rx, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (act == DG_ACT_PRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : al[j] * v[j];
+    } else if (act == DG_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == DG_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] >= 0.f ? v[j] : alpha * v[j];
+    } else if (act != DG_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, alpha);
+    }
+    if (res) {
+      float r[8];
+      V8<TO>::cvt(rr, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    V8<TO>::st(y + (p * yv.pitch + yv.off + c0), v);
+  };
+  long p = (long)blockIdx.x * R + row;
+  for (; p + (EU - 1) * stride < P; p += EU * stride) {
+    Raw rx[EU];
+    RawO rr[EU];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      rx[u] = V8<TI>::ldraw(x + ((p + u * stride) * xv.pitch + xv.off + c0));
+      if (res) rr[u] = V8<TO>::ldraw(res + ((p + u * stride) * rv.pitch + rv.off + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u) apply(rx[u], rr[u], p + u * stride);
+  }
+  for (; p < P; p += stride) {
+    Raw rx = V8<TI>::ldraw(x + (p * xv.pitch + xv.off + c0));
+    RawO rr;
+    if (res) rr = V8<TO>::ldraw(res + (p * rv.pitch + rv.off + c0));
+    apply(rx, rr, p);
+  }
+}
+
 template <typename TG, typename TX>
 struct RawPair {
   typename V8<TG>::raw g;
@@ -694,6 +813,105 @@ bn_bwd_fused8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__
     for (int j = 0; j < 8; ++j) {
       float tt;
       const float g = gterm(gy[j], xin[j], j, p, tt);
+      o[j] = fmaf(A[j], g - k0[j], B[j] * (xin[j] - mu[j]));
+    }
+    V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);
+  };
+  long p = (long)blockIdx.x * R + row;
+  for (; p + (EU - 1) * stride < P; p += EU * stride) {
+    Raw r[EU];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      r[u].g = V8<TG>::ldraw(dy + ((p + u * stride) * dv.pitch + dv.off + c0));
+      r[u].x = V8<TX>::ldraw(x + ((p + u * stride) * xv.pitch + xv.off + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u) one(r[u], p + u * stride);
+  }
+  for (; p < P; p += stride) {
+    Raw r;
+    r.g = V8<TG>::ldraw(dy + (p * dv.pitch + dv.off + c0));
+    r.x = V8<TX>::ldraw(x + (p * xv.pitch + xv.off + c0));
+    one(r, p);
+  }
+}
+
+// BatchNorm backward, dx half, when the convolution that produced dy already reduced the two per-channel sums to per-CTA rows
+// (dg_umma_conv2d_dgrad_fused: row r = [sum g' | sum g'(x - mean)] over that CTA's pixels).  Every block first sums the rows in the
+// same fixed order in double precision (nrows x 2C floats out of L2, ~75 KB for the generator trunk) -- no finalize launch, no grid
+// barrier -- block 0 writes dgamma / dbeta, and then the blocks make ONE pass over dy and x.
+template <typename TG, typename TX, typename TO, int AM>
+__global__ void __launch_bounds__(RT, 1)
+bn_bwd_dx_part8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__ x, VView xv, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ gamma, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float alpha, const float* __restrict__ partial, int nrows, long P, int C,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, TO* __restrict__ dx, VView ov) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float red8[];
+  const int E = 2 * C, E4 = E >> 2, G = E4 < RT ? RT / E4 : 1;
+  double* gsum = reinterpret_cast<double*>(red8);            // [G][E]
+  float* coef_s = reinterpret_cast<float*>(gsum + (size_t)G * E);   // [2][C]: mean of g', invstd * mean of g'(x - mean)
+  {
+    const float4* part4 = reinterpret_cast<const float4*>(partial);
+    for (int idx = threadIdx.x; idx < E4 * G; idx += RT) {
+      const int e4 = idx % E4, grp = idx / E4;
+      double s[4] = {0, 0, 0, 0};
+      int bI = grp;
+      for (; bI + 3 * G < nrows; bI += 4 * G) {     // four independent loads in flight
+        const float4 v0 = __ldg(part4 + (long)bI * E4 + e4), v1 = __ldg(part4 + (long)(bI + G) * E4 + e4);
+        const float4 v2 = __ldg(part4 + (long)(bI + 2 * G) * E4 + e4), v3 = __ldg(part4 + (long)(bI + 3 * G) * E4 + e4);
+        s[0] += (double)v0.x; s[1] += (double)v0.y; s[2] += (double)v0.z; s[3] += (double)v0.w;
+        s[0] += (double)v1.x; s[1] += (double)v1.y; s[2] += (double)v1.z; s[3] += (double)v1.w;
+        s[0] += (double)v2.x; s[1] += (double)v2.y; s[2] += (double)v2.z; s[3] += (double)v2.w;
+        s[0] += (double)v3.x; s[1] += (double)v3.y; s[2] += (double)v3.z; s[3] += (double)v3.w;
+      }
+      for (; bI < nrows; bI += G) {
+        const float4 v = __ldg(part4 + (long)bI * E4 + e4);
+        s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gsum[(long)grp * E + e4 * 4 + k] = s[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += RT) {
+      double s0 = 0, s1 = 0;
+      for (int g2 = 0; g2 < G; ++g2) { s0 += gsum[(long)g2 * E + c]; s1 += gsum[(long)g2 * E + C + c]; }
+      s1 *= (double)invstd[c];
+      if (blockIdx.x == 0) {
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;
+      }
+      coef_s[c] = (float)(s0 / (double)P);
+      coef_s[C + c] = (float)(s1 / (double)P);
+    }
+    __syncthreads();
+  }
+  typedef RawPair<TG, TX> Raw;
+  const int CV = C >> 3, R = RT / CV;
+  const int row = threadIdx.x / CV, c0 = (threadIdx.x % CV) * 8;
+  if (row >= R) return;
+  float sc[8], sh[8], mu[8], A[8], B[8], k0[8];
+  ldc8(scale + c0, sc); ldc8(shift + c0, sh); ldc8(mean + c0, mu);
+  {
+    float ga[8], is[8];
+    ldc8(gamma + c0, ga); ldc8(invstd + c0, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      k0[j] = coef_s[c0 + j];
+      A[j] = ga[j] * is[j];
+      B[j] = -A[j] * is[j] * coef_s[C + c0 + j];
+    }
+  }
+  const long stride = (long)gridDim.x * R;
+  auto one = [&](const Raw& r, long p) {
+    float gy[8], xin[8], o[8];
+    V8<TG>::cvt(r.g, gy);
+    V8<TX>::cvt(r.x, xin);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float tt = fmaf(xin[j], sc[j], sh[j]);
+      const float g = __fmul_rn(gy[j], act_deriv_t<AM>(tt, 0, alpha, 0.f));
       o[j] = fmaf(A[j], g - k0[j], B[j] * (xin[j] - mu[j]));
     }
     V8<TO>::st(dx + (p * ov.pitch + ov.off + c0), o);

@@ -31,13 +31,15 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied")
+    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
         self.bn_part = None     # (partials [blocks,2,C], blocks) when the producing conv reduced the BatchNorm statistics
         self.bn_done = None     # (name, scale, shift, mean, invstd) when the producing conv ALSO finalised them (last-CTA ticket)
         self.bn_applied = None  # (y_act, act, alpha, prelu, residual) when the producing conv ALSO applied BatchNorm + activation (+ skip)
+        self.bn_src = None      # on the OUTPUT of a training-mode bn_act: (seq, x, scale, shift, mean, act code, alpha) -- lets the input-gradient
+                                # convolution that produces this Var's gradient also reduce the BatchNorm-backward sums (dg_umma_conv2d_dgrad_fused)
 
     @property
     def shape(self):
@@ -45,10 +47,12 @@ class Var:
 
 
 class Node:
-    __slots__ = ("seq", "inputs", "out", "group", "bwd")
+    __slots__ = ("seq", "inputs", "out", "group", "bwd", "fusable", "params")
 
-    def __init__(self, seq, inputs, out, group, bwd):
+    def __init__(self, seq, inputs, out, group, bwd, fusable=False, params=()):
         self.seq, self.inputs, self.out, self.group, self.bwd = seq, inputs, out, group, bwd
+        self.params = tuple(q for q in params if q is not None)   # variables whose gradient slice this node's bwd writes
+        self.fusable = fusable    # bwd accepts fctx= (fused skip-add / BatchNorm-backward sums in the dgrad epilogue)
 
 
 class _ProfLib:
@@ -94,6 +98,7 @@ class Engine:
         self.seq = 0
         self._ws = None
         self.written: set = set()      # param names whose grad slice was written this step
+        self.complete: set = set()     # ... and whose every writer of the current backward() has been visited
         self.use_umma = bool(bf16) and bool(self.lib.dg_has_umma(self.ctx))
         self.use_umma_wgrad = self.use_umma
         self.fuse_bn_fwd = os.environ.get("DG_BN_FUSED_FWD", "0") == "1"   # one-launch BN forward: measured 1 % slower in the step graph
@@ -106,6 +111,12 @@ class Engine:
         # OFF by default: measured SLOWER in the step graph (7.57 vs 7.42 ms, same box, job r2_03) -- the tensor pipe idles
         # through the grid barrier and pass 2, and a cooperative launch cannot overlap its neighbours' tails
         self.fuse_conv_bn_act = os.environ.get("DG_CONV_BN_ACT", "0") == "1"
+        # input-gradient convolutions add the skip-connection gradient and reduce the sums of the BatchNorm backward pass in
+        # their epilogue (dg_umma_conv2d_dgrad_fused + dg_bn_bwd_dx_from_partials): no add launch, one pass over dy / x
+        # instead of two per BatchNorm of the generator trunk and of the stride-1 discriminator layers
+        self.fuse_dgrad_bn_bwd = os.environ.get("DG_DGRAD_BN_BWD", "1") != "0"
+        self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"   # dg_bn_act_fwd_from_partials instead of finalize + apply
+        self._bwd_part: dict = {}       # (bn_act seq, tag) -> (partials, rows) left by the fused dgrad for that BatchNorm's backward
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
         # dgrad / BatchNorm chain of the backward pass (joined at the end of backward())
         self.wgrad_overlap = os.environ.get("DG_WGRAD_OVERLAP", "1") != "0"
@@ -203,8 +214,8 @@ class Engine:
         self.seq += 1
         return self.seq
 
-    def _push(self, inputs, out: Var, group, bwd):
-        self.tape.append(Node(out.seq, inputs, out, group, bwd))
+    def _push(self, inputs, out: Var, group, bwd, fusable=False, params=()):
+        self.tape.append(Node(out.seq, inputs, out, group, bwd, fusable, params))
 
     @staticmethod
     def _deps(inputs, group=None):
@@ -375,7 +386,7 @@ class Engine:
                     check(self.lib.dg_copy(self.ctx, C.byref(tv), C.byref(td), 0, self.st))
             return [dx]
 
-        self._push([x], out, w.group, bwd)
+        self._push([x], out, w.group, bwd, params=(w, b))
         return out
 
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
@@ -465,7 +476,7 @@ class Engine:
         out.bn_done = bn_done
         out.bn_applied = bn_applied
 
-        def bwd(gy: torch.Tensor, need_in, need_p, tag):
+        def bwd(gy: torch.Tensor, need_in, need_p, tag, fctx=None):
             dpre = gy
             if ACT[act]:
                 dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
@@ -476,6 +487,36 @@ class Engine:
                 with self._side():
                     self._wgrad(x.t, dpre, w, b, lin, flops)
             dx = None
+            if need_in[0] and fctx is not None and umma_d and stride == 1 and dpre.dtype == torch.bfloat16 and x.t.dtype == torch.bfloat16:
+                # this launch produces the LAST contribution to dL/dx: the skip-connection gradient accumulated so far is added
+                # in the epilogue, and when x is the output of a training-mode BatchNorm its backward sums are reduced there too
+                res, src = fctx.get("residual"), x.bn_src
+                if res is not None and (res.dtype != torch.bfloat16 or tuple(res.shape) != tuple(x.shape)):
+                    res = None
+                keyq = ("dgf", N, H, W, cin, Ho, Wo, cout, kh, kw, pt, pl)
+                rows = self._cap.get(keyq)
+                if rows is None:
+                    tdq = tensor(self.buf((seq, "dx", tag), x.shape, x.t.dtype))
+                    rows = int(self.lib.dg_umma_conv2d_dgrad_fused_blocks(self.ctx, C.byref(tdp), C.byref(tdq), C.byref(lin)))
+                    self._cap[keyq] = rows
+                if rows > 0 and (res is not None or src is not None) and (res is not None or fctx.get("residual") is None):
+                    dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                    tdx = tensor(dx)
+                    tres = tensor(res) if res is not None else None
+                    st_ = None
+                    if src is not None:
+                        s_seq, s_x, s_scale, s_shift, s_mean, s_act, s_alpha = src
+                        part = self.buf((seq, "bwd_part", tag), (rows, 2, cin), torch.float32)
+                        tsx = tensor(s_x)
+                        st_ = _lib.DgBnBwdStats(C.pointer(tsx), s_scale.data_ptr(), s_shift.data_ptr(), s_mean.data_ptr(), int(s_act),
+                                                float(s_alpha), part.data_ptr())
+                        self._bwd_part[(s_seq, tag)] = (part, rows)
+                    pk = self._packed(w, 1)
+                    self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad_fused(
+                        self.ctx, C.byref(tdp), pk.data_ptr(), C.byref(tdx), C.byref(lin), C.byref(tres) if tres is not None else None,
+                        C.byref(st_) if st_ is not None else None, self.st)))
+                    fctx["fused"] = True
+                    return [dx]
             if need_in[0]:
                 dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
                 tdx = tensor(dx)
@@ -495,7 +536,7 @@ class Engine:
                         self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
             return [dx]
 
-        self._push([x], out, w.group, bwd)
+        self._push([x], out, w.group, bwd, fusable=True, params=(w, b))
         return out
 
     def _wgrad(self, x: torch.Tensor, dy: torch.Tensor, w: Param, b: Param | None, lin: DgConvParams, flops: float = 0.0):
@@ -578,7 +619,7 @@ class Engine:
                     check(self.lib.dg_conv2d_fwd(self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st))
             return [dx]
 
-        self._push([x], out, w.group, bwd)
+        self._push([x], out, w.group, bwd, params=(w, b))
         return out
 
     def _conv2d_transpose_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype):
@@ -654,7 +695,7 @@ class Engine:
                     self.ctx, C.byref(tdp), pk0.data_ptr(), None, C.byref(tdx), C.byref(lin), None, self.st)))
             return [dx]
 
-        self._push([x], out, w.group, bwd)
+        self._push([x], out, w.group, bwd, params=(w, b))
         return out
 
     def dwconv3x3(self, x: Var, w: Param, b: Param | None) -> Var:
@@ -682,7 +723,7 @@ class Engine:
                 check(self.lib.dg_dwconv3x3_dgrad(self.ctx, C.byref(tg), w.data.data_ptr(), C.byref(tdx), self.st))
             return [dx]
 
-        self._push([x], out, w.group, bwd)
+        self._push([x], out, w.group, bwd, params=(w, b))
         return out
 
     # ------------------------------------------------------------------ batch norm (+act, +residual, +dropout)
@@ -721,6 +762,13 @@ class Engine:
         bn_part = getattr(x, "bn_part", None)
         if bn_done is not None:
             pass    # scale/shift/mean/invstd and the moving statistics were written by the producing convolution
+        elif training and bn_part is not None and not drop and self.fuse_bn_finalize_apply and (rc0 := self.lib.dg_bn_act_fwd_from_partials(
+                self.ctx, C.byref(tx), bn_part[0].data_ptr(), bn_part[1], gamma.data.data_ptr(), beta.data.data_ptr(), float(eps), float(momentum),
+                mm.data.data_ptr(), mv.data.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), a_code, float(alpha),
+                _lib.ptr(prelu.data) if prelu is not None else None, C.byref(tres) if tres is not None else None, C.byref(ty), self.st)) != 2:
+            # finalize + apply in one launch: every block of the apply pass sums the per-CTA rows of the producing convolution itself
+            check(rc0)
+            fused = True
         elif training and bn_part is not None:
             # the producing convolution already reduced the batch statistics to per-CTA partials
             check(self.lib.dg_bn_finalize(self.ctx, bn_part[0].data_ptr(), bn_part[1], x.shape[0] * x.shape[1] * x.shape[2], Cc,
@@ -754,6 +802,9 @@ class Engine:
                                          _lib.ptr(step_counter), C.byref(ty), self.st))
         inputs = [x] + ([residual] if residual is not None else [])
         out = Var(y, self._deps(inputs, gamma.group), seq)
+        if (training and not drop and prelu is None and a_code in (0, 1, 2) and self.fuse_dgrad_bn_bwd and x.t.dtype == torch.bfloat16
+                and y.dtype == torch.bfloat16):
+            out.bn_src = (seq, x.t, scale, shift, mean, a_code, float(alpha))
 
         def bwd(gy, need_in, need_p, tag):
             assert training, "backward through inference-mode BN is not part of the hot path"
@@ -768,6 +819,16 @@ class Engine:
                 da = prelu.grad.data_ptr() if prelu is not None else None
             else:
                 acc, dg, db, da = 0, None, None, None
+            pre = self._bwd_part.pop((seq, tag), None)
+            if pre is not None:
+                # the convolution that produced gy already reduced sum g' and sum g'(x - mean) per CTA: one pass for dx
+                check(self.lib.dg_bn_bwd_dx_from_partials(self.ctx, C.byref(tg), C.byref(tx), scale.data_ptr(), shift.data_ptr(),
+                                                          gamma.data.data_ptr(), mean.data_ptr(), invstd.data_ptr(), a_code, float(alpha),
+                                                          pre[0].data_ptr(), int(pre[1]), C.byref(tdx), dg, db, acc, self.st))
+                res = [dx if need_in[0] else None]
+                if residual is not None:
+                    res.append(gy if need_in[1] else None)
+                return res
             ws = self.workspace(nbytes)     # the workspace of the stream this runs on (not the forward pass's: side-stream branches)
             check(self.lib.dg_bn_act_bwd(self.ctx, C.byref(tg), C.byref(tx), scale.data_ptr(), shift.data_ptr(), gamma.data.data_ptr(),
                                          mean.data_ptr(), invstd.data_ptr(), a_code, float(alpha),
@@ -779,7 +840,7 @@ class Engine:
                 res.append(gy if need_in[1] else None)
             return res
 
-        self._push(inputs, out, gamma.group, bwd)
+        self._push(inputs, out, gamma.group, bwd, params=(gamma, beta, prelu))
         return out
 
     # ------------------------------------------------------------------ structural ops
@@ -806,7 +867,7 @@ class Engine:
                                             C.byref(tdu), da, acc, ws.data_ptr(), nbytes, self.st))
             return [du if need_in[0] else None]
 
-        self._push([u], out, group, bwd)
+        self._push([u], out, group, bwd, params=(prelu,))
         return out
 
     def add(self, a: Var, b: Var) -> Var:
@@ -961,8 +1022,10 @@ class Engine:
         return loss, da
 
     # ------------------------------------------------------------------ reverse pass
-    def backward(self, seeds, group: str, tag=None, collect=None):
-        """Equivalent of `tape.gradient(loss, <variables of group>)`: `seeds` = [(Var, dL/dVar tensor)]."""
+    def backward(self, seeds, group: str, tag=None, collect=None, on_node=None):
+        """Equivalent of `tape.gradient(loss, <variables of group>)`: `seeds` = [(Var, dL/dVar tensor)].
+        `on_node()` is called after every visited tape node (the data-parallel exchange launches the gradient buckets
+        whose variables are complete, parallel.GradAllReduce.poll)."""
         tag = tag or group
         grads: dict = {}
 
@@ -983,20 +1046,58 @@ class Engine:
 
         for v, g in seeds:
             accum(v, g)
+        # consumers still to be visited per Var: the visit that brings the count to zero produces the LAST contribution to that
+        # Var's gradient and may fold the sum accumulated so far (skip connections) into its own epilogue
+        # writers still to be visited per variable of this group: a variable's gradient is COMPLETE (self.complete) once every
+        # node that accumulates into it has been visited (pix2pix's generator runs twice per step, pix2pix.py:90)
+        pending: dict = {}
+        for node in self.tape:
+            if node.group == group:
+                for q in node.params:
+                    pending[q.name] = pending.get(q.name, 0) + 1
+        self.complete = set()
+        remaining: dict = {}
+        fuse = self.fuse_dgrad_bn_bwd and self.use_umma
+        if fuse:
+            for node in self.tape:
+                if group in node.out.deps:
+                    for v in node.inputs:
+                        if group in v.deps:
+                            remaining[v.seq] = remaining.get(v.seq, 0) + 1
         for node in reversed(self.tape):
-            ent = grads.pop(node.seq, None)
-            if ent is None or group not in node.out.deps:
+            if group not in node.out.deps:
                 continue
-            if collect is not None:
-                collect[node.seq] = ent[0]
+            ent = grads.pop(node.seq, None)
             need_in = [group in v.deps for v in node.inputs]
             need_p = node.group == group
-            if not need_p and not any(need_in):
-                continue
-            gin = node.bwd(ent[0], need_in, need_p, tag)
-            for v, g in zip(node.inputs, gin):
-                if g is not None:
-                    accum(v, g)
+            if ent is not None and (need_p or any(need_in)):
+                if collect is not None:
+                    collect[node.seq] = ent[0]
+                fctx = None
+                if fuse and node.fusable and need_in[0] and remaining.get(node.inputs[0].seq, 0) == 1:
+                    cur = grads.get(node.inputs[0].seq)
+                    fctx = {"residual": cur[0] if cur is not None else None}
+                    gin = node.bwd(ent[0], need_in, need_p, tag, fctx=fctx)
+                else:
+                    gin = node.bwd(ent[0], need_in, need_p, tag)
+                if fctx is not None and fctx.get("fused"):
+                    grads[node.inputs[0].seq] = [gin[0], True]      # already holds the complete gradient
+                else:
+                    for v, g in zip(node.inputs, gin):
+                        if g is not None:
+                            accum(v, g)
+            if fuse:
+                for v in node.inputs:
+                    if v.seq in remaining:
+                        remaining[v.seq] -= 1
+            if node.group == group:
+                for q in node.params:
+                    pending[q.name] -= 1
+                    if pending[q.name] == 0:
+                        self.complete.add(q.name)
+            if on_node is not None and ent is not None:
+                on_node()
+        self._bwd_part = {k: v for k, v in self._bwd_part.items() if k[1] != tag}
         self._join_side()
 
     # ------------------------------------------------------------------ optimiser

@@ -37,17 +37,27 @@ def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: flo
     seeds_g += [(disc_fake, g_adv), (gen_output, dgen)]
 
     E.backward([(disc_real, g_real), (disc_fake, g_fake)], "d")        # :112
-    if model.comm is not None:
-        model.comm.start(model.disc_params.grad)    # overlaps the generator backward pass below
-    E.backward(seeds_g, "g", collect=E.grad_record)                                            # :111
+    comm, hook = model.comm, None
+    if comm is not None:
+        side = [E._side_stream]
+        comm.begin(model.disc_params)
+        comm.finish(model.disc_params, side)        # the discriminator arena overlaps the generator backward pass below
+        comm.begin(model.gen_params)
+        hook = lambda: comm.poll(model.gen_params, E.complete, side)    # reverse-layer-order buckets, launched as they complete
+    E.backward(seeds_g, "g", collect=E.grad_record, on_node=hook)                              # :111
 
     scale = 1.0
-    if model.comm is not None:
-        model.comm.start(model.gen_params.grad)
-        model.comm.wait()
+    if comm is not None:
+        comm.finish(model.gen_params, side)
         scale = 1.0 / model.world_size
-    model.gen_optimizer.apply(E, model.gen_params, scale)               # :115
-    model.disc_optimizer.apply(E, model.disc_params, scale)             # :116
+        # the two updates are independent: the discriminator's runs while the generator's last bucket is still in flight
+        comm.wait_for(model.disc_params)
+        model.disc_optimizer.apply(E, model.disc_params, scale)         # :116
+        comm.wait_for(model.gen_params)
+        model.gen_optimizer.apply(E, model.gen_params, scale)           # :115
+    else:
+        model.gen_optimizer.apply(E, model.gen_params, scale)           # :115
+        model.disc_optimizer.apply(E, model.disc_params, scale)         # :116
     model.iterations += 1
 
     adv = 1e-3 * adv_raw[0]

@@ -52,6 +52,21 @@ int dg_version(void);
 /* 1 if the library was built with tcgen05 kernels and `device` is sm_100. */
 int dg_has_umma(dg_ctx* ctx);
 
+/* ---- data-parallel gradient exchange (the reference is single-GPU, train_srgan.py:15).  A thin wrapper over
+ * NCCL (resolved at run time with dlopen: no link-time dependency), so that a host that is not PyTorch can run the one
+ * collective of the train step: a sum all-reduce of the flat gradient arenas of train_srgan.py:111-112's two gradient lists.
+ * Rank 0 calls dg_comm_unique_id() and ships the dg_comm_unique_id_bytes() blob to the other ranks by any means; every rank
+ * then calls dg_comm_init(); dg_comm_allreduce() enqueues an in-place fp32 sum on the caller's stream (CUDA-graph capturable).
+ * Buckets are contiguous ranges of the flat arena: there is no pack / unpack step. */
+typedef struct dg_comm dg_comm;
+int dg_comm_unique_id_bytes(void);
+int dg_comm_unique_id(void* id_out);
+int dg_comm_init(dg_comm** out, const void* unique_id, int rank, int world, int device);
+int dg_comm_allreduce(dg_comm*, float* buf, long long count, void* stream);
+int dg_comm_rank(dg_comm*);
+int dg_comm_world(dg_comm*);
+void dg_comm_destroy(dg_comm*);
+
 /* ---- convolution, CUDA-core implicit GEMM (fp32 accumulate; any channel count; fp32 or bf16 I/O).
  * Used for the fp32 parity tier and for the <16-channel first/last layers. */
 /* y = act(conv(x, w) + bias).  keras Conv2D: srgan.py:154,246; autoencoder.py:95; pix2pix.py:115,207 */
@@ -109,6 +124,28 @@ int dg_umma_conv2d_fwd_bn_act(dg_ctx*, const dg_tensor* x, const void* w_packed,
 int dg_umma_conv2d_fwd_bn_act_blocks(dg_ctx*, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p);
 int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const float* bias,
                          const dg_tensor* dx, const dg_conv_params* p, void* stream);
+/* Input gradient of a stride-1 convolution whose INPUT was the output a = act(BN_batch(yb)) (+ skip) of a training-mode
+ * BatchNormalization (srgan.py:162-169, 246-250): besides dx = dL/da the launch (i) adds the gradient arriving over the skip
+ * connection (`residual`, may be NULL; srgan.py:169,174 Add) and (ii) accumulates, from the bf16-rounded dx it stores, the two
+ * per-channel sums of the BatchNorm backward pass -- sum g' and sum g'(yb - mean), g' = dx * act'(scale*yb + shift) -- into one
+ * row [2][Cin] per CTA (`bn`, may be NULL).  dg_bn_bwd_dx_from_partials then finishes the BatchNorm backward pass in ONE read
+ * of dx and yb.  Replaces tape.gradient's separate Add / BatchNorm-grad reductions (train_srgan.py:111). */
+typedef struct {
+  const dg_tensor* y;                                   /* yb: the BatchNorm input (raw conv output), shape of dx, bf16 */
+  const float* scale; const float* shift; const float* mean;   /* forward coefficients of that BatchNorm */
+  int act; float alpha;                                 /* activation behind it: DG_ACT_NONE / RELU / LRELU */
+  float* partials;                                      /* [dg_umma_conv2d_dgrad_fused_blocks()][2][Cin] fp32 */
+} dg_bn_bwd_stats;
+int dg_umma_conv2d_dgrad_fused(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const dg_tensor* dx, const dg_conv_params* p,
+                               const dg_tensor* residual, const dg_bn_bwd_stats* bn, void* stream);
+int dg_umma_conv2d_dgrad_fused_blocks(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p);
+/* dx half of the BatchNorm(+activation) backward pass when dg_umma_conv2d_dgrad_fused already reduced the per-channel sums
+ * (`partials` = its [rows][2][C] workspace): dx = gamma*invstd*(g' - mean(g') - xhat*mean(g' xhat)); dgamma / dbeta (may be NULL)
+ * receive sum g' xhat / sum g'.  One read of dy and x instead of two (autodiff of srgan.py:155,163,167,247). */
+int dg_bn_bwd_dx_from_partials(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const float* scale, const float* shift,
+                               const float* gamma, const float* save_mean, const float* save_invstd, int act, float act_alpha,
+                               const float* partials, int rows, const dg_tensor* dx, float* dgamma, float* dbeta, int accumulate,
+                               void* stream);
 /* capability queries: 1 when the tensor-core kernels have a tile configuration for the layer (shared-memory fit);
  * callers route the remaining layers to the CUDA-core kernels explicitly */
 int dg_umma_conv2d_fwd_supported(dg_ctx*, const dg_tensor* x, const dg_tensor* y, const dg_conv_params* p);
@@ -138,6 +175,13 @@ int dg_bn_stats(dg_ctx*, const dg_tensor* x, const float* gamma, const float* be
 int dg_bn_finalize(dg_ctx*, const float* partials, int nblocks, long long pixels, int c, const float* gamma, const float* beta,
                    float eps, float momentum, float* moving_mean, float* moving_var, float* scale, float* shift,
                    float* save_mean, float* save_invstd, void* stream);
+/* dg_bn_finalize + dg_bn_act_fwd as ONE launch (training mode, no dropout; srgan.py:155-157,163-169): every block of the apply
+ * pass sums the per-CTA statistics rows itself.  Returns 2 (nothing launched) when the views do not qualify for the 8-channel
+ * vector kernel: issue the two separate calls. */
+int dg_bn_act_fwd_from_partials(dg_ctx*, const dg_tensor* x, const float* partials, int nblocks, const float* gamma, const float* beta,
+                                float eps, float momentum, float* moving_mean, float* moving_var, float* scale, float* shift,
+                                float* save_mean, float* save_invstd, int act, float act_alpha, const float* prelu_alpha,
+                                const dg_tensor* residual, const dg_tensor* y, void* stream);
 /* inference: scale/shift from the moving statistics */
 int dg_bn_infer_affine(dg_ctx*, int c, const float* gamma, const float* beta, const float* moving_mean,
                        const float* moving_var, float eps, float* scale, float* shift, void* stream);

@@ -822,6 +822,151 @@ def test_umma_conv_bn_act_one_launch(L, case):
     assert relerr(c1[0], stt["bn/moving_mean"]) < 2e-2 and relerr(c1[1], stt["bn/moving_variance"]) < 2e-2
 
 
+@pytest.mark.parametrize("case", [(64, 16, 96, 96, "relu", False), (64, 2, 24, 20, None, True), (32, 3, 40, 24, "lrelu", False), (64, 4, 32, 32, "prelu", False),
+                                  (256, 1, 12, 20, "relu", True)])
+def test_bn_act_fwd_from_partials(L, case):
+    """dg_bn_act_fwd_from_partials (finalize folded into the apply pass) against dg_bn_finalize + dg_bn_act_fwd on the same
+    per-CTA statistics rows: coefficients and moving statistics to fp32 rounding, outputs within one bf16 ulp
+    (srgan.py:155-157,163-169)."""
+    C_, N, H, W, act, with_res = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, C_, generator=g, dtype=torch.float64) * 1.3 + 0.2)
+    res = _bf16_round(torch.randn(N, H, W, C_, generator=g, dtype=torch.float64)) if with_res else None
+    gamma = torch.rand(C_, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(C_, generator=g, dtype=torch.float64) * 0.3
+    alpha = torch.rand(C_, generator=g, dtype=torch.float64) * 0.4
+    rows = 37
+    P_ = N * H * W
+    # synthetic per-CTA rows: split the pixels into `rows` groups and sum each (what the conv epilogue would have written)
+    xf = x.reshape(P_, C_)
+    idx = torch.arange(P_) % rows
+    part = torch.zeros(rows, 2, C_, dtype=torch.float64)
+    part[:, 0].index_add_(0, idx, xf); part[:, 1].index_add_(0, idx, xf * xf)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    xd, partd = dev(x, torch.bfloat16), dev(part)
+    resd = dev(res, torch.bfloat16) if with_res else None
+    gd, bed, ad = dev(gamma), dev(beta), dev(alpha)
+    a_code = {None: 0, "relu": 1, "lrelu": 2, "prelu": 5}[act]
+    tx = L.tensor(xd)
+    tres = L.tensor(resd) if with_res else None
+    outs = []
+    for fused in (0, 1):
+        mm, mv = torch.zeros(C_, device="cuda"), torch.ones(C_, device="cuda")
+        sc, sh, mean, inv = [torch.empty(C_, device="cuda") for _ in range(4)]
+        y = torch.full((N, H, W, C_), 7.0, device="cuda", dtype=torch.bfloat16)
+        ty = L.tensor(y)
+        if fused:
+            rc = lib.dg_bn_act_fwd_from_partials(ctx, C.byref(tx), partd.data_ptr(), rows, gd.data_ptr(), bed.data_ptr(), 1e-3, 0.8, mm.data_ptr(),
+                                                 mv.data_ptr(), sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), inv.data_ptr(), a_code, 0.2,
+                                                 ad.data_ptr() if act == "prelu" else None, C.byref(tres) if with_res else None, C.byref(ty), st)
+            assert rc == 0, rc
+        else:
+            L.check(lib.dg_bn_finalize(ctx, partd.data_ptr(), rows, P_, C_, gd.data_ptr(), bed.data_ptr(), 1e-3, 0.8, mm.data_ptr(), mv.data_ptr(),
+                                       sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), inv.data_ptr(), st))
+            L.check(lib.dg_bn_act_fwd(ctx, C.byref(tx), sc.data_ptr(), sh.data_ptr(), a_code, 0.2, ad.data_ptr() if act == "prelu" else None,
+                                      C.byref(tres) if with_res else None, 0, 0, 0, None, C.byref(ty), st))
+        torch.cuda.synchronize()
+        outs.append((y, sc, sh, mean, inv, mm, mv))
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert relerr(b, a) < 1e-6
+    assert relerr(outs[1][0], outs[0][0]) < 2 ** -7
+
+
+# ---------------------------------------------------------------- dgrad + skip-add + BatchNorm-backward sums in the epilogue
+@pytest.mark.parametrize("case", [(3, 64, 64, 2, 24, 20, "relu", True), (3, 64, 64, 16, 96, 96, "relu", False), (3, 64, 64, 16, 96, 96, None, True),
+                                  (3, 32, 64, 3, 40, 24, "lrelu", False), (3, 32, 32, 2, 33, 19, "lrelu", True), (1, 192, 32, 2, 16, 16, None, True),
+                                  (3, 64, 64, 5, 96, 96, None, False), (1, 32, 192, 2, 20, 12, "relu", False), (3, 64, 64, 4, 30, 50, "none_nostats", True)])
+def test_umma_dgrad_fused_bn_bwd(L, case):
+    """dg_umma_conv2d_dgrad_fused + dg_bn_bwd_dx_from_partials against the calls they replace (dg_umma_conv2d_dgrad, dg_add,
+    dg_bn_act_bwd): the summed gradient must be bit-identical to dgrad-then-add on bf16 storage up to the single rounding the
+    fusion removes (the unfused path rounds the dgrad result to bf16 BEFORE adding the skip gradient), the BatchNorm input
+    gradient and dgamma / dbeta must agree within the bf16 bound, and everything must match the float64 oracle
+    (autodiff of srgan.py:162-169: conv -> BN -> ReLU -> conv -> BN -> Add)."""
+    k, cin, cout, N, H, W, act, with_res = case
+    stats = act != "none_nostats"
+    if not stats:
+        act = None
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    # forward of the layer pair: yb = BN input (raw output of the previous conv), a = act(BN(yb)), z = conv(a)
+    yb = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64) * 1.5 + 0.3)
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * (1.0 / (k * np.sqrt(cin))))
+    gz = _bf16_round(torch.randn(N, H, W, cout, generator=g, dtype=torch.float64))
+    gres = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64)) if with_res else None
+    gamma = torch.rand(cin, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(cin, generator=g, dtype=torch.float64) * 0.3
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same")
+    ybd, gzd = dev(yb, torch.bfloat16), dev(gz, torch.bfloat16)
+    gresd = dev(gres, torch.bfloat16) if with_res else None
+    gd, bed = dev(gamma), dev(beta)
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, dev(w).data_ptr(), pk.data_ptr(), k, k, cin, cout, 1, st))
+    # BatchNorm forward coefficients of yb through the library
+    a_code = {None: 0, "relu": 1, "lrelu": 2}[act]
+    tyb = L.tensor(ybd)
+    nb = lib.dg_bn_workspace_bytes(C.byref(tyb)); wk = ws(nb)
+    sc, sh, mean, inv = [torch.empty(cin, device="cuda") for _ in range(4)]
+    L.check(lib.dg_bn_stats(ctx, C.byref(tyb), gd.data_ptr(), bed.data_ptr(), 1e-3, 0.99, None, None, sc.data_ptr(), sh.data_ptr(), mean.data_ptr(),
+                            inv.data_ptr(), wk.data_ptr(), nb, st))
+    tgz = L.tensor(gzd)
+    # ---- reference: dgrad, add, two-pass BatchNorm backward
+    dx0 = torch.empty(N, H, W, cin, device="cuda", dtype=torch.bfloat16)
+    tdx0 = L.tensor(dx0)
+    L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tgz), pk.data_ptr(), None, C.byref(tdx0), C.byref(cp), st))
+    if with_res:
+        g0 = torch.empty_like(dx0)
+        tr, tg0 = L.tensor(gresd), L.tensor(g0)
+        L.check(lib.dg_add(ctx, C.byref(tdx0), C.byref(tr), C.byref(tg0), st))
+    else:
+        g0 = dx0
+    tg0 = L.tensor(g0)
+    dyb0 = torch.empty_like(dx0); dga0 = torch.empty(cin, device="cuda"); dbe0 = torch.empty(cin, device="cuda")
+    tdyb0 = L.tensor(dyb0)
+    L.check(lib.dg_bn_act_bwd(ctx, C.byref(tg0), C.byref(tyb), sc.data_ptr(), sh.data_ptr(), gd.data_ptr(), mean.data_ptr(), inv.data_ptr(), a_code,
+                              0.2, None, 0, 0, 0, None, C.byref(tdyb0), dga0.data_ptr(), dbe0.data_ptr(), None, 0, wk.data_ptr(), nb, st))
+    # ---- fused: one dgrad launch (+ skip gradient, + sums), one dx pass; twice (no state may be left behind)
+    g1 = torch.empty_like(dx0); tg1 = L.tensor(g1)
+    rows = lib.dg_umma_conv2d_dgrad_fused_blocks(ctx, C.byref(tgz), C.byref(tg1), C.byref(cp))
+    if rows == 0:
+        assert (k, cin, cout) != (3, 64, 64), "the fused epilogue must apply to the generator trunk layers"
+        pytest.skip("the fused BatchNorm-backward epilogue does not apply to this layer")
+    part = torch.full((rows, 2, cin), float("nan"), device="cuda")
+    dyb1 = torch.empty_like(dx0); dga1 = torch.empty(cin, device="cuda"); dbe1 = torch.empty(cin, device="cuda")
+    tdyb1 = L.tensor(dyb1)
+    for rep in range(2):
+        g1.fill_(7.0); dyb1.fill_(7.0); part.fill_(float("nan"))
+        bs = L.DgBnBwdStats(C.pointer(tyb), sc.data_ptr(), sh.data_ptr(), mean.data_ptr(), a_code, 0.2, part.data_ptr())
+        tr = L.tensor(gresd) if with_res else None
+        L.check(lib.dg_umma_conv2d_dgrad_fused(ctx, C.byref(tgz), pk.data_ptr(), C.byref(tg1), C.byref(cp), C.byref(tr) if with_res else None,
+                                               C.byref(bs) if stats else None, st))
+        if stats:
+            L.check(lib.dg_bn_bwd_dx_from_partials(ctx, C.byref(tg1), C.byref(tyb), sc.data_ptr(), sh.data_ptr(), gd.data_ptr(), mean.data_ptr(),
+                                                   inv.data_ptr(), a_code, 0.2, part.data_ptr(), rows, C.byref(tdyb1), dga1.data_ptr(),
+                                                   dbe1.data_ptr(), 0, st))
+        torch.cuda.synchronize()
+        if not with_res:
+            assert torch.equal(g1, g0), "without a skip gradient the stored gradient must equal the plain dgrad bit for bit"
+        else:
+            assert relerr(g1, g0) < 2 ** -7
+        if stats:
+            assert not torch.isnan(part).any()
+            assert relerr(dbe1, dbe0) < 5e-3 and relerr(dga1, dga0) < 5e-3, (relerr(dbe1, dbe0), relerr(dga1, dga0))
+            assert relerr(dyb1, dyb0) < BF16_TOL
+    # ---- float64 oracle of the same sub-graph
+    ybr = yb.clone().requires_grad_(True); gar = gamma.clone().requires_grad_(True); ber = beta.clone().requires_grad_(True)
+    p = {"bn/gamma": gar, "bn/beta": ber, "bn/moving_mean": torch.zeros(cin, dtype=torch.float64), "bn/moving_variance": torch.ones(cin, dtype=torch.float64)}
+    t = OT.batch_norm(ybr, p, "bn", True, {}, momentum=0.99, eps=1e-3)
+    if act == "relu": t = torch.relu(t)
+    elif act == "lrelu": t = OT.leaky_relu(t, 0.2)
+    t.retain_grad()
+    z = OT.conv2d(t, w, None, stride=1, padding="same")
+    loss = (z * gz).sum() + ((t * gres).sum() if with_res else 0.0)
+    loss.backward()
+    assert relerr(g1, t.grad) < BF16_TOL
+    if stats:
+        assert relerr(dyb1, ybr.grad) < BF16_TOL and relerr(dga1, gar.grad) < BF16_TOL and relerr(dbe1, ber.grad) < BF16_TOL
+
+
 # ---------------------------------------------------------------- K-outer mode (streamed weights reused by several sub-tiles)
 @pytest.mark.parametrize("case", [(3, 256, 64, 2, 70, 20, "dgrad"), (3, 256, 64, 1, 64, 24, "fwd"), (3, 128, 256, 2, 40, 17, "fwd"),
                                   (3, 256, 256, 1, 48, 16, "fwd"), (1, 512, 64, 2, 33, 9, "fwd"), (3, 192, 96, 1, 30, 30, "dgrad")])

@@ -50,3 +50,53 @@ def test_allreduce_is_mean_of_shard_gradients(tmp_path):
         mean = (r[0][loc] + r[1][loc]) / 2
         assert torch.allclose(r[0][key], mean) and torch.allclose(r[1][key], mean)
         assert torch.equal(r[0][key], r[1][key])             # every replica applies the same update
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from collections import OrderedDict
+        from denoise_gan_b200.params import ParamSet
+        g = torch.Generator().manual_seed(5)
+        shapes = [(3, 3, 16, 64), (64,), (64,), (3, 3, 64, 64), (64,), (64,), (3, 3, 64, 64), (1, 1, 64, 3), (3,)]
+        tensors = OrderedDict((f"g/p{i}", torch.randn(*s, generator=g)) for i, s in enumerate(shapes))
+        ps = ParamSet("g", tensors, "cpu")
+        ps.grad.copy_(torch.arange(ps.grad.numel(), dtype=torch.float32) * (rank + 1))     # rank-dependent "gradients"
+        local = ps.grad.clone()
+        comm = GradAllReduce("cpu", bucket_mb=0.1)                                           # ~100 KB buckets -> several of them
+        b = comm.buckets(ps)
+        assert len(b) >= 2 and sum(c for _, c, _ in b) == ps.numel and b[0][0] + b[0][1] == ps.numel and b[-1][0] == 0
+        assert set().union(*[n for _, _, n in b]) == set(tensors)                              # every variable in exactly one bucket
+        assert sum(len(n) for _, _, n in b) == len(tensors)
+        comm.begin(ps)
+        done, launched_at = set(), []
+        for name in reversed(list(tensors)):                                                  # the backward pass completes the LAST variables first
+            done.add(name)
+            comm.poll(ps, done)
+            launched_at.append(comm.launched)
+        assert launched_at[-1] == len(b) and launched_at[0] <= 1 and sorted(launched_at) == launched_at
+        comm.poll(ps, done)                                                                    # idempotent
+        comm.finish(ps)
+        assert comm.launched == len(b)
+        # a second step where one variable never completes: finish() must still exchange its bucket
+        ps.grad.copy_(local)
+        comm.begin(ps)
+        comm.poll(ps, set(list(tensors)[1:]))
+        assert comm.launched < 2 * len(b)
+        comm.finish(ps)
+        assert comm.launched == 2 * len(b)
+        torch.save({"sum": ps.grad.clone(), "local": local}, os.path.join(out_dir, f"b{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_exchange_reverse_layer_order(tmp_path):
+    """parallel.GradAllReduce buckets: contiguous ranges of the flat arena in reverse layer order, launched by poll() as soon
+    as all their variables are complete, remaining ones by finish(); the union of the bucket all-reduces equals ONE all-reduce of
+    the whole arena."""
+    world, port = 2, _free_port()
+    mp.spawn(_bucket_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"b{i}.pt")) for i in range(world)]
+    total = r[0]["local"] + r[1]["local"]
+    assert torch.equal(r[0]["sum"], total) and torch.equal(r[1]["sum"], total)
