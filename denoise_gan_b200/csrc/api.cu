@@ -7,7 +7,9 @@
 
 static thread_local char g_err[1024] = "";
 
-int g_dg_pdl = []() { const char* e = getenv("DG_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // default OFF: inside the step's CUDA graph the early-launched CTAs cost more than the hidden launch latency (A/B: 8.43 vs 8.34 ms)
+// default ON since round 2 (same-box A/B of the C3 step: 7.21 vs 7.42 ms in job r2_02, 7.40 vs 7.70 ms in job r2_05); it had been
+// off in round 1, where the early-launched CTAs cost more than the hidden launch latency (8.43 vs 8.34 ms).  DG_PDL=0 disables.
+int g_dg_pdl = []() { const char* e = getenv("DG_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 
 int g_dg_coop = []() { const char* e = getenv("DG_COOP"); return (e && e[0] == '0') ? 0 : 1; }();   // cooperative-launch attribute of the grid-barrier kernels
 

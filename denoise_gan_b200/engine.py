@@ -114,7 +114,11 @@ class Engine:
         # input-gradient convolutions add the skip-connection gradient and reduce the sums of the BatchNorm backward pass in
         # their epilogue (dg_umma_conv2d_dgrad_fused + dg_bn_bwd_dx_from_partials): no add launch, one pass over dy / x
         # instead of two per BatchNorm of the generator trunk and of the stride-1 discriminator layers
-        self.fuse_dgrad_bn_bwd = os.environ.get("DG_DGRAD_BN_BWD", "1") != "0"
+        # Modes (DG_DGRAD_BN_BWD): 0 off; 1 (default) skip-add only; 2 skip-add + BatchNorm-backward sums.  Mode 2 is parity-green
+        # but SLOWER on B200 (job r2_05: step 7.70 vs 7.37 ms): reducing 128 rows x 128 values per tile with warp shuffles (496 per
+        # thread and tile, 32 lanes per clock and SM) takes 5-8 K cycles per tile against the 3.4 K the MMAs leave an epilogue group
+        self.fuse_dgrad_mode = int(os.environ.get("DG_DGRAD_BN_BWD", "1"))
+        self.fuse_dgrad_bn_bwd = self.fuse_dgrad_mode != 0
         self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"   # dg_bn_act_fwd_from_partials instead of finalize + apply
         self._bwd_part: dict = {}       # (bn_act seq, tag) -> (partials, rows) left by the fused dgrad for that BatchNorm's backward
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
@@ -490,7 +494,7 @@ class Engine:
             if need_in[0] and fctx is not None and umma_d and stride == 1 and dpre.dtype == torch.bfloat16 and x.t.dtype == torch.bfloat16:
                 # this launch produces the LAST contribution to dL/dx: the skip-connection gradient accumulated so far is added
                 # in the epilogue, and when x is the output of a training-mode BatchNorm its backward sums are reduced there too
-                res, src = fctx.get("residual"), x.bn_src
+                res, src = fctx.get("residual"), (x.bn_src if self.fuse_dgrad_mode >= 2 else None)
                 if res is not None and (res.dtype != torch.bfloat16 or tuple(res.shape) != tuple(x.shape)):
                     res = None
                 keyq = ("dgf", N, H, W, cin, Ho, Wo, cout, kh, kw, pt, pl)

@@ -79,4 +79,6 @@ def test_two_rank_step_matches_mean_of_shard_oracle_gradients(tmp_path, fp16):
         print(f"fp16={fp16} {key}: worst relative L2 error of the averaged gradient vs the mean of the shard oracles {worst:.3e}")
     for key in ("g", "d"):
         for name, t0 in r[0][key].items():
+            if name.endswith(("moving_mean", "moving_variance")):
+                continue            # BatchNorm moving statistics are per replica by design (rank 0's are the exported ones)
             assert torch.equal(t0, r[1][key][name]), f"{name}: replicas diverged after one step"
