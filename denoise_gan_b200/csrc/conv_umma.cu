@@ -591,119 +591,127 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
 
 #undef DG_GROUP_SYNC
 
-// Sum over the 32 lanes of a warp of x[i] for each of 32 values i, transposed: lane l returns the total of x[l].  Each step
-// halves the values a lane carries (it keeps the half named by one bit of its lane index and hands the other half to its
-// partner), 31 shuffles in all instead of 32 x 5.
-__device__ __forceinline__ float warp_transpose_sum32(float (&x)[32], int lane) {
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      const float keep = up ? x[i + h] : x[i];
-      const float send = up ? x[i] : x[i + h];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  return x[0];
+__device__ __forceinline__ uint32_t ldg_u32(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ uint4 ldg_v4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-
-// Epilogue of the BatchNorm-backward instance (UmmaConvParams::bwd_*).  Thread = accumulator row = one output pixel; it
-// fetches its pixel's skip gradient and BatchNorm input straight from global memory (NB x 2 bytes each, issued before the wait
-// for the accumulator), adds, rounds to bf16, stages the row for the bulk store, and feeds g' and g'(yb - mean) of 16 channels
-// at a time to the transposed warp sum: lane l < 16 ends up owning sum g' of channel 16k + l, lane l >= 16 sum g'(yb - mean) of
-// channel 16k + l - 16, for its warp's rows.
+// Epilogue of the BatchNorm-backward instance (UmmaConvParams::bwd_*).
+// The accumulator is read in the mma-fragment layout (tcgen05.ld 16x256b, sm100.cuh): a thread owns the column pairs
+// 8j + 2(T%4) + {0,1} (j < NB/8) of FOUR rows of a 128-row sub-tile -- the pixels (4q + {0,1,2,3}, T/4) of the 16 x 8 tile, q = the
+// warp's TMEM lane quarter -- so the per-channel sums of the BatchNorm backward pass accumulate IN THE THREAD over rows and over
+// all tiles of the CTA, and the only cross-lane step is one transposed reduction over the 8 lanes that share T%4 at the very end
+// (28 shuffles per thread and kernel).  A first version read one accumulator row per thread (32x32b) and reduced 128 rows x
+// 128 values per tile with shuffles: 496 per thread and tile, 5-8 K cycles per tile against the 3.4 K the MMAs leave an epilogue
+// group (job r2_05/06: 29 us per launch instead of 15).
+// Per element: g = acc + skip gradient, rounded to bf16 (the stored value), staged for the bulk store (4-byte pieces, swizzled:
+// the 8 quads of a warp hit 8 different 16-byte chunks, conflict-free); g' = g * act'(scale*yb + shift); sums g' and g'(yb - mean).
+// The skip gradient and yb come straight from global memory as 4-byte loads (a quad covers 16 contiguous bytes; every 128-byte
+// line is used completely by the 8 loads of a quad), issued before the wait for the accumulator.
 template <int AM, int NB>
 __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int nb0,
                                                   int total_tiles, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, float* red_s, int grp,
                                                   const float* __restrict__ cs) {
-  constexpr int NV = NB / 8, NG = NB / 16;
+  constexpr int NJ = NB / 8;          // 8-column blocks of the N block
+  constexpr int V = 4 * NJ;           // per-thread accumulators: [2 sums][NJ][2 columns]
   const uint32_t bar_id = 1u + (uint32_t)grp;
-  const int m_idx = q * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t RB = (uint32_t)NB * 2u, mask = P.stg_mask;
   const bool leader = q == 0 && lane == 0;
   const bool has_res = P.bwd_res != nullptr;
   const uint32_t stg = stg_base + (uint32_t)grp * P.stg_bytes;
-  float asum[NG];
+  const int t0 = lane & 3, t1 = lane >> 2;
+  float S[V];
 #pragma unroll
-  for (int k = 0; k < NG; ++k) asum[k] = 0.f;
+  for (int i = 0; i < V; ++i) S[i] = 0.f;
   int it = grp;
   for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
     const int b = it & ((1 << P.nbuf_shift) - 1);
     const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
     const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h, n = t2 / P.tiles_h;
-    for (int m = 0; m < P.mt; ++m) {
-      const int ph = th * 16 * P.mt + m * 16 + (m_idx >> 3);
-      const int pw = tw * 8 + (m_idx & 7);
-      const bool valid = ph < P.out_h && pw < P.out_w;
-      uint4 ry[NV], rr[NV];
+    const int pw = tw * 8 + t1;
+    for (int mh = 0; mh < 2 * P.mt; ++mh) {          // (sub-tile m, 16-lane half hb) of this warp's quarter
+      const int m = mh >> 1, hb = mh & 1;
+      const int r0 = q * 32 + hb * 16 + t1;          // accumulator rows r0 and r0 + 8 of sub-tile m
+      const int ph0 = th * 16 * P.mt + m * 16 + (r0 >> 3);
+      const bool va = ph0 < P.out_h && pw < P.out_w, vb = ph0 + 1 < P.out_h && pw < P.out_w;
+      uint32_t ya[NJ], yb[NJ], ra[NJ], rb[NJ];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) { ry[j] = make_uint4(0u, 0u, 0u, 0u); rr[j] = make_uint4(0u, 0u, 0u, 0u); }
-      if (valid && !(P.dbg_flags & 64)) {
-        if (AM >= 0) {
-          const __nv_bfloat16* yp = P.bwd_y + ((long)n * P.bwd_y_sn + (long)ph * P.bwd_y_sh + (long)pw * P.bwd_y_sw + nb0);
+      for (int j = 0; j < NJ; ++j) { ya[j] = yb[j] = ra[j] = rb[j] = 0u; }
+      if (AM >= 0) {
+        const __nv_bfloat16* yp = P.bwd_y + ((long)n * P.bwd_y_sn + (long)ph0 * P.bwd_y_sh + (long)pw * P.bwd_y_sw + nb0 + 2 * t0);
+        if (va) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j) ry[j] = ldg_v4(yp + 8 * j);
+          for (int j = 0; j < NJ; ++j) ya[j] = ldg_u32(yp + 8 * j);
         }
-        if (has_res) {
-          const __nv_bfloat16* rp = P.bwd_res + ((long)n * P.bwd_r_sn + (long)ph * P.bwd_r_sh + (long)pw * P.bwd_r_sw + nb0);
+        if (vb) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j) rr[j] = ldg_v4(rp + 8 * j);
+          for (int j = 0; j < NJ; ++j) yb[j] = ldg_u32(yp + P.bwd_y_sh + 8 * j);
         }
       }
-      if (m == 0) {
+      if (has_res) {
+        const __nv_bfloat16* rp = P.bwd_res + ((long)n * P.bwd_r_sn + (long)ph0 * P.bwd_r_sh + (long)pw * P.bwd_r_sw + nb0 + 2 * t0);
+        if (va) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) ra[j] = ldg_u32(rp + 8 * j);
+        }
+        if (vb) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) rb[j] = ldg_u32(rp + P.bwd_r_sh + 8 * j);
+        }
+      }
+      if (mh == 0) {
+        // the lines of the other half's rows (two image rows further down) start travelling to L1 under the wait below
+        if (AM >= 0 && ph0 + 3 < P.out_h && pw < P.out_w) {
+          const __nv_bfloat16* yp2 = P.bwd_y + ((long)n * P.bwd_y_sn + (long)(ph0 + 2) * P.bwd_y_sh + (long)pw * P.bwd_y_sw + nb0 + 2 * t0);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(yp2));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(yp2 + P.bwd_y_sh));
+        }
+        if (has_res && ph0 + 3 < P.out_h && pw < P.out_w) {
+          const __nv_bfloat16* rp2 = P.bwd_res + ((long)n * P.bwd_r_sn + (long)(ph0 + 2) * P.bwd_r_sh + (long)pw * P.bwd_r_sw + nb0 + 2 * t0);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(rp2));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(rp2 + P.bwd_r_sh));
+        }
         if (leader) { if (grp == 0) dbg_mark(P, 2, it >> 1, 0); tma_store_wait_read<0>(); }     // this group's previous store has left the staging buffer
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
         tc_fence_after();
         if (leader && grp == 0) dbg_mark(P, 2, it >> 1, 1);
       }
-      const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.mt + m) * NB);
-      const uint32_t row_off = (uint32_t)(m * 128 + m_idx) * RB;
+      uint32_t v[4 * NJ];
+      const uint32_t acc = tmem + ((uint32_t)(q * 32 + hb * 16) << 16) + (uint32_t)((b * P.mt + m) * NB);
+      if constexpr (NJ == 8) tmem_ld_16x256b_x8(acc, v);
+      else tmem_ld_16x256b_x4(acc, v);
+      tmem_ld_wait();
+      const uint32_t offa = (uint32_t)(m * 128 + r0) * RB + 4u * (uint32_t)t0, offb = offa + 8u * RB;
 #pragma unroll
-      for (int k = 0; k < NG; ++k) {
-        uint32_t v[16];
-        tmem_ld_32x16(acc + 16 * k, v);
-        tmem_ld_wait();
-        const uint32_t rw[8] = {rr[2 * k].x, rr[2 * k].y, rr[2 * k].z, rr[2 * k].w, rr[2 * k + 1].x, rr[2 * k + 1].y, rr[2 * k + 1].z, rr[2 * k + 1].w};
-        const uint32_t yw[8] = {ry[2 * k].x, ry[2 * k].y, ry[2 * k].z, ry[2 * k].w, ry[2 * k + 1].x, ry[2 * k + 1].y, ry[2 * k + 1].z, ry[2 * k + 1].w};
-        uint32_t gw[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float f0 = __uint_as_float(v[2 * j]) + __uint_as_float(rw[j] << 16);
-          const float f1 = __uint_as_float(v[2 * j + 1]) + __uint_as_float(rw[j] & 0xffff0000u);
-          gw[j] = valid ? pack_bf16x2(f0, f1) : 0u;     // rows outside the image: zeros (clipped by the store, neutral in the sums)
-        }
-        st_shared_v4(stg + swz(row_off + 32u * k, mask), gw[0], gw[1], gw[2], gw[3]);
-        st_shared_v4(stg + swz(row_off + 32u * k + 16u, mask), gw[4], gw[5], gw[6], gw[7]);
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t ga = va ? pack_bf16x2(__uint_as_float(v[4 * j]) + __uint_as_float(ra[j] << 16),
+                                             __uint_as_float(v[4 * j + 1]) + __uint_as_float(ra[j] & 0xffff0000u)) : 0u;
+        const uint32_t gb = vb ? pack_bf16x2(__uint_as_float(v[4 * j + 2]) + __uint_as_float(rb[j] << 16),
+                                             __uint_as_float(v[4 * j + 3]) + __uint_as_float(rb[j] & 0xffff0000u)) : 0u;
+        st_shared_u32(stg + swz(offa + 16u * j, mask), ga);
+        st_shared_u32(stg + swz(offb + 16u * j, mask), gb);
         if (AM >= 0) {
-          float x[32];
+          const float2 sc = *reinterpret_cast<const float2*>(cs + 8 * j + 2 * t0);
+          const float2 sh = *reinterpret_cast<const float2*>(cs + 64 + 8 * j + 2 * t0);
+          const float2 mu = *reinterpret_cast<const float2*>(cs + 128 + 8 * j + 2 * t0);
+          const float scv[2] = {sc.x, sc.y}, shv[2] = {sh.x, sh.y}, muv[2] = {mu.x, mu.y};
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 sc = *reinterpret_cast<const float4*>(cs + 16 * k + 4 * j4);
-            const float4 sh = *reinterpret_cast<const float4*>(cs + 64 + 16 * k + 4 * j4);
-            const float4 mu = *reinterpret_cast<const float4*>(cs + 128 + 16 * k + 4 * j4);
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, muv[4] = {mu.x, mu.y, mu.z, mu.w};
+          for (int rr = 0; rr < 2; ++rr) {
+            const uint32_t gw = rr ? gb : ga, yw = rr ? yb[j] : ya[j];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * j4 + e;                  // channel 16k + j of this pixel
-              const uint32_t gword = gw[j >> 1], yword = yw[j >> 1];
-              const float g = (j & 1) ? __uint_as_float(gword & 0xffff0000u) : __uint_as_float(gword << 16);
-              const float yv = (j & 1) ? __uint_as_float(yword & 0xffff0000u) : __uint_as_float(yword << 16);
+            for (int e = 0; e < 2; ++e) {
+              const float g = e ? __uint_as_float(gw & 0xffff0000u) : __uint_as_float(gw << 16);
+              const float yv = e ? __uint_as_float(yw & 0xffff0000u) : __uint_as_float(yw << 16);
               const float tt = fmaf(yv, scv[e], shv[e]);
               float d = 1.f;
               if (AM == 1) d = tt > 0.f ? 1.f : 0.f;
               if (AM == 2) d = tt >= 0.f ? 1.f : P.bwd_alpha;
-              const float gp = __fmul_rn(g, d);          // the same rounded product as the dx pass (bn_bwd_dx8_kernel)
-              x[j] = gp;
-              x[16 + j] = gp * (yv - muv[e]);
+              const float gp = __fmul_rn(g, d);          // the same rounded product as the dx pass (bn_bwd_dx_part8_kernel)
+              S[2 * j + e] += gp;
+              S[2 * NJ + 2 * j + e] = fmaf(gp, yv - muv[e], S[2 * NJ + 2 * j + e]);
             }
           }
-          if (P.dbg_flags & 32) asum[k] += x[0] + x[16]; else
-          asum[k] += warp_transpose_sum32(x, lane);
         }
       }
     }
@@ -720,18 +728,34 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
   }
   if (leader) tma_store_wait<0>();
   if (AM >= 0) {
-    asm volatile("bar.sync 3, 256;" ::: "memory");   // both groups: all stores have left the staging buffers, buffer 0 is the scratch of the final sum
-    const int gwarp = grp * 4 + q;                   // [8 warps][NG][32] floats <= 4 KB
+    // transposed sum over the 8 lanes that share T%4 (lane bits 4, 3, 2): each step halves the values a lane carries; the lane
+    // ends with the V/8 values i0 .. i0 + V/8 - 1, i0 = (V/2) bit4 + (V/4) bit3 + (V/8) bit2, of S = [sum][j][e]
 #pragma unroll
-    for (int k = 0; k < NG; ++k) red_s[(gwarp * NG + k) * 32 + lane] = asum[k];
+    for (int step = 0; step < 3; ++step) {
+      const int h = V >> (step + 1), lbit = 16 >> step;
+      const bool up = (lane & lbit) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const float keep = up ? S[i + h] : S[i];
+        const float send = up ? S[i] : S[i + h];
+        S[i] = keep + __shfl_xor_sync(0xffffffffu, send, lbit);
+      }
+    }
+    constexpr int KV = V / 8;
+    asm volatile("bar.sync 3, 256;" ::: "memory");   // both groups: all stores have left the staging buffers, buffer 0 is the scratch of the final sum
+    const int gwarp = grp * 4 + q;                   // [8 warps][KV][32] floats <= 4 KB
+#pragma unroll
+    for (int k = 0; k < KV; ++k) red_s[(gwarp * KV + k) * 32 + lane] = S[k];
     asm volatile("bar.sync 3, 256;" ::: "memory");
     const int etid = gwarp * 32 + lane;
-    if (etid < NG * 32) {
+    if (etid < KV * 32) {
       const int k = etid >> 5, l = etid & 31;
       float t = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) t += red_s[(r * NG + k) * 32 + l];
-      P.bn_partials[(size_t)blockIdx.x * 2 * P.cout_total + (size_t)(l >> 4) * P.cout_total + nb0 + 16 * k + (l & 15)] = t;
+      for (int r = 0; r < 8; ++r) t += red_s[(r * KV + k) * 32 + l];
+      const int i = (V / 2) * ((l >> 4) & 1) + (V / 4) * ((l >> 3) & 1) + (V / 8) * ((l >> 2) & 1) + k;   // index into [sum][j][e]
+      const int which = i / (2 * NJ), j = (i % (2 * NJ)) >> 1, e = i & 1;
+      P.bn_partials[(size_t)blockIdx.x * 2 * P.cout_total + (size_t)which * P.cout_total + nb0 + 8 * j + 2 * (l & 3) + e] = t;
     }
   }
 }

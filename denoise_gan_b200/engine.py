@@ -114,10 +114,10 @@ class Engine:
         # input-gradient convolutions add the skip-connection gradient and reduce the sums of the BatchNorm backward pass in
         # their epilogue (dg_umma_conv2d_dgrad_fused + dg_bn_bwd_dx_from_partials): no add launch, one pass over dy / x
         # instead of two per BatchNorm of the generator trunk and of the stride-1 discriminator layers
-        # Modes (DG_DGRAD_BN_BWD): 0 off; 1 (default) skip-add only; 2 skip-add + BatchNorm-backward sums.  Mode 2 is parity-green
-        # but SLOWER on B200 (job r2_05: step 7.70 vs 7.37 ms): reducing 128 rows x 128 values per tile with warp shuffles (496 per
-        # thread and tile, 32 lanes per clock and SM) takes 5-8 K cycles per tile against the 3.4 K the MMAs leave an epilogue group
-        self.fuse_dgrad_mode = int(os.environ.get("DG_DGRAD_BN_BWD", "1"))
+        # Modes (DG_DGRAD_BN_BWD): 0 off; 1 skip-add only; 2 (default) skip-add + BatchNorm-backward sums.  Same-box A/B of the C3 step
+        # (job r2_09): 7.21 ms (mode 2) vs 7.36 ms (mode 1).  The first version of mode 2 (one accumulator row per thread, 496 shuffles
+        # per thread and tile) was SLOWER (7.70 vs 7.37 ms, job r2_05); the epilogue now reads the accumulator in mma-fragment layout
+        self.fuse_dgrad_mode = int(os.environ.get("DG_DGRAD_BN_BWD", "2"))
         self.fuse_dgrad_bn_bwd = self.fuse_dgrad_mode != 0
         self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"   # dg_bn_act_fwd_from_partials instead of finalize + apply
         self._bwd_part: dict = {}       # (bn_act seq, tag) -> (partials, rows) left by the fused dgrad for that BatchNorm's backward
