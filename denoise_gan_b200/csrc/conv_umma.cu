@@ -103,7 +103,7 @@ struct UmmaConvParams {
   // the dgrad of every trunk convolution feeds the backward pass of the BatchNorm in front of it).  The epilogue
   //   * adds the gradient that arrives over the skip connection (bwd_res, srgan.py:169 Add) -- no separate add launch,
   //   * stores g (bf16, staged TMA store), and
-  //   * accumulates from the rounded g the two per-channel sums of the BatchNorm backward pass, sum g' and sum g' (yb - mean)
+  //   * accumulates from the rounded g the two per-channel sums of the BatchNorm backward pass, sum g' and sum g' yb
   //     with g' = g * act'(scale * yb + shift), into the per-CTA rows `bn_partials` ([gridDim.x][2][Cout]),
   // so that the BatchNorm backward pass is ONE read of g and yb (dg_bn_bwd_dx_from_partials) instead of two.
   int bwd_am;                      // -1: no statistics; 0 none / 1 relu / 2 leaky relu: activation behind the BatchNorm
@@ -592,8 +592,16 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
 #undef DG_GROUP_SYNC
 
 __device__ __forceinline__ uint32_t ldg_u32(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+// (no "memory" clobber on the two helpers below: volatile keeps them ordered among themselves -- a thread reads its yb words
+// before it overwrites them -- while the compiler stays free to hoist the coefficient loads and interleave the arithmetic of
+// several column blocks; with the clobber every block waited for its own shared-memory loads, IPC 0.27 per scheduler)
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint32_t ld_shared_u32_nc(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
 // Epilogue of the BatchNorm-backward instance (UmmaConvParams::bwd_*).
@@ -604,14 +612,18 @@ __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
 // (28 shuffles per thread and kernel).  A first version read one accumulator row per thread (32x32b) and reduced 128 rows x
 // 128 values per tile with shuffles: 496 per thread and tile, 5-8 K cycles per tile against the 3.4 K the MMAs leave an epilogue
 // group (job r2_05/06: 29 us per launch instead of 15).
-// Per element: g = acc + skip gradient, rounded to bf16 (the stored value), staged for the bulk store (4-byte pieces, swizzled:
-// the 8 quads of a warp hit 8 different 16-byte chunks, conflict-free); g' = g * act'(scale*yb + shift); sums g' and g'(yb - mean).
-// The skip gradient and yb come straight from global memory as 4-byte loads (a quad covers 16 contiguous bytes; every 128-byte
-// line is used completely by the 8 loads of a quad), issued before the wait for the accumulator.
+// The BatchNorm input yb travels IN PLACE through the staging buffer: the group's leader, once its previous bulk store has been
+// read out of the buffer, TMA-loads the yb tile of the group's NEXT output tile into it (same box, same swizzle as the store);
+// a thread reads its 4-byte yb words (conflict-free: the 8 quads of a warp hit 8 different 16-byte chunks) and later overwrites
+// exactly those words with g.  (Version 2 fetched yb with 4-byte global loads, 8 lines per warp instruction: 256 L1 wavefronts
+// per warp and tile, 22-25 us per launch, job r2_09.)  The skip gradient still comes from global memory (17 of the 33 trunk
+// layers have one); shared memory has no room for a second tile per group.
+// Per element: g = acc + skip gradient, rounded to bf16 (the stored value); g' = g * act'(scale*yb + shift); sums g' and g'*yb
+// (the mean is taken out by dg_bn_bwd_dx_from_partials: sum g'(yb - mean) = sum g' yb - mean sum g', in double precision).
 template <int AM, int NB>
 __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int nb0,
                                                   int total_tiles, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, float* red_s, int grp,
-                                                  const float* __restrict__ cs) {
+                                                  const float* __restrict__ cs, uint64_t* bar_y_full) {
   constexpr int NJ = NB / 8;          // 8-column blocks of the N block
   constexpr int V = 4 * NJ;           // per-thread accumulators: [2 sums][NJ][2 columns]
   const uint32_t bar_id = 1u + (uint32_t)grp;
@@ -619,12 +631,20 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
   const bool leader = q == 0 && lane == 0;
   const bool has_res = P.bwd_res != nullptr;
   const uint32_t stg = stg_base + (uint32_t)grp * P.stg_bytes;
+  const uint32_t ybar = smem_u32(&bar_y_full[grp]);
   const int t0 = lane & 3, t1 = lane >> 2;
+  const int step_tiles = 2 * (int)gridDim.x;
   float S[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) S[i] = 0.f;
   int it = grp;
-  for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
+  const int tile_first = blockIdx.x + grp * (int)gridDim.x;
+  if (AM >= 0 && leader && tile_first < total_tiles) {      // the staging buffer starts out free: yb of the group's first tile
+    const int tw = tile_first % P.tiles_w, t2 = tile_first / P.tiles_w, th = t2 % P.tiles_h, n = t2 / P.tiles_h;
+    mbar_expect_tx(ybar, P.stg_bytes);
+    tma_load_4d(stg, &P.rmap, ybar, nb0, tw * 8, th * 16 * P.mt, n);
+  }
+  for (int tile = tile_first; tile < total_tiles; tile += step_tiles, it += 2) {
     const int b = it & ((1 << P.nbuf_shift) - 1);
     const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
     const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h, n = t2 / P.tiles_h;
@@ -634,20 +654,9 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
       const int r0 = q * 32 + hb * 16 + t1;          // accumulator rows r0 and r0 + 8 of sub-tile m
       const int ph0 = th * 16 * P.mt + m * 16 + (r0 >> 3);
       const bool va = ph0 < P.out_h && pw < P.out_w, vb = ph0 + 1 < P.out_h && pw < P.out_w;
-      uint32_t ya[NJ], yb[NJ], ra[NJ], rb[NJ];
+      uint32_t ra[NJ], rb[NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) { ya[j] = yb[j] = ra[j] = rb[j] = 0u; }
-      if (AM >= 0) {
-        const __nv_bfloat16* yp = P.bwd_y + ((long)n * P.bwd_y_sn + (long)ph0 * P.bwd_y_sh + (long)pw * P.bwd_y_sw + nb0 + 2 * t0);
-        if (va) {
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) ya[j] = ldg_u32(yp + 8 * j);
-        }
-        if (vb) {
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) yb[j] = ldg_u32(yp + P.bwd_y_sh + 8 * j);
-        }
-      }
+      for (int j = 0; j < NJ; ++j) { ra[j] = rb[j] = 0u; }
       if (has_res) {
         const __nv_bfloat16* rp = P.bwd_res + ((long)n * P.bwd_r_sn + (long)ph0 * P.bwd_r_sh + (long)pw * P.bwd_r_sw + nb0 + 2 * t0);
         if (va) {
@@ -660,19 +669,18 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
         }
       }
       if (mh == 0) {
-        // the lines of the other half's rows (two image rows further down) start travelling to L1 under the wait below
-        if (AM >= 0 && ph0 + 3 < P.out_h && pw < P.out_w) {
-          const __nv_bfloat16* yp2 = P.bwd_y + ((long)n * P.bwd_y_sn + (long)(ph0 + 2) * P.bwd_y_sh + (long)pw * P.bwd_y_sw + nb0 + 2 * t0);
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(yp2));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(yp2 + P.bwd_y_sh));
-        }
+        // the lines of the other half's rows (two image rows further down) start travelling to L1 under the waits below
         if (has_res && ph0 + 3 < P.out_h && pw < P.out_w) {
           const __nv_bfloat16* rp2 = P.bwd_res + ((long)n * P.bwd_r_sn + (long)(ph0 + 2) * P.bwd_r_sh + (long)pw * P.bwd_r_sw + nb0 + 2 * t0);
           asm volatile("prefetch.global.L1 [%0];" ::"l"(rp2));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(rp2 + P.bwd_r_sh));
         }
-        if (leader) { if (grp == 0) dbg_mark(P, 2, it >> 1, 0); tma_store_wait_read<0>(); }     // this group's previous store has left the staging buffer
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (leader && grp == 0) dbg_mark(P, 2, it >> 1, 0);
+        if (AM >= 0) mbar_wait(ybar, (uint32_t)(it >> 1) & 1u);      // yb tile landed in the staging buffer (the previous store has left it)
+        else {
+          if (leader) tma_store_wait_read<0>();     // this group's previous store has left the staging buffer
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
         mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
         tc_fence_after();
         if (leader && grp == 0) dbg_mark(P, 2, it >> 1, 1);
@@ -681,8 +689,24 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
       const uint32_t acc = tmem + ((uint32_t)(q * 32 + hb * 16) << 16) + (uint32_t)((b * P.mt + m) * NB);
       if constexpr (NJ == 8) tmem_ld_16x256b_x8(acc, v);
       else tmem_ld_16x256b_x4(acc, v);
-      tmem_ld_wait();
       const uint32_t offa = (uint32_t)(m * 128 + r0) * RB + 4u * (uint32_t)t0, offb = offa + 8u * RB;
+      uint32_t ya[NJ], yb[NJ];
+      if (AM >= 0) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          ya[j] = ld_shared_u32_nc(stg + swz(offa + 16u * j, mask));
+          yb[j] = ld_shared_u32_nc(stg + swz(offb + 16u * j, mask));
+        }
+      }
+      float2 scq[NJ], shq[NJ];
+      if (AM >= 0) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          scq[j] = *reinterpret_cast<const float2*>(cs + 8 * j + 2 * t0);
+          shq[j] = *reinterpret_cast<const float2*>(cs + 64 + 8 * j + 2 * t0);
+        }
+      }
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const uint32_t ga = va ? pack_bf16x2(__uint_as_float(v[4 * j]) + __uint_as_float(ra[j] << 16),
@@ -692,10 +716,7 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
         st_shared_u32(stg + swz(offa + 16u * j, mask), ga);
         st_shared_u32(stg + swz(offb + 16u * j, mask), gb);
         if (AM >= 0) {
-          const float2 sc = *reinterpret_cast<const float2*>(cs + 8 * j + 2 * t0);
-          const float2 sh = *reinterpret_cast<const float2*>(cs + 64 + 8 * j + 2 * t0);
-          const float2 mu = *reinterpret_cast<const float2*>(cs + 128 + 8 * j + 2 * t0);
-          const float scv[2] = {sc.x, sc.y}, shv[2] = {sh.x, sh.y}, muv[2] = {mu.x, mu.y};
+          const float scv[2] = {scq[j].x, scq[j].y}, shv[2] = {shq[j].x, shq[j].y};
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
             const uint32_t gw = rr ? gb : ga, yw = rr ? yb[j] : ya[j];
@@ -709,7 +730,7 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
               if (AM == 2) d = tt >= 0.f ? 1.f : P.bwd_alpha;
               const float gp = __fmul_rn(g, d);          // the same rounded product as the dx pass (bn_bwd_dx_part8_kernel)
               S[2 * j + e] += gp;
-              S[2 * NJ + 2 * j + e] = fmaf(gp, yv - muv[e], S[2 * NJ + 2 * j + e]);
+              S[2 * NJ + 2 * j + e] = fmaf(gp, yv, S[2 * NJ + 2 * j + e]);
             }
           }
         }
@@ -724,6 +745,14 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
       tma_store_4d(&P.omap, stg, nb0, tw * 8, th * 16 * P.mt, n);
       tma_store_commit();
       if (grp == 0) dbg_mark(P, 2, it >> 1, 2);
+      if (AM >= 0 && tile + step_tiles < total_tiles) {
+        // as soon as the store has READ the buffer, the yb tile of this group's next output tile is loaded into it
+        const int tn = tile + step_tiles;
+        const int tw2 = tn % P.tiles_w, t22 = tn / P.tiles_w, th2 = t22 % P.tiles_h, n2 = t22 / P.tiles_h;
+        tma_store_wait_read<0>();
+        mbar_expect_tx(ybar, P.stg_bytes);
+        tma_load_4d(stg, &P.rmap, ybar, nb0, tw2 * 8, th2 * 16 * P.mt, n2);
+      }
     }
   }
   if (leader) tma_store_wait<0>();
@@ -1069,15 +1098,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       for (int i = etid; i < P.nb; i += 256) bias_s[i] = __ldg(P.bias + nb0 + i);
     if (BWD && P.bwd_am >= 0)
       for (int i = etid; i < P.nb; i += 256) {
-        bnp_s[i] = __ldg(P.bwd_scale + nb0 + i); bnp_s[64 + i] = __ldg(P.bwd_shift + nb0 + i); bnp_s[128 + i] = __ldg(P.bwd_mean + nb0 + i);
+        bnp_s[i] = __ldg(P.bwd_scale + nb0 + i); bnp_s[64 + i] = __ldg(P.bwd_shift + nb0 + i);
       }
     asm volatile("bar.sync 3, 256;" ::: "memory");  // epilogue warps only
     const float* bs = P.bias ? bias_s : nullptr;
     if (BWD) {
       float* red = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off);
 #define DG_EPI_BWD(AM_) \
-  { if (P.nb == 64) epilogue_role_bwd<AM_, 64>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bar_acc_full, bar_acc_empty, red, grp, bnp_s); \
-    else epilogue_role_bwd<AM_, 32>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bar_acc_full, bar_acc_empty, red, grp, bnp_s); }
+  { if (P.nb == 64) epilogue_role_bwd<AM_, 64>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bar_acc_full, bar_acc_empty, red, grp, bnp_s, bar_res_full); \
+    else epilogue_role_bwd<AM_, 32>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bar_acc_full, bar_acc_empty, red, grp, bnp_s, bar_res_full); }
       switch (P.bwd_am) {
         case 0: DG_EPI_BWD(0) break;
         case 1: DG_EPI_BWD(1) break;
@@ -1575,6 +1604,11 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
       P.bwd_y = (const __nv_bfloat16*)yb->ptr + yb->coff;
       P.bwd_y_sw = yb->cpitch; P.bwd_y_sh = (long)yb->cpitch * yb->w; P.bwd_y_sn = (long)yb->cpitch * yb->w * yb->h;
       P.bwd_scale = b->scale; P.bwd_shift = b->shift; P.bwd_mean = b->mean;
+      // yb tiles are TMA-loaded into the staging buffer: same box and swizzle as the output store
+      uint64_t dims[4] = {(uint64_t)yb->c, (uint64_t)yb->w, (uint64_t)yb->h, (uint64_t)yb->n};
+      uint64_t strides[3] = {(uint64_t)yb->cpitch * 2, (uint64_t)yb->cpitch * 2 * yb->w, (uint64_t)yb->cpitch * 2 * yb->w * yb->h};
+      uint32_t box[4] = {(uint32_t)nb, 8u, (uint32_t)(16 * mt), 1u};
+      if (encode_map(ctx, &P.rmap, (char*)yb->ptr + (size_t)yb->coff * 2, 4, dims, strides, box, nb)) return 1;
     }
   }
   const uint32_t smem = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes + (ts ? 2u * stg_bytes : 0u) + 1024;

@@ -837,7 +837,7 @@ bn_bwd_fused8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict__
 }
 
 // BatchNorm backward, dx half, when the convolution that produced dy already reduced the two per-channel sums to per-CTA rows
-// (dg_umma_conv2d_dgrad_fused: row r = [sum g' | sum g'(x - mean)] over that CTA's pixels).  Every block first sums the rows in the
+// (dg_umma_conv2d_dgrad_fused: row r = [sum g' | sum g' x] over that CTA's pixels).  Every block first sums the rows in the
 // same fixed order in double precision (nrows x 2C floats out of L2, ~75 KB for the generator trunk) -- no finalize launch, no grid
 // barrier -- block 0 writes dgamma / dbeta, and then the blocks make ONE pass over dy and x.
 template <typename TG, typename TX, typename TO, int AM>
@@ -877,7 +877,7 @@ bn_bwd_dx_part8_kernel(const TG* __restrict__ dy, VView dv, const TX* __restrict
     for (int c = threadIdx.x; c < C; c += RT) {
       double s0 = 0, s1 = 0;
       for (int g2 = 0; g2 < G; ++g2) { s0 += gsum[(long)g2 * E + c]; s1 += gsum[(long)g2 * E + C + c]; }
-      s1 *= (double)invstd[c];
+      s1 = (s1 - (double)mean[c] * s0) * (double)invstd[c];      // rows hold sum g' x: sum g'(x - mean) = sum g' x - mean sum g'
       if (blockIdx.x == 0) {
         if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s0;
         if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s1;

@@ -127,7 +127,7 @@ int dg_umma_conv2d_dgrad(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgra
 /* Input gradient of a stride-1 convolution whose INPUT was the output a = act(BN_batch(yb)) (+ skip) of a training-mode
  * BatchNormalization (srgan.py:162-169, 246-250): besides dx = dL/da the launch (i) adds the gradient arriving over the skip
  * connection (`residual`, may be NULL; srgan.py:169,174 Add) and (ii) accumulates, from the bf16-rounded dx it stores, the two
- * per-channel sums of the BatchNorm backward pass -- sum g' and sum g'(yb - mean), g' = dx * act'(scale*yb + shift) -- into one
+ * per-channel sums of the BatchNorm backward pass -- sum g' and sum g' yb, g' = dx * act'(scale*yb + shift) -- into one
  * row [2][Cin] per CTA (`bn`, may be NULL).  dg_bn_bwd_dx_from_partials then finishes the BatchNorm backward pass in ONE read
  * of dx and yb.  Replaces tape.gradient's separate Add / BatchNorm-grad reductions (train_srgan.py:111). */
 typedef struct {
