@@ -418,7 +418,11 @@ def main():
         if os.environ.get("DG_BENCH_TRACE"):
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
     import torch.distributed as dist
+    numa = None
     if world > 1:
+        from denoise_gan_b200.parallel import pin_to_numa_node
+        numa = pin_to_numa_node(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))     # before any pinned allocation / worker thread
+        trace(f"cpu affinity: {numa}")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = args.workload
@@ -551,7 +555,9 @@ def main():
             "config": {"workload": W["label"], "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
                        "content_loss": "vgg19-synthetic" if W["vgg"] else "off (G+D step)",
                        "l2": "no flush needed: one step streams >10 GB of activations through a 126 MB L2",
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph,
+                       **({"exchange": "dg_comm_allreduce (NCCL through the C ABI), reverse-layer-order buckets launched from the backward pass"
+                           if getattr(model.comm, "_comm", None) is not None else "torch.distributed all_reduce", "cpu_affinity": numa} if world > 1 else {})},
             "step_tflops": images_s * gf_img / 1e3 / world,
             "step_frac_of_bf16_burst": images_s * gf_img / 1e3 / world / burst,
             "roofline": roofline_block(fam, wl, ms, sustained, peak_src),

@@ -92,9 +92,11 @@ SIGNATURES = {
     "dg_debug_conv_timeline": (None, [_P]),
     "dg_debug_conv_flags": (None, [_i]),
     "dg_debug_wgrad_timeline": (None, [_P]),
+    "dg_im2col": (_i, [_P, _T, _CP, _i, _i, _P, _P]),
     "dg_umma_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),
     "dg_umma_conv2d_wgrad": (_i, [_P, _T, _T, _P, _P, _CP, _i, _P, _sz, _P]),
     "dg_dwconv3x3_fwd": (_i, [_P, _T, _P, _P, _T, _P]),
+    "dg_dwconv3x3_fwd_act": (_i, [_P, _T, _P, _P, _i, _T, _P]),
     "dg_dwconv3x3_dgrad": (_i, [_P, _T, _P, _T, _P]),
     "dg_dwconv3x3_wgrad_workspace_bytes": (_sz, [_T]),
     "dg_dwconv3x3_wgrad": (_i, [_P, _T, _T, _P, _P, _i, _P, _sz, _P]),

@@ -43,6 +43,7 @@ struct WgradParams {
   CUtensorMap src[MAX_SRC];
   CUtensorMap dymap;
   int n_src, kc, kco, nb, n_groups, groups_per_cta, chunks, chunk0;
+  int zblocks;      // group blocks along gridDim.z; the rest of gridDim.z enumerates BLOCKS OF CHUNKS (chunk0 += chunks per block)
   int tiles_h, tiles_w, n_img;
   int src_h0[MAX_SRC], src_w0[MAX_SRC];
   uint32_t src_off[MAX_SRC], chunk_bytes[MAX_SRC], a_sbo[MAX_SRC], a_kstep[MAX_SRC];
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const int nb0 = blockIdx.y * P.nb;
-  const int g_begin = blockIdx.z * P.groups_per_cta;
+  const int cblk = (int)blockIdx.z / P.zblocks;              // block of input-channel chunks handled by this CTA
+  const int chunk0 = P.chunk0 + cblk * P.chunks;
+  const int dst_shift = cblk * P.chunks * P.kc;              // its rows of dW
+  const int g_begin = ((int)blockIdx.z % P.zblocks) * P.groups_per_cta;
   const int g_end = min(P.n_groups, g_begin + P.groups_per_cta);
   const bool do_bias = P.has_bias && blockIdx.z == 0;
   const int total_tiles = P.n_img * P.tiles_h * P.tiles_w;
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
         const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
         for (int s = 0; s < P.n_src; ++s)
           for (int c = 0; c < P.chunks; ++c)
-            tma_load_4d(sa + P.src_off[s] + (uint32_t)c * P.chunk_bytes[s], &P.src[s], full, (P.chunk0 + c) * P.kc,
+            tma_load_4d(sa + P.src_off[s] + (uint32_t)c * P.chunk_bytes[s], &P.src[s], full, (chunk0 + c) * P.kc,
                         w0 + P.src_w0[s], h0 + P.src_h0[s], n);
         for (int a = 0; a < P.nb / P.kco; ++a)
           tma_load_4d(sa + P.dy_off + (uint32_t)a * P.dy_atom_bytes, &P.dymap, full, nb0 + a * P.kco, w0, h0, n);
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
             const int mm = q * 32 + row;
             const int dst = row < 16 ? dlo : dhi;
             if (dst >= 0)
-              *reinterpret_cast<float4*>(part + (long)(dst + (mm & (P.kc - 1))) * P.cout_total + nb0 + cb + c4 * 4) =
+              *reinterpret_cast<float4*>(part + (long)(dst + dst_shift + (mm & (P.kc - 1))) * P.cout_total + nb0 + cb + c4 * 4) =
                   *reinterpret_cast<const float4*>(stg + row * ld + c4 * 4);
           }
           __syncwarp();
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
         tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_begin) * P.nb + c0), v);
         tmem_ld_wait();
         if (dst >= 0) {
-          float4* o = reinterpret_cast<float4*>(part + (long)(dst + r) * P.cout_total + nb0 + c0);
+          float4* o = reinterpret_cast<float4*>(part + (long)(dst + dst_shift + r) * P.cout_total + nb0 + c0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             o[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
@@ -361,7 +365,7 @@ struct Plan {
   Tap taps[MAX_TAPS];
   Lat lat[MAX_SRC];
   int n_taps, n_src;
-  int kc, kco, n_chunks, nb, gpc, zblocks, yblocks, splits, has_bias;
+  int kc, kco, n_chunks, nb, gpc, zblocks, yblocks, splits, has_bias, cblocks;
   int src_split;   // 1: one launch per source (big stride-2 layers whose four halo boxes do not fit one stage)
   uint32_t slack;
 };
@@ -455,7 +459,12 @@ int make_plan(const char* name, int sm_count, const dg_tensor* x, const dg_tenso
   pl->zblocks = (n_groups + pl->gpc - 1) / pl->gpc;
   pl->yblocks = cout / best_nb;
   const int tiles = dy->n * ((dy->h + 15) / 16) * ((dy->w + 7) / 8);
-  int splits = sm_count / (pl->zblocks * pl->yblocks);
+  // Chunk blocks in the grid: a layer with more input-channel chunks than one M = 128 operand holds used to run one LAUNCH per
+  // block of chunks (4 launches for 512 channels, 64 for the im2col form of pix2pix's 4x4x512 bottleneck layers, each re-dumping
+  // and re-reducing its partials); single-source layers now enumerate the blocks along gridDim.z of ONE launch.
+  pl->cblocks = 1;
+  if (pl->n_chunks > chunks_per_launch && pl->n_chunks % chunks_per_launch == 0 && !pl->src_split) pl->cblocks = pl->n_chunks / chunks_per_launch;
+  int splits = sm_count / (pl->zblocks * pl->yblocks * pl->cblocks);
   if (splits < 1) splits = 1;
   if (splits > tiles) splits = tiles;
   pl->splits = splits;
@@ -519,7 +528,7 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
   const int atoms_full = 128 / kc;
   const int chunks_per_launch = pl.n_chunks < atoms_full ? pl.n_chunks : atoms_full;
   bool first_launch = true;
-  for (int chunk0 = 0; chunk0 < pl.n_chunks; chunk0 += chunks_per_launch)
+  for (int chunk0 = 0; chunk0 < (pl.cblocks > 1 ? 1 : pl.n_chunks); chunk0 += chunks_per_launch)
   for (int ssel = pl.src_split ? 0 : -1; ssel < (pl.src_split ? pl.n_src : 0); ++ssel) {   // -1: all sources in one launch
     const int chunks = (pl.n_chunks - chunk0) < chunks_per_launch ? (pl.n_chunks - chunk0) : chunks_per_launch;
     WgradParams P;
@@ -617,6 +626,7 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     P.n_groups = ng;
     P.groups_per_cta = pl.gpc;
     const int zblocks = (ng + pl.gpc - 1) / pl.gpc;
+    P.zblocks = zblocks;
     // shared memory: stages + ones tile + slack for padding atoms
     const uint32_t ones_bytes = P.has_bias ? 128u * kc * 2 : 0u;
     const uint32_t slack = pl.slack;
@@ -633,7 +643,7 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
       P.dump_cw = (!dbg_direct && (size_t)4 * 32 * (cw + 4) * sizeof(float) <= (size_t)n_stages * P.stage_bytes) ? cw : 0;
     }
     const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;
-    dim3 grid(pl.splits, pl.yblocks, zblocks);
+    dim3 grid(pl.splits, pl.yblocks, zblocks * pl.cblocks);
     dg_pdl_launch(umma_wgrad_kernel, grid, dim3(WG_THREADS), smem, st, P);
     DG_CHECK_LAUNCH(name);
   }

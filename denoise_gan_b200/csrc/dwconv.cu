@@ -12,7 +12,7 @@ using namespace dgred;
 template <typename T, bool FLIP>
 __global__ void dw3x3_kernel(const T* __restrict__ x, int xp, int xo, const float* __restrict__ w,
                              const float* __restrict__ bias, T* __restrict__ y, int yp, int yo, int N, int H, int W,
-                             int C) {
+                             int C, int relu) {
   long total = (long)N * H * W * C;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -34,7 +34,7 @@ __global__ void dw3x3_kernel(const T* __restrict__ x, int xp, int xo, const floa
         acc += ld_f(x + (((n * H + hh) * W + ww) * xp + xo + c)) * w[wi * C + c];
       }
     }
-    st_f(y + (p * yp + yo + c), acc);
+    st_f(y + (p * yp + yo + c), relu ? fmaxf(acc, 0.f) : acc);
   }
 }
 
@@ -98,7 +98,7 @@ __device__ __forceinline__ void dw_load_window(const T* __restrict__ x, int xp, 
 template <typename T, bool FLIP>
 __global__ void __launch_bounds__(256)
 dw3x3_strip_kernel(const T* __restrict__ x, int xp, int xo, const float* __restrict__ w, const float* __restrict__ bias,
-                   T* __restrict__ y, int yp, int yo, int N, int H, int W, int C) {
+                   T* __restrict__ y, int yp, int yo, int N, int H, int W, int C, int relu) {
   const int CV = C >> 3, SW = W / DW_TW;
   const long total = (long)N * H * SW * CV;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -134,6 +134,12 @@ dw3x3_strip_kernel(const T* __restrict__ x, int xp, int xo, const float* __restr
           for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[j], wk[j], acc[t][j]);
         }
       }
+    if (relu) {
+#pragma unroll
+      for (int t = 0; t < DW_TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaxf(acc[t][j], 0.f);
+    }
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t) V8<T>::st(y + ((((long)n * H + h) * W + w0 + t) * yp + yo + c0), acc[t]);
   }
@@ -217,21 +223,35 @@ inline unsigned blocks_for(long total, int sm) {
 
 #define ST ((cudaStream_t)stream)
 
+static int dwconv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const float* w, const float* bias, const dg_tensor* y, int relu, void* stream);
+
 extern "C" int dg_dwconv3x3_fwd(dg_ctx* ctx, const dg_tensor* x, const float* w, const float* bias, const dg_tensor* y,
                                 void* stream) {
+  return dwconv_fwd_impl(ctx, x, w, bias, y, 0, stream);
+}
+
+// DepthwiseConv2D + bias + ReLU in one pass: the inference form of fsrgan.py:149-155 (DepthwiseConv2D -> BatchNormalization ->
+// ReLU) once the BatchNorm affine has been folded into the kernel and the bias (infer_video.py:146, training=False).
+extern "C" int dg_dwconv3x3_fwd_act(dg_ctx* ctx, const dg_tensor* x, const float* w, const float* bias, int act, const dg_tensor* y,
+                                    void* stream) {
+  DG_REQUIRE(act == DG_ACT_NONE || act == DG_ACT_RELU, "dg_dwconv3x3_fwd_act: activation must be none or relu");
+  return dwconv_fwd_impl(ctx, x, w, bias, y, act == DG_ACT_RELU ? 1 : 0, stream);
+}
+
+static int dwconv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const float* w, const float* bias, const dg_tensor* y, int relu, void* stream) {
   DG_REQUIRE(dg_valid(x) && dg_valid(y) && w, "dg_dwconv3x3_fwd: null argument");
   DG_REQUIRE(dg_same_shape(x, y) && x->dtype == y->dtype, "dg_dwconv3x3_fwd: shape/dtype mismatch");
   long total = dg_pixels(x) * x->c;
   if (dw_strip_ok(x, y)) {
     DG_DISPATCH_1(x->dtype, "dg_dwconv3x3_fwd",
                   dw3x3_strip_kernel<T, false><<<blocks_for(total / (8 * DW_TW), ctx->sm_count), 256, 0, ST>>>(
-                      (const T*)x->ptr, x->cpitch, x->coff, w, bias, (T*)y->ptr, y->cpitch, y->coff, x->n, x->h, x->w, x->c););
+                      (const T*)x->ptr, x->cpitch, x->coff, w, bias, (T*)y->ptr, y->cpitch, y->coff, x->n, x->h, x->w, x->c, relu););
     DG_CHECK_LAUNCH("dg_dwconv3x3_fwd");
     return 0;
   }
   DG_DISPATCH_1(x->dtype, "dg_dwconv3x3_fwd",
                 dw3x3_kernel<T, false><<<blocks_for(total, ctx->sm_count), 256, 0, ST>>>(
-                    (const T*)x->ptr, x->cpitch, x->coff, w, bias, (T*)y->ptr, y->cpitch, y->coff, x->n, x->h, x->w, x->c););
+                    (const T*)x->ptr, x->cpitch, x->coff, w, bias, (T*)y->ptr, y->cpitch, y->coff, x->n, x->h, x->w, x->c, relu););
   DG_CHECK_LAUNCH("dg_dwconv3x3_fwd");
   return 0;
 }
@@ -244,14 +264,14 @@ extern "C" int dg_dwconv3x3_dgrad(dg_ctx* ctx, const dg_tensor* dy, const float*
     DG_DISPATCH_1(dy->dtype, "dg_dwconv3x3_dgrad",
                   dw3x3_strip_kernel<T, true><<<blocks_for(total / (8 * DW_TW), ctx->sm_count), 256, 0, ST>>>(
                       (const T*)dy->ptr, dy->cpitch, dy->coff, w, nullptr, (T*)dx->ptr, dx->cpitch, dx->coff, dy->n, dy->h,
-                      dy->w, dy->c););
+                      dy->w, dy->c, 0););
     DG_CHECK_LAUNCH("dg_dwconv3x3_dgrad");
     return 0;
   }
   DG_DISPATCH_1(dy->dtype, "dg_dwconv3x3_dgrad",
                 dw3x3_kernel<T, true><<<blocks_for(total, ctx->sm_count), 256, 0, ST>>>(
                     (const T*)dy->ptr, dy->cpitch, dy->coff, w, nullptr, (T*)dx->ptr, dx->cpitch, dx->coff, dy->n, dy->h,
-                    dy->w, dy->c););
+                    dy->w, dy->c, 0););
   DG_CHECK_LAUNCH("dg_dwconv3x3_dgrad");
   return 0;
 }

@@ -742,6 +742,46 @@ extern "C" int dg_bn_bwd_dx_from_partials(dg_ctx* ctx, const dg_tensor* dy, cons
   return 0;
 }
 
+// ------------------------------------------------------------------ im2col for the small-spatial weight gradients
+// out[p][t*C + c] = x[n, ho*stride + r - pad_t, wo*stride + s - pad_l, c] (0 outside the image), p = (n*Ho + ho)*Wo + wo,
+// t = r*kw + s.  One 16-byte vector (8 channels) per thread.  pix2pix's bottleneck layers (pix2pix.py:147-166: 4x4 stride-2
+// convolutions on 16x16 ... 1x1 maps) have so few pixels per image that the halo-tile weight gradient spends its MMAs on
+// padding (a 16 x 8 tile per 2 x 2 image); gathered like this the weight gradient is ONE dense product over all N*Ho*Wo pixels.
+__global__ void __launch_bounds__(256) im2col8_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, int pitch, int off, int kh,
+                                                      int kw, int stride, int pad_t, int pad_l, int Ho, int Wo, long P,
+                                                      __nv_bfloat16* __restrict__ out) {
+  const int CV = C >> 3, taps = kh * kw;
+  const long total = P * taps * CV;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % CV);
+    const long r1 = i / CV;
+    const int t = (int)(r1 % taps);
+    const long p = r1 / taps;
+    const int wo = (int)(p % Wo);
+    const long r2 = p / Wo;
+    const int ho = (int)(r2 % Ho);
+    const long n = r2 / Ho;
+    const int hi = ho * stride + t / kw - pad_t, wi = wo * stride + t % kw - pad_l;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = *reinterpret_cast<const uint4*>(x + ((n * H + hi) * W + wi) * pitch + off + c8 * 8);
+    *reinterpret_cast<uint4*>(out + (p * taps + t) * C + c8 * 8) = v;
+  }
+}
+
+extern "C" int dg_im2col(dg_ctx* ctx, const dg_tensor* x, const dg_conv_params* p, int out_h, int out_w, void* out, void* stream) {
+  DG_REQUIRE(dg_valid(x) && p && out && out_h > 0 && out_w > 0, "dg_im2col: null argument");
+  DG_REQUIRE(x->dtype == DG_BF16 && x->c % 8 == 0 && x->cpitch % 8 == 0 && x->coff % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0 &&
+                 ((uintptr_t)out % 16) == 0, "dg_im2col: needs bf16 views with 8-channel (16-byte) alignment");
+  const long P = (long)x->n * out_h * out_w;
+  const long total = P * p->kh * p->kw * (x->c >> 3);
+  long blocks = (total + 255) / 256;
+  if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+  im2col8_kernel<<<(unsigned)blocks, 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->h, x->w, x->c, x->cpitch, x->coff, p->kh, p->kw, p->stride,
+                                                  p->pad_t, p->pad_l, out_h, out_w, P, (__nv_bfloat16*)out);
+  DG_CHECK_LAUNCH("dg_im2col");
+  return 0;
+}
+
 extern "C" int dg_act_bwd_from_output(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* y, int act, float act_alpha,
                                       const dg_tensor* dpre, void* stream) {
   DG_REQUIRE(dg_valid(dy) && dg_valid(y) && dg_valid(dpre), "dg_act_bwd_from_output: null argument");

@@ -119,7 +119,8 @@ class Engine:
         # per thread and tile) was SLOWER (7.70 vs 7.37 ms, job r2_05); the epilogue now reads the accumulator in mma-fragment layout
         self.fuse_dgrad_mode = int(os.environ.get("DG_DGRAD_BN_BWD", "2"))
         self.fuse_dgrad_bn_bwd = self.fuse_dgrad_mode != 0
-        self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"   # dg_bn_act_fwd_from_partials instead of finalize + apply
+        self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"
+        self.small_map_gemm = os.environ.get("DG_SMALL_MAP_GEMM", "1") != "0"      # weight gradients of <= 8x8 maps as one dense product (dg_im2col)   # dg_bn_act_fwd_from_partials instead of finalize + apply
         self._bwd_part: dict = {}       # (bn_act seq, tag) -> (partials, rows) left by the fused dgrad for that BatchNorm's backward
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
         # dgrad / BatchNorm chain of the backward pass (joined at the end of backward())
@@ -552,6 +553,23 @@ class Engine:
             assert accb == acc
         dbias = b.grad.data_ptr() if b is not None else None
         kh, kw, cin, cout = lin.kh, lin.kw, x.shape[3], dy.shape[3]
+        Nn, Ho, Wo = dy.shape[0], dy.shape[1], dy.shape[2]
+        if (self.use_umma_wgrad and self.small_map_gemm and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and kh * kw > 1 and
+                Ho * Wo <= 64 and (Nn * Ho * Wo) % 8 == 0 and cin % 16 == 0 and cout % 16 == 0):
+            # maps of at most 8x8 pixels (pix2pix.py:147-166): the halo-tile kernel would spend most of its 128-pixel tiles on
+            # padding; gather the taps once (dg_im2col) and run the weight gradient as a 1x1 layer over all N*Ho*Wo pixels
+            P_ = Nn * Ho * Wo
+            col = self.buf(("im2col", self._in_side, P_, kh * kw * cin), (1, P_ // 8, 8, kh * kw * cin), torch.bfloat16)
+            check(self.lib.dg_im2col(self.ctx, C.byref(tx), C.byref(lin), Ho, Wo, col.data_ptr(), self.st))
+            tcol = tensor(col)
+            tdy2 = _lib.DgTensor(dy.data_ptr(), _lib.DG_BF16, 1, P_ // 8, 8, cout, cout, 0)
+            one = DgConvParams(1, 1, 1, 0, 0, 0, 0.0)
+            nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tcol), C.byref(tdy2), C.byref(one))
+            if nbytes > 0:
+                ws = self.workspace(nbytes)
+                self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
+                    self.ctx, C.byref(tcol), C.byref(tdy2), w.grad.data_ptr(), dbias, C.byref(one), acc, ws.data_ptr(), nbytes, self.st)))
+                return
         if (self.use_umma_wgrad and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and
                 self._umma_ok(x, cin, cout, kh, kw, lin.stride, x.shape[1], x.shape[2])):
             nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))

@@ -159,3 +159,47 @@ def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     """Rank's contiguous slice of a global batch (dim 0)."""
     per = x.shape[0] // world
     return x[rank * per:(rank + 1) * per]
+
+
+def pin_to_numa_node(local_rank: int, world_local: int | None = None) -> str:
+    """Restricts the calling process to the CPU cores of the NUMA node its GPU hangs off (PCIe root), so that the pinned staging
+    buffers of the input feed and the launch thread stay node-local (round-1 N=8 runs showed the per-batch H2D copy going from
+    0.56 to 1.24 ms with eight unpinned ranks).  Falls back to an even split of the visible cores when the topology cannot be
+    read.  Returns a one-line description (bench.py reports it); never raises."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return "affinity unsupported"
+    node = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                want = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    want.update(range(int(a), int(b or a) + 1))
+            mine = [c for c in cores if c in want]
+            if mine:
+                os.sched_setaffinity(0, mine)
+                return f"NUMA node {node}: {len(mine)} cores"
+    except Exception:
+        pass
+    n = world_local or 1
+    if n > 1 and len(cores) >= n:
+        per = len(cores) // n
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        try:
+            os.sched_setaffinity(0, mine)
+            return f"even split: {len(mine)} cores (NUMA node unknown)"
+        except Exception:
+            pass
+    return "unpinned"

@@ -154,6 +154,11 @@ int dg_umma_conv2d_dgrad_supported(dg_ctx*, const dg_tensor* dy, const dg_tensor
 void dg_debug_conv_timeline(void* dev_buffer);
 void dg_debug_conv_flags(int flags);
 void dg_debug_wgrad_timeline(void* dev_buffer);   /* same for the weight-gradient kernel */ /* debug experiments only: results are WRONG when non-zero */
+/* Gather for the weight gradient of convolutions on very small maps (pix2pix.py:147-166, the 16x16 ... 1x1 bottleneck of the
+ * U-Net): out[p][t*Cin + c] = x[n, ho*stride + r - pad_t, wo*stride + s - pad_l, c], p = (n*Ho + ho)*Wo + wo (bf16, zero outside
+ * the image).  With x' = out viewed as [1, P/8, 8, taps*Cin] and dy' = dy viewed as [1, P/8, 8, Cout], dg_umma_conv2d_wgrad of a
+ * 1x1 convolution on (x', dy') IS the weight gradient [kh,kw,Cin,Cout] of the original layer (tape.gradient, train_pix2pix.py:62). */
+int dg_im2col(dg_ctx*, const dg_tensor* x, const dg_conv_params* p, int out_h, int out_w, void* out, void* stream);
 size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
 int dg_umma_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw_hwio, float* dbias,
                          const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
@@ -161,6 +166,9 @@ int dg_umma_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float
 
 /* ---- depthwise 3x3 s1 SAME (fsrgan.py:149-154) */
 int dg_dwconv3x3_fwd(dg_ctx*, const dg_tensor* x, const float* w, const float* bias, const dg_tensor* y, void* stream);
+/* DepthwiseConv2D + bias + ReLU in one pass: inference form of fsrgan.py:149-155 with the BatchNorm affine folded into the
+ * kernel and bias (infer_video.py:146 runs the model with training=False).  act: DG_ACT_NONE or DG_ACT_RELU. */
+int dg_dwconv3x3_fwd_act(dg_ctx*, const dg_tensor* x, const float* w_33c, const float* bias, int act, const dg_tensor* y, void* stream);
 int dg_dwconv3x3_dgrad(dg_ctx*, const dg_tensor* dy, const float* w, const dg_tensor* dx, void* stream);
 size_t dg_dwconv3x3_wgrad_workspace_bytes(const dg_tensor* x);
 int dg_dwconv3x3_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, int accumulate,

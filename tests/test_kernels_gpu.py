@@ -667,6 +667,57 @@ def test_umma_wgrad_k4s2_one_launch_per_source(N, H, cin, cout):
     assert relerr(dw.cpu(), w.grad) < 2e-2 and relerr(db.cpu(), b.grad) < 2e-2
 
 
+@pytest.mark.parametrize("case", [(8, 8, 128, 64, 4, 2, True), (32, 2, 512, 512, 4, 2, False), (32, 4, 256, 512, 4, 2, False), (8, 16, 64, 32, 4, 2, True),
+                                  (16, 4, 64, 48, 3, 1, True)])
+def test_small_map_wgrad_as_one_dense_product(L, case):
+    """Weight gradient of convolutions on maps of at most 8x8 pixels (pix2pix.py:147-166) as dg_im2col + the 1x1 form of
+    dg_umma_conv2d_wgrad (one launch: the blocks of input-channel chunks run along gridDim.z), against the halo-tile launch
+    and the float oracle; also with accumulate=1 (the generator runs twice per step, pix2pix.py:90)."""
+    N, H, cin, cout, k, s, bias = case
+    lib, ctx, st = L.load(), L.ctx(0), L.stream_ptr()
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    Ho = -(-H // s)
+    x0 = torch.randn((N, H, H, cin), generator=g).to(torch.bfloat16)
+    dy0 = torch.randn((N, Ho, Ho, cout), generator=g).to(torch.bfloat16)
+    xd, dyd = x0.cuda(), dy0.cuda()
+    cp = conv_params(L, k, k, s, H, H, "same")
+    tx, tdy = L.tensor(xd), L.tensor(dyd)
+    P_ = N * Ho * Ho
+    assert P_ % 8 == 0
+    col = torch.full((1, P_ // 8, 8, k * k * cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.dg_im2col(ctx, C.byref(tx), C.byref(cp), Ho, Ho, col.data_ptr(), st))
+    tcol = L.tensor(col)
+    tdy2 = L.DgTensor(dyd.data_ptr(), L.DG_BF16, 1, P_ // 8, 8, cout, cout, 0)
+    one = L.DgConvParams(1, 1, 1, 0, 0, 0, 0.0)
+    nbytes = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tcol), C.byref(tdy2), C.byref(one))
+    assert nbytes > 0, lib.dg_last_error().decode()
+    wk = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dw = torch.full((k, k, cin, cout), 3.0, device="cuda"); db = torch.full((cout,), 3.0, device="cuda")
+    L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tcol), C.byref(tdy2), dw.data_ptr(), db.data_ptr() if bias else None, C.byref(one), 0,
+                                     wk.data_ptr(), nbytes, st))
+    torch.cuda.synchronize()
+    assert not torch.isnan(col.float()).any()
+    w = torch.zeros((k, k, cin, cout), dtype=torch.float32, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    OT.conv2d(x0.float(), w, b, stride=s).backward(dy0.float())
+    assert relerr(dw.cpu(), w.grad) < 2e-2
+    if bias:
+        assert relerr(db.cpu(), b.grad) < 2e-2
+    # accumulate on top (second generator pass of the step)
+    L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tcol), C.byref(tdy2), dw.data_ptr(), db.data_ptr() if bias else None, C.byref(one), 1,
+                                     wk.data_ptr(), nbytes, st))
+    torch.cuda.synchronize()
+    assert relerr(dw.cpu(), 2.0 * w.grad) < 2e-2
+    # the halo-tile launch on the original tensors gives the same gradient
+    nb2 = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(cp))
+    if nb2 > 0:
+        wk2 = torch.empty(nb2, dtype=torch.uint8, device="cuda")
+        dw2 = torch.empty_like(dw)
+        L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(tdy), dw2.data_ptr(), None, C.byref(cp), 0, wk2.data_ptr(), nb2, st))
+        torch.cuda.synchronize()
+        assert relerr(dw2.cpu(), w.grad) < 2e-2
+
+
 # ---------------------------------------------------------------- staged (TMA-store) epilogue + fused BatchNorm statistics
 @pytest.mark.parametrize("case", [(3, 1, 64, 64, 2, 24, 20), (3, 1, 64, 64, 16, 96, 96), (3, 1, 32, 32, 3, 40, 24), (3, 2, 32, 32, 2, 48, 40),
                                   (3, 1, 32, 64, 2, 33, 19), (3, 2, 64, 64, 2, 48, 16), (3, 1, 64, 16, 1, 20, 12), (1, 1, 192, 32, 2, 16, 16)])
