@@ -31,13 +31,14 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src")
+    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src", "bn_folded")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
         self.bn_part = None     # (partials [blocks,2,C], blocks) when the producing conv reduced the BatchNorm statistics
         self.bn_done = None     # (name, scale, shift, mean, invstd) when the producing conv ALSO finalised them (last-CTA ticket)
         self.bn_applied = None  # (y_act, act, alpha, prelu, residual) when the producing conv ALSO applied BatchNorm + activation (+ skip)
+        self.bn_folded = None   # name of the inference-mode BatchNorm (+ activation) already folded into the producing convolution
         self.bn_src = None      # on the OUTPUT of a training-mode bn_act: (seq, x, scale, shift, mean, act code, alpha) -- lets the input-gradient
                                 # convolution that produces this Var's gradient also reduce the BatchNorm-backward sums (dg_umma_conv2d_dgrad_fused)
 
@@ -120,6 +121,8 @@ class Engine:
         self.fuse_dgrad_mode = int(os.environ.get("DG_DGRAD_BN_BWD", "2"))
         self.fuse_dgrad_bn_bwd = self.fuse_dgrad_mode != 0
         self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"
+        self.fold_bn_infer = os.environ.get("DG_FOLD_BN", "1") != "0"      # inference: BatchNorm folded into the producing conv / depthwise conv
+        self._folded: dict = {}
         self.small_map_gemm = os.environ.get("DG_SMALL_MAP_GEMM", "1") != "0"      # weight gradients of <= 8x8 maps as one dense product (dg_im2col)   # dg_bn_act_fwd_from_partials instead of finalize + apply
         self._bwd_part: dict = {}       # (bn_act seq, tag) -> (partials, rows) left by the fused dgrad for that BatchNorm's backward
         # weight gradients run on a side stream: they only feed the optimiser, so their prologue/tail overlaps the
@@ -394,6 +397,31 @@ class Engine:
         self._push([x], out, w.group, bwd, params=(w, b))
         return out
 
+    def _fold(self, w: Param, b: Param | None, pset, bname: str, eps: float, axis: int):
+        """BatchNorm(training=False) folded into the kernel and bias that feed it: y = scale*(conv(x,w)+b) + shift with
+        scale = gamma/sqrt(moving_var+eps), shift = beta - moving_mean*scale (srgan.py:155,163 at inference, infer_video.py:146).
+        Returns (fp32 kernel, fp32 bias); cached until the parameter sets change (ParamSet.version).  Host-side torch
+        arithmetic on a few thousand numbers, once per model load: plumbing, not on the per-frame path."""
+        key = (w.name, bname)
+        ver = (getattr(w.owner, "version", 0), getattr(pset, "version", 0))
+        ent = self._folded.get(key)
+        if ent is None or ent[0] != ver:
+            scale = pset[bname + "/gamma"].data / torch.sqrt(pset[bname + "/moving_variance"].data + float(eps))
+            shift = pset[bname + "/beta"].data - pset[bname + "/moving_mean"].data * scale
+            shape = [1, 1, 1, 1]
+            shape[axis] = -1
+            wf = (w.data * scale.view(shape)).contiguous()
+            bf = ((b.data * scale if b is not None else 0.0) + shift).contiguous()
+            if ent is None:
+                ent = [ver, wf, bf, None]
+            else:           # keep the addresses (they may be baked into a captured graph)
+                ent[1].copy_(wf); ent[2].copy_(bf); ent[0] = ver
+                if ent[3] is not None:
+                    kh, kw, cin, cout = w.shape
+                    check(self.lib.dg_umma_pack_weights_padded(self.ctx, ent[1].data_ptr(), ent[3].data_ptr(), kh, kw, cin, cout, cin, cout, 0, self.st))
+            self._folded[key] = ent
+        return ent
+
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
                out_dtype=None, bn: bool = False, post: dict | None = None) -> Var:
         """keras Conv2D (+bias, +activation epilogue).  `bn=True`: a training-mode BatchNormalization consumes the result
@@ -421,6 +449,23 @@ class Engine:
         bias = _lib.ptr(b.data) if b is not None else None
         flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
         bn_part = bn_done = bn_applied = None
+        fold = (isinstance(bn, tuple) and len(bn) == 4 and bn[0] == "fold")
+        if fold:
+            _, f_pset, f_name, f_eps = bn
+            bn = False
+            p_act = (post or {}).get("act")
+            if (self.fold_bn_infer and umma_f and act is None and (post or {}).get("prelu") is None and (post or {}).get("residual") is None
+                    and p_act in (None, "relu", "lrelu") and y.dtype == torch.bfloat16):
+                ent = self._fold(w, b, f_pset, f_name, f_eps, axis=3)
+                if ent[3] is None:
+                    ent[3] = torch.empty(kh * kw * cin * cout, dtype=torch.bfloat16, device=self.device)
+                    check(self.lib.dg_umma_pack_weights_padded(self.ctx, ent[1].data_ptr(), ent[3].data_ptr(), kh, kw, cin, cout, cin, cout, 0, self.st))
+                cpf = DgConvParams(kh, kw, stride, pt, pl, ACT[p_act], float((post or {}).get("alpha", 0.0)))
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+                    self.ctx, C.byref(tx), ent[3].data_ptr(), ent[2].data_ptr(), C.byref(ty), C.byref(cpf), None, self.st)))
+                out = Var(y, self._deps([x], w.group), seq)
+                out.bn_folded = f_name
+                return out          # inference only: no tape node
         if umma_f:
             pk = self._packed(w, 0)
             if bn and self.fuse_conv_bn_stats and act is None:
@@ -720,11 +765,21 @@ class Engine:
         self._push([x], out, w.group, bwd, params=(w, b))
         return out
 
-    def dwconv3x3(self, x: Var, w: Param, b: Param | None) -> Var:
-        """keras DepthwiseConv2D(3, padding='same')."""
+    def dwconv3x3(self, x: Var, w: Param, b: Param | None, bn=False, post: dict | None = None) -> Var:
+        """keras DepthwiseConv2D(3, padding='same').  `bn` / `post` as for conv2d: at inference the BatchNorm (+ ReLU) that follows
+        (fsrgan.py:149-155) is folded into the kernel, the bias and the store."""
         seq = self._next()
         y = self.buf((seq, "y"), x.shape, x.t.dtype)
         tx, ty = tensor(x.t), tensor(y)
+        if (isinstance(bn, tuple) and len(bn) == 4 and bn[0] == "fold" and self.fold_bn_infer and (post or {}).get("act") in (None, "relu")
+                and (post or {}).get("prelu") is None and (post or {}).get("residual") is None):
+            _, f_pset, f_name, f_eps = bn
+            ent = self._fold(w, b, f_pset, f_name, f_eps, axis=2)          # DepthwiseConv2D kernel [3,3,C,1]
+            check(self.lib.dg_dwconv3x3_fwd_act(self.ctx, C.byref(tx), ent[1].data_ptr(), ent[2].data_ptr(), ACT[(post or {}).get("act")],
+                                                C.byref(ty), self.st))
+            out = Var(y, self._deps([x], w.group), seq)
+            out.bn_folded = f_name
+            return out
         check(self.lib.dg_dwconv3x3_fwd(self.ctx, C.byref(tx), w.data.data_ptr(), _lib.ptr(b.data) if b is not None else None, C.byref(ty), self.st))
         out = Var(y, self._deps([x], w.group), seq)
 
@@ -752,6 +807,10 @@ class Engine:
     def bn_act(self, x: Var, pset, name: str, *, training: bool, momentum=0.99, eps=1e-3, act=None, alpha=0.0,
                prelu: Param | None = None, residual: Var | None = None, dropout_seed=None, dropout_offset=0,
                step_counter: torch.Tensor | None = None) -> Var:
+        if not training and getattr(x, "bn_folded", None) == name:
+            # inference: the producing convolution already applied this BatchNorm and its activation (folded kernel / bias / epilogue)
+            assert prelu is None and residual is None and dropout_seed is None
+            return x
         gamma, beta = pset[name + "/gamma"], pset[name + "/beta"]
         mm, mv = pset[name + "/moving_mean"], pset[name + "/moving_variance"]
         Cc = x.shape[3]
@@ -1128,4 +1187,5 @@ class Engine:
         check(self.lib.dg_adam_step(self.ctx, pset.theta.data_ptr(), pset.grad.data_ptr(), pset.m.data_ptr(), pset.v.data_ptr(),
                                     pset.numel, float(lr0), float(beta1), float(beta2), float(eps), int(decay_steps), float(decay_rate),
                                     float(grad_scale), pset.opt_state.data_ptr(), self.st))
+        pset.version = getattr(pset, "version", 0) + 1
         pset.repack(self.lib, self.ctx, self.st)

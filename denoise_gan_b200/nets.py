@@ -24,7 +24,10 @@ class _Net:
     def _bn(self, name, training, momentum=0.99, eps=1e-3):
         """`bn=` argument of Engine.conv2d for a conv whose output feeds BatchNormalization `name` (same momentum / eps as
         the bn_act call that follows): the conv epilogue produces the batch statistics and its last CTA finalises them."""
-        return (self.p, name, momentum, eps) if training else False
+        if training:
+            return (self.p, name, momentum, eps)
+        # inference (infer_video.py:146, training=False): BatchNorm is an affine map of constants -> folded into the conv
+        return ("fold", self.p, name, eps)
 
 
 class SRGANGenerator(_Net):
@@ -121,7 +124,8 @@ class FastSRGANGenerator(_Net):
                 t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"], bn=self._bn(f"g/b{i}/expand_bn", training, momentum=0.999),
                              post=dict(act="relu"))
                 t = E.bn_act(t, p, f"g/b{i}/expand_bn", training=training, momentum=0.999, act="relu")
-            t = E.dwconv3x3(t, p[f"g/b{i}/dw/kernel"], p[f"g/b{i}/dw/bias"])
+            t = E.dwconv3x3(t, p[f"g/b{i}/dw/kernel"], p[f"g/b{i}/dw/bias"], bn=self._bn(f"g/b{i}/dw_bn", training, momentum=0.999),
+                            post=dict(act="relu"))
             t = E.bn_act(t, p, f"g/b{i}/dw_bn", training=training, momentum=0.999, act="relu")
             t = E.conv2d(t, p[f"g/b{i}/project/kernel"], p[f"g/b{i}/project/bias"], bn=self._bn(f"g/b{i}/project_bn", training, momentum=0.999),
                          post=dict(residual=r))

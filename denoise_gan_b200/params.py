@@ -78,6 +78,7 @@ class ParamSet:
 
     def load(self, tensors):
         """Copies host (or device) tensors by name into the arenas."""
+        self.version = getattr(self, "version", 0) + 1      # derived copies (BatchNorm-folded inference kernels) are rebuilt
         for name, t in tensors.items():
             p = self[name]
             assert tuple(t.shape) == p.shape, f"{name}: shape {tuple(t.shape)} != {p.shape}"

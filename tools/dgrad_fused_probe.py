@@ -40,7 +40,8 @@ def run(mode, flags):
     lib.dg_debug_conv_flags(0)
 
 
-for mode, flags in [("plain", 0), ("res", 0), ("bn", 0), ("res+bn", 0)]:
+MODES = [(m, 0) for m in os.environ.get("DG_PROBE_MODES", "plain,res,bn,res+bn").split(",")]
+for mode, flags in MODES:
     for _ in range(3):
         run(mode, flags)
     torch.cuda.synchronize()
