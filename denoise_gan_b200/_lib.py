@@ -87,6 +87,8 @@ SIGNATURES = {
     "dg_pad_channels": (_i, [_P, _T, _T, _P]),
     "dg_umma_pack_weights_padded": (_i, [_P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
     "dg_unpad_weight_grad": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "dg_umma_pack_weights_seg": (_i, [_P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "dg_unpad_weight_grad_seg": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
     "dg_frame_to_float": (_i, [_P, _P, _i, _i, _i, _i, _f, _f, _T, _P]),
     "dg_float_to_frame": (_i, [_P, _T, _f, _f, _i, _i, _P, _i, _i, _P]),
     "dg_debug_conv_timeline": (None, [_P]),
@@ -113,6 +115,7 @@ SIGNATURES = {
     "dg_copy": (_i, [_P, _T, _T, _i, _P]),
     "dg_maxpool2x2_fwd": (_i, [_P, _T, _T, _P]),
     "dg_maxpool2x2_bwd": (_i, [_P, _T, _T, _T, _T, _P]),
+    "dg_maxpool2x2_bwd_relu": (_i, [_P, _T, _T, _T, _T, _P]),
     "dg_upsample2x_relu_fwd": (_i, [_P, _T, _T, _P]),
     "dg_upsample2x_relu_bwd": (_i, [_P, _T, _T, _T, _P]),
     "dg_vgg_preprocess_fwd": (_i, [_P, _T, _T, _P]),

@@ -1146,8 +1146,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
 // mode 0 (forward): dst[((t*nch+kc)*Cout + o)*KC + j] = w[t][kc*KC + j][o]      (KC chunks over Cin)
 // mode 1 (dgrad)  : dst[((t*nch+kc)*Cin  + c)*KC + j] = w[t][c][kc*KC + j]      (KC chunks over Cout)
 // cin/cout are the PACKED (possibly zero-padded) dims, cin_s/cout_s the dims of the fp32 source.
+// Physically padded activations (dg_umma_pack_weights_seg): the packed input-channel axis may consist of TWO zero-padded
+// segments (a U-Net concat of two padded tensors, autoencoder.py:135): channels [0, seg_phys) hold seg_log source channels,
+// the rest holds the remaining cin_s - seg_log.  seg_phys == 0: one segment.  Returns the source channel or -1 (zero).
+__device__ __forceinline__ int seg_src_channel(int ci, int cin_s, int seg_log, int seg_phys) {
+  if (seg_phys == 0) return ci < cin_s ? ci : -1;
+  if (ci < seg_phys) return ci < seg_log ? ci : -1;
+  const int r = ci - seg_phys;
+  return r < cin_s - seg_log ? seg_log + r : -1;
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int taps, int cin,
-                                    int cout, int kc, int mode, int cin_s, int cout_s) {
+                                    int cout, int kc, int mode, int cin_s, int cout_s, int seg_log, int seg_phys) {
   long total = (long)taps * cin * cout;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int rows = mode == 0 ? cout : cin;  // rows of a block
@@ -1160,8 +1170,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     int ch = (int)(r2 % nch);
     int t = (int)(r2 / nch);
     int k = ch * kc + j;
-    const int ci = mode == 0 ? k : row, co = mode == 0 ? row : k;
-    float v = (ci < cin_s && co < cout_s) ? w[((long)t * cin_s + ci) * cout_s + co] : 0.f;
+    const int ci = seg_src_channel(mode == 0 ? k : row, cin_s, seg_log, seg_phys), co = mode == 0 ? row : k;
+    float v = (ci >= 0 && co < cout_s) ? w[((long)t * cin_s + ci) * cout_s + co] : 0.f;
     dst[i] = __float2bfloat16(v);
   }
 }
@@ -1173,7 +1183,7 @@ struct PackEntry {   // mirrored by denoise_gan_b200/params.py (48 bytes)
   const float* src;
   __nv_bfloat16* dst;
   int taps, cin, cout, kc, mode, cin_src;   // cin/cout: packed (padded) dims; *_src: dims of the fp32 source (0 = same)
-  int cout_src, pad1;
+  int cout_src, seg;   // seg: seg_log | seg_phys << 16 (two-segment input-channel axis, see seg_src_channel), 0 = one segment
 };
 
 // all kernels of a network in ONE launch: blockIdx.y selects the table entry
@@ -1186,9 +1196,10 @@ __global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
     unsigned row = r1 % rows, r2 = r1 / rows;
     unsigned ch = r2 % nch, t = r2 / nch;
     unsigned k = ch * E.kc + j;
-    const unsigned ci = E.mode == 0 ? k : row, co = E.mode == 0 ? row : k;
+    const unsigned co = E.mode == 0 ? row : k;
     const unsigned cis = E.cin_src ? E.cin_src : E.cin, cos = E.cout_src ? E.cout_src : E.cout;
-    float v = (ci < cis && co < cos) ? E.src[((long)t * cis + ci) * cos + co] : 0.f;
+    const int ci = seg_src_channel((int)(E.mode == 0 ? k : row), (int)cis, E.seg & 0xffff, E.seg >> 16);
+    float v = (ci >= 0 && co < cos) ? E.src[((long)t * cis + ci) * cos + co] : 0.f;
     E.dst[i] = __float2bfloat16(v);
   }
 }
@@ -1669,8 +1680,26 @@ extern "C" int dg_umma_pack_weights(dg_ctx* ctx, const float* w, void* packed, i
   long total = (long)kh * kw * cin * cout;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin, cout, kc, mode, cin, cout);
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin, cout, kc, mode, cin, cout, 0, 0);
   DG_CHECK_LAUNCH("dg_umma_pack_weights");
+  return 0;
+}
+
+extern "C" int dg_umma_pack_weights_seg(dg_ctx* ctx, const float* w, void* packed, int kh, int kw, int cin, int cout, int cin_pad,
+                                        int cout_pad, int seg_log, int seg_phys, int mode, void* stream) {
+  DG_REQUIRE(w && packed, "dg_umma_pack_weights_seg: null argument");
+  DG_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0 && cin <= cin_pad && cout <= cout_pad && (mode == 0 || mode == 1),
+             "dg_umma_pack_weights_seg: padded channels must be multiples of 16");
+  DG_REQUIRE(seg_phys == 0 || (seg_log >= 0 && seg_log <= seg_phys && seg_log <= cin && seg_phys % 16 == 0 && seg_phys <= cin_pad &&
+                               cin - seg_log <= cin_pad - seg_phys && cin_pad < 65536),
+             "dg_umma_pack_weights_seg: bad channel segments (%d of %d, then %d of %d)", seg_log, seg_phys, cin - seg_log, cin_pad - seg_phys);
+  int kc = kc_for(mode == 0 ? cin_pad : cout_pad);
+  long total = (long)kh * kw * cin_pad * cout_pad;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin_pad, cout_pad, kc, mode,
+                                                                          cin, cout, seg_log, seg_phys);
+  DG_CHECK_LAUNCH("dg_umma_pack_weights_seg");
   return 0;
 }
 
@@ -1684,7 +1713,7 @@ extern "C" int dg_umma_pack_weights_padded(dg_ctx* ctx, const float* w, void* pa
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, kh * kw, cin_pad, cout_pad, kc, mode,
-                                                                          cin, cout);
+                                                                          cin, cout, 0, 0);
   DG_CHECK_LAUNCH("dg_umma_pack_weights_padded");
   return 0;
 }

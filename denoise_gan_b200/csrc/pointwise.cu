@@ -355,7 +355,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, View xv, T* __restri
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, View dv, const T* __restrict__ x, View xv,
                                    const T* __restrict__ y, View yv, T* __restrict__ dx, View ov, int N, int Ho, int Wo,
-                                   int C) {
+                                   int C, int relu) {
   long total = (long)N * Ho * Wo * C;
   const int W = Wo * 2;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -374,7 +374,7 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, View dv, const T* _
     for (int k = 0; k < 4; ++k) {
       float v = ld_f(x + (pos[k] * xv.pitch + xv.off + c));
       bool hit = !done && v == m;
-      st_f(dx + (pos[k] * ov.pitch + ov.off + c), hit ? g : 0.f);
+      st_f(dx + (pos[k] * ov.pitch + ov.off + c), (hit && !(relu && v <= 0.f)) ? g : 0.f);
       done = done || hit;
     }
   }
@@ -929,6 +929,14 @@ extern "C" int dg_maxpool2x2_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_tenso
   DG_REQUIRE(x->h == 2 * y->h && x->w == 2 * y->w && x->c == y->c && x->n == y->n && x->dtype == y->dtype,
              "dg_maxpool2x2_fwd: shape mismatch (even sizes only)");
   long total = dg_pixels(y) * y->c;
+  if (dgvec::vec_ok(x) && dgvec::vec_ok(y)) {
+    const dgvec::VView vx{x->cpitch, x->coff}, vy{y->cpitch, y->coff};
+    DG_DISPATCH_1(x->dtype, "dg_maxpool2x2_fwd",
+                  dgvec::maxpool_fwd8_kernel<T><<<dgvec::ew8_blocks(total / 8, ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const T*)x->ptr, vx, (T*)y->ptr, vy, y->n, y->h, y->w, y->c););
+    DG_CHECK_LAUNCH("dg_maxpool2x2_fwd");
+    return 0;
+  }
   DG_DISPATCH_1(x->dtype, "dg_maxpool2x2_fwd",
                 maxpool_fwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
                     (const T*)x->ptr, view_of(x), (T*)y->ptr, view_of(y), y->n, y->h, y->w, y->c););
@@ -936,19 +944,36 @@ extern "C" int dg_maxpool2x2_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_tenso
   return 0;
 }
 
-extern "C" int dg_maxpool2x2_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y,
-                                 const dg_tensor* dx, void* stream) {
-  DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(y) && dg_valid(dx), "dg_maxpool2x2_bwd: null argument");
-  DG_REQUIRE(dg_same_shape(dy, y) && dg_same_shape(dx, x) && x->h == 2 * y->h && x->w == 2 * y->w,
-             "dg_maxpool2x2_bwd: shape mismatch");
-  DG_REQUIRE(dy->dtype == x->dtype && y->dtype == x->dtype && dx->dtype == x->dtype, "dg_maxpool2x2_bwd: dtype mismatch");
+static int maxpool_bwd_impl(const char* name, dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y, const dg_tensor* dx,
+                            int relu, void* stream) {
+  DG_REQUIRE(dg_valid(dy) && dg_valid(x) && dg_valid(y) && dg_valid(dx), "%s: null argument", name);
+  DG_REQUIRE(dg_same_shape(dy, y) && dg_same_shape(dx, x) && x->h == 2 * y->h && x->w == 2 * y->w, "%s: shape mismatch", name);
+  DG_REQUIRE(dy->dtype == x->dtype && y->dtype == x->dtype && dx->dtype == x->dtype, "%s: dtype mismatch", name);
   long total = dg_pixels(y) * y->c;
-  DG_DISPATCH_1(x->dtype, "dg_maxpool2x2_bwd",
+  if (dgvec::vec_ok(dy) && dgvec::vec_ok(x) && dgvec::vec_ok(y) && dgvec::vec_ok(dx)) {
+    const dgvec::VView vd{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vy{y->cpitch, y->coff}, vo{dx->cpitch, dx->coff};
+    DG_DISPATCH_1(x->dtype, name,
+                  dgvec::maxpool_bwd8_kernel<T><<<dgvec::ew8_blocks(total / 8, ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const T*)dy->ptr, vd, (const T*)x->ptr, vx, (const T*)y->ptr, vy, (T*)dx->ptr, vo, y->n, y->h, y->w, y->c, relu););
+    DG_CHECK_LAUNCH(name);
+    return 0;
+  }
+  DG_DISPATCH_1(x->dtype, name,
                 maxpool_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
                     (const T*)dy->ptr, view_of(dy), (const T*)x->ptr, view_of(x), (const T*)y->ptr, view_of(y),
-                    (T*)dx->ptr, view_of(dx), y->n, y->h, y->w, y->c););
-  DG_CHECK_LAUNCH("dg_maxpool2x2_bwd");
+                    (T*)dx->ptr, view_of(dx), y->n, y->h, y->w, y->c, relu););
+  DG_CHECK_LAUNCH(name);
   return 0;
+}
+
+extern "C" int dg_maxpool2x2_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y,
+                                 const dg_tensor* dx, void* stream) {
+  return maxpool_bwd_impl("dg_maxpool2x2_bwd", ctx, dy, x, y, dx, 0, stream);
+}
+
+extern "C" int dg_maxpool2x2_bwd_relu(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y,
+                                      const dg_tensor* dx, void* stream) {
+  return maxpool_bwd_impl("dg_maxpool2x2_bwd_relu", ctx, dy, x, y, dx, 1, stream);
 }
 
 extern "C" int dg_upsample2x_relu_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y, void* stream) {
@@ -956,6 +981,14 @@ extern "C" int dg_upsample2x_relu_fwd(dg_ctx* ctx, const dg_tensor* x, const dg_
   DG_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && x->c == y->c && x->n == y->n && x->dtype == y->dtype,
              "dg_upsample2x_relu_fwd: shape mismatch");
   long total = dg_pixels(y) * y->c;
+  if (dgvec::vec_ok(x) && dgvec::vec_ok(y)) {
+    const dgvec::VView vx{x->cpitch, x->coff}, vy{y->cpitch, y->coff};
+    DG_DISPATCH_1(x->dtype, "dg_upsample2x_relu_fwd",
+                  dgvec::upsample_relu_fwd8_kernel<T><<<dgvec::ew8_blocks(total / 32, ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const T*)x->ptr, vx, (T*)y->ptr, vy, x->n, x->h, x->w, x->c););
+    DG_CHECK_LAUNCH("dg_upsample2x_relu_fwd");
+    return 0;
+  }
   DG_DISPATCH_1(x->dtype, "dg_upsample2x_relu_fwd",
                 upsample_relu_fwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
                     (const T*)x->ptr, view_of(x), (T*)y->ptr, view_of(y), x->n, x->h, x->w, x->c););
@@ -969,6 +1002,14 @@ extern "C" int dg_upsample2x_relu_bwd(dg_ctx* ctx, const dg_tensor* dy, const dg
   DG_REQUIRE(dy->h == 2 * x->h && dy->w == 2 * x->w && dy->c == x->c && dg_same_shape(dx, x) &&
                  dy->dtype == x->dtype && dx->dtype == x->dtype, "dg_upsample2x_relu_bwd: shape mismatch");
   long total = dg_pixels(x) * x->c;
+  if (dgvec::vec_ok(dy) && dgvec::vec_ok(x) && dgvec::vec_ok(dx)) {
+    const dgvec::VView vd{dy->cpitch, dy->coff}, vx{x->cpitch, x->coff}, vo{dx->cpitch, dx->coff};
+    DG_DISPATCH_1(x->dtype, "dg_upsample2x_relu_bwd",
+                  dgvec::upsample_relu_bwd8_kernel<T><<<dgvec::ew8_blocks(total / 8, ctx->sm_count), dgvec::VT, 0, ST>>>(
+                      (const T*)dy->ptr, vd, (const T*)x->ptr, vx, (T*)dx->ptr, vo, x->n, x->h, x->w, x->c););
+    DG_CHECK_LAUNCH("dg_upsample2x_relu_bwd");
+    return 0;
+  }
   DG_DISPATCH_1(x->dtype, "dg_upsample2x_relu_bwd",
                 upsample_relu_bwd_kernel<T><<<ew_blocks(total, ctx->sm_count), 256, 0, ST>>>(
                     (const T*)dy->ptr, view_of(dy), (const T*)x->ptr, view_of(x), (T*)dx->ptr, view_of(dx), x->n, x->h,
@@ -1053,16 +1094,19 @@ pad_channels16_kernel(const TI* __restrict__ src, View sv, __nv_bfloat16* __rest
 }
 
 // dst[t][c][o] (+)= src[t][c][o] for c < cin, o < cout  (src rows are cin_p x cout_p);  dbias likewise
+// Two-segment input-channel axis (physically padded U-Net concat, see dg_umma_pack_weights_seg): source channel c lives at
+// physical row c (c < seg_log) or seg_phys + (c - seg_log); seg_phys == 0: one segment.
 __global__ void unpad_weight_grad_kernel(const float* __restrict__ src, const float* __restrict__ bsrc, float* __restrict__ dst,
                                          float* __restrict__ bdst, int taps, int cin, int cout, int cin_p, int cout_p,
-                                         int accumulate) {
+                                         int accumulate, int seg_log, int seg_phys) {
   const long n = (long)taps * cin * cout;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n + (bdst ? cout : 0); i += (long)gridDim.x * blockDim.x) {
     if (i < n) {
       const int o = (int)(i % cout);
       const long r = i / cout;
       const int c = (int)(r % cin), t = (int)(r / cin);
-      const float v = src[((long)t * cin_p + c) * cout_p + o];
+      const int cp = (seg_phys == 0 || c < seg_log) ? c : seg_phys + (c - seg_log);
+      const float v = src[((long)t * cin_p + cp) * cout_p + o];
       dst[i] = accumulate ? dst[i] + v : v;
     } else {
       const int o = (int)(i - n);
@@ -1094,7 +1138,20 @@ extern "C" int dg_unpad_weight_grad(dg_ctx* ctx, const float* dw_padded, const f
   DG_REQUIRE(dw_padded && dw && cin <= cin_pad && cout <= cout_pad && (!dbias || dbias_padded), "dg_unpad_weight_grad: bad argument");
   const long n = (long)kh * kw * cin * cout + (dbias ? cout : 0);
   unpad_weight_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(dw_padded, dbias_padded, dw, dbias, kh * kw, cin, cout,
-                                                                        cin_pad, cout_pad, accumulate);
+                                                                        cin_pad, cout_pad, accumulate, 0, 0);
   DG_CHECK_LAUNCH("dg_unpad_weight_grad");
+  return 0;
+}
+
+extern "C" int dg_unpad_weight_grad_seg(dg_ctx* ctx, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh,
+                                        int kw, int cin, int cout, int cin_pad, int cout_pad, int seg_log, int seg_phys, int accumulate,
+                                        void* stream) {
+  DG_REQUIRE(dw_padded && dw && cin <= cin_pad && cout <= cout_pad && (!dbias || dbias_padded), "dg_unpad_weight_grad_seg: bad argument");
+  DG_REQUIRE(seg_phys == 0 || (seg_log >= 0 && seg_log <= seg_phys && seg_log <= cin && seg_phys <= cin_pad &&
+                               cin - seg_log <= cin_pad - seg_phys), "dg_unpad_weight_grad_seg: bad channel segments");
+  const long n = (long)kh * kw * cin * cout + (dbias ? cout : 0);
+  unpad_weight_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(dw_padded, dbias_padded, dw, dbias, kh * kw, cin, cout,
+                                                                        cin_pad, cout_pad, accumulate, seg_log, seg_phys);
+  DG_CHECK_LAUNCH("dg_unpad_weight_grad_seg");
   return 0;
 }

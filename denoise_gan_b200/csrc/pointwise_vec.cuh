@@ -1208,6 +1208,121 @@ ew8_kernel(const TA* __restrict__ a, VView av, const TA* __restrict__ b, VView b
   }
 }
 
+// ---------------------------------------------------------------- MaxPool2D(2,2) / UpSampling2D(2)+ReLU, 8 channels per thread
+// (autoencoder.py:110,113-136; every activation of the bf16 path has a channel count that is a multiple of 16, the odd
+// widths 44/56/76/100/152/84 being physically zero-padded).  One thread = one pixel of the SMALL map x 8 channels: the four
+// pixels of its 2x2 window are four independent 16-byte accesses.
+template <typename T>
+__global__ void __launch_bounds__(VT)
+maxpool_fwd8_kernel(const T* __restrict__ x, VView xv, T* __restrict__ y, VView yv, int N, int Ho, int Wo, int C) {
+  const uint32_t CV = (uint32_t)C >> 3, total = (uint32_t)N * Ho * Wo * CV, W = 2u * Wo;
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t q = i / CV, c0 = (i - q * CV) * 8u;
+    const uint32_t wo = q % Wo, t = q / Wo, ho = t % Ho, n = t / Ho;
+    const uint32_t p00 = (n * 2u * Ho + 2u * ho) * W + 2u * wo;
+    typename V8<T>::raw r[4];
+    r[0] = V8<T>::ldraw(x + ((size_t)p00 * xv.pitch + xv.off + c0));
+    r[1] = V8<T>::ldraw(x + ((size_t)(p00 + 1) * xv.pitch + xv.off + c0));
+    r[2] = V8<T>::ldraw(x + ((size_t)(p00 + W) * xv.pitch + xv.off + c0));
+    r[3] = V8<T>::ldraw(x + ((size_t)(p00 + W + 1) * xv.pitch + xv.off + c0));
+    float m[8], v[8];
+    V8<T>::cvt(r[0], m);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      V8<T>::cvt(r[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+    V8<T>::st(y + ((size_t)q * yv.pitch + yv.off + c0), m);
+  }
+}
+
+// dx = dy routed to the first window position (row-major) whose value equals the max
+template <typename T>
+__global__ void __launch_bounds__(VT)
+maxpool_bwd8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ x, VView xv, const T* __restrict__ y, VView yv,
+                    T* __restrict__ dx, VView ov, int N, int Ho, int Wo, int C, int relu) {
+  const uint32_t CV = (uint32_t)C >> 3, total = (uint32_t)N * Ho * Wo * CV, W = 2u * Wo;
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t q = i / CV, c0 = (i - q * CV) * 8u;
+    const uint32_t wo = q % Wo, t = q / Wo, ho = t % Ho, n = t / Ho;
+    const uint32_t p00 = (n * 2u * Ho + 2u * ho) * W + 2u * wo;
+    const uint32_t pos[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    typename V8<T>::raw r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = V8<T>::ldraw(x + ((size_t)pos[k] * xv.pitch + xv.off + c0));
+    float m[8], g[8];
+    V8<T>::ld(y + ((size_t)q * yv.pitch + yv.off + c0), m);
+    V8<T>::ld(dy + ((size_t)q * dv.pitch + dv.off + c0), g);
+    bool done[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) done[j] = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8], o[8];
+      V8<T>::cvt(r[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool hit = !done[j] && v[j] == m[j];
+        o[j] = (hit && !(relu && v[j] <= 0.f)) ? g[j] : 0.f;     // relu: x is the output of a ReLU whose mask is applied here
+        done[j] = done[j] || hit;
+      }
+      V8<T>::st(dx + ((size_t)pos[k] * ov.pitch + ov.off + c0), o);
+    }
+  }
+}
+
+// y[n,2h+i,2w+j,c] = relu(x[n,h,w,c]); y may be a channel slice of the concat buffer (autoencoder.py:135)
+template <typename T>
+__global__ void __launch_bounds__(VT)
+upsample_relu_fwd8_kernel(const T* __restrict__ x, VView xv, T* __restrict__ y, VView yv, int N, int H, int W, int C) {
+  const uint32_t CV = (uint32_t)C >> 3, total = (uint32_t)N * H * W * CV, W2 = 2u * W;
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV, c0 = (i - p * CV) * 8u;
+    const uint32_t w = p % W, t = p / W, h = t % H, n = t / H;
+    float v[8];
+    V8<T>::ld(x + ((size_t)p * xv.pitch + xv.off + c0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    const uint32_t q00 = (n * 2u * H + 2u * h) * W2 + 2u * w;
+    V8<T>::st(y + ((size_t)q00 * yv.pitch + yv.off + c0), v);
+    V8<T>::st(y + ((size_t)(q00 + 1) * yv.pitch + yv.off + c0), v);
+    V8<T>::st(y + ((size_t)(q00 + W2) * yv.pitch + yv.off + c0), v);
+    V8<T>::st(y + ((size_t)(q00 + W2 + 1) * yv.pitch + yv.off + c0), v);
+  }
+}
+
+// dx[n,h,w,c] = (x > 0) * sum_{i,j} dy[n,2h+i,2w+j,c]; dy may be a channel slice of the concat gradient
+template <typename T>
+__global__ void __launch_bounds__(VT)
+upsample_relu_bwd8_kernel(const T* __restrict__ dy, VView dv, const T* __restrict__ x, VView xv, T* __restrict__ dx, VView ov, int N,
+                          int H, int W, int C) {
+  const uint32_t CV = (uint32_t)C >> 3, total = (uint32_t)N * H * W * CV, W2 = 2u * W;
+  for (uint32_t i = blockIdx.x * VT + threadIdx.x; i < total; i += gridDim.x * VT) {
+    const uint32_t p = i / CV, c0 = (i - p * CV) * 8u;
+    const uint32_t w = p % W, t = p / W, h = t % H, n = t / H;
+    const uint32_t q00 = (n * 2u * H + 2u * h) * W2 + 2u * w;
+    typename V8<T>::raw r[4];
+    r[0] = V8<T>::ldraw(dy + ((size_t)q00 * dv.pitch + dv.off + c0));
+    r[1] = V8<T>::ldraw(dy + ((size_t)(q00 + 1) * dv.pitch + dv.off + c0));
+    r[2] = V8<T>::ldraw(dy + ((size_t)(q00 + W2) * dv.pitch + dv.off + c0));
+    r[3] = V8<T>::ldraw(dy + ((size_t)(q00 + W2 + 1) * dv.pitch + dv.off + c0));
+    float xv8[8], g[8], a[8];
+    V8<T>::ld(x + ((size_t)p * xv.pitch + xv.off + c0), xv8);
+    V8<T>::cvt(r[0], g);
+    // same left-to-right order of the four additions as the scalar kernel
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      V8<T>::cvt(r[k], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += a[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = xv8[j] > 0.f ? g[j] : 0.f;
+    V8<T>::st(dx + ((size_t)p * ov.pitch + ov.off + c0), g);
+  }
+}
+
 static inline unsigned ew8_blocks(long total_vec, int sm_count) {
   long b = (total_vec + VT - 1) / VT, cap = (long)sm_count * 32;
   return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);

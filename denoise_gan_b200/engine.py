@@ -31,7 +31,7 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src", "bn_folded")
+    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src", "bn_folded", "segs", "relu_out", "n_cons", "n_mask")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
@@ -39,6 +39,12 @@ class Var:
         self.bn_done = None     # (name, scale, shift, mean, invstd) when the producing conv ALSO finalised them (last-CTA ticket)
         self.bn_applied = None  # (y_act, act, alpha, prelu, residual) when the producing conv ALSO applied BatchNorm + activation (+ skip)
         self.bn_folded = None   # name of the inference-mode BatchNorm (+ activation) already folded into the producing convolution
+        self.relu_out = False   # output of a convolution with a ReLU epilogue (values >= 0)
+        self.n_cons = 0         # tape nodes (and gradient seeds) that consume this Var ...
+        self.n_mask = 0         # ... of which those whose input gradient already carries the factor (t > 0): when ALL do, the ReLU
+                                # convolution that produced t skips its own dg_act_bwd_from_output pass (autoencoder.py:95-136)
+        self.segs = None        # physically padded channels: ((logical, physical), ...) segments of the channel axis of `t`, each
+                                # holding `logical` real channels followed by zeros; None = dense (see Engine.phys_pad)
         self.bn_src = None      # on the OUTPUT of a training-mode bn_act: (seq, x, scale, shift, mean, act code, alpha) -- lets the input-gradient
                                 # convolution that produces this Var's gradient also reduce the BatchNorm-backward sums (dg_umma_conv2d_dgrad_fused)
 
@@ -121,6 +127,10 @@ class Engine:
         self.fuse_dgrad_mode = int(os.environ.get("DG_DGRAD_BN_BWD", "2"))
         self.fuse_dgrad_bn_bwd = self.fuse_dgrad_mode != 0
         self.fuse_bn_finalize_apply = os.environ.get("DG_BN_FINALIZE_APPLY", "1") != "0"
+        # odd channel counts (autoencoder.py:150-186: 44/56/76/100/152/84) stay zero-padded to multiples of 16 from layer to layer
+        # instead of being padded and sliced around every convolution (Var.segs)
+        self.phys_pad = os.environ.get("DG_PHYS_PAD", "1") != "0"
+        self.fold_relu_bwd = os.environ.get("DG_FOLD_RELU_BWD", "1") != "0"    # see Var.n_mask
         self.fold_bn_infer = os.environ.get("DG_FOLD_BN", "1") != "0"      # inference: BatchNorm folded into the producing conv / depthwise conv
         self._folded: dict = {}
         self.small_map_gemm = os.environ.get("DG_SMALL_MAP_GEMM", "1") != "0"      # weight gradients of <= 8x8 maps as one dense product (dg_im2col)   # dg_bn_act_fwd_from_partials instead of finalize + apply
@@ -222,8 +232,17 @@ class Engine:
         self.seq += 1
         return self.seq
 
-    def _push(self, inputs, out: Var, group, bwd, fusable=False, params=()):
+    def _push(self, inputs, out: Var, group, bwd, fusable=False, params=(), masks=()):
+        """`masks`: the inputs whose gradient this node returns already multiplied by (input > 0)."""
+        for v in inputs:
+            v.n_cons += 1
+        for v in masks:
+            v.n_mask += 1
         self.tape.append(Node(out.seq, inputs, out, group, bwd, fusable, params))
+
+    def _relu_bwd_folded(self, out: Var, act) -> bool:
+        """True when every consumer of this ReLU convolution's output returns a gradient that already carries the ReLU mask."""
+        return self.fold_relu_bwd and act == "relu" and out.n_cons > 0 and out.n_mask == out.n_cons
 
     @staticmethod
     def _deps(inputs, group=None):
@@ -282,9 +301,23 @@ class Engine:
             cin_p, cout_p = p.pack_pad or (cin, cout)
             t = torch.empty(kh * kw * cin_p * cout_p, dtype=torch.bfloat16, device=self.device)
             setattr(p, attr, t)
-            check(self.lib.dg_umma_pack_weights_padded(self.ctx, p.data.data_ptr(), t.data_ptr(), kh, kw, cin, cout, cin_p, cout_p,
-                                                       mode, self.st))
+            sl, sp = p.pack_seg or (0, 0)
+            check(self.lib.dg_umma_pack_weights_seg(self.ctx, p.data.data_ptr(), t.data_ptr(), kh, kw, cin, cout, cin_p, cout_p, sl, sp,
+                                                    mode, self.st))
         return t
+
+    @staticmethod
+    def _norm_segs(segs):
+        """Merges channel segments: a segment without padding joins the one that follows it ((64,64)+(3,16) = (67,80))."""
+        out = []
+        for l, p in segs:
+            if out and out[-1][0] == out[-1][1]:
+                out[-1] = (out[-1][0] + l, out[-1][1] + p)
+            else:
+                out.append((l, p))
+        if all(l == p for l, p in out):
+            return None
+        return tuple(out)
 
     # ---- RGB-sided layers on the tensor cores through zero-padded 16-channel bf16 copies
     def _zeros(self, key, shape, dtype) -> torch.Tensor:
@@ -301,14 +334,23 @@ class Engine:
         td = _lib.DgTensor(dst.data_ptr(), _lib.DG_F32, 1, 1, 1, n, dst.numel(), 0)
         check(self.lib.dg_copy(self.ctx, C.byref(ts), C.byref(td), 0, self.st))
 
-    def _conv2d_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype):
+    def _conv2d_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype, keep=False):
         """conv2d when Cin or Cout is not a multiple of 16 (the 3-channel image side of srgan.py:154,182,236): operands are
         zero-padded to 16 channels in bf16 (dg_pad_channels / dg_umma_pack_weights_padded), the tcgen05 kernels run on the
         padded shapes, and results are sliced back (dg_copy views, dg_unpad_weight_grad).  Returns None when the tensor-core
         kernels have no tile configuration for the padded layer (the caller then uses the CUDA-core kernels)."""
-        N, H, W, cin = x.shape
-        kh, kw, _, cout = w.shape
-        cin_p, cout_p = -(-cin // 16) * 16, -(-cout // 16) * 16
+        N, H, W, cin_p = x.shape
+        kh, kw, cin, cout = w.shape
+        segs = x.segs
+        seg = (0, 0)
+        if segs is None:
+            cin_p = -(-cin // 16) * 16
+        else:
+            assert len(segs) <= 2 and x.t.dtype == torch.bfloat16, f"{w.name}: unsupported channel segments {segs}"
+            if len(segs) == 2:
+                seg = segs[0]
+        cout_p = -(-cout // 16) * 16
+        keep = keep and self.phys_pad and cout_p != cout and act in (None, "relu", "lrelu", "tanh")     # act(0) = 0 keeps the padding zero
         ydt = out_dtype or self.act_dtype
         lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
         cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
@@ -326,16 +368,17 @@ class Engine:
         if not ok:
             return None
         seq = self._next()
-        w.pack_pad = (cin_p, cout_p)
-        y = self.buf((seq, "y"), (N, Ho, Wo, cout), ydt)
-        pad_in = cin_p != cin or x.t.dtype != torch.bfloat16
+        assert w.pack_pad in (None, (cin_p, cout_p)) and w.pack_seg in (None, seg), f"{w.name}: used with two different channel layouts"
+        w.pack_pad, w.pack_seg = (cin_p, cout_p), seg
+        y = None if keep else self.buf((seq, "y"), (N, Ho, Wo, cout), ydt)
+        pad_in = segs is None and (cin_p != cin or x.t.dtype != torch.bfloat16)
         if pad_in:
             xin = self.buf((seq, "xpad"), (N, H, W, cin_p), torch.bfloat16)
             tsrc, tdst = tensor(x.t), tensor(xin)
             check(self.lib.dg_pad_channels(self.ctx, C.byref(tsrc), C.byref(tdst), self.st))
         else:
             xin = x.t
-        yp = y if cout_p == cout else self.buf((seq, "ypad"), (N, Ho, Wo, cout_p), ydt)
+        yp = y if (cout_p == cout and not keep) else self.buf((seq, "ypad"), (N, Ho, Wo, cout_p), ydt)
         bias = None
         if b is not None:
             if cout_p == cout:
@@ -349,18 +392,23 @@ class Engine:
         pk = self._packed(w, 0)
         self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
             self.ctx, C.byref(txi), pk.data_ptr(), bias, C.byref(typ), C.byref(cp), None, self.st)))
-        if yp is not y:
+        if keep:
+            y = yp
+        elif yp is not y:
             tv, ty = tensor(yp, c=cout), tensor(y)
             check(self.lib.dg_copy(self.ctx, C.byref(tv), C.byref(ty), 0, self.st))
         out = Var(y, self._deps([x], w.group), seq)
+        out.relu_out = act == "relu"
+        if keep:
+            out.segs = ((cout, cout_p),)
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag):
             dpre = gy
-            if ACT[act]:
+            if ACT[act] and not self._relu_bwd_folded(out, act):
                 dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
                 tg, tyy, td = tensor(gy), tensor(y), tensor(dpre)
                 check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
-            if cout_p != cout or dpre.dtype != torch.bfloat16:
+            if (cout_p != cout and not keep) or dpre.dtype != torch.bfloat16:
                 dpp = self.buf((seq, "dpad", tag), (N, Ho, Wo, cout_p), torch.bfloat16)
                 ts, td = tensor(dpre), tensor(dpp)
                 check(self.lib.dg_pad_channels(self.ctx, C.byref(ts), C.byref(td), self.st))
@@ -378,9 +426,9 @@ class Engine:
                     dbp = self.buf((seq, "db_pad", tag), (cout_p,), torch.float32) if b is not None else None
                     self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
                         self.ctx, C.byref(txi), C.byref(tdp), dwp.data_ptr(), _lib.ptr(dbp), C.byref(lin), 0, ws.data_ptr(), nbytes, self.st)))
-                    check(self.lib.dg_unpad_weight_grad(self.ctx, dwp.data_ptr(), _lib.ptr(dbp), w.grad.data_ptr(),
-                                                        b.grad.data_ptr() if b is not None else None, kh, kw, cin, cout, cin_p, cout_p,
-                                                        acc, self.st))
+                    check(self.lib.dg_unpad_weight_grad_seg(self.ctx, dwp.data_ptr(), _lib.ptr(dbp), w.grad.data_ptr(),
+                                                            b.grad.data_ptr() if b is not None else None, kh, kw, cin, cout, cin_p, cout_p,
+                                                            seg[0], seg[1], acc, self.st))
             dx = None
             if need_in[0]:
                 dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
@@ -423,21 +471,25 @@ class Engine:
         return ent
 
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
-               out_dtype=None, bn: bool = False, post: dict | None = None) -> Var:
-        """keras Conv2D (+bias, +activation epilogue).  `bn=True`: a training-mode BatchNormalization consumes the result
+               out_dtype=None, bn: bool = False, post: dict | None = None, keep_padded: bool = False) -> Var:
+        """keras Conv2D (+bias, +activation epilogue).  `keep_padded`: an output whose channel count is not a multiple of 16
+        stays zero-padded (Var.segs) for consumers that understand it (conv2d, maxpool2x2, upsample_concat).  `bn=True`: a training-mode BatchNormalization consumes the result
         next, so the tensor-core epilogue also produces its batch-statistics partials (picked up by bn_act).
         `post` = dict(act=, alpha=, prelu=, residual=) describes what the bn_act call that FOLLOWS will do with the result; when
         the layer qualifies, convolution, statistics, normalisation, activation and skip-add run as one cooperative launch
         and bn_act only records the tape node."""
         N, H, W, Cin = x.shape
         kh, kw, cin, cout = w.shape
+        if x.segs is not None:
+            Cin = sum(l for l, _ in x.segs)
         assert cin == Cin, f"{w.name}: Cin {cin} != input {Cin}"
         pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, stride, padding)
-        if (self.use_umma and self.pad_rgb and (cin % 16 != 0 or cout % 16 != 0) and kh * kw <= 16 and
+        if (self.use_umma and self.pad_rgb and (cin % 16 != 0 or cout % 16 != 0 or x.segs is not None) and kh * kw <= 16 and
                 stride in (1, 2) and (stride == 1 or (H % 2 == 0 and W % 2 == 0))):
-            r = self._conv2d_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype)
+            r = self._conv2d_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype, keep=keep_padded)
             if r is not None:
                 return r
+        assert x.segs is None, f"{w.name}: physically padded input needs the tensor-core path"
         seq = self._next()
         y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
         cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
@@ -525,10 +577,11 @@ class Engine:
         out.bn_part = bn_part
         out.bn_done = bn_done
         out.bn_applied = bn_applied
+        out.relu_out = act == "relu"
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag, fctx=None):
             dpre = gy
-            if ACT[act]:
+            if ACT[act] and not self._relu_bwd_folded(out, act):
                 dpre = self.buf((seq, "dpre", tag), gy.shape, gy.dtype)
                 tg, tyy, td = tensor(gy), tensor(y), tensor(dpre)
                 check(self.lib.dg_act_bwd_from_output(self.ctx, C.byref(tg), C.byref(tyy), ACT[act], float(alpha), C.byref(td), self.st))
@@ -975,6 +1028,7 @@ class Engine:
             offs.append(off)
             off += c
         out = Var(y, self._deps(parts), seq)
+        out.segs = self._norm_segs([sg for p in parts for sg in (p.segs or ((p.shape[3], p.shape[3]),))])
 
         def bwd(gy, need_in, need_p, tag):
             res = []
@@ -998,16 +1052,18 @@ class Engine:
         tx, ty = tensor(x.t), tensor(y)
         check(self.lib.dg_maxpool2x2_fwd(self.ctx, C.byref(tx), C.byref(ty), self.st))
         out = Var(y, self._deps([x]), seq)
+        out.segs = x.segs        # per-channel op: zero padding stays zero (max of zeros; its gradient is dropped by the consumers)
 
         def bwd(gy, need_in, need_p, tag):
             if not need_in[0]:
                 return [None]
             dx = self.buf((seq, "dx", tag), x.shape, gy.dtype)
             tg, tdx = tensor(gy), tensor(dx)
-            check(self.lib.dg_maxpool2x2_bwd(self.ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), self.st))
+            fn = self.lib.dg_maxpool2x2_bwd_relu if x.relu_out else self.lib.dg_maxpool2x2_bwd
+            check(fn(self.ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), self.st))
             return [dx]
 
-        self._push([x], out, None, bwd)
+        self._push([x], out, None, bwd, masks=[x] if x.relu_out else ())
         return out
 
     def upsample2x_relu(self, x: Var) -> Var:
@@ -1017,6 +1073,7 @@ class Engine:
         tx, ty = tensor(x.t), tensor(y)
         check(self.lib.dg_upsample2x_relu_fwd(self.ctx, C.byref(tx), C.byref(ty), self.st))
         out = Var(y, self._deps([x]), seq)
+        out.segs = x.segs
 
         def bwd(gy, need_in, need_p, tag):
             if not need_in[0]:
@@ -1026,7 +1083,61 @@ class Engine:
             check(self.lib.dg_upsample2x_relu_bwd(self.ctx, C.byref(tg), C.byref(tx), C.byref(tdx), self.st))
             return [dx]
 
+        self._push([x], out, None, bwd, masks=[x])      # the gradient of relu(up(x)) carries (x > 0)
+        return out
+
+    def pad_input(self, x: Var) -> Var:
+        """The network input (3-channel image, autoencoder.py:150) as a bf16 tensor zero-padded to 16 channels: consumed in
+        place by the first convolution and by the last U-Net concat (autoencoder.py:181) instead of being padded twice."""
+        N, H, W, c = x.shape
+        cp = -(-c // 16) * 16
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, H, W, cp), torch.bfloat16)
+        tx, ty = tensor(x.t), tensor(y)
+        check(self.lib.dg_pad_channels(self.ctx, C.byref(tx), C.byref(ty), self.st))
+        out = Var(y, self._deps([x]), seq)
+        out.segs = self._norm_segs([(c, cp)])
+
+        def bwd(gy, need_in, need_p, tag):
+            if not need_in[0]:
+                return [None]
+            dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+            tg, tdx = tensor(gy, c=c), tensor(dx)
+            check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tdx), 0, self.st))
+            return [dx]
+
         self._push([x], out, None, bwd)
+        return out
+
+    def upsample_concat(self, a: Var, b: Var) -> Var:
+        """concat([relu(UpSampling2D(2)(a)), b], axis=3) (autoencoder.py:113-136) with the up-sampled part written straight into
+        its channel slice of the result, and its gradient read straight from that slice: no pass over the large half of the
+        concat buffer in either direction."""
+        N, H, W, ca = a.shape
+        cb = b.shape[3]
+        assert tuple(b.shape[:3]) == (N, 2 * H, 2 * W) and a.t.dtype == b.t.dtype
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, 2 * H, 2 * W, ca + cb), a.t.dtype)
+        ta, tya = tensor(a.t), tensor(y, c=ca, coff=0)
+        check(self.lib.dg_upsample2x_relu_fwd(self.ctx, C.byref(ta), C.byref(tya), self.st))
+        tb, tyb = tensor(b.t), tensor(y, c=cb, coff=ca)
+        check(self.lib.dg_copy(self.ctx, C.byref(tb), C.byref(tyb), 0, self.st))
+        out = Var(y, self._deps([a, b]), seq)
+        out.segs = self._norm_segs(list(a.segs or ((ca, ca),)) + list(b.segs or ((cb, cb),)))
+
+        def bwd(gy, need_in, need_p, tag):
+            da = db = None
+            if need_in[0]:
+                da = self.buf((seq, "da", tag), a.shape, gy.dtype)
+                tg, tda = tensor(gy, c=ca, coff=0), tensor(da)
+                check(self.lib.dg_upsample2x_relu_bwd(self.ctx, C.byref(tg), C.byref(ta), C.byref(tda), self.st))
+            if need_in[1]:
+                db = self.buf((seq, "db", tag), b.shape, gy.dtype)
+                tg, tdb = tensor(gy, c=cb, coff=ca), tensor(db)
+                check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tdb), 0, self.st))
+            return [da, db]
+
+        self._push([a, b], out, None, bwd, masks=[a])   # da carries (a > 0)
         return out
 
     def cast(self, x: Var, dtype) -> Var:
@@ -1126,6 +1237,7 @@ class Engine:
                 check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tt), 1, self.st))
 
         for v, g in seeds:
+            v.n_cons += 1          # a gradient fed in from outside carries no ReLU mask (Var.n_mask)
             accum(v, g)
         # consumers still to be visited per Var: the visit that brings the count to zero produces the LAST contribution to that
         # Var's gradient and may fold the sum accumulated so far (skip connections) into its own epilogue

@@ -85,13 +85,18 @@ class AutoencoderGenerator(_Net):
     def __call__(self, x, training=True) -> Var:
         E, p = self.E, self.p
         x = self._in(x)
-        xin = E.cast(x, E.act_dtype)
+        # bf16 tensor-core path: the odd widths (3/44/56/76/100/152/84 channels) stay zero-padded to multiples of 16 from layer
+        # to layer (Engine.phys_pad) -- no pad / slice pass around the convolutions
+        keep = E.use_umma and E.pad_rgb and E.phys_pad and E.act_dtype == torch.bfloat16
+        xin = E.pad_input(x) if keep else E.cast(x, E.act_dtype)
+        if keep:
+            x = xin
 
         def conv(t, name, act="relu", out_dtype=None):
-            return E.conv2d(t, p[f"g/{name}/kernel"], p[f"g/{name}/bias"], act=act, out_dtype=out_dtype)
+            return E.conv2d(t, p[f"g/{name}/kernel"], p[f"g/{name}/bias"], act=act, out_dtype=out_dtype, keep_padded=keep and act == "relu")
 
         def upcat(a, b):
-            return E.concat([E.upsample2x_relu(a), b])
+            return E.upsample_concat(a, b)
 
         c1b = conv(conv(x, "conv1"), "conv1b"); p1 = E.maxpool2x2(c1b)
         p2 = E.maxpool2x2(conv(p1, "conv2"))

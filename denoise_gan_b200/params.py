@@ -22,7 +22,7 @@ ALIGN = 64  # elements; keeps every tensor 256-byte aligned inside the arena
 class Param:
     """A named slice of a parameter arena."""
 
-    __slots__ = ("name", "shape", "offset", "numel", "group", "owner", "packed_fwd", "packed_dgrad", "trainable", "pack_pad")
+    __slots__ = ("name", "shape", "offset", "numel", "group", "owner", "packed_fwd", "packed_dgrad", "trainable", "pack_pad", "pack_seg")
 
     def __init__(self, name, shape, offset, group, owner, trainable=True):
         self.name, self.shape, self.offset, self.group, self.owner = name, tuple(shape), offset, group, owner
@@ -30,6 +30,7 @@ class Param:
         self.packed_fwd = None
         self.packed_dgrad = None
         self.pack_pad = None          # (cin_pad, cout_pad) when the tensor-core copies are zero-padded to 16 channels
+        self.pack_seg = None          # (seg_log, seg_phys): two-segment input-channel axis (dg_umma_pack_weights_seg), (0, 0) = one
         self.trainable = trainable
 
     @property
@@ -106,13 +107,14 @@ class ParamSet:
                 cin_p, cout_p = p.pack_pad or (cin, cout)
                 kdim = cin_p if mode == 0 else cout_p
                 kc = 64 if kdim % 64 == 0 else (32 if kdim % 32 == 0 else 16)
-                ents.append((p.data.data_ptr(), t.data_ptr(), kh * kw, cin_p, cout_p, kc, mode, cin, cout))
+                sl, sp = p.pack_seg or (0, 0)
+                ents.append((p.data.data_ptr(), t.data_ptr(), kh * kw, cin_p, cout_p, kc, mode, cin, cout, sl | (sp << 16)))
         if not ents:
             return
         key = tuple(ents)
         if getattr(self, "_pack_key", None) != key:
-            blob = b"".join(struct.pack("<QQiiiiiiii", s, d, taps, cin, cout, kc, mode, cin_s, cout_s, 0)
-                            for s, d, taps, cin, cout, kc, mode, cin_s, cout_s in ents)
+            blob = b"".join(struct.pack("<QQiiiiiiii", s, d, taps, cin, cout, kc, mode, cin_s, cout_s, seg)
+                            for s, d, taps, cin, cout, kc, mode, cin_s, cout_s, seg in ents)
             self._pack_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.theta.device)
             self._pack_key = key
         _lib.check(lib.dg_umma_pack_weights_batch(ctx, self._pack_table.data_ptr(), len(ents), stream))

@@ -231,6 +231,9 @@ int dg_copy(dg_ctx*, const dg_tensor* src, const dg_tensor* out, int accumulate,
 /* MaxPool2D(2,2) (autoencoder.py:110) and its gradient (first max in window order gets the gradient) */
 int dg_maxpool2x2_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
 int dg_maxpool2x2_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y, const dg_tensor* dx, void* stream);
+/* the same when x is the output of a ReLU convolution (autoencoder.py:95-110, conv2d(..., relu) -> maxpool2d): the gradient is also
+ * multiplied by (x > 0), i.e. the ReLU's own backward pass is folded in and tape.gradient needs no separate pass over x */
+int dg_maxpool2x2_bwd_relu(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* y, const dg_tensor* dx, void* stream);
 /* UpSampling2D(2,'nearest') + relu into a concat slice (autoencoder.py:113-136) and its gradient */
 int dg_upsample2x_relu_fwd(dg_ctx*, const dg_tensor* x, const dg_tensor* y, void* stream);
 int dg_upsample2x_relu_bwd(dg_ctx*, const dg_tensor* dy, const dg_tensor* x, const dg_tensor* dx, void* stream);
@@ -251,6 +254,15 @@ int dg_umma_pack_weights_padded(dg_ctx*, const float* w, void* packed, int kh, i
                                 int mode, void* stream);
 int dg_unpad_weight_grad(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw, int cin,
                          int cout, int cin_pad, int cout_pad, int accumulate, void* stream);
+/* Physically padded activations (the autoencoder's 44/56/76/100/152/84-channel layers, autoencoder.py:150-186, stay zero-padded
+ * to multiples of 16 from layer to layer instead of being padded and sliced around every convolution).  The input-channel axis
+ * of a kernel that consumes a U-Net concat of two padded tensors (autoencoder.py:135) consists of TWO padded segments:
+ * physical channels [0, seg_phys) hold the first seg_log channels of the Keras kernel, [seg_phys, cin_pad) the remaining
+ * cin - seg_log; everything else is zero.  seg_phys = 0: one segment (= the functions above). */
+int dg_umma_pack_weights_seg(dg_ctx*, const float* w, void* packed, int kh, int kw, int cin, int cout, int cin_pad, int cout_pad,
+                             int seg_log, int seg_phys, int mode, void* stream);
+int dg_unpad_weight_grad_seg(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw,
+                             int cin, int cout, int cin_pad, int cout_pad, int seg_log, int seg_phys, int accumulate, void* stream);
 
 /* ---- frame pre/post-processing around the inference forward (infer_video.py:138-159, infer.py:50-68,
  * unit_test.py:67-86).  src/dst frames are packed uint8 [n, h, w, 3] in DEVICE memory.

@@ -1093,3 +1093,90 @@ def test_umma_dgrad_stride2_fused_phases(L, case):
     torch.cuda.synchronize()
     pre = ref + b
     assert relerr(out, torch.where(pre >= 0, pre, 0.3 * pre)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_pool_upsample_vector_kernels(L, dtype):
+    """8-channel-vector MaxPool2D(2,2) / UpSampling2D(2)+ReLU (autoencoder.py:110,113-136) on channel counts that are multiples of
+    8, through channel-slice views (the up-sampled half is written straight into the concat buffer): bit-exact against the
+    oracle on inputs that are exact in the storage type (max, relu and routing do no arithmetic; the backward sum of four
+    bf16 values is rounded once)."""
+    g = torch.Generator().manual_seed(11)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    x = torch.randn(3, 6, 10, 24, generator=g).to(dtype).double()
+    x[0, 0, 0, :8] = x[0, 0, 1, :8]                      # ties inside a pooling window: the first position gets the gradient
+    xr = x.clone().requires_grad_(True)
+    ref = OT.max_pool2x2(xr); gy = torch.randn(ref.shape, generator=g).to(dtype).double()
+    (ref * gy).sum().backward()
+    wide_x = torch.zeros(3, 6, 10, 40, device="cuda", dtype=dtype); wide_x[..., 8:32] = x.to(dtype).cuda()
+    wide_y = torch.zeros(3, 3, 5, 32, device="cuda", dtype=dtype)
+    gyd = dev(gy, dtype); dx = torch.zeros(3, 6, 10, 24, device="cuda", dtype=dtype)
+    tx, ty, tg, tdx = L.tensor(wide_x, c=24, coff=8), L.tensor(wide_y, c=24, coff=0), L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_maxpool2x2_fwd(ctx, C.byref(tx), C.byref(ty), st))
+    L.check(lib.dg_maxpool2x2_bwd(ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), st))
+    assert torch.equal(wide_y[..., :24].double().cpu(), ref.detach()) and (wide_y[..., 24:] == 0).all()
+    assert torch.equal(dx.double().cpu(), xr.grad)
+    # up-sampling + relu into a slice of a wider buffer, gradient read back from a slice
+    xr.grad = None
+    ref = torch.relu(OT.upsample2x_nearest(xr)); gy = torch.randn(ref.shape, generator=g).to(dtype).double()
+    (ref * gy).sum().backward()
+    cat = torch.zeros(3, 12, 20, 48, device="cuda", dtype=dtype)
+    tc = L.tensor(cat, c=24, coff=16)
+    L.check(lib.dg_upsample2x_relu_fwd(ctx, C.byref(tx), C.byref(tc), st))
+    assert torch.equal(cat[..., 16:40].double().cpu(), ref.detach()) and (cat[..., :16] == 0).all() and (cat[..., 40:] == 0).all()
+    gcat = torch.zeros(3, 12, 20, 48, device="cuda", dtype=dtype); gcat[..., 16:40] = gy.to(dtype).cuda()
+    tgc = L.tensor(gcat, c=24, coff=16)
+    dx2 = torch.zeros_like(dx); tdx2 = L.tensor(dx2)
+    L.check(lib.dg_upsample2x_relu_bwd(ctx, C.byref(tgc), C.byref(tx), C.byref(tdx2), st))
+    assert relerr(dx2, xr.grad) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_pack_and_unpad_with_channel_segments(L, mode):
+    """dg_umma_pack_weights_seg / dg_unpad_weight_grad_seg: the input-channel axis of a kernel that consumes a U-Net concat of two
+    zero-padded tensors (autoencoder.py:135: 100 of 112 channels, then 76 of 80) -- checked against dg_umma_pack_weights of the
+    same kernel scattered into the padded layout on the host, and against a host gather for the gradient."""
+    g = torch.Generator().manual_seed(5)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    kh = kw = 3; c1, c1p, c2, c2p, cout, cout_p = 100, 112, 76, 80, 152, 160
+    cin, cin_p = c1 + c2, c1p + c2p
+    w = torch.randn(kh, kw, cin, cout, generator=g)
+    wp = torch.zeros(kh, kw, cin_p, cout_p)
+    wp[:, :, :c1, :cout] = w[:, :, :c1]; wp[:, :, c1p:c1p + c2, :cout] = w[:, :, c1:]
+    wd, wpd = dev(w), dev(wp)
+    a = torch.empty(kh * kw * cin_p * cout_p, dtype=torch.bfloat16, device="cuda"); b = torch.empty_like(a)
+    L.check(lib.dg_umma_pack_weights_seg(ctx, wd.data_ptr(), a.data_ptr(), kh, kw, cin, cout, cin_p, cout_p, c1, c1p, mode, st))
+    L.check(lib.dg_umma_pack_weights(ctx, wpd.data_ptr(), b.data_ptr(), kh, kw, cin_p, cout_p, mode, st))
+    assert torch.equal(a, b)
+    # a single padded segment is the plain padded packing
+    L.check(lib.dg_umma_pack_weights_seg(ctx, wd.data_ptr(), a.data_ptr(), kh, kw, cin, cout, cin_p, cout_p, 0, 0, mode, st))
+    L.check(lib.dg_umma_pack_weights_padded(ctx, wd.data_ptr(), b.data_ptr(), kh, kw, cin, cout, cin_p, cout_p, mode, st))
+    assert torch.equal(a, b)
+    if mode == 0:
+        dwp = torch.randn(kh, kw, cin_p, cout_p, generator=g); dbp = torch.randn(cout_p, generator=g)
+        dw = torch.ones(kh, kw, cin, cout, device="cuda"); db = torch.ones(cout, device="cuda")
+        dwpd, dbpd = dev(dwp), dev(dbp)
+        L.check(lib.dg_unpad_weight_grad_seg(ctx, dwpd.data_ptr(), dbpd.data_ptr(), dw.data_ptr(), db.data_ptr(), kh, kw, cin, cout, cin_p,
+                                             cout_p, c1, c1p, 1, st))
+        ref = torch.cat([dwp[:, :, :c1, :cout], dwp[:, :, c1p:c1p + c2, :cout]], dim=2) + 1
+        assert torch.equal(dw.cpu(), ref) and torch.equal(db.cpu(), dbp[:cout] + 1)
+
+
+@pytest.mark.parametrize("channels", [5, 24])
+def test_maxpool_bwd_with_folded_relu(L, channels):
+    """dg_maxpool2x2_bwd_relu = gradient of maxpool(relu(u)) with respect to u, given x = relu(u) (autoencoder.py:95-110): the ReLU
+    mask of the convolution in front of the pooling is applied by the pooling's backward pass (scalar and 8-channel kernels)."""
+    g = torch.Generator().manual_seed(21)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    u = torch.randn(2, 8, 6, channels, generator=g, dtype=torch.float64)
+    u[0, :2, :2, 0] = -1.0                                   # a window that is zero everywhere after the ReLU: no gradient at all
+    ur = u.clone().requires_grad_(True)
+    ref = OT.max_pool2x2(torch.relu(ur)); gy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * gy).sum().backward()
+    xd, gyd = dev(torch.relu(u)), dev(gy)
+    y = torch.empty(ref.shape, device="cuda"); dx = torch.empty_like(xd)
+    tx, ty, tg, tdx = L.tensor(xd), L.tensor(y), L.tensor(gyd), L.tensor(dx)
+    L.check(lib.dg_maxpool2x2_fwd(ctx, C.byref(tx), C.byref(ty), st))
+    L.check(lib.dg_maxpool2x2_bwd_relu(ctx, C.byref(tg), C.byref(tx), C.byref(ty), C.byref(tdx), st))
+    assert relerr(y, ref) < 1e-6 and relerr(dx, ur.grad) < 1e-6
+    assert (dx[0, :2, :2, 0] == 0).all()

@@ -148,6 +148,52 @@ def test_autoencoder_step_bf16_tracks_fp64():
         assert abs(r[n].item() - float(b)) <= 2e-2 * max(1.0, abs(float(b))), (n, r[n].item(), float(b))
 
 
+def test_autoencoder_physically_padded_channels_match_pad_and_slice():
+    """Engine.phys_pad (activations of the 44/56/76/100/152/84-channel layers kept zero-padded from layer to layer, the up-sampled
+    half of every U-Net concat written in place) against the pad-and-slice path on one train step.  The two are NOT bit-identical:
+    a concat of two padded tensors has another physical width (112+80 = 192 channels instead of 176), so the kernels pick another
+    K chunking, fp32 sums come in another order and single bf16 roundings flip.  Both must sit at the same distance from the
+    float64 oracle, and within bf16 noise of each other (output L2, losses, gradient direction)."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.autoencoder import Autoencoder
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.train_common import gan_step
+    x, y = synthetic_pair(2, 64, 1, step=0)
+    g0 = perturb(P.init_autoencoder_generator(0)); d0 = perturb(P.init_patch_discriminator(1))
+    res = []
+    for phys in (True, False):
+        model = Autoencoder(SimpleNamespace(crop_size=64, lr=1e-3, fp16=1, vgg=0, retrain=0, seed=0))
+        model.engine.phys_pad = phys
+        model.gen_params.load(g0); model.disc_params.load(d0)
+        r = gan_step(model, x.cuda(), y.cuda(), from_logits=False, disc_scale=1.0)
+        torch.cuda.synchronize()
+        calls = sum(1 for k in model.engine.pool if isinstance(k[0], tuple) and len(k[0]) > 1 and k[0][1] in ("xpad", "dx_pad"))
+        res.append((r["gen_output"].t.float().clone(), {n: r[n].item() for n in ("disc_loss", "adv_loss", "mse_loss", "mae_loss")},
+                    model.gen_params.grads(), model.disc_params.grads(), calls))
+    (oa, la, ga, da, na), (ob, lb, gb, db, nb) = res
+    assert na < nb, f"physical padding should remove input pad / slice buffers ({na} vs {nb})"
+    g = {k: v.double().clone() for k, v in g0.items()}; d = {k: v.double().clone() for k, v in d0.items()}
+    out = {}
+    OS.autoencoder_train_step(g, d, None, OT.KerasAdam(1e-3, decay_steps=100000), OT.KerasAdam(5e-3, decay_steps=100000),
+                              x.double(), y.double(), out=out)
+    ea, eb, eab = relerr_l2(oa, out["gen_output"]), relerr_l2(ob, out["gen_output"]), relerr_l2(oa, ob)
+    print(f"generator output, relative L2: padded vs oracle {ea:.2e}, pad-and-slice vs oracle {eb:.2e}, padded vs pad-and-slice {eab:.2e}")
+    assert ea < 2e-2 and eb < 2e-2 and ea < 1.5 * eb + 1e-3 and eab < 2e-2
+    for n in la:
+        assert abs(la[n] - lb[n]) <= 1e-2 * max(1.0, abs(lb[n])), (n, la[n], lb[n])
+
+    def cosine(a, b):
+        a, b = a.double().flatten(), b.double().flatten()
+        return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+    worst = min((cosine(ga[n], gb[n]), n) for n in gb if n.endswith("kernel"))
+    print("worst gradient cosine between the two paths:", worst)
+    assert worst[0] > 0.9, worst
+    for name in ("g/conv11/kernel", "g/conv10b/kernel", "g/conv10/kernel", "g/conv9b/kernel", "g/conv6/kernel", "g/conv7/kernel"):
+        # kernels that consume a two-segment concat (conv6..conv10) included: direction against the ORACLE as good as the old path's
+        ca, cb = cosine(ga[name], out["gen_grads"][name]), cosine(gb[name], out["gen_grads"][name])
+        assert ca > 0.95 and ca > cb - 0.02, (name, ca, cb)
+
+
 def test_pix2pix_step_bf16_tracks_fp64():
     """bf16 path of the pix2pix step at 256x256: losses against the float64 oracle (same dropout masks)."""
     import numpy as np
