@@ -77,6 +77,8 @@ struct UmmaConvParams {
   void* out;
   long out_sn, out_sh, out_sw;
   int out_f32;
+  int out_cvalid;   // > 0 (fp32 output, one 16-channel N block): only the first out_cvalid channels of a pixel are stored -- the
+                    // 3-channel image side (srgan.py:182, fsrgan.py:217) written densely instead of padded to 16 and sliced
   // staged epilogue: the tile is written to shared memory in the TMA swizzle and leaves through ONE bulk tensor store
   // (dense bf16 output views with a 16/32/64-channel N block); optionally the BatchNorm batch-statistics partials
   // (per-channel sum and sum of squares of the STORED values) are accumulated from the staged tile
@@ -201,7 +203,14 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
         uint32_t v0[16];
         tmem_ld_32x16(acc + c0, v0);
         tmem_ld_wait();
-        if (valid) epi_store16<ACT, F32>(v0, bs ? bs + c0 : nullptr, P.alpha, P.out, pix + c0);
+        if (F32 && P.out_cvalid > 0) {
+          if (valid) {
+            float* dst = reinterpret_cast<float*>(P.out) + pix;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < P.out_cvalid) dst[j] = act_fn<ACT>(__uint_as_float(v0[j]) + (bs ? bs[j] : 0.f), P.alpha);
+          }
+        } else if (valid) epi_store16<ACT, F32>(v0, bs ? bs + c0 : nullptr, P.alpha, P.out, pix + c0);
       }
     }
     tc_fence_before();
@@ -1254,13 +1263,15 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
                 float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr,
                 const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, const BwdEpi* bwd = nullptr,
-                bool bwd_query = false) {
+                bool bwd_query = false, int out_cvalid = 0) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
+  DG_REQUIRE(out_cvalid == 0 || (out->dtype == DG_F32 && out->c == 16 && out_cvalid < 16 && n_phase == 1 && !bn_partials && !bnp && !bwd),
+             "%s: a narrow store needs an fp32 output of fewer than 16 channels", name);
   DG_REQUIRE(n_phase == 1 || (n_phase == 4 && phase_lat && n_src == 1), "%s: bad output-phase description", name);
   DG_REQUIRE(in->c % 16 == 0 && out->c % 16 == 0, "%s: channels must be multiples of 16 (got %d -> %d)", name, in->c, out->c);
   DG_REQUIRE(in->cpitch % 8 == 0 && in->coff % 8 == 0 && ((uintptr_t)in->ptr % 16) == 0, "%s: input view not 16-byte aligned", name);
   const int out_esz = out->dtype == DG_F32 ? 4 : 2;
-  DG_REQUIRE(((uintptr_t)out->ptr % 16) == 0 && (out->cpitch * out_esz) % 16 == 0 && (out->coff * out_esz) % 16 == 0,
+  DG_REQUIRE(out_cvalid > 0 || (((uintptr_t)out->ptr % 16) == 0 && (out->cpitch * out_esz) % 16 == 0 && (out->coff * out_esz) % 16 == 0),
              "%s: output view not 16-byte aligned", name);
   DG_REQUIRE(n_src >= 1 && n_src <= MAX_SRC && n_taps >= 1 && n_taps <= MAX_TAPS, "%s: too many sources/taps", name);
   DG_REQUIRE(act != DG_ACT_PRELU, "%s: PReLU is not a conv epilogue", name);
@@ -1553,6 +1564,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.out_sh = (long)out->cpitch * out->w * out_lat.step;
   P.out_sn = (long)out->cpitch * out->w * out->h;
   P.out_f32 = out->dtype == DG_F32;
+  P.out_cvalid = out_cvalid;
   P.bias = bias; P.act = act; P.alpha = alpha;
   P.dbg = g_dbg_timeline;
   P.dbg_flags = g_dbg_flags;
@@ -1729,8 +1741,8 @@ extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, in
 
 static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
                          const dg_conv_params* p, void* stream, bool dry, float* bn_partials = nullptr, int* bn_blocks = nullptr,
-                         const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false) {
-  DG_REQUIRE(dg_valid(x) && dg_valid(y) && w_packed && p, "dg_umma_conv2d_fwd: null argument");
+                         const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, int out_cvalid = 0) {
+  DG_REQUIRE(dg_valid(x) && y && y->ptr && w_packed && p, "dg_umma_conv2d_fwd: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
   DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
   DG_REQUIRE(p->kh * p->kw <= MAX_TAPS, "dg_umma_conv2d_fwd: kernel too large");
@@ -1753,7 +1765,19 @@ static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, 
       }
   }
   return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
-                     p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks, 1, nullptr, bn_fin, bnp, bnp_query);
+                     p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks, 1, nullptr, bn_fin, bnp, bnp_query, nullptr, false,
+                     out_cvalid);
+}
+
+// Conv2D whose output has fewer than 16 channels (the RGB image: srgan.py:182, fsrgan.py:217, autoencoder.py:186), fp32: the packed
+// kernel and the bias are zero-padded to 16 output channels (dg_umma_pack_weights_padded), the tensor cores compute all 16, and the
+// epilogue stores only the y->c real ones into the DENSE tensor y -- no padded copy of the output, no slicing pass.
+extern "C" int dg_umma_conv2d_fwd_narrow(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias_padded, const dg_tensor* y,
+                                         const dg_conv_params* p, void* stream) {
+  DG_REQUIRE(dg_valid(y) && y->dtype == DG_F32 && y->c < 16 && y->coff == 0, "dg_umma_conv2d_fwd_narrow: y must be an fp32 tensor of fewer than 16 channels");
+  dg_tensor y16 = *y;
+  y16.c = 16;
+  return conv_fwd_impl(ctx, x, w_packed, bias_padded, &y16, p, stream, false, nullptr, nullptr, nullptr, nullptr, false, y->c);
 }
 
 // Conv2D + training-mode BatchNormalization + activation (+ skip-add) in one cooperative launch (UmmaConvParams::bnp).

@@ -131,6 +131,7 @@ class Engine:
         # instead of being padded and sliced around every convolution (Var.segs)
         self.phys_pad = os.environ.get("DG_PHYS_PAD", "1") != "0"
         self.fold_relu_bwd = os.environ.get("DG_FOLD_RELU_BWD", "1") != "0"    # see Var.n_mask
+        self.narrow_store = os.environ.get("DG_NARROW_STORE", "1") != "0"
         self.fold_bn_infer = os.environ.get("DG_FOLD_BN", "1") != "0"      # inference: BatchNorm folded into the producing conv / depthwise conv
         self._folded: dict = {}
         self.small_map_gemm = os.environ.get("DG_SMALL_MAP_GEMM", "1") != "0"      # weight gradients of <= 8x8 maps as one dense product (dg_im2col)   # dg_bn_act_fwd_from_partials instead of finalize + apply
@@ -378,7 +379,9 @@ class Engine:
             check(self.lib.dg_pad_channels(self.ctx, C.byref(tsrc), C.byref(tdst), self.st))
         else:
             xin = x.t
-        yp = y if (cout_p == cout and not keep) else self.buf((seq, "ypad"), (N, Ho, Wo, cout_p), ydt)
+        # fewer than 16 output channels in fp32 (the RGB image): the epilogue stores the real channels densely (dg_umma_conv2d_fwd_narrow)
+        narrow = self.narrow_store and not keep and cout_p == 16 and cout < 16 and ydt == torch.float32
+        yp = y if ((cout_p == cout and not keep) or narrow) else self.buf((seq, "ypad"), (N, Ho, Wo, cout_p), ydt)
         bias = None
         if b is not None:
             if cout_p == cout:
@@ -390,8 +393,14 @@ class Engine:
         txi, typ = tensor(xin), tensor(yp)
         flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout      # ALGORITHMIC: the zero-padded channels are not counted
         pk = self._packed(w, 0)
-        self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
-            self.ctx, C.byref(txi), pk.data_ptr(), bias, C.byref(typ), C.byref(cp), None, self.st)))
+        if narrow:
+            if bias is None:
+                bias = self._zeros((seq, "bias_p"), (cout_p,), torch.float32).data_ptr()
+            self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd_narrow(
+                self.ctx, C.byref(txi), pk.data_ptr(), bias, C.byref(typ), C.byref(cp), self.st)))
+        else:
+            self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+                self.ctx, C.byref(txi), pk.data_ptr(), bias, C.byref(typ), C.byref(cp), None, self.st)))
         if keep:
             y = yp
         elif yp is not y:

@@ -254,6 +254,10 @@ int dg_umma_pack_weights_padded(dg_ctx*, const float* w, void* packed, int kh, i
                                 int mode, void* stream);
 int dg_unpad_weight_grad(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw, int cin,
                          int cout, int cin_pad, int cout_pad, int accumulate, void* stream);
+/* Conv2D with fewer than 16 output channels (the RGB side, srgan.py:182 / fsrgan.py:217 / autoencoder.py:186), fp32 output:
+ * w_packed / bias_padded are zero-padded to 16 output channels, y is the DENSE [n,h,w,c<16] result (no padded copy, no slice). */
+int dg_umma_conv2d_fwd_narrow(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias_padded, const dg_tensor* y,
+                              const dg_conv_params* p, void* stream);
 /* Physically padded activations (the autoencoder's 44/56/76/100/152/84-channel layers, autoencoder.py:150-186, stay zero-padded
  * to multiples of 16 from layer to layer instead of being padded and sliced around every convolution).  The input-channel axis
  * of a kernel that consumes a U-Net concat of two padded tensors (autoencoder.py:135) consists of TWO padded segments:

@@ -1210,3 +1210,27 @@ def test_depthwise_bf16_tma_tiles(L, C_, H, W):
     assert close(y[..., :C_], torch.relu(ref))
     L.check(lib.dg_dwconv3x3_dgrad(ctx, C.byref(tg), wd.data_ptr(), C.byref(tdx), st))
     assert close(dx, xr.grad)
+
+
+@pytest.mark.parametrize("cout,act", [(3, 3), (1, 4), (5, 0)])
+def test_conv_fwd_narrow_store(L, cout, act):
+    """dg_umma_conv2d_fwd_narrow: a convolution with fewer than 16 output channels (the RGB image, srgan.py:182) computed on the
+    tensor cores with the kernel padded to 16 output channels, the real channels stored densely in fp32 (tanh / sigmoid / none)."""
+    g = torch.Generator().manual_seed(cout)
+    N, H, W, cin, k = 2, 21, 19, 32, 3
+    x = torch.randn(N, H, W, cin, generator=g).bfloat16().double()
+    w = (torch.randn(k, k, cin, cout, generator=g) * 0.1).bfloat16().double(); b = torch.randn(cout, generator=g).double()
+    ref = OT.conv2d(x, w, b, stride=1, padding="same")
+    ref = torch.tanh(ref) if act == 3 else (torch.sigmoid(ref) if act == 4 else ref)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    xd, wd = dev(x, torch.bfloat16), dev(w)
+    bp = torch.zeros(16, device="cuda"); bp[:cout] = b.float().cuda()
+    pk = torch.empty(k * k * cin * 16, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights_padded(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, cin, 16, 0, st))
+    guard = torch.full((N * H * W * cout + 64,), 7.0, device="cuda")
+    y = guard[:N * H * W * cout].view(N, H, W, cout)
+    cp = conv_params(L, k, k, 1, H, W, "same", act)
+    tx, ty = L.tensor(xd), L.tensor(y)
+    L.check(lib.dg_umma_conv2d_fwd_narrow(ctx, C.byref(tx), pk.data_ptr(), bp.data_ptr(), C.byref(ty), C.byref(cp), st))
+    assert relerr(y, ref) < 2e-3                    # fp32 output of bf16 operands: accumulation order only
+    assert (guard[N * H * W * cout:] == 7.0).all()  # nothing written past the dense tensor
