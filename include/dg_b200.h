@@ -268,6 +268,18 @@ int dg_umma_pack_weights_seg(dg_ctx*, const float* w, void* packed, int kh, int 
 int dg_unpad_weight_grad_seg(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw,
                              int cin, int cout, int cin_pad, int cout_pad, int seg_log, int seg_phys, int accumulate, void* stream);
 
+/* ---- training-pair synthesis on the device (dataloader.py:188-229 after load_image): stack_crop (:79-93) -> scale_image =
+ * tf.image.resize(method='bicubic') (:110-124) -> adjust_jpeg_quality = tf.image.adjust_jpeg_quality (:126-140) -> normalize
+ * x*2-1 (:160-178).  src: n_src decoded uint8 images [n_src, src_h, src_w, 3] in DEVICE memory; sample b is the crop x crop
+ * window at (crop_top[b], crop_left[b]) of image crop_index[b] (three DEVICE int arrays of `batch` entries: the random offsets
+ * of tf.image.random_crop are drawn by the caller).  target [batch, crop, crop, 3] and input [batch, crop/scale, crop/scale, 3]
+ * are dense fp32 in [-1, 1].  The JPEG step is libjpeg's baseline round trip (4:2:0, 'islow' DCT, fancy up-sampling) in its own
+ * integer arithmetic, bit-exact against libjpeg-turbo; crop/scale must be a multiple of 16. */
+size_t dg_pair_synthesis_workspace_bytes(int batch, int crop, int scale);
+int dg_pair_synthesis(dg_ctx*, const uint8_t* src, int n_src, int src_h, int src_w, const int* crop_index, const int* crop_top,
+                      const int* crop_left, int batch, int crop, int scale, int jpeg_quality, float* input, float* target,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- frame pre/post-processing around the inference forward (infer_video.py:138-159, infer.py:50-68,
  * unit_test.py:67-86).  src/dst frames are packed uint8 [n, h, w, 3] in DEVICE memory.
  * dg_frame_to_float: centre crop-or-pad (tf.image.resize_with_crop_or_pad, infer_video.py:142) of the frame to
