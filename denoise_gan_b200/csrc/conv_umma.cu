@@ -8,7 +8,8 @@
 //   forward stride 1      : one source (x), taps (r-pad_t, s-pad_l)
 //   forward stride 2      : four parity lattices of x, taps fall on one lattice each
 //   dgrad stride 1        : one source (dy), flipped taps, transposed weight blocks
-//   dgrad stride 2 / Conv2DTranspose forward : four launches, one per output parity phase
+//   dgrad stride 2 / Conv2DTranspose forward : four output parity phases, in ONE launch when their accumulators fit TMEM
+//                                              together (tap_acc / tap_first / ph_off), else one launch per phase
 // A CTA owns an output tile of (16*MT) x 8 pixels.  Per 64/32/16-channel chunk it TMA-loads ONE
 // halo box per source ((16*MT+ext_h) x (8+ext_w) pixels, out-of-image pixels zero-filled by TMA =
 // SAME padding) and every tap's A operand is a row-shifted window of that box: the UMMA shared

@@ -12,8 +12,8 @@
 //     number of pixels, which is simply the descriptor's leading-dimension byte offset (LBO).
 // Every CTA keeps all its [128 x Nblk] accumulators in TMEM (<= 512 columns) across ALL of its
 // pixel tiles and writes one fp32 partial at the end; a second kernel sums the partials in CTA
-// order (deterministic split-K).  The bias gradient is one more accumulator whose A operand is a
-// constant tile of ones.
+// order (deterministic split-K).  The bias gradient is summed by the four epilogue warps (idle until the
+// accumulators are final) straight from the staged dy tiles, one more row of the per-CTA partial.
 // (Tried and dropped in round 1: summing the partials of 4-CTA clusters through distributed shared memory with
 // per-thread st.shared::cluster stores took 20 K cycles per CTA against 12.7 K for the plain per-CTA dump; a bulk-copy
 // version is the follow-up)
