@@ -90,6 +90,8 @@ SIGNATURES = {
     "dg_unpad_weight_grad": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _P]),
     "dg_umma_pack_weights_seg": (_i, [_P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
     "dg_unpad_weight_grad_seg": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "dg_image_summary_workspace_bytes": (_sz, [_i, _i, _i]),
+    "dg_image_summary": (_i, [_P, _T, _T, _i, _P, _P, _sz, _P]),
     "dg_pair_synthesis_workspace_bytes": (_sz, [_i, _i, _i]),
     "dg_pair_synthesis": (_i, [_P, _P, _i, _i, _i, _P, _P, _P, _i, _i, _i, _i, _P, _P, _P, _sz, _P]),
     "dg_frame_to_float": (_i, [_P, _P, _i, _i, _i, _i, _f, _f, _T, _P]),

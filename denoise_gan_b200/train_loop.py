@@ -7,9 +7,11 @@ train_autoencoder.py:114, train_pix2pix.py:73): iterate the dataset, run `train_
 * `LossLogger` copies every step's scalars into a small ring of pinned host buffers and hands them to the writer a few
   steps late, so logging never synchronises the device inside the loop (TensorFlow's eager scalars block on `.numpy()`).
 
-Only the scalar summaries are reproduced; the reference's image / Sobel / total-variation image summaries
-(train_srgan.py:153-172) are diagnostics outside the hot path.  `writer` is anything with
-`add_scalar(tag, value, step)` (the torch / TensorBoard SummaryWriter API), a callable `(tag, value, step)`, or None."""
+The reference's image / Sobel / total-variation image summaries (train_srgan.py:150-172) are produced on request
+(`image_summaries=True`, summaries.py): at a logging iteration the generator runs once more in inference mode and sixteen small
+uint8 images come back -- a diagnostic outside the hot path, the one place where the loop waits for the
+device.  `writer` is anything with `add_scalar(tag, value, step)` (and optionally `add_image`; the torch / TensorBoard
+SummaryWriter API), a callable `(tag, value, step)`, or None."""
 from __future__ import annotations
 
 import torch
@@ -70,7 +72,8 @@ class LossLogger:
         return self.last
 
 
-def train(model, dataset, args, writer=None, *, train_step, tags=SRGAN_TAGS, use_graph: bool = True, lag: int = 4):
+def train(model, dataset, args, writer=None, *, train_step, tags=SRGAN_TAGS, use_graph: bool = True, lag: int = 4,
+          image_summaries: bool = False, image_sink: "list | None" = None):
     """Runs `train_step(model, input, target)` over `dataset` (host or device float32 NHWC batches in [-1, 1], static batch
     shape as the reference's `drop_remainder=True`), logging `tags` every `args.save_iter` iterations.  Returns the last
     step's scalars as floats, in `train_step`'s return order (train_srgan.py:176)."""
@@ -94,5 +97,11 @@ def train(model, dataset, args, writer=None, *, train_step, tags=SRGAN_TAGS, use
             eager_steps += 1
             packed = torch.stack([v.detach().float().reshape(()) for v in out])
         logger.push(model.iterations, packed)
+        if image_summaries and model.iterations % logger.log_iter == 0:
+            from .summaries import training_image_summaries, write_image_summaries
+            images = training_image_summaries(model, x, y)       # eager inference forward between two replays of the step graph
+            write_image_summaries(writer, images, model.iterations)
+            if image_sink is not None:
+                image_sink.append((model.iterations, images))
     last = logger.flush()
     return None if last is None else tuple(last[1])

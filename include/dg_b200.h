@@ -268,6 +268,15 @@ int dg_umma_pack_weights_seg(dg_ctx*, const float* w, void* packed, int kh, int 
 int dg_unpad_weight_grad_seg(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw,
                              int cin, int cout, int cin_pad, int cout_pad, int seg_log, int seg_phys, int accumulate, void* stream);
 
+/* ---- image summaries of the training loop (train_srgan.py:27-59, 153-172): the FIRST image of batch `a` (minus the first image
+ * of `b` when b is not NULL) as uint8 [h', w', c].  kind 0: uint8(255 * clip((x+1)/2, 0, 1)) (tf2image(norm=True)); the others are
+ * auto-scaled to their own range, uint8(255 * (v - min v) / ptp v) (tf2image(norm=False)): 1 x^2, 2 |x|, 3 Sobel magnitude of
+ * renorm(x) (tf.image.sobel_edges, REFLECT padding, /4), 4 / 5 horizontal / vertical differences and 6 total variation
+ * (high_pass_x_y, total_variation: h' = h-1, w' = w-1). */
+size_t dg_image_summary_workspace_bytes(int h, int w, int c);
+int dg_image_summary(dg_ctx*, const dg_tensor* a, const dg_tensor* b, int kind, uint8_t* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* ---- training-pair synthesis on the device (dataloader.py:188-229 after load_image): stack_crop (:79-93) -> scale_image =
  * tf.image.resize(method='bicubic') (:110-124) -> adjust_jpeg_quality = tf.image.adjust_jpeg_quality (:126-140) -> normalize
  * x*2-1 (:160-178).  src: n_src decoded uint8 images [n_src, src_h, src_w, 3] in DEVICE memory; sample b is the crop x crop
