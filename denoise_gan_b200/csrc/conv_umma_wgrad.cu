@@ -36,12 +36,14 @@ constexpr int MAX_TAPS = 16;
 constexpr int MAX_GROUPS = 24;
 constexpr int MAX_ATOMS = 8;
 constexpr int MAX_STAGES = 6;
+constexpr int MAX_PROB = 4;      // layers of identical geometry whose weight gradients share ONE launch (dg_umma_conv2d_wgrad_batch)
 constexpr int WG_THREADS = 192;
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 
 struct WgradParams {
-  CUtensorMap src[MAX_SRC];
-  CUtensorMap dymap;
+  CUtensorMap src[MAX_PROB][MAX_SRC];
+  CUtensorMap dymap[MAX_PROB];
+  int splits;       // CTAs along gridDim.x PER PROBLEM: CTA blockIdx.x works on problem blockIdx.x / splits, pixel split blockIdx.x % splits
   int n_src, kc, kco, nb, n_groups, groups_per_cta, chunks, chunk0;
   int zblocks;      // group blocks along gridDim.z; the rest of gridDim.z enumerates BLOCKS OF CHUNKS (chunk0 += chunks per block)
   int tiles_h, tiles_w, n_img;
@@ -63,6 +65,33 @@ __device__ __forceinline__ void wdbg(const WgradParams& P, int role, int it, int
   if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 16) P.dbg[(role * 16 + it) * 4 + slot] = clock64();
 }
 
+template <int PROB>
+__device__ __forceinline__ void producer_loop(const WgradParams& P, int bx, int xstep, int total_tiles, uint32_t base, int nb0, int chunk0,
+                                              uint64_t* bar_full, uint64_t* bar_empty) {
+  for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[PROB][s]);
+  tma_prefetch_desc(&P.dymap[PROB]);
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = bx; tile < total_tiles; tile += xstep) {
+    int tw = tile % P.tiles_w;
+    int t2 = tile / P.tiles_w;
+    int th = t2 % P.tiles_h;
+    int n = t2 / P.tiles_h;
+    const int h0 = th * 16, w0 = tw * 8;
+    const uint32_t full = smem_u32(&bar_full[stage]);
+    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+    mbar_expect_tx(full, P.stage_tx);
+    const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
+    for (int s = 0; s < P.n_src; ++s)
+      for (int c = 0; c < P.chunks; ++c)
+        tma_load_4d(sa + P.src_off[s] + (uint32_t)c * P.chunk_bytes[s], &P.src[PROB][s], full, (chunk0 + c) * P.kc,
+                    w0 + P.src_w0[s], h0 + P.src_h0[s], n);
+    for (int a = 0; a < P.nb / P.kco; ++a)
+      tma_load_4d(sa + P.dy_off + (uint32_t)a * P.dy_atom_bytes, &P.dymap[PROB], full, nb0 + a * P.kco, w0, h0, n);
+    if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+  }
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_done;
@@ -73,6 +102,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const int nb0 = blockIdx.y * P.nb;
+  const int prob = (int)blockIdx.x / P.splits, bx = (int)blockIdx.x - prob * P.splits, xstep = P.splits;
   const int cblk = (int)blockIdx.z / P.zblocks;              // block of input-channel chunks handled by this CTA
   const int chunk0 = P.chunk0 + cblk * P.chunks;
   const int dst_shift = cblk * P.chunks * P.kc;              // its rows of dW
@@ -101,27 +131,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
-      tma_prefetch_desc(&P.dymap);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int tw = tile % P.tiles_w;
-        int t2 = tile / P.tiles_w;
-        int th = t2 % P.tiles_h;
-        int n = t2 / P.tiles_h;
-        const int h0 = th * 16, w0 = tw * 8;
-        const uint32_t full = smem_u32(&bar_full[stage]);
-        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-        mbar_expect_tx(full, P.stage_tx);
-        const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
-        for (int s = 0; s < P.n_src; ++s)
-          for (int c = 0; c < P.chunks; ++c)
-            tma_load_4d(sa + P.src_off[s] + (uint32_t)c * P.chunk_bytes[s], &P.src[s], full, (chunk0 + c) * P.kc,
-                        w0 + P.src_w0[s], h0 + P.src_h0[s], n);
-        for (int a = 0; a < P.nb / P.kco; ++a)
-          tma_load_4d(sa + P.dy_off + (uint32_t)a * P.dy_atom_bytes, &P.dymap, full, nb0 + a * P.kco, w0, h0, n);
-        if (++stage == P.n_stages) { stage = 0; phase ^= 1u; }
+      // The tensor maps of this CTA's problem must sit at COMPILE-TIME offsets of the parameter block: with a run-time index the
+      // issuing thread pays a 64-bit address computation and a move into a uniform register for every TMA instruction (16 % on
+      // the many-box stride-2 layers of pix2pix) -- hence one instance of the loop per problem.
+      switch (prob) {
+        case 1: producer_loop<1>(P, bx, xstep, total_tiles, base, nb0, chunk0, bar_full, bar_empty); break;
+        case 2: producer_loop<2>(P, bx, xstep, total_tiles, base, nb0, chunk0, bar_full, bar_empty); break;
+        case 3: producer_loop<3>(P, bx, xstep, total_tiles, base, nb0, chunk0, bar_full, bar_empty); break;
+        default: producer_loop<0>(P, bx, xstep, total_tiles, base, nb0, chunk0, bar_full, bar_empty); break;
       }
     }
   } else if (warp == 1) {
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       uint32_t phase = 0;
       uint32_t first = 1;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = bx; tile < total_tiles; tile += xstep, ++it) {
         if (lane == 0) wdbg(P, 1, it, 0);
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
@@ -187,7 +204,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
       const uint32_t col_off = P.dy_off + (uint32_t)atom_i * P.dy_atom_bytes + (uint32_t)cc * 2u;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = bx; tile < total_tiles; tile += xstep) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         if (b_active) {
           const uint32_t sa = base + (uint32_t)stage * P.stage_bytes;
@@ -295,12 +312,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) umma_wgrad_kernel(const __grid_
 
 // dst[i] (+)= sum_s part[s][i] over the [dw | dbias] rows of the per-CTA partials (fixed order, deterministic).
 // Block = 32 float4 columns x 8 groups of splits; every thread keeps eight independent 16-byte loads in flight.
+struct ReduceOut {      // one output per problem of a batched launch (blockIdx.y)
+  float* dw[MAX_PROB];
+  float* dbias[MAX_PROB];
+  int acc[MAX_PROB];
+};
+
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ part, long part_stride, int splits, float* __restrict__ dw, long n_dw,
-                    float* __restrict__ dbias, int n_bias, int accumulate) {
+wgrad_reduce_kernel(const float* __restrict__ part, long part_stride, int splits, const __grid_constant__ ReduceOut ro, long n_dw, int n_bias) {
   __shared__ float4 sm[8][32];
   pdl_trigger();
   pdl_wait();
+  part += (long)blockIdx.y * splits * part_stride;
+  float* __restrict__ dw = ro.dw[blockIdx.y];
+  float* __restrict__ dbias = ro.dbias[blockIdx.y];
+  const int accumulate = ro.acc[blockIdx.y];
   const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
   const long col = (long)blockIdx.x * 32 + e;          // float4 column
   const long total4 = (n_dw + n_bias) >> 2;
@@ -492,19 +518,40 @@ extern "C" size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const
   return (size_t)splits * per * sizeof(float);
 }
 
-extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias,
-                                    const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
-  const char* name = "dg_umma_conv2d_wgrad";
+// Weight gradients of `n` layers of IDENTICAL geometry in one launch (n = 1: the plain call).  The SMs are divided among the
+// problems (splits = SMs / n pixel splits each), so every CTA walks n times as many tiles and the fixed costs of a launch --
+// prologue, the dump of one 147 KB fp32 partial per CTA (12.9 K of a trunk layer's 34 K cycles, profiles/wgrad_timeline_r2.log),
+// the partial reduce -- are paid once per n layers.  `merged`: all problems accumulate into the SAME dW (the discriminator's
+// real and fake passes, train_srgan.py:78-79): one reduction over all n x splits partials.
+static int wgrad_impl(const char* name, dg_ctx* ctx, int n, const dg_tensor* const* xs, const dg_tensor* const* dys, float* const* dws,
+                      float* const* dbiases, const dg_conv_params* p, const int* accumulates, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  const dg_tensor *x = xs[0], *dy = dys[0];
+  float* dw = dws[0];
+  float* dbias = dbiases ? dbiases[0] : nullptr;
+  bool merged = n > 1;
+  for (int i = 1; i < n; ++i) merged = merged && dws[i] == dws[0];
   Plan pl;
-  if (make_plan(name, ctx->sm_count < 160 ? ctx->sm_count : 160, x, dy, p, dbias != nullptr, &pl)) return 1;
+  const int sms = ctx->sm_count < 160 ? ctx->sm_count : 160;
+  if (make_plan(name, sms / n, x, dy, p, dbias != nullptr, &pl)) return 1;
   DG_REQUIRE(dw && workspace, "%s: null output/workspace", name);
-  DG_REQUIRE(x->cpitch % 8 == 0 && x->coff % 8 == 0 && dy->cpitch % 8 == 0 && dy->coff % 8 == 0 &&
-                 ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)dy->ptr % 16) == 0, "%s: views not 16-byte aligned", name);
+  for (int i = 0; i < n; ++i) {
+    const dg_tensor *xi = xs[i], *di = dys[i];
+    DG_REQUIRE(dg_valid(xi) && dg_valid(di) && dws[i], "%s: null argument (problem %d)", name, i);
+    DG_REQUIRE(dg_same_shape(xi, x) && dg_same_shape(di, dy) && xi->dtype == x->dtype && di->dtype == dy->dtype &&
+                   ((dbiases && dbiases[i]) != 0) == (dbias != nullptr), "%s: problem %d differs in geometry from problem 0", name, i);
+    DG_REQUIRE(xi->cpitch % 8 == 0 && xi->coff % 8 == 0 && di->cpitch % 8 == 0 && di->coff % 8 == 0 &&
+                   ((uintptr_t)xi->ptr % 16) == 0 && ((uintptr_t)di->ptr % 16) == 0, "%s: views not 16-byte aligned", name);
+    for (int j = 0; j < i && !merged; ++j) DG_REQUIRE(dws[j] != dws[i], "%s: problems must write distinct gradients (or all the same one)", name);
+  }
+  if (n > 1) {
+    const int atoms0 = 128 / pl.kc, cpl0 = pl.n_chunks < atoms0 ? pl.n_chunks : atoms0;
+    DG_REQUIRE(!pl.src_split && (pl.n_chunks <= cpl0 || pl.cblocks > 1), "%s: this layer needs several launches and cannot be batched", name);
+  }
   const int cin = x->c, cout = dy->c, kc = pl.kc, kco = pl.kco;
   const long n_dw = (long)pl.n_taps * cin * cout;
   const long part_stride = n_dw + cout;
-  DG_REQUIRE(workspace_bytes >= (size_t)pl.splits * part_stride * sizeof(float), "%s: workspace too small", name);
+  DG_REQUIRE(workspace_bytes >= (size_t)n * pl.splits * part_stride * sizeof(float), "%s: workspace too small", name);
   cudaStream_t st = (cudaStream_t)stream;
 
   // halo extents per source
@@ -533,6 +580,7 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
     const int chunks = (pl.n_chunks - chunk0) < chunks_per_launch ? (pl.n_chunks - chunk0) : chunks_per_launch;
     WgradParams P;
     memset(&P, 0, sizeof(P));
+    P.splits = pl.splits;
     P.n_src = ssel < 0 ? pl.n_src : 1; P.kc = kc; P.kco = kco; P.nb = pl.nb; P.chunks = chunks; P.chunk0 = chunk0;
     P.tiles_h = (dy->h + 15) / 16; P.tiles_w = (dy->w + 7) / 8; P.n_img = dy->n;
     P.cout_total = cout; P.part = (float*)workspace; P.part_stride = part_stride; P.bias_off = n_dw;
@@ -555,8 +603,12 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
       uint64_t strides[3] = {(uint64_t)x->cpitch * 2 * L.step, (uint64_t)x->cpitch * 2 * x->w * L.step,
                              (uint64_t)x->cpitch * 2 * x->w * x->h};
       uint32_t box[4] = {(uint32_t)kc, (uint32_t)WW, (uint32_t)HH, 1};
-      char* ptr = (char*)x->ptr + ((size_t)x->coff + ((size_t)L.h_first * x->w + L.w_first) * x->cpitch) * 2;
-      if (encode4(ctx, &P.src[si], ptr, dims, strides, box, kc)) return 1;
+      for (int pr = 0; pr < n; ++pr) {
+        const dg_tensor* xp = xs[pr];
+        uint64_t st_p[3] = {(uint64_t)xp->cpitch * 2 * L.step, (uint64_t)xp->cpitch * 2 * xp->w * L.step, (uint64_t)xp->cpitch * 2 * xp->w * xp->h};
+        char* ptr = (char*)xp->ptr + ((size_t)xp->coff + ((size_t)L.h_first * xp->w + L.w_first) * xp->cpitch) * 2;
+        if (encode4(ctx, &P.src[pr][si], ptr, dims, st_p, box, kc)) return 1;
+      }
       P.src_h0[si] = dh_min[s]; P.src_w0[si] = dw_min[s];
       uint32_t hb = (uint32_t)HH * WW * kc * 2;
       P.chunk_bytes[si] = (hb + 1023u) & ~1023u;
@@ -570,8 +622,11 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
       uint64_t dims[4] = {(uint64_t)dy->c, (uint64_t)dy->w, (uint64_t)dy->h, (uint64_t)dy->n};
       uint64_t strides[3] = {(uint64_t)dy->cpitch * 2, (uint64_t)dy->cpitch * 2 * dy->w, (uint64_t)dy->cpitch * 2 * dy->w * dy->h};
       uint32_t box[4] = {(uint32_t)kco, 8, 16, 1};
-      char* ptr = (char*)dy->ptr + (size_t)dy->coff * 2;
-      if (encode4(ctx, &P.dymap, ptr, dims, strides, box, kco)) return 1;
+      for (int pr = 0; pr < n; ++pr) {
+        const dg_tensor* dp = dys[pr];
+        uint64_t st_p[3] = {(uint64_t)dp->cpitch * 2, (uint64_t)dp->cpitch * 2 * dp->w, (uint64_t)dp->cpitch * 2 * dp->w * dp->h};
+        if (encode4(ctx, &P.dymap[pr], (char*)dp->ptr + (size_t)dp->coff * 2, dims, st_p, box, kco)) return 1;
+      }
       P.dy_off = off;
       P.dy_atom_bytes = 128u * kco * 2;
       off += P.dy_atom_bytes * (pl.nb / kco);
@@ -643,15 +698,41 @@ extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_te
       P.dump_cw = (!dbg_direct && (size_t)4 * 32 * (cw + 4) * sizeof(float) <= (size_t)n_stages * P.stage_bytes) ? cw : 0;
     }
     const uint32_t smem = P.ones_off + ones_bytes + slack + 1024;
-    dim3 grid(pl.splits, pl.yblocks, zblocks * pl.cblocks);
+    dim3 grid(n * pl.splits, pl.yblocks, zblocks * pl.cblocks);
     dg_pdl_launch(umma_wgrad_kernel, grid, dim3(WG_THREADS), smem, st, P);
     DG_CHECK_LAUNCH(name);
   }
   const long total = n_dw + (dbias ? cout : 0);
   DG_REQUIRE(n_dw % 4 == 0 && total % 4 == 0 && part_stride % 4 == 0 && ((uintptr_t)dw % 16) == 0 && (!dbias || ((uintptr_t)dbias % 16) == 0),
              "dg_umma_conv2d_wgrad: gradient buffers must be 16-byte aligned");
-  dg_pdl_launch(wgrad_reduce_kernel, dim3((unsigned)((total / 4 + 31) / 32)), dim3(256), 0, st, (const float*)workspace, part_stride,
-                pl.splits, dw, n_dw, dbias, dbias ? cout : 0, accumulate);
+  ReduceOut ro;
+  memset(&ro, 0, sizeof(ro));
+  const int n_out = merged ? 1 : n;
+  for (int i = 0; i < n_out; ++i) { ro.dw[i] = dws[i]; ro.dbias[i] = dbiases ? dbiases[i] : nullptr; ro.acc[i] = accumulates[i]; }
+  for (int i = 0; i < n_out; ++i)
+    DG_REQUIRE(((uintptr_t)ro.dw[i] % 16) == 0 && (!ro.dbias[i] || ((uintptr_t)ro.dbias[i] % 16) == 0), "%s: gradient buffers must be 16-byte aligned", name);
+  dg_pdl_launch(wgrad_reduce_kernel, dim3((unsigned)((total / 4 + 31) / 32), (unsigned)n_out), dim3(256), 0, st, (const float*)workspace, part_stride,
+                merged ? n * pl.splits : pl.splits, ro, n_dw, dbias ? cout : 0);
   DG_CHECK_LAUNCH("dg_umma_conv2d_wgrad(reduce)");
   return 0;
+}
+
+extern "C" int dg_umma_conv2d_wgrad(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias,
+                                    const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(dy) && p, "dg_umma_conv2d_wgrad: null argument");
+  return wgrad_impl("dg_umma_conv2d_wgrad", ctx, 1, &x, &dy, &dw, &dbias, p, &accumulate, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t dg_umma_conv2d_wgrad_batch_workspace_bytes(int n, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
+  if (n < 1 || n > MAX_PROB) return 0;
+  // n x splits(SMs / n) partials; for small maps the split count is capped by the tile count, not by the SMs: n times the bound of one problem
+  return (size_t)n * dg_umma_conv2d_wgrad_workspace_bytes(x, dy, p);
+}
+
+extern "C" int dg_umma_conv2d_wgrad_batch(dg_ctx* ctx, int n, const dg_tensor* const* x, const dg_tensor* const* dy, float* const* dw,
+                                          float* const* dbias, const dg_conv_params* p, const int* accumulate, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(n >= 1 && n <= MAX_PROB && x && dy && dw && accumulate && p, "dg_umma_conv2d_wgrad_batch: bad argument (1 <= n <= %d)", MAX_PROB);
+  return wgrad_impl("dg_umma_conv2d_wgrad_batch", ctx, n, x, dy, dw, dbias, p, accumulate, workspace, workspace_bytes, stream);
 }

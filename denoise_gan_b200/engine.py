@@ -54,10 +54,11 @@ class Var:
 
 
 class Node:
-    __slots__ = ("seq", "inputs", "out", "group", "bwd", "fusable", "params")
+    __slots__ = ("seq", "inputs", "out", "group", "bwd", "fusable", "params", "wkey")
 
-    def __init__(self, seq, inputs, out, group, bwd, fusable=False, params=()):
+    def __init__(self, seq, inputs, out, group, bwd, fusable=False, params=(), wkey=None):
         self.seq, self.inputs, self.out, self.group, self.bwd = seq, inputs, out, group, bwd
+        self.wkey = wkey          # geometry key of the node's weight gradient (Engine._wgrad_enqueue), None: not a batchable convolution
         self.params = tuple(q for q in params if q is not None)   # variables whose gradient slice this node's bwd writes
         self.fusable = fusable    # bwd accepts fctx= (fused skip-add / BatchNorm-backward sums in the dgrad epilogue)
 
@@ -132,6 +133,16 @@ class Engine:
         self.phys_pad = os.environ.get("DG_PHYS_PAD", "1") != "0"
         self.fold_relu_bwd = os.environ.get("DG_FOLD_RELU_BWD", "1") != "0"    # see Var.n_mask
         self.narrow_store = os.environ.get("DG_NARROW_STORE", "1") != "0"
+        # weight gradients of layers with identical geometry (the generator trunk's 32 identical convolutions, the real / fake passes of
+        # one discriminator layer) are collected during backward() and launched up to `wgrad_batch` at a time (dg_umma_conv2d_wgrad_batch)
+        self.wgrad_batch = max(1, min(4, int(os.environ.get("DG_WGRAD_BATCH", "4"))))
+        self._wq: dict = {}             # geometry key -> [(x, dy, w, b, acc, flops, lin)]
+        self._wq_names: set = set()     # parameters with a queued weight gradient
+        self._complete_wait: set = set()
+        self._in_backward = False
+        self._bwd_tag = None
+        self._wq_seen: dict = {}        # geometry key -> weight gradients seen so far in the current backward()
+        self._wq_expect: dict = {}      # geometry key -> convolutions of that geometry on the tape whose variables the current backward() differentiates
         self.fold_bn_infer = os.environ.get("DG_FOLD_BN", "1") != "0"      # inference: BatchNorm folded into the producing conv / depthwise conv
         self._folded: dict = {}
         self.small_map_gemm = os.environ.get("DG_SMALL_MAP_GEMM", "1") != "0"      # weight gradients of <= 8x8 maps as one dense product (dg_im2col)   # dg_bn_act_fwd_from_partials instead of finalize + apply
@@ -233,13 +244,13 @@ class Engine:
         self.seq += 1
         return self.seq
 
-    def _push(self, inputs, out: Var, group, bwd, fusable=False, params=(), masks=()):
+    def _push(self, inputs, out: Var, group, bwd, fusable=False, params=(), masks=(), wkey=None):
         """`masks`: the inputs whose gradient this node returns already multiplied by (input > 0)."""
         for v in inputs:
             v.n_cons += 1
         for v in masks:
             v.n_mask += 1
-        self.tape.append(Node(out.seq, inputs, out, group, bwd, fusable, params))
+        self.tape.append(Node(out.seq, inputs, out, group, bwd, fusable, params, wkey))
 
     def _relu_bwd_folded(self, out: Var, act) -> bool:
         """True when every consumer of this ReLU convolution's output returns a gradient that already carries the ReLU mask."""
@@ -648,7 +659,8 @@ class Engine:
                         self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
             return [dx]
 
-        self._push([x], out, w.group, bwd, fusable=True, params=(w, b))
+        self._push([x], out, w.group, bwd, fusable=True, params=(w, b),
+                   wkey=(tuple(x.shape), tuple(y.shape), kh, kw, stride, pt, pl, b is None))
         return out
 
     def _wgrad(self, x: torch.Tensor, dy: torch.Tensor, w: Param, b: Param | None, lin: DgConvParams, flops: float = 0.0):
@@ -682,6 +694,9 @@ class Engine:
             nbytes = self.lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx), C.byref(tdy), C.byref(lin))
         else:
             nbytes = 0
+        if nbytes > 0 and self.wgrad_batch > 1 and self._in_backward and self._wgrad_batchable(tx, tdy, lin):
+            self._wgrad_enqueue(x, dy, w, b, acc, flops, lin)
+            return
         if nbytes > 0:     # 0 = the tensor-core wgrad has no tile configuration for this layer
             ws = self.workspace(nbytes)
             self._timed("umma_wgrad", flops, lambda: check(self.lib.dg_umma_conv2d_wgrad(
@@ -691,6 +706,65 @@ class Engine:
             ws = self.workspace(nbytes)
             self._timed("simt_wgrad", flops, lambda: check(self.lib.dg_conv2d_wgrad(
                 self.ctx, C.byref(tx), C.byref(tdy), w.grad.data_ptr(), dbias, C.byref(lin), acc, ws.data_ptr(), nbytes, self.st)))
+
+    # ---- weight gradients of identical layers, several per launch
+    def _wgrad_batchable(self, tx, tdy, lin) -> bool:
+        key = ("wgb", tx.n, tx.h, tx.w, tx.c, tdy.h, tdy.w, tdy.c, lin.kh, lin.kw, lin.stride, lin.pad_t, lin.pad_l)
+        ok = self._cap.get(key)
+        if ok is None:
+            ok = self.lib.dg_umma_conv2d_wgrad_batch_workspace_bytes(2, C.byref(tx), C.byref(tdy), C.byref(lin)) > 0 and lin.stride == 1 and tx.c <= 128
+            self._cap[key] = ok
+        return ok
+
+    def _wgrad_enqueue(self, x, dy, w, b, acc, flops, lin):
+        key = (tuple(x.shape), tuple(dy.shape), lin.kh, lin.kw, lin.stride, lin.pad_t, lin.pad_l, b is None)
+        q = self._wq.get(key)
+        if q:
+            merged = all(e[2] is q[0][2] for e in q)
+            dup = any(e[2] is w for e in q)
+            if (merged and len(q) > 1 and not dup) or (dup and not merged):
+                self._wgrad_flush(key)          # keeps "all the same gradient" and "all distinct gradients" groups apart, and the write order per parameter
+                q = None
+        if not q:
+            q = self._wq[key] = []
+        q.append((x, dy, w, b, acc, flops, lin))
+        self._wq_names.add(w.name)
+        if b is not None:
+            self._wq_names.add(b.name)
+        # a group is launched when it is full or when no partner is left to come: backward() counted the convolutions of every
+        # geometry on the tape beforehand, so a layer without partners is never held back to the end of the pass
+        seen = self._wq_seen[key] = self._wq_seen.get(key, 0) + 1
+        left = self._wq_expect.get(key, 0) - seen
+        if len(q) >= self.wgrad_batch or left <= 0:
+            self._wgrad_flush(key)
+
+    def _wgrad_flush(self, key=None):
+        """Launches the queued weight gradients of one geometry (or of all): one dg_umma_conv2d_wgrad_batch per group."""
+        keys = [key] if key is not None else list(self._wq)
+        for k in keys:
+            q = self._wq.pop(k, None)
+            if not q:
+                continue
+            with self._side():
+                n = len(q)
+                lin = q[0][6]
+                tens = [(tensor(e[0]), tensor(e[1])) for e in q]
+                xs = (C.POINTER(_lib.DgTensor) * n)(*[C.pointer(t[0]) for t in tens])
+                dys = (C.POINTER(_lib.DgTensor) * n)(*[C.pointer(t[1]) for t in tens])
+                dws = (C.c_void_p * n)(*[e[2].grad.data_ptr() for e in q])
+                dbs = (C.c_void_p * n)(*[(e[3].grad.data_ptr() if e[3] is not None else None) for e in q])
+                accs = (C.c_int * n)(*[int(e[4]) for e in q])
+                nbytes = self.lib.dg_umma_conv2d_wgrad_batch_workspace_bytes(n, C.byref(tens[0][0]), C.byref(tens[0][1]), C.byref(lin))
+                ws = self.workspace(nbytes)
+                self._timed("umma_wgrad", sum(e[5] for e in q), lambda: check(self.lib.dg_umma_conv2d_wgrad_batch(
+                    self.ctx, n, xs, dys, dws, dbs if q[0][3] is not None else None, C.byref(lin), accs, ws.data_ptr(), nbytes, self.st)))
+            for e in q:
+                for prm in (e[2], e[3]):
+                    if prm is not None:
+                        self._wq_names.discard(prm.name)
+                        if prm.name in self._complete_wait:
+                            self._complete_wait.discard(prm.name)
+                            self.complete.add(prm.name)
 
     def conv2d_transpose(self, x: Var, w: Param, b: Param | None = None, *, stride=2, act=None, alpha=0.0,
                          out_dtype=None) -> Var:
@@ -1258,6 +1332,14 @@ class Engine:
                 for q in node.params:
                     pending[q.name] = pending.get(q.name, 0) + 1
         self.complete = set()
+        self._complete_wait = set()
+        self._in_backward = True
+        self._bwd_tag = tag
+        self._wq_seen = {}
+        self._wq_expect = {}
+        for node in self.tape:
+            if node.group == group and node.wkey is not None:
+                self._wq_expect[node.wkey] = self._wq_expect.get(node.wkey, 0) + 1
         remaining: dict = {}
         fuse = self.fuse_dgrad_bn_bwd and self.use_umma
         if fuse:
@@ -1296,10 +1378,13 @@ class Engine:
                 for q in node.params:
                     pending[q.name] -= 1
                     if pending[q.name] == 0:
-                        self.complete.add(q.name)
+                        # a gradient still sitting in the batching queue becomes complete when its group is launched
+                        (self._complete_wait if q.name in self._wq_names else self.complete).add(q.name)
             if on_node is not None and ent is not None:
                 on_node()
         self._bwd_part = {k: v for k, v in self._bwd_part.items() if k[1] != tag}
+        self._in_backward = False
+        self._wgrad_flush()
         self._join_side()
 
     # ------------------------------------------------------------------ optimiser

@@ -163,6 +163,15 @@ size_t dg_umma_conv2d_wgrad_workspace_bytes(const dg_tensor* x, const dg_tensor*
 int dg_umma_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw_hwio, float* dbias,
                          const dg_conv_params* p, int accumulate, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* The same for n <= 4 layers of IDENTICAL geometry in ONE launch (the 32 identical 64->64 convolutions of the generator trunk,
+ * srgan.py:161-172; the real and fake passes of one discriminator layer, train_srgan.py:78-79): the SMs are divided among the
+ * problems and the fixed costs of a launch (prologue, one fp32 partial per CTA, the partial reduce) are paid once per n layers.
+ * x[i] / dy[i] / dw[i] / dbias[i] / accumulate[i] describe problem i; the dw pointers are either all distinct or all the same
+ * (then the n gradients are summed into it, accumulate[0] decides whether on top of its previous content). */
+size_t dg_umma_conv2d_wgrad_batch_workspace_bytes(int n, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
+int dg_umma_conv2d_wgrad_batch(dg_ctx*, int n, const dg_tensor* const* x, const dg_tensor* const* dy, float* const* dw,
+                               float* const* dbias, const dg_conv_params* p, const int* accumulate, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* ---- depthwise 3x3 s1 SAME (fsrgan.py:149-154) */
 int dg_dwconv3x3_fwd(dg_ctx*, const dg_tensor* x, const float* w, const float* bias, const dg_tensor* y, void* stream);

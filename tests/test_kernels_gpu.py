@@ -1234,3 +1234,49 @@ def test_conv_fwd_narrow_store(L, cout, act):
     L.check(lib.dg_umma_conv2d_fwd_narrow(ctx, C.byref(tx), pk.data_ptr(), bp.data_ptr(), C.byref(ty), C.byref(cp), st))
     assert relerr(y, ref) < 2e-3                    # fp32 output of bf16 operands: accumulation order only
     assert (guard[N * H * W * cout:] == 7.0).all()  # nothing written past the dense tensor
+
+
+@pytest.mark.parametrize("case", [(3, 64, 64, 2, 40, 24, False, 4), (3, 64, 64, 1, 96, 96, False, 3), (3, 32, 48, 2, 24, 24, True, 2),
+                                  (1, 64, 16, 1, 48, 40, True, 4)])
+@pytest.mark.parametrize("merged", [False, True])
+def test_umma_wgrad_batch(L, case, merged):
+    """dg_umma_conv2d_wgrad_batch: the weight gradients of n layers of identical geometry in one launch, the SMs divided among the
+    problems -- distinct outputs (the generator trunk's identical convolutions, srgan.py:161-172) and one shared output (the real and
+    fake passes of a discriminator layer, train_srgan.py:78-79), with and without a previous content to accumulate on."""
+    k, cin, cout, N, H, W, bias, n = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same")
+    xs, gys, refs_w, refs_b = [], [], [], []
+    for i in range(n):
+        x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+        w = torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64).requires_grad_(True)
+        b = torch.randn(cout, generator=g, dtype=torch.float64).requires_grad_(True)
+        y_ref = OT.conv2d(x, w, b, stride=1, padding="same")
+        gy = _bf16_round(torch.randn(y_ref.shape, generator=g, dtype=torch.float64))
+        (y_ref * gy).sum().backward()
+        xs.append(dev(x, torch.bfloat16)); gys.append(dev(gy, torch.bfloat16)); refs_w.append(w.grad); refs_b.append(b.grad)
+    tens = [(L.tensor(a), L.tensor(b_)) for a, b_ in zip(xs, gys)]
+    nb = lib.dg_umma_conv2d_wgrad_batch_workspace_bytes(n, C.byref(tens[0][0]), C.byref(tens[0][1]), C.byref(cp))
+    assert nb > 0
+    wk = ws(nb)
+    n_out = 1 if merged else n
+    dws = [torch.full((k, k, cin, cout), 0.5, device="cuda") for _ in range(n_out)]
+    dbs = [torch.full((cout,), 0.25, device="cuda") for _ in range(n_out)]
+    for acc in (0, 1):
+        px = (C.POINTER(L.DgTensor) * n)(*[C.pointer(t[0]) for t in tens])
+        pd = (C.POINTER(L.DgTensor) * n)(*[C.pointer(t[1]) for t in tens])
+        pw = (C.c_void_p * n)(*[dws[0 if merged else i].data_ptr() for i in range(n)])
+        pb = (C.c_void_p * n)(*[dbs[0 if merged else i].data_ptr() for i in range(n)])
+        pa = (C.c_int * n)(*([acc] * n))
+        L.check(lib.dg_umma_conv2d_wgrad_batch(ctx, n, px, pd, pw, pb if bias else None, C.byref(cp), pa, wk.data_ptr(), nb, st))
+        torch.cuda.synchronize()
+        if merged:
+            assert relerr(dws[0], (acc + 1) * sum(refs_w)) < 1e-4
+            if bias:
+                assert relerr(dbs[0], (acc + 1) * sum(refs_b)) < 1e-4
+        else:
+            for i in range(n):
+                assert relerr(dws[i], (acc + 1) * refs_w[i]) < 1e-4, (i, acc)
+                if bias:
+                    assert relerr(dbs[i], (acc + 1) * refs_b[i]) < 1e-4, (i, acc)
