@@ -21,6 +21,7 @@ CASES = {
     "body_fwd": ("fwd", 16, 96, 96, 64, 64, 3, 1),
     "body_dgrad": ("dgrad", 16, 96, 96, 64, 64, 3, 1),
     "body_wgrad": ("wgrad", 16, 96, 96, 64, 64, 3, 1),
+    "body_wgrad_x4": ("wgrad4", 16, 96, 96, 64, 64, 3, 1),      # four trunk layers per launch (dg_umma_conv2d_wgrad_batch): us is per LAYER
     "up1_fwd": ("fwd", 16, 96, 96, 64, 256, 3, 1),
     "up2_fwd": ("fwd", 16, 192, 192, 64, 256, 3, 1),
     "up2_dgrad": ("dgrad", 16, 192, 192, 64, 256, 3, 1),
@@ -78,6 +79,9 @@ def main():
         tx0, ty0 = L.tensor(xs[0]), L.tensor(ys[0])
         nb = lib.dg_umma_conv2d_wgrad_workspace_bytes(C.byref(tx0), C.byref(ty0), C.byref(cp))
         wk = torch.empty(max(nb, 16), dtype=torch.uint8, device="cuda")
+        if kind == "wgrad4":
+            dw4 = [torch.empty_like(w) for _ in range(4)]
+            wk4 = torch.empty(max(lib.dg_umma_conv2d_wgrad_batch_workspace_bytes(4, C.byref(tx0), C.byref(ty0), C.byref(cp)), 16), dtype=torch.uint8, device="cuda")
 
         def run(i):
             tx, ty = L.tensor(xs[i % args.sets]), L.tensor(ys[i % args.sets])
@@ -85,6 +89,11 @@ def main():
                 L.check(lib.dg_umma_conv2d_fwd(ctx, C.byref(tx), pk0.data_ptr(), None, C.byref(ty), C.byref(cp), None, L.stream_ptr()))
             elif kind == "dgrad":
                 L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(ty), pk1.data_ptr(), None, C.byref(tx), C.byref(cp), L.stream_ptr()))
+            elif kind == "wgrad4":
+                tt = [(L.tensor(xs[(i + j) % args.sets]), L.tensor(ys[(i + j) % args.sets])) for j in range(4)]
+                px = (C.POINTER(L.DgTensor) * 4)(*[C.pointer(t[0]) for t in tt]); pd = (C.POINTER(L.DgTensor) * 4)(*[C.pointer(t[1]) for t in tt])
+                pw = (C.c_void_p * 4)(*[d.data_ptr() for d in dw4]); pa = (C.c_int * 4)(0, 0, 0, 0)
+                L.check(lib.dg_umma_conv2d_wgrad_batch(ctx, 4, px, pd, pw, None, C.byref(cp), pa, wk4.data_ptr(), wk4.numel(), L.stream_ptr()))
             else:
                 L.check(lib.dg_umma_conv2d_wgrad(ctx, C.byref(tx), C.byref(ty), dw.data_ptr(), None if os.environ.get('DG_BENCH_NO_DB') else db.data_ptr(), C.byref(cp), 0, wk.data_ptr(), nb, L.stream_ptr()))
 
@@ -114,6 +123,8 @@ def main():
                 run(i)
             e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / args.iters
+        if kind == "wgrad4":
+            us /= 4
         flops = 2.0 * N * Ho * Wo * k * k * cin * cout
         byts = 2.0 * N * (H * W * cin + Ho * Wo * cout)
         print(json.dumps({"case": name, "us": round(us, 2), "tflops": round(flops / us / 1e6, 1), "frac_of_bf16_peak": round(flops / us / 1e6 / peak, 3),
