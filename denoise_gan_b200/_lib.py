@@ -75,6 +75,7 @@ SIGNATURES = {
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_umma_conv2d_dgrad_fused": (_i, [_P, _T, _P, _T, _CP, _T, C.POINTER(DgBnBwdStats), _P]),
     "dg_umma_conv2d_dgrad_fused_blocks": (_i, [_P, _T, _T, _CP]),
+    "dg_umma_conv2d_dgrad_relu_mask": (_i, [_P, _T, _P, _T, _CP, _T, _P]),
     "dg_bn_bwd_dx_from_partials": (_i, [_P, _T, _T, _P, _P, _P, _P, _P, _i, _f, _P, _i, _T, _P, _P, _i, _P]),
     "dg_umma_conv2d_fwd_supported": (_i, [_P, _T, _T, _CP]),
     "dg_umma_conv2d_fwd_bn_blocks": (_i, [_P, _T, _T, _CP]),

@@ -109,6 +109,8 @@ struct UmmaConvParams {
   //   * accumulates from the rounded g the two per-channel sums of the BatchNorm backward pass, sum g' and sum g' yb
   //     with g' = g * act'(scale * yb + shift), into the per-CTA rows `bn_partials` ([gridDim.x][2][Cout]),
   // so that the BatchNorm backward pass is ONE read of g and yb (dg_bn_bwd_dx_from_partials) instead of two.
+  int bwd_mask;                    // 1: yb is the output of a ReLU convolution (no BatchNorm): g is STORED multiplied by (yb > 0) and no sums
+                                   // are produced -- the ReLU backward of a conv -> conv chain folded into this launch (autoencoder.py:95-104)
   int bwd_am;                      // -1: no statistics; 0 none / 1 relu / 2 leaky relu: activation behind the BatchNorm
   const __nv_bfloat16* bwd_y;      // yb, the BatchNorm input (same pixel grid as the output), first channel of the view
   const __nv_bfloat16* bwd_res;    // skip-connection gradient or nullptr
@@ -719,10 +721,14 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const uint32_t ga = va ? pack_bf16x2(__uint_as_float(v[4 * j]) + __uint_as_float(ra[j] << 16),
-                                             __uint_as_float(v[4 * j + 1]) + __uint_as_float(ra[j] & 0xffff0000u)) : 0u;
-        const uint32_t gb = vb ? pack_bf16x2(__uint_as_float(v[4 * j + 2]) + __uint_as_float(rb[j] << 16),
-                                             __uint_as_float(v[4 * j + 3]) + __uint_as_float(rb[j] & 0xffff0000u)) : 0u;
+        uint32_t ga = va ? pack_bf16x2(__uint_as_float(v[4 * j]) + __uint_as_float(ra[j] << 16),
+                                       __uint_as_float(v[4 * j + 1]) + __uint_as_float(ra[j] & 0xffff0000u)) : 0u;
+        uint32_t gb = vb ? pack_bf16x2(__uint_as_float(v[4 * j + 2]) + __uint_as_float(rb[j] << 16),
+                                       __uint_as_float(v[4 * j + 3]) + __uint_as_float(rb[j] & 0xffff0000u)) : 0u;
+        if (AM == 1 && P.bwd_mask) {      // ReLU backward of the producing convolution: zero where its output is not positive
+          ga &= (__uint_as_float(ya[j] << 16) > 0.f ? 0x0000ffffu : 0u) | (__uint_as_float(ya[j] & 0xffff0000u) > 0.f ? 0xffff0000u : 0u);
+          gb &= (__uint_as_float(yb[j] << 16) > 0.f ? 0x0000ffffu : 0u) | (__uint_as_float(yb[j] & 0xffff0000u) > 0.f ? 0xffff0000u : 0u);
+        }
         st_shared_u32(stg + swz(offa + 16u * j, mask), ga);
         st_shared_u32(stg + swz(offb + 16u * j, mask), gb);
         if (AM >= 0) {
@@ -766,7 +772,7 @@ __device__ __forceinline__ void epilogue_role_bwd(const UmmaConvParams& P, uint3
     }
   }
   if (leader) tma_store_wait<0>();
-  if (AM >= 0) {
+  if (AM >= 0 && !P.bwd_mask) {
     // transposed sum over the 8 lanes that share T%4 (lane bits 4, 3, 2): each step halves the values a lane carries; the lane
     // ends with the V/8 values i0 .. i0 + V/8 - 1, i0 = (V/2) bit4 + (V/4) bit3 + (V/8) bit2, of S = [sum][j][e]
 #pragma unroll
@@ -1108,7 +1114,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
       for (int i = etid; i < P.nb; i += 256) bias_s[i] = __ldg(P.bias + nb0 + i);
     if (BWD && P.bwd_am >= 0)
       for (int i = etid; i < P.nb; i += 256) {
-        bnp_s[i] = __ldg(P.bwd_scale + nb0 + i); bnp_s[64 + i] = __ldg(P.bwd_shift + nb0 + i);
+        if (P.bwd_mask) { bnp_s[i] = 1.f; bnp_s[64 + i] = 0.f; }
+        else { bnp_s[i] = __ldg(P.bwd_scale + nb0 + i); bnp_s[64 + i] = __ldg(P.bwd_shift + nb0 + i); }
       }
     asm volatile("bar.sync 3, 256;" ::: "memory");  // epilogue warps only
     const float* bs = P.bias ? bias_s : nullptr;
@@ -1257,6 +1264,7 @@ struct BnPhase {
 struct BwdEpi {
   const dg_tensor* res;        // skip-connection gradient added to the result, or nullptr
   const dg_bn_bwd_stats* bn;   // statistics of the BatchNorm in front of the convolution, or nullptr
+  const dg_tensor* relu_y = nullptr;   // output of the ReLU convolution in front of this one: store g * (relu_y > 0), no statistics
 };
 
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
@@ -1617,6 +1625,18 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
       P.bwd_res = (const __nv_bfloat16*)r->ptr + r->coff;
       P.bwd_r_sw = r->cpitch; P.bwd_r_sh = (long)r->cpitch * r->w; P.bwd_r_sn = (long)r->cpitch * r->w * r->h;
     }
+    if (bwd->relu_y) {
+      const dg_tensor* yb = bwd->relu_y;
+      DG_REQUIRE(!bwd->bn && dg_valid(yb) && dg_same_shape(yb, out) && yb->dtype == DG_BF16 && ((uintptr_t)yb->ptr % 16) == 0 &&
+                     yb->cpitch % 8 == 0 && yb->coff % 8 == 0, "%s: bad ReLU-mask arguments", name);
+      P.bwd_am = 1; P.bwd_mask = 1; P.bwd_alpha = 0.f;
+      P.bwd_y = (const __nv_bfloat16*)yb->ptr + yb->coff;
+      P.bwd_y_sw = yb->cpitch; P.bwd_y_sh = (long)yb->cpitch * yb->w; P.bwd_y_sn = (long)yb->cpitch * yb->w * yb->h;
+      uint64_t dims[4] = {(uint64_t)yb->c, (uint64_t)yb->w, (uint64_t)yb->h, (uint64_t)yb->n};
+      uint64_t strides[3] = {(uint64_t)yb->cpitch * 2, (uint64_t)yb->cpitch * 2 * yb->w, (uint64_t)yb->cpitch * 2 * yb->w * yb->h};
+      uint32_t box[4] = {(uint32_t)nb, 8u, (uint32_t)(16 * mt), 1u};
+      if (encode_map(ctx, &P.rmap, (char*)yb->ptr + (size_t)yb->coff * 2, 4, dims, strides, box, nb)) return 1;
+    }
     if (bwd->bn) {
       const dg_bn_bwd_stats* b = bwd->bn;
       const dg_tensor* yb = b->y;
@@ -1912,6 +1932,17 @@ extern "C" int dg_umma_conv2d_dgrad_fused_blocks(dg_ctx* ctx, const dg_tensor* d
   if (p->stride != 1) return 0;
   if (conv_dgrad_impl(ctx, dy, (const void*)1, nullptr, dx, p, nullptr, true, nullptr, true, &blocks) != 0) return 0;
   return blocks;
+}
+
+// Input gradient of a stride-1 convolution whose INPUT was the output y = relu(conv(...)) of another convolution (autoencoder.py:95-104,
+// conv2d -> conv2d chains): dx is stored already multiplied by (y > 0), i.e. the ReLU backward pass of the producing layer is folded
+// into this launch (one read of y through the epilogue's staging buffer instead of a separate pass over dx and y).  Applies where
+// dg_umma_conv2d_dgrad_fused_blocks() > 0.
+extern "C" int dg_umma_conv2d_dgrad_relu_mask(dg_ctx* ctx, const dg_tensor* dy, const void* w_packed, const dg_tensor* dx, const dg_conv_params* p,
+                                              const dg_tensor* y_relu, void* stream) {
+  DG_REQUIRE(y_relu, "dg_umma_conv2d_dgrad_relu_mask: null argument");
+  BwdEpi e{nullptr, nullptr, y_relu};
+  return conv_dgrad_impl(ctx, dy, w_packed, nullptr, dx, p, stream, false, &e);
 }
 
 extern "C" int dg_umma_conv2d_dgrad_supported(dg_ctx* ctx, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p) {

@@ -252,6 +252,24 @@ class Engine:
             v.n_mask += 1
         self.tape.append(Node(out.seq, inputs, out, group, bwd, fusable, params, wkey))
 
+    def _relu_mask_rows(self, dy_shape, dx_shape, lin) -> int:
+        """> 0 when the input-gradient launch of this layer can store its result already multiplied by (input > 0)
+        (dg_umma_conv2d_dgrad_relu_mask: stride 1, staged epilogue, 32- or 64-channel N block).  OFF by default (DG_RELU_MASK_DGRAD=1
+        switches it on): measured SLOWER on the autoencoder, 11.72 against 11.50 ms per step -- the mma-fragment epilogue that pays for
+        itself when it also produces the BatchNorm-backward sums takes ~385 us on the 256x256 layers, more than the plain input
+        gradient plus a separate ReLU-backward pass (profiles/step_profile_r2b_ae_relu_mask.log)."""
+        key = ("relumask", tuple(dy_shape), tuple(dx_shape), lin.kh, lin.kw, lin.stride, lin.pad_t, lin.pad_l)
+        rows = self._cap.get(key)
+        if rows is None:
+            rows = 0
+            if lin.stride == 1 and self.use_umma and self.fold_relu_bwd and os.environ.get("DG_RELU_MASK_DGRAD", "0") != "0":
+                BF = _lib.DG_BF16
+                d_dy = _lib.DgTensor(1 << 20, BF, dy_shape[0], dy_shape[1], dy_shape[2], dy_shape[3], dy_shape[3], 0)
+                d_dx = _lib.DgTensor(1 << 20, BF, dx_shape[0], dx_shape[1], dx_shape[2], dx_shape[3], dx_shape[3], 0)
+                rows = int(self.lib.dg_umma_conv2d_dgrad_fused_blocks(self.ctx, C.byref(d_dy), C.byref(d_dx), C.byref(lin)))
+            self._cap[key] = rows
+        return rows
+
     def _relu_bwd_folded(self, out: Var, act) -> bool:
         """True when every consumer of this ReLU convolution's output returns a gradient that already carries the ReLU mask."""
         return self.fold_relu_bwd and act == "relu" and out.n_cons > 0 and out.n_mask == out.n_cons
@@ -421,6 +439,10 @@ class Engine:
         out.relu_out = act == "relu"
         if keep:
             out.segs = ((cout, cout_p),)
+        # conv -> conv chain (autoencoder.py:95-104): x is the output of a ReLU convolution and this layer's input gradient is stored
+        # already multiplied by (x > 0), so the producer needs no ReLU backward pass of its own (Var.n_mask)
+        mask_in = (x.relu_out and not pad_in and x.t.dtype == torch.bfloat16 and
+                   self._relu_mask_rows((N, Ho, Wo, cout_p), tuple(x.shape), lin) > 0)
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag):
             dpre = gy
@@ -455,14 +477,18 @@ class Engine:
                 dxp = self.buf((seq, "dx_pad", tag), (N, H, W, cin_p), torch.bfloat16) if pad_in else dx
                 tdx = tensor(dxp)
                 pkd = self._packed(w, 1)
-                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
-                    self.ctx, C.byref(tdp), pkd.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
+                if mask_in:
+                    self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad_relu_mask(
+                        self.ctx, C.byref(tdp), pkd.data_ptr(), C.byref(tdx), C.byref(lin), C.byref(txi), self.st)))
+                else:
+                    self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad(
+                        self.ctx, C.byref(tdp), pkd.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
                 if dxp is not dx:
                     tv, td = tensor(dxp, c=cin), tensor(dx)
                     check(self.lib.dg_copy(self.ctx, C.byref(tv), C.byref(td), 0, self.st))
             return [dx]
 
-        self._push([x], out, w.group, bwd, params=(w, b))
+        self._push([x], out, w.group, bwd, params=(w, b), masks=[x] if mask_in else ())
         return out
 
     def _fold(self, w: Param, b: Param | None, pset, bname: str, eps: float, axis: int):
@@ -598,6 +624,8 @@ class Engine:
         out.bn_done = bn_done
         out.bn_applied = bn_applied
         out.relu_out = act == "relu"
+        mask_in = (x.relu_out and umma_d and x.t.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and
+                   self._relu_mask_rows(tuple(y.shape), tuple(x.shape), lin) > 0)
 
         def bwd(gy: torch.Tensor, need_in, need_p, tag, fctx=None):
             dpre = gy
@@ -610,6 +638,14 @@ class Engine:
                 with self._side():
                     self._wgrad(x.t, dpre, w, b, lin, flops)
             dx = None
+            if need_in[0] and mask_in:
+                # the producer of x is a ReLU convolution that skips its own backward pass: dL/dx leaves this launch masked
+                dx = self.buf((seq, "dx", tag), x.shape, x.t.dtype)
+                tdx = tensor(dx)
+                pk = self._packed(w, 1)
+                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_dgrad_relu_mask(
+                    self.ctx, C.byref(tdp), pk.data_ptr(), C.byref(tdx), C.byref(lin), C.byref(tx), self.st)))
+                return [dx]
             if need_in[0] and fctx is not None and umma_d and stride == 1 and dpre.dtype == torch.bfloat16 and x.t.dtype == torch.bfloat16:
                 # this launch produces the LAST contribution to dL/dx: the skip-connection gradient accumulated so far is added
                 # in the epilogue, and when x is the output of a training-mode BatchNorm its backward sums are reduced there too
@@ -659,7 +695,7 @@ class Engine:
                         self.ctx, C.byref(tdp), w.data.data_ptr(), None, C.byref(tdx), C.byref(lin), self.st)))
             return [dx]
 
-        self._push([x], out, w.group, bwd, fusable=True, params=(w, b),
+        self._push([x], out, w.group, bwd, fusable=True, params=(w, b), masks=[x] if mask_in else (),
                    wkey=(tuple(x.shape), tuple(y.shape), kh, kw, stride, pt, pl, b is None))
         return out
 

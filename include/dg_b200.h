@@ -139,6 +139,11 @@ typedef struct {
 int dg_umma_conv2d_dgrad_fused(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const dg_tensor* dx, const dg_conv_params* p,
                                const dg_tensor* residual, const dg_bn_bwd_stats* bn, void* stream);
 int dg_umma_conv2d_dgrad_fused_blocks(dg_ctx*, const dg_tensor* dy, const dg_tensor* dx, const dg_conv_params* p);
+/* Input gradient of a stride-1 convolution whose input was the output y_relu = relu(conv(...)) of another convolution
+ * (autoencoder.py:95-104, the conv2d -> conv2d chains): dx is stored already multiplied by (y_relu > 0) -- the ReLU backward pass
+ * of the producing layer folded into this launch.  Applies where dg_umma_conv2d_dgrad_fused_blocks() > 0. */
+int dg_umma_conv2d_dgrad_relu_mask(dg_ctx*, const dg_tensor* dy, const void* w_packed_dgrad, const dg_tensor* dx, const dg_conv_params* p,
+                                   const dg_tensor* y_relu, void* stream);
 /* dx half of the BatchNorm(+activation) backward pass when dg_umma_conv2d_dgrad_fused already reduced the per-channel sums
  * (`partials` = its [rows][2][C] workspace): dx = gamma*invstd*(g' - mean(g') - xhat*mean(g' xhat)); dgamma / dbeta (may be NULL)
  * receive sum g' xhat / sum g'.  One read of dy and x instead of two (autodiff of srgan.py:155,163,167,247). */

@@ -1280,3 +1280,34 @@ def test_umma_wgrad_batch(L, case, merged):
                 assert relerr(dws[i], (acc + 1) * refs_w[i]) < 1e-4, (i, acc)
                 if bias:
                     assert relerr(dbs[i], (acc + 1) * refs_b[i]) < 1e-4, (i, acc)
+
+
+@pytest.mark.parametrize("case", [(3, 32, 32, 2, 40, 24), (3, 64, 160, 1, 32, 48), (1, 96, 64, 2, 24, 24), (3, 64, 64, 16, 96, 96)])
+def test_dgrad_with_folded_relu_mask(L, case):
+    """dg_umma_conv2d_dgrad_relu_mask: the input gradient of a convolution whose input was y = relu(conv(...)) (autoencoder.py:95-104),
+    stored already multiplied by (y > 0) -- against dgrad followed by the oracle's ReLU backward, and bit for bit against the plain
+    dgrad launch masked on the host (the mask only zeroes stored bf16 values)."""
+    k, cin, cout, N, H, W = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same")
+    u = torch.randn(N, H, W, cin, generator=g, dtype=torch.float64)
+    y = _bf16_round(torch.relu(u))                                   # the producing layer's stored output (about half zeros)
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * 0.1)
+    yr = y.clone().requires_grad_(True)
+    out = OT.conv2d(yr, w, None, stride=1, padding="same")
+    gy = _bf16_round(torch.randn(out.shape, generator=g, dtype=torch.float64))
+    (out * gy).sum().backward()
+    ref = yr.grad * (y > 0)
+    yd, gyd, wd = dev(y, torch.bfloat16), dev(gy, torch.bfloat16), dev(w)
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 1, st))
+    dx = torch.empty(N, H, W, cin, device="cuda", dtype=torch.bfloat16); dx0 = torch.empty_like(dx)
+    tg, tdx, tdx0, ty = L.tensor(gyd), L.tensor(dx), L.tensor(dx0), L.tensor(yd)
+    if lib.dg_umma_conv2d_dgrad_fused_blocks(ctx, C.byref(tg), C.byref(tdx), C.byref(cp)) <= 0:
+        pytest.skip("the staged 32/64-channel epilogue does not apply to this layer: callers use the plain launch")
+    L.check(lib.dg_umma_conv2d_dgrad_relu_mask(ctx, C.byref(tg), pk.data_ptr(), C.byref(tdx), C.byref(cp), C.byref(ty), st))
+    L.check(lib.dg_umma_conv2d_dgrad(ctx, C.byref(tg), pk.data_ptr(), None, C.byref(tdx0), C.byref(cp), st))
+    torch.cuda.synchronize()
+    assert relerr(dx, ref) < BF16_TOL
+    assert torch.equal(dx, dx0 * (yd > 0))
