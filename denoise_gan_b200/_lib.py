@@ -130,6 +130,7 @@ SIGNATURES = {
     "dg_vgg_preprocess_bwd": (_i, [_P, _T, _T, _P]),
     "dg_loss_workspace_bytes": (_sz, [_T]),
     "dg_image_losses": (_i, [_P, _T, _T, _f, _f, _f, _P, _T, _i, _P, _sz, _P]),
+    "dg_gan_loss_terms": (_i, [_P, _P, _P, _P, _P, _P, _f, _f, _f, _f, _P, _P]),
     "dg_bce_const_target": (_i, [_P, _T, _f, _i, _f, _P, _T, _P, _sz, _P]),
     "dg_feature_mse": (_i, [_P, _T, _T, _f, _P, _T, _P, _sz, _P]),
     "dg_adam_step": (_i, [_P, _P, _P, _P, _P, _i64, _f, _f, _f, _f, _i64, _f, _f, _P, _P]),

@@ -187,6 +187,24 @@ inline int loss_blocks(long total, int sm_count) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+
+// The scalar arithmetic between the loss reductions and the returned tuple (train_srgan.py:86-99, 118), one thread: explicitly rounded
+// fp32 operations in the order of the reference expression so that the values equal the eager computation bit for bit.
+__global__ void gan_loss_terms_kernel(const float* __restrict__ content, const float* __restrict__ adv_raw, const float* __restrict__ out3,
+                                      const float* __restrict__ real_loss, const float* __restrict__ fake_loss, float w_mae, float w_mse,
+                                      float tv_gain, float disc_scale, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float c = content ? content[0] : 0.f;
+  const float adv = __fmul_rn(1e-3f, adv_raw[0]);
+  const float mae = out3[0], mse = out3[1], var = __fmul_rn(1e-5f, out3[2]);
+  float g = __fadd_rn(c, adv);
+  g = __fadd_rn(g, __fmul_rn(mae, w_mae));
+  g = __fadd_rn(g, __fmul_rn(mse, w_mse));
+  g = __fadd_rn(g, __fmul_rn(var, tv_gain));
+  out[0] = g; out[1] = adv; out[2] = mae; out[3] = mse; out[4] = c;
+  out[5] = __fmul_rn(disc_scale, __fadd_rn(real_loss[0], fake_loss[0]));
+  out[6] = var;
+}
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -274,5 +292,15 @@ extern "C" int dg_adam_step(dg_ctx* ctx, float* theta, const float* grad, float*
   adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST>>>(theta, grad, m, v, numel, beta1, beta2, eps, grad_scale,
                                                                 iterations_dev);
   DG_CHECK_LAUNCH("dg_adam_step");
+  return 0;
+}
+
+// gen_loss = content + 1e-3 adv + w_mae mae + w_mse mse + tv_gain var, disc_loss = disc_scale (real + fake) (train_srgan.py:86-99);
+// out[7] = {gen_loss, adv_loss, mae_loss, mse_loss, content_loss, disc_loss, var_loss}, the return order of train_srgan.py:118.
+extern "C" int dg_gan_loss_terms(dg_ctx* ctx, const float* content, const float* adv_raw, const float* out3, const float* real_loss,
+                                 const float* fake_loss, float w_mae, float w_mse, float tv_gain, float disc_scale, float* out7, void* stream) {
+  DG_REQUIRE(adv_raw && out3 && real_loss && fake_loss && out7, "dg_gan_loss_terms: null argument");
+  gan_loss_terms_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(content, adv_raw, out3, real_loss, fake_loss, w_mae, w_mse, tv_gain, disc_scale, out7);
+  DG_CHECK_LAUNCH("dg_gan_loss_terms");
   return 0;
 }

@@ -105,8 +105,20 @@ class GraphedStep:
             self.out = step_fn(model, self.x, self.y)
             # the step's scalar results as ONE fp32 vector (same order), so that a caller reads them with a single copy
             scal = [v for v in self.out if isinstance(v, torch.Tensor) and v.numel() == 1]
-            self.packed = torch.stack([v.detach().float().reshape(()) for v in scal]) if scal else None
+            self.packed = self._pack(scal)
         self.kernel_nodes = self._count_kernel_nodes()
+
+    @staticmethod
+    def _pack(scal):
+        """The scalars as one fp32 vector: when they already are consecutive elements of one buffer (train_common.gan_step's loss
+        terms) that buffer itself, without another kernel in the graph; else a stacked copy."""
+        if not scal:
+            return None
+        first = scal[0]
+        if (all(v.dtype == torch.float32 and v.device == first.device for v in scal) and
+                all(v.data_ptr() == first.data_ptr() + 4 * i for i, v in enumerate(scal))):
+            return torch.as_strided(first.detach(), (len(scal),), (1,))
+        return torch.stack([v.detach().float().reshape(()) for v in scal])
 
     def _count_kernel_nodes(self):
         """Number of kernel nodes of the captured step (bench.py's `gpu_launches`), through the CUDA runtime bindings."""

@@ -27,9 +27,8 @@ def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: flo
     if model.use_vgg:
         content, dgf, gf = model.content_loss(y, gen_output)          # :86
         seeds_g.append((gf, dgf))
-        content = content[0]
     else:
-        content = torch.zeros((), dtype=torch.float32, device=E.device)
+        content = None
     adv_raw, g_adv = E.bce(disc_fake, 1.0, from_logits, 1e-3, key="adv")          # :87
     out3, dgen = E.image_losses(gen_output, y.t, w_mae, w_mse, w_tv)              # :88-90
     real_loss, g_real = E.bce(disc_real, 1.0, from_logits, disc_scale, key="dreal")   # :94
@@ -60,9 +59,11 @@ def gan_step(model, img_input, img_target, *, from_logits: bool, disc_scale: flo
         model.disc_optimizer.apply(E, model.disc_params, scale)         # :116
     model.iterations += 1
 
-    adv = 1e-3 * adv_raw[0]
-    mae, mse, var = out3[0], out3[1], 1e-5 * out3[2]
-    gen_loss = content + adv + mae * w_mae + mse * w_mse + var * (w_tv / 1e-5 if w_tv else 0.0)
-    disc_loss = disc_scale * (real_loss[0] + fake_loss[0])
-    return dict(gen_loss=gen_loss, adv_loss=adv, mae_loss=mae, mse_loss=mse, content_loss=content, disc_loss=disc_loss,
-                var_loss=var, gen_output=gen_output, disc_real=disc_real, disc_fake=disc_fake)
+    # the returned scalars (train_srgan.py:86-99, 118) in ONE launch; the dict holds 0-d views of one 7-vector, which the captured step
+    # hands out as a single device->host copy (graph.GraphedStep.packed)
+    from . import _lib
+    t = E.buf(("loss", "terms"), (7,), torch.float32)
+    _lib.check(E.lib.dg_gan_loss_terms(E.ctx, _lib.ptr(content), adv_raw.data_ptr(), out3.data_ptr(), real_loss.data_ptr(), fake_loss.data_ptr(),
+                                       float(w_mae), float(w_mse), float(w_tv / 1e-5 if w_tv else 0.0), float(disc_scale), t.data_ptr(), E.st))
+    return dict(gen_loss=t[0], adv_loss=t[1], mae_loss=t[2], mse_loss=t[3], content_loss=t[4], disc_loss=t[5],
+                var_loss=t[6], gen_output=gen_output, disc_real=disc_real, disc_fake=disc_fake)

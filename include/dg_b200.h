@@ -323,6 +323,13 @@ size_t dg_loss_workspace_bytes(const dg_tensor* t);
 int dg_image_losses(dg_ctx*, const dg_tensor* gen, const dg_tensor* target, float w_mae, float w_mse, float w_tv,
                     float* out3, const dg_tensor* dgen, int accumulate, void* workspace, size_t workspace_bytes,
                     void* stream);
+/* The scalar arithmetic of the train step between the loss reductions and the returned tuple (train_srgan.py:86-99, 118), as one
+ * launch instead of a dozen scalar tensor ops: content (device scalar, may be NULL = 0), adv_raw = BCE(ones, D(fake)), out3 =
+ * {mae, mse, mean total variation} of dg_image_losses, real / fake = the discriminator's two BCE terms.
+ * out7 = {gen_loss, adv_loss = 1e-3 adv_raw, mae_loss, mse_loss, content_loss, disc_loss = disc_scale (real + fake), var_loss = 1e-5 tv}
+ * with gen_loss = content + adv_loss + w_mae mae + w_mse mse + tv_gain var_loss. */
+int dg_gan_loss_terms(dg_ctx*, const float* content, const float* adv_raw, const float* out3, const float* real_loss,
+                      const float* fake_loss, float w_mae, float w_mse, float tv_gain, float disc_scale, float* out7, void* stream);
 /* BinaryCrossentropy against a constant target. from_logits=1: train_srgan.py:71; 0: clipped-probability
  * form, train_autoencoder.py:79.  loss_out = mean BCE ; dx = grad_scale * dBCE/dx (dx may be NULL) */
 int dg_bce_const_target(dg_ctx*, const dg_tensor* x, float target, int from_logits, float grad_scale,
