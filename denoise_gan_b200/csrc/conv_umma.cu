@@ -78,6 +78,11 @@ struct UmmaConvParams {
   void* out;
   long out_sn, out_sh, out_sw;
   int out_f32;
+  // depth_to_space(2) + PReLU as the STORE PATTERN of the convolution in front of them (srgan.py:144-146, fsrgan.py:180-186, inference:
+  // the pre-activation is not needed again): conv channel c = blk * d2s_cq + cc lands at pixel (2h + blk / 2, 2w + blk % 2), channel cc of
+  // the [n, 2h, 2w, d2s_cq] output described by out / out_s*; slope d2s_prelu[cc] (nullptr: no PReLU).  bf16 direct epilogue only.
+  int d2s_cq;
+  const float* d2s_prelu;
   int out_cvalid;   // > 0 (fp32 output, one 16-channel N block): only the first out_cvalid channels of a pixel are stored -- the
                     // 3-channel image side (srgan.py:182, fsrgan.py:217) written densely instead of padded to 16 and sliced
   // staged epilogue: the tile is written to shared memory in the TMA swizzle and leaves through ONE bulk tensor store
@@ -191,6 +196,27 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
       const long pix = (long)n * P.out_sn + (long)ph * P.out_sh + (long)pw * P.out_sw + nb0 + P.ph_off[phs];
       const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.n_phase * P.mt + pm) * P.nb);
       int c0 = 0;
+      if (!F32 && P.d2s_cq > 0) {
+        // depth_to_space + PReLU store: every 16-channel group lies inside one sub-pixel block (d2s_cq is a multiple of 16)
+        for (; c0 < P.nb; c0 += 16) {
+          uint32_t v0[16];
+          tmem_ld_32x16(acc + c0, v0);
+          tmem_ld_wait();
+          if (!valid) continue;
+          const int cg = nb0 + c0, blk = cg / P.d2s_cq, cc = cg - blk * P.d2s_cq;
+          const long e = (long)n * P.out_sn + (long)(2 * ph + (blk >> 1)) * P.out_sh + (long)(2 * pw + (blk & 1)) * P.out_sw + cc;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v0[j]) + (bs ? bs[c0 + j] : 0.f);
+          if (P.d2s_prelu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : __ldg(P.d2s_prelu + cc + j) * f[j];
+          }
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + e);
+          dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+        }
+      }
       for (; c0 + 32 <= P.nb; c0 += 32) {   // two 16-column loads in flight per wait
         uint32_t v0[16], v1[16];
         if (P.dbg_flags & 2) continue;
@@ -1272,8 +1298,10 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
                 float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr,
                 const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, const BwdEpi* bwd = nullptr,
-                bool bwd_query = false, int out_cvalid = 0) {
+                bool bwd_query = false, int out_cvalid = 0, int d2s_cq = 0, const float* d2s_prelu = nullptr) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
+  DG_REQUIRE(d2s_cq == 0 || (d2s_cq % 16 == 0 && out->dtype == DG_BF16 && n_phase == 1 && !bn_partials && !bnp && !bwd && act == DG_ACT_NONE),
+             "%s: the depth_to_space store needs a bf16 output with a multiple of 16 channels per sub-pixel block and no other epilogue", name);
   DG_REQUIRE(out_cvalid == 0 || (out->dtype == DG_F32 && out->c == 16 && out_cvalid < 16 && n_phase == 1 && !bn_partials && !bnp && !bwd),
              "%s: a narrow store needs an fp32 output of fewer than 16 channels", name);
   DG_REQUIRE(n_phase == 1 || (n_phase == 4 && phase_lat && n_src == 1), "%s: bad output-phase description", name);
@@ -1431,7 +1459,8 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   if (n_stages > MAX_STAGES) n_stages = MAX_STAGES;
   DG_REQUIRE(n_stages >= 2, "%s: internal: fewer than 2 stages", name);
   static const char* dbg_no_ts = getenv("DG_DEBUG_NO_TSTORE");   // experiments only
-  bool ts = !kouter && n_phase == 1 && (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64);
+  bool ts = !kouter && n_phase == 1 && (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64) &&
+            d2s_cq == 0;
   const uint32_t stg_bytes = (uint32_t)mt * 128u * (uint32_t)nb * 2u;
   if (ts) {
     const long room = (long)budget - (long)w_res_pre - 2L * (long)stg_bytes;
@@ -1572,8 +1601,14 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.out_sw = (long)out->cpitch * out_lat.step;
   P.out_sh = (long)out->cpitch * out->w * out_lat.step;
   P.out_sn = (long)out->cpitch * out->w * out->h;
+  if (d2s_cq > 0) {      // `out` describes the convolution's own grid; the stored tensor is [n, 2h, 2w, d2s_cq] with channel pitch out->cpitch
+    P.out_sw = (long)out->cpitch;
+    P.out_sh = (long)out->cpitch * 2 * out->w;
+    P.out_sn = (long)out->cpitch * 2 * out->w * 2 * out->h;
+  }
   P.out_f32 = out->dtype == DG_F32;
   P.out_cvalid = out_cvalid;
+  P.d2s_cq = d2s_cq; P.d2s_prelu = d2s_prelu;
   P.bias = bias; P.act = act; P.alpha = alpha;
   P.dbg = g_dbg_timeline;
   P.dbg_flags = g_dbg_flags;
@@ -1762,7 +1797,8 @@ extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, in
 
 static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
                          const dg_conv_params* p, void* stream, bool dry, float* bn_partials = nullptr, int* bn_blocks = nullptr,
-                         const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, int out_cvalid = 0) {
+                         const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, int out_cvalid = 0,
+                         int d2s_cq = 0, const float* d2s_prelu = nullptr) {
   DG_REQUIRE(dg_valid(x) && y && y->ptr && w_packed && p, "dg_umma_conv2d_fwd: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
   DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
@@ -1787,7 +1823,22 @@ static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, 
   }
   return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
                      p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks, 1, nullptr, bn_fin, bnp, bnp_query, nullptr, false,
-                     out_cvalid);
+                     out_cvalid, d2s_cq, d2s_prelu);
+}
+
+// Conv2D + depth_to_space(2) + PReLU (srgan.py:144-146, fsrgan.py:180-186: the up-sampling blocks) as ONE launch for inference: the
+// convolution's epilogue stores channel c = blk * (Cout/4) + cc of pixel (h, w) at pixel (2h + blk / 2, 2w + blk % 2), channel cc of
+// y [n, 2h, 2w, Cout/4] (TensorFlow's DCR order) after bias and PReLU(shared_axes=[1,2]) with slope prelu_alpha[cc] (may be NULL).
+// The pre-activation tensor (2.7 GB for the last block of a 1080p Fast-SRGAN frame) is never written.  Training keeps the two-launch form
+// (the backward pass needs the pre-activation).
+extern "C" int dg_umma_conv2d_fwd_d2s_prelu(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                                            const dg_conv_params* p, const float* prelu_alpha, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y) && p && p->stride == 1 && p->act == DG_ACT_NONE, "dg_umma_conv2d_fwd_d2s_prelu: bad argument");
+  DG_REQUIRE(y->dtype == DG_BF16 && y->coff == 0 && y->h % 2 == 0 && y->w % 2 == 0 && y->c % 16 == 0,
+             "dg_umma_conv2d_fwd_d2s_prelu: y must be a bf16 [n, 2h, 2w, Cout/4] tensor with a multiple of 16 channels");
+  dg_tensor yc = *y;             // the convolution's own output grid
+  yc.h = y->h / 2; yc.w = y->w / 2; yc.c = 4 * y->c;
+  return conv_fwd_impl(ctx, x, w_packed, bias, &yc, p, stream, false, nullptr, nullptr, nullptr, nullptr, false, 0, y->c, prelu_alpha);
 }
 
 // Conv2D whose output has fewer than 16 channels (the RGB image: srgan.py:182, fsrgan.py:217, autoencoder.py:186), fp32: the packed

@@ -133,6 +133,7 @@ class Engine:
         self.phys_pad = os.environ.get("DG_PHYS_PAD", "1") != "0"
         self.fold_relu_bwd = os.environ.get("DG_FOLD_RELU_BWD", "1") != "0"    # see Var.n_mask
         self.narrow_store = os.environ.get("DG_NARROW_STORE", "1") != "0"
+        self.fuse_d2s_infer = os.environ.get("DG_FUSE_D2S", "1") != "0"     # inference: depth_to_space + PReLU as the up-conv's store pattern
         # weight gradients of layers with identical geometry (the generator trunk's 32 identical convolutions, the real / fake passes of
         # one discriminator layer) are collected during backward() and launched up to `wgrad_batch` at a time (dg_umma_conv2d_wgrad_batch)
         self.wgrad_batch = max(1, min(4, int(os.environ.get("DG_WGRAD_BATCH", "4"))))
@@ -1097,6 +1098,35 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ structural ops
+    def conv2d_d2s_prelu(self, x: Var, w: Param, b: Param | None, prelu: Param | None, training: bool) -> Var:
+        """The up-sampling block Conv2D -> depth_to_space(2) -> PReLU (srgan.py:144-146, fsrgan.py:180-186).  Inference on the tensor-core
+        path: ONE launch, the convolution's epilogue stores in depth_to_space order with the PReLU applied and the pre-activation
+        tensor is never written (dg_umma_conv2d_fwd_d2s_prelu).  Training (or no tensor cores): the two ops."""
+        N, H, W, cin = x.shape
+        kh, kw, _, cout = w.shape
+        if (training or not self.fuse_d2s_infer or x.segs is not None or not self._umma_ok(x.t, cin, cout, kh, kw, 1, H, W) or cout % 64 != 0):
+            return self.d2s_prelu(self.conv2d(x, w, b), prelu)
+        pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, 1, "same")
+        lin = DgConvParams(kh, kw, 1, pt, pl, 0, 0.0)
+        d_y = _lib.DgTensor(x.t.data_ptr(), _lib.DG_BF16, N, Ho, Wo, cout, cout, 0)
+        key = ("d2sfwd", N, H, W, cin, cout, kh, kw)
+        ok = self._cap.get(key)
+        if ok is None:
+            tx0 = tensor(x.t)
+            ok = bool(self.lib.dg_umma_conv2d_fwd_supported(self.ctx, C.byref(tx0), C.byref(d_y), C.byref(lin)))
+            self._cap[key] = ok
+        if not ok:
+            return self.d2s_prelu(self.conv2d(x, w, b), prelu)
+        seq = self._next()
+        y = self.buf((seq, "y"), (N, 2 * Ho, 2 * Wo, cout // 4), torch.bfloat16)
+        tx, ty = tensor(x.t), tensor(y)
+        pk = self._packed(w, 0)
+        flops = 2.0 * N * Ho * Wo * kh * kw * cin * cout
+        self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd_d2s_prelu(
+            self.ctx, C.byref(tx), pk.data_ptr(), _lib.ptr(b.data) if b is not None else None, C.byref(ty), C.byref(lin),
+            _lib.ptr(prelu.data) if prelu is not None else None, self.st)))
+        return Var(y, self._deps([x], w.group), seq)          # inference only: no tape node
+
     def d2s_prelu(self, u: Var, prelu: Param | None) -> Var:
         """tf.nn.depth_to_space(u, 2) then PReLU(shared_axes=[1,2])."""
         N, H, W, C4 = u.shape

@@ -50,8 +50,7 @@ class SRGANGenerator(_Net):
         n2 = E.conv2d(n, p["g/conv_post/kernel"], bn=self._bn("g/bn_post", training), post=dict(residual=temp))
         n = E.mark("g/post_add", E.bn_act(n2, p, "g/bn_post", training=training, residual=temp))
         for j in range(self.scale // 2):
-            u = E.conv2d(n, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"])
-            n = E.mark(f"g/up{j}/prelu", E.d2s_prelu(u, p[f"g/up{j}/prelu/alpha"]))
+            n = E.mark(f"g/up{j}/prelu", E.conv2d_d2s_prelu(n, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"], p[f"g/up{j}/prelu/alpha"], training))
         # 1x1 conv + tanh, fp32 output ('generator_tanh', dtype float32, srgan.py:183)
         return E.mark("g/tanh", E.conv2d(n, p["g/conv_out/kernel"], p["g/conv_out/bias"], act="tanh", out_dtype=torch.float32))
 
@@ -138,7 +137,7 @@ class FastSRGANGenerator(_Net):
         c2 = E.conv2d(r, p["g/c2/kernel"], p["g/c2/bias"], bn=self._bn("g/c2_bn", training), post=dict(residual=c1))
         u = E.bn_act(c2, p, "g/c2_bn", training=training, residual=c1)
         for j in range(2):
-            u = E.d2s_prelu(E.conv2d(u, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"]), p[f"g/up{j}/prelu/alpha"])
+            u = E.conv2d_d2s_prelu(u, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"], p[f"g/up{j}/prelu/alpha"], training)
         return E.conv2d(u, p["g/conv_out/kernel"], p["g/conv_out/bias"], act="tanh", out_dtype=torch.float32)
 
 

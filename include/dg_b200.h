@@ -268,6 +268,12 @@ int dg_umma_pack_weights_padded(dg_ctx*, const float* w, void* packed, int kh, i
                                 int mode, void* stream);
 int dg_unpad_weight_grad(dg_ctx*, const float* dw_padded, const float* dbias_padded, float* dw, float* dbias, int kh, int kw, int cin,
                          int cout, int cin_pad, int cout_pad, int accumulate, void* stream);
+/* Conv2D + tf.nn.depth_to_space(.., 2) + PReLU(shared_axes=[1,2]) (srgan.py:144-146, fsrgan.py:180-186) as one launch for INFERENCE:
+ * y is the [n, 2h, 2w, Cout/4] bf16 result; channel c = blk*(Cout/4) + cc of conv pixel (h, w) is stored at (2h + blk/2, 2w + blk%2, cc)
+ * after bias and PReLU with slope prelu_alpha[cc] (may be NULL).  The pre-activation tensor is never written (training keeps
+ * dg_umma_conv2d_fwd + dg_d2s_prelu_fwd: the backward pass needs it). */
+int dg_umma_conv2d_fwd_d2s_prelu(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                                 const dg_conv_params* p, const float* prelu_alpha, void* stream);
 /* Conv2D with fewer than 16 output channels (the RGB side, srgan.py:182 / fsrgan.py:217 / autoencoder.py:186), fp32 output:
  * w_packed / bias_padded are zero-padded to 16 output channels, y is the DENSE [n,h,w,c<16] result (no padded copy, no slice). */
 int dg_umma_conv2d_fwd_narrow(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias_padded, const dg_tensor* y,

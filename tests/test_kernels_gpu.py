@@ -1311,3 +1311,29 @@ def test_dgrad_with_folded_relu_mask(L, case):
     torch.cuda.synchronize()
     assert relerr(dx, ref) < BF16_TOL
     assert torch.equal(dx, dx0 * (yd > 0))
+
+
+@pytest.mark.parametrize("case", [(3, 32, 128, 2, 21, 19, True), (3, 64, 256, 1, 32, 24, True), (3, 32, 64, 1, 16, 16, False)])
+def test_conv_d2s_prelu_store(L, case):
+    """dg_umma_conv2d_fwd_d2s_prelu: Conv2D + depth_to_space(2) + PReLU (srgan.py:144-146, fsrgan.py:180-186) in one launch, the
+    convolution's epilogue storing in TensorFlow's DCR order -- against the oracle's three ops."""
+    k, cin, cout, N, H, W, use_prelu = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * 0.1)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    alpha = torch.rand(cout // 4, generator=g, dtype=torch.float64) - 0.3
+    ref = OT.depth_to_space(OT.conv2d(x, w, b, stride=1, padding="same"), 2)
+    if use_prelu:
+        ref = OT.prelu(ref, alpha)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same")
+    xd, wd, bd, ad = dev(x, torch.bfloat16), dev(w), dev(b), dev(alpha)
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 0, st))
+    y = torch.full((N, 2 * H, 2 * W, cout // 4), 7.0, device="cuda", dtype=torch.bfloat16)
+    tx, ty = L.tensor(xd), L.tensor(y)
+    L.check(lib.dg_umma_conv2d_fwd_d2s_prelu(ctx, C.byref(tx), pk.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp),
+                                             ad.data_ptr() if use_prelu else None, st))
+    torch.cuda.synchronize()
+    assert relerr(y, ref) < BF16_TOL
