@@ -1364,10 +1364,21 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   };
   int best_nb = 0, best_mt = 0, best_res = 0;
   const long tiles_mt2 = (long)in->n * ((out_h + 31) / 32) * ((out_w + 7) / 8);
+  // A wide layer with a SHORT contraction (the 1x1 expand convolutions of Fast-SRGAN, fsrgan.py:134-147: K = 32, 192 outputs) does
+  // almost no tensor work per byte it stores: with one 192-channel N block it runs the direct epilogue (a warp's 16-byte stores land
+  // on 32 different lines, 436 us for 1.17 GB at 1080p) and cannot carry the BatchNorm statistics.  64-channel N blocks re-read the
+  // small input from L2 but leave through the staged TMA store and keep the statistics / BatchNorm-backward epilogues available.
+  static const char* no_smallk = getenv("DG_DEBUG_NO_SMALLK_NB64");   // experiments only
+  const bool small_k = !no_smallk && (long)n_taps * in->c <= 64 && cout > 64 && cout % 64 == 0 && out->dtype == DG_BF16 && out_lat.step == 1 &&
+                       n_phase == 1 && d2s_cq == 0 &&
+                       // plain launches only: the statistics / BatchNorm-backward epilogues and their row-count queries keep the layout
+                       // they were validated with (one partial row per CTA of a single N block)
+                       !bn_partials && !bn_blocks && !bnp && !bnp_query && !bwd && !bwd_query && !bn_fin;
   for (int res = 1; res >= 0 && !best_nb; --res)
     for (int mt = 2; mt >= 1 && !best_nb; --mt)
       for (int nb = cout > 256 ? 256 : cout; nb >= 16 && !best_nb; nb -= 16) {
         if (cout % nb != 0 || 2 * n_phase * mt * nb > 512) continue;
+        if (small_k && nb > 64) continue;
         uint32_t wblk = (uint32_t)nb * kc * 2;
         uint32_t wres = (uint32_t)n_taps * n_chunks * wblk;
         uint32_t stage = halo_bytes(mt) + (res ? 0 : (uint32_t)n_taps * wblk);
