@@ -173,7 +173,8 @@ __device__ __forceinline__ void epi_store16(const uint32_t (&v)[16], const float
 
 template <int ACT, bool F32>
 __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t tmem, int q, int lane, int nb0, int total_tiles,
-                                              const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, int grp) {
+                                              const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, int grp,
+                                              const float* __restrict__ ps = nullptr) {
   const int m_idx = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   int it = grp;
@@ -197,24 +198,37 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
       const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.n_phase * P.mt + pm) * P.nb);
       int c0 = 0;
       if (!F32 && P.d2s_cq > 0) {
-        // depth_to_space + PReLU store: every 16-channel group lies inside one sub-pixel block (d2s_cq is a multiple of 16)
-        for (; c0 < P.nb; c0 += 16) {
-          uint32_t v0[16];
+        // depth_to_space + PReLU store: a 32-channel group lies inside one sub-pixel block (d2s_cq is a multiple of 32, see the host
+        // check); two 16-column accumulator loads in flight per wait, slopes from shared memory (ps: broadcast reads)
+        for (; c0 < P.nb; c0 += 32) {
+          uint32_t v0[16], v1[16];
           tmem_ld_32x16(acc + c0, v0);
+          tmem_ld_32x16(acc + c0 + 16, v1);
           tmem_ld_wait();
           if (!valid) continue;
           const int cg = nb0 + c0, blk = cg / P.d2s_cq, cc = cg - blk * P.d2s_cq;
           const long e = (long)n * P.out_sn + (long)(2 * ph + (blk >> 1)) * P.out_sh + (long)(2 * pw + (blk & 1)) * P.out_sw + cc;
-          float f[16];
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v0[j]) + (bs ? bs[c0 + j] : 0.f);
-          if (P.d2s_prelu) {
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v0[j]) + (bs ? bs[c0 + j] : 0.f);
+            f[16 + j] = __uint_as_float(v1[j]) + (bs ? bs[c0 + 16 + j] : 0.f);
+          }
+          if (ps) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : __ldg(P.d2s_prelu + cc + j) * f[j];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 a = *reinterpret_cast<const float4*>(ps + cc + 4 * j4);
+              f[4 * j4 + 0] = f[4 * j4 + 0] > 0.f ? f[4 * j4 + 0] : a.x * f[4 * j4 + 0];
+              f[4 * j4 + 1] = f[4 * j4 + 1] > 0.f ? f[4 * j4 + 1] : a.y * f[4 * j4 + 1];
+              f[4 * j4 + 2] = f[4 * j4 + 2] > 0.f ? f[4 * j4 + 2] : a.z * f[4 * j4 + 2];
+              f[4 * j4 + 3] = f[4 * j4 + 3] > 0.f ? f[4 * j4 + 3] : a.w * f[4 * j4 + 3];
+            }
           }
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + e);
-          dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dst[k] = make_uint4(pack_bf16x2(f[8 * k], f[8 * k + 1]), pack_bf16x2(f[8 * k + 2], f[8 * k + 3]), pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
+                                pack_bf16x2(f[8 * k + 6], f[8 * k + 7]));
         }
       }
       for (; c0 + 32 <= P.nb; c0 += 32) {   // two 16-column loads in flight per wait
@@ -1138,6 +1152,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     const int etid = grp * 128 + (warp - (grp ? 7 : 2)) * 32 + lane;   // 0..255 over both epilogue groups
     if (P.bias)
       for (int i = etid; i < P.nb; i += 256) bias_s[i] = __ldg(P.bias + nb0 + i);
+    if (!BWD && P.d2s_prelu)
+      for (int i = etid; i < P.d2s_cq; i += 256) bnp_s[i] = __ldg(P.d2s_prelu + i);      // PReLU slopes of the depth_to_space store (d2s_cq <= 192)
     if (BWD && P.bwd_am >= 0)
       for (int i = etid; i < P.nb; i += 256) {
         if (P.bwd_mask) { bnp_s[i] = 1.f; bnp_s[64 + i] = 0.f; }
@@ -1163,7 +1179,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
                                       reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp, bnp_s, \
                                       bar_res_full, bar_res_empty, stage_base); \
   else if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, grp); \
-  else epilogue_role<ACT, false>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, grp);
+  else epilogue_role<ACT, false>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, grp, P.d2s_prelu ? bnp_s : nullptr);
     switch (P.act) {
       case DG_ACT_RELU: DG_EPI(DG_ACT_RELU) break;
       case DG_ACT_LRELU: DG_EPI(DG_ACT_LRELU) break;
@@ -1300,8 +1316,8 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
                 const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, const BwdEpi* bwd = nullptr,
                 bool bwd_query = false, int out_cvalid = 0, int d2s_cq = 0, const float* d2s_prelu = nullptr) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
-  DG_REQUIRE(d2s_cq == 0 || (d2s_cq % 16 == 0 && out->dtype == DG_BF16 && n_phase == 1 && !bn_partials && !bnp && !bwd && act == DG_ACT_NONE),
-             "%s: the depth_to_space store needs a bf16 output with a multiple of 16 channels per sub-pixel block and no other epilogue", name);
+  DG_REQUIRE(d2s_cq == 0 || (d2s_cq % 32 == 0 && d2s_cq <= 192 && out->dtype == DG_BF16 && n_phase == 1 && !bn_partials && !bnp && !bwd && act == DG_ACT_NONE),
+             "%s: the depth_to_space store needs a bf16 output with a multiple of 32 (<= 192) channels per sub-pixel block and no other epilogue", name);
   DG_REQUIRE(out_cvalid == 0 || (out->dtype == DG_F32 && out->c == 16 && out_cvalid < 16 && n_phase == 1 && !bn_partials && !bnp && !bwd),
              "%s: a narrow store needs an fp32 output of fewer than 16 channels", name);
   DG_REQUIRE(n_phase == 1 || (n_phase == 4 && phase_lat && n_src == 1), "%s: bad output-phase description", name);
@@ -1845,8 +1861,8 @@ static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, 
 extern "C" int dg_umma_conv2d_fwd_d2s_prelu(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
                                             const dg_conv_params* p, const float* prelu_alpha, void* stream) {
   DG_REQUIRE(dg_valid(x) && dg_valid(y) && p && p->stride == 1 && p->act == DG_ACT_NONE, "dg_umma_conv2d_fwd_d2s_prelu: bad argument");
-  DG_REQUIRE(y->dtype == DG_BF16 && y->coff == 0 && y->h % 2 == 0 && y->w % 2 == 0 && y->c % 16 == 0,
-             "dg_umma_conv2d_fwd_d2s_prelu: y must be a bf16 [n, 2h, 2w, Cout/4] tensor with a multiple of 16 channels");
+  DG_REQUIRE(y->dtype == DG_BF16 && y->coff == 0 && y->h % 2 == 0 && y->w % 2 == 0 && y->c % 32 == 0 && y->c <= 192,
+             "dg_umma_conv2d_fwd_d2s_prelu: y must be a bf16 [n, 2h, 2w, Cout/4] tensor with a multiple of 32 (<= 192) channels");
   dg_tensor yc = *y;             // the convolution's own output grid
   yc.h = y->h / 2; yc.w = y->w / 2; yc.c = 4 * y->c;
   return conv_fwd_impl(ctx, x, w_packed, bias, &yc, p, stream, false, nullptr, nullptr, nullptr, nullptr, false, 0, y->c, prelu_alpha);

@@ -1104,7 +1104,7 @@ class Engine:
         tensor is never written (dg_umma_conv2d_fwd_d2s_prelu).  Training (or no tensor cores): the two ops."""
         N, H, W, cin = x.shape
         kh, kw, _, cout = w.shape
-        if (training or not self.fuse_d2s_infer or x.segs is not None or not self._umma_ok(x.t, cin, cout, kh, kw, 1, H, W) or cout % 64 != 0):
+        if (training or not self.fuse_d2s_infer or x.segs is not None or not self._umma_ok(x.t, cin, cout, kh, kw, 1, H, W) or cout % 128 != 0 or cout > 768):
             return self.d2s_prelu(self.conv2d(x, w, b), prelu)
         pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, 1, "same")
         lin = DgConvParams(kh, kw, 1, pt, pl, 0, 0.0)
