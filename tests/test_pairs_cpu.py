@@ -87,3 +87,17 @@ def test_synth_pair_contract():
     smooth = np.clip(np.stack([127 + 100 * np.sin(xx / 9.0 + c) + 20 * np.cos(yy / 7.0) for c in range(3)], -1), 0, 255).astype(np.uint8)
     x1, y1 = P.synth_pair(smooth, 5, 7, 64, 1, 90)                            # denoising pair: same size, mild artefacts
     assert x1.shape == (64, 64, 3) and 0 < np.abs(x1 - y1).mean() < 0.05
+
+
+def test_bicubic_kernel_and_border_rule_match_pillow_on_enlargement():
+    """Pillow's BICUBIC is the same Keys a = -0.5 kernel on half-pixel centres with out-of-image taps dropped and the rest renormalised;
+    it differs from tf.image.resize(antialias=False) only when SHRINKING (Pillow widens the kernel).  On enlargement the oracle must
+    agree: exactly for a scale whose phases fall on TensorFlow's 1/1024 weight table (x2), to the table's quantisation otherwise."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    x = rng.random((13, 17)).astype(np.float32)
+    im = Image.fromarray(x, mode="F")
+    for (oh, ow), tol in (((26, 34), 1e-6), ((39, 51), 2e-3), ((20, 30), 2e-3)):
+        ref = np.array(im.resize((ow, oh), Image.BICUBIC), dtype=np.float32)
+        ours = P.bicubic_resize(x[..., None], oh, ow)[..., 0]
+        assert np.abs(ref - ours).max() < tol, ((oh, ow), float(np.abs(ref - ours).max()))

@@ -26,3 +26,16 @@ def test_total_variation_shapes_and_values():
     assert tv[1, 2, 0] == 2.0 and tv[1, 1, 0] == 1.0 and tv[0, 2, 0] == 1.0
     u = OS.summary_u8(OS.TV, x)
     assert u.max() == 255 and u.min() == 0 and u[1, 1, 0] == 127
+
+
+def test_sobel_magnitude_matches_opencv():
+    """tf.image.sobel_edges = the 3x3 Sobel pair on a REFLECT-padded image; OpenCV's Sobel with BORDER_REFLECT_101 is the same operator."""
+    import pytest
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    img = (rng.random((12, 15, 3)).astype(np.float32) * 2 - 1)
+    r = OS.renorm(img)
+    gx = cv2.Sobel(r, cv2.CV_32F, 1, 0, ksize=3, borderType=cv2.BORDER_REFLECT_101)
+    gy = cv2.Sobel(r, cv2.CV_32F, 0, 1, ksize=3, borderType=cv2.BORDER_REFLECT_101)
+    ref = np.sqrt((gx / 4) ** 2 + (gy / 4) ** 2)
+    assert np.abs(ref - OS.sobel_variation(img)).max() < 1e-6
