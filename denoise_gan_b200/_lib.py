@@ -104,6 +104,7 @@ SIGNATURES = {
     "dg_im2col": (_i, [_P, _T, _CP, _i, _i, _P, _P]),
     "dg_umma_conv2d_wgrad_workspace_bytes": (_sz, [_T, _T, _CP]),
     "dg_umma_conv2d_wgrad": (_i, [_P, _T, _T, _P, _P, _CP, _i, _P, _sz, _P]),
+    "dg_umma_conv2d_wgrad_batch_supported": (_i, [_P, _i, _T, _T, _CP]),
     "dg_umma_conv2d_wgrad_batch_workspace_bytes": (_sz, [_i, _T, _T, _CP]),
     "dg_umma_conv2d_wgrad_batch": (_i, [_P, _i, _P, _P, _P, _P, _CP, _P, _P, _sz, _P]),
     "dg_dwconv3x3_fwd": (_i, [_P, _T, _P, _P, _T, _P]),

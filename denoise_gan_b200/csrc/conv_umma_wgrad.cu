@@ -730,6 +730,22 @@ extern "C" size_t dg_umma_conv2d_wgrad_batch_workspace_bytes(int n, const dg_ten
   return (size_t)n * dg_umma_conv2d_wgrad_workspace_bytes(x, dy, p);
 }
 
+// 1 when dg_umma_conv2d_wgrad_batch takes n layers of this geometry in one launch (a single-launch tile configuration exists).
+extern "C" int dg_umma_conv2d_wgrad_batch_supported(dg_ctx* ctx, int n, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p) {
+  if (n < 1 || n > MAX_PROB || !dg_valid(x) || !dg_valid(dy) || !p) return 0;
+  if (x->dtype != DG_BF16 || dy->dtype != DG_BF16 || x->c % 16 != 0 || dy->c % 16 != 0 || (p->stride != 1 && p->stride != 2) ||
+      p->kh * p->kw > MAX_TAPS || x->n != dy->n || (p->stride == 2 && (x->h % 2 != 0 || x->w % 2 != 0)))
+    return 0;
+  Plan pl;
+  const int sms = ctx->sm_count < 160 ? ctx->sm_count : 160;
+  for (int has_bias = 0; has_bias < 2; ++has_bias) {
+    if (make_plan("dg_umma_conv2d_wgrad_batch_supported", sms / n, x, dy, p, has_bias, &pl)) return 0;
+    const int atoms0 = 128 / pl.kc, cpl0 = pl.n_chunks < atoms0 ? pl.n_chunks : atoms0;
+    if (pl.src_split || !(pl.n_chunks <= cpl0 || pl.cblocks > 1)) return 0;
+  }
+  return 1;
+}
+
 extern "C" int dg_umma_conv2d_wgrad_batch(dg_ctx* ctx, int n, const dg_tensor* const* x, const dg_tensor* const* dy, float* const* dw,
                                           float* const* dbias, const dg_conv_params* p, const int* accumulate, void* workspace,
                                           size_t workspace_bytes, void* stream) {

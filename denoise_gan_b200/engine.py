@@ -749,7 +749,12 @@ class Engine:
         key = ("wgb", tx.n, tx.h, tx.w, tx.c, tdy.h, tdy.w, tdy.c, lin.kh, lin.kw, lin.stride, lin.pad_t, lin.pad_l)
         ok = self._cap.get(key)
         if ok is None:
-            ok = self.lib.dg_umma_conv2d_wgrad_batch_workspace_bytes(2, C.byref(tx), C.byref(tdy), C.byref(lin)) > 0 and lin.stride == 1 and tx.c <= 128
+            # every group size up to wgrad_batch must have a single-launch tile configuration (stride-2 and > 128-channel
+            # discriminator layers included; DG_WGRAD_BATCH_WIDE=0 restores the stride-1 / <= 128-channel rule for A/B runs)
+            ok = all(bool(self.lib.dg_umma_conv2d_wgrad_batch_supported(self.ctx, k, C.byref(tx), C.byref(tdy), C.byref(lin)))
+                     for k in range(2, self.wgrad_batch + 1))
+            if os.environ.get("DG_WGRAD_BATCH_WIDE", "1") == "0":
+                ok = ok and lin.stride == 1 and tx.c <= 128
             self._cap[key] = ok
         return ok
 

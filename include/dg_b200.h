@@ -173,6 +173,7 @@ int dg_umma_conv2d_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float
  * problems and the fixed costs of a launch (prologue, one fp32 partial per CTA, the partial reduce) are paid once per n layers.
  * x[i] / dy[i] / dw[i] / dbias[i] / accumulate[i] describe problem i; the dw pointers are either all distinct or all the same
  * (then the n gradients are summed into it, accumulate[0] decides whether on top of its previous content). */
+int dg_umma_conv2d_wgrad_batch_supported(dg_ctx*, int n, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
 size_t dg_umma_conv2d_wgrad_batch_workspace_bytes(int n, const dg_tensor* x, const dg_tensor* dy, const dg_conv_params* p);
 int dg_umma_conv2d_wgrad_batch(dg_ctx*, int n, const dg_tensor* const* x, const dg_tensor* const* dy, float* const* dw,
                                float* const* dbias, const dg_conv_params* p, const int* accumulate, void* workspace,
