@@ -1,0 +1,386 @@
+// Fast-SRGAN inverted-residual block at inference as ONE launch (fsrgan.py:112-176 with training=False, the model
+// infer_video.py:92-97,146 runs): 1x1 expand 32 -> 192 (+ BatchNorm + ReLU), depthwise 3x3 (+ BatchNorm + ReLU), 1x1 project
+// 192 -> 32 (+ BatchNorm), + block input.  The three BatchNorms are folded into the kernels and biases by the caller.
+//
+// As three launches the 192-channel intermediates of a 1080p frame (1280 x 2048 padded, 1 GB each) cross HBM four times
+// (~4.3 GB per block, ~1.0 ms: profiles/infer_profile_r2*_fsrgan.log); here they never leave the SM: the block moves
+// 168 MB in and 168 MB out.
+//
+// One persistent CTA per SM walks 16 x 8 output tiles:
+//   control warp : TMA of the (8+2) x (16+2) x 32 halo tile (2-stage ring, out-of-image pixels zero-filled), and the two
+//                  tcgen05 products -- expand: [256 halo rows (180 used)] x 32 . 32 x 192 -> TMEM (2 x 192 columns),
+//                  project: [128 output pixels] x 192 . 192 x 32 -> TMEM (2 x 32 columns, double-buffered);
+//   12 compute warps, per tile:
+//     E  accumulator -> + bias, ReLU, zero for out-of-image pixels (the depthwise convolution pads ITS input with zeros,
+//        not relu(bias)) -> bf16 [180][192] in shared memory (pixel pitch 400 B: conflict-free 16-byte stores);
+//     D  depthwise 3x3 on CUDA cores: a thread owns a channel pair and two output rows, rolling 4 x 3 window in registers,
+//        packed fp32x2 FMAs (FFMA2), fp32 accumulate as dg_dwconv3x3_fwd_act; + bias, ReLU -> bf16 straight into the
+//        128-byte-swizzled K-major A operand of the project product;
+//     P  (tile i-1, four warps) accumulator + bias + block input (re-read from L2) -> bf16 -> global.
+//   The expand product of tile i+1 runs under D(i), the project product of tile i under E(i+1): the tensor pipe is never
+//   waited for.  The kernel is bound by the CUDA-core depthwise stage (FP32 pipe), not by HBM.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "dg_common.cuh"
+#include "sm100.cuh"
+
+namespace {
+using namespace sm100;
+
+constexpr int FB_C = 32, FB_E = 192;                  // block channels, expanded channels (expansion 6, fsrgan.py:121)
+constexpr int FB_TW = 16, FB_TH = 8;                  // output tile
+constexpr int FB_IW = FB_TW + 2, FB_IH = FB_TH + 2;   // halo tile
+constexpr int FB_HALO = FB_IW * FB_IH;                // 180 rows of the expand product
+constexpr int FB_COMPUTE_WARPS = 12, FB_THREADS = (FB_COMPUTE_WARPS + 1) * 32;
+constexpr uint32_t FB_PITCH = 400;                    // bytes per pixel of the expanded tile (384 + 16: bank spread)
+constexpr uint32_t OFF_W1 = 0;                        // expand B operand: 192 rows x 64 B, 64-byte swizzle
+constexpr uint32_t OFF_W2 = 12288;                    // project B operand: 3 K blocks x (32 rows x 128 B), 128-byte swizzle
+constexpr uint32_t OFF_A = 24576;                     // project A operand: 3 K blocks x (128 rows x 128 B)
+constexpr uint32_t OFF_X = OFF_A + 3 * 16384;         // halo stages: 2 x 16 KB (256 rows x 64 B addressed by the product, 180 written)
+constexpr uint32_t OFF_I = OFF_X + 2 * 16384;         // expanded tile
+constexpr uint32_t OFF_B = OFF_I + ((FB_HALO * FB_PITCH + 127u) & ~127u);   // biases: expand[192], project[32] (fp32)
+constexpr uint32_t FB_SMEM = OFF_B + (FB_E + FB_C) * 4 + 1024;
+constexpr uint32_t X_BYTES = FB_HALO * FB_C * 2;
+constexpr uint32_t TM_E = 0, TM_P = 2 * FB_E;         // TMEM columns: expand accumulators (2 x 192), project accumulators (2 x 32)
+
+struct FbParams {
+  CUtensorMap xmap;
+  const __nv_bfloat16* x;       // block input (residual), pixel pitch xp, channel offset already applied
+  const __nv_bfloat16* w1;      // [192][32]  expand kernel, BatchNorm folded, K-major
+  const __nv_bfloat16* w2;      // [32][192]  project kernel, BatchNorm folded, K-major
+  const float* b1;              // [192]
+  const float* wd;              // [9][192]   depthwise kernel, BatchNorm folded
+  const float* bd;              // [192]
+  const float* b2;              // [32]
+  __nv_bfloat16* y;
+  int xp, yp, N, H, W, tiles_w, tiles_h, total;
+};
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ u64 bf2_to_f2(uint32_t v) {     // bf16x2 -> fp32x2 (low half = lower channel)
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(v << 16), "r"(v & 0xffff0000u));
+  return d;
+}
+__device__ __forceinline__ uint32_t relu_pack(u64 v) {     // max(v, 0) -> bf16x2
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  __nv_bfloat162 r = __floats2bfloat162_rn(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FB_COMPUTE_WARPS * 32) : "memory"); }
+
+__global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __grid_constant__ FbParams P) {
+  extern __shared__ uint8_t fb_raw[];
+  __shared__ __align__(8) uint64_t bar_x[2], bar_e, bar_efree, bar_a, bar_p[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(fb_raw) + 1023u) & ~1023u;
+  uint8_t* gen = fb_raw + (base - smem_u32(fb_raw));
+  const int n_local = ((int)blockIdx.x < P.total) ? (P.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_x[0]), 1); mbar_init(smem_u32(&bar_x[1]), 1);
+    mbar_init(smem_u32(&bar_e), 1);
+    mbar_init(smem_u32(&bar_efree), FB_COMPUTE_WARPS);
+    mbar_init(smem_u32(&bar_a), FB_COMPUTE_WARPS);
+    mbar_init(smem_u32(&bar_p[0]), 1); mbar_init(smem_u32(&bar_p[1]), 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&P.xmap);
+  }
+  if (warp == FB_COMPUTE_WARPS) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  // ---- the two B operands (24 KB) and the biases, once per CTA: 16-byte chunks to their swizzled places
+  for (int i = tid; i < FB_E * 4; i += FB_THREADS) {          // expand: row n (0..191), chunk c (0..3) of 64 B
+    const int n = i >> 2, c = i & 3;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.w1) + i);
+    *reinterpret_cast<uint4*>(gen + OFF_W1 + n * 64 + ((c ^ ((n >> 1) & 3)) << 4)) = v;
+  }
+  for (int i = tid; i < FB_C * 24; i += FB_THREADS) {         // project: row n (0..31), 24 chunks of the 384-byte K row
+    const int n = i / 24, c = i - n * 24, kb = c >> 3, cc = c & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.w2) + i);
+    *reinterpret_cast<uint4*>(gen + OFF_W2 + kb * 4096 + n * 128 + ((cc ^ (n & 7)) << 4)) = v;
+  }
+  float* bias_s = reinterpret_cast<float*>(gen + OFF_B);
+  for (int i = tid; i < FB_E + FB_C; i += FB_THREADS) bias_s[i] = i < FB_E ? P.b1[i] : P.b2[i - FB_E];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  auto tile_coords = [&](int it, int& n, int& h0, int& w0) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h;
+    n = t2 / P.tiles_h; h0 = th * FB_TH; w0 = tw * FB_TW;
+  };
+
+  if (warp == FB_COMPUTE_WARPS) {
+    // ------------------------------------------------------------------ control warp (whole warp, tcgen05 / TMA under elect_one)
+    const uint32_t idesc_e = make_idesc_bf16(128, FB_E, 0, 0), idesc_p = make_idesc_bf16(128, FB_C, 0, 0);
+    const uint64_t hi64 = make_smem_desc_hi(512, LAYOUT_SW64) << 32, hi128 = make_smem_desc_hi(1024, LAYOUT_SW128) << 32;
+    const uint32_t lbo16 = 1u << 16;
+    auto load_x = [&](int it) {
+      int n, h0, w0;
+      tile_coords(it, n, h0, w0);
+      const uint32_t bar = smem_u32(&bar_x[it & 1]);
+      mbar_expect_tx(bar, X_BYTES);
+      tma_load_4d(base + OFF_X + (uint32_t)(it & 1) * 16384u, &P.xmap, bar, 0, w0 - 1, h0 - 1, n);
+    };
+    auto mma_expand = [&](int it) {
+      const uint32_t a16 = ((base + OFF_X + (uint32_t)(it & 1) * 16384u) >> 4) | lbo16, b16 = ((base + OFF_W1) >> 4) | lbo16;
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_f16(tmem + TM_E + (uint32_t)mb * FB_E, hi64 | (uint64_t)(a16 + (uint32_t)mb * 512u + 2u * k), hi64 | (uint64_t)(b16 + 2u * k), idesc_e,
+                   k != 0);
+      umma_commit(smem_u32(&bar_e));
+    };
+    auto mma_project = [&](int it) {
+      const uint32_t a16 = ((base + OFF_A) >> 4) | lbo16, b16 = ((base + OFF_W2) >> 4) | lbo16;
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem + TM_P + (uint32_t)(it & 1) * FB_C, hi128 | (uint64_t)(a16 + (uint32_t)kb * 1024u + 2u * k),
+                   hi128 | (uint64_t)(b16 + (uint32_t)kb * 256u + 2u * k), idesc_p, (kb | k) != 0);
+      umma_commit(smem_u32(&bar_p[it & 1]));
+    };
+    if (n_local > 0) {
+      if (elect_one()) {
+        load_x(0);
+        if (n_local > 1) load_x(1);
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar_x[0]), 0);
+      tc_fence_after();
+      if (elect_one()) mma_expand(0);
+      __syncwarp();
+    }
+    for (int it = 0; it < n_local; ++it) {
+      mbar_wait(smem_u32(&bar_efree), (uint32_t)it & 1u);        // E(it) has read the expand accumulators
+      tc_fence_after();
+      if (it + 1 < n_local) {
+        mbar_wait(smem_u32(&bar_x[(it + 1) & 1]), ((uint32_t)(it + 1) >> 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) mma_expand(it + 1);
+        __syncwarp();
+      }
+      if (it + 2 < n_local && elect_one()) load_x(it + 2);       // its stage was read by the expand product of tile it: complete
+      __syncwarp();
+      mbar_wait(smem_u32(&bar_a), (uint32_t)it & 1u);            // D(it) has written the A operand
+      tc_fence_after();
+      if (elect_one()) mma_project(it);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int q = warp & 3, j3 = warp >> 2;        // E: TMEM lane quarter, 64-column third
+    const int g = warp % 3, rg = warp / 3;         // D: 64-channel group, output rows 2rg, 2rg+1
+    const int cpair = g * 32 + lane;               // channel pair (channels 2cpair, 2cpair+1)
+    u64 wk[9], bdw;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = pack2(P.wd[t * FB_E + 2 * cpair], P.wd[t * FB_E + 2 * cpair + 1]);
+    bdw = pack2(P.bd[2 * cpair], P.bd[2 * cpair + 1]);
+    const uint32_t inter = base + OFF_I, abuf = base + OFF_A;
+
+    auto project_out = [&](int it) {               // P(it): warps 0..3, one output pixel per thread
+      int n, h0, w0;
+      tile_coords(it, n, h0, w0);
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + TM_P + (uint32_t)(it & 1) * FB_C + ((uint32_t)(q * 32) << 16), v);
+      const int r = q * 32 + lane, h = h0 + (r >> 4), w = w0 + (r & 15);
+      const bool ok = h < P.H && w < P.W;
+      const long pix = ((long)n * P.H + h) * P.W + w;
+      uint4 res[4];
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) res[k] = __ldg(reinterpret_cast<const uint4*>(P.x + pix * P.xp) + k);
+      }
+      tmem_ld_wait();
+      if (ok) {
+        const float* b2 = bias_s + FB_E;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t rr[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = k * 8 + e * 2;
+            const float lo = __uint_as_float(v[c]) + b2[c] + __uint_as_float(rr[e] << 16);
+            const float hi = __uint_as_float(v[c + 1]) + b2[c + 1] + __uint_as_float(rr[e] & 0xffff0000u);
+            __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+            o[e] = *reinterpret_cast<uint32_t*>(&pk);
+          }
+          reinterpret_cast<uint4*>(P.y + pix * P.yp)[k] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    };
+
+    for (int it = 0; it < n_local; ++it) {
+      int n, h0, w0;
+      tile_coords(it, n, h0, w0);
+      // ---- E(it): expand accumulators -> bf16 expanded tile
+      mbar_wait(smem_u32(&bar_e), (uint32_t)it & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        if (mb == 1 && q * 32 >= FB_HALO - 128) continue;          // rows 180..255 of the product are not part of the tile
+        const int row = mb * 128 + q * 32 + lane;
+        const int hh = row / FB_IW, ww = row - hh * FB_IW;
+        const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+        const bool in_tile = row < FB_HALO;
+        const bool in_img = h >= 0 && h < P.H && w >= 0 && w < P.W;
+        const uint32_t dst = inter + (uint32_t)row * FB_PITCH + (uint32_t)j3 * 128u;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem + TM_E + (uint32_t)mb * FB_E + (uint32_t)(j3 * 64 + b * 32) + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          const float* b1 = bias_s + j3 * 64 + b * 32;
+          if (in_tile) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = k * 8 + e * 2;
+                const float lo = fmaxf(__uint_as_float(v[c]) + b1[c], 0.f), hi = fmaxf(__uint_as_float(v[c + 1]) + b1[c + 1], 0.f);
+                __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                o[e] = in_img ? *reinterpret_cast<uint32_t*>(&pk) : 0u;
+              }
+              sts128(dst + (uint32_t)(b * 64 + k * 16), make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_efree));
+      compute_sync();                                              // the expanded tile is complete
+      if (it > 0) {                                                // project product of tile it-1: A operand free, accumulator ready
+        mbar_wait(smem_u32(&bar_p[(it - 1) & 1]), ((uint32_t)(it - 1) >> 1) & 1u);
+      }
+      // ---- D(it): depthwise 3x3 + bias + ReLU -> A operand of the project product
+      {
+        const uint32_t src = inter + (uint32_t)(2 * rg * FB_IW) * FB_PITCH + (uint32_t)cpair * 4u;
+        u64 win[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          win[r][0] = bf2_to_f2(lds32(src + (uint32_t)(r * FB_IW + 0) * FB_PITCH));
+          win[r][1] = bf2_to_f2(lds32(src + (uint32_t)(r * FB_IW + 1) * FB_PITCH));
+        }
+        const uint32_t arow0 = abuf + (uint32_t)g * 16384u + (uint32_t)(2 * rg * FB_TW) * 128u + (uint32_t)(lane & 3) * 4u;
+#pragma unroll
+        for (int c = 0; c < FB_TW; ++c) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) win[r][(c + 2) % 3] = bf2_to_f2(lds32(src + (uint32_t)(r * FB_IW + c + 2) * FB_PITCH));
+          u64 a0 = bdw, a1 = bdw;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              a0 = ffma2(win[a][(c + b) % 3], wk[a * 3 + b], a0);
+              a1 = ffma2(win[a + 1][(c + b) % 3], wk[a * 3 + b], a1);
+            }
+          // output pixel rows 2rg*16 + c and (2rg+1)*16 + c of the 128-row A operand; 16-byte chunk lane/4, XOR row%8
+          const uint32_t r0 = (uint32_t)(2 * rg * FB_TW + c);
+          sts32(arow0 + (uint32_t)c * 128u + ((((uint32_t)lane >> 2) ^ (r0 & 7u)) << 4), relu_pack(a0));
+          sts32(arow0 + (uint32_t)(c + FB_TW) * 128u + ((((uint32_t)lane >> 2) ^ ((r0 + FB_TW) & 7u)) << 4), relu_pack(a1));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_a));
+      // ---- P(it-1)
+      if (it > 0 && warp < 4) {
+        tc_fence_after();
+        project_out(it - 1);
+        tc_fence_before();
+      }
+      compute_sync();                                              // everyone has read the expanded tile
+    }
+    if (n_local > 0 && warp < 4) {
+      mbar_wait(smem_u32(&bar_p[(n_local - 1) & 1]), ((uint32_t)(n_local - 1) >> 1) & 1u);
+      tc_fence_after();
+      project_out(n_local - 1);
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == FB_COMPUTE_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*FbEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
+
+extern "C" int dg_fsrgan_block_infer_supported(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y) {
+  static const char* off = getenv("DG_FSRGAN_BLOCK");
+  if (off && off[0] == '0') return 0;
+  return ctx && ctx->encode_tiled && ctx->cc_major == 10 && dg_valid(x) && dg_valid(y) && x->dtype == DG_BF16 && y->dtype == DG_BF16 &&
+         x->c == FB_C && y->c == FB_C && x->n == y->n && x->h == y->h && x->w == y->w && x->cpitch % 8 == 0 && x->coff % 8 == 0 &&
+         y->cpitch % 8 == 0 && y->coff % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)y->ptr % 16) == 0 && x->h >= 2 && x->w >= 2 &&
+         (long)x->n * x->h * x->w < (1L << 30);
+}
+
+extern "C" int dg_fsrgan_block_infer(dg_ctx* ctx, const dg_tensor* x, const void* w_expand, const float* b_expand, const float* w_dw,
+                                     const float* b_dw, const void* w_project, const float* b_project, const dg_tensor* y, void* stream) {
+  DG_REQUIRE(ctx && w_expand && b_expand && w_dw && b_dw && w_project && b_project, "dg_fsrgan_block_infer: null argument");
+  DG_REQUIRE(dg_fsrgan_block_infer_supported(ctx, x, y), "dg_fsrgan_block_infer: needs bf16 NHWC tensors of %d channels (16-byte aligned pixels) on sm_100", FB_C);
+  DG_REQUIRE(((uintptr_t)w_expand % 16) == 0 && ((uintptr_t)w_project % 16) == 0, "dg_fsrgan_block_infer: kernels must be 16-byte aligned");
+  FbParams P;
+  memset(&P, 0, sizeof(P));
+  uint64_t dims[4] = {(uint64_t)FB_C, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+  uint64_t strides[3] = {(uint64_t)x->cpitch * 2, (uint64_t)x->cpitch * 2 * x->w, (uint64_t)x->cpitch * 2 * x->w * x->h};
+  uint32_t box[4] = {(uint32_t)FB_C, (uint32_t)FB_IW, (uint32_t)FB_IH, 1}, ones[4] = {1, 1, 1, 1};
+  CUresult r = ((FbEncodeFn)ctx->encode_tiled)(&P.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (char*)x->ptr + (size_t)x->coff * 2,
+                                               (const cuuint64_t*)dims, (const cuuint64_t*)strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DG_FAIL("dg_fsrgan_block_infer: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  P.x = (const __nv_bfloat16*)x->ptr + x->coff;
+  P.y = (__nv_bfloat16*)y->ptr + y->coff;
+  P.w1 = (const __nv_bfloat16*)w_expand; P.w2 = (const __nv_bfloat16*)w_project;
+  P.b1 = b_expand; P.wd = w_dw; P.bd = b_dw; P.b2 = b_project;
+  P.xp = x->cpitch; P.yp = y->cpitch; P.N = x->n; P.H = x->h; P.W = x->w;
+  P.tiles_w = (x->w + FB_TW - 1) / FB_TW; P.tiles_h = (x->h + FB_TH - 1) / FB_TH;
+  P.total = P.N * P.tiles_h * P.tiles_w;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fsrgan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);
+    if (e != cudaSuccess) DG_FAIL("dg_fsrgan_block_infer: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(P.total < ctx->sm_count ? P.total : ctx->sm_count);
+  fsrgan_block_kernel<<<grid, FB_THREADS, FB_SMEM, (cudaStream_t)stream>>>(P);
+  DG_CHECK_LAUNCH("dg_fsrgan_block_infer");
+  return 0;
+}

@@ -134,6 +134,7 @@ class Engine:
         self.fold_relu_bwd = os.environ.get("DG_FOLD_RELU_BWD", "1") != "0"    # see Var.n_mask
         self.narrow_store = os.environ.get("DG_NARROW_STORE", "1") != "0"
         self.fuse_d2s_infer = os.environ.get("DG_FUSE_D2S", "1") != "0"     # inference: depth_to_space + PReLU as the up-conv's store pattern
+        self.fuse_fsrgan_block = os.environ.get("DG_FSRGAN_BLOCK", "1") != "0"   # inference: a Fast-SRGAN inverted-residual block as one launch
         # weight gradients of layers with identical geometry (the generator trunk's 32 identical convolutions, the real / fake passes of
         # one discriminator layer) are collected during backward() and launched up to `wgrad_batch` at a time (dg_umma_conv2d_wgrad_batch)
         self.wgrad_batch = max(1, min(4, int(os.environ.get("DG_WGRAD_BATCH", "4"))))
@@ -942,6 +943,42 @@ class Engine:
 
         self._push([x], out, w.group, bwd, params=(w, b))
         return out
+
+    def fsrgan_block_infer(self, x: Var, pset, prefix: str, eps: float = 1e-3) -> Var | None:
+        """Inverted-residual block `prefix` (e.g. "g/b3") of the Fast-SRGAN generator with training=False as ONE launch
+        (fsrgan.py:112-176; dg_fsrgan_block_infer): expand -> BN -> ReLU -> depthwise -> BN -> ReLU -> project -> BN -> + x, the
+        BatchNorms folded into kernels and biases (_fold).  Returns None when the tensors do not qualify (the caller then issues
+        the layer calls)."""
+        if not (self.fuse_fsrgan_block and self.fold_bn_infer and self.use_umma and x.t.dtype == torch.bfloat16 and x.segs is None):
+            return None
+        we, be = pset[prefix + "/expand/kernel"], pset[prefix + "/expand/bias"]
+        wd, bd = pset[prefix + "/dw/kernel"], pset[prefix + "/dw/bias"]
+        wp, bp = pset[prefix + "/project/kernel"], pset[prefix + "/project/bias"]
+        if tuple(we.shape) != (1, 1, 32, 192) or tuple(wd.shape) != (3, 3, 192, 1) or tuple(wp.shape) != (1, 1, 192, 32) or x.shape[3] != 32:
+            return None
+        seq = self._next()
+        y = self.buf((seq, "y"), x.shape, torch.bfloat16)
+        tx, ty = tensor(x.t), tensor(y)
+        if not self.lib.dg_fsrgan_block_infer_supported(self.ctx, C.byref(tx), C.byref(ty)):
+            return None
+        fe = self._fold(we, be, pset, prefix + "/expand_bn", eps, axis=3)
+        fd = self._fold(wd, bd, pset, prefix + "/dw_bn", eps, axis=2)
+        fp = self._fold(wp, bp, pset, prefix + "/project_bn", eps, axis=3)
+        ver = (fe[0], fd[0], fp[0])
+        ent = self._folded.get(("fsrgan_block", prefix))
+        if ent is None or ent[0] != ver:
+            # output-channel-major bf16 copies of the two 1x1 kernels (the K-major B operands of the two products); addresses are
+            # kept across parameter updates (they may be baked into a captured graph)
+            w1 = fe[1].view(32, 192).t().contiguous().to(torch.bfloat16)
+            w2 = fp[1].view(192, 32).t().contiguous().to(torch.bfloat16)
+            if ent is None:
+                ent = [ver, w1, w2]
+            else:
+                ent[1].copy_(w1); ent[2].copy_(w2); ent[0] = ver
+            self._folded[("fsrgan_block", prefix)] = ent
+        check(self.lib.dg_fsrgan_block_infer(self.ctx, C.byref(tx), ent[1].data_ptr(), fe[2].data_ptr(), fd[1].data_ptr(), fd[2].data_ptr(),
+                                             ent[2].data_ptr(), fp[2].data_ptr(), C.byref(ty), self.st))
+        return Var(y, self._deps([x], we.group), seq)     # inference only: no tape node
 
     def dwconv3x3(self, x: Var, w: Param, b: Param | None, bn=False, post: dict | None = None) -> Var:
         """keras DepthwiseConv2D(3, padding='same').  `bn` / `post` as for conv2d: at inference the BatchNorm (+ ReLU) that follows

@@ -124,6 +124,12 @@ class FastSRGANGenerator(_Net):
         r = c1
         for i in range(self.n_blocks):
             t = r
+            if i and not training:
+                # inference: expand -> depthwise -> project -> add as one launch, the 192-channel intermediates never reach HBM
+                fused = E.fsrgan_block_infer(r, p, f"g/b{i}")
+                if fused is not None:
+                    r = fused
+                    continue
             if i:
                 t = E.conv2d(t, p[f"g/b{i}/expand/kernel"], p[f"g/b{i}/expand/bias"], bn=self._bn(f"g/b{i}/expand_bn", training, momentum=0.999),
                              post=dict(act="relu"))

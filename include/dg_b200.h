@@ -184,6 +184,14 @@ int dg_dwconv3x3_fwd(dg_ctx*, const dg_tensor* x, const float* w, const float* b
 /* DepthwiseConv2D + bias + ReLU in one pass: inference form of fsrgan.py:149-155 with the BatchNorm affine folded into the
  * kernel and bias (infer_video.py:146 runs the model with training=False).  act: DG_ACT_NONE or DG_ACT_RELU. */
 int dg_dwconv3x3_fwd_act(dg_ctx*, const dg_tensor* x, const float* w_33c, const float* bias, int act, const dg_tensor* y, void* stream);
+/* Inverted-residual block of the Fast-SRGAN generator at inference as ONE launch (fsrgan.py:112-176 under training=False,
+ * infer_video.py:92-97,146): y = x + project(relu(depthwise3x3(relu(expand(x))))) with the three BatchNorms folded into the
+ * kernels / biases by the caller.  x, y: bf16 NHWC, 32 channels.  w_expand: bf16 [192][32] (output-channel major),
+ * w_dw: fp32 [3*3][192], w_project: bf16 [32][192]; biases fp32.  The 192-channel intermediates stay in shared / tensor memory.
+ * dg_fsrgan_block_infer_supported() is 1 when the tensors qualify (otherwise the caller issues the three layer calls). */
+int dg_fsrgan_block_infer_supported(dg_ctx*, const dg_tensor* x, const dg_tensor* y);
+int dg_fsrgan_block_infer(dg_ctx*, const dg_tensor* x, const void* w_expand, const float* b_expand, const float* w_dw, const float* b_dw,
+                          const void* w_project, const float* b_project, const dg_tensor* y, void* stream);
 int dg_dwconv3x3_dgrad(dg_ctx*, const dg_tensor* dy, const float* w, const dg_tensor* dx, void* stream);
 size_t dg_dwconv3x3_wgrad_workspace_bytes(const dg_tensor* x);
 int dg_dwconv3x3_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, int accumulate,
