@@ -109,6 +109,7 @@ SIGNATURES = {
     "dg_umma_conv2d_wgrad_batch": (_i, [_P, _i, _P, _P, _P, _P, _CP, _P, _P, _sz, _P]),
     "dg_dwconv3x3_fwd": (_i, [_P, _T, _P, _P, _T, _P]),
     "dg_fsrgan_block_infer_supported": (_i, [_P, _T, _T]),
+    "dg_debug_fsrgan_block_timeline": (None, [_P]),
     "dg_fsrgan_block_infer": (_i, [_P, _T, _P, _P, _P, _P, _P, _P, _T, _P]),
     "dg_dwconv3x3_fwd_act": (_i, [_P, _T, _P, _P, _i, _T, _P]),
     "dg_dwconv3x3_dgrad": (_i, [_P, _T, _P, _T, _P]),

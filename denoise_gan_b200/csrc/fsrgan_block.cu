@@ -7,20 +7,29 @@
 // 168 MB in and 168 MB out.
 //
 // One persistent CTA per SM walks 16 x 8 output tiles:
-//   control warp : TMA of the (8+2) x (16+2) x 32 halo tile (2-stage ring, out-of-image pixels zero-filled), and the two
-//                  tcgen05 products -- expand: [256 halo rows (180 used)] x 32 . 32 x 192 -> TMEM (2 x 192 columns),
-//                  project: [128 output pixels] x 192 . 192 x 32 -> TMEM (2 x 32 columns, double-buffered);
-//   12 compute warps, per tile:
-//     E  accumulator -> + bias, ReLU, zero for out-of-image pixels (the depthwise convolution pads ITS input with zeros,
-//        not relu(bias)) -> bf16 [180][192] in shared memory (pixel pitch 400 B: conflict-free 16-byte stores);
+//   control warp : TMA of the (8+2) x (16+2) x 32 halo tile (2-stage ring, out-of-image pixels zero-filled), and the
+//                  tcgen05 products -- expand: ones . bias (the fp32 bias as two bf16 terms), then [256 halo rows (180 used)] x 32 .
+//                  32 x 192 -> TMEM (2 x 192 columns); project: [128 output pixels] x 192 . 192 x 32 -> TMEM (2 x 32 columns,
+//                  double-buffered);
+//   12 compute warps, per tile (E and D below); four epilogue warps (the control warp is one of them) run P a tile behind:
+//     E  accumulator -> ReLU, zero for out-of-image pixels (the depthwise convolution pads ITS input with zeros, not
+//        relu(bias)) -> fp16 [180][192] in shared memory (pixel pitch 400 B: conflict-free 16-byte stores);
 //     D  depthwise 3x3 on CUDA cores: a thread owns a channel pair and two output rows, rolling 4 x 3 window in registers,
-//        packed fp32x2 FMAs (FFMA2), fp32 accumulate as dg_dwconv3x3_fwd_act; + bias, ReLU -> bf16 straight into the
-//        128-byte-swizzled K-major A operand of the project product;
-//     P  (tile i-1, four warps) accumulator + bias + block input (re-read from L2) -> bf16 -> global.
+//        packed half-precision FMAs (HFMA2, the ninth with ReLU) -> straight into the 128-byte-swizzled K-major A operand
+//        of the project product;
+//     P  (tile i-1, epilogue warps) accumulator + bias + block input (re-read from L2) -> bf16 -> global; its TMEM / L2 latencies
+//        never stall the compute warps.
 //   The expand product of tile i+1 runs under D(i), the project product of tile i under E(i+1): the tensor pipe is never
-//   waited for.  The kernel is bound by the CUDA-core depthwise stage (FP32 pipe), not by HBM.
+//   waited for.
+// Why fp16 inside: the kernel is bound by the CUDA-core depthwise stage.  With fp32 FMAs (fma.rn.f32x2: the FP32 pipe retires 64
+// FMAs per clock and SM either way) D took 3790 of a tile's 6875 cycles (tools/fsrgan_block_timeline.py, profiles/); HFMA2 runs
+// at twice that rate and needs no unpacking.  The two intermediates are stored as fp16 (11 mantissa bits against bf16's 8 in
+// the three-launch path; conversions saturate to +-65504, activations here are O(1)) -- the precision of the reference's own
+// 'mixed_float16' policy (train_fsrgan.py:314, --fp16) -- and the nine-tap sum is accumulated in fp16: its rounding (<= 9 x 2^-12
+// of the partial sum) is of the order of the bf16 rounding of the three-launch path's stored result.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "dg_common.cuh"
@@ -33,15 +42,17 @@ constexpr int FB_C = 32, FB_E = 192;                  // block channels, expande
 constexpr int FB_TW = 16, FB_TH = 8;                  // output tile
 constexpr int FB_IW = FB_TW + 2, FB_IH = FB_TH + 2;   // halo tile
 constexpr int FB_HALO = FB_IW * FB_IH;                // 180 rows of the expand product
-constexpr int FB_COMPUTE_WARPS = 12, FB_THREADS = (FB_COMPUTE_WARPS + 1) * 32;
+constexpr int FB_COMPUTE_WARPS = 12, FB_EPI_WARPS = 4, FB_THREADS = (FB_COMPUTE_WARPS + FB_EPI_WARPS) * 32;   // warp 12: control + epilogue
 constexpr uint32_t FB_PITCH = 400;                    // bytes per pixel of the expanded tile (384 + 16: bank spread)
-constexpr uint32_t OFF_W1 = 0;                        // expand B operand: 192 rows x 64 B, 64-byte swizzle
-constexpr uint32_t OFF_W2 = 12288;                    // project B operand: 3 K blocks x (32 rows x 128 B), 128-byte swizzle
-constexpr uint32_t OFF_A = 24576;                     // project A operand: 3 K blocks x (128 rows x 128 B)
+constexpr uint32_t OFF_W1 = 0;                        // expand B operand: 192 rows x 64 B (bf16), 64-byte swizzle
+constexpr uint32_t OFF_WB = 12288;                    // expand bias as a B operand: row n = {hi(b[n]), lo(b[n]), 0 ...} (bf16), same layout
+constexpr uint32_t OFF_W2 = 24576;                    // project B operand: 3 K blocks x (32 rows x 128 B) (fp16), 128-byte swizzle
+constexpr uint32_t OFF_ONES = 36864;                  // A operand of the bias product: 128 rows x 64 B, {1, 1, 0 ...} (bf16)
+constexpr uint32_t OFF_A = 45056;                     // project A operand: 3 K blocks x (128 rows x 128 B) (fp16)
 constexpr uint32_t OFF_X = OFF_A + 3 * 16384;         // halo stages: 2 x 16 KB (256 rows x 64 B addressed by the product, 180 written)
-constexpr uint32_t OFF_I = OFF_X + 2 * 16384;         // expanded tile
-constexpr uint32_t OFF_B = OFF_I + ((FB_HALO * FB_PITCH + 127u) & ~127u);   // biases: expand[192], project[32] (fp32)
-constexpr uint32_t FB_SMEM = OFF_B + (FB_E + FB_C) * 4 + 1024;
+constexpr uint32_t OFF_I = OFF_X + 2 * 16384;         // expanded tile (fp16)
+constexpr uint32_t OFF_B = OFF_I + ((FB_HALO * FB_PITCH + 127u) & ~127u);   // project bias [32] (fp32)
+constexpr uint32_t FB_SMEM = OFF_B + FB_C * 4 + 1024;
 constexpr uint32_t X_BYTES = FB_HALO * FB_C * 2;
 constexpr uint32_t TM_E = 0, TM_P = 2 * FB_E;         // TMEM columns: expand accumulators (2 x 192), project accumulators (2 x 32)
 
@@ -49,36 +60,34 @@ struct FbParams {
   CUtensorMap xmap;
   const __nv_bfloat16* x;       // block input (residual), pixel pitch xp, channel offset already applied
   const __nv_bfloat16* w1;      // [192][32]  expand kernel, BatchNorm folded, K-major
-  const __nv_bfloat16* w2;      // [32][192]  project kernel, BatchNorm folded, K-major
+  const __half* w2;             // [32][192]  project kernel, BatchNorm folded, K-major, fp16
   const float* b1;              // [192]
   const float* wd;              // [9][192]   depthwise kernel, BatchNorm folded
   const float* bd;              // [192]
   const float* b2;              // [32]
   __nv_bfloat16* y;
   int xp, yp, N, H, W, tiles_w, tiles_h, total;
+  long long* dbg;               // clock64 marks of CTA 0 ([16 tiles][8]; tools/fsrgan_block_timeline.py), or null
 };
 
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-  u64 d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ u64 bf2_to_f2(uint32_t v) {     // bf16x2 -> fp32x2 (low half = lower channel)
-  u64 d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(v << 16), "r"(v & 0xffff0000u));
+__device__ __forceinline__ uint32_t relu_pack_h2(uint32_t lo, uint32_t hi) {     // fp32 bits -> max(v, 0), saturated to the fp16 range -> f16x2
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
   return d;
 }
-__device__ __forceinline__ uint32_t relu_pack(u64 v) {     // max(v, 0) -> bf16x2
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  __nv_bfloat162 r = __floats2bfloat162_rn(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
-  return *reinterpret_cast<uint32_t*>(&r);
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
@@ -89,11 +98,14 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void fb_mark(const FbParams& P, int it, int slot) {
+  if (P.dbg && blockIdx.x == 0 && it < 16) P.dbg[it * 8 + slot] = clock64();
+}
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FB_COMPUTE_WARPS * 32) : "memory"); }
 
 __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __grid_constant__ FbParams P) {
   extern __shared__ uint8_t fb_raw[];
-  __shared__ __align__(8) uint64_t bar_x[2], bar_e, bar_efree, bar_a, bar_p[2];
+  __shared__ __align__(8) uint64_t bar_x[2], bar_e, bar_efree, bar_a, bar_p[2], bar_pfree[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(fb_raw) + 1023u) & ~1023u;
@@ -106,6 +118,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
     mbar_init(smem_u32(&bar_efree), FB_COMPUTE_WARPS);
     mbar_init(smem_u32(&bar_a), FB_COMPUTE_WARPS);
     mbar_init(smem_u32(&bar_p[0]), 1); mbar_init(smem_u32(&bar_p[1]), 1);
+    mbar_init(smem_u32(&bar_pfree[0]), FB_EPI_WARPS); mbar_init(smem_u32(&bar_pfree[1]), FB_EPI_WARPS);
     fence_mbar_init();
     tma_prefetch_desc(&P.xmap);
   }
@@ -124,8 +137,24 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.w2) + i);
     *reinterpret_cast<uint4*>(gen + OFF_W2 + kb * 4096 + n * 128 + ((cc ^ (n & 7)) << 4)) = v;
   }
+  // the expand bias rides on the tensor pipe: accumulator = ones[128 x 16] . biasB[16 x 192] before the x . W1 product, the fp32
+  // bias split into two bf16 terms (hi + lo: 16 mantissa bits) in K elements 0 and 1; E then has no per-element add
+  for (int i = tid; i < FB_E * 4; i += FB_THREADS) {
+    const int n = i >> 2, c = i & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c == 0) {
+      const float b = P.b1[n];
+      const __nv_bfloat16 hi = __float2bfloat16(b), lo = __float2bfloat16(b - __bfloat162float(hi));
+      v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    }
+    *reinterpret_cast<uint4*>(gen + OFF_WB + n * 64 + ((c ^ ((n >> 1) & 3)) << 4)) = v;
+  }
+  for (int i = tid; i < 128 * 4; i += FB_THREADS) {
+    const int r = i >> 2, c = i & 3;
+    *reinterpret_cast<uint4*>(gen + OFF_ONES + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = make_uint4(c == 0 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+  }
   float* bias_s = reinterpret_cast<float*>(gen + OFF_B);
-  for (int i = tid; i < FB_E + FB_C; i += FB_THREADS) bias_s[i] = i < FB_E ? P.b1[i] : P.b2[i - FB_E];
+  for (int i = tid; i < FB_C; i += FB_THREADS) bias_s[i] = P.b2[i];
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -138,9 +167,53 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
     n = t2 / P.tiles_h; h0 = th * FB_TH; w0 = tw * FB_TW;
   };
 
+  // P(it): one output pixel per thread of the four epilogue warps (TMEM lane quarter q = warp % 4)
+  auto project_out = [&](int it, int q) {
+    int n, h0, w0;
+    tile_coords(it, n, h0, w0);
+    uint32_t v[32];
+    tmem_ld_32x32(tmem + TM_P + (uint32_t)(it & 1) * FB_C + ((uint32_t)(q * 32) << 16), v);
+    const int r = q * 32 + lane, h = h0 + (r >> 4), w = w0 + (r & 15);
+    const bool ok = h < P.H && w < P.W;
+    const long pix = ((long)n * P.H + h) * P.W + w;
+    uint4 res[4];
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) res[k] = __ldg(reinterpret_cast<const uint4*>(P.x + pix * P.xp) + k);
+    }
+    tmem_ld_wait();
+    if (ok) {
+      const float* b2 = reinterpret_cast<const float*>(gen + OFF_B);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t rr[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = k * 8 + e * 2;
+          const float lo = __uint_as_float(v[c]) + b2[c] + __uint_as_float(rr[e] << 16);
+          const float hi = __uint_as_float(v[c + 1]) + b2[c + 1] + __uint_as_float(rr[e] & 0xffff0000u);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+          o[e] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        reinterpret_cast<uint4*>(P.y + pix * P.yp)[k] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  };
+  auto epilogue_tile = [&](int it, int q) {
+    mbar_wait(smem_u32(&bar_p[it & 1]), ((uint32_t)it >> 1) & 1u);
+    tc_fence_after();
+    project_out(it, q);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_pfree[it & 1]));
+  };
+
   if (warp == FB_COMPUTE_WARPS) {
-    // ------------------------------------------------------------------ control warp (whole warp, tcgen05 / TMA under elect_one)
-    const uint32_t idesc_e = make_idesc_bf16(128, FB_E, 0, 0), idesc_p = make_idesc_bf16(128, FB_C, 0, 0);
+    // ------------------------------------------------------------------ control warp (whole warp, tcgen05 / TMA under elect_one);
+    // between its two waits per tile it is also the epilogue warp of TMEM lane quarter 0
+    const uint32_t idesc_e = make_idesc_bf16(128, FB_E, 0, 0);
+    const uint32_t idesc_p = (1u << 4) | ((uint32_t)(FB_C >> 3) << 17) | ((128u >> 4) << 24);   // fp16 A and B (format 0), fp32 accumulate
     const uint64_t hi64 = make_smem_desc_hi(512, LAYOUT_SW64) << 32, hi128 = make_smem_desc_hi(1024, LAYOUT_SW128) << 32;
     const uint32_t lbo16 = 1u << 16;
     auto load_x = [&](int it) {
@@ -152,12 +225,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
     };
     auto mma_expand = [&](int it) {
       const uint32_t a16 = ((base + OFF_X + (uint32_t)(it & 1) * 16384u) >> 4) | lbo16, b16 = ((base + OFF_W1) >> 4) | lbo16;
+      const uint32_t o16 = ((base + OFF_ONES) >> 4) | lbo16, wb16 = ((base + OFF_WB) >> 4) | lbo16;
 #pragma unroll
-      for (int mb = 0; mb < 2; ++mb)
+      for (int mb = 0; mb < 2; ++mb) {
+        umma_f16(tmem + TM_E + (uint32_t)mb * FB_E, hi64 | (uint64_t)o16, hi64 | (uint64_t)wb16, idesc_e, 0u);      // bias
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-          umma_f16(tmem + TM_E + (uint32_t)mb * FB_E, hi64 | (uint64_t)(a16 + (uint32_t)mb * 512u + 2u * k), hi64 | (uint64_t)(b16 + 2u * k), idesc_e,
-                   k != 0);
+          umma_f16(tmem + TM_E + (uint32_t)mb * FB_E, hi64 | (uint64_t)(a16 + (uint32_t)mb * 512u + 2u * k), hi64 | (uint64_t)(b16 + 2u * k), idesc_e, 1u);
+      }
       umma_commit(smem_u32(&bar_e));
     };
     auto mma_project = [&](int it) {
@@ -184,6 +259,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
     for (int it = 0; it < n_local; ++it) {
       mbar_wait(smem_u32(&bar_efree), (uint32_t)it & 1u);        // E(it) has read the expand accumulators
       tc_fence_after();
+      if (lane == 0) fb_mark(P, it, 4);
       if (it + 1 < n_local) {
         mbar_wait(smem_u32(&bar_x[(it + 1) & 1]), ((uint32_t)(it + 1) >> 1) & 1u);
         tc_fence_after();
@@ -192,143 +268,125 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
       }
       if (it + 2 < n_local && elect_one()) load_x(it + 2);       // its stage was read by the expand product of tile it: complete
       __syncwarp();
+      if (it > 0) epilogue_tile(it - 1, 0);                      // well inside D(it): the A operand of tile it is not ready before
+      if (lane == 0) fb_mark(P, it, 5);
       mbar_wait(smem_u32(&bar_a), (uint32_t)it & 1u);            // D(it) has written the A operand
+      if (lane == 0) fb_mark(P, it, 6);
+      if (it >= 2) mbar_wait(smem_u32(&bar_pfree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // P(it-2) has read this accumulator
       tc_fence_after();
       if (elect_one()) mma_project(it);
       __syncwarp();
     }
+    if (n_local > 0) epilogue_tile(n_local - 1, 0);
+  } else if (warp > FB_COMPUTE_WARPS) {
+    // ------------------------------------------------------------------ epilogue warps of lane quarters 1..3
+    for (int it = 0; it < n_local; ++it) epilogue_tile(it, warp & 3);
   } else {
     // ------------------------------------------------------------------ compute warps
     const int q = warp & 3, j3 = warp >> 2;        // E: TMEM lane quarter, 64-column third
     const int g = warp % 3, rg = warp / 3;         // D: 64-channel group, output rows 2rg, 2rg+1
     const int cpair = g * 32 + lane;               // channel pair (channels 2cpair, 2cpair+1)
-    u64 wk[9], bdw;
+    uint32_t wk[9], bdw;                           // f16x2
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wk[t] = pack2(P.wd[t * FB_E + 2 * cpair], P.wd[t * FB_E + 2 * cpair + 1]);
-    bdw = pack2(P.bd[2 * cpair], P.bd[2 * cpair + 1]);
+    for (int t = 0; t < 9; ++t) wk[t] = pack_h2(P.wd[t * FB_E + 2 * cpair], P.wd[t * FB_E + 2 * cpair + 1]);
+    bdw = pack_h2(P.bd[2 * cpair], P.bd[2 * cpair + 1]);
     const uint32_t inter = base + OFF_I, abuf = base + OFF_A;
-
-    auto project_out = [&](int it) {               // P(it): warps 0..3, one output pixel per thread
-      int n, h0, w0;
-      tile_coords(it, n, h0, w0);
-      uint32_t v[32];
-      tmem_ld_32x32(tmem + TM_P + (uint32_t)(it & 1) * FB_C + ((uint32_t)(q * 32) << 16), v);
-      const int r = q * 32 + lane, h = h0 + (r >> 4), w = w0 + (r & 15);
-      const bool ok = h < P.H && w < P.W;
-      const long pix = ((long)n * P.H + h) * P.W + w;
-      uint4 res[4];
-      if (ok) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) res[k] = __ldg(reinterpret_cast<const uint4*>(P.x + pix * P.xp) + k);
-      }
-      tmem_ld_wait();
-      if (ok) {
-        const float* b2 = bias_s + FB_E;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t rr[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
-          uint32_t o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = k * 8 + e * 2;
-            const float lo = __uint_as_float(v[c]) + b2[c] + __uint_as_float(rr[e] << 16);
-            const float hi = __uint_as_float(v[c + 1]) + b2[c + 1] + __uint_as_float(rr[e] & 0xffff0000u);
-            __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-            o[e] = *reinterpret_cast<uint32_t*>(&pk);
-          }
-          reinterpret_cast<uint4*>(P.y + pix * P.yp)[k] = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    };
+    const int n_units = q * 32 < FB_HALO - 128 ? 4 : 2;            // 32-column batches of this warp: rows 180..255 are not part of the tile
 
     for (int it = 0; it < n_local; ++it) {
       int n, h0, w0;
       tile_coords(it, n, h0, w0);
-      // ---- E(it): expand accumulators -> bf16 expanded tile
+      // ---- E(it): expand accumulators -> + bias, ReLU -> bf16 expanded tile.  Batch u = (M block u/2, 32 columns u%2); the load
+      // of batch u+1 is in flight while batch u is converted.
       mbar_wait(smem_u32(&bar_e), (uint32_t)it & 1u);
       tc_fence_after();
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        if (mb == 1 && q * 32 >= FB_HALO - 128) continue;          // rows 180..255 of the product are not part of the tile
-        const int row = mb * 128 + q * 32 + lane;
-        const int hh = row / FB_IW, ww = row - hh * FB_IW;
-        const int h = h0 - 1 + hh, w = w0 - 1 + ww;
-        const bool in_tile = row < FB_HALO;
-        const bool in_img = h >= 0 && h < P.H && w >= 0 && w < P.W;
-        const uint32_t dst = inter + (uint32_t)row * FB_PITCH + (uint32_t)j3 * 128u;
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem + TM_E + (uint32_t)mb * FB_E + (uint32_t)(j3 * 64 + b * 32) + ((uint32_t)(q * 32) << 16), v);
-          tmem_ld_wait();
-          const float* b1 = bias_s + j3 * 64 + b * 32;
-          if (in_tile) {
+      if (tid == 0) fb_mark(P, it, 0);
+      {
+        uint32_t v[2][32];
+        auto ld = [&](int u, uint32_t (&dst)[32]) {
+          tmem_ld_32x32(tmem + TM_E + (uint32_t)(u >> 1) * FB_E + (uint32_t)(j3 * 64 + (u & 1) * 32) + ((uint32_t)(q * 32) << 16), dst);
+        };
+        auto conv = [&](int u, const uint32_t (&src)[32]) {
+          const int row = (u >> 1) * 128 + q * 32 + lane;
+          const int hh = row / FB_IW, ww = row - hh * FB_IW;
+          const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+          if (row >= FB_HALO) return;
+          const uint32_t dst = inter + (uint32_t)row * FB_PITCH + (uint32_t)j3 * 128u + (uint32_t)(u & 1) * 64u;
+          if (h >= 0 && h < P.H && w >= 0 && w < P.W) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               uint32_t o[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = k * 8 + e * 2;
-                const float lo = fmaxf(__uint_as_float(v[c]) + b1[c], 0.f), hi = fmaxf(__uint_as_float(v[c + 1]) + b1[c + 1], 0.f);
-                __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-                o[e] = in_img ? *reinterpret_cast<uint32_t*>(&pk) : 0u;
-              }
-              sts128(dst + (uint32_t)(b * 64 + k * 16), make_uint4(o[0], o[1], o[2], o[3]));
+              for (int e = 0; e < 4; ++e) o[e] = relu_pack_h2(src[k * 8 + e * 2], src[k * 8 + e * 2 + 1]);
+              sts128(dst + (uint32_t)k * 16u, make_uint4(o[0], o[1], o[2], o[3]));
             }
+          } else {
+            // outside the image the depthwise convolution sees ZERO padding, not relu(bias)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sts128(dst + (uint32_t)k * 16u, make_uint4(0u, 0u, 0u, 0u));
           }
+        };
+        ld(0, v[0]);
+        ld(1, v[1]);
+        tmem_ld_wait();
+        conv(0, v[0]);
+        if (n_units == 4) ld(2, v[0]);
+        conv(1, v[1]);
+        if (n_units == 4) {
+          ld(3, v[1]);
+          tmem_ld_wait();
+          conv(2, v[0]);
+          conv(3, v[1]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_efree));
+      if (tid == 0) fb_mark(P, it, 1);
       compute_sync();                                              // the expanded tile is complete
-      if (it > 0) {                                                // project product of tile it-1: A operand free, accumulator ready
-        mbar_wait(smem_u32(&bar_p[(it - 1) & 1]), ((uint32_t)(it - 1) >> 1) & 1u);
-      }
+      if (it > 0) mbar_wait(smem_u32(&bar_p[(it - 1) & 1]), ((uint32_t)(it - 1) >> 1) & 1u);   // project product of tile it-1 has read the A operand
       // ---- D(it): depthwise 3x3 + bias + ReLU -> A operand of the project product
+      if (tid == 0) fb_mark(P, it, 2);
       {
         const uint32_t src = inter + (uint32_t)(2 * rg * FB_IW) * FB_PITCH + (uint32_t)cpair * 4u;
-        u64 win[4][3];
+        uint32_t win[4][4];                          // f16x2, straight from shared memory; column c+3 is loaded one step ahead
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          win[r][0] = bf2_to_f2(lds32(src + (uint32_t)(r * FB_IW + 0) * FB_PITCH));
-          win[r][1] = bf2_to_f2(lds32(src + (uint32_t)(r * FB_IW + 1) * FB_PITCH));
+          win[r][0] = lds32(src + (uint32_t)(r * FB_IW + 0) * FB_PITCH);
+          win[r][1] = lds32(src + (uint32_t)(r * FB_IW + 1) * FB_PITCH);
+          win[r][2] = lds32(src + (uint32_t)(r * FB_IW + 2) * FB_PITCH);
         }
         const uint32_t arow0 = abuf + (uint32_t)g * 16384u + (uint32_t)(2 * rg * FB_TW) * 128u + (uint32_t)(lane & 3) * 4u;
 #pragma unroll
         for (int c = 0; c < FB_TW; ++c) {
+          if (c + 3 < FB_IW) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) win[r][(c + 2) % 3] = bf2_to_f2(lds32(src + (uint32_t)(r * FB_IW + c + 2) * FB_PITCH));
-          u64 a0 = bdw, a1 = bdw;
+            for (int r = 0; r < 4; ++r) win[r][(c + 3) % 4] = lds32(src + (uint32_t)(r * FB_IW + c + 3) * FB_PITCH);
+          }
+          uint32_t a0 = bdw, a1 = bdw;
 #pragma unroll
           for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
-              a0 = ffma2(win[a][(c + b) % 3], wk[a * 3 + b], a0);
-              a1 = ffma2(win[a + 1][(c + b) % 3], wk[a * 3 + b], a1);
+              if (a * 3 + b < 8) {
+                a0 = hfma2(win[a][(c + b) % 4], wk[a * 3 + b], a0);
+                a1 = hfma2(win[a + 1][(c + b) % 4], wk[a * 3 + b], a1);
+              } else {                                  // the ninth tap carries the ReLU
+                a0 = hfma2_relu(win[a][(c + b) % 4], wk[a * 3 + b], a0);
+                a1 = hfma2_relu(win[a + 1][(c + b) % 4], wk[a * 3 + b], a1);
+              }
             }
           // output pixel rows 2rg*16 + c and (2rg+1)*16 + c of the 128-row A operand; 16-byte chunk lane/4, XOR row%8
           const uint32_t r0 = (uint32_t)(2 * rg * FB_TW + c);
-          sts32(arow0 + (uint32_t)c * 128u + ((((uint32_t)lane >> 2) ^ (r0 & 7u)) << 4), relu_pack(a0));
-          sts32(arow0 + (uint32_t)(c + FB_TW) * 128u + ((((uint32_t)lane >> 2) ^ ((r0 + FB_TW) & 7u)) << 4), relu_pack(a1));
+          sts32(arow0 + (uint32_t)c * 128u + ((((uint32_t)lane >> 2) ^ (r0 & 7u)) << 4), a0);
+          sts32(arow0 + (uint32_t)(c + FB_TW) * 128u + ((((uint32_t)lane >> 2) ^ ((r0 + FB_TW) & 7u)) << 4), a1);
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_a));
-      // ---- P(it-1)
-      if (it > 0 && warp < 4) {
-        tc_fence_after();
-        project_out(it - 1);
-        tc_fence_before();
-      }
+      if (tid == 0) fb_mark(P, it, 3);
       compute_sync();                                              // everyone has read the expanded tile
-    }
-    if (n_local > 0 && warp < 4) {
-      mbar_wait(smem_u32(&bar_p[(n_local - 1) & 1]), ((uint32_t)(n_local - 1) >> 1) & 1u);
-      tc_fence_after();
-      project_out(n_local - 1);
-      tc_fence_before();
     }
   }
   __syncthreads();
@@ -342,6 +400,9 @@ typedef CUresult (*FbEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 }  // namespace
+
+static long long* g_fb_dbg = nullptr;
+extern "C" void dg_debug_fsrgan_block_timeline(long long* buf) { g_fb_dbg = buf; }
 
 extern "C" int dg_fsrgan_block_infer_supported(dg_ctx* ctx, const dg_tensor* x, const dg_tensor* y) {
   static const char* off = getenv("DG_FSRGAN_BLOCK");
@@ -368,11 +429,12 @@ extern "C" int dg_fsrgan_block_infer(dg_ctx* ctx, const dg_tensor* x, const void
   if (r != CUDA_SUCCESS) DG_FAIL("dg_fsrgan_block_infer: cuTensorMapEncodeTiled failed (%d)", (int)r);
   P.x = (const __nv_bfloat16*)x->ptr + x->coff;
   P.y = (__nv_bfloat16*)y->ptr + y->coff;
-  P.w1 = (const __nv_bfloat16*)w_expand; P.w2 = (const __nv_bfloat16*)w_project;
+  P.w1 = (const __nv_bfloat16*)w_expand; P.w2 = (const __half*)w_project;
   P.b1 = b_expand; P.wd = w_dw; P.bd = b_dw; P.b2 = b_project;
   P.xp = x->cpitch; P.yp = y->cpitch; P.N = x->n; P.H = x->h; P.W = x->w;
   P.tiles_w = (x->w + FB_TW - 1) / FB_TW; P.tiles_h = (x->h + FB_TH - 1) / FB_TH;
   P.total = P.N * P.tiles_h * P.tiles_w;
+  P.dbg = g_fb_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fsrgan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);

@@ -967,10 +967,10 @@ class Engine:
         ver = (fe[0], fd[0], fp[0])
         ent = self._folded.get(("fsrgan_block", prefix))
         if ent is None or ent[0] != ver:
-            # output-channel-major bf16 copies of the two 1x1 kernels (the K-major B operands of the two products); addresses are
+            # output-channel-major copies of the two 1x1 kernels (the K-major B operands of the two products: bf16 / fp16); addresses are
             # kept across parameter updates (they may be baked into a captured graph)
             w1 = fe[1].view(32, 192).t().contiguous().to(torch.bfloat16)
-            w2 = fp[1].view(192, 32).t().contiguous().to(torch.bfloat16)
+            w2 = fp[1].view(192, 32).t().contiguous().to(torch.float16)
             if ent is None:
                 ent = [ver, w1, w2]
             else:

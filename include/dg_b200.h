@@ -187,9 +187,12 @@ int dg_dwconv3x3_fwd_act(dg_ctx*, const dg_tensor* x, const float* w_33c, const 
 /* Inverted-residual block of the Fast-SRGAN generator at inference as ONE launch (fsrgan.py:112-176 under training=False,
  * infer_video.py:92-97,146): y = x + project(relu(depthwise3x3(relu(expand(x))))) with the three BatchNorms folded into the
  * kernels / biases by the caller.  x, y: bf16 NHWC, 32 channels.  w_expand: bf16 [192][32] (output-channel major),
- * w_dw: fp32 [3*3][192], w_project: bf16 [32][192]; biases fp32.  The 192-channel intermediates stay in shared / tensor memory.
+ * w_dw: fp32 [3*3][192], w_project: FP16 [32][192]; biases fp32.  The 192-channel intermediates stay in shared / tensor memory
+ * as fp16 (saturating), the depthwise taps are accumulated in fp16 (csrc/fsrgan_block.cu explains why).
  * dg_fsrgan_block_infer_supported() is 1 when the tensors qualify (otherwise the caller issues the three layer calls). */
 int dg_fsrgan_block_infer_supported(dg_ctx*, const dg_tensor* x, const dg_tensor* y);
+/* debug aid: clock64 marks of CTA 0's phases ([16 tiles][8] int64) of the next dg_fsrgan_block_infer launches; NULL turns it off */
+void dg_debug_fsrgan_block_timeline(long long* buf);
 int dg_fsrgan_block_infer(dg_ctx*, const dg_tensor* x, const void* w_expand, const float* b_expand, const float* w_dw, const float* b_dw,
                           const void* w_project, const float* b_project, const dg_tensor* y, void* stream);
 int dg_dwconv3x3_dgrad(dg_ctx*, const dg_tensor* dy, const float* w, const dg_tensor* dx, void* stream);
