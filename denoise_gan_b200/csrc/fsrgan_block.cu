@@ -21,10 +21,14 @@
 //        never stall the compute warps.
 //   The expand product of tile i+1 runs under D(i), the project product of tile i under E(i+1): the tensor pipe is never
 //   waited for.
-// Why fp16 inside: the kernel is bound by the CUDA-core depthwise stage.  With fp32 FMAs (fma.rn.f32x2: the FP32 pipe retires 64
-// FMAs per clock and SM either way) D took 3790 of a tile's 6875 cycles (tools/fsrgan_block_timeline.py, profiles/); HFMA2 runs
-// at twice that rate and needs no unpacking.  The two intermediates are stored as fp16 (11 mantissa bits against bf16's 8 in
-// the three-launch path; conversions saturate to +-65504, activations here are O(1)) -- the precision of the reference's own
+// Why fp16 inside: the kernel is bound by the CUDA-core depthwise stage and by shared-memory bandwidth (~370 KB per tile through a
+// 128 B/clock port), not by HBM.  B200 retires 128 FMAs per clock and SM whether they are issued as FFMA, FFMA2 (fma.rn.f32x2) or
+// HFMA2 (probes/fma_rate_probe.cu, profiles/fma_rate_probe_r2.log), so half precision buys no arithmetic rate; what it removes
+// is every other instruction of the stage: with fp32 accumulation a step of the window walk is 4 loads, 8 unpack operations, 18
+// FFMA2, 2 ReLU-converts and 2 stores, with HFMA2 it is 4 loads, 18 HFMA2 (the ninth carries the ReLU) and 2 stores, and E needs
+// no add.  Measured (tools/fsrgan_block_timeline.py, profiles/fsrgan_block_timeline_r2_*.log): D 3790 -> 2730 cycles, E 2090 ->
+// 1110, a tile 6875 -> 4750 cycles.  The two intermediates are stored as fp16 (11 mantissa bits against bf16's 8 in the
+// three-launch path; conversions saturate to +-65504, activations here are O(1)) -- the storage type of the reference's own
 // 'mixed_float16' policy (train_fsrgan.py:314, --fp16) -- and the nine-tap sum is accumulated in fp16: its rounding (<= 9 x 2^-12
 // of the partial sum) is of the order of the bf16 rounding of the three-launch path's stored result.
 #include <cuda.h>
@@ -293,19 +297,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
     const uint32_t inter = base + OFF_I, abuf = base + OFF_A;
     const int n_units = q * 32 < FB_HALO - 128 ? 4 : 2;            // 32-column batches of this warp: rows 180..255 are not part of the tile
 
+    // E reads the accumulator in 32-column batches u = (M block u/2, columns u%2); the first two are requested BEFORE the barrier
+    // that ends the previous tile, so their TMEM latency runs under the barrier skew, and batch u+2 is in flight while u is converted
+    uint32_t v[2][32];
+    auto ld_e = [&](int u, uint32_t (&dst)[32]) {
+      tmem_ld_32x32(tmem + TM_E + (uint32_t)(u >> 1) * FB_E + (uint32_t)(j3 * 64 + (u & 1) * 32) + ((uint32_t)(q * 32) << 16), dst);
+    };
+    auto request_e = [&](int it) {
+      mbar_wait(smem_u32(&bar_e), (uint32_t)it & 1u);
+      tc_fence_after();
+      ld_e(0, v[0]);
+      ld_e(1, v[1]);
+    };
+    if (n_local > 0) request_e(0);
     for (int it = 0; it < n_local; ++it) {
       int n, h0, w0;
       tile_coords(it, n, h0, w0);
-      // ---- E(it): expand accumulators -> + bias, ReLU -> bf16 expanded tile.  Batch u = (M block u/2, 32 columns u%2); the load
-      // of batch u+1 is in flight while batch u is converted.
-      mbar_wait(smem_u32(&bar_e), (uint32_t)it & 1u);
-      tc_fence_after();
+      // ---- E(it): expand accumulators (bias already in them) -> ReLU -> fp16 expanded tile
       if (tid == 0) fb_mark(P, it, 0);
       {
-        uint32_t v[2][32];
-        auto ld = [&](int u, uint32_t (&dst)[32]) {
-          tmem_ld_32x32(tmem + TM_E + (uint32_t)(u >> 1) * FB_E + (uint32_t)(j3 * 64 + (u & 1) * 32) + ((uint32_t)(q * 32) << 16), dst);
-        };
         auto conv = [&](int u, const uint32_t (&src)[32]) {
           const int row = (u >> 1) * 128 + q * 32 + lane;
           const int hh = row / FB_IW, ww = row - hh * FB_IW;
@@ -326,14 +336,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
             for (int k = 0; k < 4; ++k) sts128(dst + (uint32_t)k * 16u, make_uint4(0u, 0u, 0u, 0u));
           }
         };
-        ld(0, v[0]);
-        ld(1, v[1]);
-        tmem_ld_wait();
+        tmem_ld_wait();                 // batches 0 and 1 were requested before the end-of-tile barrier
         conv(0, v[0]);
-        if (n_units == 4) ld(2, v[0]);
+        if (n_units == 4) ld_e(2, v[0]);
         conv(1, v[1]);
         if (n_units == 4) {
-          ld(3, v[1]);
+          ld_e(3, v[1]);
           tmem_ld_wait();
           conv(2, v[0]);
           conv(3, v[1]);
@@ -386,6 +394,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_a));
       if (tid == 0) fb_mark(P, it, 3);
+      if (it + 1 < n_local) request_e(it + 1);                     // expand product of tile it+1: issued under D(it), complete long ago
       compute_sync();                                              // everyone has read the expanded tile
     }
   }
