@@ -214,10 +214,18 @@ def dtype_code(t: torch.Tensor) -> int:
 
 
 def tensor(t: torch.Tensor, c: int | None = None, coff: int = 0) -> DgTensor:
-    """NHWC view descriptor of `t` ([N,H,W,Cpitch], dense); optional logical channel slice."""
-    assert t.is_cuda and t.dim() == 4 and t.is_contiguous(), "expected a dense CUDA NHWC tensor"
-    n, h, w, cp = t.shape
-    return DgTensor(t.data_ptr(), dtype_code(t), n, h, w, cp if c is None else c, cp, coff)
+    """NHWC view descriptor of `t`: a dense [N,H,W,C] tensor (optionally a logical channel slice c / coff of it), or a torch
+    view `buf[..., a:b]` of a dense NHWC buffer (the halves of an in-place U-Net concat): the pixel pitch comes from the strides."""
+    assert t.is_cuda and t.dim() == 4, "expected a CUDA NHWC tensor"
+    n, h, w, cc = t.shape
+    if t.is_contiguous():
+        cp = cc
+    else:
+        sn, sh, sw, sc = t.stride()
+        cp = sw if w > 1 else (sh if h > 1 else sn)
+        assert (sc == 1 and cp >= cc and (w == 1 or sw == cp) and (h == 1 or sh == w * cp) and (n == 1 or sn == h * w * cp)
+                and c is None and coff == 0), "expected a dense NHWC tensor or a channel slice of one"
+    return DgTensor(t.data_ptr(), dtype_code(t), n, h, w, cc if c is None else c, cp, coff)
 
 
 def ptr(t) -> int | None:

@@ -134,6 +134,7 @@ class Engine:
         self.fold_relu_bwd = os.environ.get("DG_FOLD_RELU_BWD", "1") != "0"    # see Var.n_mask
         self.narrow_store = os.environ.get("DG_NARROW_STORE", "1") != "0"
         self.fuse_d2s_infer = os.environ.get("DG_FUSE_D2S", "1") != "0"     # inference: depth_to_space + PReLU as the up-conv's store pattern
+        self.inplace_concat = os.environ.get("DG_INPLACE_CONCAT", "1") != "0"   # pix2pix U-Net: layers write into their half of the concat buffer
         self.fuse_fsrgan_block = os.environ.get("DG_FSRGAN_BLOCK", "1") != "0"   # inference: a Fast-SRGAN inverted-residual block as one launch
         # weight gradients of layers with identical geometry (the generator trunk's 32 identical convolutions, the real / fake passes of
         # one discriminator layer) are collected during backward() and launched up to `wgrad_batch` at a time (dg_umma_conv2d_wgrad_batch)
@@ -366,7 +367,14 @@ class Engine:
         td = _lib.DgTensor(dst.data_ptr(), _lib.DG_F32, 1, 1, 1, n, dst.numel(), 0)
         check(self.lib.dg_copy(self.ctx, C.byref(ts), C.byref(td), 0, self.st))
 
-    def _conv2d_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype, keep=False):
+    def _out_or_buf(self, out, key, shape, dtype) -> torch.Tensor:
+        """The caller's output view (`out=`: the layer writes straight into its channel slice of a U-Net concat buffer) or a pool buffer."""
+        if out is None:
+            return self.buf(key, shape, dtype)
+        assert tuple(out.shape) == tuple(shape) and out.dtype == dtype, f"out= view {tuple(out.shape)} {out.dtype} != {tuple(shape)} {dtype}"
+        return out
+
+    def _conv2d_padded(self, x: Var, w: Param, b: Param | None, stride, pt, pl, Ho, Wo, act, alpha, out_dtype, keep=False, out=None):
         """conv2d when Cin or Cout is not a multiple of 16 (the 3-channel image side of srgan.py:154,182,236): operands are
         zero-padded to 16 channels in bf16 (dg_pad_channels / dg_umma_pack_weights_padded), the tcgen05 kernels run on the
         padded shapes, and results are sliced back (dg_copy views, dg_unpad_weight_grad).  Returns None when the tensor-core
@@ -402,7 +410,8 @@ class Engine:
         seq = self._next()
         assert w.pack_pad in (None, (cin_p, cout_p)) and w.pack_seg in (None, seg), f"{w.name}: used with two different channel layouts"
         w.pack_pad, w.pack_seg = (cin_p, cout_p), seg
-        y = None if keep else self.buf((seq, "y"), (N, Ho, Wo, cout), ydt)
+        assert out is None or (not keep and cout_p == cout), f"{w.name}: out= needs a 16-channel-multiple output"
+        y = None if keep else self._out_or_buf(out, (seq, "y"), (N, Ho, Wo, cout), ydt)
         pad_in = segs is None and (cin_p != cin or x.t.dtype != torch.bfloat16)
         if pad_in:
             xin = self.buf((seq, "xpad"), (N, H, W, cin_p), torch.bfloat16)
@@ -519,7 +528,7 @@ class Engine:
         return ent
 
     def conv2d(self, x: Var, w: Param, b: Param | None = None, *, stride=1, padding="same", act=None, alpha=0.0,
-               out_dtype=None, bn: bool = False, post: dict | None = None, keep_padded: bool = False) -> Var:
+               out_dtype=None, bn: bool = False, post: dict | None = None, keep_padded: bool = False, out: torch.Tensor | None = None) -> Var:
         """keras Conv2D (+bias, +activation epilogue).  `keep_padded`: an output whose channel count is not a multiple of 16
         stays zero-padded (Var.segs) for consumers that understand it (conv2d, maxpool2x2, upsample_concat).  `bn=True`: a training-mode BatchNormalization consumes the result
         next, so the tensor-core epilogue also produces its batch-statistics partials (picked up by bn_act).
@@ -534,12 +543,12 @@ class Engine:
         pt, pl, Ho, Wo = self._conv_geom(H, W, kh, kw, stride, padding)
         if (self.use_umma and self.pad_rgb and (cin % 16 != 0 or cout % 16 != 0 or x.segs is not None) and kh * kw <= 16 and
                 stride in (1, 2) and (stride == 1 or (H % 2 == 0 and W % 2 == 0))):
-            r = self._conv2d_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype, keep=keep_padded)
+            r = self._conv2d_padded(x, w, b, stride, pt, pl, Ho, Wo, act, alpha, out_dtype, keep=keep_padded, out=out)
             if r is not None:
                 return r
         assert x.segs is None, f"{w.name}: physically padded input needs the tensor-core path"
         seq = self._next()
-        y = self.buf((seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
+        y = self._out_or_buf(out, (seq, "y"), (N, Ho, Wo, cout), out_dtype or self.act_dtype)
         cp = DgConvParams(kh, kw, stride, pt, pl, ACT[act], float(alpha))
         lin = DgConvParams(kh, kw, stride, pt, pl, 0, 0.0)
         umma = self._umma_ok(x.t, cin, cout, kh, kw, stride, H, W)
@@ -1021,8 +1030,9 @@ class Engine:
     # ------------------------------------------------------------------ batch norm (+act, +residual, +dropout)
     def bn_act(self, x: Var, pset, name: str, *, training: bool, momentum=0.99, eps=1e-3, act=None, alpha=0.0,
                prelu: Param | None = None, residual: Var | None = None, dropout_seed=None, dropout_offset=0,
-               step_counter: torch.Tensor | None = None) -> Var:
+               step_counter: torch.Tensor | None = None, out: torch.Tensor | None = None) -> Var:
         if not training and getattr(x, "bn_folded", None) == name:
+            assert out is None, f"{name}: the folded inference form has no out= (the producing convolution owns the buffer)"
             # inference: the producing convolution already applied this BatchNorm and its activation (folded kernel / bias / epilogue)
             assert prelu is None and residual is None and dropout_seed is None
             return x
@@ -1049,8 +1059,9 @@ class Engine:
             y, f_act, f_alpha, f_prelu, f_res = applied
             assert (f_act or None) == (act or None) and f_prelu is prelu and f_res is residual and \
                 (act != "lrelu" or abs(f_alpha - float(alpha)) < 1e-12), f"{name}: fused conv epilogue does not match this bn_act call"
+            assert out is None
         else:
-            y = self.buf((seq, "y"), x.shape, x.t.dtype)
+            y = self._out_or_buf(out, (seq, "y"), x.shape, x.t.dtype)
         ty = tensor(y)
         tres = tensor(residual.t) if residual is not None else None
         a_code = ACT["prelu"] if prelu is not None else ACT[act]
@@ -1232,6 +1243,38 @@ class Engine:
                 check(self.lib.dg_copy(self.ctx, C.byref(tg), C.byref(tgi), 0, self.st))
                 res.append(g)
             return res
+
+        self._push(list(parts), out, None, bwd)
+        return out
+
+    def concat_buffer(self, shape, dtype, splits):
+        """A concat result allocated BEFORE its parts exist, and the channel-slice views the producing layers write into
+        (`out=` of conv2d / bn_act): tf.concat([up, skip], axis=3) of the pix2pix U-Net (pix2pix.py:188) without a copy."""
+        seq = self._next()
+        y = self.buf((seq, "cat"), shape, dtype)
+        views, off = [], 0
+        for c in splits:
+            views.append(y[..., off:off + c])
+            off += c
+        assert off == shape[3]
+        return y, views
+
+    def concat_views(self, y: torch.Tensor, parts: list[Var]) -> Var:
+        """tf.concat(parts, axis=3) whose parts were written in place into the channel slices of `y` (concat_buffer): no forward
+        copy, and the gradient of every part is the matching channel slice of the gradient of the result (a view: the consumers
+        read it with the result's pixel pitch)."""
+        off, offs = 0, []
+        for p_ in parts:
+            assert p_.t.data_ptr() == y.data_ptr() + off * y.element_size() and tuple(p_.shape[:3]) == tuple(y.shape[:3]), \
+                "part is not the slice of the concat buffer"
+            offs.append(off)
+            off += p_.shape[3]
+        assert off == y.shape[3]
+        seq = self._next()
+        out = Var(y, self._deps(parts), seq)
+
+        def bwd(gy, need_in, need_p, tag):
+            return [gy[..., offs[i]:offs[i] + p_.shape[3]] if need_in[i] else None for i, p_ in enumerate(parts)]
 
         self._push(list(parts), out, None, bwd)
         return out

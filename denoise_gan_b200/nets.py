@@ -179,22 +179,34 @@ class Pix2PixGenerator(_Net):
         (gen_output and the identity term, pix2pix.py:90)."""
         E, p = self.E, self.p
         t = E.cast(self._in(x), E.act_dtype)
+        nd, nu = len(self.DOWN), len(self.UP)
+        N, H, W, _ = t.shape
+        inplace = E.inplace_concat and E.bf16 and training     # (inference folds BatchNorm into the convolutions, which own their outputs)
+        cat = [None] * nu
+        if inplace:
+            # concat([up_k, down_{nd-2-k}]) (pix2pix.py:188): both halves are written straight into the concat buffer by the layers
+            # that produce them (`out=`), and their gradients are read as slices of its gradient: no copy in either direction
+            for k in range(nu):
+                j = nd - 2 - k
+                cat[k] = E.concat_buffer((N, H >> (j + 1), W >> (j + 1), self.UP[k] + self.DOWN[j]), E.act_dtype, (self.UP[k], self.DOWN[j]))
         skips = []
-        for i in range(len(self.DOWN)):
+        for i in range(nd):
             w = p[f"g/down{i}/conv/kernel"]
+            dst = cat[nd - 2 - i][1][1] if (inplace and i <= nd - 2) else None
             if i == 0:
-                t = E.conv2d(t, w, None, stride=2, act="lrelu", alpha=0.3)
+                t = E.conv2d(t, w, None, stride=2, act="lrelu", alpha=0.3, out=dst)
             else:
                 t = E.conv2d(t, w, None, stride=2, bn=self._bn(f"g/down{i}/bn", training), post=dict(act="lrelu", alpha=0.3))
-                t = E.bn_act(t, p, f"g/down{i}/bn", training=training, act="lrelu", alpha=0.3)
+                t = E.bn_act(t, p, f"g/down{i}/bn", training=training, act="lrelu", alpha=0.3, out=dst)
             skips.append(t)
         skips = list(reversed(skips[:-1]))
-        for i in range(len(self.UP)):
+        for i in range(nu):
             t = E.conv2d_transpose(t, p[f"g/up{i}/convt/kernel"], None, stride=2)
             drop = self.dropout_seed if (i < 3 and training) else None
             t = E.bn_act(t, p, f"g/up{i}/bn", training=training, act="relu", dropout_seed=drop,
-                         dropout_offset=(pass_id * 3 + i) << 24, step_counter=p.opt_state if p.trainable else None)
-            t = E.concat([t, skips[i]])
+                         dropout_offset=(pass_id * 3 + i) << 24, step_counter=p.opt_state if p.trainable else None,
+                         out=cat[i][1][0] if inplace else None)
+            t = E.concat_views(cat[i][0], [t, skips[i]]) if inplace else E.concat([t, skips[i]])
         return E.conv2d_transpose(t, p["g/last/kernel"], p["g/last/bias"], stride=2, act="tanh", out_dtype=torch.float32)
 
 

@@ -220,6 +220,37 @@ def test_pix2pix_step_bf16_tracks_fp64():
         assert abs(a - float(b)) <= 3e-2 * max(1.0, abs(float(b))), (n, a, float(b))
 
 
+def test_pix2pix_inplace_concat_matches_copies():
+    """The U-Net concat of pix2pix.py:188 without copies (layers write into their channel slice of the concat buffer, gradients
+    are read as slices of its gradient: Engine.concat_buffer / concat_views) against the copying form: same kernels on the same
+    numbers with another pixel pitch, so losses and every parameter gradient of one bf16 step (both generator passes, dropout,
+    the skip gradients folded into the input-gradient epilogues) must agree to rounding-order noise."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.dataloader import synthetic_pair
+    from denoise_gan_b200.pix2pix import Pix2Pix
+    from denoise_gan_b200.train_pix2pix import train_step
+    res = {}
+    for inplace in (False, True):
+        model = Pix2Pix(SimpleNamespace(crop_size=256, lr=2e-4, fp16=1, vgg=0, retrain=0, seed=0, dropout_seed=7))
+        g0, d0 = P.init_pix2pix(0)
+        model.gen_params.load(perturb(g0)); model.disc_params.load(perturb(d0))
+        model.engine.inplace_concat = inplace
+        x, y = synthetic_pair(2, 256, 1, step=3)
+        losses = [float(v) for v in train_step(model, x.cuda(), y.cuda())]
+        torch.cuda.synchronize()
+        res[inplace] = (losses, {k: v.clone() for k, v in model.gen_params.grads().items()}, {k: v.clone() for k, v in model.disc_params.grads().items()})
+    for a, b in zip(res[False][0], res[True][0]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (res[False][0], res[True][0])
+    worst = []
+    for net in (1, 2):
+        for k, ga in res[False][net].items():
+            gb = res[True][net][k]
+            worst.append((((ga.double() - gb.double()).norm() / ga.double().norm().clamp_min(1e-30)).item(), k))
+    worst.sort(reverse=True)
+    print("in-place concat vs copies, worst relative gradient differences:", worst[:4])
+    assert worst[0][0] <= 1e-5, worst[:4]
+
+
 def test_pix2pix_step_fp32():
     """train_pix2pix.py:33-71 at the reference's hard-coded 256x256 (batch 1): 8-down/8-up U-Net with
     Conv2DTranspose, dropout (shared counter-based mask), PatchGAN on concat(input, target), identity pass."""
