@@ -20,7 +20,8 @@
 //     P  (tile i-1, epilogue warps) accumulator + bias + block input (re-read from L2) -> bf16 -> global; its TMEM / L2 latencies
 //        never stall the compute warps.
 //   The expand product of tile i+1 runs under D(i), the project product of tile i under E(i+1): the tensor pipe is never
-//   waited for.
+//   waited for.  (The sub-partition that hosts the control warp finishes D ~400 cycles after the other three -- the 18 tcgen05.mma
+//   it issues per tile cost it issue slots; sleeping between barrier polls changed nothing: profiles/fsrgan_block_timeline_r2_warps.log.)
 // Why fp16 inside: the kernel is bound by the CUDA-core depthwise stage and by shared-memory bandwidth (~370 KB per tile through a
 // 128 B/clock port), not by HBM.  B200 retires 128 FMAs per clock and SM whether they are issued as FFMA, FFMA2 (fma.rn.f32x2) or
 // HFMA2 (probes/fma_rate_probe.cu, profiles/fma_rate_probe_r2.log), so half precision buys no arithmetic rate; what it removes
@@ -71,7 +72,7 @@ struct FbParams {
   const float* b2;              // [32]
   __nv_bfloat16* y;
   int xp, yp, N, H, W, tiles_w, tiles_h, total;
-  long long* dbg;               // clock64 marks of CTA 0 ([16 tiles][8]; tools/fsrgan_block_timeline.py), or null
+  long long* dbg;               // clock64 marks of CTA 0 ([16 tiles][40]; tools/fsrgan_block_timeline.py), or null
 };
 
 __device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
@@ -103,7 +104,7 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void fb_mark(const FbParams& P, int it, int slot) {
-  if (P.dbg && blockIdx.x == 0 && it < 16) P.dbg[it * 8 + slot] = clock64();
+  if (P.dbg && blockIdx.x == 0 && it < 16) P.dbg[it * 40 + slot] = clock64();
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FB_COMPUTE_WARPS * 32) : "memory"); }
 
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
       if (it > 0) mbar_wait(smem_u32(&bar_p[(it - 1) & 1]), ((uint32_t)(it - 1) >> 1) & 1u);   // project product of tile it-1 has read the A operand
       // ---- D(it): depthwise 3x3 + bias + ReLU -> A operand of the project product
       if (tid == 0) fb_mark(P, it, 2);
+      if (lane == 0) fb_mark(P, it, 8 + warp);
       {
         const uint32_t src = inter + (uint32_t)(2 * rg * FB_IW) * FB_PITCH + (uint32_t)cpair * 4u;
         uint32_t win[4][4];                          // f16x2, straight from shared memory; column c+3 is loaded one step ahead
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_a));
       if (tid == 0) fb_mark(P, it, 3);
+      if (lane == 0) fb_mark(P, it, 24 + warp);
       if (it + 1 < n_local) request_e(it + 1);                     // expand product of tile it+1: issued under D(it), complete long ago
       compute_sync();                                              // everyone has read the expanded tile
     }

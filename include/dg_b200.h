@@ -191,7 +191,7 @@ int dg_dwconv3x3_fwd_act(dg_ctx*, const dg_tensor* x, const float* w_33c, const 
  * as fp16 (saturating), the depthwise taps are accumulated in fp16 (csrc/fsrgan_block.cu explains why).
  * dg_fsrgan_block_infer_supported() is 1 when the tensors qualify (otherwise the caller issues the three layer calls). */
 int dg_fsrgan_block_infer_supported(dg_ctx*, const dg_tensor* x, const dg_tensor* y);
-/* debug aid: clock64 marks of CTA 0's phases ([16 tiles][8] int64) of the next dg_fsrgan_block_infer launches; NULL turns it off */
+/* debug aid: clock64 marks of CTA 0's phases ([16 tiles][40] int64) of the next dg_fsrgan_block_infer launches; NULL turns it off */
 void dg_debug_fsrgan_block_timeline(long long* buf);
 int dg_fsrgan_block_infer(dg_ctx*, const dg_tensor* x, const void* w_expand, const float* b_expand, const float* w_dw, const float* b_dw,
                           const void* w_project, const float* b_project, const dg_tensor* y, void* stream);

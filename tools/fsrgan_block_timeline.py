@@ -33,12 +33,12 @@ for _ in range(10):
     run()
 ev[1].record(); torch.cuda.synchronize()
 print(f"{ev[0].elapsed_time(ev[1]) * 100:.1f} us per launch ({H}x{W}, {(H // 8) * (W // 16)} tiles)")
-dbg = torch.zeros(16 * 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(16 * 40, dtype=torch.int64, device="cuda")
 lib.dg_debug_fsrgan_block_timeline(dbg.data_ptr())
 run()
 torch.cuda.synchronize()
 lib.dg_debug_fsrgan_block_timeline(None)
-t = dbg.cpu().view(16, 8)
+t = dbg.cpu().view(16, 40)
 t0 = int(t[0, 0])
 names = ["E start", "E done", "D start", "D done", "ctl: E read", "ctl: P(i-1) done", "ctl: A ready"]
 for it in range(16):
@@ -46,3 +46,7 @@ for it in range(16):
 d = t[1:15]
 print("mean cycles: E", float((d[:, 1] - d[:, 0]).float().mean()), " sync+wait", float((d[:, 2] - d[:, 1]).float().mean()),
       " D", float((d[:, 3] - d[:, 2]).float().mean()), " tile period", float((t[2:15, 0] - t[1:14, 0]).float().mean()))
+print("per compute warp, tiles 4..7: D start and D done relative to the tile's E start")
+for it in range(4, 8):
+    print(f"tile {it}: D start " + " ".join(str(int(t[it, 8 + w]) - int(t[it, 0])) for w in range(12)))
+    print(f"        D done  " + " ".join(str(int(t[it, 24 + w]) - int(t[it, 0])) for w in range(12)))
