@@ -985,8 +985,10 @@ class Engine:
             else:
                 ent[1].copy_(w1); ent[2].copy_(w2); ent[0] = ver
             self._folded[("fsrgan_block", prefix)] = ent
-        check(self.lib.dg_fsrgan_block_infer(self.ctx, C.byref(tx), ent[1].data_ptr(), fe[2].data_ptr(), fd[1].data_ptr(), fd[2].data_ptr(),
-                                             ent[2].data_ptr(), fp[2].data_ptr(), C.byref(ty), self.st))
+        flops = float(x.shape[0] * x.shape[1] * x.shape[2]) * (2 * 32 * 192 + 2 * 9 * 192 + 2 * 192 * 32)   # expand + depthwise + project
+        self._timed("fsrgan_block", flops, lambda: check(self.lib.dg_fsrgan_block_infer(
+            self.ctx, C.byref(tx), ent[1].data_ptr(), fe[2].data_ptr(), fd[1].data_ptr(), fd[2].data_ptr(), ent[2].data_ptr(), fp[2].data_ptr(),
+            C.byref(ty), self.st)))
         return Var(y, self._deps([x], we.group), seq)     # inference only: no tape node
 
     def dwconv3x3(self, x: Var, w: Param, b: Param | None, bn=False, post: dict | None = None) -> Var:
