@@ -408,6 +408,291 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fsrgan_block_kernel(const __gri
   }
 }
 
+// ---------------------------------------------------------------- warp-specialised variant: E of tile i+1 under D of tile i
+// In the kernel above the twelve compute warps run E (accumulator -> shared memory: TMEM-read / latency bound) and D (depthwise
+// stage: FMA-pipe bound) one after the other, ~1100 + ~2750 of a tile's ~4800 cycles, and no pipe is busy half the time.  Here
+// the two phases belong to different warps and overlap:
+//   E warps 12..15 (one per TMEM lane quarter): expand accumulator (double-buffered, 2 x 192 columns) -> fp16 expanded tile,
+//   D warps 0..11: depthwise stage from the expanded tile (double-buffered in shared memory) into the project A operand (double-buffered:
+//                  with one copy D(i) waited for the project product of tile i-1 -- 2530 instead of ~1500 cycles per tile),
+//   P warps 16, 17: project accumulator + bias + block input -> global,
+//   control warps 18 (TMA, expand products) and 19 (project products).
+// The expanded tile must fit shared memory twice, so the tile is 16 x 4 output pixels (halo 18 x 6 = 108 rows: ONE 128-row expand
+// product, every lane quarter carries its share; the project product runs with 64 of its 128 rows in use).  All hand-overs are
+// mbarriers; there is no CTA-wide or group barrier inside the tile loop.
+constexpr int W2_TW = 16, W2_TH = 4, W2_IW = W2_TW + 2, W2_IH = W2_TH + 2, W2_HALO = W2_IW * W2_IH;   // 108
+constexpr int W2_D_WARPS = 12, W2_E_WARPS = 4, W2_P_WARPS = 2, W2_THREADS = (W2_D_WARPS + W2_E_WARPS + W2_P_WARPS + 2) * 32;
+constexpr uint32_t W2_OFF_W1 = 0, W2_OFF_WB = 12288, W2_OFF_W2 = 24576, W2_OFF_ONES = 36864;
+constexpr uint32_t W2_OFF_A = 45056, W2_A_BYTES = 3 * 8192;   // project A operand, twice: 3 K blocks x (64 rows x 128 B) at 8 KB; the product
+                                                              // addresses 128 rows per K block (the upper 64 are somebody else's bytes): + 8 KB slack
+constexpr uint32_t W2_OFF_X = W2_OFF_A + 2 * W2_A_BYTES + 8192;   // 3 halo stages x 8 KB (128 rows x 64 B addressed, 108 written)
+constexpr uint32_t W2_I_BYTES = (W2_HALO * FB_PITCH + 127u) & ~127u;
+constexpr uint32_t W2_OFF_I = W2_OFF_X + 3 * 8192;         // expanded tile, twice
+constexpr uint32_t W2_OFF_B = W2_OFF_I + 2 * W2_I_BYTES;   // project bias [32] (fp32)
+constexpr uint32_t W2_SMEM = W2_OFF_B + FB_C * 4 + 1024;
+constexpr uint32_t W2_X_BYTES = W2_HALO * FB_C * 2;
+
+__global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __grid_constant__ FbParams P) {
+  extern __shared__ uint8_t fb_raw[];
+  __shared__ __align__(8) uint64_t bar_x[3], bar_e[2], bar_efree[2], bar_ifull[2], bar_ifree[2], bar_a, bar_p[2], bar_pfree[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(fb_raw) + 1023u) & ~1023u;
+  uint8_t* gen = fb_raw + (base - smem_u32(fb_raw));
+  const int n_local = ((int)blockIdx.x < P.total) ? (P.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr int WARP_E0 = W2_D_WARPS, WARP_P0 = WARP_E0 + W2_E_WARPS, WARP_CX = WARP_P0 + W2_P_WARPS, WARP_CP = WARP_CX + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bar_x[i]), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_e[i]), 1);
+      mbar_init(smem_u32(&bar_efree[i]), W2_E_WARPS);
+      mbar_init(smem_u32(&bar_ifull[i]), W2_E_WARPS);
+      mbar_init(smem_u32(&bar_ifree[i]), W2_D_WARPS);
+      mbar_init(smem_u32(&bar_p[i]), 1);
+      mbar_init(smem_u32(&bar_pfree[i]), W2_P_WARPS);
+    }
+    mbar_init(smem_u32(&bar_a), W2_D_WARPS);
+    fence_mbar_init();
+    tma_prefetch_desc(&P.xmap);
+  }
+  if (warp == WARP_CX) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < FB_E * 4; i += W2_THREADS) {          // expand kernel and its bias (hi + lo bf16 terms), 64-byte swizzle
+    const int n = i >> 2, c = i & 3;
+    const uint32_t sw = (uint32_t)(n * 64 + ((c ^ ((n >> 1) & 3)) << 4));
+    *reinterpret_cast<uint4*>(gen + W2_OFF_W1 + sw) = __ldg(reinterpret_cast<const uint4*>(P.w1) + i);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c == 0) {
+      const float b = P.b1[n];
+      const __nv_bfloat16 hi = __float2bfloat16(b), lo = __float2bfloat16(b - __bfloat162float(hi));
+      v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    }
+    *reinterpret_cast<uint4*>(gen + W2_OFF_WB + sw) = v;
+  }
+  for (int i = tid; i < FB_C * 24; i += W2_THREADS) {         // project kernel, 128-byte swizzle
+    const int n = i / 24, c = i - n * 24, kb = c >> 3, cc = c & 7;
+    *reinterpret_cast<uint4*>(gen + W2_OFF_W2 + kb * 4096 + n * 128 + ((cc ^ (n & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(P.w2) + i);
+  }
+  for (int i = tid; i < 128 * 4; i += W2_THREADS) {
+    const int r = i >> 2, c = i & 3;
+    *reinterpret_cast<uint4*>(gen + W2_OFF_ONES + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = make_uint4(c == 0 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+  }
+  float* bias_s = reinterpret_cast<float*>(gen + W2_OFF_B);
+  for (int i = tid; i < FB_C; i += W2_THREADS) bias_s[i] = P.b2[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  auto tile_coords = [&](int it, int& n, int& h0, int& w0) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h;
+    n = t2 / P.tiles_h; h0 = th * W2_TH; w0 = tw * W2_TW;
+  };
+  const uint32_t lbo16 = 1u << 16;
+
+  if (warp == WARP_CX) {
+    // ------------------------------------------------------------------ control: halo loads and expand products
+    const uint32_t idesc_e = make_idesc_bf16(128, FB_E, 0, 0);
+    const uint64_t hi64 = make_smem_desc_hi(512, LAYOUT_SW64) << 32;
+    auto load_x = [&](int it) {
+      int n, h0, w0;
+      tile_coords(it, n, h0, w0);
+      const uint32_t bar = smem_u32(&bar_x[it % 3]);
+      mbar_expect_tx(bar, W2_X_BYTES);
+      tma_load_4d(base + W2_OFF_X + (uint32_t)(it % 3) * 8192u, &P.xmap, bar, 0, w0 - 1, h0 - 1, n);
+    };
+    if (elect_one())
+      for (int it = 0; it < 3 && it < n_local; ++it) load_x(it);
+    __syncwarp();
+    for (int it = 0; it < n_local; ++it) {
+      mbar_wait(smem_u32(&bar_x[it % 3]), ((uint32_t)(it / 3)) & 1u);
+      if (it >= 2) mbar_wait(smem_u32(&bar_efree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // E(it-2) has read this accumulator
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a16 = ((base + W2_OFF_X + (uint32_t)(it % 3) * 8192u) >> 4) | lbo16, b16 = ((base + W2_OFF_W1) >> 4) | lbo16;
+        const uint32_t o16 = ((base + W2_OFF_ONES) >> 4) | lbo16, wb16 = ((base + W2_OFF_WB) >> 4) | lbo16;
+        const uint32_t acc = tmem + TM_E + (uint32_t)(it & 1) * FB_E;
+        umma_f16(acc, hi64 | (uint64_t)o16, hi64 | (uint64_t)wb16, idesc_e, 0u);      // bias
+        umma_f16(acc, hi64 | (uint64_t)a16, hi64 | (uint64_t)b16, idesc_e, 1u);
+        umma_f16(acc, hi64 | (uint64_t)(a16 + 2u), hi64 | (uint64_t)(b16 + 2u), idesc_e, 1u);
+        umma_commit(smem_u32(&bar_e[it & 1]));
+      }
+      __syncwarp();
+      if (it >= 1 && it + 2 < n_local) {
+        // stage (it+2) % 3 was read by the expand product of tile it-1 (issued one iteration ago: complete in steady state)
+        mbar_wait(smem_u32(&bar_e[(it - 1) & 1]), ((uint32_t)(it - 1) >> 1) & 1u);
+        if (elect_one()) load_x(it + 2);
+        __syncwarp();
+      }
+    }
+  } else if (warp == WARP_CP) {
+    // ------------------------------------------------------------------ control: project products
+    const uint32_t idesc_p = (1u << 4) | ((uint32_t)(FB_C >> 3) << 17) | ((128u >> 4) << 24);   // fp16 A and B, fp32 accumulate
+    const uint64_t hi128 = make_smem_desc_hi(1024, LAYOUT_SW128) << 32;
+    for (int it = 0; it < n_local; ++it) {
+      mbar_wait(smem_u32(&bar_a), (uint32_t)it & 1u);                                            // D(it) has written the A operand
+      if (it >= 2) mbar_wait(smem_u32(&bar_pfree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);      // P(it-2) has read this accumulator
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a16 = ((base + W2_OFF_A + (uint32_t)(it & 1) * W2_A_BYTES) >> 4) | lbo16, b16 = ((base + W2_OFF_W2) >> 4) | lbo16;
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem + TM_P + (uint32_t)(it & 1) * FB_C, hi128 | (uint64_t)(a16 + (uint32_t)kb * 512u + 2u * k),
+                     hi128 | (uint64_t)(b16 + (uint32_t)kb * 256u + 2u * k), idesc_p, (kb | k) != 0);
+        umma_commit(smem_u32(&bar_p[it & 1]));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= WARP_P0) {
+    // ------------------------------------------------------------------ P warps: rows 0..63 of the project accumulator
+    const int q = warp & 3;      // warps 16, 17 -> lane quarters 0, 1
+    const float* b2 = reinterpret_cast<const float*>(gen + W2_OFF_B);
+    for (int it = 0; it < n_local; ++it) {
+      int n, h0, w0;
+      tile_coords(it, n, h0, w0);
+      const int r = q * 32 + lane, h = h0 + (r >> 4), w = w0 + (r & 15);
+      const bool ok = h < P.H && w < P.W;
+      const long pix = ((long)n * P.H + h) * P.W + w;
+      uint4 res[4];
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) res[k] = __ldg(reinterpret_cast<const uint4*>(P.x + pix * P.xp) + k);
+      }
+      mbar_wait(smem_u32(&bar_p[it & 1]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + TM_P + (uint32_t)(it & 1) * FB_C + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_pfree[it & 1]));
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t rr[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = k * 8 + e * 2;
+            const float lo = __uint_as_float(v[c]) + b2[c] + __uint_as_float(rr[e] << 16);
+            const float hi = __uint_as_float(v[c + 1]) + b2[c + 1] + __uint_as_float(rr[e] & 0xffff0000u);
+            __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+            o[e] = *reinterpret_cast<uint32_t*>(&pk);
+          }
+          reinterpret_cast<uint4*>(P.y + pix * P.yp)[k] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  } else if (warp >= WARP_E0) {
+    // ------------------------------------------------------------------ E warps: expand accumulator -> ReLU -> fp16 expanded tile
+    const int q = warp & 3;      // warps 12..15 -> lane quarters 0..3
+    const int row = q * 32 + lane, hh = row / W2_IW, ww = row - hh * W2_IW;
+    for (int it = 0; it < n_local; ++it) {
+      int n, h0, w0;
+      tile_coords(it, n, h0, w0);
+      const int h = h0 - 1 + hh, w = w0 - 1 + ww;
+      const bool in_img = h >= 0 && h < P.H && w >= 0 && w < P.W;
+      const uint32_t dst = base + W2_OFF_I + (uint32_t)(it & 1) * W2_I_BYTES + (uint32_t)row * FB_PITCH;
+      const uint32_t acc = tmem + TM_E + (uint32_t)(it & 1) * FB_E + ((uint32_t)(q * 32) << 16);
+      mbar_wait(smem_u32(&bar_e[it & 1]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[2][32];
+      tmem_ld_32x32(acc, v[0]);
+      tmem_ld_32x32(acc + 32u, v[1]);
+      if (it >= 2) mbar_wait(smem_u32(&bar_ifree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // D(it-2) has read this copy of the tile
+      auto conv = [&](int u, const uint32_t (&src)[32]) {
+        if (row >= W2_HALO) return;
+        const uint32_t d = dst + (uint32_t)u * 64u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = in_img ? relu_pack_h2(src[k * 8 + e * 2], src[k * 8 + e * 2 + 1]) : 0u;   // zero padding outside the image
+          sts128(d + (uint32_t)k * 16u, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < 6; u += 2) {
+        tmem_ld_wait();
+        conv(u, v[0]);
+        if (u + 2 < 6) tmem_ld_32x32(acc + (uint32_t)(u + 2) * 32u, v[0]);
+        conv(u + 1, v[1]);
+        if (u + 3 < 6) tmem_ld_32x32(acc + (uint32_t)(u + 3) * 32u, v[1]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar_efree[it & 1]));
+        mbar_arrive(smem_u32(&bar_ifull[it & 1]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ D warps: depthwise 3x3 + bias + ReLU -> project A operand
+    const int g = warp >> 2, sub = warp & 3, rp = sub & 1, chf = sub >> 1;   // 64-channel group; output rows 2rp, 2rp+1; columns 8chf..8chf+7
+    const int cpair = g * 32 + lane;
+    uint32_t wk[9], bdw;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = pack_h2(P.wd[t * FB_E + 2 * cpair], P.wd[t * FB_E + 2 * cpair + 1]);
+    bdw = pack_h2(P.bd[2 * cpair], P.bd[2 * cpair + 1]);
+    const uint32_t src_off = (uint32_t)(2 * rp * W2_IW + 8 * chf) * FB_PITCH + (uint32_t)cpair * 4u;
+    const uint32_t arow00 = base + W2_OFF_A + (uint32_t)g * 8192u + (uint32_t)(2 * rp * W2_TW + 8 * chf) * 128u + (uint32_t)(lane & 3) * 4u;
+    for (int it = 0; it < n_local; ++it) {
+      const uint32_t src = base + W2_OFF_I + (uint32_t)(it & 1) * W2_I_BYTES + src_off;
+      const uint32_t arow0 = arow00 + (uint32_t)(it & 1) * W2_A_BYTES;
+      mbar_wait(smem_u32(&bar_ifull[it & 1]), ((uint32_t)it >> 1) & 1u);
+      uint32_t win[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        win[r][0] = lds32(src + (uint32_t)(r * W2_IW + 0) * FB_PITCH);
+        win[r][1] = lds32(src + (uint32_t)(r * W2_IW + 1) * FB_PITCH);
+        win[r][2] = lds32(src + (uint32_t)(r * W2_IW + 2) * FB_PITCH);
+      }
+      if (it >= 2) mbar_wait(smem_u32(&bar_p[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // the project product of tile it-2 has read this copy of the A operand
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c + 3 < 10) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) win[r][(c + 3) % 4] = lds32(src + (uint32_t)(r * W2_IW + c + 3) * FB_PITCH);
+        }
+        uint32_t a0 = bdw, a1 = bdw;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            if (a * 3 + b < 8) {
+              a0 = hfma2(win[a][(c + b) % 4], wk[a * 3 + b], a0);
+              a1 = hfma2(win[a + 1][(c + b) % 4], wk[a * 3 + b], a1);
+            } else {
+              a0 = hfma2_relu(win[a][(c + b) % 4], wk[a * 3 + b], a0);
+              a1 = hfma2_relu(win[a + 1][(c + b) % 4], wk[a * 3 + b], a1);
+            }
+          }
+        const uint32_t r0 = (uint32_t)(2 * rp * W2_TW + 8 * chf + c);
+        sts32(arow0 + (uint32_t)c * 128u + ((((uint32_t)lane >> 2) ^ (r0 & 7u)) << 4), a0);
+        sts32(arow0 + (uint32_t)(c + W2_TW) * 128u + ((((uint32_t)lane >> 2) ^ ((r0 + W2_TW) & 7u)) << 4), a1);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar_a));
+        mbar_arrive(smem_u32(&bar_ifree[it & 1]));
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == WARP_CX) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 typedef CUresult (*FbEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -434,7 +719,9 @@ extern "C" int dg_fsrgan_block_infer(dg_ctx* ctx, const dg_tensor* x, const void
   memset(&P, 0, sizeof(P));
   uint64_t dims[4] = {(uint64_t)FB_C, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
   uint64_t strides[3] = {(uint64_t)x->cpitch * 2, (uint64_t)x->cpitch * 2 * x->w, (uint64_t)x->cpitch * 2 * x->w * x->h};
-  uint32_t box[4] = {(uint32_t)FB_C, (uint32_t)FB_IW, (uint32_t)FB_IH, 1}, ones[4] = {1, 1, 1, 1};
+  static const char* wsenv0 = getenv("DG_FSRGAN_BLOCK_WS");
+  const bool ws0 = !(wsenv0 && wsenv0[0] == '0');
+  uint32_t box[4] = {(uint32_t)FB_C, (uint32_t)FB_IW, (uint32_t)(ws0 ? W2_IH : FB_IH), 1}, ones[4] = {1, 1, 1, 1};
   CUresult r = ((FbEncodeFn)ctx->encode_tiled)(&P.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (char*)x->ptr + (size_t)x->coff * 2,
                                                (const cuuint64_t*)dims, (const cuuint64_t*)strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -444,17 +731,22 @@ extern "C" int dg_fsrgan_block_infer(dg_ctx* ctx, const dg_tensor* x, const void
   P.w1 = (const __nv_bfloat16*)w_expand; P.w2 = (const __half*)w_project;
   P.b1 = b_expand; P.wd = w_dw; P.bd = b_dw; P.b2 = b_project;
   P.xp = x->cpitch; P.yp = y->cpitch; P.N = x->n; P.H = x->h; P.W = x->w;
-  P.tiles_w = (x->w + FB_TW - 1) / FB_TW; P.tiles_h = (x->h + FB_TH - 1) / FB_TH;
+  static const char* wsenv = getenv("DG_FSRGAN_BLOCK_WS");    // 0: the lock-step kernel (16 x 8 tiles); default: the warp-specialised one (16 x 4)
+  const bool ws = !(wsenv && wsenv[0] == '0');
+  const int TH = ws ? W2_TH : FB_TH;
+  P.tiles_w = (x->w + FB_TW - 1) / FB_TW; P.tiles_h = (x->h + TH - 1) / TH;
   P.total = P.N * P.tiles_h * P.tiles_w;
   P.dbg = g_fb_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fsrgan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fsrgan_block_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM);
     if (e != cudaSuccess) DG_FAIL("dg_fsrgan_block_infer: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const unsigned grid = (unsigned)(P.total < ctx->sm_count ? P.total : ctx->sm_count);
-  fsrgan_block_kernel<<<grid, FB_THREADS, FB_SMEM, (cudaStream_t)stream>>>(P);
+  if (ws) fsrgan_block_ws_kernel<<<grid, W2_THREADS, W2_SMEM, (cudaStream_t)stream>>>(P);
+  else fsrgan_block_kernel<<<grid, FB_THREADS, FB_SMEM, (cudaStream_t)stream>>>(P);
   DG_CHECK_LAUNCH("dg_fsrgan_block_infer");
   return 0;
 }
