@@ -511,8 +511,10 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
     __syncwarp();
     for (int it = 0; it < n_local; ++it) {
       mbar_wait(smem_u32(&bar_x[it % 3]), ((uint32_t)(it / 3)) & 1u);
+      if (lane == 0) fb_mark(P, it, 24);
       if (it >= 2) mbar_wait(smem_u32(&bar_efree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // E(it-2) has read this accumulator
       tc_fence_after();
+      if (lane == 0) fb_mark(P, it, 25);
       if (elect_one()) {
         const uint32_t a16 = ((base + W2_OFF_X + (uint32_t)(it % 3) * 8192u) >> 4) | lbo16, b16 = ((base + W2_OFF_W1) >> 4) | lbo16;
         const uint32_t o16 = ((base + W2_OFF_ONES) >> 4) | lbo16, wb16 = ((base + W2_OFF_WB) >> 4) | lbo16;
@@ -536,6 +538,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
     const uint64_t hi128 = make_smem_desc_hi(1024, LAYOUT_SW128) << 32;
     for (int it = 0; it < n_local; ++it) {
       mbar_wait(smem_u32(&bar_a), (uint32_t)it & 1u);                                            // D(it) has written the A operand
+      if (lane == 0) fb_mark(P, it, 28);
       if (it >= 2) mbar_wait(smem_u32(&bar_pfree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);      // P(it-2) has read this accumulator
       tc_fence_after();
       if (elect_one()) {
@@ -565,8 +568,10 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
 #pragma unroll
         for (int k = 0; k < 4; ++k) res[k] = __ldg(reinterpret_cast<const uint4*>(P.x + pix * P.xp) + k);
       }
+      if (lane == 0 && q == 0) fb_mark(P, it, 16);
       mbar_wait(smem_u32(&bar_p[it & 1]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      if (lane == 0 && q == 0) fb_mark(P, it, 17);
       uint32_t v[32];
       tmem_ld_32x32(tmem + TM_P + (uint32_t)(it & 1) * FB_C + ((uint32_t)(q * 32) << 16), v);
       tmem_ld_wait();
@@ -601,12 +606,15 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
       const bool in_img = h >= 0 && h < P.H && w >= 0 && w < P.W;
       const uint32_t dst = base + W2_OFF_I + (uint32_t)(it & 1) * W2_I_BYTES + (uint32_t)row * FB_PITCH;
       const uint32_t acc = tmem + TM_E + (uint32_t)(it & 1) * FB_E + ((uint32_t)(q * 32) << 16);
+      if (lane == 0 && q == 0) fb_mark(P, it, 0);
       mbar_wait(smem_u32(&bar_e[it & 1]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      if (lane == 0 && q == 0) fb_mark(P, it, 1);
       uint32_t v[2][32];
       tmem_ld_32x32(acc, v[0]);
       tmem_ld_32x32(acc + 32u, v[1]);
       if (it >= 2) mbar_wait(smem_u32(&bar_ifree[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // D(it-2) has read this copy of the tile
+      if (lane == 0 && q == 0) fb_mark(P, it, 2);
       auto conv = [&](int u, const uint32_t (&src)[32]) {
         if (row >= W2_HALO) return;
         const uint32_t d = dst + (uint32_t)u * 64u;
@@ -628,6 +636,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
       }
       tc_fence_before();
       __syncwarp();
+      if (lane == 0 && q == 0) fb_mark(P, it, 3);
       if (lane == 0) {
         mbar_arrive(smem_u32(&bar_efree[it & 1]));
         mbar_arrive(smem_u32(&bar_ifull[it & 1]));
@@ -646,7 +655,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
     for (int it = 0; it < n_local; ++it) {
       const uint32_t src = base + W2_OFF_I + (uint32_t)(it & 1) * W2_I_BYTES + src_off;
       const uint32_t arow0 = arow00 + (uint32_t)(it & 1) * W2_A_BYTES;
+      if (tid == 0) fb_mark(P, it, 8);
       mbar_wait(smem_u32(&bar_ifull[it & 1]), ((uint32_t)it >> 1) & 1u);
+      if (tid == 0) fb_mark(P, it, 9);
       uint32_t win[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -655,6 +666,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
         win[r][2] = lds32(src + (uint32_t)(r * W2_IW + 2) * FB_PITCH);
       }
       if (it >= 2) mbar_wait(smem_u32(&bar_p[it & 1]), ((uint32_t)(it - 2) >> 1) & 1u);   // the project product of tile it-2 has read this copy of the A operand
+      if (tid == 0) fb_mark(P, it, 10);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         if (c + 3 < 10) {
@@ -680,6 +692,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) fsrgan_block_ws_kernel(const __
       }
       fence_proxy_async();
       __syncwarp();
+      if (tid == 0) fb_mark(P, it, 11);
       if (lane == 0) {
         mbar_arrive(smem_u32(&bar_a));
         mbar_arrive(smem_u32(&bar_ifree[it & 1]));

@@ -50,3 +50,10 @@ print("per compute warp, tiles 4..7: D start and D done relative to the tile's E
 for it in range(4, 8):
     print(f"tile {it}: D start " + " ".join(str(int(t[it, 8 + w]) - int(t[it, 0])) for w in range(12)))
     print(f"        D done  " + " ".join(str(int(t[it, 24 + w]) - int(t[it, 0])) for w in range(12)))
+if os.environ.get("DG_FSRGAN_BLOCK_WS", "1") != "0":
+    print("warp-specialised kernel, CTA 0, cycles after the first mark: E warp (wait acc | acc ready | tile copy free | E done), D warp 0 (top | tile full | A free | D done), "
+          "P warp (top | acc ready), control (x landed | acc free), project control (A ready)")
+    t0 = int(t[0][t[0] > 0].min())
+    for it in range(4, 12):
+        r = lambda sl: " ".join(str(int(t[it, k]) - t0) for k in sl)
+        print(f"tile {it:2d}  E {r(range(0, 4))}   D {r(range(8, 12))}   P {r(range(16, 18))}   X {r(range(24, 26))}   CP {r(range(28, 29))}")
