@@ -732,9 +732,9 @@ extern "C" int dg_fsrgan_block_infer(dg_ctx* ctx, const dg_tensor* x, const void
   memset(&P, 0, sizeof(P));
   uint64_t dims[4] = {(uint64_t)FB_C, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
   uint64_t strides[3] = {(uint64_t)x->cpitch * 2, (uint64_t)x->cpitch * 2 * x->w, (uint64_t)x->cpitch * 2 * x->w * x->h};
-  static const char* wsenv0 = getenv("DG_FSRGAN_BLOCK_WS");
-  const bool ws0 = !(wsenv0 && wsenv0[0] == '0');
-  uint32_t box[4] = {(uint32_t)FB_C, (uint32_t)FB_IW, (uint32_t)(ws0 ? W2_IH : FB_IH), 1}, ones[4] = {1, 1, 1, 1};
+  const char* wsenv = getenv("DG_FSRGAN_BLOCK_WS");     // 0: the lock-step kernel (16 x 8 tiles); default: the warp-specialised one (16 x 4); read per call (tests run both)
+  const bool ws = !(wsenv && wsenv[0] == '0');
+  uint32_t box[4] = {(uint32_t)FB_C, (uint32_t)FB_IW, (uint32_t)(ws ? W2_IH : FB_IH), 1}, ones[4] = {1, 1, 1, 1};
   CUresult r = ((FbEncodeFn)ctx->encode_tiled)(&P.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (char*)x->ptr + (size_t)x->coff * 2,
                                                (const cuuint64_t*)dims, (const cuuint64_t*)strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -744,8 +744,6 @@ extern "C" int dg_fsrgan_block_infer(dg_ctx* ctx, const dg_tensor* x, const void
   P.w1 = (const __nv_bfloat16*)w_expand; P.w2 = (const __half*)w_project;
   P.b1 = b_expand; P.wd = w_dw; P.bd = b_dw; P.b2 = b_project;
   P.xp = x->cpitch; P.yp = y->cpitch; P.N = x->n; P.H = x->h; P.W = x->w;
-  static const char* wsenv = getenv("DG_FSRGAN_BLOCK_WS");    // 0: the lock-step kernel (16 x 8 tiles); default: the warp-specialised one (16 x 4)
-  const bool ws = !(wsenv && wsenv[0] == '0');
   const int TH = ws ? W2_TH : FB_TH;
   P.tiles_w = (x->w + FB_TW - 1) / FB_TW; P.tiles_h = (x->h + TH - 1) / TH;
   P.total = P.N * P.tiles_h * P.tiles_w;

@@ -1339,14 +1339,17 @@ def test_conv_d2s_prelu_store(L, case):
     assert relerr(y, ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("ws", ["1", "0"])
 @pytest.mark.parametrize("N,H,W", [(1, 8, 16), (2, 21, 37), (1, 64, 160), (1, 3, 5)])
-def test_fsrgan_block_infer_one_launch(L, N, H, W):
+def test_fsrgan_block_infer_one_launch(L, N, H, W, ws, monkeypatch):
     """dg_fsrgan_block_infer: expand 1x1 (+ReLU) -> depthwise 3x3 (+ReLU) -> project 1x1 -> + input of an inverted-residual block
     (fsrgan.py:112-176 with the inference-mode BatchNorms folded into kernels / biases) in one launch, against the float64 oracle
     with the kernel's storage roundings (the two 192-channel intermediates are fp16, saturating).  Covers a single
     tile, partial tiles in both directions with several images, many tiles per CTA, and a map smaller than one tile; the input is
     a channel slice of a wider tensor.  SAME padding of the depthwise convolution must see ZEROS outside the image, not
-    relu(bias) of the expand layer: biases are large enough for the border to show it."""
+    relu(bias) of the expand layer: biases are large enough for the border to show it.  Both kernels: the warp-specialised one
+    (16 x 4 tiles, the default) and the lock-step one (16 x 8 tiles, DG_FSRGAN_BLOCK_WS=0)."""
+    monkeypatch.setenv("DG_FSRGAN_BLOCK_WS", ws)
     g = torch.Generator().manual_seed(H * 131 + W)
     bf = lambda t: t.bfloat16().double()
     x = bf(torch.randn(N, H, W, 32, generator=g))
