@@ -111,6 +111,9 @@ SIGNATURES = {
     "dg_fsrgan_block_infer_supported": (_i, [_P, _T, _T]),
     "dg_debug_fsrgan_block_timeline": (None, [_P]),
     "dg_fsrgan_block_infer": (_i, [_P, _T, _P, _P, _P, _P, _P, _P, _T, _P]),
+    "dg_conv3x3_tapsum_supported": (_i, [_P, _T, _i]),
+    "dg_conv3x3_tapsum_fwd": (_i, [_P, _T, _P, _P, _i, _f, _T, _P]),
+    "dg_conv3x3_tapsum_frame": (_i, [_P, _T, _P, _P, _i, _f, _f, _f, _i, _i, _P, _i, _i, _P]),
     "dg_dwconv3x3_fwd_act": (_i, [_P, _T, _P, _P, _i, _T, _P]),
     "dg_dwconv3x3_dgrad": (_i, [_P, _T, _P, _T, _P]),
     "dg_dwconv3x3_wgrad_workspace_bytes": (_sz, [_T]),

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["api.cu", "comm.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_wgrad.cu", "pointwise.cu", "dwconv.cu", "fsrgan_block.cu", "frames.cu", "loss_adam.cu", "pairs.cu", "summaries.cu"]
+SOURCES = ["api.cu", "comm.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_wgrad.cu", "pointwise.cu", "dwconv.cu", "fsrgan_block.cu", "conv_tapsum.cu", "frames.cu", "loss_adam.cu", "pairs.cu", "summaries.cu"]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + ["../../include/dg_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

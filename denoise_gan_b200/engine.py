@@ -136,6 +136,8 @@ class Engine:
         self.fuse_d2s_infer = os.environ.get("DG_FUSE_D2S", "1") != "0"     # inference: depth_to_space + PReLU as the up-conv's store pattern
         self.inplace_concat = os.environ.get("DG_INPLACE_CONCAT", "1") != "0"   # pix2pix U-Net: layers write into their half of the concat buffer
         self.fuse_fsrgan_block = os.environ.get("DG_FSRGAN_BLOCK", "1") != "0"   # inference: a Fast-SRGAN inverted-residual block as one launch
+        self.tapsum_infer = os.environ.get("DG_CONV_TAPSUM", "1") != "0"     # inference: the 32 -> 3 image convolution in tap-sum form (conv_tapsum.cu)
+        self.frame_sink = None   # FrameRunner: dict(out=uint8 frame, h, w, scale, offset, clip, flip, done) consumed by conv3x3_image_infer
         # weight gradients of layers with identical geometry (the generator trunk's 32 identical convolutions, the real / fake passes of
         # one discriminator layer) are collected during backward() and launched up to `wgrad_batch` at a time (dg_umma_conv2d_wgrad_batch)
         self.wgrad_batch = max(1, min(4, int(os.environ.get("DG_WGRAD_BATCH", "4"))))
@@ -990,6 +992,38 @@ class Engine:
             self.ctx, C.byref(tx), ent[1].data_ptr(), fe[2].data_ptr(), fd[1].data_ptr(), fd[2].data_ptr(), ent[2].data_ptr(), fp[2].data_ptr(),
             C.byref(ty), self.st)))
         return Var(y, self._deps([x], we.group), seq)     # inference only: no tape node
+
+    def conv3x3_image_infer(self, x: Var, w: Param, b: Param | None, act=None, alpha=0.0) -> Var | None:
+        """The generator's last layer at inference -- Conv2D(3, 3x3, SAME) + tanh in float32 on the up-scaled image
+        (fsrgan.py:216-217) -- in tap-sum form (dg_conv3x3_tapsum_fwd: one tensor-core product against all nine taps, then nine
+        shifted adds).  When a frame sink is installed (FrameRunner: infer_video.py:150-159) the uint8 frame is written directly
+        (dg_conv3x3_tapsum_frame) and the float image never exists.  Returns None when the layer does not qualify (the caller
+        then uses conv2d)."""
+        if not (self.tapsum_infer and self.use_umma and x.segs is None and x.t.dtype == torch.bfloat16):
+            return None
+        kh, kw, cin, cout = w.shape
+        N, H, W, C_ = x.shape
+        if (kh, kw, cin) != (3, 3, 32) or C_ != 32 or not 1 <= cout <= 3:
+            return None
+        tx = tensor(x.t)
+        if not self.lib.dg_conv3x3_tapsum_supported(self.ctx, C.byref(tx), cout):
+            return None
+        seq = self._next()
+        bias = _lib.ptr(b.data) if b is not None else None
+        flops = 2.0 * N * H * W * 9 * cin * cout
+        sink = self.frame_sink
+        if sink is not None and not sink["done"] and cout == 3 and N == 1 and sink["h"] <= H and sink["w"] <= W:
+            out = sink["out"]
+            self._timed("tapsum_conv", flops * (sink["h"] * sink["w"]) / (H * W), lambda: check(self.lib.dg_conv3x3_tapsum_frame(
+                self.ctx, C.byref(tx), w.data.data_ptr(), bias, ACT[act], float(alpha), float(sink["scale"]), float(sink["offset"]),
+                int(sink["clip"]), int(sink["flip"]), out.data_ptr(), sink["h"], sink["w"], self.st)))
+            sink["done"] = True
+            return Var(out, self._deps([x], w.group), seq)      # inference only: no tape node; the uint8 frame IS the result
+        y = self.buf((seq, "y"), (N, H, W, cout), torch.float32)
+        ty = tensor(y)
+        self._timed("tapsum_conv", flops, lambda: check(self.lib.dg_conv3x3_tapsum_fwd(
+            self.ctx, C.byref(tx), w.data.data_ptr(), bias, ACT[act], float(alpha), C.byref(ty), self.st)))
+        return Var(y, self._deps([x], w.group), seq)            # inference only: no tape node
 
     def dwconv3x3(self, x: Var, w: Param, b: Param | None, bn=False, post: dict | None = None) -> Var:
         """keras DepthwiseConv2D(3, padding='same').  `bn` / `post` as for conv2d: at inference the BatchNorm (+ ReLU) that follows

@@ -11,6 +11,8 @@ upload of frame i+1 and the download of frame i-1 overlap the forward of frame i
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -21,6 +23,24 @@ def padded_size(fh: int, fw: int, block: int = 256, model_scale: int = 1):
     """infer_video.py:79-83."""
     m = block * model_scale
     return (fh + m) - fh % m, (fw + m) - fw % m
+
+
+def tight_size(fh: int, fw: int, receptive_radius: float | None = None):
+    """The padded size a video frame is run at.  The reference pads every frame to the next multiple of 256 (infer_video.py:79-83,
+    141) and crops the centre of the output (:152): only output pixels whose receptive field reaches the frame can differ from
+    'the network on a constant image', and everything else is cropped away.  A generator that declares its receptive-field radius
+    (in input pixels: stride-1 convolutions, per-pixel inference BatchNorm, no pooling) is therefore run on the frame plus a
+    margin >= that radius (a multiple of 8) instead of the full padding -- the cropped frame is the same, pixel for pixel
+    (tests/test_infer_gpu.py), and a 1080p Fast-SRGAN frame is 1112 x 1952 instead of 1280 x 2048 pixels of work in every layer.
+    The reference's size is kept when no radius is declared, when the padding is odd (the reference's crop is then not centred
+    on the frame) or when it is smaller than the margin."""
+    nh, nw = padded_size(fh, fw)
+    if receptive_radius is None:
+        return nh, nw
+    m = -(-int(np.ceil(receptive_radius)) // 8) * 8
+    if (nh - fh) % 2 or (nw - fw) % 2 or (nh - fh) // 2 < m or (nw - fw) // 2 < m:
+        return nh, nw
+    return fh + 2 * m, fw + 2 * m
 
 
 def frames_for_rank(num_frames: int, rank: int, world: int, start: int = 0):
@@ -44,6 +64,7 @@ class FrameRunner:
         self.upscale = int(upscale if upscale is not None else getattr(model, "scale", 1))
         self.copy_stream = torch.cuda.Stream(device=self.E.device)       # uploads
         self.d2h_stream = torch.cuda.Stream(device=self.E.device)        # downloads
+        self.tight_padding = os.environ.get("DG_INFER_TIGHT_PAD", "1") != "0"   # video frames: frame + receptive-field margin instead of the full padding
         self._pin: dict = {}
         self._pin_ev: dict = {}       # pinned staging buffer -> event after the last device copy that read it
 
@@ -60,6 +81,23 @@ class FrameRunner:
         out = E.buf(("infer_out", slot), (out_h, out_w, 3), torch.uint8)
         _lib.check(E.lib.dg_float_to_frame(E.ctx, _lib.tensor(y), scale, offset, int(clip), int(flip), out.data_ptr(), out_h, out_w, E.st))
         return out
+
+    def _forward_to_frame(self, x: torch.Tensor, out_h: int | None, out_w: int | None, scale: float, offset: float, clip: bool, flip: bool, slot=0):
+        """forward + _to_frame.  A generator whose last layer can write the uint8 frame itself (Engine.conv3x3_image_infer: the
+        Fast-SRGAN output convolution) is offered the frame as a sink: the float image is then never written and pixels outside
+        the centre crop are not computed.  out_h / out_w None: the generator's own output size (infer.py:62-68)."""
+        E = self.E
+        if out_h is None:
+            out_h, out_w = x.shape[1] * self.upscale, x.shape[2] * self.upscale
+        out = E.buf(("infer_out", slot), (out_h, out_w, 3), torch.uint8)
+        E.frame_sink = dict(out=out, h=out_h, w=out_w, scale=scale, offset=offset, clip=clip, flip=flip, done=False)
+        try:
+            y = self.forward(x)
+        finally:
+            sink, E.frame_sink = E.frame_sink, None
+        if sink["done"]:
+            return out
+        return self._to_frame(y, out_h, out_w, scale, offset, clip, flip, slot)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """NHWC float [-1,1] (or [0,1] for infer.py / unit_test.py callers) -> generator output, training=False."""
@@ -86,31 +124,35 @@ class FrameRunner:
         self._pin_ev[("in", slot)] = ev
         return dev
 
+    def compute_size(self, fh: int, fw: int):
+        """The size the generator runs on for an fh x fw video frame (see `tight_size`)."""
+        r = getattr(self.model.generator, "receptive_radius", None) if self.tight_padding else None
+        return tight_size(fh, fw, r)
+
     # ---- the three reference call sites
     def video_frame(self, frame_bgr, to_host: bool = True, out_slot: int = 0):
         """infer_video.py:138-159: BGR uint8 [fh,fw,3] -> RGB uint8 [fh*s, fw*s, 3]."""
         f = _u8(frame_bgr)
         fh, fw = f.shape[:2]
-        nh, nw = padded_size(fh, fw)
+        nh, nw = self.compute_size(fh, fw)
         x = self._to_float(self._h2d(f), nh, nw, flip=True, norm_mode=0, scale=2.0, offset=-1.0)
-        y = self.forward(x)
-        out = self._to_frame(y, fh * self.upscale, fw * self.upscale, 0.5, 0.5, clip=True, flip=False, slot=out_slot)
+        out = self._forward_to_frame(x, fh * self.upscale, fw * self.upscale, 0.5, 0.5, clip=True, flip=False, slot=out_slot)
         return self._d2h(out) if to_host else out
 
     def still_image(self, img_bgr, to_host: bool = True):
         """infer.py:50-68: BGR uint8 -> [0,1] RGB (float64 division) -> forward -> ((sr+1)/2)*255 -> BGR uint8."""
         f = _u8(img_bgr)
         h, w = f.shape[:2]
-        y = self.forward(self._to_float(self._h2d(f), h, w, flip=True, norm_mode=1, scale=1.0, offset=0.0))
-        out = self._to_frame(y, y.shape[1], y.shape[2], 0.5, 0.5, clip=False, flip=True)
+        out = self._forward_to_frame(self._to_float(self._h2d(f), h, w, flip=True, norm_mode=1, scale=1.0, offset=0.0), None, None, 0.5, 0.5,
+                                     clip=False, flip=True)
         return self._d2h(out) if to_host else out
 
     def unit_image(self, img_bgr, to_host: bool = True):
         """unit_test.py:67-86: top-left 256x256 crop, float32 / 255, forward, np.uint8(((sr+1)/2)*255) (RGB)."""
         f = _u8(img_bgr)[:256, :256].contiguous()
         h, w = f.shape[:2]
-        y = self.forward(self._to_float(self._h2d(f), h, w, flip=True, norm_mode=2, scale=1.0, offset=0.0))
-        out = self._to_frame(y, y.shape[1], y.shape[2], 0.5, 0.5, clip=False, flip=False)
+        out = self._forward_to_frame(self._to_float(self._h2d(f), h, w, flip=True, norm_mode=2, scale=1.0, offset=0.0), None, None, 0.5, 0.5,
+                                     clip=False, flip=False)
         return self._d2h(out) if to_host else out
 
     def _d2h(self, out_dev: torch.Tensor, slot=0) -> torch.Tensor:

@@ -116,6 +116,9 @@ class FastSRGANGenerator(_Net):
     def __init__(self, engine, pset, n_blocks=6):
         super().__init__(engine, pset)
         self.n_blocks = n_blocks
+        # receptive-field radius at inference, in input pixels: c1 (1) + one depthwise 3x3 per block + c2 (1) + the first up-conv (1)
+        # + the second at 2x (1/2) + the output conv at 4x (1/4); every other layer is per-pixel (FrameRunner.compute_size)
+        self.receptive_radius = n_blocks + 3.75
 
     def __call__(self, x, training=True) -> Var:
         E, p = self.E, self.p
@@ -144,6 +147,11 @@ class FastSRGANGenerator(_Net):
         u = E.bn_act(c2, p, "g/c2_bn", training=training, residual=c1)
         for j in range(2):
             u = E.conv2d_d2s_prelu(u, p[f"g/up{j}/conv/kernel"], p[f"g/up{j}/conv/bias"], p[f"g/up{j}/prelu/alpha"], training)
+        if not training:
+            # inference: one tensor-core product against all nine taps + nine shifted adds (and straight to the uint8 frame when asked)
+            img = E.conv3x3_image_infer(u, p["g/conv_out/kernel"], p["g/conv_out/bias"], act="tanh")
+            if img is not None:
+                return img
         return E.conv2d(u, p["g/conv_out/kernel"], p["g/conv_out/bias"], act="tanh", out_dtype=torch.float32)
 
 

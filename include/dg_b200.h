@@ -195,6 +195,20 @@ int dg_fsrgan_block_infer_supported(dg_ctx*, const dg_tensor* x, const dg_tensor
 void dg_debug_fsrgan_block_timeline(long long* buf);
 int dg_fsrgan_block_infer(dg_ctx*, const dg_tensor* x, const void* w_expand, const float* b_expand, const float* w_dw, const float* b_dw,
                           const void* w_project, const float* b_project, const dg_tensor* y, void* stream);
+/* Conv2D(1..3 filters, 3x3, stride 1, SAME) from a 32-channel bf16 tensor at INFERENCE -- the generator's last layer,
+ * fsrgan.py:216-217 ('generator_tanh', dtype float32), which infer_video.py:146 runs on the 4x up-scaled frame -- in tap-sum
+ * form (csrc/conv_tapsum.cu): ONE tcgen05 product per pixel against all nine taps (N = 9*cout), then the nine shifted adds on
+ * the CUDA cores; 2 tensor instructions per 128 pixels instead of 18.  w_hwio: the Keras kernel [3][3][32][cout] in fp32
+ * (rounded to bf16 by the kernel, as dg_umma_pack_weights does), bias fp32 [cout] or NULL, act/alpha as dg_conv_params.
+ * _fwd writes the fp32 [n,h,w,cout] tensor y; _frame (cout = 3) writes the uint8 frame [n][dst_h][dst_w][3] directly with
+ * dg_float_to_frame's arithmetic (infer_video.py:150-159, infer.py:62-68): v*scale + offset, optional clip to [0,1], *255,
+ * truncation, optional channel flip, centre crop to dst_h x dst_w (<= h x w) -- pixels outside the crop are not computed and
+ * the fp32 image is never written.  _supported() is 1 when x qualifies (otherwise the caller uses dg_umma_conv2d_fwd_narrow). */
+int dg_conv3x3_tapsum_supported(dg_ctx*, const dg_tensor* x, int cout);
+int dg_conv3x3_tapsum_fwd(dg_ctx*, const dg_tensor* x, const float* w_hwio, const float* bias, int act, float alpha, const dg_tensor* y,
+                          void* stream);
+int dg_conv3x3_tapsum_frame(dg_ctx*, const dg_tensor* x, const float* w_hwio, const float* bias, int act, float alpha, float scale,
+                            float offset, int clip01, int flip_channels, uint8_t* dst, int dst_h, int dst_w, void* stream);
 int dg_dwconv3x3_dgrad(dg_ctx*, const dg_tensor* dy, const float* w, const dg_tensor* dx, void* stream);
 size_t dg_dwconv3x3_wgrad_workspace_bytes(const dg_tensor* x);
 int dg_dwconv3x3_wgrad(dg_ctx*, const dg_tensor* x, const dg_tensor* dy, float* dw, float* dbias, int accumulate,

@@ -37,8 +37,22 @@ def test_c_abi_declares_the_round2_entry_points():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dg_b200.h")).read()
     for sym in ("dg_umma_conv2d_wgrad_batch", "dg_umma_conv2d_fwd_narrow", "dg_umma_conv2d_fwd_d2s_prelu", "dg_umma_conv2d_dgrad_relu_mask",
                 "dg_umma_pack_weights_seg", "dg_unpad_weight_grad_seg", "dg_maxpool2x2_bwd_relu", "dg_pair_synthesis", "dg_image_summary",
-                "dg_gan_loss_terms", "dg_comm_allreduce"):
+                "dg_gan_loss_terms", "dg_comm_allreduce", "dg_conv3x3_tapsum_fwd", "dg_conv3x3_tapsum_frame", "dg_conv3x3_tapsum_supported"):
         assert sym + "(" in hdr, sym
     from denoise_gan_b200 import _lib
     lib = _lib.load()                                                  # binds every declared symbol or raises
     assert all(hasattr(lib, s) for s in ("dg_umma_conv2d_wgrad_batch", "dg_pair_synthesis", "dg_image_summary"))
+
+
+def test_tight_size_keeps_the_reference_geometry():
+    """FrameRunner.compute_size: frame + receptive-field margin when the reference's padding (infer_video.py:79-83) is even and at
+    least that wide on both axes, the reference's size otherwise."""
+    from denoise_gan_b200.infer import padded_size, tight_size
+    assert padded_size(1080, 1920) == (1280, 2048)
+    assert tight_size(1080, 1920, None) == (1280, 2048)
+    assert tight_size(1080, 1920, 9.75) == (1112, 1952)           # margin 16 = the radius rounded up to a multiple of 8
+    assert tight_size(1080, 1920, 40.0) == (1160, 2000)
+    assert tight_size(1080, 1920, 70.0) == (1280, 2048)           # 72 > the 64 columns of padding
+    assert tight_size(1081, 1920, 9.75) == padded_size(1081, 1920)   # odd padding: the reference's crop is off-centre by half a pixel
+    assert tight_size(256, 256, 9.75) == (288, 288)               # a multiple of 256 is padded by a full block (infer_video.py:81-82)
+    assert tight_size(250, 250, 9.75) == padded_size(250, 250)    # 3 pixels of padding < margin

@@ -147,3 +147,27 @@ def test_video_shard_pipeline_matches_single_frames():
     assert sorted(seen) == list(range(5))
     for i in range(5):
         np.testing.assert_array_equal(seen[i], single[i])
+
+
+def test_video_frame_tight_padding_and_frame_sink_are_exact():
+    """FrameRunner runs a Fast-SRGAN video frame on the frame + a receptive-field margin instead of the reference's padding to a
+    multiple of 256 (infer_video.py:79-83,141,152): the cropped output must be the same bit for bit.  And the output convolution
+    that writes the uint8 frame itself (dg_conv3x3_tapsum_frame) must agree with convolution + dg_float_to_frame to a level."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.fsrgan import FastSRGAN
+    from denoise_gan_b200.infer import FrameRunner
+    model = FastSRGAN(SimpleNamespace(crop_size=384, scale=4, lr=1e-3, fp16=1, vgg=0, seed=0))
+    model.gen_params.load(_randomise_stats(P.init_fsrgan_generator(0)))
+    run = FrameRunner(model, upscale=4)
+    f = _frame(300, 420, seed=7)
+    assert run.compute_size(300, 420) == (332, 452)
+    tight = run.video_frame(f).numpy()
+    run.tight_padding = False
+    assert run.compute_size(300, 420) == (512, 512)
+    full = run.video_frame(f).numpy()
+    assert tight.shape == full.shape == (1200, 1680, 3)
+    np.testing.assert_array_equal(tight, full)
+    model.engine.tapsum_infer = False                   # implicit-GEMM output convolution + dg_float_to_frame
+    old = run.video_frame(f).numpy()
+    mx, frac = _levels(full, old)
+    assert mx <= 1 and frac < 1e-3, (mx, frac)          # fp32 accumulation order of the last layer only

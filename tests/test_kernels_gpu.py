@@ -1236,6 +1236,78 @@ def test_conv_fwd_narrow_store(L, cout, act):
     assert (guard[N * H * W * cout:] == 7.0).all()  # nothing written past the dense tensor
 
 
+TAPSUM_CASES = [  # (cout, act, N, H, W, channel offset of the 32-channel input inside a wider buffer)
+    (3, 3, 2, 21, 19, 0),      # smaller than one 30 x 14 tile (the halo box is wider than the image)
+    (3, 3, 1, 45, 70, 8),      # 4 x 3 tiles with ragged right / bottom tiles, input = a channel slice (pixel pitch 48)
+    (1, 4, 2, 28, 60, 0),      # exact multiples of the tile
+    (2, 0, 1, 15, 31, 0),      # one pixel more than a tile in both directions
+    (3, 0, 3, 64, 96, 0),      # more tiles than fit two rounds of a small grid
+]
+
+
+@pytest.mark.parametrize("case", TAPSUM_CASES)
+def test_conv3x3_tapsum_fwd(L, case):
+    """dg_conv3x3_tapsum_fwd (fsrgan.py:216-217 at inference): one tensor-core product against all nine taps (N = 9*cout) plus nine
+    shifted fp32 adds must equal Conv2D(cout, 3, padding='same') + activation; bf16 operands, fp32 accumulation -> 1e-5."""
+    cout, act, N, H, W, coff = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = torch.randn(N, H, W, 32, generator=g).bfloat16().double()
+    w = (torch.randn(3, 3, 32, cout, generator=g) * 0.1).bfloat16().double(); b = torch.randn(cout, generator=g).double()
+    ref = OT.conv2d(x, w, b, stride=1, padding="same")
+    ref = torch.tanh(ref) if act == 3 else (torch.sigmoid(ref) if act == 4 else ref)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    wide = torch.randn(N, H, W, 32 + 2 * coff, generator=g).bfloat16().cuda()      # neighbouring channels must not leak in
+    wide[..., coff:coff + 32] = x.to(torch.bfloat16).cuda()
+    tx = L.tensor(wide, c=32, coff=coff)
+    assert lib.dg_conv3x3_tapsum_supported(ctx, C.byref(tx), cout) == 1
+    wd, bd = dev(w), dev(b)
+    guard = torch.full((N * H * W * cout + 64,), 7.0, device="cuda")
+    y = guard[:N * H * W * cout].view(N, H, W, cout)
+    ty = L.tensor(y)
+    L.check(lib.dg_conv3x3_tapsum_fwd(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), act, 0.0, C.byref(ty), st))
+    err = (y.double().cpu() - ref).abs().max().item()
+    assert err < FP32_TOL * max(1.0, ref.abs().max().item()), err
+    assert (guard[N * H * W * cout:] == 7.0).all()
+    # no bias: same call with a null pointer
+    L.check(lib.dg_conv3x3_tapsum_fwd(ctx, C.byref(tx), wd.data_ptr(), None, 0, 0.0, C.byref(ty), st))
+    assert (y.double().cpu() - OT.conv2d(x, w, None, stride=1, padding="same")).abs().max().item() < FP32_TOL * max(1.0, ref.abs().max().item())
+    # and the implicit-GEMM kernel it replaces gives the same image (accumulation order only)
+    if cout == 3 and coff == 0:
+        bp = torch.zeros(16, device="cuda"); bp[:cout] = bd
+        pk = torch.empty(9 * 32 * 16, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.dg_umma_pack_weights_padded(ctx, wd.data_ptr(), pk.data_ptr(), 3, 3, 32, cout, 32, 16, 0, st))
+        y2 = torch.empty_like(y)
+        cp = conv_params(L, 3, 3, 1, H, W, "same", act)
+        t2 = L.tensor(y2)
+        L.check(lib.dg_conv3x3_tapsum_fwd(ctx, C.byref(tx), wd.data_ptr(), bd.data_ptr(), act, 0.0, C.byref(ty), st))
+        L.check(lib.dg_umma_conv2d_fwd_narrow(ctx, C.byref(tx), pk.data_ptr(), bp.data_ptr(), C.byref(t2), C.byref(cp), st))
+        assert (y - y2).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("geom", [(1, 40, 70, 40, 70), (1, 45, 70, 33, 52), (1, 64, 128, 20, 120), (1, 30, 44, 29, 43)])
+@pytest.mark.parametrize("clip,flip", [(1, 0), (0, 1)])
+def test_conv3x3_tapsum_frame_bit_exact(L, geom, clip, flip):
+    """dg_conv3x3_tapsum_frame writes the uint8 frame of infer_video.py:150-159 / infer.py:62-68 straight from the convolution: bit for
+    bit what dg_float_to_frame makes of dg_conv3x3_tapsum_fwd's float image (centre crop, (y+1)/2, clip, *255, truncation, flip)."""
+    N, H, W, dh, dw = geom
+    g = torch.Generator().manual_seed(zlib.crc32(str((geom, clip, flip)).encode()) & 0xFFFF)
+    x = (torch.randn(N, H, W, 32, generator=g) * 1.5).bfloat16().cuda()
+    w = dev(torch.randn(3, 3, 32, 3, generator=g) * 0.15); b = dev(torch.randn(3, generator=g) * 0.3)
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    tx = L.tensor(x)
+    y = torch.empty(N, H, W, 3, device="cuda"); ty = L.tensor(y)
+    L.check(lib.dg_conv3x3_tapsum_fwd(ctx, C.byref(tx), w.data_ptr(), b.data_ptr(), 3, 0.0, C.byref(ty), st))
+    ref = torch.empty(dh, dw, 3, dtype=torch.uint8, device="cuda")
+    L.check(lib.dg_float_to_frame(ctx, C.byref(ty), 0.6, 0.5, clip, flip, ref.data_ptr(), dh, dw, st))     # 0.6: some values leave [0, 1]
+    guard = torch.full((dh * dw * 3 + 64,), 77, dtype=torch.uint8, device="cuda")
+    L.check(lib.dg_conv3x3_tapsum_frame(ctx, C.byref(tx), w.data_ptr(), b.data_ptr(), 3, 0.0, 0.6, 0.5, clip, flip, guard.data_ptr(), dh, dw, st))
+    assert torch.equal(guard[:dh * dw * 3].view(dh, dw, 3), ref)
+    assert (guard[dh * dw * 3:] == 77).all()
+    assert len(torch.unique(ref)) > 50                      # the comparison is not between two constant images
+    # a frame larger than the convolution's output is refused (crop only)
+    assert lib.dg_conv3x3_tapsum_frame(ctx, C.byref(tx), w.data_ptr(), b.data_ptr(), 3, 0.0, 0.5, 0.5, 1, 0, guard.data_ptr(), H + 1, W, st) != 0
+
+
 @pytest.mark.parametrize("case", [(3, 64, 64, 2, 40, 24, False, 4), (3, 64, 64, 1, 96, 96, False, 3), (3, 32, 48, 2, 24, 24, True, 2),
                                   (1, 64, 16, 1, 48, 40, True, 4)])
 @pytest.mark.parametrize("merged", [False, True])
