@@ -13,11 +13,17 @@
 // Out-of-image pixels of the halo box are zero-filled by the TMA unit, so their D rows are zero: SAME padding.
 //
 // One persistent CTA per SM walks 30 x 14 output tiles (32 x 16 halo box = 512 pixels = four 128-row M blocks):
-//   warp 0  TMA producer: the 32 KB halo box of a tile into a 3-stage ring (64-byte rows, 64-byte swizzle);
-//   warp 1  eight tcgen05.mma per tile into one of two 128-column accumulators, tcgen05.commit frees the stage;
-//   2 x 8 epilogue warps, the two groups take alternate tiles: accumulator -> registers -> fp32 scratch [9*Cout][512] in shared
-//           memory (column-major: pixel-consecutive lanes are conflict-free both when writing rows and when reading shifted
-//           windows) -> per output pixel the 9*Cout shifted reads in a fixed order -> bias, activation -> store.
+//   warp 0  TMA producer: the 32 KB halo box of a tile into a 4-stage ring (64-byte rows, 64-byte swizzle);
+//   warp 1  eight tcgen05.mma per tile into one of four 128-column accumulators, tcgen05.commit frees the stage;
+//   4 x 4 epilogue warps, the four groups take tiles round-robin.  A halo row is 32 pixels = the 32 accumulator lanes one warp
+//           may read, so a warp holds whole halo rows (quarter q of M block mb = halo row 4 mb + q), lane = column:
+//             H  the three horizontal taps of every filter row meet in the warp -- two shuffles per (filter row, channel);
+//                the 3*Cout partial sums per pixel go to an fp32 scratch [3*Cout][512] in shared memory (18 KB per group);
+//             V  after the group's barrier a warp owns output rows, lane = column: three scratch reads per channel (filter
+//                rows, conflict-free), bias, activation, store.
+//           (The first version wrote all 9*Cout columns to a 55 KB scratch and gathered 27 values per pixel with pixels dealt to
+//           threads linearly: a 30-wide tile row never matches the 32 lanes, every read was a 2-way bank conflict and the kernel
+//           sat at 56 % of the shared-memory pipe with half its issue slots stalled on it: 712 us.)
 // Two stores: the dense fp32 NHWC tensor ('generator_tanh', dtype float32), or -- dg_conv3x3_tapsum_frame -- straight to the
 // uint8 frame with the arithmetic of dg_float_to_frame (infer_video.py:150-159: (y+1)/2, clip, *255, truncate, centre crop):
 // then only the tiles inside the crop window are computed, and the fp32 image (500 MB written and read back at this size)
@@ -37,17 +43,28 @@ constexpr int TS_HW = 32, TS_HH = 16;             // halo box
 constexpr int TS_OW = TS_HW - 2, TS_OH = TS_HH - 2;
 constexpr int TS_PIX = TS_HW * TS_HH;             // 512 rows of the product
 constexpr int TS_MB = TS_PIX / 128;               // M blocks
-constexpr int TS_NST = 3;                         // halo stages
+constexpr int TS_NST = 4;                         // halo stages
 constexpr int TS_N = 32;                          // accumulator columns per M block
-constexpr int TS_GW = 8;                          // warps per epilogue group
-constexpr int TS_THREADS = (2 + 2 * TS_GW) * 32;
+constexpr int TS_NG = 4, TS_GW = 4;               // epilogue groups, warps per group (one per TMEM lane quarter)
+constexpr int TS_THREADS = (2 + TS_NG * TS_GW) * 32;
 constexpr uint32_t TS_STAGE = TS_PIX * TS_C * 2;  // 32 KB
 constexpr uint32_t OFF_W = 0;                     // B operand: 32 rows (tap*Cout + co) x 64 B (bf16 over ci), 64-byte swizzle
 constexpr uint32_t OFF_BIAS = 2048;
 constexpr uint32_t OFF_X = 4096;
 constexpr uint32_t OFF_S = OFF_X + TS_NST * TS_STAGE;
-constexpr uint32_t TS_SCRATCH = 27 * TS_PIX * 4;  // per group
-constexpr uint32_t TS_SMEM = OFF_S + 2 * TS_SCRATCH + 1024;
+constexpr uint32_t TS_SCRATCH = 9 * TS_PIX * 4;   // per group: [3 filter rows x Cout <= 3][512] fp32
+constexpr uint32_t TS_SMEM = OFF_S + TS_NG * TS_SCRATCH + 1024;
+
+// tcgen05.wait::ld that also "modifies" the loaded registers, so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 struct TsParams {
   CUtensorMap xmap;
@@ -68,7 +85,7 @@ template <int COUT>
 __global__ void __launch_bounds__(TS_THREADS, 1) conv_tapsum_kernel(const __grid_constant__ TsParams P) {
   constexpr int NCOL = 9 * COUT;
   extern __shared__ uint8_t ts_raw[];
-  __shared__ __align__(8) uint64_t bar_full[TS_NST], bar_empty[TS_NST], bar_acc[2], bar_accfree[2];
+  __shared__ __align__(8) uint64_t bar_full[TS_NST], bar_empty[TS_NST], bar_acc[TS_NG], bar_accfree[TS_NG];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(ts_raw) + 1023u) & ~1023u;
@@ -77,12 +94,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tapsum_kernel(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < TS_NST; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(smem_u32(&bar_acc[g]), 1); mbar_init(smem_u32(&bar_accfree[g]), 1); }
+    for (int g = 0; g < TS_NG; ++g) { mbar_init(smem_u32(&bar_acc[g]), 1); mbar_init(smem_u32(&bar_accfree[g]), 1); }
     fence_mbar_init();
     tma_prefetch_desc(&P.xmap);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_slot), 2 * TS_MB * TS_N);
+    tmem_alloc(smem_u32(&tmem_slot), TS_NG * TS_MB * TS_N);
     tmem_relinquish();
   }
   // B operand: row n = tap*COUT + co holds w[tap][0..31][co] as bf16 (K-major), rows >= 9*COUT are zero
@@ -136,9 +153,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tapsum_kernel(const __grid
     const uint32_t lbo16 = 1u << 16;
     const uint32_t b16 = ((base + OFF_W) >> 4) | lbo16;
     for (int it = 0; it < n_local; ++it) {
-      const int s = it % TS_NST, use = it / TS_NST, g = it & 1;
+      const int s = it % TS_NST, use = it / TS_NST, g = it % TS_NG;
       mbar_wait(smem_u32(&bar_full[s]), (uint32_t)use & 1u);
-      if (it >= 2) mbar_wait(smem_u32(&bar_accfree[g]), (uint32_t)((it >> 1) - 1) & 1u);
+      if (it >= TS_NG) mbar_wait(smem_u32(&bar_accfree[g]), (uint32_t)(it / TS_NG - 1) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a16 = ((base + OFF_X + (uint32_t)s * TS_STAGE) >> 4) | lbo16;
@@ -154,50 +171,61 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tapsum_kernel(const __grid
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue groups (alternate tiles)
-    const int g = (warp - 2) / TS_GW, wg = (warp - 2) % TS_GW, tg = wg * 32 + lane;
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = wg >> 2;               // warps wg and wg + 4 share a quarter and split the four M blocks between them
+    // ------------------------------------------------------------------ epilogue groups (tiles round-robin)
+    const int g = (warp - 2) / TS_GW, wg = (warp - 2) % TS_GW;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read: halo rows q, q + 4, q + 8, q + 12 of the tile
     float* S = reinterpret_cast<float*>(gen + OFF_S + (uint32_t)g * TS_SCRATCH);
     float bias[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) bias[c] = bias_s[c];
-    for (int it = g; it < n_local; it += 2) {
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(TS_GW * 32) : "memory"); };
+    // H: lane = halo column x; partial[ky][co](x) = sum_kx D[(row, x + kx), (ky, kx, co)] for output column x (lanes 30, 31: unused)
+    auto horizontal = [&](const uint32_t (&v)[32], int hr) {
+      float* dst = S + hr * TS_HW + lane;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float a = __uint_as_float(v[(ky * 3 + 0) * COUT + co]);
+          const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(v[(ky * 3 + 1) * COUT + co]), 1);
+          const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v[(ky * 3 + 2) * COUT + co]), 2);
+          dst[(ky * COUT + co) * TS_PIX] = (a + b) + c;
+        }
+    };
+    for (int it = g; it < n_local; it += TS_NG) {
       int n, h0, w0;
       tile_coords(it, n, h0, w0);
-      mbar_wait(smem_u32(&bar_acc[g]), (uint32_t)(it >> 1) & 1u);
+      mbar_wait(smem_u32(&bar_acc[g]), (uint32_t)(it / TS_NG) & 1u);
       tc_fence_after();
       {
+        const uint32_t t0 = tmem + (uint32_t)(g * TS_MB) * TS_N + ((uint32_t)(q * 32) << 16);
         uint32_t v0[32], v1[32];
-        const int mb0 = half * 2;
-        tmem_ld_32x32(tmem + (uint32_t)(g * TS_MB + mb0) * TS_N + ((uint32_t)(q * 32) << 16), v0);
-        tmem_ld_32x32(tmem + (uint32_t)(g * TS_MB + mb0 + 1) * TS_N + ((uint32_t)(q * 32) << 16), v1);
-        tmem_ld_wait();
-        float* s0 = S + mb0 * 128 + q * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < NCOL; ++c) {
-          s0[c * TS_PIX] = __uint_as_float(v0[c]);
-          s0[c * TS_PIX + 128] = __uint_as_float(v1[c]);
-        }
+        tmem_ld_32x32(t0, v0);
+        tmem_ld_32x32(t0 + TS_N, v1);
+        tmem_ld_wait_on(v0); tmem_ld_wait_on(v1);
+        horizontal(v0, q);
+        horizontal(v1, 4 + q);
+        tmem_ld_32x32(t0 + 2 * TS_N, v0);
+        tmem_ld_32x32(t0 + 3 * TS_N, v1);
+        tmem_ld_wait_on(v0); tmem_ld_wait_on(v1);
+        horizontal(v0, 8 + q);
+        horizontal(v1, 12 + q);
       }
       tc_fence_before();
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(TS_GW * 32) : "memory");
-      if (tg == 0) mbar_arrive(smem_u32(&bar_accfree[g]));
+      group_sync();
+      if (wg == 0 && lane == 0) mbar_arrive(smem_u32(&bar_accfree[g]));
+      // V: this warp's output rows r = wg, wg + 4, ...; lane = output column
+      const int w = w0 + lane;
+      const bool col_ok = lane < TS_OW && w < P.ox + P.OW;
 #pragma unroll 1
-      for (int i = tg; i < TS_OW * TS_OH; i += TS_GW * 32) {
-        const int r = i / TS_OW, c = i - r * TS_OW;
-        const int h = h0 + r, w = w0 + c;
+      for (int r = wg; r < TS_OH; r += TS_GW) {
+        const int h = h0 + r;
+        const float* sp = S + r * TS_HW + lane;
         float acc[COUT];
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = bias[co];
-        const float* sp = S + r * TS_HW + c;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int co = 0; co < COUT; ++co) acc[co] += sp[((ky * 3 + kx) * COUT + co) * TS_PIX + ky * TS_HW + kx];
-        if (h < P.oy + P.OH && w < P.ox + P.OW) {
+        for (int co = 0; co < COUT; ++co)
+          acc[co] = ((bias[co] + sp[co * TS_PIX]) + sp[(COUT + co) * TS_PIX + TS_HW]) + sp[(2 * COUT + co) * TS_PIX + 2 * TS_HW];
+        if (col_ok && h < P.oy + P.OH) {
           if (P.frame) {
             uint8_t* qd = P.frame + (((long)n * P.OH + (h - P.oy)) * P.OW + (w - P.ox)) * 3;
 #pragma unroll
@@ -215,14 +243,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tapsum_kernel(const __grid
           }
         }
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(TS_GW * 32) : "memory");     // the scratch is rewritten by the group's next tile
+      group_sync();     // the scratch is rewritten by the group's next tile
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 2 * TS_MB * TS_N);
+    tmem_dealloc(tmem, TS_NG * TS_MB * TS_N);
   }
 }
 
