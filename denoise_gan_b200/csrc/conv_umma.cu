@@ -90,6 +90,7 @@ struct UmmaConvParams {
   // (per-channel sum and sum of squares of the STORED values) are accumulated from the staged tile
   CUtensorMap omap;
   int tstore;
+  int d2s_ts;       // depth_to_space store through the staging buffers (epilogue_role_d2s_ts)
   uint32_t stg_off, stg_bytes, stg_mask;
   float* bn_partials;   // [gridDim.x][2][cout_total] or nullptr
   int bn_fin;           // the last CTA (ticket) turns the partial rows into scale/shift/mean/invstd + moving statistics
@@ -126,7 +127,7 @@ struct UmmaConvParams {
   int act;
   float alpha;
   uint32_t layout, idesc;
-  int dbg_flags;   // debug experiments (tools/conv_timeline.py): 1 no stores, 2 no epilogue work, 4 no TMA reloads, 8 unshifted taps; 16 (host) force K-outer
+  int dbg_flags;   // debug experiments (tools/conv_timeline.py): 1 no stores, 2 no epilogue work, 4 no TMA reloads, 8 unshifted taps; 16 (host) force K-outer; 64: direct depth_to_space store without 32-byte stores
   long long* dbg;  // optional per-role timeline of CTA 0 (tools/conv_timeline.py); nullptr in production
 };
 
@@ -146,6 +147,17 @@ __device__ __forceinline__ float act_fn(float v, float alpha) {
   if (ACT == DG_ACT_TANH) return tanhf(v);
   if (ACT == DG_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
   return v;
+}
+
+// tcgen05.wait::ld that also "modifies" the loaded registers: no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 
 // one 16-column group of one accumulator row: + bias, activation, store
@@ -199,21 +211,19 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
       int c0 = 0;
       if (!F32 && P.d2s_cq > 0) {
         // depth_to_space + PReLU store: a 32-channel group lies inside one sub-pixel block (d2s_cq is a multiple of 32, see the host
-        // check); two 16-column accumulator loads in flight per wait, slopes from shared memory (ps: broadcast reads)
-        for (; c0 < P.nb; c0 += 32) {
-          uint32_t v0[16], v1[16];
-          tmem_ld_32x16(acc + c0, v0);
-          tmem_ld_32x16(acc + c0 + 16, v1);
-          tmem_ld_wait();
-          if (!valid) continue;
-          const int cg = nb0 + c0, blk = cg / P.d2s_cq, cc = cg - blk * P.d2s_cq;
+        // check); slopes from shared memory (ps: broadcast reads).  A thread's 32 channels are 64 contiguous bytes: two 32-byte stores
+        // (st.global.v8: full sectors, half the store instructions; 1078 -> 959 us on the 1080p up-convolution) when the row is 32-byte
+        // aligned.  Requesting the next 32 accumulator columns before converting the current ones was measured slower (1065 us:
+        // profiles/infer_profile_r2d_d2s_flags.log) and is not kept.
+        // (Dense 32-channel outputs of a 128-channel layer leave through epilogue_role_d2s_ts instead.)
+        const bool wide = !(P.dbg_flags & 64) && (((uintptr_t)P.out | (uintptr_t)(P.out_sw * 2)) & 31) == 0;
+        uint32_t va[32];
+        auto convert_store = [&](const uint32_t (&v)[32], int cb) {
+          const int cg = nb0 + cb, blk = cg / P.d2s_cq, cc = cg - blk * P.d2s_cq;
           const long e = (long)n * P.out_sn + (long)(2 * ph + (blk >> 1)) * P.out_sh + (long)(2 * pw + (blk & 1)) * P.out_sw + cc;
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v0[j]) + (bs ? bs[c0 + j] : 0.f);
-            f[16 + j] = __uint_as_float(v1[j]) + (bs ? bs[c0 + 16 + j] : 0.f);
-          }
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bs ? bs[cb + j] : 0.f);
           if (ps) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -224,11 +234,26 @@ __device__ __forceinline__ void epilogue_role(const UmmaConvParams& P, uint32_t 
               f[4 * j4 + 3] = f[4 * j4 + 3] > 0.f ? f[4 * j4 + 3] : a.w * f[4 * j4 + 3];
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + e);
+          uint32_t o[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            dst[k] = make_uint4(pack_bf16x2(f[8 * k], f[8 * k + 1]), pack_bf16x2(f[8 * k + 2], f[8 * k + 3]), pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
-                                pack_bf16x2(f[8 * k + 6], f[8 * k + 7]));
+          for (int k = 0; k < 16; ++k) o[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
+          __nv_bfloat16* dstp = reinterpret_cast<__nv_bfloat16*>(P.out) + e;
+          if (wide && (cc & 15) == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dstp + 16 * k), "r"(o[8 * k]), "r"(o[8 * k + 1]), "r"(o[8 * k + 2]),
+                           "r"(o[8 * k + 3]), "r"(o[8 * k + 4]), "r"(o[8 * k + 5]), "r"(o[8 * k + 6]), "r"(o[8 * k + 7])
+                           : "memory");
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(dstp);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+          }
+        };
+        for (; c0 < P.nb; c0 += 32) {
+          tmem_ld_32x32(acc + c0, va);
+          tmem_ld_wait_on(va);
+          if (valid) convert_store(va, c0);
         }
       }
       for (; c0 + 32 <= P.nb; c0 += 32) {   // two 16-column loads in flight per wait
@@ -471,6 +496,68 @@ __device__ __forceinline__ void bnp_phase(const UmmaConvParams& P, uint32_t tmem
     case DG_ACT_PRELU: bnp_pass2<DG_ACT_PRELU>(P, tmem, stg, q, lane, nb0, total_tiles, bs, cs, bar_res_full, bar_res_empty, stage_base, grp); break;
     default: bnp_pass2<DG_ACT_NONE>(P, tmem, stg, q, lane, nb0, total_tiles, bs, cs, bar_res_full, bar_res_empty, stage_base, grp); break;
   }
+}
+
+// depth_to_space(2) + PReLU store through shared memory (32 -> 4 x 32 channels, fsrgan.py:180-186 at inference; one 128-channel N
+// block, 16 x 8 tiles).  The direct store of epilogue_role gives every thread its own 128-byte lines: a warp-wide 16-byte store touches
+// 32 lines, and the LSU takes a line per cycle -- 2048 cycles per tile on the four epilogue warps' stores alone.  Here a thread
+// writes its four 64-byte groups into the tile's OUTPUT image in shared memory -- 32 x 16 pixels x 32 channels, rows of two pixels
+// (128 bytes) in the TMA's 128-byte swizzle: chunk k of row R sits at k ^ (R & 7) and R & 7 is the pixel's column in the tile, so the
+// eight columns of a warp-wide store cover all banks -- and one bulk tensor store per tile writes full lines, clipped at the image
+// border by the TMA unit.  Two staging buffers (one per epilogue group): the store of tile i drains under tile i+1.
+__device__ __forceinline__ void epilogue_role_d2s_ts(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int total_tiles,
+                                                     const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, int grp,
+                                                     const float* __restrict__ ps) {
+  const uint32_t bar_id = 1u + (uint32_t)grp;
+  const int m_idx = q * 32 + lane, ph_l = m_idx >> 3, pw_l = m_idx & 7;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const bool leader = q == 0 && lane == 0;
+  const uint32_t stg = stg_base + (uint32_t)grp * P.stg_bytes;
+  int it = grp;
+  for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, it += 2) {
+    const int b = it & ((1 << P.nbuf_shift) - 1);
+    const uint32_t acc_phase = (uint32_t)(it >> P.nbuf_shift) & 1u;
+    const int tw = tile % P.tiles_w, t2 = tile / P.tiles_w, th = t2 % P.tiles_h, n = t2 / P.tiles_h;
+    if (leader) tma_store_wait_read<0>();     // this group's previous store has left the buffer
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    mbar_wait(smem_u32(&bar_acc_full[b]), acc_phase);
+    tc_fence_after();
+    const uint32_t acc = tmem + lane_base + (uint32_t)(b * P.nb);
+#pragma unroll 1
+    for (int blk = 0; blk < 4; ++blk) {
+      uint32_t v[32];
+      tmem_ld_32x32(acc + (uint32_t)(blk * 32), v);
+      tmem_ld_wait_on(v);
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bs ? bs[blk * 32 + j] : 0.f);
+      if (ps) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 a = *reinterpret_cast<const float4*>(ps + 4 * j4);
+          f[4 * j4 + 0] = f[4 * j4 + 0] > 0.f ? f[4 * j4 + 0] : a.x * f[4 * j4 + 0];
+          f[4 * j4 + 1] = f[4 * j4 + 1] > 0.f ? f[4 * j4 + 1] : a.y * f[4 * j4 + 1];
+          f[4 * j4 + 2] = f[4 * j4 + 2] > 0.f ? f[4 * j4 + 2] : a.z * f[4 * j4 + 2];
+          f[4 * j4 + 3] = f[4 * j4 + 3] > 0.f ? f[4 * j4 + 3] : a.w * f[4 * j4 + 3];
+        }
+      }
+      const uint32_t row = stg + (uint32_t)(((2 * ph_l + (blk >> 1)) * 8 + pw_l) * 128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        st_shared_v4(row + ((uint32_t)(((blk & 1) * 4 + k) ^ pw_l) << 4), pack_bf16x2(f[8 * k], f[8 * k + 1]), pack_bf16x2(f[8 * k + 2], f[8 * k + 3]),
+                     pack_bf16x2(f[8 * k + 4], f[8 * k + 5]), pack_bf16x2(f[8 * k + 6], f[8 * k + 7]));
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));   // the accumulator is free as soon as it is in registers
+    fence_proxy_async();                                         // generic-proxy writes -> visible to the bulk store
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    if (leader) {
+      tma_store_4d(&P.omap, stg, 0, tw * 8, th * 32, n);        // (pixel pairs x 32 channels, pair column, output row, image)
+      tma_store_commit();
+    }
+  }
+  if (leader) tma_store_wait<0>();
 }
 
 // Epilogue through shared memory: TMEM -> registers -> bias/activation -> bf16 rows in the TMA swizzle (conflict-free
@@ -922,7 +1009,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     // step (348 vs 369 TFLOP/s) and the step 7.64 vs 7.42 ms.)
     for (int s = 0; s < P.n_src; ++s) tma_prefetch_desc(&P.src[s]);
     tma_prefetch_desc(&P.wmap);
-    if (P.tstore) tma_prefetch_desc(&P.omap);
+    if (P.tstore || P.d2s_ts) tma_prefetch_desc(&P.omap);
     if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0) P.dbg[193] = clock64();
     if (P.resident) {
       const uint32_t bw = smem_u32(&bar_w);
@@ -1175,7 +1262,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
 #undef DG_EPI_BWD
     } else {
 #define DG_EPI(ACT)                                                                                     \
-  if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
+  if (P.d2s_ts) epilogue_role_d2s_ts(P, tmem, base + P.stg_off, q, lane, total_tiles, bs, bar_acc_full, bar_acc_empty, grp, P.d2s_prelu ? bnp_s : nullptr); \
+  else if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
                                       reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp, bnp_s, \
                                       bar_res_full, bar_res_empty, stage_base); \
   else if (P.out_f32) epilogue_role<ACT, true>(P, tmem, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, grp); \
@@ -1236,7 +1324,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 static long long* g_dbg_timeline = nullptr;
-static int g_dbg_flags = 0;
+static int g_dbg_flags = getenv("DG_CONV_DBG_FLAGS") ? atoi(getenv("DG_CONV_DBG_FLAGS")) : 0;   // see UmmaConvParams::dbg_flags
 
 struct PackEntry {   // mirrored by denoise_gan_b200/params.py (48 bytes)
   const float* src;
@@ -1488,7 +1576,18 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   static const char* dbg_no_ts = getenv("DG_DEBUG_NO_TSTORE");   // experiments only
   bool ts = !kouter && n_phase == 1 && (!dbg_no_ts || bn_partials || bn_blocks) && out->dtype == DG_BF16 && out_lat.step == 1 && (nb == 16 || nb == 32 || nb == 64) &&
             d2s_cq == 0;
+  // depth_to_space store of a 32 -> 4 x 32 channel layer through the staging buffers (epilogue_role_d2s_ts): one 128-channel N block,
+  // 16 x 8 tiles, dense output pixels (two of them are one 128-byte staged row)
+  static const char* dbg_no_d2s_ts = getenv("DG_DEBUG_NO_D2S_TSTORE");   // experiments only
+  bool d2s_ts = !dbg_no_d2s_ts && d2s_cq == 32 && nb == 128 && cout == 128 && mt == 1 && !kouter && !split && n_phase == 1 && out->dtype == DG_BF16 &&
+                out->cpitch == 32 && out->coff == 0 && ((uintptr_t)out->ptr % 128) == 0 && !bn_partials && !bn_blocks && !bnp && !bwd;
   const uint32_t stg_bytes = (uint32_t)mt * 128u * (uint32_t)nb * 2u;
+  if (d2s_ts) {
+    const long room = (long)budget - (long)w_res_pre - 2L * (long)stg_bytes;
+    int ns = room > 0 ? (int)(room / (long)stage_bytes_pre) : 0;
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    if (ns >= 4 || (ns >= 2 && n_stages < 4)) n_stages = ns; else d2s_ts = false;
+  }
   if (ts) {
     const long room = (long)budget - (long)w_res_pre - 2L * (long)stg_bytes;
     int ns = room > 0 ? (int)(room / (long)stage_bytes_pre) : 0;
@@ -1572,6 +1671,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   }
   DG_REQUIRE(P.stage_bytes == stage_bytes_pre && P.w_res_bytes == w_res_pre, "%s: internal: stage accounting mismatch", name);
   P.tstore = ts ? 1 : 0;
+  P.d2s_ts = d2s_ts ? 1 : 0;
   P.stg_bytes = stg_bytes;
   P.stg_mask = nb == 64 ? 7u : (nb == 32 ? 3u : 1u);
   P.bn_partials = bn_partials;
@@ -1641,6 +1741,13 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   P.dbg_flags = g_dbg_flags;
 
   P.stg_off = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes;
+  if (d2s_ts) {
+    // the stored [n, 2h, 2w, 32] tensor as (pixel pair x 32 channels = 128 bytes, w pairs, 2h rows, n); one box = the tile's 32 x 16 output pixels
+    uint64_t dims[4] = {64u, (uint64_t)out->w, 2ull * (uint64_t)out->h, (uint64_t)out->n};
+    uint64_t strides[3] = {128u, 128ull * (uint64_t)out->w, 128ull * (uint64_t)out->w * 2ull * (uint64_t)out->h};
+    uint32_t box[4] = {64u, 8u, 32u, 1u};
+    if (encode_map(ctx, &P.omap, out->ptr, 4, dims, strides, box, 64)) return 1;
+  }
   if (ts) {
     // output view as a 4-D tensor map (C, W, H, N); one box = the CTA's tile, clipped at the image border by the TMA unit
     uint64_t dims[4] = {(uint64_t)out->c, (uint64_t)out->w, (uint64_t)out->h, (uint64_t)out->n};
@@ -1717,7 +1824,7 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
       if (encode_map(ctx, &P.rmap, (char*)yb->ptr + (size_t)yb->coff * 2, 4, dims, strides, box, nb)) return 1;
     }
   }
-  const uint32_t smem = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes + (ts ? 2u * stg_bytes : 0u) + 1024;
+  const uint32_t smem = P.w_res_bytes + ring_bytes + (uint32_t)n_stages * P.stage_bytes + ((ts || d2s_ts) ? 2u * stg_bytes : 0u) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 3072);

@@ -1409,6 +1409,16 @@ def test_conv_d2s_prelu_store(L, case):
                                              ad.data_ptr() if use_prelu else None, st))
     torch.cuda.synchronize()
     assert relerr(y, ref) < BF16_TOL
+    # the same store into the leading channels of a wider buffer: the pixel pitch is only 16-byte aligned, so the 32-byte stores of
+    # the dense case do not apply; the neighbouring channels stay untouched
+    cq = cout // 4
+    wide = torch.full((N, 2 * H, 2 * W, cq + 24), 7.0, device="cuda", dtype=torch.bfloat16)
+    tw = L.tensor(wide, c=cq, coff=0)
+    L.check(lib.dg_umma_conv2d_fwd_d2s_prelu(ctx, C.byref(tx), pk.data_ptr(), bd.data_ptr(), C.byref(tw), C.byref(cp),
+                                             ad.data_ptr() if use_prelu else None, st))
+    torch.cuda.synchronize()
+    assert torch.equal(wide[..., :cq], y)
+    assert (wide[..., cq:] == 7.0).all()
 
 
 @pytest.mark.parametrize("ws", ["1", "0"])

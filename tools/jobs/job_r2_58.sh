@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2, job 58: depth_to_space + PReLU store of the up-sampling convolutions with the accumulator prefetch and 32-byte stores: tests, A/B by debug flag, ncu
+set -x
+mkdir -p gpurun_out
+timeout 300 python -u -m pytest -x -q --timeout 120 --timeout-method thread tests/test_kernels_gpu.py -k "d2s or narrow or tapsum" > gpurun_out/r2_58_pytest_k.log 2>&1
+rc=$?; tail -25 gpurun_out/r2_58_pytest_k.log
+if [ $rc -eq 0 ]; then
+  timeout 600 python -u -m pytest -x -q --timeout 300 --timeout-method thread tests/test_infer_gpu.py > gpurun_out/r2_58_pytest_infer.log 2>&1; tail -5 gpurun_out/r2_58_pytest_infer.log
+  for f in 0 32 64 96; do
+    DG_CONV_DBG_FLAGS=$f timeout 300 python tools/infer_profile.py --model fsrgan --list 2 > gpurun_out/r2_58_infer_fsrgan_flags$f.log 2>&1; grep -h "frame wall\|d2s_prelu" gpurun_out/r2_58_infer_fsrgan_flags$f.log
+  done
+  timeout 300 python bench.py --workload infer_fsrgan_1080p --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_58_bench_infer_fsrgan.log 2>&1
+  grep -h '"metric"' gpurun_out/r2_58_bench_*.log | cut -c1-200
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:umma_conv_kernel -s 15 -c 5 -o /tmp/r2_58_uc python tools/infer_profile.py --model fsrgan > gpurun_out/r2_58_ncu_uc.log 2>&1
+  ncu -i /tmp/r2_58_uc.ncu-rep --page raw --csv > gpurun_out/r2_58_umma_conv_infer_raw.csv 2>/dev/null
+fi
+ls -la gpurun_out/r2_58_*
