@@ -505,6 +505,9 @@ __device__ __forceinline__ void bnp_phase(const UmmaConvParams& P, uint32_t tmem
 // (128 bytes) in the TMA's 128-byte swizzle: chunk k of row R sits at k ^ (R & 7) and R & 7 is the pixel's column in the tile, so the
 // eight columns of a warp-wide store cover all banks -- and one bulk tensor store per tile writes full lines, clipped at the image
 // border by the TMA unit.  Two staging buffers (one per epilogue group): the store of tile i drains under tile i+1.
+// (Bias and slope products as packed fp32 pairs -- add.rn.f32x2 / mul.rn.f32x2 -- with the slopes in registers were measured neutral,
+// 742 against 725 us: the epilogue is not issue-bound; the kernel sits at ~60 % of the shared-memory port, which the tcgen05 operand
+// reads of an N = 128 instruction alone saturate while they run.  Not kept.)
 __device__ __forceinline__ void epilogue_role_d2s_ts(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int total_tiles,
                                                      const float* __restrict__ bs, uint64_t* bar_acc_full, uint64_t* bar_acc_empty, int grp,
                                                      const float* __restrict__ ps) {
@@ -965,7 +968,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
   __shared__ __align__(8) uint64_t bar_acc_full[MAX_ACC], bar_acc_empty[MAX_ACC], bar_w, bar_wf[2], bar_we[2];
   __shared__ __align__(8) uint64_t bar_res_full[MAX_STAGES], bar_res_empty[MAX_STAGES];   // BatchNorm phase: residual tiles
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_s[256];
+  __shared__ __align__(16) float bias_s[256];
   __shared__ __align__(16) float bnp_s[3 * 64];   // BatchNorm phase: scale | shift | PReLU slope of the N block
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
