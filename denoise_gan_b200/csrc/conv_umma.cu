@@ -83,6 +83,11 @@ struct UmmaConvParams {
   // the [n, 2h, 2w, d2s_cq] output described by out / out_s*; slope d2s_prelu[cc] (nullptr: no PReLU).  bf16 direct epilogue only.
   int d2s_cq;
   const float* d2s_prelu;
+  // staged epilogue at inference (BatchNorm folded into kernel and bias): y = act(acc + bias) + residual, act = PReLU with per-channel
+  // slopes epi_prelu (else `act`); epi_res: bf16 NHWC view of the output's shape (fsrgan.py:172-176, :208-210; srgan.py:166-169)
+  const __nv_bfloat16* epi_res;
+  long res_sn, res_sh, res_sw;
+  const float* epi_prelu;
   int out_cvalid;   // > 0 (fp32 output, one 16-channel N block): only the first out_cvalid channels of a pixel are stored -- the
                     // 3-channel image side (srgan.py:182, fsrgan.py:217) written densely instead of padded to 16 and sliced
   // staged epilogue: the tile is written to shared memory in the TMA swizzle and leaves through ONE bulk tensor store
@@ -299,9 +304,11 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 }
 
 // one 16-column group of one accumulator row: + bias, activation, bf16, two 16-byte chunks of the staged row
-template <int ACT>
+// (EXTRA: PReLU slopes `sl` instead of ACT, then + the 16 bf16 values at `rr` -- the skip connection -- when they are given)
+template <int ACT, bool EXTRA = false>
 __device__ __forceinline__ void epi_stage16(const uint32_t (&v)[16], const float* __restrict__ bs, float alpha, bool valid, uint32_t stg,
-                                            uint32_t off, uint32_t mask) {
+                                            uint32_t off, uint32_t mask, const __nv_bfloat16* __restrict__ rr = nullptr,
+                                            const float* __restrict__ sl = nullptr) {
   float f[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -309,8 +316,24 @@ __device__ __forceinline__ void epi_stage16(const uint32_t (&v)[16], const float
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] += bs[j];
   }
+  if (EXTRA && sl) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = valid ? act_fn<ACT>(f[j], alpha) : 0.f;   // rows outside the image: zeros (clipped by the store, neutral in the sums)
+    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : sl[j] * f[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = act_fn<ACT>(f[j], alpha);
+  }
+  if (EXTRA && rr && valid) {
+    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rr)), r1 = __ldg(reinterpret_cast<const uint4*>(rr) + 1);
+    const uint32_t r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[2 * j] += __uint_as_float(r[j] << 16);
+      f[2 * j + 1] += __uint_as_float(r[j] & 0xffff0000u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = valid ? f[j] : 0.f;   // rows outside the image: zeros (clipped by the store, neutral in the sums)
   st_shared_v4(stg + swz(off, mask), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
   st_shared_v4(stg + swz(off + 16u, mask), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
                pack_bf16x2(f[14], f[15]));
@@ -569,7 +592,7 @@ __device__ __forceinline__ void epilogue_role_d2s_ts(const UmmaConvParams& P, ui
 // With P.bn_partials the same staged tile feeds the BatchNorm batch statistics: a thread owns one channel pair and
 // walks the rows of its warp's quarter (one 4-byte word per lane: conflict-free), so the statistics cost no extra
 // pass over the tensor and no launch (srgan.py:155 BatchNormalization after every conv of the residual trunk).
-template <int ACT>
+template <int ACT, bool EXTRA = false>
 __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32_t tmem, uint32_t stg_base, int q, int lane, int nb0,
                                                  int total_tiles, const float* __restrict__ bs, uint64_t* bar_acc_full,
                                                  uint64_t* bar_acc_empty, float* red_s, int grp, float* bnp_s, uint64_t* bar_res_full,
@@ -606,20 +629,23 @@ __device__ __forceinline__ void epilogue_role_ts(const UmmaConvParams& P, uint32
       const bool valid = ph < P.out_h && pw < P.out_w;
       const uint32_t acc = tmem + lane_base + (uint32_t)((b * P.mt + m) * P.nb);
       const uint32_t row_off = (uint32_t)(m * 128 + m_idx) * RB;
+      const __nv_bfloat16* rr = (EXTRA && P.epi_res) ? P.epi_res + (long)n * P.res_sn + (long)ph * P.res_sh + (long)pw * P.res_sw + nb0 : nullptr;
+      const float* sl = (EXTRA && P.epi_prelu) ? bnp_s : nullptr;
       int c0 = 0;
       for (; c0 + 32 <= P.nb; c0 += 32) {
         uint32_t v0[16], v1[16];
         tmem_ld_32x16(acc + c0, v0);
         tmem_ld_32x16(acc + c0 + 16, v1);
         tmem_ld_wait();
-        epi_stage16<ACT>(v0, bs ? bs + c0 : nullptr, P.alpha, valid, stg, row_off + 2u * c0, mask);
-        epi_stage16<ACT>(v1, bs ? bs + c0 + 16 : nullptr, P.alpha, valid, stg, row_off + 2u * c0 + 32u, mask);
+        epi_stage16<ACT, EXTRA>(v0, bs ? bs + c0 : nullptr, P.alpha, valid, stg, row_off + 2u * c0, mask, rr ? rr + c0 : nullptr, sl ? sl + c0 : nullptr);
+        epi_stage16<ACT, EXTRA>(v1, bs ? bs + c0 + 16 : nullptr, P.alpha, valid, stg, row_off + 2u * c0 + 32u, mask, rr ? rr + c0 + 16 : nullptr,
+                                sl ? sl + c0 + 16 : nullptr);
       }
       if (c0 < P.nb) {
         uint32_t v0[16];
         tmem_ld_32x16(acc + c0, v0);
         tmem_ld_wait();
-        epi_stage16<ACT>(v0, bs ? bs + c0 : nullptr, P.alpha, valid, stg, row_off + 2u * c0, mask);
+        epi_stage16<ACT, EXTRA>(v0, bs ? bs + c0 : nullptr, P.alpha, valid, stg, row_off + 2u * c0, mask, rr ? rr + c0 : nullptr, sl ? sl + c0 : nullptr);
       }
     }
     tc_fence_before();
@@ -1242,6 +1268,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     const int etid = grp * 128 + (warp - (grp ? 7 : 2)) * 32 + lane;   // 0..255 over both epilogue groups
     if (P.bias)
       for (int i = etid; i < P.nb; i += 256) bias_s[i] = __ldg(P.bias + nb0 + i);
+    if (!BWD && P.epi_prelu)
+      for (int i = etid; i < P.nb; i += 256) bnp_s[i] = __ldg(P.epi_prelu + nb0 + i);      // PReLU slopes of the staged epilogue (nb <= 64)
     if (!BWD && P.d2s_prelu)
       for (int i = etid; i < P.d2s_cq; i += 256) bnp_s[i] = __ldg(P.d2s_prelu + i);      // PReLU slopes of the depth_to_space store (d2s_cq <= 192)
     if (BWD && P.bwd_am >= 0)
@@ -1266,6 +1294,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     } else {
 #define DG_EPI(ACT)                                                                                     \
   if (P.d2s_ts) epilogue_role_d2s_ts(P, tmem, base + P.stg_off, q, lane, total_tiles, bs, bar_acc_full, bar_acc_empty, grp, P.d2s_prelu ? bnp_s : nullptr); \
+  else if (P.tstore && (P.epi_res || P.epi_prelu)) epilogue_role_ts<DG_ACT_NONE, true>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
+                                      reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp, bnp_s, \
+                                      bar_res_full, bar_res_empty, stage_base); \
   else if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
                                       reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp, bnp_s, \
                                       bar_res_full, bar_res_empty, stage_base); \
@@ -1400,12 +1431,18 @@ struct BwdEpi {
   const dg_tensor* relu_y = nullptr;   // output of the ReLU convolution in front of this one: store g * (relu_y > 0), no statistics
 };
 
+// residual / PReLU of the staged forward epilogue (UmmaConvParams::epi_res / epi_prelu)
+struct EpiExtra {
+  const dg_tensor* res;
+  const float* prelu;
+};
+
 int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattice* src_lat, int n_src,
                 const TapSpec* taps_in, int n_taps, const void* w_packed, int w_rows_per_block /*cout_total*/,
                 const dg_tensor* out, Lattice out_lat, const float* bias, int act, float alpha, cudaStream_t st, bool dry = false,
                 float* bn_partials = nullptr, int* bn_blocks = nullptr, int n_phase = 1, const Lattice* phase_lat = nullptr,
                 const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, const BwdEpi* bwd = nullptr,
-                bool bwd_query = false, int out_cvalid = 0, int d2s_cq = 0, const float* d2s_prelu = nullptr) {
+                bool bwd_query = false, int out_cvalid = 0, int d2s_cq = 0, const float* d2s_prelu = nullptr, const EpiExtra* ex = nullptr) {
   DG_REQUIRE(in->dtype == DG_BF16, "%s: tensor-core path needs bf16 input", name);
   DG_REQUIRE(d2s_cq == 0 || (d2s_cq % 32 == 0 && d2s_cq <= 192 && out->dtype == DG_BF16 && n_phase == 1 && !bn_partials && !bnp && !bwd && act == DG_ACT_NONE),
              "%s: the depth_to_space store needs a bf16 output with a multiple of 32 (<= 192) channels per sub-pixel block and no other epilogue", name);
@@ -1675,6 +1712,18 @@ int launch_conv(dg_ctx* ctx, const char* name, const dg_tensor* in, const Lattic
   DG_REQUIRE(P.stage_bytes == stage_bytes_pre && P.w_res_bytes == w_res_pre, "%s: internal: stage accounting mismatch", name);
   P.tstore = ts ? 1 : 0;
   P.d2s_ts = d2s_ts ? 1 : 0;
+  if (ex && (ex->res || ex->prelu)) {
+    DG_REQUIRE(ts && !bn_partials && !bn_blocks && !bnp && !bnp_query && !bwd && !bwd_query && !bn_fin && (!ex->prelu || act == DG_ACT_NONE),
+               "%s: the residual / PReLU epilogue needs the staged store (dense bf16 output, 16/32/64-channel N block) and no other epilogue", name);
+    if (ex->res) {
+      const dg_tensor* r = ex->res;
+      DG_REQUIRE(dg_valid(r) && r->dtype == DG_BF16 && dg_same_shape(r, out) && r->cpitch % 8 == 0 && r->coff % 8 == 0 && ((uintptr_t)r->ptr % 16) == 0,
+                 "%s: the residual must be a bf16 tensor of the output's shape with 16-byte aligned pixels", name);
+      P.epi_res = (const __nv_bfloat16*)r->ptr + r->coff;
+      P.res_sw = r->cpitch; P.res_sh = (long)r->cpitch * r->w; P.res_sn = (long)r->cpitch * r->w * r->h;
+    }
+    P.epi_prelu = ex->prelu;
+  }
   P.stg_bytes = stg_bytes;
   P.stg_mask = nb == 64 ? 7u : (nb == 32 ? 3u : 1u);
   P.bn_partials = bn_partials;
@@ -1935,7 +1984,7 @@ extern "C" int dg_umma_pack_weights_batch(dg_ctx* ctx, const void* table_dev, in
 static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
                          const dg_conv_params* p, void* stream, bool dry, float* bn_partials = nullptr, int* bn_blocks = nullptr,
                          const dg_bn_fused* bn_fin = nullptr, const BnPhase* bnp = nullptr, bool bnp_query = false, int out_cvalid = 0,
-                         int d2s_cq = 0, const float* d2s_prelu = nullptr) {
+                         int d2s_cq = 0, const float* d2s_prelu = nullptr, const EpiExtra* ex = nullptr) {
   DG_REQUIRE(dg_valid(x) && y && y->ptr && w_packed && p, "dg_umma_conv2d_fwd: null argument");
   DG_REQUIRE(p->stride == 1 || p->stride == 2, "dg_umma_conv2d_fwd: stride must be 1 or 2");
   DG_REQUIRE(x->n == y->n, "dg_umma_conv2d_fwd: batch mismatch");
@@ -1960,7 +2009,7 @@ static int conv_fwd_impl(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, 
   }
   return launch_conv(ctx, "dg_umma_conv2d_fwd", x, lat, n_src, taps, n_taps, w_packed, y->c, y, Lattice{1, 0, 0}, bias,
                      p->act, p->act_alpha, (cudaStream_t)stream, dry, bn_partials, bn_blocks, 1, nullptr, bn_fin, bnp, bnp_query, nullptr, false,
-                     out_cvalid, d2s_cq, d2s_prelu);
+                     out_cvalid, d2s_cq, d2s_prelu, ex);
 }
 
 // Conv2D + depth_to_space(2) + PReLU (srgan.py:144-146, fsrgan.py:180-186: the up-sampling blocks) as ONE launch for inference: the
@@ -1976,6 +2025,17 @@ extern "C" int dg_umma_conv2d_fwd_d2s_prelu(dg_ctx* ctx, const dg_tensor* x, con
   dg_tensor yc = *y;             // the convolution's own output grid
   yc.h = y->h / 2; yc.w = y->w / 2; yc.c = 4 * y->c;
   return conv_fwd_impl(ctx, x, w_packed, bias, &yc, p, stream, false, nullptr, nullptr, nullptr, nullptr, false, 0, y->c, prelu_alpha);
+}
+
+// Conv2D -> BatchNormalization(training=False) -> [PReLU] -> [Add skip] as ONE launch for inference (fsrgan.py:172-176 project + add,
+// :208-210 post-residual conv + add; srgan.py:166-169, :174-176): the BatchNorm is folded into w_packed / bias by the caller, the staged
+// epilogue applies y = act(acc + bias) + residual with act = PReLU(prelu_alpha[c]) when slopes are given (else p->act).  Fails when the
+// layer does not take the staged epilogue (dg_umma_conv2d_fwd_bn_blocks() == 0): the caller then issues convolution and pointwise pass.
+extern "C" int dg_umma_conv2d_fwd_res_prelu(dg_ctx* ctx, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                                            const dg_conv_params* p, const dg_tensor* residual, const float* prelu_alpha, void* stream) {
+  DG_REQUIRE(dg_valid(x) && dg_valid(y) && p, "dg_umma_conv2d_fwd_res_prelu: bad argument");
+  EpiExtra ex{residual, prelu_alpha};
+  return conv_fwd_impl(ctx, x, w_packed, bias, y, p, stream, false, nullptr, nullptr, nullptr, nullptr, false, 0, 0, nullptr, &ex);
 }
 
 // Conv2D whose output has fewer than 16 channels (the RGB image: srgan.py:182, fsrgan.py:217, autoencoder.py:186), fp32: the packed

@@ -36,6 +36,12 @@ class SRGANGenerator(_Net):
     def __init__(self, engine, pset, scale=4):
         super().__init__(engine, pset)
         self.scale = scale
+        # receptive-field radius at inference in input pixels, from the kernel sizes (FrameRunner.compute_size): every convolution
+        # is stride 1, the BatchNorms are per-pixel, an up-sampling block halves the reach of the layers behind it
+        half = lambda name: (pset[name].shape[0] - 1) / 2.0
+        r = half("g/conv_in/kernel") + sum(half(f"g/res{i}/conv1/kernel") + half(f"g/res{i}/conv2/kernel") for i in range(16))
+        r += half("g/conv_post/kernel") + sum(half(f"g/up{j}/conv/kernel") / 2 ** j for j in range(scale // 2))
+        self.receptive_radius = r + half("g/conv_out/kernel") / 2 ** (scale // 2)
 
     def __call__(self, x, training=True) -> Var:
         E, p = self.E, self.p

@@ -171,3 +171,21 @@ def test_video_frame_tight_padding_and_frame_sink_are_exact():
     old = run.video_frame(f).numpy()
     mx, frac = _levels(full, old)
     assert mx <= 1 and frac < 1e-3, (mx, frac)          # fp32 accumulation order of the last layer only
+
+
+def test_srgan_video_frame_tight_padding_is_exact():
+    """The same property for the SRGAN generator (srgan.py:129-185: 35 stride-1 3x3 convolutions deep, radius 35.5 -> margin 40)."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.infer import FrameRunner
+    from denoise_gan_b200.srgan import SRGAN
+    model = SRGAN(SimpleNamespace(crop_size=384, scale=4, lr=1e-3, fp16=1, vgg=0, seed=0))
+    model.gen_params.load(_randomise_stats(P.init_srgan_generator(0, 4)))
+    run = FrameRunner(model, upscale=4)
+    assert model.generator.receptive_radius == 35.5
+    f = _frame(140, 170, seed=8)                     # padded_size: 256 x 256, margins 58 / 43 >= 40
+    assert run.compute_size(140, 170) == (220, 250)
+    tight = run.video_frame(f).numpy()
+    run.tight_padding = False
+    assert run.compute_size(140, 170) == (256, 256)
+    full = run.video_frame(f).numpy()
+    np.testing.assert_array_equal(tight, full)
