@@ -72,6 +72,7 @@ SIGNATURES = {
     "dg_umma_pack_weights_batch": (_i, [_P, _P, _i, _P]),
     "dg_umma_conv2d_fwd": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
     "dg_umma_conv2d_fwd_narrow": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
+    "dg_umma_conv2d_fwd_res_prelu": (_i, [_P, _T, _P, _P, _T, _CP, _T, _P, _P]),
     "dg_umma_conv2d_fwd_d2s_prelu": (_i, [_P, _T, _P, _P, _T, _CP, _P, _P]),
     "dg_umma_conv2d_dgrad": (_i, [_P, _T, _P, _P, _T, _CP, _P]),
     "dg_umma_conv2d_dgrad_fused": (_i, [_P, _T, _P, _T, _CP, _T, C.POINTER(DgBnBwdStats), _P]),

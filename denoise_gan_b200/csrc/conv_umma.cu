@@ -1294,7 +1294,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) umma_conv_kernel(const __grid
     } else {
 #define DG_EPI(ACT)                                                                                     \
   if (P.d2s_ts) epilogue_role_d2s_ts(P, tmem, base + P.stg_off, q, lane, total_tiles, bs, bar_acc_full, bar_acc_empty, grp, P.d2s_prelu ? bnp_s : nullptr); \
-  else if (P.tstore && (P.epi_res || P.epi_prelu)) epilogue_role_ts<DG_ACT_NONE, true>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
+  else if (P.tstore && (P.epi_res || P.epi_prelu)) epilogue_role_ts<ACT, true>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \
                                       reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + P.stg_off), grp, bnp_s, \
                                       bar_res_full, bar_res_empty, stage_base); \
   else if (P.tstore) epilogue_role_ts<ACT>(P, tmem, base + P.stg_off, q, lane, nb0, total_tiles, bs, bar_acc_full, bar_acc_empty, \

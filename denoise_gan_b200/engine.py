@@ -31,7 +31,7 @@ def same_pads(in_size: int, k: int, s: int):
 
 class Var:
     """An NHWC activation on the tape."""
-    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src", "bn_folded", "segs", "relu_out", "n_cons", "n_mask")
+    __slots__ = ("t", "deps", "seq", "bn_part", "bn_done", "bn_applied", "bn_src", "bn_folded", "bn_folded_post", "segs", "relu_out", "n_cons", "n_mask")
 
     def __init__(self, t: torch.Tensor, deps=frozenset(), seq=-1):
         self.t, self.deps, self.seq = t, deps, seq
@@ -39,6 +39,7 @@ class Var:
         self.bn_done = None     # (name, scale, shift, mean, invstd) when the producing conv ALSO finalised them (last-CTA ticket)
         self.bn_applied = None  # (y_act, act, alpha, prelu, residual) when the producing conv ALSO applied BatchNorm + activation (+ skip)
         self.bn_folded = None   # name of the inference-mode BatchNorm (+ activation) already folded into the producing convolution
+        self.bn_folded_post = False   # ... together with the PReLU / skip-add behind it
         self.relu_out = False   # output of a convolution with a ReLU epilogue (values >= 0)
         self.n_cons = 0         # tape nodes (and gradient seeds) that consume this Var ...
         self.n_mask = 0         # ... of which those whose input gradient already carries the factor (t > 0): when ALL do, the ReLU
@@ -136,6 +137,8 @@ class Engine:
         self.fuse_d2s_infer = os.environ.get("DG_FUSE_D2S", "1") != "0"     # inference: depth_to_space + PReLU as the up-conv's store pattern
         self.inplace_concat = os.environ.get("DG_INPLACE_CONCAT", "1") != "0"   # pix2pix U-Net: layers write into their half of the concat buffer
         self.fuse_fsrgan_block = os.environ.get("DG_FSRGAN_BLOCK", "1") != "0"   # inference: a Fast-SRGAN inverted-residual block as one launch
+        self.fuse_res_epilogue = os.environ.get("DG_FUSE_RES_EPILOGUE", "1") != "0"   # inference: PReLU / skip-add behind a folded BatchNorm in the conv epilogue
+        self.concat_pad32 = os.environ.get("DG_CONCAT_PAD32", "1") != "0"     # U-Net concats of 16 (mod 32) channels get 16 zero channels more (32-channel K chunks)
         self.tapsum_infer = os.environ.get("DG_CONV_TAPSUM", "1") != "0"     # inference: the 32 -> 3 image convolution in tap-sum form (conv_tapsum.cu)
         self.frame_sink = None   # FrameRunner: dict(out=uint8 frame, h, w, scale, offset, clip, flip, done) consumed by conv3x3_image_infer
         # weight gradients of layers with identical geometry (the generator trunk's 32 identical convolutions, the real / fake passes of
@@ -565,17 +568,37 @@ class Engine:
             _, f_pset, f_name, f_eps = bn
             bn = False
             p_act = (post or {}).get("act")
-            if (self.fold_bn_infer and umma_f and act is None and (post or {}).get("prelu") is None and (post or {}).get("residual") is None
+            p_prelu, p_res = (post or {}).get("prelu"), (post or {}).get("residual")
+            # a PReLU / skip-add behind the BatchNorm rides on the staged epilogue (dg_umma_conv2d_fwd_res_prelu) when the layer takes it
+            extra = p_prelu is not None or p_res is not None
+            extra_ok = False
+            if extra and self.fold_bn_infer and self.fuse_res_epilogue and umma_f and act is None and y.dtype == torch.bfloat16 and \
+                    (p_prelu is None or p_act is None) and (p_res is None or (p_res.t.dtype == torch.bfloat16 and p_res.segs is None and
+                                                                               tuple(p_res.shape) == (N, Ho, Wo, cout))):
+                keyb = ("bnblk", N, H, W, cin, Ho, Wo, cout, kh, kw, stride, pt, pl)
+                blocks = self._cap.get(keyb)
+                if blocks is None:
+                    blocks = int(self.lib.dg_umma_conv2d_fwd_bn_blocks(self.ctx, C.byref(tx), C.byref(ty), C.byref(cp)))
+                    self._cap[keyb] = blocks
+                extra_ok = blocks > 0
+            if (self.fold_bn_infer and umma_f and act is None and (not extra or extra_ok)
                     and p_act in (None, "relu", "lrelu") and y.dtype == torch.bfloat16):
                 ent = self._fold(w, b, f_pset, f_name, f_eps, axis=3)
                 if ent[3] is None:
                     ent[3] = torch.empty(kh * kw * cin * cout, dtype=torch.bfloat16, device=self.device)
                     check(self.lib.dg_umma_pack_weights_padded(self.ctx, ent[1].data_ptr(), ent[3].data_ptr(), kh, kw, cin, cout, cin, cout, 0, self.st))
                 cpf = DgConvParams(kh, kw, stride, pt, pl, ACT[p_act], float((post or {}).get("alpha", 0.0)))
-                self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
-                    self.ctx, C.byref(tx), ent[3].data_ptr(), ent[2].data_ptr(), C.byref(ty), C.byref(cpf), None, self.st)))
-                out = Var(y, self._deps([x], w.group), seq)
+                if extra:
+                    tr = tensor(p_res.t) if p_res is not None else None
+                    self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd_res_prelu(
+                        self.ctx, C.byref(tx), ent[3].data_ptr(), ent[2].data_ptr(), C.byref(ty), C.byref(cpf),
+                        C.byref(tr) if tr is not None else None, _lib.ptr(p_prelu.data) if p_prelu is not None else None, self.st)))
+                else:
+                    self._timed("umma_conv", flops, lambda: check(self.lib.dg_umma_conv2d_fwd(
+                        self.ctx, C.byref(tx), ent[3].data_ptr(), ent[2].data_ptr(), C.byref(ty), C.byref(cpf), None, self.st)))
+                out = Var(y, self._deps([x] + ([p_res] if p_res is not None else []), w.group), seq)
                 out.bn_folded = f_name
+                out.bn_folded_post = extra
                 return out          # inference only: no tape node
         if umma_f:
             pk = self._packed(w, 0)
@@ -1069,8 +1092,9 @@ class Engine:
                step_counter: torch.Tensor | None = None, out: torch.Tensor | None = None) -> Var:
         if not training and getattr(x, "bn_folded", None) == name:
             assert out is None, f"{name}: the folded inference form has no out= (the producing convolution owns the buffer)"
-            # inference: the producing convolution already applied this BatchNorm and its activation (folded kernel / bias / epilogue)
-            assert prelu is None and residual is None and dropout_seed is None
+            # inference: the producing convolution already applied this BatchNorm and its activation (folded kernel / bias / epilogue),
+            # and -- bn_folded_post -- the PReLU / skip-add that follow it (dg_umma_conv2d_fwd_res_prelu)
+            assert dropout_seed is None and (x.bn_folded_post or (prelu is None and residual is None))
             return x
         gamma, beta = pset[name + "/gamma"], pset[name + "/beta"]
         mm, mv = pset[name + "/moving_mean"], pset[name + "/moving_variance"]
@@ -1387,13 +1411,21 @@ class Engine:
         cb = b.shape[3]
         assert tuple(b.shape[:3]) == (N, 2 * H, 2 * W) and a.t.dtype == b.t.dtype
         seq = self._next()
-        y = self.buf((seq, "y"), (N, 2 * H, 2 * W, ca + cb), a.t.dtype)
+        # a concat of 16 (mod 32) physical channels would make its consumer walk 16-channel K chunks (32-byte rows: half the bytes per
+        # TMA row and per MMA operand fetch -- the 80-channel last concat of the autoencoder ran 441 us at 1080p against ~250 for 96): the
+        # buffer gets 16 more zero channels, counted as padding of the last segment; only the two slices are ever written
+        tail = 16 if (self.concat_pad32 and self.phys_pad and a.t.dtype == torch.bfloat16 and (ca + cb) % 32 == 16 and ca + cb > 32) else 0
+        y = (self._zeros((seq, "ycat"), (N, 2 * H, 2 * W, ca + cb + tail), a.t.dtype) if tail else
+             self.buf((seq, "y"), (N, 2 * H, 2 * W, ca + cb), a.t.dtype))
         ta, tya = tensor(a.t), tensor(y, c=ca, coff=0)
         check(self.lib.dg_upsample2x_relu_fwd(self.ctx, C.byref(ta), C.byref(tya), self.st))
         tb, tyb = tensor(b.t), tensor(y, c=cb, coff=ca)
         check(self.lib.dg_copy(self.ctx, C.byref(tb), C.byref(tyb), 0, self.st))
         out = Var(y, self._deps([a, b]), seq)
-        out.segs = self._norm_segs(list(a.segs or ((ca, ca),)) + list(b.segs or ((cb, cb),)))
+        segs_b = list(b.segs or ((cb, cb),))
+        if tail:
+            segs_b[-1] = (segs_b[-1][0], segs_b[-1][1] + tail)
+        out.segs = self._norm_segs(list(a.segs or ((ca, ca),)) + segs_b)
 
         def bwd(gy, need_in, need_p, tag):
             da = db = None

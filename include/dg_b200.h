@@ -300,6 +300,13 @@ int dg_unpad_weight_grad(dg_ctx*, const float* dw_padded, const float* dbias_pad
  * dg_umma_conv2d_fwd + dg_d2s_prelu_fwd: the backward pass needs it). */
 int dg_umma_conv2d_fwd_d2s_prelu(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
                                  const dg_conv_params* p, const float* prelu_alpha, void* stream);
+/* Conv2D -> BatchNormalization(training=False) -> [PReLU(shared_axes=[1,2])] -> [Add skip] as ONE launch for INFERENCE
+ * (fsrgan.py:172-176 project + add, :208-210 post-residual conv + add; srgan.py:166-169, :174-176): the BatchNorm is folded into
+ * w_packed / bias by the caller, the staged epilogue computes y = act(conv + bias) + residual, where act is PReLU with per-channel
+ * slopes prelu_alpha (NULL: p->act) and residual is a bf16 tensor of y's shape (NULL: none).  Applies to layers that take the staged
+ * epilogue -- dg_umma_conv2d_fwd_bn_blocks() > 0: dense bf16 output, 16/32/64-channel blocks -- and fails otherwise. */
+int dg_umma_conv2d_fwd_res_prelu(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias, const dg_tensor* y,
+                                 const dg_conv_params* p, const dg_tensor* residual, const float* prelu_alpha, void* stream);
 /* Conv2D with fewer than 16 output channels (the RGB side, srgan.py:182 / fsrgan.py:217 / autoencoder.py:186), fp32 output:
  * w_packed / bias_padded are zero-padded to 16 output channels, y is the DENSE [n,h,w,c<16] result (no padded copy, no slice). */
 int dg_umma_conv2d_fwd_narrow(dg_ctx*, const dg_tensor* x, const void* w_packed, const float* bias_padded, const dg_tensor* y,

@@ -37,7 +37,7 @@ def test_c_abi_declares_the_round2_entry_points():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dg_b200.h")).read()
     for sym in ("dg_umma_conv2d_wgrad_batch", "dg_umma_conv2d_fwd_narrow", "dg_umma_conv2d_fwd_d2s_prelu", "dg_umma_conv2d_dgrad_relu_mask",
                 "dg_umma_pack_weights_seg", "dg_unpad_weight_grad_seg", "dg_maxpool2x2_bwd_relu", "dg_pair_synthesis", "dg_image_summary",
-                "dg_gan_loss_terms", "dg_comm_allreduce", "dg_conv3x3_tapsum_fwd", "dg_conv3x3_tapsum_frame", "dg_conv3x3_tapsum_supported"):
+                "dg_gan_loss_terms", "dg_comm_allreduce", "dg_conv3x3_tapsum_fwd", "dg_conv3x3_tapsum_frame", "dg_conv3x3_tapsum_supported", "dg_umma_conv2d_fwd_res_prelu"):
         assert sym + "(" in hdr, sym
     from denoise_gan_b200 import _lib
     lib = _lib.load()                                                  # binds every declared symbol or raises

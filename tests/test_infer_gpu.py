@@ -189,3 +189,30 @@ def test_srgan_video_frame_tight_padding_is_exact():
     assert run.compute_size(140, 170) == (256, 256)
     full = run.video_frame(f).numpy()
     np.testing.assert_array_equal(tight, full)
+
+
+def test_srgan_bf16_inference_with_fused_skip_epilogue():
+    """SRGAN generator in bf16 at inference: the 17 `conv -> BN -> Add` pairs (srgan.py:166-169, :174-176) run as convolutions with the
+    folded BatchNorm and the skip-add in their epilogue (dg_umma_conv2d_fwd_res_prelu).  Against the fp64 oracle, and against the same
+    model with the skip-adds as separate passes."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.infer import FrameRunner
+    from denoise_gan_b200.srgan import SRGAN
+    g0 = _randomise_stats(P.init_srgan_generator(0, 4))
+    model = SRGAN(SimpleNamespace(crop_size=256, scale=4, lr=1e-3, fp16=1, vgg=0, seed=0, retrain=0))
+    model.gen_params.load(g0)
+    run = FrameRunner(model, upscale=4)
+    f = _frame(64, 64, seed=2)
+    fused = run.unit_image(f).numpy()
+    y = OM.srgan_generator({k: v.double() for k, v in g0.items()}, torch.from_numpy(F.unit_pre(f))[None].double(), training=False)[0].float().numpy()
+    ref = F.unit_post(y)
+    d = np.abs(fused.astype(np.int32) - ref.astype(np.int32))
+    print("bf16 fused vs fp64 oracle: max", int(d.max()), "mean", float(d.mean()))
+    assert d.mean() < 4.0 and d.max() <= 40, (int(d.max()), float(d.mean()))      # 35 bf16 layers deep
+    model.engine.fuse_res_epilogue = False
+    plain = run.unit_image(f).numpy()
+    d2 = np.abs(fused.astype(np.int32) - plain.astype(np.int32))
+    d3 = np.abs(plain.astype(np.int32) - ref.astype(np.int32))
+    print("fused vs separate passes: max", int(d2.max()), "mean", float(d2.mean()), "| separate vs oracle mean", float(d3.mean()))
+    assert d2.mean() < 2.0, (int(d2.max()), float(d2.mean()))
+    assert d.mean() <= d3.mean() + 0.25            # one rounding per layer instead of two: not worse than the separate passes

@@ -1236,6 +1236,45 @@ def test_conv_fwd_narrow_store(L, cout, act):
     assert (guard[N * H * W * cout:] == 7.0).all()  # nothing written past the dense tensor
 
 
+@pytest.mark.parametrize("case", [(3, 32, 32, 2, 21, 19, True, True, 0), (1, 192, 32, 1, 40, 24, False, True, 0), (3, 64, 64, 1, 32, 32, True, False, 0),
+                                  (3, 32, 32, 1, 16, 24, False, True, 1)])
+def test_conv_fwd_res_prelu_epilogue(L, case):
+    """dg_umma_conv2d_fwd_res_prelu: Conv2D (+ folded inference BatchNorm) -> [PReLU] -> [+ skip] in the staged epilogue
+    (fsrgan.py:172-176, :208-210; srgan.py:166-169) against the oracle's separate ops; the skip tensor may be a channel slice."""
+    k, cin, cout, N, H, W, use_prelu, use_res, act = case
+    g = torch.Generator().manual_seed(zlib.crc32(str(case).encode()) & 0xFFFF)
+    x = _bf16_round(torch.randn(N, H, W, cin, generator=g, dtype=torch.float64))
+    w = _bf16_round(torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64) * 0.1)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    alpha = torch.rand(cout, generator=g, dtype=torch.float64) - 0.3
+    res = _bf16_round(torch.randn(N, H, W, cout, generator=g, dtype=torch.float64))
+    ref = OT.conv2d(x, w, b, stride=1, padding="same")
+    if use_prelu:
+        ref = OT.prelu(ref, alpha)
+    elif act == 1:
+        ref = torch.relu(ref)
+    if use_res:
+        ref = ref + res
+    ctx = L.ctx(0); lib = L.load(); st = L.stream_ptr()
+    cp = conv_params(L, k, k, 1, H, W, "same", act)
+    xd, wd, bd, ad = dev(x, torch.bfloat16), dev(w), dev(b), dev(alpha)
+    pk = torch.empty(w.numel(), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.dg_umma_pack_weights(ctx, wd.data_ptr(), pk.data_ptr(), k, k, cin, cout, 0, st))
+    y = torch.full((N, H, W, cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    wide = torch.randn(N, H, W, cout + 16, generator=g).bfloat16().cuda()
+    wide[..., 8:8 + cout] = res.to(torch.bfloat16).cuda()
+    tx, ty, tr = L.tensor(xd), L.tensor(y), L.tensor(wide, c=cout, coff=8)
+    if lib.dg_umma_conv2d_fwd_bn_blocks(ctx, C.byref(tx), C.byref(ty), C.byref(cp)) <= 0:
+        pytest.skip("the staged epilogue does not apply to this layer")
+    L.check(lib.dg_umma_conv2d_fwd_res_prelu(ctx, C.byref(tx), pk.data_ptr(), bd.data_ptr(), C.byref(ty), C.byref(cp),
+                                             C.byref(tr) if use_res else None, ad.data_ptr() if use_prelu else None, st))
+    torch.cuda.synchronize()
+    assert relerr(y, ref) < BF16_TOL
+    # one rounding: the result is the bf16 rounding of the fp32 value act(conv + bias) + skip, not of a rounded intermediate
+    err = (y.double().cpu() - ref).abs()
+    assert (err <= 2.0 ** -8 * ref.abs() + 1e-4).all()
+
+
 TAPSUM_CASES = [  # (cout, act, N, H, W, channel offset of the 32-channel input inside a wider buffer)
     (3, 3, 2, 21, 19, 0),      # smaller than one 30 x 14 tile (the halo box is wider than the image)
     (3, 3, 1, 45, 70, 8),      # 4 x 3 tiles with ragged right / bottom tiles, input = a channel slice (pixel pitch 48)
