@@ -56,3 +56,15 @@ def test_tight_size_keeps_the_reference_geometry():
     assert tight_size(1081, 1920, 9.75) == padded_size(1081, 1920)   # odd padding: the reference's crop is off-centre by half a pixel
     assert tight_size(256, 256, 9.75) == (288, 288)               # a multiple of 256 is padded by a full block (infer_video.py:81-82)
     assert tight_size(250, 250, 9.75) == padded_size(250, 250)    # 3 pixels of padding < margin
+
+
+def test_concat_segments_with_a_padded_tail():
+    """Engine.upsample_concat pads a concat of 16 (mod 32) physical channels with 16 zero channels, counted as padding of the last
+    segment: the autoencoder's last concat (64 + 3 of 16 channels, autoencoder.py:181) becomes one (67 logical, 96 physical) segment,
+    the others keep two segments -- the two forms conv2d's packed kernels understand."""
+    from denoise_gan_b200.engine import Engine
+    norm = Engine._norm_segs
+    assert norm([(64, 64), (3, 16)]) == ((67, 80),)
+    assert norm([(64, 64), (3, 32)]) == ((67, 96),)
+    assert norm([(44, 48), (32, 48)]) == ((44, 48), (32, 48))
+    assert norm([(64, 64), (32, 32)]) is None
