@@ -6,7 +6,8 @@ pre/post), :79-83 (padded size); infer.py:38-68 (still images); unit_test.py:56-
 
 Only uint8 frames cross PCIe: the crop-or-pad, scaling and channel flip run on the device
 (csrc/frames.cu) next to the forward; host staging buffers are pinned and double-buffered in BOTH directions, so the
-upload of frame i+1 and the download of frame i-1 overlap the forward of frame i (`FrameRunner.video`).  Frames shard round-robin across ranks with no collective
+upload of frame i+1 and the download of frame i-1 overlap the forward of frame i (`FrameRunner.video`), whose launches are one CUDA-graph
+replay from the third frame of a staging slot on (`device_frame`).  Frames shard round-robin across ranks with no collective
 (`frames_for_rank`).
 """
 from __future__ import annotations
@@ -65,6 +66,9 @@ class FrameRunner:
         self.copy_stream = torch.cuda.Stream(device=self.E.device)       # uploads
         self.d2h_stream = torch.cuda.Stream(device=self.E.device)        # downloads
         self.tight_padding = os.environ.get("DG_INFER_TIGHT_PAD", "1") != "0"   # video frames: frame + receptive-field margin instead of the full padding
+        self.use_graphs = os.environ.get("DG_INFER_GRAPH", "1") != "0"       # video(): frames as CUDA-graph replays
+        self._graphs: dict = {}
+        self._graph_seen: dict = {}
         self._pin: dict = {}
         self._pin_ev: dict = {}       # pinned staging buffer -> event after the last device copy that read it
 
@@ -139,6 +143,27 @@ class FrameRunner:
         out = self._forward_to_frame(x, fh * self.upscale, fw * self.upscale, 0.5, 0.5, clip=True, flip=False, slot=out_slot)
         return self._d2h(out) if to_host else out
 
+    def device_frame(self, dev: torch.Tensor, slot: int) -> torch.Tensor:
+        """video_frame(dev, to_host=False, out_slot=slot) for a uint8 BGR frame already in the device buffer `dev`, as a CUDA-graph replay
+        from the third frame of that buffer on: a frame is ~20 launches behind a few hundred microseconds of Python each, which
+        is most of what the host does per frame (and eight ranks share one host).  Every address in the frame is fixed -- staging
+        buffer, pooled activations, result slot -- so the captured frame is the eager one; `DG_INFER_GRAPH=0` keeps the eager loop."""
+        key = (tuple(dev.shape), dev.data_ptr(), slot)
+        g = self._graphs.get(key)
+        if g is not None:
+            g[0].replay()
+            return g[1]
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if not self.use_graphs or seen < 2:          # eager frames first: they allocate the pooled buffers and fill the caches
+            return self.video_frame(dev, to_host=False, out_slot=slot)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.video_frame(dev, to_host=False, out_slot=slot)
+        self._graphs[key] = (graph, out)
+        graph.replay()                               # capture records, it does not run
+        return out
+
     def still_image(self, img_bgr, to_host: bool = True):
         """infer.py:50-68: BGR uint8 -> [0,1] RGB (float64 division) -> forward -> ((sr+1)/2)*255 -> BGR uint8."""
         f = _u8(img_bgr)
@@ -194,7 +219,7 @@ class FrameRunner:
             dev, ev = nxt
             main.wait_event(ev)
             slot = k & 1
-            out = self.video_frame(dev, to_host=False, out_slot=slot)     # device result slot: its previous download (frame k-2) was waited for below
+            out = self.device_frame(dev, slot)                        # device result slot: its previous download (frame k-2) was waited for below
             done = torch.cuda.Event(); done.record(main)
             if k + 1 < len(idx):
                 nxt = upload(k + 1)         # other input slot

@@ -216,3 +216,20 @@ def test_srgan_bf16_inference_with_fused_skip_epilogue():
     print("fused vs separate passes: max", int(d2.max()), "mean", float(d2.mean()), "| separate vs oracle mean", float(d3.mean()))
     assert d2.mean() < 2.0, (int(d2.max()), float(d2.mean()))
     assert d.mean() <= d3.mean() + 0.25            # one rounding per layer instead of two: not worse than the separate passes
+
+
+def test_video_graph_replay_matches_eager_frames():
+    """FrameRunner.video() replays a captured CUDA graph per staging slot from the third frame of that slot on: eight frames through
+    one rank (eager, eager, capture, replay per slot) must equal the eager single-frame results, in order."""
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.fsrgan import FastSRGAN
+    from denoise_gan_b200.infer import FrameRunner
+    model = FastSRGAN(SimpleNamespace(crop_size=384, scale=4, lr=1e-3, fp16=1, vgg=0, seed=0))
+    model.gen_params.load(_randomise_stats(P.init_fsrgan_generator(0)))
+    run = FrameRunner(model, upscale=4)
+    frames = [_frame(48, 64, seed=30 + i) for i in range(8)]
+    single = [run.video_frame(fr).numpy() for fr in frames]
+    got = {i: out.numpy() for i, out in run.video(frames, rank=0, world=1)}
+    assert sorted(got) == list(range(8)) and len(run._graphs) == 2
+    for i in range(8):
+        np.testing.assert_array_equal(got[i], single[i])
