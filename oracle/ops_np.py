@@ -48,6 +48,34 @@ def conv2d(x, w, b=None, stride=1, padding="same"):
     return y
 
 
+def conv3x3_tapsum(x, w, b=None, tile_h=14, tile_w=30):
+    """The tap-sum form of Conv2D(3x3, stride 1, SAME) that csrc/conv_tapsum.cu computes for the generator's image convolution
+    (fsrgan.py:216-217), restated tile by tile: per 30 x 14 output tile ONE product of the zero-filled (tile + 2)-pixel halo box
+    against all nine taps, D[q, tap, co] = sum_ci x[q, ci] w[tap, ci, co], then y[p, co] = b[co] + sum_tap D[p + offset(tap), tap, co]
+    with the three taps of a filter row combined first (the kernel's shuffle step), then the three rows.  Test infrastructure: it
+    pins the algebra (and the tiling / border handling) of the kernel against conv2d() on the CPU."""
+    n, h, wd, c = x.shape
+    kh, kw, ci, co = w.shape
+    assert (kh, kw) == (3, 3) and ci == c
+    y = np.zeros((n, h, wd, co), dtype=np.float64)
+    wf = w.astype(np.float64).reshape(9, ci, co)
+    for b_i in range(n):
+        for h0 in range(0, h, tile_h):
+            for w0 in range(0, wd, tile_w):
+                box = np.zeros((tile_h + 2, tile_w + 2, c), dtype=np.float64)          # out-of-image pixels: zero (TMA fill)
+                ys, xs = max(h0 - 1, 0), max(w0 - 1, 0)
+                ye, xe = min(h0 + tile_h + 1, h), min(w0 + tile_w + 1, wd)
+                box[ys - (h0 - 1):ye - (h0 - 1), xs - (w0 - 1):xe - (w0 - 1)] = x[b_i, ys:ye, xs:xe]
+                d = np.einsum("hwc,tco->hwto", box, wf)                                  # [halo_h, halo_w, 9, co]
+                rows = [sum(d[:, kx:kx + tile_w, ky * 3 + kx] for kx in range(3)) for ky in range(3)]    # horizontal taps per filter row
+                out = sum(rows[ky][ky:ky + tile_h] for ky in range(3))                                 # then the three rows
+                if b is not None:
+                    out = out + b
+                th, tw = min(tile_h, h - h0), min(tile_w, wd - w0)
+                y[b_i, h0:h0 + th, w0:w0 + tw] = out[:th, :tw]
+    return y
+
+
 def conv2d_transpose(x, w, b=None, stride=2):
     """keras.layers.Conv2DTranspose(padding='same') (pix2pix.py:130,169): the input-gradient of the
     SAME forward conv; out = in*stride and y[s*i + k - pad_before] += x[i] * W[k]; kernel [kh,kw,Cout,Cin]."""

@@ -84,3 +84,87 @@ def test_golden_fixture_srgan_step():
     np.testing.assert_allclose([float(v) for v in losses], z["losses"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(out["gen_output"].numpy(), z["gen_output"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(g["g/conv_out/kernel"].numpy(), z["g_conv_out_kernel_after"], rtol=1e-9, atol=1e-12)
+
+
+def test_tapsum_form_equals_conv2d():
+    """oracle.ops_np.conv3x3_tapsum (the algebra and tiling of csrc/conv_tapsum.cu) == Conv2D(3x3, SAME), ragged tiles and images
+    smaller than a tile included (fsrgan.py:216-217)."""
+    import numpy as np
+    from oracle import ops_np as ON
+    rng = np.random.default_rng(3)
+    for (n, h, w, co) in [(1, 5, 7, 3), (2, 14, 30, 3), (1, 31, 45, 1), (1, 29, 61, 2)]:
+        x = rng.standard_normal((n, h, w, 32))
+        k = rng.standard_normal((3, 3, 32, co)) * 0.1
+        b = rng.standard_normal(co)
+        ref = ON.conv2d(x, k, b, stride=1, padding="same")
+        got = ON.conv3x3_tapsum(x, k, b)
+        assert np.abs(got - ref).max() < 1e-12, (n, h, w, co)
+
+
+def test_fsrgan_frame_plus_margin_equals_full_padding_in_the_crop():
+    """The property FrameRunner.compute_size rests on, checked on the fp64 oracle: the Fast-SRGAN generator at inference has a
+    receptive-field radius of 9.75 input pixels (fsrgan.py:99-220: stride-1 convolutions, per-pixel BatchNorm), so running the frame
+    with a 16-pixel margin gives, inside the centre crop, exactly what the reference's padding to a multiple of 256 gives
+    (infer_video.py:79-83,141,152) -- and a margin below the radius does not."""
+    import numpy as np
+    import torch
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.infer import tight_size
+    from oracle import frames as F
+    from oracle import models as OM
+    g = {k: v.double() for k, v in P.init_fsrgan_generator(0).items()}
+    gen = torch.Generator().manual_seed(5)
+    for k in g:                                   # non-trivial inference statistics, biases and slopes
+        if k.endswith("moving_mean"):
+            g[k] = torch.randn(g[k].shape, generator=gen).double() * 0.2
+        elif k.endswith("moving_variance"):
+            g[k] = torch.rand(g[k].shape, generator=gen).double() * 1.5 + 0.25
+        elif k.endswith(("bias", "beta", "alpha")):
+            g[k] = torch.randn(g[k].shape, generator=gen).double() * 0.1
+    fh, fw = 20, 36
+    f = np.random.default_rng(1).integers(0, 256, size=(fh, fw, 3), dtype=np.uint8)
+
+    def run(nh, nw):
+        x = torch.from_numpy(F.video_pre(f, nh, nw))[None].double()
+        y = OM.fsrgan_generator(g, x, training=False)[0].numpy()
+        oy, ox = (4 * nh - 4 * fh) // 2, (4 * nw - 4 * fw) // 2
+        return y[oy:oy + 4 * fh, ox:ox + 4 * fw]
+    assert tight_size(fh, fw, 9.75) == (52, 68)
+    ref = run(128, 128)                           # a stand-in for the reference's 256 x 256 (any padding >= the radius is equivalent)
+    tight = run(52, 68)
+    assert np.abs(tight - ref).max() < 1e-9
+    short = run(fh + 16, fw + 16)                 # margin 8 < 9.75: the border of the computed region reaches the crop
+    assert np.abs(short - ref).max() > 1e-6
+
+
+def test_srgan_frame_plus_margin_equals_full_padding_in_the_crop():
+    """Same property for the SRGAN generator (srgan.py:129-185): radius 35.5 input pixels from its kernel sizes, margin 40."""
+    import numpy as np
+    import torch
+    from denoise_gan_b200 import params as P
+    from denoise_gan_b200.infer import tight_size
+    from oracle import frames as F
+    from oracle import models as OM
+    g = {k: v.double() for k, v in P.init_srgan_generator(0, 4).items()}
+    gen = torch.Generator().manual_seed(6)
+    for k in g:
+        if k.endswith("moving_mean"):
+            g[k] = torch.randn(g[k].shape, generator=gen).double() * 0.2
+        elif k.endswith("moving_variance"):
+            g[k] = torch.rand(g[k].shape, generator=gen).double() * 1.5 + 0.25
+    half = lambda name: (g[name].shape[0] - 1) / 2.0
+    radius = (half("g/conv_in/kernel") + sum(half(f"g/res{i}/conv1/kernel") + half(f"g/res{i}/conv2/kernel") for i in range(16)) +
+              half("g/conv_post/kernel") + half("g/up0/conv/kernel") + half("g/up1/conv/kernel") / 2 + half("g/conv_out/kernel") / 4)
+    assert radius == 35.5
+    fh, fw = 12, 20
+    f = np.random.default_rng(2).integers(0, 256, size=(fh, fw, 3), dtype=np.uint8)
+
+    def run(nh, nw):
+        x = torch.from_numpy(F.video_pre(f, nh, nw))[None].double()
+        y = OM.srgan_generator(g, x, training=False)[0].numpy()
+        oy, ox = (4 * nh - 4 * fh) // 2, (4 * nw - 4 * fw) // 2
+        return y[oy:oy + 4 * fh, ox:ox + 4 * fw]
+    assert tight_size(fh, fw, radius) == (92, 100)
+    ref = run(108, 116)                           # 48 pixels of padding on every side: more than the radius, as the reference's 256 is
+    tight = run(92, 100)
+    assert np.abs(tight - ref).max() < 1e-9
