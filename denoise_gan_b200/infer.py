@@ -69,6 +69,7 @@ class FrameRunner:
         self.use_graphs = os.environ.get("DG_INFER_GRAPH", "1") != "0"       # video(): frames as CUDA-graph replays
         self._graphs: dict = {}
         self._graph_seen: dict = {}
+        self._graph_ver = None
         self._pin: dict = {}
         self._pin_ev: dict = {}       # pinned staging buffer -> event after the last device copy that read it
 
@@ -148,6 +149,10 @@ class FrameRunner:
         from the third frame of that buffer on: a frame is ~20 launches behind a few hundred microseconds of Python each, which
         is most of what the host does per frame (and eight ranks share one host).  Every address in the frame is fixed -- staging
         buffer, pooled activations, result slot -- so the captured frame is the eager one; `DG_INFER_GRAPH=0` keeps the eager loop."""
+        ver = getattr(getattr(self.model, "gen_params", None), "version", 0)
+        if ver != self._graph_ver:                   # new weights (load / optimiser step): the folded kernels a captured frame reads are rebuilt eagerly
+            self._graphs.clear(); self._graph_seen.clear()
+            self._graph_ver = ver
         key = (tuple(dev.shape), dev.data_ptr(), slot)
         g = self._graphs.get(key)
         if g is not None:

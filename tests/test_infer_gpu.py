@@ -233,3 +233,10 @@ def test_video_graph_replay_matches_eager_frames():
     assert sorted(got) == list(range(8)) and len(run._graphs) == 2
     for i in range(8):
         np.testing.assert_array_equal(got[i], single[i])
+    # new weights invalidate the captured frames (they read BatchNorm-folded kernels that are rebuilt eagerly)
+    model.gen_params.load(_randomise_stats(P.init_fsrgan_generator(3), seed=9))
+    single2 = [run.video_frame(fr).numpy() for fr in frames]
+    got2 = {i: out.numpy() for i, out in run.video(frames, rank=0, world=1)}
+    assert any((single2[i] != single[i]).any() for i in range(8))
+    for i in range(8):
+        np.testing.assert_array_equal(got2[i], single2[i])
